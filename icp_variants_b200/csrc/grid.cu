@@ -1,0 +1,231 @@
+// grid.cu -- buildIndex: the on-device search structure that replaces FLANN's kd-tree
+// (reference: NearestNeighborSearchFlann::buildIndex, NearestNeighbor.h:122-141 / :209-232).
+//
+// Structure: a uniform grid of 2^T cells whose cell codes are Morton-style bit interleavings of
+// the per-axis cell indices (the axis taken at each bit is chosen so that cells end up near-cubic).
+// Points are counting-sorted by cell code (one radix pass, radix 2^T), and the exclusive prefix sum
+// of the per-cell counts, cell_start[0..2^T], doubles as an implicit binary tree: the node at depth d
+// with code prefix p owns points [cell_start[p << (T-d)], cell_start[(p+1) << (T-d)]).  No node
+// storage, no pointers; empty subtrees are recognised by an empty range.
+//
+// Launches (all on one stream, no host synchronisation): pack -> bbox -> params -> memset ->
+// keys+count -> scan (3) -> scatter.
+#include "icp_internal.cuh"
+
+// ---------------------------------------------------------------------------- pack AoS3 -> float4
+__global__ void pack_cloud_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const uint8_t* __restrict__ rgba,
+                                  int n, float4* __restrict__ pts, float4* __restrict__ nrmo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // Layout in HBM: points {x,y,z,aux}, normals {nx,ny,nz,aux}; the source keeps rgba in pts.w, the
+    // target keeps rgba in nrm.w (its pts.w becomes the original index after sorting).
+    unsigned int c = 0;
+    if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
+    float4 p; p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2]; p.w = __uint_as_float(c);
+    float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
+    if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
+    pts[i] = p; nrmo[i] = m;
+}
+
+cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
+                                  cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    pack_cloud_kernel<<<(n + 255) / 256, 256, 0, s>>>(xyz, nrm, rgba, n, pts, nrmo);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- bounding box
+__device__ __forceinline__ unsigned int enc_f(float f) { unsigned int b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float dec_f(unsigned int e) { return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e); }
+
+// bbox[0..2] = encoded min, bbox[3..5] = encoded max (initialised to 0xFFFFFFFF / 0)
+__global__ void bbox_kernel(const float4* __restrict__ pts, int n, unsigned int* __restrict__ bbox) {
+    unsigned int mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        if (!finite3(p.x, p.y, p.z)) continue;
+        const unsigned int e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], e[a]); mx[a] = max(mx[a], e[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
+        mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { atomicMin(&bbox[a], mn[a]); atomicMax(&bbox[3 + a], mx[a]); }
+    }
+}
+
+__global__ void grid_params_kernel(const unsigned int* __restrict__ bbox, int T, GridParams* __restrict__ g) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    GridParams P;
+    float e[3], maxabs[3];
+    const bool empty = bbox[0] == 0xFFFFFFFFu && bbox[3] == 0u;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = empty ? 0.f : dec_f(bbox[a]), hi = empty ? 0.f : dec_f(bbox[3 + a]);
+        P.o[a] = lo;
+        maxabs[a] = fmaxf(fabsf(lo), fabsf(hi));
+        e[a] = fmaxf(hi - lo, 1e-20f + 1e-6f * maxabs[a]);   // zero-extent axes stay well defined
+        P.bits[a] = 0;
+    }
+    // Level k of the implicit tree halves the axis whose cells are currently the longest.
+    float cur[3] = {e[0], e[1], e[2]};
+    unsigned long long seq = 0ull;
+    for (int k = 0; k < T; ++k) {
+        int a = -1; float best = -1.f;
+        for (int c = 0; c < 3; ++c) if (P.bits[c] < ICP_MAX_BITS_PER_AXIS && cur[c] > best) { best = cur[c]; a = c; }
+        if (a < 0) a = 0;   // unreachable for T <= 3*ICP_MAX_BITS_PER_AXIS
+        seq |= (unsigned long long)a << (2 * k);
+        P.bits[a] += 1; cur[a] *= 0.5f;
+    }
+    for (int a = 0; a < 3; ++a) {
+        P.h[a] = e[a] * (1.0f + 1e-5f) / (float)(1 << P.bits[a]);
+        P.inv_h[a] = 1.0f / P.h[a];
+        P.delta[a] = 1e-3f * P.h[a] + 1e-6f * maxabs[a];
+    }
+    P.T = T; P.axis_seq = seq; P.n_finite = 0; P.pad = 0;
+    *g = P;
+}
+
+__device__ __forceinline__ int cell_index(const GridParams& g, int a, float x) {
+    const float u = pmul(psub(x, g.o[a]), g.inv_h[a]);
+    int i = (int)floorf(u);
+    const int hi = (1 << g.bits[a]) - 1;
+    return min(max(i, 0), hi);
+}
+
+__device__ __forceinline__ unsigned int cell_code(const GridParams& g, float x, float y, float z) {
+    const int c0 = cell_index(g, 0, x), c1 = cell_index(g, 1, y), c2 = cell_index(g, 2, z);
+    int r0 = g.bits[0], r1 = g.bits[1], r2 = g.bits[2];
+    unsigned int code = 0;
+    unsigned long long seq = g.axis_seq;
+    for (int k = 0; k < g.T; ++k) {
+        const int a = (int)(seq & 3ull); seq >>= 2;
+        int bit;
+        if (a == 0) { --r0; bit = (c0 >> r0) & 1; }
+        else if (a == 1) { --r1; bit = (c1 >> r1) & 1; }
+        else { --r2; bit = (c2 >> r2) & 1; }
+        code = (code << 1) | (unsigned int)bit;
+    }
+    return code;
+}
+
+// key per point + rank within its cell (the count array becomes cell_start after the scan)
+__global__ void keys_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
+                            unsigned int* __restrict__ keys, unsigned int* __restrict__ ranks, unsigned int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridParams g = *gp;
+    const float4 p = pts[i];
+    if (!finite3(p.x, p.y, p.z)) { keys[i] = 0xFFFFFFFFu; return; }   // can never win the strict '>' scan of NearestNeighbor.h:87
+    const unsigned int c = cell_code(g, p.x, p.y, p.z);
+    keys[i] = c;
+    ranks[i] = atomicAdd(&counts[c], 1u);
+}
+
+// ---------------------------------------------------------------------------- exclusive scan over 2^T+1 counters
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 16
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total) {
+    __shared__ unsigned int warp_sums[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0u, si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, si, o); if (lane >= o) si += t; }
+        warp_sums[lane] = si - s;
+        if (lane == 31 && total) *total = si;
+    }
+    __syncthreads();
+    const unsigned int r = inc - v + warp_sums[w];
+    __syncthreads();
+    return r;
+}
+
+__global__ void scan_tile_sums_kernel(const unsigned int* __restrict__ data, int n, unsigned int* __restrict__ tile_sums) {
+    const int base = blockIdx.x * SCAN_TILE;
+    unsigned int s = 0;
+    for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_THREADS) { const int i = base + k; if (i < n) s += data[i]; }
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    __shared__ unsigned int ws[SCAN_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned int t = 0; for (int w = 0; w < SCAN_THREADS / 32; ++w) t += ws[w]; tile_sums[blockIdx.x] = t; }
+}
+
+// single block: exclusive scan of up to 1024*8 tile sums in place
+__global__ void scan_tile_offsets_kernel(unsigned int* __restrict__ tile_sums, int n_tiles) {
+    __shared__ unsigned int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < n_tiles ? tile_sums[i] : 0u;
+        __shared__ unsigned int total;
+        const unsigned int ex = block_exclusive_scan(v, &total);
+        const unsigned int carry = carry_s;
+        if (i < n_tiles) tile_sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void scan_apply_kernel(unsigned int* __restrict__ data, int n, const unsigned int* __restrict__ tile_offsets) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned int v[SCAN_ITEMS]; unsigned int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; v[k] = i < n ? data[i] : 0u; s += v[k]; }
+    unsigned int ex = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; if (i < n) data[i] = ex; ex += v[k]; }
+}
+
+// ---------------------------------------------------------------------------- scatter into cell order
+__global__ void scatter_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n,
+                               const unsigned int* __restrict__ keys, const unsigned int* __restrict__ ranks,
+                               const unsigned int* __restrict__ cell_start, float4* __restrict__ pts_sorted,
+                               float4* __restrict__ nrm_sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int k = keys[i];
+    if (k == 0xFFFFFFFFu) return;
+    const unsigned int pos = cell_start[k] + ranks[i];
+    float4 p = pts[i]; p.w = __int_as_float(i);     // keep the original index: tie-break + API output
+    pts_sorted[pos] = p;
+    nrm_sorted[pos] = nrm[i];
+}
+
+cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid,
+                                  unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
+                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, cudaStream_t s, int* n_launches) {
+    cudaError_t e;
+    const int n_cells1 = (1 << T) + 1;
+    if ((e = cudaMemsetAsync(bbox_scratch, 0xFF, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bbox_scratch + 3, 0x00, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(cell_start, 0, sizeof(unsigned int) * (size_t)n_cells1, s)) != cudaSuccess) return e;
+    int launches = 0;
+    if (n > 0) {
+        const int nb = min((n + 255) / 256, 148 * 8);
+        bbox_kernel<<<nb, 256, 0, s>>>(pts_in, n, bbox_scratch); ++launches;
+    }
+    grid_params_kernel<<<1, 32, 0, s>>>(bbox_scratch, T, grid); ++launches;
+    if (n > 0) { keys_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_in, n, grid, keys, ranks, cell_start); ++launches; }
+    const int n_tiles = (n_cells1 + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(cell_start, n_cells1, block_sums); ++launches;
+    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(block_sums, n_tiles); ++launches;
+    scan_apply_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(cell_start, n_cells1, block_sums); ++launches;
+    if (n > 0) { scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_in, nrm_in, n, keys, ranks, cell_start, pts_sorted, nrm_sorted); ++launches; }
+    if (n_launches) *n_launches += launches;
+    return cudaGetLastError();
+}

@@ -1,0 +1,169 @@
+// icp_internal.cuh -- shared device/host declarations of libicp_gpu (sm_100a).
+//
+// Numerics contract (DESIGN.md "Numerics contract"; the oracle follows the same one):
+//   D1 squared distance: fp32, dx=q-p.., ((dx*dx+dy*dy)+dz*dz) [+dr^2, +dg^2, +db^2], no FMA
+//   D2 ties -> lowest original target index;  D3 valid iff d2 <= max (fp32)
+//   D4 transform ((r0*x+r1*y)+r2*z)+t in fp32, no FMA; normals with the cofactor inverse-transpose
+//   D5 normal equations in fp64 from fp32 inputs; solve in fp64; increment rounded to fp32;
+//      pose product in fp32, no FMA
+//   D6 rejection: acos(c) > 60 deg  <=>  -1 <= c <= 0.5f
+// Everything that must be bit-exact goes through the p* helpers below (explicit round-to-nearest
+// intrinsics are never contracted into FMAs by nvcc).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/icp_gpu.h"
+
+#define ICP_MAX_ITERS 256          // upper bound on iterations per estimate_pose call
+#define ICP_NRED 32                // doubles per partial-sum row (27..30 used)
+#define ICP_REDUCE_THREADS 256
+#define ICP_MATCH_THREADS 128
+#define ICP_LEAF_MAX 8             // a grid node with <= this many points is scanned, not split
+#define ICP_MAX_BITS_PER_AXIS 10   // keeps the cell-index rounding error << the bound margin
+
+__device__ __forceinline__ float pmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float padd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float psub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float pdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
+
+// Implicit binary tree over a dense table of 2^T Morton-ordered cells (see grid.cu).
+struct GridParams {
+    float o[3];       // origin = min finite coordinate per axis
+    float h[3];       // cell size per axis at full depth
+    float inv_h[3];
+    float delta[3];   // bound margin: every point of cell k lies in [o+k*h-delta, o+(k+1)*h+delta]
+    int bits[3];      // bits per axis, sum = T
+    int T;            // depth of the implicit tree, 2^T cells
+    unsigned long long axis_seq;  // 2 bits per level, level 0 (root split) in the low bits
+    int n_finite;     // points inserted (finite coordinates)
+    int pad;
+};
+
+struct IterDesc {
+    int n_queries;     // threads that own a query slot this iteration
+    int stride;        // source index = slot * stride when sel_offset < 0
+    int sel_offset;    // offset into the selection index array, or -1
+    int filter_finite; // 1: a slot whose point or normal is non-finite is not a query (PointCloud.h:335)
+    unsigned int rng_key; // device selection stream key (ICP_GPU_RNG_DEVICE)
+    float proba;       // device selection probability, <0 = off
+    int pad0, pad1;
+};
+
+// Device-resident loop state; one per context.
+struct DevState {
+    float pose[16];      // current estimate, column-major
+    float nrm[9];        // (R^-1)^T row-major, rebuilt whenever pose changes
+    int iter;            // iterations launched so far in this call (indexes the descriptors)
+    int iters_done;      // iterations whose increment was applied
+    int status;          // 0 or first ICP_GPU_E_* raised on the device
+    unsigned int ticket; // last-block ticket of the reduction
+    unsigned int ticket2;
+    float mean_s[3];     // unweighted means of the kept matches (symmetric metric), rounded to fp32
+    float mean_d[3];
+    double mean_s64[3], mean_d64[3];
+    unsigned long long n_queries, n_matched, n_evals, n_nodes;
+    // Levenberg-Marquardt state (lm.cu)
+    double lm_x[6], lm_cand[6], lm_cost, lm_H[36], lm_g[6], lm_scale[6], lm_diag[6];
+    double lm_radius, lm_decrease, lm_model_change;
+    int lm_iter, lm_done, lm_reuse_diag, lm_invalid, lm_step_ok, lm_have_cand;
+    double shard_partials[ICP_NRED];
+};
+
+struct MatchArgs {
+    const float4* src_pts;   // {x,y,z,rgba bits}
+    const float4* src_nrm;   // {nx,ny,nz,0}
+    int n_src;
+    const int* sel;          // selection indices (all iterations concatenated) or null
+    const IterDesc* desc;    // [ICP_MAX_ITERS]
+    const DevState* state_ro;
+    DevState* state;
+    // target, grid order
+    const GridParams* grid;
+    const unsigned int* cell_start;
+    const float4* tgt_pts;   // sorted {x,y,z,orig idx bits}; brute / projective: original order
+    const float4* tgt_nrm;   // same order {nx,ny,nz,rgba bits}
+    int n_tgt;
+    // projective
+    float fx, fy, cx, cy; unsigned int width, height;
+    // config
+    int weighting, rejection, color_icp;
+    float max_d2;
+    // outputs (slot-indexed)
+    int* match_pos;          // position in tgt_pts order, -1 = none
+    float* match_w;
+    int* match_idx;          // original target index (API output), may be null
+    int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
+};
+
+struct ReduceArgs {
+    const float4* src_pts; const float4* src_nrm; int n_src;
+    const int* sel; const IterDesc* desc; DevState* state;
+    const float4* tgt_pts; const float4* tgt_nrm;
+    const int* match_pos; const float* match_w;
+    double* partials;        // [grid][ICP_NRED]
+    float* pose_history;     // [ICP_MAX_ITERS][16] or null
+    int metric; int desc_index; int solve;   // solve=0: leave the summed row in state->shard_partials
+};
+
+// ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
+struct TargetBuffers;
+cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
+                                  cudaStream_t s);
+cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid,
+                                  unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
+                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, cudaStream_t s, int* n_launches);
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm /*0 grid,1 brute,2 projective*/, int max_queries, cudaStream_t s);
+cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
+cudaError_t icp_launch_reduce(const ReduceArgs& a, int max_queries, int n_blocks, cudaStream_t s, int* n_launches);
+int icp_reduce_blocks(int max_queries, int n_sms);
+cudaError_t icp_launch_shard_apply(DevState* st, int mode, float* history, cudaStream_t s);
+cudaError_t icp_launch_lm(const ReduceArgs& a, int max_queries, int n_blocks, int lm_max_iterations, cudaStream_t s, int* n_launches);
+
+// pinned 4x4 product, column-major: C = A * B  (ICPOptimizer.h:614-620)
+__device__ __forceinline__ void mat4_mul_pinned(const float* A, const float* B, float* C) {
+    float T[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            T[i + 4 * j] = padd(padd(padd(pmul(A[i], B[4 * j]), pmul(A[i + 4], B[1 + 4 * j])), pmul(A[i + 8], B[2 + 4 * j])),
+                                pmul(A[i + 12], B[3 + 4 * j]));
+#pragma unroll
+    for (int k = 0; k < 16; ++k) C[k] = T[k];
+}
+
+// (R^-1)^T by cofactors (utils.h:129, Eigen's 3x3 inverse), row-major out.
+__device__ __forceinline__ void inv_transpose3_pinned(const float* P, float* N) {
+    const float r00 = P[0], r10 = P[1], r20 = P[2], r01 = P[4], r11 = P[5], r21 = P[6], r02 = P[8], r12 = P[9], r22 = P[10];
+    const float c00 = psub(pmul(r11, r22), pmul(r12, r21)), c01 = psub(pmul(r12, r20), pmul(r10, r22)), c02 = psub(pmul(r10, r21), pmul(r11, r20));
+    const float c10 = psub(pmul(r02, r21), pmul(r01, r22)), c11 = psub(pmul(r00, r22), pmul(r02, r20)), c12 = psub(pmul(r01, r20), pmul(r00, r21));
+    const float c20 = psub(pmul(r01, r12), pmul(r02, r11)), c21 = psub(pmul(r02, r10), pmul(r00, r12)), c22 = psub(pmul(r00, r11), pmul(r01, r10));
+    const float det = padd(padd(pmul(r00, c00), pmul(r01, c01)), pmul(r02, c02));
+    const float id = pdiv(1.0f, det);
+    N[0] = pmul(c00, id); N[1] = pmul(c01, id); N[2] = pmul(c02, id);
+    N[3] = pmul(c10, id); N[4] = pmul(c11, id); N[5] = pmul(c12, id);
+    N[6] = pmul(c20, id); N[7] = pmul(c21, id); N[8] = pmul(c22, id);
+}
+
+// transformPoints (utils.h:106-118), contract D4
+__device__ __forceinline__ void xform_point(const float* P, float x, float y, float z, float& ox, float& oy, float& oz) {
+    ox = padd(padd(padd(pmul(P[0], x), pmul(P[4], y)), pmul(P[8], z)), P[12]);
+    oy = padd(padd(padd(pmul(P[1], x), pmul(P[5], y)), pmul(P[9], z)), P[13]);
+    oz = padd(padd(padd(pmul(P[2], x), pmul(P[6], y)), pmul(P[10], z)), P[14]);
+}
+// transformNormals (utils.h:122-133)
+__device__ __forceinline__ void xform_normal(const float* N, float x, float y, float z, float& ox, float& oy, float& oz) {
+    ox = padd(padd(pmul(N[0], x), pmul(N[1], y)), pmul(N[2], z));
+    oy = padd(padd(pmul(N[3], x), pmul(N[4], y)), pmul(N[5], z));
+    oz = padd(padd(pmul(N[6], x), pmul(N[7], y)), pmul(N[8], z));
+}
+
+// Source index owned by query slot k in iteration descriptor d, or -1 when the slot is not a query.
+__device__ __forceinline__ int slot_source_index(const IterDesc& d, const int* sel, int k, int n_src) {
+    if (k >= d.n_queries) return -1;
+    if (d.sel_offset >= 0) return sel[d.sel_offset + k];
+    const long long i = (long long)k * d.stride;
+    return i < n_src ? (int)i : -1;
+}

@@ -1,0 +1,420 @@
+// solve.cu -- stages 5-6 of one ICP iteration: residual / Jacobian assembly reduced straight to the
+// normal equations (never materialising the reference's 4M x 6 matrix A), the 6x6 solve (or the 3x3
+// Procrustes SVD), and the pose update, in ONE launch per iteration:
+//   every block: per-thread fp64 accumulators -> recursive-halving warp reduce-scatter (62 shuffles
+//   for 32 values) -> fixed-order block sum -> partial row in global memory;
+//   last block (atomic ticket): fixed-order sum of all partial rows -> solve -> pose <- inc * pose.
+// Deterministic: no floating-point atomics anywhere.
+//
+// Reference: gather (ICPOptimizer.h:583-610), estimatePosePointToPoint -> ProcrustesAligner
+// (ICPOptimizer.h:666-674, ProcrustesAligner.h:6-70), estimatePosePointToPlane (:676-782),
+// estimatePoseSymmetricICP (:784-898), pose accumulation (:614-620).
+#include "icp_internal.cuh"
+
+struct PoseSmR { float P[16]; };
+
+// ---------------------------------------------------------------------------- reductions
+template <int H>
+__device__ __forceinline__ void halve_step(double (&v)[32], int lane) {
+    const bool upper = (lane & H) != 0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const double send = upper ? v[k] : v[k + H];
+        const double keep = upper ? v[k + H] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, H);
+    }
+}
+// After the call, lane L holds in v[0] the warp-wide sum of element L.
+__device__ __forceinline__ void warp_reduce_scatter32(double (&v)[32], int lane) {
+    halve_step<16>(v, lane); halve_step<8>(v, lane); halve_step<4>(v, lane); halve_step<2>(v, lane); halve_step<1>(v, lane);
+}
+
+// ---------------------------------------------------------------------------- small dense algebra (fp64, one thread)
+__device__ int solve6_dev(double* A /*row-major 6x6, destroyed*/, double* b, double* x) {
+    for (int k = 0; k < 6; ++k) {
+        int p = k; double mx = fabs(A[k * 6 + k]);
+        for (int i = k + 1; i < 6; ++i) if (fabs(A[i * 6 + k]) > mx) { mx = fabs(A[i * 6 + k]); p = i; }
+        if (!(mx > 0.0)) return -1;
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[p * 6 + j]; A[p * 6 + j] = t; }
+            const double t = b[k]; b[k] = b[p]; b[p] = t;
+        }
+        for (int i = k + 1; i < 6; ++i) {
+            const double f = A[i * 6 + k] / A[k * 6 + k];
+            for (int j = k; j < 6; ++j) A[i * 6 + j] -= f * A[k * 6 + j];
+            b[i] -= f * b[k];
+        }
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = b[i];
+        for (int j = i + 1; j < 6; ++j) s -= A[i * 6 + j] * x[j];
+        x[i] = s / A[i * 6 + i];
+    }
+    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return -1;
+    return 0;
+}
+
+// One-sided Jacobi SVD of a 3x3 (row-major), singular values descending, A = U diag(S) V^T.
+__device__ void svd3_dev(const double* A, double* U, double* S, double* V) {
+    double W[9];
+    for (int i = 0; i < 9; ++i) { W[i] = A[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            double a = 0, b = 0, c = 0;
+            for (int k = 0; k < 3; ++k) { a += W[k * 3 + p] * W[k * 3 + p]; b += W[k * 3 + q] * W[k * 3 + q]; c += W[k * 3 + p] * W[k * 3 + q]; }
+            if (fabs(c) <= 1e-300 || fabs(c) <= 1e-17 * sqrt(a * b)) continue;
+            off += fabs(c);
+            const double zeta = (b - a) / (2.0 * c);
+            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+            for (int k = 0; k < 3; ++k) {
+                const double wp = W[k * 3 + p], wq = W[k * 3 + q];
+                W[k * 3 + p] = cs * wp - sn * wq; W[k * 3 + q] = sn * wp + cs * wq;
+                const double vp = V[k * 3 + p], vq = V[k * 3 + q];
+                V[k * 3 + p] = cs * vp - sn * vq; V[k * 3 + q] = sn * vp + cs * vq;
+            }
+        }
+        if (off == 0.0) break;
+    }
+    for (int j = 0; j < 3; ++j) S[j] = sqrt(W[j] * W[j] + W[3 + j] * W[3 + j] + W[6 + j] * W[6 + j]);
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 2; ++i) for (int j = i + 1; j < 3; ++j) if (S[ord[j]] > S[ord[i]]) { const int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+    double Ws[9], Vs[9], Ss[3];
+    for (int j = 0; j < 3; ++j) { Ss[j] = S[ord[j]]; for (int k = 0; k < 3; ++k) { Ws[k * 3 + j] = W[k * 3 + ord[j]]; Vs[k * 3 + j] = V[k * 3 + ord[j]]; } }
+    for (int j = 0; j < 3; ++j) S[j] = Ss[j];
+    for (int i = 0; i < 9; ++i) V[i] = Vs[i];
+    const double tiny = 1e-14 * (S[0] > 0 ? S[0] : 1.0);
+    for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k) U[k * 3 + j] = S[j] > tiny ? Ws[k * 3 + j] / S[j] : 0.0;
+    if (!(S[0] > tiny)) { for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0 : 0.0; return; }
+    if (!(S[1] > tiny)) {   // complete a rank-1 U
+        const double u0[3] = {U[0], U[3], U[6]};
+        const int m = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[m] = 1.0;
+        const double u1[3] = {u0[1] * e[2] - u0[2] * e[1], u0[2] * e[0] - u0[0] * e[2], u0[0] * e[1] - u0[1] * e[0]};
+        const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        for (int k = 0; k < 3; ++k) U[k * 3 + 1] = u1[k] / n1;
+    }
+    if (!(S[2] > tiny)) {
+        const double u0[3] = {U[0], U[3], U[6]}, u1[3] = {U[1], U[4], U[7]};
+        U[2] = u0[1] * u1[2] - u0[2] * u1[1]; U[5] = u0[2] * u1[0] - u0[0] * u1[2]; U[8] = u0[0] * u1[1] - u0[1] * u1[0];
+    }
+}
+
+__device__ __forceinline__ void mat4_identity_dev(float* M) {
+    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+
+// ---------------------------------------------------------------------------- finishers: summed row -> increment
+// Row layouts.  PLANE / SYMMETRIC: [0..20] A^T A upper triangle row-major, [21..26] A^T b, [27] count.
+//               P2P: [0] count, [1..3] sum s, [4..6] sum d, [7] sum w, [8..10] sum w s, [11..13] sum w d, [14..22] sum w d s^T.
+//               SUMS: [0] count, [1..3] sum s, [4..6] sum d.
+__device__ int expand_and_solve(const double* row, double lambda2, double* x) {
+    double A[36], b[6];
+    int k = 0;
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { A[i * 6 + j] = row[k]; A[j * 6 + i] = row[k]; ++k; }
+    for (int i = 0; i < 6; ++i) { A[i * 6 + i] += lambda2; b[i] = row[21 + i]; }
+    return solve6_dev(A, b, x);
+}
+
+__device__ int finish_p2plane(const double* row, float* inc) {
+    mat4_identity_dev(inc);
+    if (!(row[27] > 0.0)) return ICP_GPU_E_NO_MATCHES;
+    double x[6];
+    if (expand_and_solve(row, 0.0, x) != 0) return ICP_GPU_E_NUMERIC;
+    // ICPOptimizer.h:768-779: R = Rx(alpha) * Ry(beta) * Rz(gamma) in fp32, t = x[3..5]
+    const float al = (float)x[0], be = (float)x[1], ga = (float)x[2];
+    const float ca = (float)cos((double)al), sa = (float)sin((double)al), cb = (float)cos((double)be), sb = (float)sin((double)be),
+                cg = (float)cos((double)ga), sg = (float)sin((double)ga);
+    float Rx[16], Ry[16], Rz[16], T[16];
+    mat4_identity_dev(Rx); mat4_identity_dev(Ry); mat4_identity_dev(Rz);
+    Rx[5] = ca; Rx[9] = -sa; Rx[6] = sa; Rx[10] = ca;
+    Ry[0] = cb; Ry[8] = sb; Ry[2] = -sb; Ry[10] = cb;
+    Rz[0] = cg; Rz[4] = -sg; Rz[1] = sg; Rz[5] = cg;
+    mat4_mul_pinned(Rx, Ry, T); mat4_mul_pinned(T, Rz, inc);
+    inc[12] = (float)x[3]; inc[13] = (float)x[4]; inc[14] = (float)x[5];
+    return 0;
+}
+
+__device__ int finish_symmetric(const double* row, const float* meanS, const float* meanT, float* inc) {
+    mat4_identity_dev(inc);
+    if (!(row[27] > 0.0)) return ICP_GPU_E_NO_MATCHES;
+    const float lambda = 0.0001f;                                   // ICPOptimizer.h:858-864
+    double x[6];
+    if (expand_and_solve(row, (double)pmul(lambda, lambda), x) != 0) return ICP_GPU_E_NUMERIC;
+    // ICPOptimizer.h:876-895
+    const float at0 = (float)x[0], at1 = (float)x[1], at2 = (float)x[2];
+    const float tt[3] = {(float)x[3], (float)x[4], (float)x[5]};
+    const float tan_theta = __fsqrt_rn(padd(padd(pmul(at0, at0), pmul(at1, at1)), pmul(at2, at2)));
+    float R4[16]; mat4_identity_dev(R4);
+    float cos_theta = 1.0f;
+    if (tan_theta > 0.f) {       // the reference divides 0/0 here; guarded (documented deviation)
+        const float a[3] = {pdiv(at0, tan_theta), pdiv(at1, tan_theta), pdiv(at2, tan_theta)};
+        const float sin_theta = (float)((double)tan_theta / sqrt(1.0 + (double)pmul(tan_theta, tan_theta)));
+        cos_theta = pdiv(sin_theta, tan_theta);
+        const float K[9] = {0.f, -a[2], a[1], a[2], 0.f, -a[0], -a[1], a[0], 0.f};   // row-major [a]x
+        const float omc = psub(1.0f, cos_theta);
+        float K1[9], KK[9];
+        for (int i = 0; i < 9; ++i) K1[i] = pmul(omc, K[i]);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+            KK[r * 3 + c] = padd(padd(pmul(K1[r * 3], K[c]), pmul(K1[r * 3 + 1], K[3 + c])), pmul(K1[r * 3 + 2], K[6 + c]));
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+            R4[r + 4 * c] = padd((r == c) ? 1.0f : 0.0f, padd(pmul(sin_theta, K[r * 3 + c]), KK[r * 3 + c]));   // getRodriguesMatrix, utils.h:171-176
+    }
+    float Td[16], Tt[16], Ts[16], M1[16], M2[16], M3[16];
+    mat4_identity_dev(Td); mat4_identity_dev(Tt); mat4_identity_dev(Ts);
+    for (int k = 0; k < 3; ++k) { Td[12 + k] = meanT[k]; Tt[12 + k] = pmul(tt[k], cos_theta); Ts[12 + k] = -meanS[k]; }
+    mat4_mul_pinned(Td, R4, M1); mat4_mul_pinned(M1, Tt, M2); mat4_mul_pinned(M2, R4, M3); mat4_mul_pinned(M3, Ts, inc);
+    return 0;
+}
+
+__device__ int finish_p2p(const double* row, float* inc) {
+    mat4_identity_dev(inc);
+    const double M = row[0];
+    if (!(M > 0.0)) return ICP_GPU_E_NO_MATCHES;
+    double sm[3], dm[3];
+    for (int k = 0; k < 3; ++k) { sm[k] = row[1 + k] / M; dm[k] = row[4 + k] / M; }
+    // ProcrustesAligner.h:50-54 with unweighted means: sum w (d - dm)(s - sm)^T expanded in raw moments
+    double A[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+        A[r * 3 + c] = row[14 + r * 3 + c] - dm[r] * row[8 + c] - row[11 + r] * sm[c] + row[7] * dm[r] * sm[c];
+    double U[9], S[3], V[9];
+    svd3_dev(A, U, S, V);
+    double UVt[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) UVt[r * 3 + c] = U[r * 3] * V[c * 3] + U[r * 3 + 1] * V[c * 3 + 1] + U[r * 3 + 2] * V[c * 3 + 2];
+    const double dd = UVt[0] * (UVt[4] * UVt[8] - UVt[5] * UVt[7]) - UVt[1] * (UVt[3] * UVt[8] - UVt[5] * UVt[6]) + UVt[2] * (UVt[3] * UVt[7] - UVt[4] * UVt[6]);
+    double R[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = U[r * 3] * V[c * 3] + U[r * 3 + 1] * V[c * 3 + 1] + dd * U[r * 3 + 2] * V[c * 3 + 2];
+    for (int r = 0; r < 3; ++r) {
+        double rt = 0, rd = 0;
+        for (int c = 0; c < 3; ++c) { rt += R[r * 3 + c] * (dm[c] - sm[c]); rd += R[r * 3 + c] * dm[c]; }
+        inc[r + 12] = (float)(rt - rd + dm[r]);                       // ProcrustesAligner.h:26
+        for (int c = 0; c < 3; ++c) inc[r + 4 * c] = (float)R[r * 3 + c];
+    }
+    for (int i = 0; i < 16; ++i) if (!isfinite(inc[i])) return ICP_GPU_E_NUMERIC;
+    return 0;
+}
+
+// estimatedPose = increment * estimatedPose (ICPOptimizer.h:614-620); history as handed to
+// ConvergenceMeasure::recordAlignmentError (:629-631).
+__device__ void apply_increment(DevState* st, const float* inc, int rc, float* history) {
+    if (st->status == 0) {
+        if (rc != 0) st->status = rc;
+        else {
+            float np[16];
+            mat4_mul_pinned(inc, st->pose, np);
+            for (int i = 0; i < 16; ++i) st->pose[i] = np[i];
+            inv_transpose3_pinned(st->pose, st->nrm);
+            if (history) for (int i = 0; i < 16; ++i) history[16 * st->iters_done + i] = np[i];
+            st->iters_done += 1;
+        }
+    }
+    st->iter += 1;
+}
+
+__device__ void finish_row(DevState* st, const double* row, int mode, float* history) {
+    float inc[16]; int rc;
+    if (mode == 0) rc = finish_p2p(row, inc);
+    else if (mode == 1) rc = finish_p2plane(row, inc);
+    else rc = finish_symmetric(row, st->mean_s, st->mean_d, inc);
+    apply_increment(st, inc, rc, history);
+}
+
+__device__ void finish_sums(DevState* st, const double* row) {
+    // unweighted means of the kept matches, rounded to fp32 (ICPOptimizer.h:797-798)
+    const double M = row[0];
+    for (int k = 0; k < 3; ++k) {
+        st->mean_s[k] = M > 0.0 ? (float)(row[1 + k] / M) : 0.f;
+        st->mean_d[k] = M > 0.0 ? (float)(row[4 + k] / M) : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------- the reduction kernel
+// MODE 0 p2p moments, 1 point-to-plane, 2 symmetric (needs means in state), 3 sums only
+template <int MODE>
+__global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const ReduceArgs a) {
+    __shared__ float P[16];
+    __shared__ float mS[3], mD[3], Nm[9];
+    __shared__ double red[ICP_REDUCE_THREADS / 32][32];
+    __shared__ double fin[8][32];
+    __shared__ bool is_last;
+    if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
+    if (threadIdx.x >= 64 && threadIdx.x < 73) Nm[threadIdx.x - 64] = a.state->nrm[threadIdx.x - 64];
+    __syncthreads();
+    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state->iter];
+    double v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.0;
+    const double LP = (double)0.1f, LQ = (double)1.0f;   // LAMBDA_POINT / LAMBDA_PLANE|SYMMETRIC (ICPOptimizer.h:737-738, :840-841)
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < d.n_queries; slot += gridDim.x * blockDim.x) {
+        const int pos = a.match_pos[slot];
+        if (pos < 0) continue;
+        const int i = slot_source_index(d, a.sel, slot, a.n_src);
+        const float4 sp = __ldg(&a.src_pts[i]);
+        float sxf, syf, szf;
+        xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
+        const float4 tp = __ldg(&a.tgt_pts[pos]);
+        if (!finite3(sxf, syf, szf) || !finite3(tp.x, tp.y, tp.z)) continue;        // ICPOptimizer.h:590-592
+        const double w = (double)a.match_w[slot];
+        if (MODE == 3) {
+            v[0] += 1.0; v[1] += sxf; v[2] += syf; v[3] += szf; v[4] += tp.x; v[5] += tp.y; v[6] += tp.z;
+        } else if (MODE == 0) {
+            const double s[3] = {sxf, syf, szf}, t[3] = {tp.x, tp.y, tp.z};
+            v[0] += 1.0; v[7] += w;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { v[1 + k] += s[k]; v[4 + k] += t[k]; v[8 + k] += w * s[k]; v[11 + k] += w * t[k]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[14 + r * 3 + c] += w * t[r] * s[c];
+        } else {
+            double s[3] = {sxf, syf, szf}, t[3] = {tp.x, tp.y, tp.z};
+            const float4 tn = __ldg(&a.tgt_nrm[pos]);
+            double n[3] = {tn.x, tn.y, tn.z};
+            bool use_row = finite3(tn.x, tn.y, tn.z);
+            double u[3] = {s[0], s[1], s[2]};
+            if (MODE == 2) {
+                const float4 sn4 = __ldg(&a.src_nrm[i]);
+                // the source normal is transformed by the current pose's inverse-transpose (ICPOptimizer.h:554)
+                float nx, ny, nz;
+                xform_normal(Nm, sn4.x, sn4.y, sn4.z, nx, ny, nz);
+                use_row = use_row && finite3(nx, ny, nz);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { s[k] -= (double)mS[k]; t[k] -= (double)mD[k]; }   // :797-806
+                n[0] += (double)nx; n[1] += (double)ny; n[2] += (double)nz;                      // n_t + n_s
+#pragma unroll
+                for (int k = 0; k < 3; ++k) u[k] = s[k] + t[k];
+            }
+            const double e[3] = {t[0] - s[0], t[1] - s[1], t[2] - s[2]};
+            const double b2 = (LP * w) * (LP * w);
+            // three point rows [-[s]x | I], rhs e  (:716-733 / :817-835):  P^T P = [[|s|^2 I - s s^T, [s]x], [-[s]x, I]]
+            const double ss = s[0] * s[0] + s[1] * s[1] + s[2] * s[2];
+            double c[6] = {0, 0, 0, 0, 0, 0}; double r = 0.0, a2 = 0.0;
+            if (use_row) {
+                // plane row [u x n | n], rhs n.e  (:698-710 ; symmetric :809-815 with u = s~ + d~, n = n_t + n_s)
+                c[0] = u[1] * n[2] - u[2] * n[1]; c[1] = u[2] * n[0] - u[0] * n[2]; c[2] = u[0] * n[1] - u[1] * n[0];
+                c[3] = n[0]; c[4] = n[1]; c[5] = n[2];
+                r = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+                a2 = (LQ * w) * (LQ * w);
+            }
+            // upper triangle, row-major
+            v[0] += a2 * c[0] * c[0] + b2 * (ss - s[0] * s[0]);
+            v[1] += a2 * c[0] * c[1] - b2 * s[0] * s[1];
+            v[2] += a2 * c[0] * c[2] - b2 * s[0] * s[2];
+            v[3] += a2 * c[0] * c[3];
+            v[4] += a2 * c[0] * c[4] - b2 * s[2];
+            v[5] += a2 * c[0] * c[5] + b2 * s[1];
+            v[6] += a2 * c[1] * c[1] + b2 * (ss - s[1] * s[1]);
+            v[7] += a2 * c[1] * c[2] - b2 * s[1] * s[2];
+            v[8] += a2 * c[1] * c[3] + b2 * s[2];
+            v[9] += a2 * c[1] * c[4];
+            v[10] += a2 * c[1] * c[5] - b2 * s[0];
+            v[11] += a2 * c[2] * c[2] + b2 * (ss - s[2] * s[2]);
+            v[12] += a2 * c[2] * c[3] - b2 * s[1];
+            v[13] += a2 * c[2] * c[4] + b2 * s[0];
+            v[14] += a2 * c[2] * c[5];
+            v[15] += a2 * c[3] * c[3] + b2;
+            v[16] += a2 * c[3] * c[4];
+            v[17] += a2 * c[3] * c[5];
+            v[18] += a2 * c[4] * c[4] + b2;
+            v[19] += a2 * c[4] * c[5];
+            v[20] += a2 * c[5] * c[5] + b2;
+            // rhs: a^2 r c + b^2 [s x d ; e]   (s x e == s x d)
+            v[21] += a2 * r * c[0] + b2 * (s[1] * e[2] - s[2] * e[1]);
+            v[22] += a2 * r * c[1] + b2 * (s[2] * e[0] - s[0] * e[2]);
+            v[23] += a2 * r * c[2] + b2 * (s[0] * e[1] - s[1] * e[0]);
+            v[24] += a2 * r * c[3] + b2 * e[0];
+            v[25] += a2 * r * c[4] + b2 * e[1];
+            v[26] += a2 * r * c[5] + b2 * e[2];
+            v[27] += 1.0;
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    warp_reduce_scatter32(v, lane);
+    red[wid][lane] = v[0];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < ICP_REDUCE_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * ICP_NRED + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&a.state->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    {
+        const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+        double s = 0.0;
+        for (int b = g; b < (int)gridDim.x; b += ICP_REDUCE_THREADS / 32) s += __ldcg(&a.partials[(size_t)b * ICP_NRED + c]);
+        fin[g][c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < ICP_REDUCE_THREADS / 32; ++g) s += fin[g][threadIdx.x];
+        fin[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.state->ticket = 0;
+        if (MODE == 3) finish_sums(a.state, fin[0]);
+        else if (!a.solve) { for (int k = 0; k < ICP_NRED; ++k) a.state->shard_partials[k] = fin[0][k]; }
+        else finish_row(a.state, fin[0], MODE, a.pose_history);
+    }
+}
+
+int icp_reduce_blocks(int max_queries, int n_sms) {
+    int nb = (max_queries + ICP_REDUCE_THREADS * 4 - 1) / (ICP_REDUCE_THREADS * 4);   // ~4 points per thread
+    if (nb > 2 * n_sms) nb = 2 * n_sms;
+    if (nb < 1) nb = 1;
+    return nb;
+}
+
+cudaError_t icp_launch_reduce(const ReduceArgs& a, int max_queries, int n_blocks, cudaStream_t s, int* n_launches) {
+    (void)max_queries;
+    int launches = 0;
+    if (a.metric == ICP_GPU_METRIC_P2P) { reduce_kernel<0><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches; }
+    else if (a.metric == ICP_GPU_METRIC_P2PLANE) { reduce_kernel<1><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches; }
+    else {
+        reduce_kernel<3><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches;
+        reduce_kernel<2><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches;
+    }
+    if (n_launches) *n_launches += launches;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- pose upload / shard apply
+__global__ void pose_init_kernel(DevState* st, const float* pose16) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = 0; i < 16; ++i) st->pose[i] = pose16[i];
+    inv_transpose3_pinned(st->pose, st->nrm);
+    st->iter = 0; st->iters_done = 0; st->status = 0; st->ticket = 0; st->ticket2 = 0;
+    st->n_queries = 0; st->n_matched = 0; st->n_evals = 0; st->n_nodes = 0;
+    for (int k = 0; k < 3; ++k) { st->mean_s[k] = 0.f; st->mean_d[k] = 0.f; }
+    st->lm_done = 0; st->lm_iter = 0;
+}
+
+cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s) {
+    pose_init_kernel<<<1, 32, 0, s>>>(st, pose_dev16);
+    return cudaGetLastError();
+}
+
+__global__ void shard_apply_kernel(DevState* st, int mode, float* history) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (mode == 3) finish_sums(st, st->shard_partials);
+    else finish_row(st, st->shard_partials, mode, history);
+}
+
+cudaError_t icp_launch_shard_apply(DevState* st, int mode, float* history, cudaStream_t s) {
+    shard_apply_kernel<<<1, 32, 0, s>>>(st, mode, history);
+    return cudaGetLastError();
+}

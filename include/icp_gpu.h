@@ -1,0 +1,190 @@
+/*
+ * icp_gpu.h -- C ABI of the B200 (sm_100a) registration inner loop.
+ *
+ * This is the drop-in boundary for the path BASELINE.json names: the body of
+ * ICPOptimizer::estimatePose's iteration loop plus NearestNeighborSearch::buildIndex /
+ * queryMatches of the reference (icp-variants/ICPOptimizer.h:185-349, :493-663;
+ * icp-variants/NearestNeighbor.h:12-36).  The reference has no FFI layer -- its seam is the C++
+ * virtual interface -- so the entry points below are what the C++14 drop-in classes in
+ * include/icp_b200/ (same names and signatures as the reference's) bind, and what any other
+ * host (ctypes, cgo, JNI) would bind.  See INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch / Eigen types: pointers and sizes only;
+ *   - points / normals: packed float[3*n]  (std::vector<Eigen::Vector3f>::data());
+ *     colours: uint8_t[4*n]                (std::vector<Vector4uc>::data());
+ *     poses: float[16] column-major        (Eigen::Matrix4f::data());
+ *     camera matrix: float[9] column-major (Eigen::Matrix3f::data());
+ *   - every call returns ICP_GPU_OK (0) or a negative ICP_GPU_E_* code; the message is
+ *     available from icp_gpu_last_error().  Nothing hangs (the reference's ASSERT is
+ *     `while(1);`, Eigen.h:9) and nothing throws across the ABI;
+ *   - the caller owns every host array (borrowed for the duration of the call); the context
+ *     owns device memory, its stream and its CUDA graphs;
+ *   - one context = one device + one stream; calls on one context must be serialised by the
+ *     caller, different contexts may be driven concurrently from different threads/processes;
+ *   - there is NO CPU fallback: every entry point fails with ICP_GPU_E_CUDA when no sm_100-class
+ *     device is usable.
+ */
+#ifndef ICP_GPU_H
+#define ICP_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICP_GPU_ABI_VERSION 1
+
+enum {
+    ICP_GPU_OK = 0,
+    ICP_GPU_E_CUDA = -1,       /* CUDA runtime / driver error, or no usable device                  */
+    ICP_GPU_E_ARG = -2,        /* bad argument (null pointer, negative size, unknown enum value)    */
+    ICP_GPU_E_STATE = -3,      /* call order: no target / source / camera set for what was asked    */
+    ICP_GPU_E_NO_MATCHES = -4, /* an iteration had no surviving correspondence (reference: hangs in
+                                  ASSERT, ICPOptimizer.h:668,680,788); pose is the last good one    */
+    ICP_GPU_E_NUMERIC = -5     /* singular normal equations                                         */
+};
+
+/* ICPOptimizer::setMetric (ICPOptimizer.h:46): 0 point-to-point, 1 point-to-plane, 2 symmetric   */
+enum { ICP_GPU_METRIC_P2P = 0, ICP_GPU_METRIC_P2PLANE = 1, ICP_GPU_METRIC_SYMMETRIC = 2 };
+/* LinearICPOptimizer (ICPOptimizer.h:489) / CeresICPOptimizer (:181)                              */
+enum { ICP_GPU_MIN_LINEAR = 0, ICP_GPU_MIN_LM = 1 };
+/* ICPOptimizer::setMatchingMethod (ICPOptimizer.h:71): 0 k-NN, 1 projective                       */
+enum { ICP_GPU_MATCH_KNN = 0, ICP_GPU_MATCH_PROJECTIVE = 1 };
+/* selection.h:8                                                                                  */
+enum { ICP_GPU_SELECT_ALL = 0, ICP_GPU_SELECT_RANDOM = 1 };
+/* weighting.h:8                                                                                  */
+enum { ICP_GPU_WEIGHT_CONSTANT = 0, ICP_GPU_WEIGHT_DISTANCES = 1, ICP_GPU_WEIGHT_NORMALS = 2, ICP_GPU_WEIGHT_COLORS = 3 };
+/* Nearest-neighbour kernel choice (both exact, same answers): 0 = by target size               */
+enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2 };
+/* Random selection stream: 0 = std::mt19937 + uniform_real_distribution<double> drawn on the host
+ * exactly as selection.h:88-104 does (reference-compatible for a given seed); 1 = counter-based
+ * hash drawn on the device (fast, not reference-compatible).                                      */
+enum { ICP_GPU_RNG_MT19937 = 0, ICP_GPU_RNG_DEVICE = 1 };
+/* Multi-resolution level construction: 0 = index stride with finite filter, the reference's
+ * PointCloud::getCoarseResolution (PointCloud.h:325-343).                                        */
+enum { ICP_GPU_PYRAMID_STRIDE = 0 };
+
+typedef struct icp_gpu_config {
+    int32_t  metric;            /* setMetric                 default 0      (ICPOptimizer.h:29)      */
+    int32_t  minimizer;         /* Linear / Ceres-LM class   default linear                          */
+    int32_t  matching;          /* setMatchingMethod         default k-NN   (ICPOptimizer.h:31)      */
+    int32_t  selection;         /* setSelectionMethod        default all    (ICPOptimizer.h:29)      */
+    double   proba;             /* setSelectionMethod proba  default 1.0                             */
+    uint32_t seed;              /* reference seeds from std::random_device (selection.h:76-79)       */
+    int32_t  selection_rng;     /* ICP_GPU_RNG_*                                                    */
+    int32_t  weighting;         /* setWeightingMethod        default constant                        */
+    int32_t  rejection;         /* setRejectionMethod        default 1 = on (ICPOptimizer.h:30)      */
+    float    max_distance_sq;   /* setMatchingMaxDistance, SQUARED metres, default 0.0003 (:31)      */
+    int32_t  color_icp;         /* enableColorICP            default off                             */
+    int32_t  multires;          /* enableMultiResolution     default off                             */
+    int32_t  pyramid_mode;      /* ICP_GPU_PYRAMID_*                                                */
+    int32_t  n_iterations;      /* setNbOfIterations         default 20                              */
+    int32_t  lm_max_iterations; /* Ceres max_num_iterations  default 10     (ICPOptimizer.h:358)     */
+    int32_t  nn_algorithm;      /* ICP_GPU_NN_*                                                     */
+    int32_t  use_graph;         /* 1 (default): replay the iteration loop as one CUDA graph          */
+} icp_gpu_config;
+
+/* Per-stage device times of the last icp_gpu_estimate_pose call made with timings != NULL
+ * (the fields TimeMeasure accumulates, TimeMeasure.h:7-62), in milliseconds, CUDA-event timed
+ * on the context's stream.  Requesting timings runs the loop launch-by-launch (no graph). */
+typedef struct icp_gpu_timings {
+    double selection_ms;   /* TimeMeasure::selectionTime   */
+    double matching_ms;    /* TimeMeasure::matchingTime    (transform + search + weighting + rejection kernel) */
+    double weighting_ms;   /* TimeMeasure::weighingTime    (0: fused into matching)                */
+    double rejection_ms;   /* TimeMeasure::rejectionTime   (0: fused into matching)                */
+    double solver_ms;      /* TimeMeasure::solverTime      (residual/Jacobian reduction + solve + pose update) */
+    double index_ms;       /* buildIndex (grid build), once per registration                       */
+    double total_ms;       /* TimeMeasure::convergenceTime                                         */
+    int32_t n_iterations;  /* iterations executed                                                   */
+    int32_t n_match_launches, n_solver_launches;
+} icp_gpu_timings;
+
+/* Work counters of the last estimate_pose / query_matches (for roofline accounting). */
+typedef struct icp_gpu_stats {
+    uint64_t n_queries;        /* source points submitted to matching, summed over iterations      */
+    uint64_t n_matched;        /* correspondences that survived threshold + rejection              */
+    uint64_t n_distance_evals; /* point-to-point squared distances evaluated by the search         */
+    uint64_t n_nodes_visited;  /* grid nodes (cells at any level) whose bound was tested           */
+    uint64_t n_kernel_launches;/* kernels launched by this library in the call                     */
+} icp_gpu_stats;
+
+typedef struct icp_gpu_ctx icp_gpu_ctx;
+
+int icp_gpu_abi_version(void);
+/* Number of CUDA devices visible (0 when there is none or no driver). */
+int icp_gpu_device_count(void);
+
+int icp_gpu_create(icp_gpu_ctx** out, int device);
+int icp_gpu_destroy(icp_gpu_ctx* ctx);
+const char* icp_gpu_last_error(const icp_gpu_ctx* ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL restores
+ * the context's own stream. */
+int icp_gpu_set_stream(icp_gpu_ctx* ctx, void* cuda_stream);
+int icp_gpu_synchronize(icp_gpu_ctx* ctx);
+
+/* ICPOptimizer constructor defaults (ICPOptimizer.h:29-37). */
+void icp_gpu_default_config(icp_gpu_config* cfg);
+/* The ICPOptimizer setters (ICPOptimizer.h:41-95) in one call. */
+int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* cfg);
+int icp_gpu_get_config(const icp_gpu_ctx* ctx, icp_gpu_config* cfg);
+/* ICPOptimizer::setCameraParamsMatchingMethod / NearestNeighborSearch::setCameraParams
+ * (ICPOptimizer.h:80, NearestNeighbor.h:26-30). */
+int icp_gpu_set_camera(icp_gpu_ctx* ctx, const float K_colmajor[9], uint32_t width, uint32_t height);
+
+/* NearestNeighborSearch::buildIndex(points[, colours]) (NearestNeighbor.h:122-141, :209-232,
+ * :324-331) plus the target normals the later stages read.  nrm / rgba may be NULL when the
+ * configured variant does not read them.  Copies to device and builds the search grid. */
+int icp_gpu_set_target(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n);
+/* The source cloud estimatePose iterates over (ICPOptimizer.h:493). */
+int icp_gpu_set_source(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n);
+/* Same, from device pointers (same packed layouts) already resident on the context's device. */
+int icp_gpu_set_target_dev(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n);
+int icp_gpu_set_source_dev(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n);
+
+/* Stages 2-4 of one iteration at a given pose: transformPoints/transformNormals (utils.h:106-133),
+ * queryMatches (NearestNeighbor.h:143-207, :234-303, :333-421), applyWeights (weighting.h:39-99)
+ * and pruneCorrespondences (ICPOptimizer.h:157-174).  sel_idx (nullable) = ascending source
+ * indices of the selected subset; NULL = all points.  idx_out / weight_out have n_sel (or n_source)
+ * entries: Match{idx, weight}; idx is an index into the target as passed to set_target. */
+int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t* sel_idx, int64_t n_sel,
+                          int32_t* idx_out, float* weight_out);
+
+/* ICPOptimizer::estimatePose (ICPOptimizer.h:140): the whole iteration loop on the device.
+ * pose_history (nullable) receives 16 floats per executed iteration (what the reference hands to
+ * ConvergenceMeasure::recordAlignmentError, ICPOptimizer.h:629-631); it must hold
+ * icp_gpu_max_iterations() entries.  n_iterations_out (nullable) = iterations executed. */
+int icp_gpu_estimate_pose(icp_gpu_ctx* ctx, float pose_inout[16], float* pose_history, int32_t* n_iterations_out,
+                          icp_gpu_timings* timings);
+/* Upper bound of the iterations estimate_pose will run for the current config and source
+ * (max(nIter, pyramid levels) in multi-resolution mode, ICPOptimizer.h:540,634-655). */
+int icp_gpu_max_iterations(const icp_gpu_ctx* ctx);
+/* Asynchronous form for queues of pairs: enqueue the registration on the context's stream without
+ * waiting; the result is fetched (and waited for) by icp_gpu_estimate_pose_finish. */
+int icp_gpu_estimate_pose_async(icp_gpu_ctx* ctx, const float pose_in[16]);
+int icp_gpu_estimate_pose_finish(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out);
+
+int icp_gpu_get_stats(icp_gpu_ctx* ctx, icp_gpu_stats* out);
+
+/* Point-sharded registration of one very large pair across ranks (one context per rank, each
+ * holding the whole target and its shard of the source).  Per iteration:
+ *   icp_gpu_iteration_local   -> this rank's partial sums (linear metrics: the normal equations,
+ *                                <= ICP_GPU_MAX_PARTIALS doubles; the count is written to *n_values);
+ *   (the caller all-reduces them, e.g. one NCCL ncclAllReduce(ncclDouble, ncclSum));
+ *   icp_gpu_iteration_apply   -> every rank solves the identical system and updates its pose.
+ * Symmetric / point-to-point need the matched-set means first: phase 0 yields 7 sums, phase 1 the
+ * system.  n_phases = icp_gpu_iteration_phases(). */
+#define ICP_GPU_MAX_PARTIALS 32
+int icp_gpu_iteration_phases(const icp_gpu_ctx* ctx);
+int icp_gpu_iteration_begin(icp_gpu_ctx* ctx, const float pose_in[16]);
+int icp_gpu_iteration_local(icp_gpu_ctx* ctx, int phase, double* partials_out, int32_t* n_values);
+int icp_gpu_iteration_apply(icp_gpu_ctx* ctx, int phase, const double* reduced_in, int32_t n_values);
+int icp_gpu_iteration_end(icp_gpu_ctx* ctx, float pose_out[16]);
+/* Device-pointer forms of the two above for collectives that run on the stream (NCCL):
+ * returns the device address of the context's partial-sum buffer (ICP_GPU_MAX_PARTIALS doubles). */
+int icp_gpu_iteration_local_dev(icp_gpu_ctx* ctx, int phase, double** partials_dev, int32_t* n_values);
+int icp_gpu_iteration_apply_dev(icp_gpu_ctx* ctx, int phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICP_GPU_H */
