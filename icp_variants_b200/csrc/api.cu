@@ -1,0 +1,728 @@
+// api.cu -- the icp_gpu_* C ABI (include/icp_gpu.h): context, device buffers, iteration planning,
+// CUDA-graph replay of the registration loop.  Host code only; the kernels live in grid.cu,
+// match.cu, solve.cu and lm.cu.
+//
+// What runs where: the host plans the iterations (level strides, selection masks) and enqueues
+// them; every iteration is {match kernel, reduction(+solve) kernel(s)} on one stream with no host
+// synchronisation in between -- the loop state (pose, iteration counter, status) lives in DevState
+// on the device.  The only host<->device traffic of estimate_pose is the iteration descriptors and
+// the 16-float pose up, and the pose, pose history and DevState down.
+//
+// Reference: ICPOptimizer.h:185-349 / :493-663 (the loop), NearestNeighbor.h:12-36 (matcher API).
+#include "icp_internal.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#define DESC_QUERY (ICP_MAX_ITERS)       // descriptor slot used by icp_gpu_query_matches
+#define DESC_SHARD (ICP_MAX_ITERS + 1)   // descriptor slot used by the point-sharded iteration API
+#define DESC_TOTAL (ICP_MAX_ITERS + 2)
+
+namespace {
+
+// std::mt19937 + libstdc++ generate_canonical<double,53> (selection.h:88-104, contract D7)
+struct Mt19937 {
+    uint32_t mt[624]; int idx;
+    void seed(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; ++i) {
+                const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    }
+    double canonical() {
+        const double lo = (double)next(), hi = (double)next();
+        double v = (lo + hi * 4294967296.0) / 18446744073709551616.0;
+        if (v >= 1.0) v = nextafter(1.0, 0.0);
+        return v;
+    }
+};
+
+long long __float_as_int_host(float f) { int32_t i; memcpy(&i, &f, 4); return (long long)i; }
+
+struct DeviceBuf {
+    void* p = nullptr; size_t cap = 0;
+};
+
+struct Plan {
+    int n_iters = 0;
+    std::vector<IterDesc> desc;       // n_iters entries
+    std::vector<int> grid_queries;    // launch-size bound per iteration (independent of the random draw)
+    std::vector<int> sel;             // concatenated selection index lists (mt19937 mode)
+};
+
+}  // namespace
+
+struct icp_gpu_ctx {
+    int device = 0, n_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    icp_gpu_config cfg;
+    float K[9]; uint32_t width = 0, height = 0; bool have_camera = false;
+    // clouds
+    DeviceBuf stage, src_pts, src_nrm, tgt_pts, tgt_nrm, tgt_pts_sorted, tgt_nrm_sorted;
+    int n_src = -1, n_tgt = -1;
+    std::vector<uint8_t> src_finite;   // host copy of "point and normal finite" per source point
+    bool src_finite_valid = false;
+    // grid
+    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums;
+    int T = 0; bool grid_built = false; double index_ms = 0.0;
+    // loop state
+    DeviceBuf state, desc, sel, match_pos, match_w, match_idx, partials, pose_dev, history;
+    float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
+    IterDesc* h_desc = nullptr;                                                       // pinned, DESC_TOTAL
+    int n_reduce_blocks = 1;
+    // graph cache
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<long long> graph_key;
+    uint64_t graph_launches = 0;
+    // async call state
+    bool pending = false; int pending_iters = 0;
+    // shard iteration state
+    bool shard_open = false; int shard_algo = 0;
+    icp_gpu_stats stats;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    char err[512];
+};
+
+namespace {
+
+int fail(icp_gpu_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) return fail(ctx, ICP_GPU_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+int ensure(icp_gpu_ctx* ctx, DeviceBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return 0;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
+    if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+int bind(icp_gpu_ctx* ctx) {
+    CU(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+int pick_T(int n) {
+    // ~2-4 points per occupied cell for surface-like clouds: cells = 4..8 x points
+    int T = 3;
+    while (T < 24 && (1ll << T) < 4ll * (long long)(n > 0 ? n : 1)) ++T;
+    if (T > 3 * ICP_MAX_BITS_PER_AXIS) T = 3 * ICP_MAX_BITS_PER_AXIS;
+    return T;
+}
+
+int choose_algorithm(const icp_gpu_ctx* c) {   // 0 grid, 1 brute, 2 projective
+    if (c->cfg.matching == ICP_GPU_MATCH_PROJECTIVE) return 2;
+    if (c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE) return 1;
+    if (c->cfg.nn_algorithm == ICP_GPU_NN_GRID) return 0;
+    return c->n_tgt <= 2048 ? 1 : 0;
+}
+
+int coarsest_stride(long long n) {   // ICPOptimizer.h:503-516
+    float res = 1.0f; int sz = (int)n;
+    for (;;) { sz = (int)(sz / 2.0); if (sz < 100) break; res *= 2.0f; }
+    return (int)res;
+}
+
+int upload_cloud(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n, bool device_ptrs,
+                 DeviceBuf& pts, DeviceBuf& nrmb) {
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    if (ensure(ctx, pts, n1 * sizeof(float4)) || ensure(ctx, nrmb, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
+    if (n == 0) return 0;
+    const float* dx = xyz; const float* dn = nrm; const uint8_t* dc = rgba;
+    if (!device_ptrs) {
+        const size_t bx = (size_t)n * 12, bc = (size_t)n * 4;
+        const size_t ox = 0, on = (bx + 255) / 256 * 256, oc = on + (nrm ? (bx + 255) / 256 * 256 : 0);
+        if (ensure(ctx, ctx->stage, oc + (rgba ? bc : 0) + 256)) return ICP_GPU_E_CUDA;
+        char* st = (char*)ctx->stage.p;
+        CU(cudaMemcpyAsync(st + ox, xyz, bx, cudaMemcpyHostToDevice, ctx->stream));
+        dx = (const float*)(st + ox);
+        if (nrm) { CU(cudaMemcpyAsync(st + on, nrm, bx, cudaMemcpyHostToDevice, ctx->stream)); dn = (const float*)(st + on); }
+        if (rgba) { CU(cudaMemcpyAsync(st + oc, rgba, bc, cudaMemcpyHostToDevice, ctx->stream)); dc = (const uint8_t*)(st + oc); }
+    }
+    CU(icp_launch_pack_cloud(dx, dn, dc, (int)n, (float4*)pts.p, (float4*)nrmb.p, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+    return 0;
+}
+
+int build_grid(icp_gpu_ctx* ctx) {
+    const int n = ctx->n_tgt;
+    ctx->T = pick_T(n);
+    const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->T) + 1;
+    if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) ||
+        ensure(ctx, ctx->keys, n1 * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->cell_start, cells1 * 4) ||
+        ensure(ctx, ctx->block_sums, (cells1 / 4096 + 2) * 4) || ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64))
+        return ICP_GPU_E_CUDA;
+    int launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CU(icp_launch_grid_build((const float4*)ctx->tgt_pts.p, (const float4*)ctx->tgt_nrm.p, n, ctx->T, (GridParams*)ctx->grid.p,
+                             (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
+                             (unsigned int*)ctx->cell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->tgt_pts_sorted.p,
+                             (float4*)ctx->tgt_nrm_sorted.p, ctx->stream, &launches));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    ctx->grid_built = true;
+    return 0;
+}
+
+int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n, bool dev) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (n < 0 || n > 0x7fffffff / 4 || (n > 0 && !xyz)) return fail(ctx, ICP_GPU_E_ARG, "bad cloud (n=%lld, xyz=%p)", (long long)n, (const void*)xyz);
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    if (target) {
+        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->tgt_pts, ctx->tgt_nrm)) return ICP_GPU_E_CUDA;
+        ctx->n_tgt = (int)n;
+        // buildIndex: the grid is always built (cheap), the matcher choice is made per call
+        if (build_grid(ctx)) return ICP_GPU_E_CUDA;
+    } else {
+        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->src_pts, ctx->src_nrm)) return ICP_GPU_E_CUDA;
+        ctx->n_src = (int)n;
+        ctx->src_finite_valid = false;
+        if (!dev) {
+            ctx->src_finite.resize((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                bool f = isfinite(xyz[3 * i]) && isfinite(xyz[3 * i + 1]) && isfinite(xyz[3 * i + 2]);
+                if (nrm) f = f && isfinite(nrm[3 * i]) && isfinite(nrm[3 * i + 1]) && isfinite(nrm[3 * i + 2]);
+                ctx->src_finite[(size_t)i] = f ? 1 : 0;
+            }
+            ctx->src_finite_valid = true;
+        }
+        const size_t n1 = (size_t)(n > 0 ? n : 1);
+        if (ensure(ctx, ctx->match_pos, n1 * 4) || ensure(ctx, ctx->match_w, n1 * 4) || ensure(ctx, ctx->match_idx, n1 * 4)) return ICP_GPU_E_CUDA;
+        ctx->n_reduce_blocks = icp_reduce_blocks((int)n, ctx->n_sms);
+        if (ensure(ctx, ctx->partials, (size_t)ctx->n_reduce_blocks * ICP_NRED * sizeof(double))) return ICP_GPU_E_CUDA;
+    }
+    // Host arrays are only borrowed for the duration of the call, so wait for the copies; the
+    // device-pointer form stays asynchronous (stream-ordered with everything that follows).
+    if (!dev) CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
+}
+
+// "point and normal finite" flags of a device-resident source, fetched lazily (mt19937 + multires only)
+int fetch_src_finite(icp_gpu_ctx* ctx) {
+    if (ctx->src_finite_valid) return 0;
+    const size_t n = (size_t)ctx->n_src;
+    std::vector<float4> p(n), m(n);
+    CU(cudaMemcpyAsync(p.data(), ctx->src_pts.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(m.data(), ctx->src_nrm.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->src_finite.resize(n);
+    for (size_t i = 0; i < n; ++i)
+        ctx->src_finite[i] = (isfinite(p[i].x) && isfinite(p[i].y) && isfinite(p[i].z) && isfinite(m[i].x) && isfinite(m[i].y) && isfinite(m[i].z)) ? 1 : 0;
+    ctx->src_finite_valid = true;
+    return 0;
+}
+
+// The iteration schedule of estimatePose (ICPOptimizer.h:503-525, :540, :549-550, :634-655; Appendix A of SURVEY.md).
+int make_plan(icp_gpu_ctx* ctx, Plan& plan) {
+    const icp_gpu_config& cfg = ctx->cfg;
+    const int n = ctx->n_src;
+    const bool host_rng = cfg.selection == ICP_GPU_SELECT_RANDOM && cfg.selection_rng == ICP_GPU_RNG_MT19937;
+    const bool dev_rng = cfg.selection == ICP_GPU_SELECT_RANDOM && cfg.selection_rng == ICP_GPU_RNG_DEVICE;
+    if (host_rng && cfg.multires && fetch_src_finite(ctx)) return ICP_GPU_E_CUDA;
+    int stride = cfg.multires ? coarsest_stride(n) : 1;
+    Mt19937 rng; uint32_t n_selections = 0;
+    if (host_rng) rng.seed(cfg.seed + n_selections++);      // PointSelection ctor -> initSampler
+    else ++n_selections;
+    for (int i = 0; i < cfg.n_iterations || cfg.multires; ++i) {
+        if (plan.n_iters >= ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "more than %d iterations", ICP_MAX_ITERS);
+        IterDesc d; memset(&d, 0, sizeof(d));
+        const int level_slots = (int)(((long long)n + stride - 1) / stride);
+        d.stride = stride; d.sel_offset = -1; d.filter_finite = cfg.multires ? 1 : 0; d.proba = -1.0f; d.n_queries = level_slots;
+        if (dev_rng) { d.proba = (float)cfg.proba; d.rng_key = cfg.seed * 2654435761u + (uint32_t)(i + 1) * 0x9E3779B9u; }
+        if (host_rng) {
+            // resample(): one draw per point of the current level's cloud, in order (selection.h:88-104)
+            d.sel_offset = (int)plan.sel.size();
+            int c = 0;
+            for (long long k = 0; k < n; k += stride) {
+                if (cfg.multires && !ctx->src_finite[(size_t)k]) continue;      // not part of the level cloud (PointCloud.h:335)
+                if (rng.canonical() < cfg.proba) { plan.sel.push_back((int)k); ++c; }
+            }
+            d.n_queries = c; d.stride = 1; d.filter_finite = 0;
+        }
+        plan.desc.push_back(d);
+        plan.grid_queries.push_back(level_slots);
+        plan.n_iters += 1;
+        if (cfg.multires) {
+            if (stride == 1 && i >= cfg.n_iterations - 1) break;
+            if (stride == 1) continue;
+            stride /= 2; if (stride < 1) stride = 1;
+            if (host_rng) rng.seed(cfg.seed + n_selections++); else ++n_selections;   // new PointSelection per level (:652)
+        }
+    }
+    return 0;
+}
+
+int check_ready(icp_gpu_ctx* ctx) {
+    if (ctx->n_src < 0) return fail(ctx, ICP_GPU_E_STATE, "no source cloud set");
+    if (ctx->n_tgt < 0) return fail(ctx, ICP_GPU_E_STATE, "no target cloud set (buildIndex)");
+    if (ctx->cfg.matching == ICP_GPU_MATCH_PROJECTIVE) {
+        // NearestNeighbor.h:335-349
+        if (!ctx->have_camera) return fail(ctx, ICP_GPU_E_STATE, "projective matching needs icp_gpu_set_camera");
+        if ((long long)ctx->width * ctx->height != (long long)ctx->n_tgt || ctx->height == 0)
+            return fail(ctx, ICP_GPU_E_STATE, "projective matching: target size %d != width*height %u*%u", ctx->n_tgt, ctx->width, ctx->height);
+    }
+    return 0;
+}
+
+void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, bool want_idx) {
+    memset(&a, 0, sizeof(a));
+    a.src_pts = (const float4*)c->src_pts.p; a.src_nrm = (const float4*)c->src_nrm.p; a.n_src = c->n_src;
+    a.sel = (const int*)c->sel.p; a.desc = (const IterDesc*)c->desc.p;
+    a.state_ro = (const DevState*)c->state.p; a.state = (DevState*)c->state.p;
+    a.grid = (const GridParams*)c->grid.p; a.cell_start = (const unsigned int*)c->cell_start.p;
+    a.tgt_pts = (const float4*)(algo == 0 ? c->tgt_pts_sorted.p : c->tgt_pts.p);
+    a.tgt_nrm = (const float4*)(algo == 0 ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
+    a.n_tgt = c->n_tgt;
+    if (c->have_camera) { a.fx = c->K[0]; a.fy = c->K[4]; a.cx = c->K[6]; a.cy = c->K[7]; }   // column-major Matrix3f
+    a.width = c->width; a.height = c->height;
+    a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
+    a.max_d2 = c->cfg.max_distance_sq;
+    a.match_pos = (int*)c->match_pos.p; a.match_w = (float*)c->match_w.p; a.match_idx = want_idx ? (int*)c->match_idx.p : nullptr;
+    a.desc_index = desc_index;
+}
+
+void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int desc_index, int solve) {
+    memset(&r, 0, sizeof(r));
+    r.src_pts = (const float4*)c->src_pts.p; r.src_nrm = (const float4*)c->src_nrm.p; r.n_src = c->n_src;
+    r.sel = (const int*)c->sel.p; r.desc = (const IterDesc*)c->desc.p; r.state = (DevState*)c->state.p;
+    r.tgt_pts = (const float4*)(algo == 0 ? c->tgt_pts_sorted.p : c->tgt_pts.p);
+    r.tgt_nrm = (const float4*)(algo == 0 ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
+    r.match_pos = (const int*)c->match_pos.p; r.match_w = (const float*)c->match_w.p;
+    r.partials = (double*)c->partials.p; r.pose_history = (float*)c->history.p;
+    r.metric = c->cfg.metric; r.desc_index = desc_index; r.solve = solve;
+}
+
+int blocks_for(const icp_gpu_ctx* c, int queries) {
+    int nb = icp_reduce_blocks(queries, c->n_sms);
+    return nb < c->n_reduce_blocks ? nb : c->n_reduce_blocks;
+}
+
+// Enqueue the whole loop.  ev_marks (nullable): events recorded around each stage for the timings report.
+int enqueue_iterations(icp_gpu_ctx* ctx, const Plan& plan, int algo, std::vector<cudaEvent_t>* ev_marks) {
+    MatchArgs ma; ReduceArgs ra;
+    fill_match_args(ctx, ma, algo, -1, false);
+    fill_reduce_args(ctx, ra, algo, -1, 1);
+    int launches = 0;
+    for (int i = 0; i < plan.n_iters; ++i) {
+        const int q = plan.grid_queries[i];
+        if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * i], ctx->stream));
+        CU(icp_launch_match(ma, algo, q, ctx->stream)); if (q > 0) ++launches;
+        if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * i + 1], ctx->stream));
+        if (ctx->cfg.minimizer == ICP_GPU_MIN_LM) CU(icp_launch_lm(ra, q, blocks_for(ctx, q), ctx->cfg.lm_max_iterations, ctx->stream, &launches));
+        else CU(icp_launch_reduce(ra, q, blocks_for(ctx, q), ctx->stream, &launches));
+    }
+    if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * plan.n_iters], ctx->stream));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    return 0;
+}
+
+int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timings* timings) {
+    if (!ctx || !pose_in) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is already pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    int rc = check_ready(ctx); if (rc) return rc;
+    Plan plan;
+    rc = make_plan(ctx, plan); if (rc) return rc;
+    const int algo = choose_algorithm(ctx);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    // descriptors + selection lists + pose up (pinned staging, stream-ordered)
+    memcpy(ctx->h_desc, plan.desc.data(), sizeof(IterDesc) * (size_t)plan.n_iters);
+    if (plan.n_iters > 0) CU(cudaMemcpyAsync(ctx->desc.p, ctx->h_desc, sizeof(IterDesc) * (size_t)plan.n_iters, cudaMemcpyHostToDevice, ctx->stream));
+    if (!plan.sel.empty()) {
+        if (ensure(ctx, ctx->sel, plan.sel.size() * sizeof(int))) return ICP_GPU_E_CUDA;
+        CU(cudaMemcpyAsync(ctx->sel.p, plan.sel.data(), plan.sel.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // plan.sel is pageable and dies with this frame
+    }
+    memcpy(ctx->h_pose, pose_in, 16 * sizeof(float));
+    CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+
+    std::vector<cudaEvent_t> marks;
+    if (timings) {
+        memset(timings, 0, sizeof(*timings));
+        marks.resize((size_t)2 * plan.n_iters + 1);
+        for (auto& e : marks) CU(cudaEventCreate(&e));
+        rc = enqueue_iterations(ctx, plan, algo, &marks);
+    } else if (ctx->cfg.use_graph && plan.n_iters > 0) {
+        // The graph depends only on launch shapes and pointers, not on descriptor contents.
+        std::vector<long long> key;
+        key.push_back(algo); key.push_back(ctx->cfg.metric); key.push_back(ctx->cfg.minimizer); key.push_back(ctx->cfg.lm_max_iterations);
+        key.push_back(ctx->cfg.weighting); key.push_back(ctx->cfg.rejection); key.push_back(ctx->cfg.color_icp);
+        key.push_back((long long)__float_as_int_host(ctx->cfg.max_distance_sq));
+        key.push_back(ctx->n_src); key.push_back(ctx->n_tgt); key.push_back(ctx->T); key.push_back(ctx->width); key.push_back(ctx->height);
+        for (int k = 0; k < 9; ++k) key.push_back((long long)__float_as_int_host(ctx->have_camera ? ctx->K[k] : 0.f));
+        key.push_back((long long)(uintptr_t)ctx->sel.p); key.push_back((long long)(uintptr_t)ctx->stream);
+        for (int q : plan.grid_queries) key.push_back(q);
+        if (!ctx->graph_exec || key != ctx->graph_key) {
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const uint64_t before = ctx->stats.n_kernel_launches;
+            rc = enqueue_iterations(ctx, plan, algo, nullptr);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(ctx, ICP_GPU_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { ctx->graph_exec = nullptr; return fail(ctx, ICP_GPU_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+            ctx->graph_key = key;
+            ctx->graph_launches = ctx->stats.n_kernel_launches - before;
+        } else {
+            ctx->stats.n_kernel_launches += ctx->graph_launches;
+        }
+        CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    } else {
+        rc = enqueue_iterations(ctx, plan, algo, nullptr);
+    }
+    if (rc) return rc;
+    // results down
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (plan.n_iters > 0) CU(cudaMemcpyAsync(ctx->h_history, ctx->history.p, sizeof(float) * 16 * (size_t)plan.n_iters, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending = true; ctx->pending_iters = plan.n_iters;
+    if (timings) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < plan.n_iters; ++i) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, marks[2 * i], marks[2 * i + 1]);
+            cudaEventElapsedTime(&b, marks[2 * i + 1], marks[2 * i + 2]);
+            timings->matching_ms += a; timings->solver_ms += b;
+        }
+        float tot = 0.f;
+        if (plan.n_iters > 0) cudaEventElapsedTime(&tot, marks[0], marks[2 * plan.n_iters]);
+        float idx_ms = 0.f;
+        if (ctx->grid_built && cudaEventElapsedTime(&idx_ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->index_ms = idx_ms; else cudaGetLastError();
+        timings->total_ms = tot; timings->index_ms = ctx->index_ms; timings->n_iterations = plan.n_iters;
+        timings->n_match_launches = plan.n_iters;
+        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters;
+        for (auto& e : marks) cudaEventDestroy(e);
+    }
+    return ICP_GPU_OK;
+}
+
+int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (!ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "no registration pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    ctx->pending = false;
+    CU(cudaStreamSynchronize(ctx->stream));
+    const DevState& st = *ctx->h_state;
+    if (pose_out) memcpy(pose_out, st.pose, 16 * sizeof(float));
+    if (pose_history && st.iters_done > 0) memcpy(pose_history, ctx->h_history, sizeof(float) * 16 * (size_t)st.iters_done);
+    if (n_iterations_out) *n_iterations_out = st.iters_done;
+    ctx->stats.n_queries = st.n_queries; ctx->stats.n_matched = st.n_matched;
+    ctx->stats.n_distance_evals = st.n_evals; ctx->stats.n_nodes_visited = st.n_nodes;
+    if (st.status == ICP_GPU_E_NO_MATCHES)
+        return fail(ctx, ICP_GPU_E_NO_MATCHES, "iteration %d had no surviving correspondence (the reference hangs in ASSERT here)", st.iters_done);
+    if (st.status != 0) return fail(ctx, st.status, "iteration %d: singular / non-finite normal equations", st.iters_done);
+    return ICP_GPU_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int icp_gpu_abi_version(void) { return ICP_GPU_ABI_VERSION; }
+
+int icp_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void icp_gpu_default_config(icp_gpu_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->metric = ICP_GPU_METRIC_P2P; cfg->minimizer = ICP_GPU_MIN_LINEAR; cfg->matching = ICP_GPU_MATCH_KNN;
+    cfg->selection = ICP_GPU_SELECT_ALL; cfg->proba = 1.0; cfg->seed = 0; cfg->selection_rng = ICP_GPU_RNG_MT19937;
+    cfg->weighting = ICP_GPU_WEIGHT_CONSTANT; cfg->rejection = 1; cfg->max_distance_sq = 0.0003f;
+    cfg->color_icp = 0; cfg->multires = 0; cfg->pyramid_mode = ICP_GPU_PYRAMID_STRIDE; cfg->n_iterations = 20;
+    cfg->lm_max_iterations = 10; cfg->nn_algorithm = ICP_GPU_NN_AUTO; cfg->use_graph = 1;
+}
+
+int icp_gpu_create(icp_gpu_ctx** out, int device) {
+    if (!out) return ICP_GPU_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return ICP_GPU_E_CUDA; }   // no CPU fallback
+    if (device < 0 || device >= n) return ICP_GPU_E_ARG;
+    icp_gpu_ctx* ctx = new (std::nothrow) icp_gpu_ctx();
+    if (!ctx) return ICP_GPU_E_CUDA;
+    ctx->err[0] = 0; ctx->device = device;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    icp_gpu_default_config(&ctx->cfg);
+    cudaDeviceProp prop;
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok && prop.major < 10) ok = false;   // the kernels are built for sm_100a only
+    if (ok) ctx->n_sms = prop.multiProcessorCount;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_pose, 16 * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_history, 16 * sizeof(float) * ICP_MAX_ITERS) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_state, sizeof(DevState)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_desc, sizeof(IterDesc) * DESC_TOTAL) == cudaSuccess;
+    ok = ok && ensure(ctx, ctx->state, sizeof(DevState)) == 0 && ensure(ctx, ctx->desc, sizeof(IterDesc) * DESC_TOTAL) == 0 &&
+         ensure(ctx, ctx->pose_dev, 64) == 0 && ensure(ctx, ctx->history, 16 * sizeof(float) * ICP_MAX_ITERS) == 0 &&
+         ensure(ctx, ctx->sel, 256) == 0;
+    if (ok) ok = cudaMemsetAsync(ctx->state.p, 0, sizeof(DevState), ctx->stream) == cudaSuccess && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); icp_gpu_destroy(ctx); return ICP_GPU_E_CUDA; }
+    *out = ctx;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_destroy(icp_gpu_ctx* ctx) {
+    if (!ctx) return ICP_GPU_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    DeviceBuf* bufs[] = {&ctx->stage, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
+                         &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->sel,
+                         &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history};
+    for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
+    if (ctx->h_history) cudaFreeHost(ctx->h_history);
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return ICP_GPU_OK;
+}
+
+const char* icp_gpu_last_error(const icp_gpu_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int icp_gpu_set_stream(icp_gpu_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_synchronize(icp_gpu_ctx* ctx) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
+    if (!ctx || !c) return ICP_GPU_E_ARG;
+    if (c->metric < 0 || c->metric > 2) return fail(ctx, ICP_GPU_E_ARG, "metric %d", c->metric);
+    if (c->minimizer < 0 || c->minimizer > 1) return fail(ctx, ICP_GPU_E_ARG, "minimizer %d", c->minimizer);
+    if (c->matching < 0 || c->matching > 1) return fail(ctx, ICP_GPU_E_ARG, "matching %d", c->matching);
+    if (c->selection < 0 || c->selection > 1) return fail(ctx, ICP_GPU_E_ARG, "selection %d", c->selection);
+    if (c->selection_rng < 0 || c->selection_rng > 1) return fail(ctx, ICP_GPU_E_ARG, "selection_rng %d", c->selection_rng);
+    if (c->weighting < 0 || c->weighting > 3) return fail(ctx, ICP_GPU_E_ARG, "weighting %d", c->weighting);
+    if (c->nn_algorithm < 0 || c->nn_algorithm > 2) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
+    if (c->pyramid_mode != ICP_GPU_PYRAMID_STRIDE) return fail(ctx, ICP_GPU_E_ARG, "pyramid_mode %d", c->pyramid_mode);
+    if (c->n_iterations < 0 || c->n_iterations > ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "n_iterations %d (max %d)", c->n_iterations, ICP_MAX_ITERS);
+    if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);
+    if (c->matching == ICP_GPU_MATCH_PROJECTIVE && c->color_icp) return fail(ctx, ICP_GPU_E_ARG, "colour ICP is a k-NN variant (main.cpp:240-243)");
+    ctx->cfg = *c;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_get_config(const icp_gpu_ctx* ctx, icp_gpu_config* c) {
+    if (!ctx || !c) return ICP_GPU_E_ARG;
+    *c = ctx->cfg;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_set_camera(icp_gpu_ctx* ctx, const float K[9], uint32_t width, uint32_t height) {
+    if (!ctx || !K) return ICP_GPU_E_ARG;
+    memcpy(ctx->K, K, 9 * sizeof(float));
+    ctx->width = width; ctx->height = height; ctx->have_camera = true;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_set_target(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n) { return set_cloud(ctx, true, xyz, nrm, rgba, n, false); }
+int icp_gpu_set_source(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n) { return set_cloud(ctx, false, xyz, nrm, rgba, n, false); }
+int icp_gpu_set_target_dev(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n) { return set_cloud(ctx, true, xyz, nrm, rgba, n, true); }
+int icp_gpu_set_source_dev(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n) { return set_cloud(ctx, false, xyz, nrm, rgba, n, true); }
+
+int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t* sel_idx, int64_t n_sel, int32_t* idx_out, float* weight_out) {
+    if (!ctx || !pose || !idx_out || !weight_out) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    int rc = check_ready(ctx); if (rc) return rc;
+    const int nq = sel_idx ? (int)n_sel : ctx->n_src;
+    if (sel_idx && (n_sel < 0 || n_sel > ctx->n_src)) return fail(ctx, ICP_GPU_E_ARG, "n_sel %lld", (long long)n_sel);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    IterDesc d; memset(&d, 0, sizeof(d));
+    d.n_queries = nq; d.stride = 1; d.sel_offset = sel_idx ? 0 : -1; d.filter_finite = 0; d.proba = -1.0f;
+    if (sel_idx && nq > 0) {
+        for (int64_t k = 0; k < n_sel; ++k) if (sel_idx[k] < 0 || sel_idx[k] >= ctx->n_src) return fail(ctx, ICP_GPU_E_ARG, "sel_idx[%lld] out of range", (long long)k);
+        if (ensure(ctx, ctx->sel, (size_t)nq * sizeof(int))) return ICP_GPU_E_CUDA;
+        CU(cudaMemcpyAsync(ctx->sel.p, sel_idx, (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->h_desc[DESC_QUERY] = d;
+    CU(cudaMemcpyAsync((IterDesc*)ctx->desc.p + DESC_QUERY, &ctx->h_desc[DESC_QUERY], sizeof(IterDesc), cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(ctx->h_pose, pose, 16 * sizeof(float));
+    CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
+    const int algo = choose_algorithm(ctx);
+    MatchArgs ma; fill_match_args(ctx, ma, algo, DESC_QUERY, true);
+    CU(icp_launch_match(ma, algo, nq, ctx->stream));
+    ctx->stats.n_kernel_launches += 2;
+    if (nq > 0) {
+        CU(cudaMemcpyAsync(idx_out, ctx->match_idx.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(weight_out, ctx->match_w.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.n_queries = ctx->h_state->n_queries; ctx->stats.n_matched = ctx->h_state->n_matched;
+    ctx->stats.n_distance_evals = ctx->h_state->n_evals; ctx->stats.n_nodes_visited = ctx->h_state->n_nodes;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_max_iterations(const icp_gpu_ctx* ctx) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (!ctx->cfg.multires) return ctx->cfg.n_iterations;
+    int levels = 1, s = coarsest_stride(ctx->n_src > 0 ? ctx->n_src : 0);
+    while (s > 1) { s /= 2; ++levels; }
+    return levels > ctx->cfg.n_iterations ? levels : ctx->cfg.n_iterations;
+}
+
+int icp_gpu_estimate_pose_async(icp_gpu_ctx* ctx, const float pose_in[16]) { return start_registration(ctx, pose_in, nullptr); }
+
+int icp_gpu_estimate_pose_finish(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out) {
+    return finish_registration(ctx, pose_out, pose_history, n_iterations_out);
+}
+
+int icp_gpu_estimate_pose(icp_gpu_ctx* ctx, float pose_inout[16], float* pose_history, int32_t* n_iterations_out, icp_gpu_timings* timings) {
+    int rc = start_registration(ctx, pose_inout, timings);
+    if (rc) return rc;
+    return finish_registration(ctx, pose_inout, pose_history, n_iterations_out);
+}
+
+int icp_gpu_get_stats(icp_gpu_ctx* ctx, icp_gpu_stats* out) {
+    if (!ctx || !out) return ICP_GPU_E_ARG;
+    *out = ctx->stats;
+    return ICP_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------- point-sharded iteration
+int icp_gpu_iteration_phases(const icp_gpu_ctx* ctx) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    return ctx->cfg.metric == ICP_GPU_METRIC_SYMMETRIC ? 2 : 1;
+}
+
+static int shard_values(int metric, int phase) {
+    if (metric == ICP_GPU_METRIC_P2P) return 23;
+    if (metric == ICP_GPU_METRIC_SYMMETRIC && phase == 0) return 7;
+    return 28;
+}
+
+int icp_gpu_iteration_begin(icp_gpu_ctx* ctx, const float pose_in[16]) {
+    if (!ctx || !pose_in) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (ctx->cfg.minimizer != ICP_GPU_MIN_LINEAR) return fail(ctx, ICP_GPU_E_ARG, "the point-sharded path supports the linear minimiser only");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    int rc = check_ready(ctx); if (rc) return rc;
+    IterDesc d; memset(&d, 0, sizeof(d));
+    d.n_queries = ctx->n_src; d.stride = 1; d.sel_offset = -1; d.filter_finite = 0; d.proba = -1.0f;
+    ctx->h_desc[DESC_SHARD] = d;
+    CU(cudaMemcpyAsync((IterDesc*)ctx->desc.p + DESC_SHARD, &ctx->h_desc[DESC_SHARD], sizeof(IterDesc), cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(ctx->h_pose, pose_in, 16 * sizeof(float));
+    CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
+    ctx->shard_open = true; ctx->shard_algo = choose_algorithm(ctx);
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_iteration_local_dev(icp_gpu_ctx* ctx, int phase, double** partials_dev, int32_t* n_values) {
+    if (!ctx || !partials_dev || !n_values) return ICP_GPU_E_ARG;
+    if (!ctx->shard_open) return fail(ctx, ICP_GPU_E_STATE, "icp_gpu_iteration_begin not called");
+    if (phase < 0 || phase >= icp_gpu_iteration_phases(ctx)) return fail(ctx, ICP_GPU_E_ARG, "phase %d", phase);
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    const int algo = ctx->shard_algo;
+    int launches = 0;
+    if (phase == 0) {
+        MatchArgs ma; fill_match_args(ctx, ma, algo, DESC_SHARD, false);
+        CU(icp_launch_match(ma, algo, ctx->n_src, ctx->stream)); ++launches;
+    }
+    ReduceArgs ra; fill_reduce_args(ctx, ra, algo, DESC_SHARD, 0);
+    CU(icp_launch_reduce_phase(ra, blocks_for(ctx, ctx->n_src), phase, ctx->stream, &launches));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    *partials_dev = ((DevState*)ctx->state.p)->shard_partials;
+    *n_values = shard_values(ctx->cfg.metric, phase);
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_iteration_local(icp_gpu_ctx* ctx, int phase, double* partials_out, int32_t* n_values) {
+    if (!partials_out) return ICP_GPU_E_ARG;
+    double* dev = nullptr;
+    int rc = icp_gpu_iteration_local_dev(ctx, phase, &dev, n_values);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(partials_out, dev, sizeof(double) * (size_t)*n_values, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_iteration_apply_dev(icp_gpu_ctx* ctx, int phase) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (!ctx->shard_open) return fail(ctx, ICP_GPU_E_STATE, "icp_gpu_iteration_begin not called");
+    if (phase < 0 || phase >= icp_gpu_iteration_phases(ctx)) return fail(ctx, ICP_GPU_E_ARG, "phase %d", phase);
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    const int mode = ctx->cfg.metric == ICP_GPU_METRIC_SYMMETRIC ? (phase == 0 ? 3 : 2) : ctx->cfg.metric;
+    CU(icp_launch_shard_apply((DevState*)ctx->state.p, mode, (float*)ctx->history.p, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_iteration_apply(icp_gpu_ctx* ctx, int phase, const double* reduced_in, int32_t n_values) {
+    if (!ctx || !reduced_in) return ICP_GPU_E_ARG;
+    if (n_values < 0 || n_values > ICP_GPU_MAX_PARTIALS) return fail(ctx, ICP_GPU_E_ARG, "n_values %d", n_values);
+    if (!ctx->shard_open) return fail(ctx, ICP_GPU_E_STATE, "icp_gpu_iteration_begin not called");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    CU(cudaMemcpyAsync(((DevState*)ctx->state.p)->shard_partials, reduced_in, sizeof(double) * (size_t)n_values, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // reduced_in is pageable caller memory
+    return icp_gpu_iteration_apply_dev(ctx, phase);
+}
+
+int icp_gpu_iteration_end(icp_gpu_ctx* ctx, float pose_out[16]) {
+    if (!ctx || !pose_out) return ICP_GPU_E_ARG;
+    if (!ctx->shard_open) return fail(ctx, ICP_GPU_E_STATE, "icp_gpu_iteration_begin not called");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    ctx->shard_open = false;
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(pose_out, ctx->h_state->pose, 16 * sizeof(float));
+    if (ctx->h_state->status == ICP_GPU_E_NO_MATCHES) return fail(ctx, ICP_GPU_E_NO_MATCHES, "no surviving correspondence on any rank");
+    if (ctx->h_state->status != 0) return fail(ctx, ctx->h_state->status, "singular / non-finite normal equations");
+    return ICP_GPU_OK;
+}
+
+}  // extern "C"

@@ -117,6 +117,8 @@ cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, in
 cudaError_t icp_launch_match(const MatchArgs& a, int algorithm /*0 grid,1 brute,2 projective*/, int max_queries, cudaStream_t s);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int max_queries, int n_blocks, cudaStream_t s, int* n_launches);
+// one phase of the point-sharded iteration: the summed row is left in state->shard_partials
+cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase, cudaStream_t s, int* n_launches);
 int icp_reduce_blocks(int max_queries, int n_sms);
 cudaError_t icp_launch_shard_apply(DevState* st, int mode, float* history, cudaStream_t s);
 cudaError_t icp_launch_lm(const ReduceArgs& a, int max_queries, int n_blocks, int lm_max_iterations, cudaStream_t s, int* n_launches);
@@ -166,4 +168,113 @@ __device__ __forceinline__ int slot_source_index(const IterDesc& d, const int* s
     if (d.sel_offset >= 0) return sel[d.sel_offset + k];
     const long long i = (long long)k * d.stride;
     return i < n_src ? (int)i : -1;
+}
+
+// ---------------------------------------------------------------------------- reductions
+template <int H>
+__device__ __forceinline__ void halve_step(double (&v)[32], int lane) {
+    const bool upper = (lane & H) != 0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const double send = upper ? v[k] : v[k + H];
+        const double keep = upper ? v[k + H] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, H);
+    }
+}
+// After the call, lane L holds in v[0] the warp-wide sum of element L.
+__device__ __forceinline__ void warp_reduce_scatter32(double (&v)[32], int lane) {
+    halve_step<16>(v, lane); halve_step<8>(v, lane); halve_step<4>(v, lane); halve_step<2>(v, lane); halve_step<1>(v, lane);
+}
+
+// ---------------------------------------------------------------------------- small dense algebra (fp64, one thread)
+static __device__ int solve6_dev(double* A /*row-major 6x6, destroyed*/, double* b, double* x) {
+    for (int k = 0; k < 6; ++k) {
+        int p = k; double mx = fabs(A[k * 6 + k]);
+        for (int i = k + 1; i < 6; ++i) if (fabs(A[i * 6 + k]) > mx) { mx = fabs(A[i * 6 + k]); p = i; }
+        if (!(mx > 0.0)) return -1;
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[p * 6 + j]; A[p * 6 + j] = t; }
+            const double t = b[k]; b[k] = b[p]; b[p] = t;
+        }
+        for (int i = k + 1; i < 6; ++i) {
+            const double f = A[i * 6 + k] / A[k * 6 + k];
+            for (int j = k; j < 6; ++j) A[i * 6 + j] -= f * A[k * 6 + j];
+            b[i] -= f * b[k];
+        }
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = b[i];
+        for (int j = i + 1; j < 6; ++j) s -= A[i * 6 + j] * x[j];
+        x[i] = s / A[i * 6 + i];
+    }
+    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return -1;
+    return 0;
+}
+
+
+__device__ __forceinline__ void mat4_identity_dev(float* M) {
+    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+
+
+// estimatedPose = increment * estimatedPose (ICPOptimizer.h:614-620); history as handed to
+// ConvergenceMeasure::recordAlignmentError (:629-631).
+static __device__ void apply_increment(DevState* st, const float* inc, int rc, float* history) {
+    if (st->status == 0) {
+        if (rc != 0) st->status = rc;
+        else {
+            float np[16];
+            mat4_mul_pinned(inc, st->pose, np);
+            for (int i = 0; i < 16; ++i) st->pose[i] = np[i];
+            inv_transpose3_pinned(st->pose, st->nrm);
+            if (history) for (int i = 0; i < 16; ++i) history[16 * st->iters_done + i] = np[i];
+            st->iters_done += 1;
+        }
+    }
+    st->iter += 1;
+}
+
+
+// Block + grid reduction of one 32-double row per thread.  Every block writes its row to
+// partials[block][32]; the block that draws the last ticket sums all rows in a fixed order
+// (deterministic, no floating-point atomics).  Returns true in every thread of that last block,
+// with the total in fin[0][0..31].  red: [THREADS/32][32], fin: [THREADS/32][32] shared scratch.
+template <int THREADS>
+__device__ __forceinline__ bool grid_reduce_row(double (&v)[32], double* __restrict__ partials, unsigned int* ticket,
+                                                double (*red)[32], double (*fin)[32], bool* is_last) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    warp_reduce_scatter32(v, lane);
+    red[wid][lane] = v[0];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) s += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * ICP_NRED + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        *is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*is_last) return false;
+    __threadfence();
+    {
+        const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+        double s = 0.0;
+        for (int b = g; b < (int)gridDim.x; b += THREADS / 32) s += __ldcg(&partials[(size_t)b * ICP_NRED + c]);
+        fin[g][c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < THREADS / 32; ++g) s += fin[g][threadIdx.x];
+        fin[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *ticket = 0;
+    return true;
 }

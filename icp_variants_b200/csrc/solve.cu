@@ -13,47 +13,6 @@
 
 struct PoseSmR { float P[16]; };
 
-// ---------------------------------------------------------------------------- reductions
-template <int H>
-__device__ __forceinline__ void halve_step(double (&v)[32], int lane) {
-    const bool upper = (lane & H) != 0;
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-        const double send = upper ? v[k] : v[k + H];
-        const double keep = upper ? v[k + H] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, H);
-    }
-}
-// After the call, lane L holds in v[0] the warp-wide sum of element L.
-__device__ __forceinline__ void warp_reduce_scatter32(double (&v)[32], int lane) {
-    halve_step<16>(v, lane); halve_step<8>(v, lane); halve_step<4>(v, lane); halve_step<2>(v, lane); halve_step<1>(v, lane);
-}
-
-// ---------------------------------------------------------------------------- small dense algebra (fp64, one thread)
-__device__ int solve6_dev(double* A /*row-major 6x6, destroyed*/, double* b, double* x) {
-    for (int k = 0; k < 6; ++k) {
-        int p = k; double mx = fabs(A[k * 6 + k]);
-        for (int i = k + 1; i < 6; ++i) if (fabs(A[i * 6 + k]) > mx) { mx = fabs(A[i * 6 + k]); p = i; }
-        if (!(mx > 0.0)) return -1;
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[p * 6 + j]; A[p * 6 + j] = t; }
-            const double t = b[k]; b[k] = b[p]; b[p] = t;
-        }
-        for (int i = k + 1; i < 6; ++i) {
-            const double f = A[i * 6 + k] / A[k * 6 + k];
-            for (int j = k; j < 6; ++j) A[i * 6 + j] -= f * A[k * 6 + j];
-            b[i] -= f * b[k];
-        }
-    }
-    for (int i = 5; i >= 0; --i) {
-        double s = b[i];
-        for (int j = i + 1; j < 6; ++j) s -= A[i * 6 + j] * x[j];
-        x[i] = s / A[i * 6 + i];
-    }
-    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return -1;
-    return 0;
-}
-
 // One-sided Jacobi SVD of a 3x3 (row-major), singular values descending, A = U diag(S) V^T.
 __device__ void svd3_dev(const double* A, double* U, double* S, double* V) {
     double W[9];
@@ -100,10 +59,6 @@ __device__ void svd3_dev(const double* A, double* U, double* S, double* V) {
         const double u0[3] = {U[0], U[3], U[6]}, u1[3] = {U[1], U[4], U[7]};
         U[2] = u0[1] * u1[2] - u0[2] * u1[1]; U[5] = u0[2] * u1[0] - u0[0] * u1[2]; U[8] = u0[0] * u1[1] - u0[1] * u1[0];
     }
-}
-
-__device__ __forceinline__ void mat4_identity_dev(float* M) {
-    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.f : 0.f;
 }
 
 // ---------------------------------------------------------------------------- finishers: summed row -> increment
@@ -196,23 +151,6 @@ __device__ int finish_p2p(const double* row, float* inc) {
     return 0;
 }
 
-// estimatedPose = increment * estimatedPose (ICPOptimizer.h:614-620); history as handed to
-// ConvergenceMeasure::recordAlignmentError (:629-631).
-__device__ void apply_increment(DevState* st, const float* inc, int rc, float* history) {
-    if (st->status == 0) {
-        if (rc != 0) st->status = rc;
-        else {
-            float np[16];
-            mat4_mul_pinned(inc, st->pose, np);
-            for (int i = 0; i < 16; ++i) st->pose[i] = np[i];
-            inv_transpose3_pinned(st->pose, st->nrm);
-            if (history) for (int i = 0; i < 16; ++i) history[16 * st->iters_done + i] = np[i];
-            st->iters_done += 1;
-        }
-    }
-    st->iter += 1;
-}
-
 __device__ void finish_row(DevState* st, const double* row, int mode, float* history) {
     float inc[16]; int rc;
     if (mode == 0) rc = finish_p2p(row, inc);
@@ -237,7 +175,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     __shared__ float P[16];
     __shared__ float mS[3], mD[3], Nm[9];
     __shared__ double red[ICP_REDUCE_THREADS / 32][32];
-    __shared__ double fin[8][32];
+    __shared__ double fin[ICP_REDUCE_THREADS / 32][32];
     __shared__ bool is_last;
     if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
@@ -331,43 +269,10 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
             v[27] += 1.0;
         }
     }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    warp_reduce_scatter32(v, lane);
-    red[wid][lane] = v[0];
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < ICP_REDUCE_THREADS / 32; ++w) s += red[w][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * ICP_NRED + threadIdx.x] = s;
-        __threadfence();
-    }
-    __syncthreads();
+    if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last)) return;
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&a.state->ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    {
-        const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-        double s = 0.0;
-        for (int b = g; b < (int)gridDim.x; b += ICP_REDUCE_THREADS / 32) s += __ldcg(&a.partials[(size_t)b * ICP_NRED + c]);
-        fin[g][c] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double s = 0.0;
-#pragma unroll
-        for (int g = 0; g < ICP_REDUCE_THREADS / 32; ++g) s += fin[g][threadIdx.x];
-        fin[0][threadIdx.x] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        a.state->ticket = 0;
-        if (MODE == 3) finish_sums(a.state, fin[0]);
-        else if (!a.solve) { for (int k = 0; k < ICP_NRED; ++k) a.state->shard_partials[k] = fin[0][k]; }
+        if (!a.solve) { for (int k = 0; k < ICP_NRED; ++k) a.state->shard_partials[k] = fin[0][k]; }
+        else if (MODE == 3) finish_sums(a.state, fin[0]);
         else finish_row(a.state, fin[0], MODE, a.pose_history);
     }
 }
@@ -389,6 +294,15 @@ cudaError_t icp_launch_reduce(const ReduceArgs& a, int max_queries, int n_blocks
         reduce_kernel<2><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches;
     }
     if (n_launches) *n_launches += launches;
+    return cudaGetLastError();
+}
+
+cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase, cudaStream_t s, int* n_launches) {
+    if (a.metric == ICP_GPU_METRIC_P2P) reduce_kernel<0><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+    else if (a.metric == ICP_GPU_METRIC_P2PLANE) reduce_kernel<1><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+    else if (phase == 0) reduce_kernel<3><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+    else reduce_kernel<2><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+    if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
 

@@ -1,0 +1,372 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the icp_gpu_* C
+ABI, against the CPU oracle on the same inputs.
+
+Protocol:
+  (i)  teacher-forced: at every pose of the oracle's trajectory the device matcher must return the
+       oracle's correspondence indices BIT-EXACTLY and the same weights;
+  (ii) free-running: the pose after the fixed iteration count must agree with the oracle's within
+       ROT_TOL rad / TRANS_TOL m (north_star: 1e-5 / 1e-5).
+"""
+import numpy as np
+import pytest
+
+from icp_variants_b200 import capi, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-5     # rad
+TRANS_TOL = 1e-5   # m
+
+
+def rot_angle(pa, pb):
+    # ||Ra - Rb||_F = 2*sqrt(2)*sin(theta/2): well conditioned at small angles, unlike acos((tr-1)/2),
+    # which turns the 1e-7 non-orthonormality of an fp32 rotation into a 3e-4 rad "angle"
+    d = np.linalg.norm(pa[:3, :3].astype(np.float64) - pb[:3, :3].astype(np.float64))
+    return float(2.0 * np.arcsin(min(d / (2.0 * np.sqrt(2.0)), 1.0)))
+
+
+def pose_close(pa, pb, rot_tol=ROT_TOL, trans_tol=TRANS_TOL):
+    return rot_angle(pa, pb) <= rot_tol and float(np.linalg.norm(pa[:3, 3].astype(np.float64) - pb[:3, 3])) <= trans_tol
+
+
+def gpu_config(ocfg: orc.Config, **kw) -> capi.Config:
+    c = capi.default_config()
+    c.metric, c.minimizer, c.matching, c.selection = ocfg.metric, ocfg.minimizer, ocfg.matching, ocfg.selection
+    c.proba, c.seed, c.weighting, c.rejection = ocfg.proba, ocfg.seed, ocfg.weighting, ocfg.rejection
+    c.max_distance_sq, c.color_icp, c.multires = ocfg.max_distance_sq, int(ocfg.color_icp), int(ocfg.multires)
+    c.n_iterations, c.lm_max_iterations = ocfg.n_iterations, ocfg.lm_max_iterations
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def load(ctx, src, tgt):
+    ctx.set_target(tgt.points, tgt.normals, tgt.colors)
+    ctx.set_source(src.points, src.normals, src.colors)
+
+
+def assert_matches_equal(idx, w, om, what=""):
+    assert np.array_equal(idx, om["idx"]), f"{what}: {np.count_nonzero(idx != om['idx'])} of {len(idx)} correspondence indices differ"
+    assert np.array_equal(w, om["weight"]), f"{what}: max weight diff {np.nanmax(np.abs(w - om['weight']))}"
+
+
+# ----------------------------------------------------------------------------- (i) teacher-forced
+@pytest.mark.parametrize("nn", [1, 2], ids=["brute", "grid"])
+@pytest.mark.parametrize("weighting", [0, 1, 2, 3])
+@pytest.mark.parametrize("rejection", [1, 0])
+def test_bunny_teacher_forced(ctx, bunny, nn, weighting, rejection):
+    src, tgt, _, _ = bunny
+    ocfg = orc.Config(metric=1, weighting=weighting, rejection=rejection, max_distance_sq=0.0003, n_iterations=8)
+    rc, _, hist, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, nn_algorithm=nn))
+    tree = orc.KdTree(tgt.points)
+    poses = [np.eye(4, dtype=np.float32)] + list(hist)
+    for k, pose in enumerate(poses):
+        om = orc.match_pipeline(ocfg, pose, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors, tree=tree)
+        idx, w = ctx.query_matches(pose)
+        assert_matches_equal(idx, w, om, f"iteration {k}")
+    assert (om["idx"] >= 0).sum() > 500
+
+
+@pytest.mark.parametrize("max_d2", [0.1, 10.0])
+def test_eth_teacher_forced_grid(ctx, small_eth_pair, max_d2):
+    src, tgt, _ = small_eth_pair
+    ocfg = orc.Config(metric=1, max_distance_sq=max_d2, n_iterations=6)
+    rc, _, hist, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, nn_algorithm=2))
+    tree = orc.KdTree(tgt.points)
+    for k, pose in enumerate([np.eye(4, dtype=np.float32)] + list(hist)):
+        om = orc.match_pipeline(ocfg, pose, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors, tree=tree)
+        idx, w = ctx.query_matches(pose)
+        assert_matches_equal(idx, w, om, f"iteration {k}")
+    st = ctx.stats()
+    assert st.n_queries == len(src) and st.n_distance_evals > 0
+
+
+def test_grid_equals_brute_on_ties_and_nonfinite(ctx):
+    """Quantised coordinates (many exact ties), duplicated target points, non-finite targets and
+    queries: lowest original index must win, non-finite points never match."""
+    rng = np.random.default_rng(7)
+    tgt = (rng.integers(0, 12, size=(6000, 3)) * 0.25).astype(np.float32)
+    tgt[100:200] = tgt[0:100]                      # duplicates with higher indices
+    tgt[300] = [np.inf, 0, 0]
+    tgt[301] = [np.nan, 1, 1]
+    tgt[302] = [-np.inf, -np.inf, -np.inf]
+    qry = (rng.integers(-2, 14, size=(4000, 3)) * 0.25 + 0.125 * rng.integers(0, 2, size=(4000, 3))).astype(np.float32)
+    qry[5] = [np.nan, 0, 0]
+    qry[6] = [-np.inf, -np.inf, -np.inf]
+    zeros_t, zeros_q = np.zeros_like(tgt), np.zeros_like(qry)
+    ref = orc.knn_brute(tgt, qry, 1.0)
+    for nn in (1, 2):
+        c = capi.default_config()
+        c.nn_algorithm, c.max_distance_sq, c.rejection = nn, 1.0, 0
+        ctx.set_config(c)
+        ctx.set_target(tgt, zeros_t, None)
+        ctx.set_source(qry, zeros_q, None)
+        idx, w = ctx.query_matches(np.eye(4, dtype=np.float32))
+        assert_matches_equal(idx, w, ref, f"nn={nn}")
+    assert ref["idx"][5] == -1 and ref["idx"][6] == -1
+
+
+def test_color_icp_6d_teacher_forced(ctx):
+    src, tgt, _ = synth.eth_pair(seed=4321, n_sweeps=40, n_beams=120, colors="texture")
+    ocfg = orc.Config(metric=2, weighting=3, color_icp=True, max_distance_sq=0.1, n_iterations=3)
+    rc, _, hist, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    tree = orc.KdTree(tgt.points, tgt.colors)
+    for nn in (1, 2):
+        ctx.set_config(gpu_config(ocfg, nn_algorithm=nn))
+        for k, pose in enumerate([np.eye(4, dtype=np.float32)] + list(hist)):
+            om = orc.match_pipeline(ocfg, pose, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors, tree=tree)
+            idx, w = ctx.query_matches(pose)
+            assert_matches_equal(idx, w, om, f"nn={nn} iteration {k}")
+
+
+@pytest.fixture(scope="module")
+def small_tum():
+    return synth.tum_pair(seed=1234, frame_gap=10, width=160, height=120)
+
+
+@pytest.mark.parametrize("weighting", [0, 2])
+def test_projective_teacher_forced(ctx, small_tum, weighting):
+    src, tgt, k, _ = small_tum
+    ocfg = orc.Config(metric=2, matching=1, weighting=weighting, max_distance_sq=0.1, n_iterations=4,
+                      fx=float(k[0, 0]), fy=float(k[1, 1]), cx=float(k[0, 2]), cy=float(k[1, 2]), width=160, height=120)
+    rc, _, hist, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_camera(k, 160, 120)
+    ctx.set_config(gpu_config(ocfg))
+    for it, pose in enumerate([np.eye(4, dtype=np.float32)] + list(hist)):
+        om = orc.match_pipeline(ocfg, pose, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+        idx, w = ctx.query_matches(pose)
+        assert_matches_equal(idx, w, om, f"iteration {it}")
+    assert (om["idx"] > 0).sum() > 1000
+
+
+def test_selection_subset_query(ctx, bunny):
+    src, tgt, _, _ = bunny
+    ocfg = orc.Config(metric=0, max_distance_sq=0.0003)
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg))
+    sel = np.arange(3, len(src), 7, dtype=np.int32)
+    om = orc.match_pipeline(ocfg, np.eye(4, dtype=np.float32), src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors,
+                            sel_idx=sel)
+    idx, w = ctx.query_matches(np.eye(4, dtype=np.float32), sel)
+    assert_matches_equal(idx, w, om)
+
+
+# ----------------------------------------------------------------------------- (ii) free-running
+VARIANTS = [(mini, metric) for mini in (0, 1) for metric in (0, 1, 2)]
+
+
+@pytest.mark.parametrize("minimizer,metric", VARIANTS)
+@pytest.mark.parametrize("use_graph", [1, 0])
+def test_bunny_free_running(ctx, bunny, minimizer, metric, use_graph):
+    src, tgt, gs, gt = bunny
+    ocfg = orc.Config(metric=metric, minimizer=minimizer, max_distance_sq=0.0003, n_iterations=20)
+    rc, opose, ohist, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, use_graph=use_graph))
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == 20 and len(hist) == 20
+    assert ctx.stats().n_queries == nq
+    for k in range(20):
+        assert pose_close(hist[k], ohist[k]), f"iteration {k}: rot {rot_angle(hist[k], ohist[k]):.2e} trans {np.linalg.norm(hist[k][:3, 3] - ohist[k][:3, 3]):.2e}"
+    assert pose_close(pose, opose)
+    assert np.array_equal(pose, hist[-1])
+    # running it again replays the cached graph and must give the same bits
+    pose2, _, _ = ctx.estimate_pose()
+    assert np.array_equal(pose, pose2)
+
+
+@pytest.mark.parametrize("minimizer,metric", VARIANTS)
+def test_eth_free_running(ctx, small_eth_pair, minimizer, metric):
+    src, tgt, _ = small_eth_pair
+    ocfg = orc.Config(metric=metric, minimizer=minimizer, max_distance_sq=0.1, n_iterations=10)
+    rc, opose, ohist, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg))
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == 10
+    assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
+
+
+@pytest.mark.parametrize("weighting", [1, 2])
+def test_bunny_weighted_free_running(ctx, bunny, weighting):
+    src, tgt, _, _ = bunny
+    ocfg = orc.Config(metric=1, weighting=weighting, max_distance_sq=0.0003, n_iterations=20)
+    rc, opose, _, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg))
+    pose, _, _ = ctx.estimate_pose()
+    assert pose_close(pose, opose)
+
+
+@pytest.mark.parametrize("minimizer,metric", [(0, 1), (0, 2), (1, 2)])
+def test_bunny_multires(ctx, bunny, minimizer, metric):
+    """Stride pyramid (PointCloud.h:325-343, ICPOptimizer.h:503-525,634-655): 1054 points -> strides 8,4,2,1."""
+    src, tgt, _, _ = bunny
+    ocfg = orc.Config(metric=metric, minimizer=minimizer, multires=True, max_distance_sq=0.0003, n_iterations=20)
+    rc, opose, ohist, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg))
+    assert ctx.max_iterations() == 20
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == len(ohist)
+    assert ctx.stats().n_queries == nq
+    assert pose_close(pose, opose)
+
+
+def test_multires_more_levels_than_iterations(ctx, small_eth_pair):
+    src, tgt, _ = small_eth_pair
+    ocfg = orc.Config(metric=1, multires=True, max_distance_sq=0.1, n_iterations=3)
+    rc, opose, ohist, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0 and len(ohist) > 3
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg))
+    assert ctx.max_iterations() == len(ohist)
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == len(ohist) and ctx.stats().n_queries == nq
+    assert pose_close(pose, opose)
+
+
+@pytest.mark.parametrize("multires", [False, True])
+def test_random_selection_mt19937(ctx, bunny, multires):
+    """selection.h:88-104 with an explicit seed: the host draws the reference's mt19937 stream."""
+    src, tgt, _, _ = bunny
+    ocfg = orc.Config(metric=1, selection=1, proba=0.5, seed=42, multires=multires, max_distance_sq=0.0003, n_iterations=12)
+    rc, opose, ohist, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg))
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == len(ohist) and ctx.stats().n_queries == nq
+    assert pose_close(pose, opose)
+
+
+def test_random_selection_device_stream(ctx, bunny):
+    """The device selection stream is not reference-compatible; it must select ~p of the points and converge."""
+    src, tgt, gs, gt = bunny
+    c = capi.default_config()
+    c.metric, c.selection, c.proba, c.seed, c.selection_rng, c.n_iterations = 2, 1, 0.5, 3, 1, 20
+    load(ctx, src, tgt)
+    ctx.set_config(c)
+    pose, _, n_it = ctx.estimate_pose()
+    frac = ctx.stats().n_queries / (20 * len(src))
+    assert 0.45 < frac < 0.55
+    assert orc.rmse(pose, src.points[gs], tgt.points[gt]) < 1e-3
+
+
+def test_projective_free_running(ctx, small_tum):
+    src, tgt, k, gt = small_tum
+    ocfg = orc.Config(metric=2, matching=1, weighting=2, max_distance_sq=0.1, n_iterations=10,
+                      fx=float(k[0, 0]), fy=float(k[1, 1]), cx=float(k[0, 2]), cy=float(k[1, 2]), width=160, height=120)
+    rc, opose, _, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_camera(k, 160, 120)
+    ctx.set_config(gpu_config(ocfg))
+    pose, _, n_it = ctx.estimate_pose()
+    assert n_it == 10
+    assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
+
+
+def test_bunny_known_answer(ctx, bunny):
+    """bunny_part2_trans maps onto bunny_part1 by Rz(12.2348 deg), t=(-0.0151362,-0.0032822,0)."""
+    src, tgt, gs, gt = bunny
+    c = capi.default_config()
+    c.metric, c.n_iterations = 2, 20
+    load(ctx, src, tgt)
+    ctx.set_config(c)
+    pose, _, _ = ctx.estimate_pose()
+    assert abs(np.degrees(np.arctan2(pose[1, 0], pose[0, 0])) - 12.2348) < 0.1
+    assert np.allclose(pose[:3, 3], [-0.0151362, -0.0032822, 0.0], atol=3e-4)
+    assert orc.rmse(pose, src.points[gs], tgt.points[gt]) < 4e-4
+
+
+# ----------------------------------------------------------------------------- error behaviour
+def test_error_codes(bunny):
+    src, tgt, _, _ = bunny
+    with capi.Context(0) as c:
+        with pytest.raises(capi.IcpGpuError) as e:
+            c.estimate_pose()
+        assert e.value.code == capi.E_STATE
+        c.set_target(tgt.points, tgt.normals, tgt.colors)
+        far = src.points + np.float32(100.0)
+        c.set_source(far, src.normals, src.colors)
+        with pytest.raises(capi.IcpGpuError) as e:      # the reference hangs in ASSERT (Eigen.h:9)
+            c.estimate_pose()
+        assert e.value.code == capi.E_NO_MATCHES
+        assert np.array_equal(e.value.pose, np.eye(4, dtype=np.float32))
+        cfg = capi.default_config()
+        cfg.matching = 1
+        c.set_config(cfg)
+        with pytest.raises(capi.IcpGpuError) as e:      # projective without camera
+            c.estimate_pose()
+        assert e.value.code == capi.E_STATE
+        cfg.metric = 7
+        with pytest.raises(capi.IcpGpuError) as e:
+            c.set_config(cfg)
+        assert e.value.code == capi.E_ARG
+
+
+def test_empty_clouds(ctx, bunny):
+    src, tgt, _, _ = bunny
+    c = capi.default_config()
+    ctx.set_config(c)
+    ctx.set_target(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), None)
+    ctx.set_source(src.points, src.normals, src.colors)
+    idx, w = ctx.query_matches(np.eye(4, dtype=np.float32))
+    assert (idx == -1).all() and (w == 0).all()
+    ctx.set_target(tgt.points, tgt.normals, tgt.colors)
+    ctx.set_source(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), None)
+    idx, w = ctx.query_matches(np.eye(4, dtype=np.float32))
+    assert len(idx) == 0
+    with pytest.raises(capi.IcpGpuError) as e:
+        ctx.estimate_pose()
+    assert e.value.code == capi.E_NO_MATCHES
+
+
+# ----------------------------------------------------------------------------- point-sharded iteration (one GPU, two contexts)
+@pytest.mark.parametrize("metric", [0, 1, 2])
+def test_point_sharded_equals_single(bunny, metric):
+    """Two contexts each hold the whole target and half of the source; summing their partial rows and
+    applying the sum on both must reproduce the single-context trajectory."""
+    src, tgt, _, _ = bunny
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations = metric, 5
+    with capi.Context(0) as full, capi.Context(0) as a, capi.Context(0) as b:
+        full.set_config(cfg); a.set_config(cfg); b.set_config(cfg)
+        full.set_target(tgt.points, tgt.normals, tgt.colors)
+        full.set_source(src.points, src.normals, src.colors)
+        ref_pose, _, _ = full.estimate_pose()
+        h = len(src) // 2
+        for c, sl in ((a, slice(0, h)), (b, slice(h, None))):
+            c.set_target(tgt.points, tgt.normals, tgt.colors)
+            c.set_source(src.points[sl], src.normals[sl], src.colors[sl])
+        eye = np.eye(4, dtype=np.float32)
+        a.iteration_begin(eye); b.iteration_begin(eye)
+        for _ in range(5):
+            for ph in range(a.iteration_phases()):
+                tot = a.iteration_local(ph) + b.iteration_local(ph)
+                a.iteration_apply(ph, tot); b.iteration_apply(ph, tot)
+        pa, pb = a.iteration_end(), b.iteration_end()
+        assert np.array_equal(pa, pb)
+        assert pose_close(pa, ref_pose, 1e-6, 1e-6)
