@@ -188,6 +188,7 @@ def main():
     cfg.metric, cfg.minimizer, cfg.matching, cfg.n_iterations = 1, 0, 0, N_ITER
     cfg.max_distance_sq = args.max_dist2
     cfg.nn_algorithm = 2
+    cfg.collect_stats = 0                                     # work counters cost device atomics: off while timing
     ctx.set_config(cfg)
 
     # device-resident raw clouds (reference layouts: packed float[3N], uint8[4N])
@@ -247,14 +248,21 @@ def main():
     total_ms, launches, pose = timed(step_resident, args.steps, args.warmup)
     e2e_ms, _, pose_e2e = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    st = ctx.stats()
+    launches_per_step = launches // (args.steps * world)
 
     # per-kernel timing of the dominant kernel: one extra registration, launch by launch with CUDA events
     ctx.set_target_dev(d["tp"].data_ptr(), d["tn"].data_ptr(), d["tc"].data_ptr(), nt)
     ctx.set_source_dev(d["sp"].data_ptr(), d["sn"].data_ptr(), d["sc"].data_ptr(), ns)
     for _ in range(2):
         _, _, _, tm = ctx.estimate_pose(want_history=False, timings=True)
+    # work counters (distance evaluations, staged points, deferred queries): one more, instrumented, registration
+    cfg.collect_stats = 1
+    ctx.set_config(cfg)
+    ctx.set_target_dev(d["tp"].data_ptr(), d["tn"].data_ptr(), d["tc"].data_ptr(), nt)
+    ctx.set_source_dev(d["sp"].data_ptr(), d["sn"].data_ptr(), d["sc"].data_ptr(), ns)
+    ctx.estimate_pose(want_history=False)
     st_t = ctx.stats()
+    st = st_t
     match_ms = tm.matching_ms / N_ITER
     solve_ms = tm.solver_ms / N_ITER
 
@@ -279,13 +287,15 @@ def main():
             "e2e": {"value": regs / (e2e_ms * 1e-3), "unit": "reg/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int((ns + nt) * 28 + 64 + 32 * N_ITER), "d2h_bytes_per_step": int(64 + 16 * 4 * N_ITER + 1024)},
             "gpu_launches": launches,
-            "roofline": {"kernel": "knn_grid_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "knn_tile_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": match_ms,
                          "note": "latency/issue-bound tree search, clouds are L2-resident; see roofline_fp32"},
-            "roofline_fp32": {"kernel": "knn_grid_kernel<false>", "distance_evals_per_launch": evals_per_launch,
+            "roofline_fp32": {"kernel": "knn_tile_kernel<false>", "distance_evals_per_launch": evals_per_launch,
                               "gevals_per_s": evals_per_launch / (match_ms * 1e-3) / 1e9, "flop_per_eval": 8,
-                              "tflops": evals_per_launch * 8 / (match_ms * 1e-3) / 1e12, "nodes_per_launch": st_t.n_nodes_visited / N_ITER},
+                              "tflops": evals_per_launch * 8 / (match_ms * 1e-3) / 1e12, "nodes_per_launch": st_t.n_nodes_visited / N_ITER,
+                              "deferred_queries_per_launch": st_t.n_deferred / N_ITER, "block_staged_points_per_launch": st_t.n_points_staged / N_ITER,
+                              "tiles": st_t.n_tiles, "matched_per_launch": st_t.n_matched / N_ITER},
             "stage_ms_per_iteration": {"match": match_ms, "reduce_solve": solve_ms, "index_build": tm.index_ms},
             "clocks": clocks,
             "pose_checksum": float(np.abs(pose).sum()),

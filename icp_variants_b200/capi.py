@@ -35,7 +35,7 @@ class Config(C.Structure):
                 ("proba", C.c_double), ("seed", C.c_uint32), ("selection_rng", C.c_int32), ("weighting", C.c_int32),
                 ("rejection", C.c_int32), ("max_distance_sq", C.c_float), ("color_icp", C.c_int32), ("multires", C.c_int32),
                 ("pyramid_mode", C.c_int32), ("n_iterations", C.c_int32), ("lm_max_iterations", C.c_int32),
-                ("nn_algorithm", C.c_int32), ("use_graph", C.c_int32)]
+                ("nn_algorithm", C.c_int32), ("use_graph", C.c_int32), ("collect_stats", C.c_int32)]
 
 
 class Timings(C.Structure):
@@ -46,7 +46,8 @@ class Timings(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_queries", C.c_uint64), ("n_matched", C.c_uint64), ("n_distance_evals", C.c_uint64),
-                ("n_nodes_visited", C.c_uint64), ("n_kernel_launches", C.c_uint64)]
+                ("n_nodes_visited", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("n_points_staged", C.c_uint64),
+                ("n_deferred", C.c_uint64), ("n_tiles", C.c_uint64)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

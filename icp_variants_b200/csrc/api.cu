@@ -18,8 +18,7 @@
 #include <vector>
 
 #define DESC_QUERY (ICP_MAX_ITERS)       // descriptor slot used by icp_gpu_query_matches
-#define DESC_SHARD (ICP_MAX_ITERS + 1)   // descriptor slot used by the point-sharded iteration API
-#define DESC_TOTAL (ICP_MAX_ITERS + 2)
+#define DESC_TOTAL (ICP_MAX_ITERS + 1)
 
 namespace {
 
@@ -59,9 +58,8 @@ struct DeviceBuf {
 
 struct Plan {
     int n_iters = 0;
-    std::vector<IterDesc> desc;       // n_iters entries
-    std::vector<int> grid_queries;    // launch-size bound per iteration (independent of the random draw)
-    std::vector<int> sel;             // concatenated selection index lists (mt19937 mode)
+    std::vector<IterDesc> desc;         // n_iters entries
+    std::vector<uint32_t> mask;         // concatenated selection masks, one bit per original source index (mt19937 mode)
 };
 
 }  // namespace
@@ -72,15 +70,21 @@ struct icp_gpu_ctx {
     icp_gpu_config cfg;
     float K[9]; uint32_t width = 0, height = 0; bool have_camera = false;
     // clouds
-    DeviceBuf stage, src_pts, src_nrm, tgt_pts, tgt_nrm, tgt_pts_sorted, tgt_nrm_sorted;
+    DeviceBuf stage, src_raw_pts, src_raw_nrm, src_pts, src_nrm, tgt_pts, tgt_nrm, tgt_pts_sorted, tgt_nrm_sorted;
     int n_src = -1, n_tgt = -1;
-    std::vector<uint8_t> src_finite;   // host copy of "point and normal finite" per source point
+    std::vector<uint8_t> src_finite;   // host copy of "point and normal finite" per ORIGINAL source index
     bool src_finite_valid = false;
-    // grid
+    std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
+    bool src_rank_valid = false;
+    // target grid
     DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
+    // source grid (only its sort order and tiles are used) and tiles
+    DeviceBuf sgrid, scell_start, tiles, n_tiles_dev, order_dev;
+    int Ts = 0, n_tiles = 0;
+    unsigned int* h_n_tiles = nullptr;   // pinned
     // loop state
-    DeviceBuf state, desc, sel, match_pos, match_w, match_idx, partials, pose_dev, history;
+    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, deferred, partials, pose_dev, history;
     float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
     IterDesc* h_desc = nullptr;                                                       // pinned, DESC_TOTAL
     int n_reduce_blocks = 1;
@@ -91,7 +95,7 @@ struct icp_gpu_ctx {
     // async call state
     bool pending = false; int pending_iters = 0;
     // shard iteration state
-    bool shard_open = false; int shard_algo = 0;
+    bool shard_open = false; int shard_algo = 0, shard_iters = 0;
     icp_gpu_stats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     char err[512];
@@ -132,7 +136,7 @@ int bind(icp_gpu_ctx* ctx) {
 int pick_T(int n) {
     // ~2-4 points per occupied cell for surface-like clouds: cells = 4..8 x points
     int T = 3;
-    while (T < 24 && (1ll << T) < 4ll * (long long)(n > 0 ? n : 1)) ++T;
+    while (T < 24 && (1ll << T) < 8ll * (long long)(n > 0 ? n : 1)) ++T;
     if (T > 3 * ICP_MAX_BITS_PER_AXIS) T = 3 * ICP_MAX_BITS_PER_AXIS;
     return T;
 }
@@ -141,6 +145,7 @@ int choose_algorithm(const icp_gpu_ctx* c) {   // 0 grid, 1 brute, 2 projective
     if (c->cfg.matching == ICP_GPU_MATCH_PROJECTIVE) return 2;
     if (c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE) return 1;
     if (c->cfg.nn_algorithm == ICP_GPU_NN_GRID) return 0;
+    if (c->cfg.nn_algorithm == ICP_GPU_NN_TREE) return 3;
     return c->n_tgt <= 2048 ? 1 : 0;
 }
 
@@ -184,10 +189,32 @@ int build_grid(icp_gpu_ctx* ctx) {
     CU(icp_launch_grid_build((const float4*)ctx->tgt_pts.p, (const float4*)ctx->tgt_nrm.p, n, ctx->T, (GridParams*)ctx->grid.p,
                              (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
                              (unsigned int*)ctx->cell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->tgt_pts_sorted.p,
-                             (float4*)ctx->tgt_nrm_sorted.p, ctx->stream, &launches));
+                             (float4*)ctx->tgt_nrm_sorted.p, 0, ctx->stream, &launches));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     ctx->grid_built = true;
+    return 0;
+}
+
+// Sorts the source into the cell order of its own grid and cuts it into spatially compact tiles.
+int build_source(icp_gpu_ctx* ctx) {
+    const int n = ctx->n_src;
+    ctx->Ts = pick_T(n);
+    const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->Ts) + 1;
+    if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4)) ||
+        ensure(ctx, ctx->keys, n1 * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->scell_start, cells1 * 4) ||
+        ensure(ctx, ctx->block_sums, (cells1 / 4096 + 2) * 4) || ensure(ctx, ctx->sgrid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64) ||
+        ensure(ctx, ctx->tiles, n1 * sizeof(int2)) || ensure(ctx, ctx->n_tiles_dev, 64))
+        return ICP_GPU_E_CUDA;
+    int launches = 0;
+    CU(icp_launch_grid_build((const float4*)ctx->src_raw_pts.p, (const float4*)ctx->src_raw_nrm.p, n, ctx->Ts, (GridParams*)ctx->sgrid.p,
+                             (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
+                             (unsigned int*)ctx->scell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->src_pts.p,
+                             (float4*)ctx->src_nrm.p, 1, ctx->stream, &launches));
+    CU(icp_launch_make_tiles((const unsigned int*)ctx->scell_start.p, ctx->Ts, n, (int2*)ctx->tiles.p, (unsigned int*)ctx->n_tiles_dev.p,
+                             ctx->stream, &launches));
+    CU(cudaMemcpyAsync(ctx->h_n_tiles, ctx->n_tiles_dev.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
     return 0;
 }
 
@@ -202,9 +229,9 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
         // buildIndex: the grid is always built (cheap), the matcher choice is made per call
         if (build_grid(ctx)) return ICP_GPU_E_CUDA;
     } else {
-        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->src_pts, ctx->src_nrm)) return ICP_GPU_E_CUDA;
+        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->src_raw_pts, ctx->src_raw_nrm)) return ICP_GPU_E_CUDA;
         ctx->n_src = (int)n;
-        ctx->src_finite_valid = false;
+        ctx->src_finite_valid = false; ctx->src_rank_valid = false;
         if (!dev) {
             ctx->src_finite.resize((size_t)n);
             for (int64_t i = 0; i < n; ++i) {
@@ -215,14 +242,40 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
             ctx->src_finite_valid = true;
         }
         const size_t n1 = (size_t)(n > 0 ? n : 1);
-        if (ensure(ctx, ctx->match_pos, n1 * 4) || ensure(ctx, ctx->match_w, n1 * 4) || ensure(ctx, ctx->match_idx, n1 * 4)) return ICP_GPU_E_CUDA;
+        if (ensure(ctx, ctx->match_pos, n1 * 4) || ensure(ctx, ctx->match_w, n1 * 4) || ensure(ctx, ctx->match_idx, n1 * 4) ||
+            ensure(ctx, ctx->nn_pos, n1 * 4)) return ICP_GPU_E_CUDA;
         ctx->n_reduce_blocks = icp_reduce_blocks((int)n, ctx->n_sms);
         if (ensure(ctx, ctx->partials, (size_t)ctx->n_reduce_blocks * ICP_NRED * sizeof(double))) return ICP_GPU_E_CUDA;
+        if (build_source(ctx)) return ICP_GPU_E_CUDA;
     }
-    // Host arrays are only borrowed for the duration of the call, so wait for the copies; the
-    // device-pointer form stays asynchronous (stream-ordered with everything that follows).
-    if (!dev) CU(cudaStreamSynchronize(ctx->stream));
+    // a new cloud invalidates the neighbours remembered from earlier searches
+    if (ctx->n_src > 0 && ctx->nn_pos.p) { CU(icp_launch_fill_int((int*)ctx->nn_pos.p, ctx->n_src, -1, ctx->stream)); ctx->stats.n_kernel_launches += 1; }
+    // Host arrays are only borrowed for the duration of the call, and the tile count is needed to size
+    // launches: wait.  (The target's device-pointer form stays asynchronous.)
+    if (!dev || !target) CU(cudaStreamSynchronize(ctx->stream));
+    if (!target) {
+        ctx->n_tiles = (int)*ctx->h_n_tiles;
+        if (ensure(ctx, ctx->deferred, ((size_t)(n > 0 ? n : 1) + 32 * (size_t)ctx->n_tiles) * 4)) return ICP_GPU_E_CUDA;
+    }
     return ICP_GPU_OK;
+}
+
+// original index -> sorted position (host copy), fetched lazily: only the host-drawn selection
+// masks and the query_matches output order need it
+int fetch_src_rank(icp_gpu_ctx* ctx) {
+    if (ctx->src_rank_valid) return 0;
+    const size_t n = (size_t)ctx->n_src;
+    std::vector<int> order(n);
+    if (n > 0) {
+        if (ensure(ctx, ctx->order_dev, n * 4)) return ICP_GPU_E_CUDA;
+        CU(icp_launch_extract_order((const float4*)ctx->src_pts.p, (int)n, (int*)ctx->order_dev.p, ctx->stream));
+        CU(cudaMemcpyAsync(order.data(), ctx->order_dev.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->src_rank.assign(n, 0);
+    for (size_t p = 0; p < n; ++p) ctx->src_rank[(size_t)order[p]] = (int)p;
+    ctx->src_rank_valid = true;
+    return 0;
 }
 
 // "point and normal finite" flags of a device-resident source, fetched lazily (mt19937 + multires only)
@@ -230,8 +283,8 @@ int fetch_src_finite(icp_gpu_ctx* ctx) {
     if (ctx->src_finite_valid) return 0;
     const size_t n = (size_t)ctx->n_src;
     std::vector<float4> p(n), m(n);
-    CU(cudaMemcpyAsync(p.data(), ctx->src_pts.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(m.data(), ctx->src_nrm.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(p.data(), ctx->src_raw_pts.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(m.data(), ctx->src_raw_nrm.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->src_finite.resize(n);
     for (size_t i = 0; i < n; ++i)
@@ -247,6 +300,7 @@ int make_plan(icp_gpu_ctx* ctx, Plan& plan) {
     const bool host_rng = cfg.selection == ICP_GPU_SELECT_RANDOM && cfg.selection_rng == ICP_GPU_RNG_MT19937;
     const bool dev_rng = cfg.selection == ICP_GPU_SELECT_RANDOM && cfg.selection_rng == ICP_GPU_RNG_DEVICE;
     if (host_rng && cfg.multires && fetch_src_finite(ctx)) return ICP_GPU_E_CUDA;
+    const size_t mask_words = ((size_t)(n > 0 ? n : 1) + 31) / 32;
     int stride = cfg.multires ? coarsest_stride(n) : 1;
     Mt19937 rng; uint32_t n_selections = 0;
     if (host_rng) rng.seed(cfg.seed + n_selections++);      // PointSelection ctor -> initSampler
@@ -254,21 +308,19 @@ int make_plan(icp_gpu_ctx* ctx, Plan& plan) {
     for (int i = 0; i < cfg.n_iterations || cfg.multires; ++i) {
         if (plan.n_iters >= ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "more than %d iterations", ICP_MAX_ITERS);
         IterDesc d; memset(&d, 0, sizeof(d));
-        const int level_slots = (int)(((long long)n + stride - 1) / stride);
-        d.stride = stride; d.sel_offset = -1; d.filter_finite = cfg.multires ? 1 : 0; d.proba = -1.0f; d.n_queries = level_slots;
+        d.stride = stride; d.mask_word_offset = -1; d.filter_finite = cfg.multires ? 1 : 0; d.proba = -1.0f;
         if (dev_rng) { d.proba = (float)cfg.proba; d.rng_key = cfg.seed * 2654435761u + (uint32_t)(i + 1) * 0x9E3779B9u; }
         if (host_rng) {
             // resample(): one draw per point of the current level's cloud, in order (selection.h:88-104)
-            d.sel_offset = (int)plan.sel.size();
-            int c = 0;
+            d.mask_word_offset = (int)plan.mask.size();
+            plan.mask.resize(plan.mask.size() + mask_words, 0u);
+            uint32_t* m = plan.mask.data() + d.mask_word_offset;
             for (long long k = 0; k < n; k += stride) {
                 if (cfg.multires && !ctx->src_finite[(size_t)k]) continue;      // not part of the level cloud (PointCloud.h:335)
-                if (rng.canonical() < cfg.proba) { plan.sel.push_back((int)k); ++c; }
+                if (rng.canonical() < cfg.proba) m[k >> 5] |= 1u << (k & 31);
             }
-            d.n_queries = c; d.stride = 1; d.filter_finite = 0;
         }
         plan.desc.push_back(d);
-        plan.grid_queries.push_back(level_slots);
         plan.n_iters += 1;
         if (cfg.multires) {
             if (stride == 1 && i >= cfg.n_iterations - 1) break;
@@ -294,50 +346,51 @@ int check_ready(icp_gpu_ctx* ctx) {
 
 void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, bool want_idx) {
     memset(&a, 0, sizeof(a));
+    const bool grid_order = (algo == 0 || algo == 3);
     a.src_pts = (const float4*)c->src_pts.p; a.src_nrm = (const float4*)c->src_nrm.p; a.n_src = c->n_src;
-    a.sel = (const int*)c->sel.p; a.desc = (const IterDesc*)c->desc.p;
+    a.tiles = (const int2*)c->tiles.p; a.n_tiles = c->n_tiles;
+    a.mask = (const unsigned int*)c->mask.p; a.desc = (const IterDesc*)c->desc.p;
     a.state_ro = (const DevState*)c->state.p; a.state = (DevState*)c->state.p;
     a.grid = (const GridParams*)c->grid.p; a.cell_start = (const unsigned int*)c->cell_start.p;
-    a.tgt_pts = (const float4*)(algo == 0 ? c->tgt_pts_sorted.p : c->tgt_pts.p);
-    a.tgt_nrm = (const float4*)(algo == 0 ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
+    a.tgt_pts = (const float4*)(grid_order ? c->tgt_pts_sorted.p : c->tgt_pts.p);
+    a.tgt_nrm = (const float4*)(grid_order ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
     a.n_tgt = c->n_tgt;
     if (c->have_camera) { a.fx = c->K[0]; a.fy = c->K[4]; a.cx = c->K[6]; a.cy = c->K[7]; }   // column-major Matrix3f
     a.width = c->width; a.height = c->height;
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
     a.max_d2 = c->cfg.max_distance_sq;
     a.match_pos = (int*)c->match_pos.p; a.match_w = (float*)c->match_w.p; a.match_idx = want_idx ? (int*)c->match_idx.p : nullptr;
+    a.nn_pos = (int*)c->nn_pos.p; a.deferred = (int*)c->deferred.p;
     a.desc_index = desc_index;
+    a.use_seed = grid_order ? 1 : 0;
+    a.collect_stats = c->cfg.collect_stats;
 }
 
-void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int desc_index, int solve) {
+void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     memset(&r, 0, sizeof(r));
+    const bool grid_order = (algo == 0 || algo == 3);
     r.src_pts = (const float4*)c->src_pts.p; r.src_nrm = (const float4*)c->src_nrm.p; r.n_src = c->n_src;
-    r.sel = (const int*)c->sel.p; r.desc = (const IterDesc*)c->desc.p; r.state = (DevState*)c->state.p;
-    r.tgt_pts = (const float4*)(algo == 0 ? c->tgt_pts_sorted.p : c->tgt_pts.p);
-    r.tgt_nrm = (const float4*)(algo == 0 ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
+    r.state = (DevState*)c->state.p;
+    r.tgt_pts = (const float4*)(grid_order ? c->tgt_pts_sorted.p : c->tgt_pts.p);
+    r.tgt_nrm = (const float4*)(grid_order ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
     r.match_pos = (const int*)c->match_pos.p; r.match_w = (const float*)c->match_w.p;
     r.partials = (double*)c->partials.p; r.pose_history = (float*)c->history.p;
-    r.metric = c->cfg.metric; r.desc_index = desc_index; r.solve = solve;
-}
-
-int blocks_for(const icp_gpu_ctx* c, int queries) {
-    int nb = icp_reduce_blocks(queries, c->n_sms);
-    return nb < c->n_reduce_blocks ? nb : c->n_reduce_blocks;
+    r.metric = c->cfg.metric; r.solve = solve;
 }
 
 // Enqueue the whole loop.  ev_marks (nullable): events recorded around each stage for the timings report.
 int enqueue_iterations(icp_gpu_ctx* ctx, const Plan& plan, int algo, std::vector<cudaEvent_t>* ev_marks) {
     MatchArgs ma; ReduceArgs ra;
     fill_match_args(ctx, ma, algo, -1, false);
-    fill_reduce_args(ctx, ra, algo, -1, 1);
+    fill_reduce_args(ctx, ra, algo, 1);
     int launches = 0;
+    const int nb = ctx->n_reduce_blocks;
     for (int i = 0; i < plan.n_iters; ++i) {
-        const int q = plan.grid_queries[i];
         if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * i], ctx->stream));
-        CU(icp_launch_match(ma, algo, q, ctx->stream)); if (q > 0) ++launches;
+        CU(icp_launch_match(ma, algo, ctx->n_sms, ctx->stream, &launches));
         if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * i + 1], ctx->stream));
-        if (ctx->cfg.minimizer == ICP_GPU_MIN_LM) CU(icp_launch_lm(ra, q, blocks_for(ctx, q), ctx->cfg.lm_max_iterations, ctx->stream, &launches));
-        else CU(icp_launch_reduce(ra, q, blocks_for(ctx, q), ctx->stream, &launches));
+        if (ctx->cfg.minimizer == ICP_GPU_MIN_LM) CU(icp_launch_lm(ra, nb, ctx->cfg.lm_max_iterations, ctx->stream, &launches));
+        else CU(icp_launch_reduce(ra, nb, ctx->stream, &launches));
     }
     if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * plan.n_iters], ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
@@ -356,10 +409,10 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     // descriptors + selection lists + pose up (pinned staging, stream-ordered)
     memcpy(ctx->h_desc, plan.desc.data(), sizeof(IterDesc) * (size_t)plan.n_iters);
     if (plan.n_iters > 0) CU(cudaMemcpyAsync(ctx->desc.p, ctx->h_desc, sizeof(IterDesc) * (size_t)plan.n_iters, cudaMemcpyHostToDevice, ctx->stream));
-    if (!plan.sel.empty()) {
-        if (ensure(ctx, ctx->sel, plan.sel.size() * sizeof(int))) return ICP_GPU_E_CUDA;
-        CU(cudaMemcpyAsync(ctx->sel.p, plan.sel.data(), plan.sel.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));   // plan.sel is pageable and dies with this frame
+    if (!plan.mask.empty()) {
+        if (ensure(ctx, ctx->mask, plan.mask.size() * sizeof(uint32_t))) return ICP_GPU_E_CUDA;
+        CU(cudaMemcpyAsync(ctx->mask.p, plan.mask.data(), plan.mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // plan.mask is pageable and dies with this frame
     }
     memcpy(ctx->h_pose, pose_in, 16 * sizeof(float));
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -376,12 +429,12 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         // The graph depends only on launch shapes and pointers, not on descriptor contents.
         std::vector<long long> key;
         key.push_back(algo); key.push_back(ctx->cfg.metric); key.push_back(ctx->cfg.minimizer); key.push_back(ctx->cfg.lm_max_iterations);
-        key.push_back(ctx->cfg.weighting); key.push_back(ctx->cfg.rejection); key.push_back(ctx->cfg.color_icp);
+        key.push_back(ctx->cfg.weighting); key.push_back(ctx->cfg.rejection); key.push_back(ctx->cfg.color_icp); key.push_back(ctx->cfg.collect_stats);
         key.push_back((long long)__float_as_int_host(ctx->cfg.max_distance_sq));
         key.push_back(ctx->n_src); key.push_back(ctx->n_tgt); key.push_back(ctx->T); key.push_back(ctx->width); key.push_back(ctx->height);
         for (int k = 0; k < 9; ++k) key.push_back((long long)__float_as_int_host(ctx->have_camera ? ctx->K[k] : 0.f));
-        key.push_back((long long)(uintptr_t)ctx->sel.p); key.push_back((long long)(uintptr_t)ctx->stream);
-        for (int q : plan.grid_queries) key.push_back(q);
+        key.push_back((long long)(uintptr_t)ctx->mask.p); key.push_back((long long)(uintptr_t)ctx->stream);
+        key.push_back(ctx->n_tiles); key.push_back(plan.n_iters);
         if (!ctx->graph_exec || key != ctx->graph_key) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -421,11 +474,19 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         float idx_ms = 0.f;
         if (ctx->grid_built && cudaEventElapsedTime(&idx_ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->index_ms = idx_ms; else cudaGetLastError();
         timings->total_ms = tot; timings->index_ms = ctx->index_ms; timings->n_iterations = plan.n_iters;
-        timings->n_match_launches = plan.n_iters;
-        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters;
+        const int per_match = algo == 0 ? 2 : 1;
+        timings->n_match_launches = plan.n_iters * per_match;
+        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters * per_match;
         for (auto& e : marks) cudaEventDestroy(e);
     }
     return ICP_GPU_OK;
+}
+
+void copy_counters(icp_gpu_ctx* ctx) {
+    const DevState& st = *ctx->h_state;
+    ctx->stats.n_queries = st.n_queries; ctx->stats.n_matched = st.n_matched;
+    ctx->stats.n_distance_evals = st.n_evals; ctx->stats.n_nodes_visited = st.n_nodes;
+    ctx->stats.n_points_staged = st.n_staged; ctx->stats.n_deferred = st.n_deferred_total; ctx->stats.n_tiles = (uint64_t)ctx->n_tiles;
 }
 
 int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out) {
@@ -438,8 +499,7 @@ int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_histor
     if (pose_out) memcpy(pose_out, st.pose, 16 * sizeof(float));
     if (pose_history && st.iters_done > 0) memcpy(pose_history, ctx->h_history, sizeof(float) * 16 * (size_t)st.iters_done);
     if (n_iterations_out) *n_iterations_out = st.iters_done;
-    ctx->stats.n_queries = st.n_queries; ctx->stats.n_matched = st.n_matched;
-    ctx->stats.n_distance_evals = st.n_evals; ctx->stats.n_nodes_visited = st.n_nodes;
+    copy_counters(ctx);
     if (st.status == ICP_GPU_E_NO_MATCHES)
         return fail(ctx, ICP_GPU_E_NO_MATCHES, "iteration %d had no surviving correspondence (the reference hangs in ASSERT here)", st.iters_done);
     if (st.status != 0) return fail(ctx, st.status, "iteration %d: singular / non-finite normal equations", st.iters_done);
@@ -466,7 +526,7 @@ void icp_gpu_default_config(icp_gpu_config* cfg) {
     cfg->selection = ICP_GPU_SELECT_ALL; cfg->proba = 1.0; cfg->seed = 0; cfg->selection_rng = ICP_GPU_RNG_MT19937;
     cfg->weighting = ICP_GPU_WEIGHT_CONSTANT; cfg->rejection = 1; cfg->max_distance_sq = 0.0003f;
     cfg->color_icp = 0; cfg->multires = 0; cfg->pyramid_mode = ICP_GPU_PYRAMID_STRIDE; cfg->n_iterations = 20;
-    cfg->lm_max_iterations = 10; cfg->nn_algorithm = ICP_GPU_NN_AUTO; cfg->use_graph = 1;
+    cfg->lm_max_iterations = 10; cfg->nn_algorithm = ICP_GPU_NN_AUTO; cfg->use_graph = 1; cfg->collect_stats = 1;
 }
 
 int icp_gpu_create(icp_gpu_ctx** out, int device) {
@@ -491,9 +551,10 @@ int icp_gpu_create(icp_gpu_ctx** out, int device) {
     ok = ok && cudaMallocHost((void**)&ctx->h_history, 16 * sizeof(float) * ICP_MAX_ITERS) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_state, sizeof(DevState)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_desc, sizeof(IterDesc) * DESC_TOTAL) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_n_tiles, 64) == cudaSuccess;
     ok = ok && ensure(ctx, ctx->state, sizeof(DevState)) == 0 && ensure(ctx, ctx->desc, sizeof(IterDesc) * DESC_TOTAL) == 0 &&
          ensure(ctx, ctx->pose_dev, 64) == 0 && ensure(ctx, ctx->history, 16 * sizeof(float) * ICP_MAX_ITERS) == 0 &&
-         ensure(ctx, ctx->sel, 256) == 0;
+         ensure(ctx, ctx->mask, 256) == 0;
     if (ok) ok = cudaMemsetAsync(ctx->state.p, 0, sizeof(DevState), ctx->stream) == cudaSuccess && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     if (!ok) { cudaGetLastError(); icp_gpu_destroy(ctx); return ICP_GPU_E_CUDA; }
     *out = ctx;
@@ -506,13 +567,16 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     DeviceBuf* bufs[] = {&ctx->stage, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
-                         &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->sel,
-                         &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history};
+                         &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
+                         &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
+                         &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->tiles, &ctx->n_tiles_dev, &ctx->order_dev,
+                         &ctx->nn_pos, &ctx->deferred};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    if (ctx->h_n_tiles) cudaFreeHost(ctx->h_n_tiles);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -545,7 +609,7 @@ int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
     if (c->selection < 0 || c->selection > 1) return fail(ctx, ICP_GPU_E_ARG, "selection %d", c->selection);
     if (c->selection_rng < 0 || c->selection_rng > 1) return fail(ctx, ICP_GPU_E_ARG, "selection_rng %d", c->selection_rng);
     if (c->weighting < 0 || c->weighting > 3) return fail(ctx, ICP_GPU_E_ARG, "weighting %d", c->weighting);
-    if (c->nn_algorithm < 0 || c->nn_algorithm > 2) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
+    if (c->nn_algorithm < 0 || c->nn_algorithm > 3) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
     if (c->pyramid_mode != ICP_GPU_PYRAMID_STRIDE) return fail(ctx, ICP_GPU_E_ARG, "pyramid_mode %d", c->pyramid_mode);
     if (c->n_iterations < 0 || c->n_iterations > ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "n_iterations %d (max %d)", c->n_iterations, ICP_MAX_ITERS);
     if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);
@@ -577,15 +641,23 @@ int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t*
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
-    const int nq = sel_idx ? (int)n_sel : ctx->n_src;
-    if (sel_idx && (n_sel < 0 || n_sel > ctx->n_src)) return fail(ctx, ICP_GPU_E_ARG, "n_sel %lld", (long long)n_sel);
+    const int n = ctx->n_src;
+    const int nq = sel_idx ? (int)n_sel : n;
+    if (sel_idx && (n_sel < 0 || n_sel > n)) return fail(ctx, ICP_GPU_E_ARG, "n_sel %lld", (long long)n_sel);
     memset(&ctx->stats, 0, sizeof(ctx->stats));
+    if (fetch_src_rank(ctx)) return ICP_GPU_E_CUDA;
     IterDesc d; memset(&d, 0, sizeof(d));
-    d.n_queries = nq; d.stride = 1; d.sel_offset = sel_idx ? 0 : -1; d.filter_finite = 0; d.proba = -1.0f;
-    if (sel_idx && nq > 0) {
-        for (int64_t k = 0; k < n_sel; ++k) if (sel_idx[k] < 0 || sel_idx[k] >= ctx->n_src) return fail(ctx, ICP_GPU_E_ARG, "sel_idx[%lld] out of range", (long long)k);
-        if (ensure(ctx, ctx->sel, (size_t)nq * sizeof(int))) return ICP_GPU_E_CUDA;
-        CU(cudaMemcpyAsync(ctx->sel.p, sel_idx, (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    d.stride = 1; d.mask_word_offset = -1; d.filter_finite = 0; d.proba = -1.0f;
+    std::vector<uint32_t> mask;
+    if (sel_idx) {
+        mask.assign(((size_t)(n > 0 ? n : 1) + 31) / 32, 0u);
+        for (int64_t k = 0; k < n_sel; ++k) {
+            if (sel_idx[k] < 0 || sel_idx[k] >= n) return fail(ctx, ICP_GPU_E_ARG, "sel_idx[%lld] out of range", (long long)k);
+            mask[(size_t)sel_idx[k] >> 5] |= 1u << (sel_idx[k] & 31);
+        }
+        if (ensure(ctx, ctx->mask, mask.size() * 4)) return ICP_GPU_E_CUDA;
+        CU(cudaMemcpyAsync(ctx->mask.p, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d.mask_word_offset = 0;
     }
     ctx->h_desc[DESC_QUERY] = d;
     CU(cudaMemcpyAsync((IterDesc*)ctx->desc.p + DESC_QUERY, &ctx->h_desc[DESC_QUERY], sizeof(IterDesc), cudaMemcpyHostToDevice, ctx->stream));
@@ -594,16 +666,22 @@ int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t*
     CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
     const int algo = choose_algorithm(ctx);
     MatchArgs ma; fill_match_args(ctx, ma, algo, DESC_QUERY, true);
-    CU(icp_launch_match(ma, algo, nq, ctx->stream));
-    ctx->stats.n_kernel_launches += 2;
-    if (nq > 0) {
-        CU(cudaMemcpyAsync(idx_out, ctx->match_idx.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(weight_out, ctx->match_w.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int launches = 1;
+    CU(icp_launch_match(ma, algo, ctx->n_sms, ctx->stream, &launches));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    std::vector<int> idx_s((size_t)n); std::vector<float> w_s((size_t)n);
+    if (n > 0) {
+        CU(cudaMemcpyAsync(idx_s.data(), ctx->match_idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(w_s.data(), ctx->match_w.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.n_queries = ctx->h_state->n_queries; ctx->stats.n_matched = ctx->h_state->n_matched;
-    ctx->stats.n_distance_evals = ctx->h_state->n_evals; ctx->stats.n_nodes_visited = ctx->h_state->n_nodes;
+    // device results are in sorted-source order; the caller gets its own order back
+    for (int k = 0; k < nq; ++k) {
+        const int p = ctx->src_rank[(size_t)(sel_idx ? sel_idx[k] : k)];
+        idx_out[k] = idx_s[(size_t)p]; weight_out[k] = w_s[(size_t)p];
+    }
+    copy_counters(ctx);
     return ICP_GPU_OK;
 }
 
@@ -652,13 +730,13 @@ int icp_gpu_iteration_begin(icp_gpu_ctx* ctx, const float pose_in[16]) {
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
     IterDesc d; memset(&d, 0, sizeof(d));
-    d.n_queries = ctx->n_src; d.stride = 1; d.sel_offset = -1; d.filter_finite = 0; d.proba = -1.0f;
-    ctx->h_desc[DESC_SHARD] = d;
-    CU(cudaMemcpyAsync((IterDesc*)ctx->desc.p + DESC_SHARD, &ctx->h_desc[DESC_SHARD], sizeof(IterDesc), cudaMemcpyHostToDevice, ctx->stream));
+    d.stride = 1; d.mask_word_offset = -1; d.filter_finite = 0; d.proba = -1.0f;
+    for (int i = 0; i < ICP_MAX_ITERS; ++i) ctx->h_desc[i] = d;      // every iteration of the shard loop: all points
+    CU(cudaMemcpyAsync(ctx->desc.p, ctx->h_desc, sizeof(IterDesc) * ICP_MAX_ITERS, cudaMemcpyHostToDevice, ctx->stream));
     memcpy(ctx->h_pose, pose_in, 16 * sizeof(float));
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
-    ctx->shard_open = true; ctx->shard_algo = choose_algorithm(ctx);
+    ctx->shard_open = true; ctx->shard_algo = choose_algorithm(ctx); ctx->shard_iters = 0;
     return ICP_GPU_OK;
 }
 
@@ -670,11 +748,13 @@ int icp_gpu_iteration_local_dev(icp_gpu_ctx* ctx, int phase, double** partials_d
     const int algo = ctx->shard_algo;
     int launches = 0;
     if (phase == 0) {
-        MatchArgs ma; fill_match_args(ctx, ma, algo, DESC_SHARD, false);
-        CU(icp_launch_match(ma, algo, ctx->n_src, ctx->stream)); ++launches;
+        if (ctx->shard_iters >= ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "more than %d iterations since icp_gpu_iteration_begin", ICP_MAX_ITERS);
+        ctx->shard_iters += 1;
+        MatchArgs ma; fill_match_args(ctx, ma, algo, -1, false);
+        CU(icp_launch_match(ma, algo, ctx->n_sms, ctx->stream, &launches));
     }
-    ReduceArgs ra; fill_reduce_args(ctx, ra, algo, DESC_SHARD, 0);
-    CU(icp_launch_reduce_phase(ra, blocks_for(ctx, ctx->n_src), phase, ctx->stream, &launches));
+    ReduceArgs ra; fill_reduce_args(ctx, ra, algo, 0);
+    CU(icp_launch_reduce_phase(ra, ctx->n_reduce_blocks, phase, ctx->stream, &launches));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     *partials_dev = ((DevState*)ctx->state.p)->shard_partials;
     *n_values = shard_values(ctx->cfg.metric, phase);

@@ -17,11 +17,10 @@ __global__ void pack_cloud_kernel(const float* __restrict__ xyz, const float* __
                                   int n, float4* __restrict__ pts, float4* __restrict__ nrmo) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // Layout in HBM: points {x,y,z,aux}, normals {nx,ny,nz,aux}; the source keeps rgba in pts.w, the
-    // target keeps rgba in nrm.w (its pts.w becomes the original index after sorting).
+    // Layout in HBM: points {x,y,z,original index bits}, normals {nx,ny,nz,rgba bits}.
     unsigned int c = 0;
     if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
-    float4 p; p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2]; p.w = __uint_as_float(c);
+    float4 p; p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2]; p.w = __int_as_float(i);
     float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
     if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
     pts[i] = p; nrmo[i] = m;
@@ -194,25 +193,97 @@ __global__ void scan_apply_kernel(unsigned int* __restrict__ data, int n, const 
 // ---------------------------------------------------------------------------- scatter into cell order
 __global__ void scatter_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n,
                                const unsigned int* __restrict__ keys, const unsigned int* __restrict__ ranks,
-                               const unsigned int* __restrict__ cell_start, float4* __restrict__ pts_sorted,
+                               const unsigned int* __restrict__ cell_start, unsigned int n_cells, int keep_nonfinite,
+                               unsigned int* __restrict__ nonfinite_counter, float4* __restrict__ pts_sorted,
                                float4* __restrict__ nrm_sorted) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned int k = keys[i];
-    if (k == 0xFFFFFFFFu) return;
-    const unsigned int pos = cell_start[k] + ranks[i];
-    float4 p = pts[i]; p.w = __int_as_float(i);     // keep the original index: tie-break + API output
-    pts_sorted[pos] = p;
+    unsigned int pos;
+    if (k == 0xFFFFFFFFu) {
+        if (!keep_nonfinite) return;
+        pos = cell_start[n_cells] + atomicAdd(nonfinite_counter, 1u);   // after the last cell; never part of any search
+    } else {
+        pos = cell_start[k] + ranks[i];
+    }
+    pts_sorted[pos] = pts[i];                        // .w already holds the original index: tie-break + API output
     nrm_sorted[pos] = nrm[i];
+}
+
+// ---------------------------------------------------------------------------- source tiles
+// A tile is a node of the implicit tree with <= ICP_TILE points whose parent has more (or a chunk of an
+// over-full finest cell): a run of the sorted source that lies in ONE axis-aligned box of the source grid,
+// so the transformed queries of a tile stay spatially compact under any rigid pose.
+__global__ void make_tiles_kernel(const unsigned int* __restrict__ cs, int T, int n, int2* __restrict__ tiles,
+                                  unsigned int* __restrict__ n_tiles) {
+    const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n_nodes = (2ull << T) - 1ull;
+    if (id < n_nodes) {
+        const int d = 63 - __clzll((long long)(id + 1ull));
+        const unsigned int p = (unsigned int)(id + 1ull - (1ull << d));
+        const int sh = T - d;
+        const unsigned int s = cs[(size_t)p << sh], e = cs[((size_t)p + 1) << sh];
+        const unsigned int cnt = e - s;
+        if (cnt == 0u) return;
+        bool parent_big = true;
+        if (d > 0) { const unsigned int pp = p >> 1; parent_big = cs[((size_t)pp + 1) << (sh + 1)] - cs[(size_t)pp << (sh + 1)] > (unsigned int)ICP_TILE; }
+        if (!parent_big) return;
+        if (cnt <= (unsigned int)ICP_TILE) {
+            tiles[atomicAdd(n_tiles, 1u)] = make_int2((int)s, (int)cnt);
+        } else if (d == T) {
+            const unsigned int chunks = (cnt + ICP_TILE - 1) / ICP_TILE;
+            const unsigned int base = atomicAdd(n_tiles, chunks);
+            for (unsigned int c = 0; c < chunks; ++c)
+                tiles[base + c] = make_int2((int)(s + c * ICP_TILE), (int)min((unsigned int)ICP_TILE, cnt - c * ICP_TILE));
+        }
+    } else if (id == n_nodes) {
+        // the non-finite bucket after the last cell: never queries, but every point needs its outputs written
+        const unsigned int s = cs[(size_t)1 << T];
+        if ((unsigned int)n > s) {
+            const unsigned int cnt = (unsigned int)n - s, chunks = (cnt + ICP_TILE - 1) / ICP_TILE;
+            const unsigned int base = atomicAdd(n_tiles, chunks);
+            for (unsigned int c = 0; c < chunks; ++c)
+                tiles[base + c] = make_int2((int)(s + c * ICP_TILE), (int)min((unsigned int)ICP_TILE, cnt - c * ICP_TILE));
+        }
+    }
+}
+
+cudaError_t icp_launch_make_tiles(const unsigned int* cell_start, int T, int n, int2* tiles, unsigned int* n_tiles_dev, cudaStream_t s,
+                                  int* n_launches) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(n_tiles_dev, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+    const unsigned long long threads = (2ull << T);
+    make_tiles_kernel<<<(unsigned int)((threads + 255) / 256), 256, 0, s>>>(cell_start, T, n, tiles, n_tiles_dev);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+__global__ void extract_order_kernel(const float4* __restrict__ pts_sorted, int n, int* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[i] = __float_as_int(pts_sorted[i].w);
+}
+cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s) {
+    if (n > 0) extract_order_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_sorted, n, order);
+    return cudaGetLastError();
+}
+
+__global__ void fill_int_kernel(int* __restrict__ p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
+    if (n > 0) fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
+    return cudaGetLastError();
 }
 
 cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid,
                                   unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
-                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, cudaStream_t s, int* n_launches) {
+                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
+                                  cudaStream_t s, int* n_launches) {
     cudaError_t e;
     const int n_cells1 = (1 << T) + 1;
     if ((e = cudaMemsetAsync(bbox_scratch, 0xFF, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(bbox_scratch + 3, 0x00, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bbox_scratch + 3, 0x00, 5 * sizeof(unsigned int), s)) != cudaSuccess) return e;   // max[3], spare, non-finite counter
     if ((e = cudaMemsetAsync(cell_start, 0, sizeof(unsigned int) * (size_t)n_cells1, s)) != cudaSuccess) return e;
     int launches = 0;
     if (n > 0) {
@@ -225,7 +296,11 @@ cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, in
     scan_tile_sums_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(cell_start, n_cells1, block_sums); ++launches;
     scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(block_sums, n_tiles); ++launches;
     scan_apply_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(cell_start, n_cells1, block_sums); ++launches;
-    if (n > 0) { scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_in, nrm_in, n, keys, ranks, cell_start, pts_sorted, nrm_sorted); ++launches; }
+    if (n > 0) {
+        scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_in, nrm_in, n, keys, ranks, cell_start, 1u << T, keep_nonfinite, bbox_scratch + 7,
+                                                       pts_sorted, nrm_sorted);
+        ++launches;
+    }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }

@@ -19,6 +19,7 @@
 #define ICP_NRED 32                // doubles per partial-sum row (27..30 used)
 #define ICP_REDUCE_THREADS 256
 #define ICP_MATCH_THREADS 128
+#define ICP_TILE 128                // queries per tile = threads per block of the tiled search
 #define ICP_LEAF_MAX 8             // a grid node with <= this many points is scanned, not split
 #define ICP_MAX_BITS_PER_AXIS 10   // keeps the cell-index rounding error << the bound margin
 
@@ -41,14 +42,19 @@ struct GridParams {
     int pad;
 };
 
+// One ICP iteration's query set.  Queries are addressed by p = position in the Morton-sorted source
+// (grid.cu); the sorted source keeps the original index in pts.w.  Query p is active iff
+//   orig % stride == 0                           (PointCloud.h:325-343 level stride; 1 = all)
+//   and (filter_finite == 0 or point and normal finite)          (PointCloud.h:335)
+//   and (mask_word_offset < 0 or bit `orig` of the mask is set)  (selection.h:88-104, drawn on the host)
+//   and (proba < 0 or hash(rng_key, orig) < proba)               (device selection stream)
 struct IterDesc {
-    int n_queries;     // threads that own a query slot this iteration
-    int stride;        // source index = slot * stride when sel_offset < 0
-    int sel_offset;    // offset into the selection index array, or -1
-    int filter_finite; // 1: a slot whose point or normal is non-finite is not a query (PointCloud.h:335)
-    unsigned int rng_key; // device selection stream key (ICP_GPU_RNG_DEVICE)
-    float proba;       // device selection probability, <0 = off
-    int pad0, pad1;
+    int stride;
+    int filter_finite;
+    int mask_word_offset;   // offset (32-bit words) into the selection mask array, or -1
+    unsigned int rng_key;
+    float proba;
+    int pad0, pad1, pad2;
 };
 
 // Device-resident loop state; one per context.
@@ -63,26 +69,30 @@ struct DevState {
     float mean_s[3];     // unweighted means of the kept matches (symmetric metric), rounded to fp32
     float mean_d[3];
     double mean_s64[3], mean_d64[3];
-    unsigned long long n_queries, n_matched, n_evals, n_nodes;
+    unsigned long long n_queries, n_matched, n_evals, n_nodes, n_staged, n_deferred_total;
     // Levenberg-Marquardt state (lm.cu)
     double lm_x[6], lm_cand[6], lm_cost, lm_H[36], lm_g[6], lm_scale[6], lm_diag[6];
     double lm_radius, lm_decrease, lm_model_change;
     int lm_iter, lm_done, lm_reuse_diag, lm_invalid, lm_step_ok, lm_have_cand;
     double shard_partials[ICP_NRED];
+    unsigned int n_deferred[ICP_MAX_ITERS + 2];   // per iteration: queries handed from the tile kernel to the tree kernel
 };
 
 struct MatchArgs {
-    const float4* src_pts;   // {x,y,z,rgba bits}
-    const float4* src_nrm;   // {nx,ny,nz,0}
+    // source, Morton-sorted (grid.cu): pts {x,y,z,orig idx bits}, nrm {nx,ny,nz,rgba bits}
+    const float4* src_pts;
+    const float4* src_nrm;
     int n_src;
-    const int* sel;          // selection indices (all iterations concatenated) or null
-    const IterDesc* desc;    // [ICP_MAX_ITERS]
+    const int2* tiles;       // [n_tiles] {first p, count <= ICP_TILE}: spatially compact runs of the sorted source
+    int n_tiles;
+    const unsigned int* mask; // selection masks (bit per original source index), all iterations concatenated
+    const IterDesc* desc;    // [ICP_MAX_ITERS + 2]
     const DevState* state_ro;
     DevState* state;
-    // target, grid order
+    // target
     const GridParams* grid;
     const unsigned int* cell_start;
-    const float4* tgt_pts;   // sorted {x,y,z,orig idx bits}; brute / projective: original order
+    const float4* tgt_pts;   // grid order {x,y,z,orig idx bits}; brute / projective: original order
     const float4* tgt_nrm;   // same order {nx,ny,nz,rgba bits}
     int n_tgt;
     // projective
@@ -90,38 +100,50 @@ struct MatchArgs {
     // config
     int weighting, rejection, color_icp;
     float max_d2;
-    // outputs (slot-indexed)
+    // per-query state, indexed by p
     int* match_pos;          // position in tgt_pts order, -1 = none
     float* match_w;
     int* match_idx;          // original target index (API output), may be null
+    int* nn_pos;             // nearest neighbour found the last time p was a query (-1 none): seeds the next search
+    int* deferred;           // [n_src + 32 * n_tiles] queries the tile kernel could not resolve, one warp-padded run per tile
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
+    int use_seed;
+    int collect_stats;       // work counters in DevState (atomics); off in timed runs
 };
 
 struct ReduceArgs {
     const float4* src_pts; const float4* src_nrm; int n_src;
-    const int* sel; const IterDesc* desc; DevState* state;
+    DevState* state;
     const float4* tgt_pts; const float4* tgt_nrm;
     const int* match_pos; const float* match_w;
     double* partials;        // [grid][ICP_NRED]
     float* pose_history;     // [ICP_MAX_ITERS][16] or null
-    int metric; int desc_index; int solve;   // solve=0: leave the summed row in state->shard_partials
+    int metric; int solve;   // solve=0: leave the summed row in state->shard_partials
 };
 
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
-struct TargetBuffers;
 cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
                                   cudaStream_t s);
+// Sorts a cloud into grid-cell (Morton) order and builds the dense cell table.  keep_nonfinite: points
+// with a non-finite coordinate are appended after the last cell (source clouds: every point needs a slot).
 cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid,
                                   unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
-                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, cudaStream_t s, int* n_launches);
-cudaError_t icp_launch_match(const MatchArgs& a, int algorithm /*0 grid,1 brute,2 projective*/, int max_queries, cudaStream_t s);
+                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
+                                  cudaStream_t s, int* n_launches);
+// Partition of the sorted source into spatially compact tiles (<= ICP_TILE points each).
+cudaError_t icp_launch_make_tiles(const unsigned int* cell_start, int T, int n, int2* tiles, unsigned int* n_tiles_dev, cudaStream_t s,
+                                  int* n_launches);
+cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
+cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
+// algorithm: 0 tiled grid search (+ tree kernel for deferred queries), 1 brute force, 2 projective, 3 tree search for every query
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
-cudaError_t icp_launch_reduce(const ReduceArgs& a, int max_queries, int n_blocks, cudaStream_t s, int* n_launches);
+cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);
 // one phase of the point-sharded iteration: the summed row is left in state->shard_partials
 cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase, cudaStream_t s, int* n_launches);
-int icp_reduce_blocks(int max_queries, int n_sms);
+int icp_reduce_blocks(int n_src, int n_sms);
 cudaError_t icp_launch_shard_apply(DevState* st, int mode, float* history, cudaStream_t s);
-cudaError_t icp_launch_lm(const ReduceArgs& a, int max_queries, int n_blocks, int lm_max_iterations, cudaStream_t s, int* n_launches);
+cudaError_t icp_launch_lm(const ReduceArgs& a, int n_blocks, int lm_max_iterations, cudaStream_t s, int* n_launches);
 
 // pinned 4x4 product, column-major: C = A * B  (ICPOptimizer.h:614-620)
 __device__ __forceinline__ void mat4_mul_pinned(const float* A, const float* B, float* C) {
@@ -162,12 +184,22 @@ __device__ __forceinline__ void xform_normal(const float* N, float x, float y, f
     oz = padd(padd(pmul(N[6], x), pmul(N[7], y)), pmul(N[8], z));
 }
 
-// Source index owned by query slot k in iteration descriptor d, or -1 when the slot is not a query.
-__device__ __forceinline__ int slot_source_index(const IterDesc& d, const int* sel, int k, int n_src) {
-    if (k >= d.n_queries) return -1;
-    if (d.sel_offset >= 0) return sel[d.sel_offset + k];
-    const long long i = (long long)k * d.stride;
-    return i < n_src ? (int)i : -1;
+__device__ __forceinline__ float unit_hash(unsigned int key, unsigned int k) {
+    // counter-based stream for ICP_GPU_RNG_DEVICE (two rounds of a 32-bit mix)
+    unsigned int x = k * 0x9E3779B9u + key;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    x += key * 0x85EBCA6Bu; x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+// Is the sorted-source point (p4 = point, n4 = normal) a query of the iteration described by d?
+__device__ __forceinline__ bool query_active(const IterDesc& d, const unsigned int* __restrict__ mask, const float4& p4, const float4& n4) {
+    const unsigned int orig = (unsigned int)__float_as_int(p4.w);
+    if (d.stride > 1 && (orig % (unsigned int)d.stride) != 0u) return false;
+    if (d.filter_finite && !(finite3(p4.x, p4.y, p4.z) && finite3(n4.x, n4.y, n4.z))) return false;
+    if (d.mask_word_offset >= 0 && !((__ldg(&mask[d.mask_word_offset + (orig >> 5)]) >> (orig & 31u)) & 1u)) return false;
+    if (d.proba >= 0.0f && !(unit_hash(d.rng_key, orig) < d.proba)) return false;
+    return true;
 }
 
 // ---------------------------------------------------------------------------- reductions

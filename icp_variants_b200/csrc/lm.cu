@@ -205,7 +205,6 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) lm_eval_kernel(const Reduc
     if (threadIdx.x >= 32 && threadIdx.x < 41) Nm[threadIdx.x - 32] = a.state->nrm[threadIdx.x - 32];
     if (threadIdx.x >= 64 && threadIdx.x < 70) xs[threadIdx.x - 64] = step_index == 0 ? 0.0 : a.state->lm_cand[threadIdx.x - 64];
     __syncthreads();
-    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state->iter];
     double v[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = 0.0;
@@ -214,16 +213,15 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) lm_eval_kernel(const Reduc
     Rotator rot; rotator_init(rot, pose);                     // PoseIncrement::apply, utils.h:44-56
     Rotator rinv;
     if (METRIC == ICP_GPU_METRIC_SYMMETRIC) { const Jet ninv[3] = {jneg(pose[0]), jneg(pose[1]), jneg(pose[2])}; rotator_init(rinv, ninv); }   // utils.h:60-72
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < d.n_queries; slot += gridDim.x * blockDim.x) {
-        const int pos = a.match_pos[slot];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += gridDim.x * blockDim.x) {
+        const int pos = a.match_pos[i];
         if (pos < 0) continue;
-        const int i = slot_source_index(d, a.sel, slot, a.n_src);
         const float4 sp = __ldg(&a.src_pts[i]);
         float sxf, syf, szf;
         xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
         const float4 tp = __ldg(&a.tgt_pts[pos]);
         if (!finite3(sxf, syf, szf) || !finite3(tp.x, tp.y, tp.z)) continue;        // ICPOptimizer.h:378
-        const double w = (double)a.match_w[slot];
+        const double w = (double)a.match_w[i];
         const double s[3] = {sxf, syf, szf}, t[3] = {tp.x, tp.y, tp.z};
         Jet y[3];
         rotate_const(rot, s, y);
@@ -257,8 +255,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) lm_eval_kernel(const Reduc
 
 }  // namespace
 
-cudaError_t icp_launch_lm(const ReduceArgs& a, int max_queries, int n_blocks, int lm_max_iterations, cudaStream_t s, int* n_launches) {
-    (void)max_queries;
+cudaError_t icp_launch_lm(const ReduceArgs& a, int n_blocks, int lm_max_iterations, cudaStream_t s, int* n_launches) {
     for (int step = 0; step <= lm_max_iterations; ++step) {
         if (a.metric == ICP_GPU_METRIC_P2P) lm_eval_kernel<0><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a, step, lm_max_iterations);
         else if (a.metric == ICP_GPU_METRIC_P2PLANE) lm_eval_kernel<1><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a, step, lm_max_iterations);

@@ -1,5 +1,5 @@
 // match.cu -- stages 1-4 of one ICP iteration fused into one kernel per matching method:
-//   selection slot -> source index            (selection.h:28-60, PointCloud.h:325-343)
+//   selection predicate on the sorted source   (selection.h:28-60,88-104, PointCloud.h:325-343)
 //   transformPoints / transformNormals        (utils.h:106-133)
 //   queryMatches: exact 1-NN (3-D / 6-D) or projective window search
 //                                             (NearestNeighbor.h:143-207, :234-303, :333-421)
@@ -8,10 +8,25 @@
 // The reference's FLANN search (1 randomized kd-tree, 16 checks) is approximate; these kernels return
 // the exact nearest neighbour under contract D1-D3 with ties to the lowest target index, i.e. what
 // NearestNeighborSearchBruteForce's scan order (NearestNeighbor.h:81-97) yields on squared distances.
+//
+// k-NN kernels:
+//   knn_tile_kernel   one block per source tile (<= 128 spatially compact queries).  Every query starts
+//                     from an upper bound (the neighbour it had the last time it was matched, else the
+//                     distance threshold); the block stages the target points of all grid cells that meet
+//                     the union of the queries' search balls in shared memory and every thread scans the
+//                     staged points (shared-memory broadcast reads, no divergence).  Queries whose ball
+//                     does not fit the tile's budget are handed to
+//   knn_tree_kernel   one thread per query: depth-first descent of the implicit tree over the cell table
+//                     with box-distance pruning (any bound, any distance; also usable for all queries).
+//   knn_brute_kernel  small targets: one warp per query, warp-shuffle arg-min.
 #include "icp_internal.cuh"
 #include <limits.h>
 
 #define MINF_F (-INFINITY)
+#define FLT_BIG 3.4028234e38f
+#define TILE_CHUNK 1024        // staged target points per round
+#define TILE_MAX_CELLS ICP_TILE // candidate cells per pass: one per thread
+#define TILE_BUDGET 12288      // target points in the candidate cells of one tile before its search radius is cut
 
 __device__ __forceinline__ int sel3i(int a, int x, int y, int z) { return a == 0 ? x : (a == 1 ? y : z); }
 __device__ __forceinline__ float sel3f(int a, float x, float y, float z) { return a == 0 ? x : (a == 1 ? y : z); }
@@ -31,15 +46,22 @@ __device__ __forceinline__ float color_feature(unsigned int rgba, int k) {
     return pmul(1.0f / 255.0f, (float)((rgba >> (8 * k)) & 0xFFu));
 }
 
+__device__ __forceinline__ float dist3(const Query& q, const float4 c) {
+    const float dx = psub(q.x, c.x), dy = psub(q.y, c.y), dz = psub(q.z, c.z);
+    return padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));               // D1
+}
+__device__ __forceinline__ float dist6_tail(const Query& q, float d, unsigned int rgba) {
+    const float dr = psub(q.cr, color_feature(rgba, 0)), dg = psub(q.cg, color_feature(rgba, 1)), db = psub(q.cb, color_feature(rgba, 2));
+    d = padd(d, pmul(dr, dr)); d = padd(d, pmul(dg, dg)); d = padd(d, pmul(db, db));   // FLANN L2 order for 6 dims
+    return d;
+}
+
 template <bool COLOR>
 __device__ __forceinline__ float dist2(const Query& q, const float4 c, float best, const float4* __restrict__ nrm, unsigned int i) {
-    const float dx = psub(q.x, c.x), dy = psub(q.y, c.y), dz = psub(q.z, c.z);
-    float d = padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));            // D1
+    float d = dist3(q, c);
     if (COLOR) {
         if (d > best) return d;                                                // 3-D part already loses; adding squares cannot help
-        const unsigned int rgba = __float_as_uint(__ldg(&nrm[i].w));
-        const float dr = psub(q.cr, color_feature(rgba, 0)), dg = psub(q.cg, color_feature(rgba, 1)), db = psub(q.cb, color_feature(rgba, 2));
-        d = padd(d, pmul(dr, dr)); d = padd(d, pmul(dg, dg)); d = padd(d, pmul(db, db));   // FLANN L2 order for 6 dims
+        d = dist6_tail(q, d, __float_as_uint(__ldg(&nrm[i].w)));
     }
     return d;
 }
@@ -70,7 +92,7 @@ __device__ __forceinline__ float gap2(const GridParams& g, int a, float q, int l
 // far child only if its box bound does not exceed the best distance so far ('>' keeps equal bounds
 // alive so that an equally distant point with a lower index is still found).
 template <bool COLOR>
-__device__ void grid_search(const GridParams& g, const unsigned int* __restrict__ cs, const float4* __restrict__ pts,
+__device__ void tree_search(const GridParams& g, const unsigned int* __restrict__ cs, const float4* __restrict__ pts,
                             const float4* __restrict__ nrm, const Query& q, Best& b, unsigned int& evals, unsigned int& nodes) {
     const int T = g.T;
     const unsigned int s0 = __ldg(&cs[0]), e0 = __ldg(&cs[1u << T]);
@@ -131,16 +153,8 @@ __device__ __forceinline__ void load_pose(PoseSm& sm, const DevState* st) {
     __syncthreads();
 }
 
-__device__ __forceinline__ float unit_hash(unsigned int key, unsigned int k) {
-    // counter-based stream for ICP_GPU_RNG_DEVICE (two rounds of a 32-bit mix)
-    unsigned int x = k * 0x9E3779B9u + key;
-    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-    x += key * 0x85EBCA6Bu; x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-    return (float)(x >> 8) * (1.0f / 16777216.0f);
-}
-
-// Stages 3-4 for one query given its match; writes the slot's outputs.
-__device__ __forceinline__ void finish_match(const MatchArgs& a, int slot, bool matched, float w_const, int t_idx, int t_pos,
+// Stages 3-4 for one query given its match; writes the query's outputs.
+__device__ __forceinline__ void finish_match(const MatchArgs& a, int p, bool matched, float w_const, int t_idx, int t_pos,
                                              float sx, float sy, float sz, float snx, float sny, float snz, unsigned int s_rgba,
                                              unsigned int& n_matched) {
     int out_idx = -1, out_pos = -1; float w = 0.0f;
@@ -183,12 +197,18 @@ __device__ __forceinline__ void finish_match(const MatchArgs& a, int slot, bool 
         }
         if (out_pos >= 0) ++n_matched;
     }
-    a.match_pos[slot] = out_pos;
-    a.match_w[slot] = w;
-    if (a.match_idx) a.match_idx[slot] = out_idx;
+    a.match_pos[p] = out_pos;
+    a.match_w[p] = w;
+    if (a.match_idx) a.match_idx[p] = out_idx;
 }
 
-__device__ __forceinline__ void flush_stats(DevState* st, unsigned int nq, unsigned int nm, unsigned int ev, unsigned int nd) {
+__device__ __forceinline__ void write_no_query(const MatchArgs& a, int p) {
+    a.match_pos[p] = -1; a.match_w[p] = 0.0f; if (a.match_idx) a.match_idx[p] = -1;
+}
+
+__device__ __forceinline__ void flush_stats(const MatchArgs& a, unsigned int nq, unsigned int nm, unsigned int ev, unsigned int nd) {
+    if (!a.collect_stats) return;     // ~10^5 same-address atomics per launch are not free: off in timed runs
+    DevState* st = a.state;
     nq = __reduce_add_sync(0xFFFFFFFFu, nq); nm = __reduce_add_sync(0xFFFFFFFFu, nm);
     // evals / nodes can exceed 32 bits only per launch, not per warp
     ev = __reduce_add_sync(0xFFFFFFFFu, ev); nd = __reduce_add_sync(0xFFFFFFFFu, nd);
@@ -200,44 +220,379 @@ __device__ __forceinline__ void flush_stats(DevState* st, unsigned int nq, unsig
     }
 }
 
-// Resolves the slot to a source point and transforms it. Returns false when the slot is not a query.
-__device__ __forceinline__ bool prepare_query(const MatchArgs& a, const IterDesc& d, const PoseSm& sm, int slot, Query& q,
+// Loads sorted-source point p, decides whether it is a query of this iteration and transforms it.
+__device__ __forceinline__ bool prepare_query(const MatchArgs& a, const IterDesc& d, const PoseSm& sm, int p, Query& q,
                                               float& snx, float& sny, float& snz, unsigned int& s_rgba) {
-    const int i = slot_source_index(d, a.sel, slot, a.n_src);
-    if (i < 0) return false;
-    const float4 p = __ldg(&a.src_pts[i]);
-    const float4 n = __ldg(&a.src_nrm[i]);
-    if (d.filter_finite && !(finite3(p.x, p.y, p.z) && finite3(n.x, n.y, n.z))) return false;   // PointCloud.h:335
-    if (d.proba >= 0.0f && !(unit_hash(d.rng_key, (unsigned int)slot) < d.proba)) return false;   // device selection stream
-    xform_point(sm.P, p.x, p.y, p.z, q.x, q.y, q.z);
-    xform_normal(sm.N, n.x, n.y, n.z, snx, sny, snz);
-    s_rgba = __float_as_uint(p.w);
+    const float4 p4 = __ldg(&a.src_pts[p]);
+    const float4 n4 = __ldg(&a.src_nrm[p]);
+    if (!query_active(d, a.mask, p4, n4)) return false;
+    xform_point(sm.P, p4.x, p4.y, p4.z, q.x, q.y, q.z);
+    xform_normal(sm.N, n4.x, n4.y, n4.z, snx, sny, snz);
+    s_rgba = __float_as_uint(n4.w);
     q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
     return true;
 }
 
+// Initial bound of a search: the distance threshold (D3), tightened by the neighbour this query had before.
 template <bool COLOR>
-__global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_grid_kernel(const MatchArgs a) {
-    __shared__ PoseSm sm;
-    load_pose(sm, a.state_ro);
-    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-    if (slot < d.n_queries) {
-        Query q; float snx, sny, snz; unsigned int s_rgba;
-        if (prepare_query(a, d, sm, slot, q, snx, sny, snz, s_rgba)) {
-            ++nq;
-            Best b; b.d = fminf(a.max_d2, 3.4028234e38f); b.idx = INT_MAX; b.pos = -1;
-            if (finite3(q.x, q.y, q.z)) {
-                const GridParams g = *a.grid;
-                grid_search<COLOR>(g, a.cell_start, a.tgt_pts, a.tgt_nrm, q, b, ev, nd);
-            }
-            finish_match(a, slot, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
-        } else {
-            a.match_pos[slot] = -1; a.match_w[slot] = 0.0f; if (a.match_idx) a.match_idx[slot] = -1;
+__device__ __forceinline__ void seed_best(const MatchArgs& a, const Query& q, int p, Best& b) {
+    b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
+    if (a.use_seed) {
+        const int sp = a.nn_pos[p];
+        if (sp >= 0 && sp < a.n_tgt) {
+            const float4 c = __ldg(&a.tgt_pts[sp]);
+            const float d = dist2<COLOR>(q, c, b.d, a.tgt_nrm, (unsigned int)sp);
+            const int idx = __float_as_int(c.w);
+            if (better(d, idx, b)) { b.d = d; b.idx = idx; b.pos = sp; }
         }
     }
-    flush_stats(a.state, nq, nm, ev, nd);
+}
+
+// ---------------------------------------------------------------------------- tiled search
+struct TileSm {
+    PoseSm pose;
+    float4 pts[TILE_CHUNK];
+    unsigned int rgba[TILE_CHUNK];
+    unsigned int cell_s[TILE_MAX_CELLS];
+    unsigned int cell_pref[TILE_MAX_CELLS + 1];
+    float red[ICP_TILE / 32][8];
+    float box[8];            // B1: lo[3], hi[3]
+    unsigned int warp_sums[ICP_TILE / 32];
+    unsigned int count;      // staged points of the current round
+    unsigned int total;      // points in the candidate cells
+    int any_active;
+};
+
+// every point x with lo <= x <= hi is binned in a cell of [cell_lo, cell_hi]: cell_index() is monotone
+__device__ __forceinline__ int cell_index_axis(const GridParams& g, int a, float x) {
+    const float o = sel3f(a, g.o[0], g.o[1], g.o[2]), ih = sel3f(a, g.inv_h[0], g.inv_h[1], g.inv_h[2]);
+    const int bits = sel3i(a, g.bits[0], g.bits[1], g.bits[2]);
+    const float u = pmul(psub(x, o), ih);
+    const int i = (int)floorf(u);
+    return min(max(i, 0), (1 << bits) - 1);
+}
+
+template <bool COLOR>
+__global__ void __launch_bounds__(ICP_TILE) knn_tile_kernel(const MatchArgs a) {
+    __shared__ TileSm sm;
+    load_pose(sm.pose, a.state_ro);
+    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
+    const IterDesc d = a.desc[it];
+    const int2 tile = a.tiles[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int p = tile.x + tid;
+    const bool in_tile = tid < tile.y;
+    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
+
+    Query q; float snx = 0.f, sny = 0.f, snz = 0.f; unsigned int s_rgba = 0;
+    bool is_query = in_tile && prepare_query(a, d, sm.pose, p, q, snx, sny, snz, s_rgba);
+    if (is_query) ++nq;
+    const bool searching = is_query && finite3(q.x, q.y, q.z);
+    Best b; b.d = -1.0f; b.idx = INT_MAX; b.pos = -1;
+    float r = 0.0f;
+    if (searching) {
+        seed_best<COLOR>(a, q, p, b);
+        // every target point that can still win has |q - p| <= r per axis (monotone fp32 rounding of D1)
+        r = b.d < FLT_BIG ? __fmul_ru(__fsqrt_ru(b.d), 1.00001f) : FLT_BIG;
+    } else {
+        q.x = q.y = q.z = __int_as_float(0x7fc00000);   // NaN: never improves on anything
+        q.cr = q.cg = q.cb = 0.f;
+    }
+
+    // ---- tile box B0 and the radius cap
+    float lo[3] = {searching ? q.x : FLT_BIG, searching ? q.y : FLT_BIG, searching ? q.z : FLT_BIG};
+    float hi[3] = {searching ? q.x : -FLT_BIG, searching ? q.y : -FLT_BIG, searching ? q.z : -FLT_BIG};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
+    if (lane == 0) { for (int k = 0; k < 3; ++k) { sm.red[wid][k] = lo[k]; sm.red[wid][3 + k] = hi[k]; } }
+    if (tid == 0) sm.any_active = 0;
+    __syncthreads();
+    if (searching) sm.any_active = 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = fminf(fminf(sm.red[0][k], sm.red[1][k]), fminf(sm.red[2][k], sm.red[3][k]));
+        hi[k] = fmaxf(fmaxf(sm.red[0][3 + k], sm.red[1][3 + k]), fmaxf(sm.red[2][3 + k], sm.red[3][3 + k]));
+    }
+    __syncthreads();
+    if (!sm.any_active) {                          // block-uniform
+        if (in_tile) { if (is_query) finish_match(a, p, false, 0.f, -1, -1, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm); else write_no_query(a, p); }
+        flush_stats(a, nq, nm, ev, nd);
+        return;
+    }
+    const GridParams g = *a.grid;
+    const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    float cap = ext + 2.0f * fmaxf(fmaxf(g.h[0], g.h[1]), g.h[2]);
+    float rho = 0.f;
+    int depth = 0, rem0 = 0, rem1 = 0, rem2 = 0, k0 = 0, k1 = 0, k2 = 0, n0 = 1, n1 = 1, n2 = 1;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        // ---- B1 = union of the balls (q_i, min(r_i, cap)), rounded outwards
+        rho = fminf(r, cap);
+        float blo[3], bhi[3];
+        blo[0] = searching ? __fsub_rd(q.x, rho) : FLT_BIG; blo[1] = searching ? __fsub_rd(q.y, rho) : FLT_BIG; blo[2] = searching ? __fsub_rd(q.z, rho) : FLT_BIG;
+        bhi[0] = searching ? __fadd_ru(q.x, rho) : -FLT_BIG; bhi[1] = searching ? __fadd_ru(q.y, rho) : -FLT_BIG; bhi[2] = searching ? __fadd_ru(q.z, rho) : -FLT_BIG;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { blo[k] = fminf(blo[k], __shfl_xor_sync(0xFFFFFFFFu, blo[k], o)); bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(0xFFFFFFFFu, bhi[k], o)); }
+        if (lane == 0) { for (int k = 0; k < 3; ++k) { sm.red[wid][k] = blo[k]; sm.red[wid][3 + k] = bhi[k]; } }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            blo[k] = fminf(fminf(sm.red[0][k], sm.red[1][k]), fminf(sm.red[2][k], sm.red[3][k]));
+            bhi[k] = fmaxf(fmaxf(sm.red[0][3 + k], sm.red[1][3 + k]), fmaxf(sm.red[2][3 + k], sm.red[3][3 + k]));
+        }
+        if (tid == 0) { for (int k = 0; k < 3; ++k) { sm.box[k] = blo[k]; sm.box[3 + k] = bhi[k]; } }
+        // ---- cells of the coarsest-needed depth that meet B1 (uniform computation in every thread)
+        const int fl0 = cell_index_axis(g, 0, blo[0]), fh0 = cell_index_axis(g, 0, bhi[0]);
+        const int fl1 = cell_index_axis(g, 1, blo[1]), fh1 = cell_index_axis(g, 1, bhi[1]);
+        const int fl2 = cell_index_axis(g, 2, blo[2]), fh2 = cell_index_axis(g, 2, bhi[2]);
+        depth = g.T; rem0 = rem1 = rem2 = 0;
+        for (;;) {
+            k0 = fl0 >> rem0; k1 = fl1 >> rem1; k2 = fl2 >> rem2;
+            n0 = (fh0 >> rem0) - k0 + 1; n1 = (fh1 >> rem1) - k1 + 1; n2 = (fh2 >> rem2) - k2 + 1;
+            if ((long long)n0 * n1 * n2 <= TILE_MAX_CELLS || depth == 0) break;
+            --depth;
+            const int ax = (int)((g.axis_seq >> (2 * depth)) & 3ull);
+            if (ax == 0) ++rem0; else if (ax == 1) ++rem1; else ++rem2;
+        }
+        // thread c owns candidate cell c
+        unsigned int cs_ = 0, cnt = 0;
+        if (tid < n0 * n1 * n2) {
+            const int i0 = k0 + tid % n0, i1 = k1 + (tid / n0) % n1, i2 = k2 + tid / (n0 * n1);
+            int b0 = g.bits[0] - rem0, b1 = g.bits[1] - rem1, b2 = g.bits[2] - rem2;
+            unsigned int code = 0;
+            for (int k = 0; k < depth; ++k) {
+                const int ax = (int)((g.axis_seq >> (2 * k)) & 3ull);
+                int bit;
+                if (ax == 0) { --b0; bit = (i0 >> b0) & 1; } else if (ax == 1) { --b1; bit = (i1 >> b1) & 1; } else { --b2; bit = (i2 >> b2) & 1; }
+                code = (code << 1) | (unsigned int)bit;
+            }
+            const int sh = g.T - depth;
+            cs_ = __ldg(&a.cell_start[(size_t)code << sh]);
+            cnt = __ldg(&a.cell_start[((size_t)code + 1) << sh]) - cs_;
+        }
+        // block exclusive scan of cnt
+        unsigned int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sm.warp_sums[wid] = inc;
+        __syncthreads();
+        unsigned int woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < ICP_TILE / 32; ++w) { const unsigned int v = sm.warp_sums[w]; if (w < wid) woff += v; total += v; }
+        sm.cell_s[tid] = cs_;
+        sm.cell_pref[tid] = woff + inc - cnt;
+        if (tid == 0) { sm.cell_pref[TILE_MAX_CELLS] = total; sm.total = total; }
+        __syncthreads();
+        if (total <= TILE_BUDGET || !(cap > 0.f)) break;
+        cap = attempt < 4 ? 0.5f * cap : 0.0f;     // too many candidate points: cut the radius, the cut queries are deferred
+    }
+    const float box_lo0 = sm.box[0], box_lo1 = sm.box[1], box_lo2 = sm.box[2], box_hi0 = sm.box[3], box_hi1 = sm.box[4], box_hi2 = sm.box[5];
+    const unsigned int total = sm.total;
+
+    // ---- rounds: stage the candidate points that lie inside B1, then every thread scans them
+    unsigned int staged_total = 0;
+    for (unsigned int base = 0; base < total; base += TILE_CHUNK) {
+        if (tid == 0) sm.count = 0;
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < TILE_CHUNK / ICP_TILE; ++j) {
+            const unsigned int f = base + (unsigned int)j * ICP_TILE + tid;
+            bool keep = false; float4 c = make_float4(0.f, 0.f, 0.f, 0.f); unsigned int gi = 0;
+            if (f < total) {
+                int lo_c = 0, hi_c = TILE_MAX_CELLS;                       // last cell with pref <= f
+                while (hi_c - lo_c > 1) { const int mid = (lo_c + hi_c) >> 1; if (sm.cell_pref[mid] <= f) lo_c = mid; else hi_c = mid; }
+                gi = sm.cell_s[lo_c] + (f - sm.cell_pref[lo_c]);
+                c = __ldg(&a.tgt_pts[gi]);
+                keep = c.x >= box_lo0 && c.x <= box_hi0 && c.y >= box_lo1 && c.y <= box_hi1 && c.z >= box_lo2 && c.z <= box_hi2;
+            }
+            const unsigned int m = __ballot_sync(0xFFFFFFFFu, keep);
+            unsigned int wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(&sm.count, (unsigned int)__popc(m));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (keep) {
+                const unsigned int slot = wbase + (unsigned int)__popc(m & ((1u << lane) - 1u));
+                c.w = __int_as_float((int)gi);                               // position; the original index is re-read on a hit
+                sm.pts[slot] = c;
+                if (COLOR) sm.rgba[slot] = __float_as_uint(__ldg(&a.tgt_nrm[gi].w));
+            }
+        }
+        __syncthreads();
+        const unsigned int n_st = sm.count;
+        staged_total += n_st;
+        // scan: shared-memory broadcast reads, identical trip count in every thread
+#pragma unroll 4
+        for (unsigned int i = 0; i < n_st; ++i) {
+            const float4 c = sm.pts[i];
+            float dd = dist3(q, c);
+            if (dd <= b.d) {
+                if (COLOR) dd = dist6_tail(q, dd, sm.rgba[i]);
+                const int pos = __float_as_int(c.w);
+                const int idx = __float_as_int(__ldg(&a.tgt_pts[pos].w));
+                if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = pos; }
+            }
+        }
+        __syncthreads();
+    }
+    if (searching) ev += staged_total;
+
+    // ---- resolved iff the scanned box covered the ball of the final bound
+    bool defer = false;
+    if (in_tile) {
+        if (!is_query) write_no_query(a, p);
+        else if (!searching) finish_match(a, p, false, 0.f, -1, -1, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+        else {
+            const float r_now = b.d < FLT_BIG ? __fmul_ru(__fsqrt_ru(b.d), 1.00001f) : FLT_BIG;
+            a.nn_pos[p] = b.pos;
+            if (r_now <= rho) finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+            else defer = true;
+        }
+    }
+    // Unresolved queries go to the packet kernel: one contiguous, warp-padded run per tile, so that a
+    // packet (32 consecutive entries) only holds queries of one compact tile.
+    {
+        const unsigned int m = __ballot_sync(0xFFFFFFFFu, defer);
+        if (lane == 0) sm.warp_sums[wid] = (unsigned int)__popc(m);
+        __syncthreads();
+        unsigned int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < ICP_TILE / 32; ++w) { const unsigned int v = sm.warp_sums[w]; if (w < wid) before += v; tot += v; }
+        if (tot > 0) {                                        // block-uniform
+            const unsigned int padded = (tot + 31u) & ~31u;
+            if (tid == 0) sm.count = atomicAdd(&a.state->n_deferred[it], padded);
+            __syncthreads();
+            const unsigned int base = sm.count;
+            if (defer) a.deferred[base + before + (unsigned int)__popc(m & ((1u << lane) - 1u))] = p;
+            if ((unsigned int)tid < padded - tot) a.deferred[base + tot + tid] = -1;
+            nd = defer ? 1u : 0u;
+        }
+    }
+    flush_stats(a, nq, nm, ev, 0u);
+    if (a.collect_stats) {
+        nd = __reduce_add_sync(0xFFFFFFFFu, nd);
+        if (lane == 0 && nd) atomicAdd(&a.state->n_deferred_total, (unsigned long long)nd);
+        if (tid == 0) atomicAdd(&a.state->n_staged, (unsigned long long)staged_total);
+    }
+}
+
+#define PACKET_LEAF 32   // a node with <= this many points is scanned by the packet, not split
+
+// Packet traversal: the 32 lanes of a warp hold 32 queries of one tile and walk the implicit tree
+// TOGETHER (uniform control flow, cell-table reads shared by the warp).  A node is entered when ANY lane
+// still needs it; every lane keeps its own per-axis gaps and its own best, and scans a leaf only if its
+// own bound admits it (leaf points are read at the same address by all lanes: one broadcast transaction).
+template <bool COLOR>
+__device__ void tree_search_packet(const GridParams& g, const unsigned int* __restrict__ cs, const float4* __restrict__ pts,
+                                   const float4* __restrict__ nrm, const Query& q, bool active, Best& b, unsigned int& evals,
+                                   unsigned int& nodes) {
+    const unsigned int FULL = 0xFFFFFFFFu;
+    const int T = g.T;
+    const unsigned int s0 = __ldg(&cs[0]), e0 = __ldg(&cs[1u << T]);
+    if (e0 == s0) return;
+    const unsigned int act = __ballot_sync(FULL, active);
+    if (!act) return;
+    const int half = __popc(act) >> 1;
+    int lo0 = 0, lo1 = 0, lo2 = 0, r0 = g.bits[0], r1 = g.bits[1], r2 = g.bits[2];
+    float t0 = gap2(g, 0, q.x, 0, r0), t1 = gap2(g, 1, q.y, 0, r1), t2 = gap2(g, 2, q.z, 0, r2);
+    ++nodes;
+    bool need = active && !(padd(padd(t0, t1), t2) > b.d);
+    if (!__any_sync(FULL, need)) return;
+    if (e0 - s0 <= PACKET_LEAF || T == 0) { if (need) scan_range<COLOR>(pts, nrm, s0, e0, q, b, evals); return; }
+    int d = 0, stage = 0, from = 0; unsigned int p = 0; bool asc = false;
+    for (;;) {
+        const int a = (int)((g.axis_seq >> (2 * d)) & 3ull);
+        const int lo = sel3i(a, lo0, lo1, lo2), r = sel3i(a, r0, r1, r2) - 1;
+        const float qa = sel3f(a, q.x, q.y, q.z);
+        const float plane = sel3f(a, g.o[0], g.o[1], g.o[2]) + (float)(lo + (1 << r)) * sel3f(a, g.h[0], g.h[1], g.h[2]);
+        // visiting order only (any choice is correct): the side most of the packet's queries are on
+        const int nb = __popc(__ballot_sync(FULL, active && qa >= plane)) > half ? 1 : 0;
+        if (asc) { stage = (from == nb) ? 1 : 2; asc = false; }
+        if (stage == 2) {                                   // both children done: ascend
+            if (d == 0) break;
+            from = (int)(p & 1u); --d; p >>= 1;
+            const int a2 = (int)((g.axis_seq >> (2 * d)) & 3ull);
+            const int rc = sel3i(a2, r0, r1, r2), lc = sel3i(a2, lo0, lo1, lo2);
+            const int lp = lc - (from ? (1 << rc) : 0), rp = rc + 1;
+            const float tp = gap2(g, a2, sel3f(a2, q.x, q.y, q.z), lp, rp);
+            if (a2 == 0) { lo0 = lp; r0 = rp; t0 = tp; } else if (a2 == 1) { lo1 = lp; r1 = rp; t1 = tp; } else { lo2 = lp; r2 = rp; t2 = tp; }
+            asc = true;
+            continue;
+        }
+        const int bch = stage == 0 ? nb : (nb ^ 1);
+        ++stage;
+        const int lc = lo + (bch ? (1 << r) : 0);
+        const float tc = gap2(g, a, qa, lc, r);
+        const float lb = padd(padd(a == 0 ? tc : t0, a == 1 ? tc : t1), a == 2 ? tc : t2);
+        ++nodes;
+        need = active && !(lb > b.d);
+        if (!__any_sync(FULL, need)) continue;
+        const unsigned int c = 2u * p + (unsigned int)bch; const int sh = T - d - 1;
+        const unsigned int ns = __ldg(&cs[c << sh]), ne = __ldg(&cs[(c + 1u) << sh]);
+        if (ne == ns) continue;
+        if (ne - ns <= PACKET_LEAF || d + 1 == T) { if (need) scan_range<COLOR>(pts, nrm, ns, ne, q, b, evals); continue; }
+        if (a == 0) { lo0 = lc; r0 = r; t0 = tc; } else if (a == 1) { lo1 = lc; r1 = r; t1 = tc; } else { lo2 = lc; r2 = r; t2 = tc; }
+        ++d; p = c; stage = 0;
+    }
+}
+
+// The queries the tile kernel deferred, one packet (warp) per 32 list entries.
+template <bool COLOR>
+__global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_packet_kernel(const MatchArgs a) {
+    __shared__ PoseSm sm;
+    load_pose(sm, a.state_ro);
+    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
+    const IterDesc d = a.desc[it];
+    const int n = (int)a.state_ro->n_deferred[it];             // multiple of 32
+    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
+    const GridParams g = *a.grid;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32 < n; w += warps) {
+        const int p = a.deferred[w * 32 + lane];
+        Query q; float snx = 0.f, sny = 0.f, snz = 0.f; unsigned int s_rgba = 0;
+        bool active = p >= 0 && prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba);
+        Best b; b.d = -1.f; b.idx = INT_MAX; b.pos = -1;
+        if (active) seed_best<COLOR>(a, q, p, b);
+        else { q.x = q.y = q.z = __int_as_float(0x7fc00000); q.cr = q.cg = q.cb = 0.f; }
+        tree_search_packet<COLOR>(g, a.cell_start, a.tgt_pts, a.tgt_nrm, q, active, b, ev, nd);
+        if (active) {
+            a.nn_pos[p] = b.pos;
+            finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+        }
+    }
+    flush_stats(a, nq, nm, ev, nd);
+}
+
+// One thread per query: all queries (LIST = false, grid-stride over the sorted source) or the
+// queries the tile kernel deferred (LIST = true), seeded with the best candidate found so far.
+template <bool COLOR, bool LIST>
+__global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_tree_kernel(const MatchArgs a) {
+    __shared__ PoseSm sm;
+    load_pose(sm, a.state_ro);
+    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
+    const IterDesc d = a.desc[it];
+    const int n = LIST ? (int)a.state_ro->n_deferred[it] : a.n_src;
+    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
+    const GridParams g = *a.grid;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int p = LIST ? a.deferred[k] : k;
+        Query q; float snx, sny, snz; unsigned int s_rgba;
+        if (prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {
+            if (!LIST) ++nq;
+            Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
+            if (finite3(q.x, q.y, q.z)) {
+                seed_best<COLOR>(a, q, p, b);
+                tree_search<COLOR>(g, a.cell_start, a.tgt_pts, a.tgt_nrm, q, b, ev, nd);
+                a.nn_pos[p] = b.pos;
+            }
+            finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+        } else if (!LIST) {
+            write_no_query(a, p);
+        }
+    }
+    flush_stats(a, nq, nm, ev, nd);
 }
 
 // Small targets: one warp per query, lanes stride over the target (original order, L1-resident),
@@ -248,12 +603,12 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int lane = threadIdx.x & 31;
-    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-    if (slot < d.n_queries) {
+    if (p < a.n_src) {
         Query q; float snx, sny, snz; unsigned int s_rgba;
-        if (prepare_query(a, d, sm, slot, q, snx, sny, snz, s_rgba)) {     // warp-uniform
-            Best b; b.d = fminf(a.max_d2, 3.4028234e38f); b.idx = INT_MAX; b.pos = -1;
+        if (prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {     // warp-uniform
+            Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
             if (finite3(q.x, q.y, q.z)) {
                 for (int j = lane; j < a.n_tgt; j += 32) {
                     const float4 c = __ldg(&a.tgt_pts[j]);
@@ -268,12 +623,12 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
                 }
                 if (b.idx == INT_MAX) b.pos = -1; else b.pos = b.idx;
             }
-            if (lane == 0) { ++nq; finish_match(a, slot, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm); }
+            if (lane == 0) { ++nq; finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm); }
         } else if (lane == 0) {
-            a.match_pos[slot] = -1; a.match_w[slot] = 0.0f; if (a.match_idx) a.match_idx[slot] = -1;
+            write_no_query(a, p);
         }
     }
-    flush_stats(a.state, nq, nm, ev, nd);
+    flush_stats(a, nq, nm, ev, nd);
 }
 
 // Projective matching (NearestNeighbor.h:333-421): literal restatement of the window scan, unsigned
@@ -282,20 +637,20 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) projective_kernel(const Mat
     __shared__ PoseSm sm;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-    if (slot < d.n_queries) {
+    if (p < a.n_src) {
         Query q; float snx, sny, snz; unsigned int s_rgba;
-        if (prepare_query(a, d, sm, slot, q, snx, sny, snz, s_rgba)) {
+        if (prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {
             ++nq;
             if (q.x == MINF_F) {
                 // :372-373 `continue` leaves the value-initialised Match{0, 0.f} (:353)
-                finish_match(a, slot, true, 0.0f, 0, 0, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+                finish_match(a, p, true, 0.0f, 0, 0, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
             } else {
                 const unsigned int searchWindow = 12u;                         // NearestNeighbor.h:319
                 const unsigned int uP = x86_float_to_u32(roundf(padd(pdiv(pmul(q.x, a.fx), q.z), a.cx)));
                 const unsigned int vP = x86_float_to_u32(roundf(padd(pdiv(pmul(q.y, a.fy), q.z), a.cy)));
-                float minDist = 3.4028234e38f; unsigned int idx = 0xFFFFFFFFu;
+                float minDist = FLT_BIG; unsigned int idx = 0xFFFFFFFFu;
                 for (unsigned int v = vP - searchWindow; (v < a.height && v <= vP + searchWindow); v++) {
                     for (unsigned int u = uP - searchWindow; (u < a.width && u <= uP + searchWindow); u++) {
                         const unsigned int ni = a.width * v + u;
@@ -308,27 +663,41 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) projective_kernel(const Mat
                     }
                 }
                 const bool ok = minDist <= a.max_d2 && idx != 0xFFFFFFFFu;
-                finish_match(a, slot, ok, 1.0f, (int)idx, (int)idx, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+                finish_match(a, p, ok, 1.0f, (int)idx, (int)idx, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
             }
         } else {
-            a.match_pos[slot] = -1; a.match_w[slot] = 0.0f; if (a.match_idx) a.match_idx[slot] = -1;
+            write_no_query(a, p);
         }
     }
-    flush_stats(a.state, nq, nm, ev, nd);
+    flush_stats(a, nq, nm, ev, nd);
 }
 
-cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int max_queries, cudaStream_t s) {
-    if (max_queries <= 0) return cudaSuccess;
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches) {
+    if (a.n_src <= 0) return cudaSuccess;
     const int T = ICP_MATCH_THREADS;
+    int launches = 0;
     if (algorithm == 2) {
-        projective_kernel<<<(max_queries + T - 1) / T, T, 0, s>>>(a);
+        projective_kernel<<<(a.n_src + T - 1) / T, T, 0, s>>>(a); ++launches;
     } else if (algorithm == 1) {
-        const long long threads = (long long)max_queries * 32;
+        const long long threads = (long long)a.n_src * 32;
         const int nb = (int)((threads + T - 1) / T);
         if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
+        ++launches;
+    } else if (algorithm == 3) {
+        const int nb = (a.n_src + T - 1) / T;
+        if (a.color_icp) knn_tree_kernel<true, false><<<nb, T, 0, s>>>(a); else knn_tree_kernel<false, false><<<nb, T, 0, s>>>(a);
+        ++launches;
     } else {
-        const int nb = (max_queries + T - 1) / T;
-        if (a.color_icp) knn_grid_kernel<true><<<nb, T, 0, s>>>(a); else knn_grid_kernel<false><<<nb, T, 0, s>>>(a);
+        if (a.n_tiles > 0) {
+            if (a.color_icp) knn_tile_kernel<true><<<a.n_tiles, ICP_TILE, 0, s>>>(a); else knn_tile_kernel<false><<<a.n_tiles, ICP_TILE, 0, s>>>(a);
+            ++launches;
+            int nb = (a.n_src / 2 + 3) / 4;                      // deferred queries: one warp per packet, grid-stride over the list
+            if (nb > 16 * n_sms) nb = 16 * n_sms;
+            if (nb < 1) nb = 1;
+            if (a.color_icp) knn_packet_kernel<true><<<nb, T, 0, s>>>(a); else knn_packet_kernel<false><<<nb, T, 0, s>>>(a);
+            ++launches;
+        }
     }
+    if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }

@@ -181,21 +181,20 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
     if (threadIdx.x >= 64 && threadIdx.x < 73) Nm[threadIdx.x - 64] = a.state->nrm[threadIdx.x - 64];
     __syncthreads();
-    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state->iter];
     double v[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = 0.0;
     const double LP = (double)0.1f, LQ = (double)1.0f;   // LAMBDA_POINT / LAMBDA_PLANE|SYMMETRIC (ICPOptimizer.h:737-738, :840-841)
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < d.n_queries; slot += gridDim.x * blockDim.x) {
-        const int pos = a.match_pos[slot];
+    // queries are addressed by their position in the Morton-sorted source; a query without a surviving match has pos -1
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += gridDim.x * blockDim.x) {
+        const int pos = a.match_pos[i];
         if (pos < 0) continue;
-        const int i = slot_source_index(d, a.sel, slot, a.n_src);
         const float4 sp = __ldg(&a.src_pts[i]);
         float sxf, syf, szf;
         xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
         const float4 tp = __ldg(&a.tgt_pts[pos]);
         if (!finite3(sxf, syf, szf) || !finite3(tp.x, tp.y, tp.z)) continue;        // ICPOptimizer.h:590-592
-        const double w = (double)a.match_w[slot];
+        const double w = (double)a.match_w[i];
         if (MODE == 3) {
             v[0] += 1.0; v[1] += sxf; v[2] += syf; v[3] += szf; v[4] += tp.x; v[5] += tp.y; v[6] += tp.z;
         } else if (MODE == 0) {
@@ -277,15 +276,14 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     }
 }
 
-int icp_reduce_blocks(int max_queries, int n_sms) {
-    int nb = (max_queries + ICP_REDUCE_THREADS * 4 - 1) / (ICP_REDUCE_THREADS * 4);   // ~4 points per thread
+int icp_reduce_blocks(int n_src, int n_sms) {
+    int nb = (n_src + ICP_REDUCE_THREADS * 4 - 1) / (ICP_REDUCE_THREADS * 4);   // ~4 points per thread
     if (nb > 2 * n_sms) nb = 2 * n_sms;
     if (nb < 1) nb = 1;
     return nb;
 }
 
-cudaError_t icp_launch_reduce(const ReduceArgs& a, int max_queries, int n_blocks, cudaStream_t s, int* n_launches) {
-    (void)max_queries;
+cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches) {
     int launches = 0;
     if (a.metric == ICP_GPU_METRIC_P2P) { reduce_kernel<0><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches; }
     else if (a.metric == ICP_GPU_METRIC_P2PLANE) { reduce_kernel<1><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches; }
@@ -308,17 +306,18 @@ cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase
 
 // ---------------------------------------------------------------------------- pose upload / shard apply
 __global__ void pose_init_kernel(DevState* st, const float* pose16) {
+    for (int k = threadIdx.x; k < ICP_MAX_ITERS + 2; k += blockDim.x) st->n_deferred[k] = 0u;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int i = 0; i < 16; ++i) st->pose[i] = pose16[i];
     inv_transpose3_pinned(st->pose, st->nrm);
     st->iter = 0; st->iters_done = 0; st->status = 0; st->ticket = 0; st->ticket2 = 0;
-    st->n_queries = 0; st->n_matched = 0; st->n_evals = 0; st->n_nodes = 0;
+    st->n_queries = 0; st->n_matched = 0; st->n_evals = 0; st->n_nodes = 0; st->n_staged = 0; st->n_deferred_total = 0;
     for (int k = 0; k < 3; ++k) { st->mean_s[k] = 0.f; st->mean_d[k] = 0.f; }
     st->lm_done = 0; st->lm_iter = 0;
 }
 
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s) {
-    pose_init_kernel<<<1, 32, 0, s>>>(st, pose_dev16);
+    pose_init_kernel<<<1, 128, 0, s>>>(st, pose_dev16);
     return cudaGetLastError();
 }
 

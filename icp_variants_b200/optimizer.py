@@ -138,7 +138,7 @@ class ICPOptimizer:
         self.proba = 1.0
         self.seed = 0                 # the reference seeds from std::random_device (selection.h:76-79)
         self.selection_rng = 0        # 0 mt19937 (reference-compatible), 1 device stream
-        self.nn_algorithm = 0         # 0 auto, 1 brute force, 2 grid
+        self.nn_algorithm = 0         # 0 auto, 1 brute force, 2 tiled grid search, 3 per-query tree search
         self.use_graph = True
         self.m_timeMeasure: TimeMeasure | None = None
         self.m_convergenceMeasure: ConvergenceMeasure | None = None

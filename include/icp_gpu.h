@@ -54,8 +54,10 @@ enum { ICP_GPU_MATCH_KNN = 0, ICP_GPU_MATCH_PROJECTIVE = 1 };
 enum { ICP_GPU_SELECT_ALL = 0, ICP_GPU_SELECT_RANDOM = 1 };
 /* weighting.h:8                                                                                  */
 enum { ICP_GPU_WEIGHT_CONSTANT = 0, ICP_GPU_WEIGHT_DISTANCES = 1, ICP_GPU_WEIGHT_NORMALS = 2, ICP_GPU_WEIGHT_COLORS = 3 };
-/* Nearest-neighbour kernel choice (both exact, same answers): 0 = by target size               */
-enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2 };
+/* Nearest-neighbour kernel choice (all exact, same answers): AUTO = by target size; BRUTE = warp per
+ * query over the whole target; GRID = tiled shared-memory search over the cell grid (tree search for
+ * the few queries a tile cannot resolve); TREE = per-query tree search over the cell grid              */
+enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2, ICP_GPU_NN_TREE = 3 };
 /* Random selection stream: 0 = std::mt19937 + uniform_real_distribution<double> drawn on the host
  * exactly as selection.h:88-104 does (reference-compatible for a given seed); 1 = counter-based
  * hash drawn on the device (fast, not reference-compatible).                                      */
@@ -82,6 +84,8 @@ typedef struct icp_gpu_config {
     int32_t  lm_max_iterations; /* Ceres max_num_iterations  default 10     (ICPOptimizer.h:358)     */
     int32_t  nn_algorithm;      /* ICP_GPU_NN_*                                                     */
     int32_t  use_graph;         /* 1 (default): replay the iteration loop as one CUDA graph          */
+    int32_t  collect_stats;     /* 1 (default): fill icp_gpu_stats' work counters (device atomics);
+                                   0: fastest, icp_gpu_get_stats then only reports kernel launches   */
 } icp_gpu_config;
 
 /* Per-stage device times of the last icp_gpu_estimate_pose call made with timings != NULL
@@ -106,6 +110,9 @@ typedef struct icp_gpu_stats {
     uint64_t n_distance_evals; /* point-to-point squared distances evaluated by the search         */
     uint64_t n_nodes_visited;  /* grid nodes (cells at any level) whose bound was tested           */
     uint64_t n_kernel_launches;/* kernels launched by this library in the call                     */
+    uint64_t n_points_staged;  /* target points staged in shared memory by the tiled search        */
+    uint64_t n_deferred;       /* queries the tiled search handed to the packet tree search        */
+    uint64_t n_tiles;          /* source tiles (blocks of the tiled search)                        */
 } icp_gpu_stats;
 
 typedef struct icp_gpu_ctx icp_gpu_ctx;
