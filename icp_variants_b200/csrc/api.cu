@@ -77,7 +77,8 @@ struct icp_gpu_ctx {
     std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
     bool src_rank_valid = false;
     // target grid
-    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums;
+    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box;
+    BvhDesc bvh;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
     // source grid (only its sort order and tiles are used) and tiles
     DeviceBuf sgrid, scell_start, tiles, n_tiles_dev, order_dev;
@@ -190,6 +191,11 @@ int build_grid(icp_gpu_ctx* ctx) {
                              (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
                              (unsigned int*)ctx->cell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->tgt_pts_sorted.p,
                              (float4*)ctx->tgt_nrm_sorted.p, 0, ctx->stream, &launches));
+    icp_bvh_layout(n, &ctx->bvh);
+    const size_t n_nodes = (size_t)ctx->bvh.offset[ctx->bvh.n_levels - 1] + (size_t)ctx->bvh.count[ctx->bvh.n_levels - 1];
+    if (ensure(ctx, ctx->bvh_box, n_nodes * 2 * sizeof(float4))) return ICP_GPU_E_CUDA;
+    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, (const unsigned int*)ctx->cell_start.p + ((size_t)1 << ctx->T), ctx->bvh,
+                            (float4*)ctx->bvh_box.p, ctx->stream, &launches));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     ctx->grid_built = true;
@@ -255,7 +261,7 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
     if (!dev || !target) CU(cudaStreamSynchronize(ctx->stream));
     if (!target) {
         ctx->n_tiles = (int)*ctx->h_n_tiles;
-        if (ensure(ctx, ctx->deferred, ((size_t)(n > 0 ? n : 1) + 32 * (size_t)ctx->n_tiles) * 4)) return ICP_GPU_E_CUDA;
+        if (ensure(ctx, ctx->deferred, (size_t)(n > 0 ? n : 1) * 4)) return ICP_GPU_E_CUDA;
     }
     return ICP_GPU_OK;
 }
@@ -355,6 +361,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.tgt_pts = (const float4*)(grid_order ? c->tgt_pts_sorted.p : c->tgt_pts.p);
     a.tgt_nrm = (const float4*)(grid_order ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
     a.n_tgt = c->n_tgt;
+    a.bvh_box = (const float4*)c->bvh_box.p; a.bvh = c->bvh;
     if (c->have_camera) { a.fx = c->K[0]; a.fy = c->K[4]; a.cx = c->K[6]; a.cy = c->K[7]; }   // column-major Matrix3f
     a.width = c->width; a.height = c->height;
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
@@ -570,7 +577,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->tiles, &ctx->n_tiles_dev, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->deferred};
+                         &ctx->nn_pos, &ctx->deferred, &ctx->bvh_box};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);

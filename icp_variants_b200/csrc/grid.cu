@@ -11,6 +11,7 @@
 // Launches (all on one stream, no host synchronisation): pack -> bbox -> params -> memset ->
 // keys+count -> scan (3) -> scatter.
 #include "icp_internal.cuh"
+#include <string.h>
 
 // ---------------------------------------------------------------------------- pack AoS3 -> float4
 __global__ void pack_cloud_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const uint8_t* __restrict__ rgba,
@@ -273,6 +274,59 @@ __global__ void fill_int_kernel(int* __restrict__ p, int n, int v) {
 }
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
     if (n > 0) fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- BVH over the sorted cloud
+void icp_bvh_layout(int n, BvhDesc* out) {
+    BvhDesc b; memset(&b, 0, sizeof(b));
+    int cnt = (n + 31) / 32; if (cnt < 1) cnt = 1;
+    int off = 0, l = 0;
+    for (;;) {
+        b.count[l] = cnt; b.offset[l] = off; off += cnt; ++l;
+        if (cnt == 1 || l == ICP_BVH_MAX_LEVELS) break;
+        cnt = (cnt + 31) / 32;
+    }
+    b.n_levels = l;
+    *out = b;
+}
+
+// one warp per node: level 0 reads 32 points, level l > 0 reads 32 child boxes; warp min/max; slots
+// beyond the last finite point (or beyond the last child) are empty: box = [+inf, -inf], never entered
+__global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ n_finite_dev, float4* __restrict__ box,
+                                 int level, int count, int offset, int child_count, int child_offset) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= count) return;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (level == 0) {
+        const unsigned int i = (unsigned int)node * 32u + lane;
+        if (i < *n_finite_dev) { const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
+    } else {
+        const int c = node * 32 + lane;
+        if (c < child_count) {
+            const float4 a = box[2 * (size_t)(child_offset + c)], b = box[2 * (size_t)(child_offset + c) + 1];
+            lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; hi[0] = b.x; hi[1] = b.y; hi[2] = b.z;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
+    if (lane == 0) {
+        box[2 * (size_t)(offset + node)] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        box[2 * (size_t)(offset + node) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+}
+
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const unsigned int* n_finite_dev, const BvhDesc& bvh, float4* box,
+                                 cudaStream_t s, int* n_launches) {
+    for (int l = 0; l < bvh.n_levels; ++l) {
+        const int warps_per_block = 8;
+        const int nb = (bvh.count[l] + warps_per_block - 1) / warps_per_block;
+        bvh_level_kernel<<<nb, warps_per_block * 32, 0, s>>>(pts_sorted, n_finite_dev, box, l, bvh.count[l], bvh.offset[l],
+                                                             l > 0 ? bvh.count[l - 1] : 0, l > 0 ? bvh.offset[l - 1] : 0);
+        if (n_launches) *n_launches += 1;
+    }
     return cudaGetLastError();
 }
 

@@ -48,6 +48,16 @@ struct GridParams {
 //   and (filter_finite == 0 or point and normal finite)          (PointCloud.h:335)
 //   and (mask_word_offset < 0 or bit `orig` of the mask is set)  (selection.h:88-104, drawn on the host)
 //   and (proba < 0 or hash(rng_key, orig) < proba)               (device selection stream)
+// 32-ary bounding-volume hierarchy over the cell-sorted target (grid.cu): level 0 = leaves of 32
+// consecutive points, level l+1 = 32 consecutive nodes of level l; every node stores the TIGHT
+// axis-aligned box of its points as two float4 {lo.xyz,_} {hi.xyz,_} at box[2*(offset[l]+j)].
+#define ICP_BVH_MAX_LEVELS 7
+struct BvhDesc {
+    int n_levels;                      // levels 0 .. n_levels-1; the top level has one node
+    int count[ICP_BVH_MAX_LEVELS];     // nodes per level
+    int offset[ICP_BVH_MAX_LEVELS];    // first node of the level in the box array
+};
+
 struct IterDesc {
     int stride;
     int filter_finite;
@@ -95,6 +105,8 @@ struct MatchArgs {
     const float4* tgt_pts;   // grid order {x,y,z,orig idx bits}; brute / projective: original order
     const float4* tgt_nrm;   // same order {nx,ny,nz,rgba bits}
     int n_tgt;
+    const float4* bvh_box;   // tight boxes of the BVH nodes (grid order only)
+    BvhDesc bvh;
     // projective
     float fx, fy, cx, cy; unsigned int width, height;
     // config
@@ -130,12 +142,16 @@ cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, in
                                   unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
                                   unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
                                   cudaStream_t s, int* n_launches);
+// Tight-box 32-ary BVH over the cell-sorted cloud; n_finite_dev = device address of the number of sorted points.
+void icp_bvh_layout(int n, BvhDesc* out);
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const unsigned int* n_finite_dev, const BvhDesc& bvh, float4* box,
+                                 cudaStream_t s, int* n_launches);
 // Partition of the sorted source into spatially compact tiles (<= ICP_TILE points each).
 cudaError_t icp_launch_make_tiles(const unsigned int* cell_start, int T, int n, int2* tiles, unsigned int* n_tiles_dev, cudaStream_t s,
                                   int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
-// algorithm: 0 tiled grid search (+ tree kernel for deferred queries), 1 brute force, 2 projective, 3 tree search for every query
+// algorithm: 0 tiled grid search (+ BVH kernel for deferred queries), 1 brute force, 2 projective, 3 BVH search for every query
 cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);

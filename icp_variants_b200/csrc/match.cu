@@ -16,8 +16,9 @@
 //                     the union of the queries' search balls in shared memory and every thread scans the
 //                     staged points (shared-memory broadcast reads, no divergence).  Queries whose ball
 //                     does not fit the tile's budget are handed to
-//   knn_tree_kernel   one thread per query: depth-first descent of the implicit tree over the cell table
-//                     with box-distance pruning (any bound, any distance; also usable for all queries).
+//   knn_bvh_kernel    one warp per query: depth-first walk of a 32-ary tight-box BVH over the cell-sorted
+//                     target, 32 child boxes tested per step (lane = child) and leaves of 32 points scanned
+//                     per step (lane = point); any bound, any distance; also usable for all queries.
 //   knn_brute_kernel  small targets: one warp per query, warp-shuffle arg-min.
 #include "icp_internal.cuh"
 #include <limits.h>
@@ -64,77 +65,6 @@ __device__ __forceinline__ float dist2(const Query& q, const float4 c, float bes
         d = dist6_tail(q, d, __float_as_uint(__ldg(&nrm[i].w)));
     }
     return d;
-}
-
-template <bool COLOR>
-__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, const float4* __restrict__ nrm, unsigned int s, unsigned int e,
-                                           const Query& q, Best& b, unsigned int& evals) {
-    for (unsigned int i = s; i < e; ++i) {
-        const float4 c = __ldg(&pts[i]);
-        const float d = dist2<COLOR>(q, c, b.d, nrm, i);
-        const int idx = __float_as_int(c.w);
-        if (better(d, idx, b)) { b.d = d; b.idx = idx; b.pos = (int)i; }
-    }
-    evals += e - s;
-}
-
-// Squared gap between q and the slab of cells [lo, lo + 2^r) on axis a, a lower bound (under fp32
-// rounding, by monotonicity) of the per-axis term of D1 for every point stored in those cells.
-__device__ __forceinline__ float gap2(const GridParams& g, int a, float q, int lo, int r) {
-    const float o = sel3f(a, g.o[0], g.o[1], g.o[2]), h = sel3f(a, g.h[0], g.h[1], g.h[2]), dl = sel3f(a, g.delta[0], g.delta[1], g.delta[2]);
-    const float L = (o + (float)lo * h) - dl;
-    const float U = (o + (float)(lo + (1 << r)) * h) + dl;
-    const float t = q < L ? psub(L, q) : (q > U ? psub(q, U) : 0.0f);
-    return pmul(t, t);
-}
-
-// Exact nearest neighbour by depth-first descent of the implicit tree (grid.cu): near child first,
-// far child only if its box bound does not exceed the best distance so far ('>' keeps equal bounds
-// alive so that an equally distant point with a lower index is still found).
-template <bool COLOR>
-__device__ void tree_search(const GridParams& g, const unsigned int* __restrict__ cs, const float4* __restrict__ pts,
-                            const float4* __restrict__ nrm, const Query& q, Best& b, unsigned int& evals, unsigned int& nodes) {
-    const int T = g.T;
-    const unsigned int s0 = __ldg(&cs[0]), e0 = __ldg(&cs[1u << T]);
-    if (e0 == s0) return;
-    int lo0 = 0, lo1 = 0, lo2 = 0, r0 = g.bits[0], r1 = g.bits[1], r2 = g.bits[2];
-    float t0 = gap2(g, 0, q.x, 0, r0), t1 = gap2(g, 1, q.y, 0, r1), t2 = gap2(g, 2, q.z, 0, r2);
-    ++nodes;
-    if (padd(padd(t0, t1), t2) > b.d) return;
-    if (e0 - s0 <= ICP_LEAF_MAX || T == 0) { scan_range<COLOR>(pts, nrm, s0, e0, q, b, evals); return; }
-    int d = 0, stage = 0, from = 0; unsigned int p = 0; bool asc = false;
-    for (;;) {
-        const int a = (int)((g.axis_seq >> (2 * d)) & 3ull);
-        const int lo = sel3i(a, lo0, lo1, lo2), r = sel3i(a, r0, r1, r2) - 1;
-        const float qa = sel3f(a, q.x, q.y, q.z);
-        const float plane = sel3f(a, g.o[0], g.o[1], g.o[2]) + (float)(lo + (1 << r)) * sel3f(a, g.h[0], g.h[1], g.h[2]);
-        const int nb = qa >= plane ? 1 : 0;                 // visiting order only; any choice is correct
-        if (asc) { stage = (from == nb) ? 1 : 2; asc = false; }
-        if (stage == 2) {                                   // both children done: ascend
-            if (d == 0) break;
-            from = (int)(p & 1u); --d; p >>= 1;
-            const int a2 = (int)((g.axis_seq >> (2 * d)) & 3ull);
-            const int rc = sel3i(a2, r0, r1, r2), lc = sel3i(a2, lo0, lo1, lo2);
-            const int lp = lc - (from ? (1 << rc) : 0), rp = rc + 1;
-            const float tp = gap2(g, a2, sel3f(a2, q.x, q.y, q.z), lp, rp);
-            if (a2 == 0) { lo0 = lp; r0 = rp; t0 = tp; } else if (a2 == 1) { lo1 = lp; r1 = rp; t1 = tp; } else { lo2 = lp; r2 = rp; t2 = tp; }
-            asc = true;
-            continue;
-        }
-        const int bch = stage == 0 ? nb : (nb ^ 1);
-        ++stage;
-        const int lc = lo + (bch ? (1 << r) : 0);
-        const float tc = gap2(g, a, qa, lc, r);
-        const float lb = padd(padd(a == 0 ? tc : t0, a == 1 ? tc : t1), a == 2 ? tc : t2);
-        ++nodes;
-        if (lb > b.d) continue;
-        const unsigned int c = 2u * p + (unsigned int)bch; const int sh = T - d - 1;
-        const unsigned int ns = __ldg(&cs[c << sh]), ne = __ldg(&cs[(c + 1u) << sh]);
-        if (ne == ns) continue;
-        if (ne - ns <= ICP_LEAF_MAX || d + 1 == T) { scan_range<COLOR>(pts, nrm, ns, ne, q, b, evals); continue; }
-        if (a == 0) { lo0 = lc; r0 = r; t0 = tc; } else if (a == 1) { lo1 = lc; r1 = r; t1 = tc; } else { lo2 = lc; r2 = r; t2 = tc; }
-        ++d; p = c; stage = 0;
-    }
 }
 
 // x86-64 gcc semantics of `unsigned = std::round(float)` (NearestNeighbor.h:378-379): cvttss2si to
@@ -450,8 +380,7 @@ __global__ void __launch_bounds__(ICP_TILE) knn_tile_kernel(const MatchArgs a) {
             else defer = true;
         }
     }
-    // Unresolved queries go to the packet kernel: one contiguous, warp-padded run per tile, so that a
-    // packet (32 consecutive entries) only holds queries of one compact tile.
+    // Unresolved queries go to the BVH kernel (one atomic per tile)
     {
         const unsigned int m = __ballot_sync(0xFFFFFFFFu, defer);
         if (lane == 0) sm.warp_sums[wid] = (unsigned int)__popc(m);
@@ -460,12 +389,9 @@ __global__ void __launch_bounds__(ICP_TILE) knn_tile_kernel(const MatchArgs a) {
 #pragma unroll
         for (int w = 0; w < ICP_TILE / 32; ++w) { const unsigned int v = sm.warp_sums[w]; if (w < wid) before += v; tot += v; }
         if (tot > 0) {                                        // block-uniform
-            const unsigned int padded = (tot + 31u) & ~31u;
-            if (tid == 0) sm.count = atomicAdd(&a.state->n_deferred[it], padded);
+            if (tid == 0) sm.count = atomicAdd(&a.state->n_deferred[it], tot);
             __syncthreads();
-            const unsigned int base = sm.count;
-            if (defer) a.deferred[base + before + (unsigned int)__popc(m & ((1u << lane) - 1u))] = p;
-            if ((unsigned int)tid < padded - tot) a.deferred[base + tot + tid] = -1;
+            if (defer) a.deferred[sm.count + before + (unsigned int)__popc(m & ((1u << lane) - 1u))] = p;
             nd = defer ? 1u : 0u;
         }
     }
@@ -477,119 +403,106 @@ __global__ void __launch_bounds__(ICP_TILE) knn_tile_kernel(const MatchArgs a) {
     }
 }
 
-#define PACKET_LEAF 32   // a node with <= this many points is scanned by the packet, not split
+// ---------------------------------------------------------------------------- BVH search, one warp per query
+#define BVH_WARPS 4
+#define BVH_STACK (32 * ICP_BVH_MAX_LEVELS)   // <= 32 pushed children per level below the top
 
-// Packet traversal: the 32 lanes of a warp hold 32 queries of one tile and walk the implicit tree
-// TOGETHER (uniform control flow, cell-table reads shared by the warp).  A node is entered when ANY lane
-// still needs it; every lane keeps its own per-axis gaps and its own best, and scans a leaf only if its
-// own bound admits it (leaf points are read at the same address by all lanes: one broadcast transaction).
-template <bool COLOR>
-__device__ void tree_search_packet(const GridParams& g, const unsigned int* __restrict__ cs, const float4* __restrict__ pts,
-                                   const float4* __restrict__ nrm, const Query& q, bool active, Best& b, unsigned int& evals,
-                                   unsigned int& nodes) {
+// fp32 lower bound (under D1's rounding and association, by monotonicity) of the squared distance from q
+// to any point inside the box
+__device__ __forceinline__ float box_dist2(const Query& q, const float4 lo, const float4 hi) {
+    const float gx = fmaxf(fmaxf(psub(lo.x, q.x), psub(q.x, hi.x)), 0.0f);
+    const float gy = fmaxf(fmaxf(psub(lo.y, q.y), psub(q.y, hi.y)), 0.0f);
+    const float gz = fmaxf(fmaxf(psub(lo.z, q.z), psub(q.z, hi.z)), 0.0f);
+    return padd(padd(pmul(gx, gx), pmul(gy, gy)), pmul(gz, gz));
+}
+
+// The warp walks the 32-ary tree depth-first with an explicit stack: one step tests the 32 children of a
+// node in parallel (lane = child, one coalesced 1 KB read of tight boxes), a leaf is scanned by the 32
+// lanes in parallel (lane = point, one coalesced 512 B read).  ALL = every sorted-source point p is a
+// query (grid-stride); otherwise the queries come from the tile kernel's deferred list.
+template <bool COLOR, bool ALL>
+__global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs a) {
+    __shared__ PoseSm sm;
+    __shared__ unsigned int s_node[BVH_WARPS][BVH_STACK];
+    __shared__ float s_lb[BVH_WARPS][BVH_STACK];
+    load_pose(sm, a.state_ro);
     const unsigned int FULL = 0xFFFFFFFFu;
-    const int T = g.T;
-    const unsigned int s0 = __ldg(&cs[0]), e0 = __ldg(&cs[1u << T]);
-    if (e0 == s0) return;
-    const unsigned int act = __ballot_sync(FULL, active);
-    if (!act) return;
-    const int half = __popc(act) >> 1;
-    int lo0 = 0, lo1 = 0, lo2 = 0, r0 = g.bits[0], r1 = g.bits[1], r2 = g.bits[2];
-    float t0 = gap2(g, 0, q.x, 0, r0), t1 = gap2(g, 1, q.y, 0, r1), t2 = gap2(g, 2, q.z, 0, r2);
-    ++nodes;
-    bool need = active && !(padd(padd(t0, t1), t2) > b.d);
-    if (!__any_sync(FULL, need)) return;
-    if (e0 - s0 <= PACKET_LEAF || T == 0) { if (need) scan_range<COLOR>(pts, nrm, s0, e0, q, b, evals); return; }
-    int d = 0, stage = 0, from = 0; unsigned int p = 0; bool asc = false;
-    for (;;) {
-        const int a = (int)((g.axis_seq >> (2 * d)) & 3ull);
-        const int lo = sel3i(a, lo0, lo1, lo2), r = sel3i(a, r0, r1, r2) - 1;
-        const float qa = sel3f(a, q.x, q.y, q.z);
-        const float plane = sel3f(a, g.o[0], g.o[1], g.o[2]) + (float)(lo + (1 << r)) * sel3f(a, g.h[0], g.h[1], g.h[2]);
-        // visiting order only (any choice is correct): the side most of the packet's queries are on
-        const int nb = __popc(__ballot_sync(FULL, active && qa >= plane)) > half ? 1 : 0;
-        if (asc) { stage = (from == nb) ? 1 : 2; asc = false; }
-        if (stage == 2) {                                   // both children done: ascend
-            if (d == 0) break;
-            from = (int)(p & 1u); --d; p >>= 1;
-            const int a2 = (int)((g.axis_seq >> (2 * d)) & 3ull);
-            const int rc = sel3i(a2, r0, r1, r2), lc = sel3i(a2, lo0, lo1, lo2);
-            const int lp = lc - (from ? (1 << rc) : 0), rp = rc + 1;
-            const float tp = gap2(g, a2, sel3f(a2, q.x, q.y, q.z), lp, rp);
-            if (a2 == 0) { lo0 = lp; r0 = rp; t0 = tp; } else if (a2 == 1) { lo1 = lp; r1 = rp; t1 = tp; } else { lo2 = lp; r2 = rp; t2 = tp; }
-            asc = true;
+    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
+    const IterDesc d = a.desc[it];
+    const int n = ALL ? a.n_src : (int)a.state_ro->n_deferred[it];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned int n_finite = __ldg(&a.cell_start[1u << a.grid->T]);
+    const BvhDesc& bvh = a.bvh;
+    const int top_level = bvh.n_levels - 1;
+    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
+    unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        const int p = ALL ? k : a.deferred[k];
+        Query q; float snx, sny, snz; unsigned int s_rgba;
+        if (!prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {            // warp-uniform
+            if (ALL && lane == 0) write_no_query(a, p);
             continue;
         }
-        const int bch = stage == 0 ? nb : (nb ^ 1);
-        ++stage;
-        const int lc = lo + (bch ? (1 << r) : 0);
-        const float tc = gap2(g, a, qa, lc, r);
-        const float lb = padd(padd(a == 0 ? tc : t0, a == 1 ? tc : t1), a == 2 ? tc : t2);
-        ++nodes;
-        need = active && !(lb > b.d);
-        if (!__any_sync(FULL, need)) continue;
-        const unsigned int c = 2u * p + (unsigned int)bch; const int sh = T - d - 1;
-        const unsigned int ns = __ldg(&cs[c << sh]), ne = __ldg(&cs[(c + 1u) << sh]);
-        if (ne == ns) continue;
-        if (ne - ns <= PACKET_LEAF || d + 1 == T) { if (need) scan_range<COLOR>(pts, nrm, ns, ne, q, b, evals); continue; }
-        if (a == 0) { lo0 = lc; r0 = r; t0 = tc; } else if (a == 1) { lo1 = lc; r1 = r; t1 = tc; } else { lo2 = lc; r2 = r; t2 = tc; }
-        ++d; p = c; stage = 0;
-    }
-}
-
-// The queries the tile kernel deferred, one packet (warp) per 32 list entries.
-template <bool COLOR>
-__global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_packet_kernel(const MatchArgs a) {
-    __shared__ PoseSm sm;
-    load_pose(sm, a.state_ro);
-    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
-    const IterDesc d = a.desc[it];
-    const int n = (int)a.state_ro->n_deferred[it];             // multiple of 32
-    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-    const GridParams g = *a.grid;
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32 < n; w += warps) {
-        const int p = a.deferred[w * 32 + lane];
-        Query q; float snx = 0.f, sny = 0.f, snz = 0.f; unsigned int s_rgba = 0;
-        bool active = p >= 0 && prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba);
-        Best b; b.d = -1.f; b.idx = INT_MAX; b.pos = -1;
-        if (active) seed_best<COLOR>(a, q, p, b);
-        else { q.x = q.y = q.z = __int_as_float(0x7fc00000); q.cr = q.cg = q.cb = 0.f; }
-        tree_search_packet<COLOR>(g, a.cell_start, a.tgt_pts, a.tgt_nrm, q, active, b, ev, nd);
-        if (active) {
+        if (ALL && lane == 0) ++nq;
+        Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
+        if (finite3(q.x, q.y, q.z) && n_finite > 0u) {
+            seed_best<COLOR>(a, q, p, b);                                       // uniform: every lane starts from the seed
+            float bound = b.d;
+            int top = 0;
+            if (lane == 0) { st_node[0] = (unsigned int)top_level << 27; st_lb[0] = 0.0f; }
+            top = 1;
+            __syncwarp();
+            while (top > 0) {
+                --top;
+                const unsigned int nd_id = st_node[top]; const float nlb = st_lb[top];
+                __syncwarp();
+                if (nlb > bound) continue;
+                const int lvl = (int)(nd_id >> 27), j = (int)(nd_id & 0x7FFFFFFu);
+                if (lane == 0) ++nd;
+                if (lvl == 0) {
+                    // leaf j: lane = point
+                    const unsigned int i = (unsigned int)j * 32u + lane;
+                    if (i < n_finite) {
+                        const float4 c = __ldg(&a.tgt_pts[i]);
+                        const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
+                        const int idx = __float_as_int(c.w);
+                        if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                        ++ev;
+                    }
+                    bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));   // d >= 0: bit order = value order
+                    continue;
+                }
+                // internal node: lane = child
+                const int cl = lvl - 1, c = j * 32 + lane;
+                float clb = FLT_BIG; bool keep = false;
+                if (c < bvh.count[cl]) {
+                    const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c) + 1]);
+                    clb = box_dist2(q, lo, hi);
+                    keep = !(clb > bound);                                       // NaN-free: empty boxes give +inf
+                }
+                // push far children first and the children that contain q last (popped first)
+                const bool near = keep && clb == 0.0f, far = keep && clb > 0.0f;
+                const unsigned int mf = __ballot_sync(FULL, far), mn = __ballot_sync(FULL, near);
+                const unsigned int lt = (1u << lane) - 1u;
+                if (far) { const int s = top + __popc(mf & lt); st_node[s] = ((unsigned int)cl << 27) | (unsigned int)c; st_lb[s] = clb; }
+                top += __popc(mf);
+                if (near) { const int s = top + __popc(mn & lt); st_node[s] = ((unsigned int)cl << 27) | (unsigned int)c; st_lb[s] = clb; }
+                top += __popc(mn);
+                __syncwarp();
+            }
+            // warp arg-min on (d, idx)
+            const unsigned int dmin = __reduce_min_sync(FULL, __float_as_uint(b.d));
+            const int cand = (__float_as_uint(b.d) == dmin) ? b.idx : INT_MAX;
+            const int imin = __reduce_min_sync(FULL, cand);
+            const unsigned int who = __ballot_sync(FULL, cand == imin);
+            const int src_lane = __ffs((int)who) - 1;
+            b.d = __uint_as_float(dmin); b.idx = imin; b.pos = __shfl_sync(FULL, b.pos, src_lane);
+            if (b.idx == INT_MAX) b.pos = -1;
+        }
+        if (lane == 0) {
             a.nn_pos[p] = b.pos;
             finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
-        }
-    }
-    flush_stats(a, nq, nm, ev, nd);
-}
-
-// One thread per query: all queries (LIST = false, grid-stride over the sorted source) or the
-// queries the tile kernel deferred (LIST = true), seeded with the best candidate found so far.
-template <bool COLOR, bool LIST>
-__global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_tree_kernel(const MatchArgs a) {
-    __shared__ PoseSm sm;
-    load_pose(sm, a.state_ro);
-    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
-    const IterDesc d = a.desc[it];
-    const int n = LIST ? (int)a.state_ro->n_deferred[it] : a.n_src;
-    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-    const GridParams g = *a.grid;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int p = LIST ? a.deferred[k] : k;
-        Query q; float snx, sny, snz; unsigned int s_rgba;
-        if (prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {
-            if (!LIST) ++nq;
-            Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
-            if (finite3(q.x, q.y, q.z)) {
-                seed_best<COLOR>(a, q, p, b);
-                tree_search<COLOR>(g, a.cell_start, a.tgt_pts, a.tgt_nrm, q, b, ev, nd);
-                a.nn_pos[p] = b.pos;
-            }
-            finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
-        } else if (!LIST) {
-            write_no_query(a, p);
         }
     }
     flush_stats(a, nq, nm, ev, nd);
@@ -684,17 +597,18 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
         ++launches;
     } else if (algorithm == 3) {
-        const int nb = (a.n_src + T - 1) / T;
-        if (a.color_icp) knn_tree_kernel<true, false><<<nb, T, 0, s>>>(a); else knn_tree_kernel<false, false><<<nb, T, 0, s>>>(a);
+        int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
+        if (nb > 64 * n_sms) nb = 64 * n_sms;
+        if (a.color_icp) knn_bvh_kernel<true, true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, true><<<nb, BVH_WARPS * 32, 0, s>>>(a);
         ++launches;
     } else {
         if (a.n_tiles > 0) {
             if (a.color_icp) knn_tile_kernel<true><<<a.n_tiles, ICP_TILE, 0, s>>>(a); else knn_tile_kernel<false><<<a.n_tiles, ICP_TILE, 0, s>>>(a);
             ++launches;
-            int nb = (a.n_src / 2 + 3) / 4;                      // deferred queries: one warp per packet, grid-stride over the list
-            if (nb > 16 * n_sms) nb = 16 * n_sms;
+            int nb = (a.n_src / 4 + BVH_WARPS - 1) / BVH_WARPS;      // deferred queries: one warp each, grid-stride over the list
+            if (nb > 32 * n_sms) nb = 32 * n_sms;
             if (nb < 1) nb = 1;
-            if (a.color_icp) knn_packet_kernel<true><<<nb, T, 0, s>>>(a); else knn_packet_kernel<false><<<nb, T, 0, s>>>(a);
+            if (a.color_icp) knn_bvh_kernel<true, false><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
             ++launches;
         }
     }
