@@ -287,15 +287,14 @@ def main():
             "e2e": {"value": regs / (e2e_ms * 1e-3), "unit": "reg/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int((ns + nt) * 28 + 64 + 32 * N_ITER), "d2h_bytes_per_step": int(64 + 16 * 4 * N_ITER + 1024)},
             "gpu_launches": launches,
-            "roofline": {"kernel": "knn_tile_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "knn_bvh_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": match_ms,
-                         "note": "latency/issue-bound tree search, clouds are L2-resident; see roofline_fp32"},
-            "roofline_fp32": {"kernel": "knn_tile_kernel<false>", "distance_evals_per_launch": evals_per_launch,
+                         "note": "issue-bound tree search over L2-resident clouds; see roofline_fp32"},
+            "roofline_fp32": {"kernel": "knn_bvh_kernel<false>", "distance_evals_per_launch": evals_per_launch,
                               "gevals_per_s": evals_per_launch / (match_ms * 1e-3) / 1e9, "flop_per_eval": 8,
                               "tflops": evals_per_launch * 8 / (match_ms * 1e-3) / 1e12, "nodes_per_launch": st_t.n_nodes_visited / N_ITER,
-                              "deferred_queries_per_launch": st_t.n_deferred / N_ITER, "block_staged_points_per_launch": st_t.n_points_staged / N_ITER,
-                              "tiles": st_t.n_tiles, "matched_per_launch": st_t.n_matched / N_ITER},
+                              "matched_per_launch": st_t.n_matched / N_ITER},
             "stage_ms_per_iteration": {"match": match_ms, "reduce_solve": solve_ms, "index_build": tm.index_ms},
             "clocks": clocks,
             "pose_checksum": float(np.abs(pose).sum()),

@@ -46,8 +46,7 @@ class Timings(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_queries", C.c_uint64), ("n_matched", C.c_uint64), ("n_distance_evals", C.c_uint64),
-                ("n_nodes_visited", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("n_points_staged", C.c_uint64),
-                ("n_deferred", C.c_uint64), ("n_tiles", C.c_uint64)]
+                ("n_nodes_visited", C.c_uint64), ("n_kernel_launches", C.c_uint64)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -77,15 +77,13 @@ struct icp_gpu_ctx {
     std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
     bool src_rank_valid = false;
     // target grid
-    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box;
-    BvhDesc bvh;
+    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box, bvh_desc, leaf_start;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
-    // source grid (only its sort order and tiles are used) and tiles
-    DeviceBuf sgrid, scell_start, tiles, n_tiles_dev, order_dev;
-    int Ts = 0, n_tiles = 0;
-    unsigned int* h_n_tiles = nullptr;   // pinned
+    // source grid: only its sort order is used (consecutive queries are spatial neighbours: coherent tree walks)
+    DeviceBuf sgrid, scell_start, order_dev;
+    int Ts = 0;
     // loop state
-    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, deferred, partials, pose_dev, history;
+    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, partials, pose_dev, history;
     float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
     IterDesc* h_desc = nullptr;                                                       // pinned, DESC_TOTAL
     int n_reduce_blocks = 1;
@@ -146,7 +144,6 @@ int choose_algorithm(const icp_gpu_ctx* c) {   // 0 grid, 1 brute, 2 projective
     if (c->cfg.matching == ICP_GPU_MATCH_PROJECTIVE) return 2;
     if (c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE) return 1;
     if (c->cfg.nn_algorithm == ICP_GPU_NN_GRID) return 0;
-    if (c->cfg.nn_algorithm == ICP_GPU_NN_TREE) return 3;
     return c->n_tgt <= 2048 ? 1 : 0;
 }
 
@@ -181,9 +178,12 @@ int build_grid(icp_gpu_ctx* ctx) {
     const int n = ctx->n_tgt;
     ctx->T = pick_T(n);
     const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->T) + 1;
+    const size_t scan_len = cells1 > n1 + 2 ? cells1 : n1 + 2;
     if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) ||
-        ensure(ctx, ctx->keys, n1 * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->cell_start, cells1 * 4) ||
-        ensure(ctx, ctx->block_sums, (cells1 / 4096 + 2) * 4) || ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64))
+        ensure(ctx, ctx->keys, (n1 + 2) * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->cell_start, cells1 * 4) ||
+        ensure(ctx, ctx->block_sums, (scan_len / 4096 + 2) * 4) || ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64) ||
+        ensure(ctx, ctx->leaf_start, (n1 + 2) * 4) || ensure(ctx, ctx->bvh_desc, sizeof(BvhDesc)) ||
+        ensure(ctx, ctx->bvh_box, icp_bvh_max_nodes(n) * 2 * sizeof(float4)))
         return ICP_GPU_E_CUDA;
     int launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -191,35 +191,30 @@ int build_grid(icp_gpu_ctx* ctx) {
                              (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
                              (unsigned int*)ctx->cell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->tgt_pts_sorted.p,
                              (float4*)ctx->tgt_nrm_sorted.p, 0, ctx->stream, &launches));
-    icp_bvh_layout(n, &ctx->bvh);
-    const size_t n_nodes = (size_t)ctx->bvh.offset[ctx->bvh.n_levels - 1] + (size_t)ctx->bvh.count[ctx->bvh.n_levels - 1];
-    if (ensure(ctx, ctx->bvh_box, n_nodes * 2 * sizeof(float4))) return ICP_GPU_E_CUDA;
-    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, (const unsigned int*)ctx->cell_start.p + ((size_t)1 << ctx->T), ctx->bvh,
-                            (float4*)ctx->bvh_box.p, ctx->stream, &launches));
+    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, n, (const GridParams*)ctx->grid.p, (const unsigned int*)ctx->cell_start.p, ctx->T,
+                            (unsigned int*)ctx->keys.p, (unsigned int*)ctx->block_sums.p, (unsigned int*)ctx->leaf_start.p,
+                            (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ctx->stream, &launches));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     ctx->grid_built = true;
     return 0;
 }
 
-// Sorts the source into the cell order of its own grid and cuts it into spatially compact tiles.
+// Sorts the source into the cell order of its own grid (Morton order).
 int build_source(icp_gpu_ctx* ctx) {
     const int n = ctx->n_src;
     ctx->Ts = pick_T(n);
     const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->Ts) + 1;
     if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4)) ||
-        ensure(ctx, ctx->keys, n1 * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->scell_start, cells1 * 4) ||
-        ensure(ctx, ctx->block_sums, (cells1 / 4096 + 2) * 4) || ensure(ctx, ctx->sgrid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64) ||
-        ensure(ctx, ctx->tiles, n1 * sizeof(int2)) || ensure(ctx, ctx->n_tiles_dev, 64))
+        ensure(ctx, ctx->keys, (n1 + 2) * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->scell_start, cells1 * 4) ||
+        ensure(ctx, ctx->block_sums, ((cells1 > n1 + 2 ? cells1 : n1 + 2) / 4096 + 2) * 4) || ensure(ctx, ctx->sgrid, sizeof(GridParams)) ||
+        ensure(ctx, ctx->bbox, 64))
         return ICP_GPU_E_CUDA;
     int launches = 0;
     CU(icp_launch_grid_build((const float4*)ctx->src_raw_pts.p, (const float4*)ctx->src_raw_nrm.p, n, ctx->Ts, (GridParams*)ctx->sgrid.p,
                              (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
                              (unsigned int*)ctx->scell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->src_pts.p,
                              (float4*)ctx->src_nrm.p, 1, ctx->stream, &launches));
-    CU(icp_launch_make_tiles((const unsigned int*)ctx->scell_start.p, ctx->Ts, n, (int2*)ctx->tiles.p, (unsigned int*)ctx->n_tiles_dev.p,
-                             ctx->stream, &launches));
-    CU(cudaMemcpyAsync(ctx->h_n_tiles, ctx->n_tiles_dev.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     return 0;
 }
@@ -256,13 +251,9 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
     }
     // a new cloud invalidates the neighbours remembered from earlier searches
     if (ctx->n_src > 0 && ctx->nn_pos.p) { CU(icp_launch_fill_int((int*)ctx->nn_pos.p, ctx->n_src, -1, ctx->stream)); ctx->stats.n_kernel_launches += 1; }
-    // Host arrays are only borrowed for the duration of the call, and the tile count is needed to size
-    // launches: wait.  (The target's device-pointer form stays asynchronous.)
-    if (!dev || !target) CU(cudaStreamSynchronize(ctx->stream));
-    if (!target) {
-        ctx->n_tiles = (int)*ctx->h_n_tiles;
-        if (ensure(ctx, ctx->deferred, (size_t)(n > 0 ? n : 1) * 4)) return ICP_GPU_E_CUDA;
-    }
+    // Host arrays are only borrowed for the duration of the call: wait for the copies.  The device-pointer
+    // forms stay asynchronous (stream-ordered with everything that follows).
+    if (!dev) CU(cudaStreamSynchronize(ctx->stream));
     return ICP_GPU_OK;
 }
 
@@ -352,22 +343,21 @@ int check_ready(icp_gpu_ctx* ctx) {
 
 void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, bool want_idx) {
     memset(&a, 0, sizeof(a));
-    const bool grid_order = (algo == 0 || algo == 3);
+    const bool grid_order = (algo == 0);
     a.src_pts = (const float4*)c->src_pts.p; a.src_nrm = (const float4*)c->src_nrm.p; a.n_src = c->n_src;
-    a.tiles = (const int2*)c->tiles.p; a.n_tiles = c->n_tiles;
     a.mask = (const unsigned int*)c->mask.p; a.desc = (const IterDesc*)c->desc.p;
     a.state_ro = (const DevState*)c->state.p; a.state = (DevState*)c->state.p;
     a.grid = (const GridParams*)c->grid.p; a.cell_start = (const unsigned int*)c->cell_start.p;
     a.tgt_pts = (const float4*)(grid_order ? c->tgt_pts_sorted.p : c->tgt_pts.p);
     a.tgt_nrm = (const float4*)(grid_order ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
     a.n_tgt = c->n_tgt;
-    a.bvh_box = (const float4*)c->bvh_box.p; a.bvh = c->bvh;
+    a.bvh_box = (const float4*)c->bvh_box.p; a.bvh = (const BvhDesc*)c->bvh_desc.p; a.leaf_start = (const unsigned int*)c->leaf_start.p;
     if (c->have_camera) { a.fx = c->K[0]; a.fy = c->K[4]; a.cx = c->K[6]; a.cy = c->K[7]; }   // column-major Matrix3f
     a.width = c->width; a.height = c->height;
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
     a.max_d2 = c->cfg.max_distance_sq;
     a.match_pos = (int*)c->match_pos.p; a.match_w = (float*)c->match_w.p; a.match_idx = want_idx ? (int*)c->match_idx.p : nullptr;
-    a.nn_pos = (int*)c->nn_pos.p; a.deferred = (int*)c->deferred.p;
+    a.nn_pos = (int*)c->nn_pos.p;
     a.desc_index = desc_index;
     a.use_seed = grid_order ? 1 : 0;
     a.collect_stats = c->cfg.collect_stats;
@@ -375,7 +365,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
 
 void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     memset(&r, 0, sizeof(r));
-    const bool grid_order = (algo == 0 || algo == 3);
+    const bool grid_order = (algo == 0);
     r.src_pts = (const float4*)c->src_pts.p; r.src_nrm = (const float4*)c->src_nrm.p; r.n_src = c->n_src;
     r.state = (DevState*)c->state.p;
     r.tgt_pts = (const float4*)(grid_order ? c->tgt_pts_sorted.p : c->tgt_pts.p);
@@ -441,7 +431,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         key.push_back(ctx->n_src); key.push_back(ctx->n_tgt); key.push_back(ctx->T); key.push_back(ctx->width); key.push_back(ctx->height);
         for (int k = 0; k < 9; ++k) key.push_back((long long)__float_as_int_host(ctx->have_camera ? ctx->K[k] : 0.f));
         key.push_back((long long)(uintptr_t)ctx->mask.p); key.push_back((long long)(uintptr_t)ctx->stream);
-        key.push_back(ctx->n_tiles); key.push_back(plan.n_iters);
+        key.push_back(plan.n_iters);
         if (!ctx->graph_exec || key != ctx->graph_key) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -481,9 +471,8 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         float idx_ms = 0.f;
         if (ctx->grid_built && cudaEventElapsedTime(&idx_ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->index_ms = idx_ms; else cudaGetLastError();
         timings->total_ms = tot; timings->index_ms = ctx->index_ms; timings->n_iterations = plan.n_iters;
-        const int per_match = algo == 0 ? 2 : 1;
-        timings->n_match_launches = plan.n_iters * per_match;
-        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters * per_match;
+        timings->n_match_launches = plan.n_iters;
+        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters;
         for (auto& e : marks) cudaEventDestroy(e);
     }
     return ICP_GPU_OK;
@@ -493,7 +482,6 @@ void copy_counters(icp_gpu_ctx* ctx) {
     const DevState& st = *ctx->h_state;
     ctx->stats.n_queries = st.n_queries; ctx->stats.n_matched = st.n_matched;
     ctx->stats.n_distance_evals = st.n_evals; ctx->stats.n_nodes_visited = st.n_nodes;
-    ctx->stats.n_points_staged = st.n_staged; ctx->stats.n_deferred = st.n_deferred_total; ctx->stats.n_tiles = (uint64_t)ctx->n_tiles;
 }
 
 int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out) {
@@ -558,7 +546,6 @@ int icp_gpu_create(icp_gpu_ctx** out, int device) {
     ok = ok && cudaMallocHost((void**)&ctx->h_history, 16 * sizeof(float) * ICP_MAX_ITERS) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_state, sizeof(DevState)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_desc, sizeof(IterDesc) * DESC_TOTAL) == cudaSuccess;
-    ok = ok && cudaMallocHost((void**)&ctx->h_n_tiles, 64) == cudaSuccess;
     ok = ok && ensure(ctx, ctx->state, sizeof(DevState)) == 0 && ensure(ctx, ctx->desc, sizeof(IterDesc) * DESC_TOTAL) == 0 &&
          ensure(ctx, ctx->pose_dev, 64) == 0 && ensure(ctx, ctx->history, 16 * sizeof(float) * ICP_MAX_ITERS) == 0 &&
          ensure(ctx, ctx->mask, 256) == 0;
@@ -576,14 +563,13 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     DeviceBuf* bufs[] = {&ctx->stage, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
-                         &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->tiles, &ctx->n_tiles_dev, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->deferred, &ctx->bvh_box};
+                         &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
-    if (ctx->h_n_tiles) cudaFreeHost(ctx->h_n_tiles);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -616,7 +602,7 @@ int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
     if (c->selection < 0 || c->selection > 1) return fail(ctx, ICP_GPU_E_ARG, "selection %d", c->selection);
     if (c->selection_rng < 0 || c->selection_rng > 1) return fail(ctx, ICP_GPU_E_ARG, "selection_rng %d", c->selection_rng);
     if (c->weighting < 0 || c->weighting > 3) return fail(ctx, ICP_GPU_E_ARG, "weighting %d", c->weighting);
-    if (c->nn_algorithm < 0 || c->nn_algorithm > 3) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
+    if (c->nn_algorithm < 0 || c->nn_algorithm > 2) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
     if (c->pyramid_mode != ICP_GPU_PYRAMID_STRIDE) return fail(ctx, ICP_GPU_E_ARG, "pyramid_mode %d", c->pyramid_mode);
     if (c->n_iterations < 0 || c->n_iterations > ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "n_iterations %d (max %d)", c->n_iterations, ICP_MAX_ITERS);
     if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);

@@ -191,6 +191,15 @@ __global__ void scan_apply_kernel(unsigned int* __restrict__ data, int n, const 
     for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; if (i < n) data[i] = ex; ex += v[k]; }
 }
 
+static cudaError_t launch_exclusive_scan(unsigned int* data, int n, unsigned int* block_sums, cudaStream_t s, int* launches) {
+    const int n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(data, n, block_sums);
+    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(block_sums, n_tiles);
+    scan_apply_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(data, n, block_sums);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------- scatter into cell order
 __global__ void scatter_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n,
                                const unsigned int* __restrict__ keys, const unsigned int* __restrict__ ranks,
@@ -209,54 +218,6 @@ __global__ void scatter_kernel(const float4* __restrict__ pts, const float4* __r
     }
     pts_sorted[pos] = pts[i];                        // .w already holds the original index: tie-break + API output
     nrm_sorted[pos] = nrm[i];
-}
-
-// ---------------------------------------------------------------------------- source tiles
-// A tile is a node of the implicit tree with <= ICP_TILE points whose parent has more (or a chunk of an
-// over-full finest cell): a run of the sorted source that lies in ONE axis-aligned box of the source grid,
-// so the transformed queries of a tile stay spatially compact under any rigid pose.
-__global__ void make_tiles_kernel(const unsigned int* __restrict__ cs, int T, int n, int2* __restrict__ tiles,
-                                  unsigned int* __restrict__ n_tiles) {
-    const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long n_nodes = (2ull << T) - 1ull;
-    if (id < n_nodes) {
-        const int d = 63 - __clzll((long long)(id + 1ull));
-        const unsigned int p = (unsigned int)(id + 1ull - (1ull << d));
-        const int sh = T - d;
-        const unsigned int s = cs[(size_t)p << sh], e = cs[((size_t)p + 1) << sh];
-        const unsigned int cnt = e - s;
-        if (cnt == 0u) return;
-        bool parent_big = true;
-        if (d > 0) { const unsigned int pp = p >> 1; parent_big = cs[((size_t)pp + 1) << (sh + 1)] - cs[(size_t)pp << (sh + 1)] > (unsigned int)ICP_TILE; }
-        if (!parent_big) return;
-        if (cnt <= (unsigned int)ICP_TILE) {
-            tiles[atomicAdd(n_tiles, 1u)] = make_int2((int)s, (int)cnt);
-        } else if (d == T) {
-            const unsigned int chunks = (cnt + ICP_TILE - 1) / ICP_TILE;
-            const unsigned int base = atomicAdd(n_tiles, chunks);
-            for (unsigned int c = 0; c < chunks; ++c)
-                tiles[base + c] = make_int2((int)(s + c * ICP_TILE), (int)min((unsigned int)ICP_TILE, cnt - c * ICP_TILE));
-        }
-    } else if (id == n_nodes) {
-        // the non-finite bucket after the last cell: never queries, but every point needs its outputs written
-        const unsigned int s = cs[(size_t)1 << T];
-        if ((unsigned int)n > s) {
-            const unsigned int cnt = (unsigned int)n - s, chunks = (cnt + ICP_TILE - 1) / ICP_TILE;
-            const unsigned int base = atomicAdd(n_tiles, chunks);
-            for (unsigned int c = 0; c < chunks; ++c)
-                tiles[base + c] = make_int2((int)(s + c * ICP_TILE), (int)min((unsigned int)ICP_TILE, cnt - c * ICP_TILE));
-        }
-    }
-}
-
-cudaError_t icp_launch_make_tiles(const unsigned int* cell_start, int T, int n, int2* tiles, unsigned int* n_tiles_dev, cudaStream_t s,
-                                  int* n_launches) {
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(n_tiles_dev, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
-    const unsigned long long threads = (2ull << T);
-    make_tiles_kernel<<<(unsigned int)((threads + 255) / 256), 256, 0, s>>>(cell_start, T, n, tiles, n_tiles_dev);
-    if (n_launches) *n_launches += 1;
-    return cudaGetLastError();
 }
 
 __global__ void extract_order_kernel(const float4* __restrict__ pts_sorted, int n, int* __restrict__ order) {
@@ -278,55 +239,113 @@ cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------- BVH over the sorted cloud
-void icp_bvh_layout(int n, BvhDesc* out) {
-    BvhDesc b; memset(&b, 0, sizeof(b));
-    int cnt = (n + 31) / 32; if (cnt < 1) cnt = 1;
-    int off = 0, l = 0;
-    for (;;) {
-        b.count[l] = cnt; b.offset[l] = off; off += cnt; ++l;
-        if (cnt == 1 || l == ICP_BVH_MAX_LEVELS) break;
-        cnt = (cnt + 31) / 32;
+// Leaves = nodes of the implicit cell tree with <= 32 points whose parent has more (an over-full finest cell is
+// cut into runs of 32): cell-aligned, hence pairwise disjoint in space -- a search ball meets only the few
+// leaves around it, unlike fixed runs of the Z-curve, whose boxes straddle the curve's jumps.
+__global__ void mark_leaves_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
+                                   const unsigned int* __restrict__ cs, int T, unsigned int* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const unsigned int n_finite = cs[(size_t)1 << T];
+    if ((unsigned int)i >= n_finite) { flags[i] = 0u; return; }
+    const GridParams g = *gp;
+    const float4 p = pts[i];
+    const unsigned int c = cell_code(g, p.x, p.y, p.z);
+    // smallest depth whose node holds <= 32 points (the count is monotone in the depth)
+    const unsigned int sT = cs[c], eT = cs[(size_t)c + 1];
+    if (eT - sT > 32u) { flags[i] = ((unsigned int)i - sT) % 32u == 0u ? 1u : 0u; return; }
+    int lo = 0, hi = T;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1, sh = T - mid;
+        const unsigned int pre = c >> sh;
+        const unsigned int cnt = cs[((size_t)pre + 1) << sh] - cs[(size_t)pre << sh];
+        if (cnt <= 32u) hi = mid; else lo = mid + 1;
     }
-    b.n_levels = l;
-    *out = b;
+    const int sh = T - lo;
+    flags[i] = (unsigned int)i == cs[(size_t)(c >> sh) << sh] ? 1u : 0u;
 }
 
-// one warp per node: level 0 reads 32 points, level l > 0 reads 32 child boxes; warp min/max; slots
-// beyond the last finite point (or beyond the last child) are empty: box = [+inf, -inf], never entered
-__global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ n_finite_dev, float4* __restrict__ box,
-                                 int level, int count, int offset, int child_count, int child_offset) {
-    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (node >= count) return;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (level == 0) {
-        const unsigned int i = (unsigned int)node * 32u + lane;
-        if (i < *n_finite_dev) { const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
-    } else {
-        const int c = node * 32 + lane;
-        if (c < child_count) {
-            const float4 a = box[2 * (size_t)(child_offset + c)], b = box[2 * (size_t)(child_offset + c) + 1];
-            lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; hi[0] = b.x; hi[1] = b.y; hi[2] = b.z;
+// flags have been exclusive-scanned in place: rank[i] = number of leaf starts before i
+__global__ void leaf_starts_kernel(const unsigned int* __restrict__ rank, int n, const unsigned int* __restrict__ cs, int T,
+                                   unsigned int* __restrict__ leaf_start, BvhDesc* __restrict__ bvh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int n_finite = cs[(size_t)1 << T];
+    if (i < n && (unsigned int)i < n_finite && rank[i + 1] != rank[i]) leaf_start[rank[i]] = (unsigned int)i;
+    if (i == 0) {
+        const int L = (int)rank[n_finite];
+        leaf_start[L] = n_finite;
+        BvhDesc b;
+        b.n_leaves = L;
+        int cnt = L > 0 ? L : 1, off = 0, l = 0;
+        for (;;) {
+            b.count[l] = cnt; b.offset[l] = off; off += cnt; ++l;
+            if (cnt == 1 || l == ICP_BVH_MAX_LEVELS) break;
+            cnt = (cnt + 31) / 32;
+        }
+        b.n_levels = l;
+        for (int k = l; k < ICP_BVH_MAX_LEVELS; ++k) { b.count[k] = 0; b.offset[k] = off; }
+        *bvh = b;
+    }
+}
+
+// one warp per node (grid-stride): level 0 reads the leaf's points, level l > 0 reads 32 child boxes; an empty
+// node gets the box [+inf, -inf], which no search enters
+__global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ leaf_start,
+                                 const BvhDesc* __restrict__ bvh, float4* __restrict__ box, int level) {
+    const BvhDesc b = *bvh;
+    if (level >= b.n_levels) return;
+    const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    const int count = b.count[level], offset = b.offset[level];
+    for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < count; node += warps) {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        if (level == 0) {
+            if (node < b.n_leaves) {
+                const unsigned int i = leaf_start[node] + lane;
+                if (i < leaf_start[node + 1]) { const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
+            }
+        } else {
+            const int c = node * 32 + lane;
+            if (c < b.count[level - 1]) {
+                const float4 u = box[2 * (size_t)(b.offset[level - 1] + c)], v = box[2 * (size_t)(b.offset[level - 1] + c) + 1];
+                lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; hi[0] = v.x; hi[1] = v.y; hi[2] = v.z;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
+        if (lane == 0) {
+            box[2 * (size_t)(offset + node)] = make_float4(lo[0], lo[1], lo[2], 0.f);
+            box[2 * (size_t)(offset + node) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
-    if (lane == 0) {
-        box[2 * (size_t)(offset + node)] = make_float4(lo[0], lo[1], lo[2], 0.f);
-        box[2 * (size_t)(offset + node) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
-    }
 }
 
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const unsigned int* n_finite_dev, const BvhDesc& bvh, float4* box,
-                                 cudaStream_t s, int* n_launches) {
-    for (int l = 0; l < bvh.n_levels; ++l) {
-        const int warps_per_block = 8;
-        const int nb = (bvh.count[l] + warps_per_block - 1) / warps_per_block;
-        bvh_level_kernel<<<nb, warps_per_block * 32, 0, s>>>(pts_sorted, n_finite_dev, box, l, bvh.count[l], bvh.offset[l],
-                                                             l > 0 ? bvh.count[l - 1] : 0, l > 0 ? bvh.offset[l - 1] : 0);
-        if (n_launches) *n_launches += 1;
+size_t icp_bvh_max_nodes(int n) {
+    // worst case: every point its own leaf
+    size_t cnt = (size_t)(n > 0 ? n : 1), tot = 0;
+    for (int l = 0; l < ICP_BVH_MAX_LEVELS; ++l) { tot += cnt; if (cnt == 1) break; cnt = (cnt + 31) / 32; }
+    return tot + 8;
+}
+
+static cudaError_t launch_exclusive_scan(unsigned int* data, int n, unsigned int* block_sums, cudaStream_t s, int* launches);
+
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
+                                 unsigned int* flags_scratch, unsigned int* block_sums, unsigned int* leaf_start, BvhDesc* bvh_dev,
+                                 float4* box, int n_sms, cudaStream_t s, int* n_launches) {
+    int launches = 0;
+    mark_leaves_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(pts_sorted, n, grid, cell_start, T, flags_scratch); ++launches;
+    cudaError_t e = launch_exclusive_scan(flags_scratch, n + 1, block_sums, s, &launches);
+    if (e != cudaSuccess) return e;
+    leaf_starts_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(flags_scratch, n, cell_start, T, leaf_start, bvh_dev); ++launches;
+    // number of levels an n-point cloud can need (the real count is on the device; surplus launches return at once)
+    int max_levels = 1; { long long c = n > 0 ? n : 1; while (c > 1 && max_levels < ICP_BVH_MAX_LEVELS) { c = (c + 31) / 32; ++max_levels; } }
+    for (int l = 0; l < max_levels; ++l) {
+        long long nodes = n > 0 ? n : 1; for (int k = 0; k < l; ++k) nodes = (nodes + 31) / 32;
+        long long nb = (nodes + 7) / 8; if (nb > 8ll * n_sms) nb = 8ll * n_sms; if (nb < 1) nb = 1;
+        bvh_level_kernel<<<(int)nb, 256, 0, s>>>(pts_sorted, leaf_start, bvh_dev, box, l); ++launches;
     }
+    if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }
 

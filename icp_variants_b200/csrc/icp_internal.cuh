@@ -19,7 +19,6 @@
 #define ICP_NRED 32                // doubles per partial-sum row (27..30 used)
 #define ICP_REDUCE_THREADS 256
 #define ICP_MATCH_THREADS 128
-#define ICP_TILE 128                // queries per tile = threads per block of the tiled search
 #define ICP_LEAF_MAX 8             // a grid node with <= this many points is scanned, not split
 #define ICP_MAX_BITS_PER_AXIS 10   // keeps the cell-index rounding error << the bound margin
 
@@ -42,22 +41,25 @@ struct GridParams {
     int pad;
 };
 
+// 32-ary bounding-volume hierarchy over the cell-sorted target (grid.cu).  Level 0 = leaves: the nodes of
+// the implicit cell tree with <= 32 points (disjoint, cell-aligned runs of the sorted array, leaf j =
+// [leaf_start[j], leaf_start[j+1])); level l+1 groups 32 consecutive nodes of level l.  Every node stores the
+// TIGHT axis-aligned box of its points as two float4 {lo.xyz,_} {hi.xyz,_} at box[2*(offset[l]+j)].
+// The number of leaves is only known on the device, so the descriptor lives in device memory.
+#define ICP_BVH_MAX_LEVELS 7
+struct BvhDesc {
+    int n_levels;                      // levels 0 .. n_levels-1; the top level has one node
+    int n_leaves;
+    int count[ICP_BVH_MAX_LEVELS];     // nodes per level
+    int offset[ICP_BVH_MAX_LEVELS];    // first node of the level in the box array
+};
+
 // One ICP iteration's query set.  Queries are addressed by p = position in the Morton-sorted source
 // (grid.cu); the sorted source keeps the original index in pts.w.  Query p is active iff
 //   orig % stride == 0                           (PointCloud.h:325-343 level stride; 1 = all)
 //   and (filter_finite == 0 or point and normal finite)          (PointCloud.h:335)
 //   and (mask_word_offset < 0 or bit `orig` of the mask is set)  (selection.h:88-104, drawn on the host)
 //   and (proba < 0 or hash(rng_key, orig) < proba)               (device selection stream)
-// 32-ary bounding-volume hierarchy over the cell-sorted target (grid.cu): level 0 = leaves of 32
-// consecutive points, level l+1 = 32 consecutive nodes of level l; every node stores the TIGHT
-// axis-aligned box of its points as two float4 {lo.xyz,_} {hi.xyz,_} at box[2*(offset[l]+j)].
-#define ICP_BVH_MAX_LEVELS 7
-struct BvhDesc {
-    int n_levels;                      // levels 0 .. n_levels-1; the top level has one node
-    int count[ICP_BVH_MAX_LEVELS];     // nodes per level
-    int offset[ICP_BVH_MAX_LEVELS];    // first node of the level in the box array
-};
-
 struct IterDesc {
     int stride;
     int filter_finite;
@@ -79,13 +81,12 @@ struct DevState {
     float mean_s[3];     // unweighted means of the kept matches (symmetric metric), rounded to fp32
     float mean_d[3];
     double mean_s64[3], mean_d64[3];
-    unsigned long long n_queries, n_matched, n_evals, n_nodes, n_staged, n_deferred_total;
+    unsigned long long n_queries, n_matched, n_evals, n_nodes;
     // Levenberg-Marquardt state (lm.cu)
     double lm_x[6], lm_cand[6], lm_cost, lm_H[36], lm_g[6], lm_scale[6], lm_diag[6];
     double lm_radius, lm_decrease, lm_model_change;
     int lm_iter, lm_done, lm_reuse_diag, lm_invalid, lm_step_ok, lm_have_cand;
     double shard_partials[ICP_NRED];
-    unsigned int n_deferred[ICP_MAX_ITERS + 2];   // per iteration: queries handed from the tile kernel to the tree kernel
 };
 
 struct MatchArgs {
@@ -93,8 +94,6 @@ struct MatchArgs {
     const float4* src_pts;
     const float4* src_nrm;
     int n_src;
-    const int2* tiles;       // [n_tiles] {first p, count <= ICP_TILE}: spatially compact runs of the sorted source
-    int n_tiles;
     const unsigned int* mask; // selection masks (bit per original source index), all iterations concatenated
     const IterDesc* desc;    // [ICP_MAX_ITERS + 2]
     const DevState* state_ro;
@@ -106,7 +105,8 @@ struct MatchArgs {
     const float4* tgt_nrm;   // same order {nx,ny,nz,rgba bits}
     int n_tgt;
     const float4* bvh_box;   // tight boxes of the BVH nodes (grid order only)
-    BvhDesc bvh;
+    const BvhDesc* bvh;      // device-resident
+    const unsigned int* leaf_start;
     // projective
     float fx, fy, cx, cy; unsigned int width, height;
     // config
@@ -117,7 +117,6 @@ struct MatchArgs {
     float* match_w;
     int* match_idx;          // original target index (API output), may be null
     int* nn_pos;             // nearest neighbour found the last time p was a query (-1 none): seeds the next search
-    int* deferred;           // [n_src + 32 * n_tiles] queries the tile kernel could not resolve, one warp-padded run per tile
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
     int use_seed;
     int collect_stats;       // work counters in DevState (atomics); off in timed runs
@@ -142,16 +141,14 @@ cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, in
                                   unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
                                   unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
                                   cudaStream_t s, int* n_launches);
-// Tight-box 32-ary BVH over the cell-sorted cloud; n_finite_dev = device address of the number of sorted points.
-void icp_bvh_layout(int n, BvhDesc* out);
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const unsigned int* n_finite_dev, const BvhDesc& bvh, float4* box,
-                                 cudaStream_t s, int* n_launches);
-// Partition of the sorted source into spatially compact tiles (<= ICP_TILE points each).
-cudaError_t icp_launch_make_tiles(const unsigned int* cell_start, int T, int n, int2* tiles, unsigned int* n_tiles_dev, cudaStream_t s,
-                                  int* n_launches);
+// Tight-box 32-ary BVH over the cell-sorted cloud (uses keys / ranks as scratch; leaf_start has n + 2 entries).
+size_t icp_bvh_max_nodes(int n);
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
+                                 unsigned int* flags_scratch, unsigned int* block_sums, unsigned int* leaf_start, BvhDesc* bvh_dev,
+                                 float4* box, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
-// algorithm: 0 tiled grid search (+ BVH kernel for deferred queries), 1 brute force, 2 projective, 3 BVH search for every query
+// algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective
 cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);

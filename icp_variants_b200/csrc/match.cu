@@ -10,27 +10,20 @@
 // NearestNeighborSearchBruteForce's scan order (NearestNeighbor.h:81-97) yields on squared distances.
 //
 // k-NN kernels:
-//   knn_tile_kernel   one block per source tile (<= 128 spatially compact queries).  Every query starts
-//                     from an upper bound (the neighbour it had the last time it was matched, else the
-//                     distance threshold); the block stages the target points of all grid cells that meet
-//                     the union of the queries' search balls in shared memory and every thread scans the
-//                     staged points (shared-memory broadcast reads, no divergence).  Queries whose ball
-//                     does not fit the tile's budget are handed to
-//   knn_bvh_kernel    one warp per query: depth-first walk of a 32-ary tight-box BVH over the cell-sorted
-//                     target, 32 child boxes tested per step (lane = child) and leaves of 32 points scanned
-//                     per step (lane = point); any bound, any distance; also usable for all queries.
-//   knn_brute_kernel  small targets: one warp per query, warp-shuffle arg-min.
+//   knn_bvh_kernel    one warp per query walks a 32-ary bounding-volume hierarchy over the cell-sorted target
+//                     (grid.cu) depth-first with an explicit shared-memory stack.  Leaves are the nodes of the
+//                     implicit cell tree with <= 32 points (disjoint aligned cells, TIGHT boxes); an internal
+//                     node groups 32 consecutive nodes of the level below.  One step tests the 32 children of a
+//                     node in parallel (lane = child, one coalesced 1 KB read of boxes); a leaf is scanned by the
+//                     32 lanes in parallel (lane = point, one coalesced 512 B read) with a warp arg-min at the end.
+//                     Every query starts from an upper bound: the neighbour it had the last time it was matched
+//                     (the pose moves little between ICP iterations), else the distance threshold.
+//   knn_brute_kernel  small targets: one warp per query over the whole target, warp-shuffle arg-min.
 #include "icp_internal.cuh"
 #include <limits.h>
 
 #define MINF_F (-INFINITY)
 #define FLT_BIG 3.4028234e38f
-#define TILE_CHUNK 1024        // staged target points per round
-#define TILE_MAX_CELLS ICP_TILE // candidate cells per pass: one per thread
-#define TILE_BUDGET 12288      // target points in the candidate cells of one tile before its search radius is cut
-
-__device__ __forceinline__ int sel3i(int a, int x, int y, int z) { return a == 0 ? x : (a == 1 ? y : z); }
-__device__ __forceinline__ float sel3f(int a, float x, float y, float z) { return a == 0 ? x : (a == 1 ? y : z); }
 
 struct Query {
     float x, y, z;        // transformed source point
@@ -178,231 +171,6 @@ __device__ __forceinline__ void seed_best(const MatchArgs& a, const Query& q, in
     }
 }
 
-// ---------------------------------------------------------------------------- tiled search
-struct TileSm {
-    PoseSm pose;
-    float4 pts[TILE_CHUNK];
-    unsigned int rgba[TILE_CHUNK];
-    unsigned int cell_s[TILE_MAX_CELLS];
-    unsigned int cell_pref[TILE_MAX_CELLS + 1];
-    float red[ICP_TILE / 32][8];
-    float box[8];            // B1: lo[3], hi[3]
-    unsigned int warp_sums[ICP_TILE / 32];
-    unsigned int count;      // staged points of the current round
-    unsigned int total;      // points in the candidate cells
-    int any_active;
-};
-
-// every point x with lo <= x <= hi is binned in a cell of [cell_lo, cell_hi]: cell_index() is monotone
-__device__ __forceinline__ int cell_index_axis(const GridParams& g, int a, float x) {
-    const float o = sel3f(a, g.o[0], g.o[1], g.o[2]), ih = sel3f(a, g.inv_h[0], g.inv_h[1], g.inv_h[2]);
-    const int bits = sel3i(a, g.bits[0], g.bits[1], g.bits[2]);
-    const float u = pmul(psub(x, o), ih);
-    const int i = (int)floorf(u);
-    return min(max(i, 0), (1 << bits) - 1);
-}
-
-template <bool COLOR>
-__global__ void __launch_bounds__(ICP_TILE) knn_tile_kernel(const MatchArgs a) {
-    __shared__ TileSm sm;
-    load_pose(sm.pose, a.state_ro);
-    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
-    const IterDesc d = a.desc[it];
-    const int2 tile = a.tiles[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int p = tile.x + tid;
-    const bool in_tile = tid < tile.y;
-    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-
-    Query q; float snx = 0.f, sny = 0.f, snz = 0.f; unsigned int s_rgba = 0;
-    bool is_query = in_tile && prepare_query(a, d, sm.pose, p, q, snx, sny, snz, s_rgba);
-    if (is_query) ++nq;
-    const bool searching = is_query && finite3(q.x, q.y, q.z);
-    Best b; b.d = -1.0f; b.idx = INT_MAX; b.pos = -1;
-    float r = 0.0f;
-    if (searching) {
-        seed_best<COLOR>(a, q, p, b);
-        // every target point that can still win has |q - p| <= r per axis (monotone fp32 rounding of D1)
-        r = b.d < FLT_BIG ? __fmul_ru(__fsqrt_ru(b.d), 1.00001f) : FLT_BIG;
-    } else {
-        q.x = q.y = q.z = __int_as_float(0x7fc00000);   // NaN: never improves on anything
-        q.cr = q.cg = q.cb = 0.f;
-    }
-
-    // ---- tile box B0 and the radius cap
-    float lo[3] = {searching ? q.x : FLT_BIG, searching ? q.y : FLT_BIG, searching ? q.z : FLT_BIG};
-    float hi[3] = {searching ? q.x : -FLT_BIG, searching ? q.y : -FLT_BIG, searching ? q.z : -FLT_BIG};
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
-    if (lane == 0) { for (int k = 0; k < 3; ++k) { sm.red[wid][k] = lo[k]; sm.red[wid][3 + k] = hi[k]; } }
-    if (tid == 0) sm.any_active = 0;
-    __syncthreads();
-    if (searching) sm.any_active = 1;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        lo[k] = fminf(fminf(sm.red[0][k], sm.red[1][k]), fminf(sm.red[2][k], sm.red[3][k]));
-        hi[k] = fmaxf(fmaxf(sm.red[0][3 + k], sm.red[1][3 + k]), fmaxf(sm.red[2][3 + k], sm.red[3][3 + k]));
-    }
-    __syncthreads();
-    if (!sm.any_active) {                          // block-uniform
-        if (in_tile) { if (is_query) finish_match(a, p, false, 0.f, -1, -1, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm); else write_no_query(a, p); }
-        flush_stats(a, nq, nm, ev, nd);
-        return;
-    }
-    const GridParams g = *a.grid;
-    const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
-    float cap = ext + 2.0f * fmaxf(fmaxf(g.h[0], g.h[1]), g.h[2]);
-    float rho = 0.f;
-    int depth = 0, rem0 = 0, rem1 = 0, rem2 = 0, k0 = 0, k1 = 0, k2 = 0, n0 = 1, n1 = 1, n2 = 1;
-    for (int attempt = 0; attempt < 6; ++attempt) {
-        // ---- B1 = union of the balls (q_i, min(r_i, cap)), rounded outwards
-        rho = fminf(r, cap);
-        float blo[3], bhi[3];
-        blo[0] = searching ? __fsub_rd(q.x, rho) : FLT_BIG; blo[1] = searching ? __fsub_rd(q.y, rho) : FLT_BIG; blo[2] = searching ? __fsub_rd(q.z, rho) : FLT_BIG;
-        bhi[0] = searching ? __fadd_ru(q.x, rho) : -FLT_BIG; bhi[1] = searching ? __fadd_ru(q.y, rho) : -FLT_BIG; bhi[2] = searching ? __fadd_ru(q.z, rho) : -FLT_BIG;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { blo[k] = fminf(blo[k], __shfl_xor_sync(0xFFFFFFFFu, blo[k], o)); bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(0xFFFFFFFFu, bhi[k], o)); }
-        if (lane == 0) { for (int k = 0; k < 3; ++k) { sm.red[wid][k] = blo[k]; sm.red[wid][3 + k] = bhi[k]; } }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            blo[k] = fminf(fminf(sm.red[0][k], sm.red[1][k]), fminf(sm.red[2][k], sm.red[3][k]));
-            bhi[k] = fmaxf(fmaxf(sm.red[0][3 + k], sm.red[1][3 + k]), fmaxf(sm.red[2][3 + k], sm.red[3][3 + k]));
-        }
-        if (tid == 0) { for (int k = 0; k < 3; ++k) { sm.box[k] = blo[k]; sm.box[3 + k] = bhi[k]; } }
-        // ---- cells of the coarsest-needed depth that meet B1 (uniform computation in every thread)
-        const int fl0 = cell_index_axis(g, 0, blo[0]), fh0 = cell_index_axis(g, 0, bhi[0]);
-        const int fl1 = cell_index_axis(g, 1, blo[1]), fh1 = cell_index_axis(g, 1, bhi[1]);
-        const int fl2 = cell_index_axis(g, 2, blo[2]), fh2 = cell_index_axis(g, 2, bhi[2]);
-        depth = g.T; rem0 = rem1 = rem2 = 0;
-        for (;;) {
-            k0 = fl0 >> rem0; k1 = fl1 >> rem1; k2 = fl2 >> rem2;
-            n0 = (fh0 >> rem0) - k0 + 1; n1 = (fh1 >> rem1) - k1 + 1; n2 = (fh2 >> rem2) - k2 + 1;
-            if ((long long)n0 * n1 * n2 <= TILE_MAX_CELLS || depth == 0) break;
-            --depth;
-            const int ax = (int)((g.axis_seq >> (2 * depth)) & 3ull);
-            if (ax == 0) ++rem0; else if (ax == 1) ++rem1; else ++rem2;
-        }
-        // thread c owns candidate cell c
-        unsigned int cs_ = 0, cnt = 0;
-        if (tid < n0 * n1 * n2) {
-            const int i0 = k0 + tid % n0, i1 = k1 + (tid / n0) % n1, i2 = k2 + tid / (n0 * n1);
-            int b0 = g.bits[0] - rem0, b1 = g.bits[1] - rem1, b2 = g.bits[2] - rem2;
-            unsigned int code = 0;
-            for (int k = 0; k < depth; ++k) {
-                const int ax = (int)((g.axis_seq >> (2 * k)) & 3ull);
-                int bit;
-                if (ax == 0) { --b0; bit = (i0 >> b0) & 1; } else if (ax == 1) { --b1; bit = (i1 >> b1) & 1; } else { --b2; bit = (i2 >> b2) & 1; }
-                code = (code << 1) | (unsigned int)bit;
-            }
-            const int sh = g.T - depth;
-            cs_ = __ldg(&a.cell_start[(size_t)code << sh]);
-            cnt = __ldg(&a.cell_start[((size_t)code + 1) << sh]) - cs_;
-        }
-        // block exclusive scan of cnt
-        unsigned int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) sm.warp_sums[wid] = inc;
-        __syncthreads();
-        unsigned int woff = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < ICP_TILE / 32; ++w) { const unsigned int v = sm.warp_sums[w]; if (w < wid) woff += v; total += v; }
-        sm.cell_s[tid] = cs_;
-        sm.cell_pref[tid] = woff + inc - cnt;
-        if (tid == 0) { sm.cell_pref[TILE_MAX_CELLS] = total; sm.total = total; }
-        __syncthreads();
-        if (total <= TILE_BUDGET || !(cap > 0.f)) break;
-        cap = attempt < 4 ? 0.5f * cap : 0.0f;     // too many candidate points: cut the radius, the cut queries are deferred
-    }
-    const float box_lo0 = sm.box[0], box_lo1 = sm.box[1], box_lo2 = sm.box[2], box_hi0 = sm.box[3], box_hi1 = sm.box[4], box_hi2 = sm.box[5];
-    const unsigned int total = sm.total;
-
-    // ---- rounds: stage the candidate points that lie inside B1, then every thread scans them
-    unsigned int staged_total = 0;
-    for (unsigned int base = 0; base < total; base += TILE_CHUNK) {
-        if (tid == 0) sm.count = 0;
-        __syncthreads();
-#pragma unroll 2
-        for (int j = 0; j < TILE_CHUNK / ICP_TILE; ++j) {
-            const unsigned int f = base + (unsigned int)j * ICP_TILE + tid;
-            bool keep = false; float4 c = make_float4(0.f, 0.f, 0.f, 0.f); unsigned int gi = 0;
-            if (f < total) {
-                int lo_c = 0, hi_c = TILE_MAX_CELLS;                       // last cell with pref <= f
-                while (hi_c - lo_c > 1) { const int mid = (lo_c + hi_c) >> 1; if (sm.cell_pref[mid] <= f) lo_c = mid; else hi_c = mid; }
-                gi = sm.cell_s[lo_c] + (f - sm.cell_pref[lo_c]);
-                c = __ldg(&a.tgt_pts[gi]);
-                keep = c.x >= box_lo0 && c.x <= box_hi0 && c.y >= box_lo1 && c.y <= box_hi1 && c.z >= box_lo2 && c.z <= box_hi2;
-            }
-            const unsigned int m = __ballot_sync(0xFFFFFFFFu, keep);
-            unsigned int wbase = 0;
-            if (lane == 0 && m) wbase = atomicAdd(&sm.count, (unsigned int)__popc(m));
-            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-            if (keep) {
-                const unsigned int slot = wbase + (unsigned int)__popc(m & ((1u << lane) - 1u));
-                c.w = __int_as_float((int)gi);                               // position; the original index is re-read on a hit
-                sm.pts[slot] = c;
-                if (COLOR) sm.rgba[slot] = __float_as_uint(__ldg(&a.tgt_nrm[gi].w));
-            }
-        }
-        __syncthreads();
-        const unsigned int n_st = sm.count;
-        staged_total += n_st;
-        // scan: shared-memory broadcast reads, identical trip count in every thread
-#pragma unroll 4
-        for (unsigned int i = 0; i < n_st; ++i) {
-            const float4 c = sm.pts[i];
-            float dd = dist3(q, c);
-            if (dd <= b.d) {
-                if (COLOR) dd = dist6_tail(q, dd, sm.rgba[i]);
-                const int pos = __float_as_int(c.w);
-                const int idx = __float_as_int(__ldg(&a.tgt_pts[pos].w));
-                if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = pos; }
-            }
-        }
-        __syncthreads();
-    }
-    if (searching) ev += staged_total;
-
-    // ---- resolved iff the scanned box covered the ball of the final bound
-    bool defer = false;
-    if (in_tile) {
-        if (!is_query) write_no_query(a, p);
-        else if (!searching) finish_match(a, p, false, 0.f, -1, -1, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
-        else {
-            const float r_now = b.d < FLT_BIG ? __fmul_ru(__fsqrt_ru(b.d), 1.00001f) : FLT_BIG;
-            a.nn_pos[p] = b.pos;
-            if (r_now <= rho) finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
-            else defer = true;
-        }
-    }
-    // Unresolved queries go to the BVH kernel (one atomic per tile)
-    {
-        const unsigned int m = __ballot_sync(0xFFFFFFFFu, defer);
-        if (lane == 0) sm.warp_sums[wid] = (unsigned int)__popc(m);
-        __syncthreads();
-        unsigned int before = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < ICP_TILE / 32; ++w) { const unsigned int v = sm.warp_sums[w]; if (w < wid) before += v; tot += v; }
-        if (tot > 0) {                                        // block-uniform
-            if (tid == 0) sm.count = atomicAdd(&a.state->n_deferred[it], tot);
-            __syncthreads();
-            if (defer) a.deferred[sm.count + before + (unsigned int)__popc(m & ((1u << lane) - 1u))] = p;
-            nd = defer ? 1u : 0u;
-        }
-    }
-    flush_stats(a, nq, nm, ev, 0u);
-    if (a.collect_stats) {
-        nd = __reduce_add_sync(0xFFFFFFFFu, nd);
-        if (lane == 0 && nd) atomicAdd(&a.state->n_deferred_total, (unsigned long long)nd);
-        if (tid == 0) atomicAdd(&a.state->n_staged, (unsigned long long)staged_total);
-    }
-}
-
 // ---------------------------------------------------------------------------- BVH search, one warp per query
 #define BVH_WARPS 4
 #define BVH_STACK (32 * ICP_BVH_MAX_LEVELS)   // <= 32 pushed children per level below the top
@@ -416,42 +184,35 @@ __device__ __forceinline__ float box_dist2(const Query& q, const float4 lo, cons
     return padd(padd(pmul(gx, gx), pmul(gy, gy)), pmul(gz, gz));
 }
 
-// The warp walks the 32-ary tree depth-first with an explicit stack: one step tests the 32 children of a
-// node in parallel (lane = child, one coalesced 1 KB read of tight boxes), a leaf is scanned by the 32
-// lanes in parallel (lane = point, one coalesced 512 B read).  ALL = every sorted-source point p is a
-// query (grid-stride); otherwise the queries come from the tile kernel's deferred list.
-template <bool COLOR, bool ALL>
+template <bool COLOR>
 __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     __shared__ unsigned int s_node[BVH_WARPS][BVH_STACK];
     __shared__ float s_lb[BVH_WARPS][BVH_STACK];
-    load_pose(sm, a.state_ro);
+    __shared__ BvhDesc s_bvh;
+    if (threadIdx.x < sizeof(BvhDesc) / 4) reinterpret_cast<int*>(&s_bvh)[threadIdx.x] = reinterpret_cast<const int*>(a.bvh)[threadIdx.x];
+    load_pose(sm, a.state_ro);      // __syncthreads inside
     const unsigned int FULL = 0xFFFFFFFFu;
-    const int it = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
-    const IterDesc d = a.desc[it];
-    const int n = ALL ? a.n_src : (int)a.state_ro->n_deferred[it];
+    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned int n_finite = __ldg(&a.cell_start[1u << a.grid->T]);
-    const BvhDesc& bvh = a.bvh;
+    const BvhDesc& bvh = s_bvh;
     const int top_level = bvh.n_levels - 1;
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
     unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
-    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
-        const int p = ALL ? k : a.deferred[k];
+    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < a.n_src; p += warps) {
         Query q; float snx, sny, snz; unsigned int s_rgba;
         if (!prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {            // warp-uniform
-            if (ALL && lane == 0) write_no_query(a, p);
+            if (lane == 0) write_no_query(a, p);
             continue;
         }
-        if (ALL && lane == 0) ++nq;
+        if (lane == 0) ++nq;
         Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
-        if (finite3(q.x, q.y, q.z) && n_finite > 0u) {
+        if (finite3(q.x, q.y, q.z) && bvh.n_leaves > 0) {
             seed_best<COLOR>(a, q, p, b);                                       // uniform: every lane starts from the seed
             float bound = b.d;
-            int top = 0;
+            int top = 1;
             if (lane == 0) { st_node[0] = (unsigned int)top_level << 27; st_lb[0] = 0.0f; }
-            top = 1;
             __syncwarp();
             while (top > 0) {
                 --top;
@@ -460,10 +221,10 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                 if (nlb > bound) continue;
                 const int lvl = (int)(nd_id >> 27), j = (int)(nd_id & 0x7FFFFFFu);
                 if (lane == 0) ++nd;
-                if (lvl == 0) {
-                    // leaf j: lane = point
-                    const unsigned int i = (unsigned int)j * 32u + lane;
-                    if (i < n_finite) {
+                if (lvl == 0) {                                                 // only when the whole tree is one leaf
+                    const unsigned int ls = __ldg(&a.leaf_start[j]), le = __ldg(&a.leaf_start[j + 1]);
+                    const unsigned int i = ls + lane;
+                    if (i < le) {
                         const float4 c = __ldg(&a.tgt_pts[i]);
                         const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
                         const int idx = __float_as_int(c.w);
@@ -473,13 +234,37 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                     bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));   // d >= 0: bit order = value order
                     continue;
                 }
-                // internal node: lane = child
+                // lane = child
                 const int cl = lvl - 1, c = j * 32 + lane;
                 float clb = FLT_BIG; bool keep = false;
                 if (c < bvh.count[cl]) {
                     const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c) + 1]);
                     clb = box_dist2(q, lo, hi);
-                    keep = !(clb > bound);                                       // NaN-free: empty boxes give +inf
+                    keep = !(clb > bound);
+                }
+                if (cl == 0) {
+                    // the children are leaves: scan the ones that can still matter, nearest first
+                    unsigned int ls = 0, le = 0;
+                    if (keep) { ls = __ldg(&a.leaf_start[c]); le = __ldg(&a.leaf_start[c + 1]); }
+                    unsigned int key = keep ? __float_as_uint(clb) : 0xFFFFFFFFu;
+                    for (;;) {
+                        const unsigned int kmin = __reduce_min_sync(FULL, key);
+                        if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bound) break;
+                        const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
+                        const unsigned int s0 = __shfl_sync(FULL, ls, src), e0 = __shfl_sync(FULL, le, src);
+                        if (lane == src) key = 0xFFFFFFFFu;
+                        const unsigned int i = s0 + lane;
+                        if (i < e0) {
+                            const float4 pt = __ldg(&a.tgt_pts[i]);
+                            const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
+                            const int idx = __float_as_int(pt.w);
+                            if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                            ++ev;
+                        }
+                        if (lane == 0) ++nd;
+                        bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
+                    }
+                    continue;
                 }
                 // push far children first and the children that contain q last (popped first)
                 const bool near = keep && clb == 0.0f, far = keep && clb > 0.0f;
@@ -596,21 +381,11 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         const int nb = (int)((threads + T - 1) / T);
         if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
         ++launches;
-    } else if (algorithm == 3) {
+    } else {
         int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
         if (nb > 64 * n_sms) nb = 64 * n_sms;
-        if (a.color_icp) knn_bvh_kernel<true, true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, true><<<nb, BVH_WARPS * 32, 0, s>>>(a);
+        if (a.color_icp) knn_bvh_kernel<true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
         ++launches;
-    } else {
-        if (a.n_tiles > 0) {
-            if (a.color_icp) knn_tile_kernel<true><<<a.n_tiles, ICP_TILE, 0, s>>>(a); else knn_tile_kernel<false><<<a.n_tiles, ICP_TILE, 0, s>>>(a);
-            ++launches;
-            int nb = (a.n_src / 4 + BVH_WARPS - 1) / BVH_WARPS;      // deferred queries: one warp each, grid-stride over the list
-            if (nb > 32 * n_sms) nb = 32 * n_sms;
-            if (nb < 1) nb = 1;
-            if (a.color_icp) knn_bvh_kernel<true, false><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
-            ++launches;
-        }
     }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();

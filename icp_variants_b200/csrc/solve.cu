@@ -306,18 +306,17 @@ cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase
 
 // ---------------------------------------------------------------------------- pose upload / shard apply
 __global__ void pose_init_kernel(DevState* st, const float* pose16) {
-    for (int k = threadIdx.x; k < ICP_MAX_ITERS + 2; k += blockDim.x) st->n_deferred[k] = 0u;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int i = 0; i < 16; ++i) st->pose[i] = pose16[i];
     inv_transpose3_pinned(st->pose, st->nrm);
     st->iter = 0; st->iters_done = 0; st->status = 0; st->ticket = 0; st->ticket2 = 0;
-    st->n_queries = 0; st->n_matched = 0; st->n_evals = 0; st->n_nodes = 0; st->n_staged = 0; st->n_deferred_total = 0;
+    st->n_queries = 0; st->n_matched = 0; st->n_evals = 0; st->n_nodes = 0;
     for (int k = 0; k < 3; ++k) { st->mean_s[k] = 0.f; st->mean_d[k] = 0.f; }
     st->lm_done = 0; st->lm_iter = 0;
 }
 
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s) {
-    pose_init_kernel<<<1, 128, 0, s>>>(st, pose_dev16);
+    pose_init_kernel<<<1, 32, 0, s>>>(st, pose_dev16);
     return cudaGetLastError();
 }
 

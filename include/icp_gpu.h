@@ -54,10 +54,10 @@ enum { ICP_GPU_MATCH_KNN = 0, ICP_GPU_MATCH_PROJECTIVE = 1 };
 enum { ICP_GPU_SELECT_ALL = 0, ICP_GPU_SELECT_RANDOM = 1 };
 /* weighting.h:8                                                                                  */
 enum { ICP_GPU_WEIGHT_CONSTANT = 0, ICP_GPU_WEIGHT_DISTANCES = 1, ICP_GPU_WEIGHT_NORMALS = 2, ICP_GPU_WEIGHT_COLORS = 3 };
-/* Nearest-neighbour kernel choice (all exact, same answers): AUTO = by target size; BRUTE = warp per
- * query over the whole target; GRID = tiled shared-memory search over the cell grid (tree search for
- * the few queries a tile cannot resolve); TREE = per-query tree search over the cell grid              */
-enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2, ICP_GPU_NN_TREE = 3 };
+/* Nearest-neighbour kernel choice (both exact, same answers): AUTO = by target size; BRUTE = one warp per
+ * query over the whole target; GRID = one warp per query over a tight-box 32-ary BVH built on the target
+ * sorted into the cell (Morton) order of a uniform grid                                               */
+enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2 };
 /* Random selection stream: 0 = std::mt19937 + uniform_real_distribution<double> drawn on the host
  * exactly as selection.h:88-104 does (reference-compatible for a given seed); 1 = counter-based
  * hash drawn on the device (fast, not reference-compatible).                                      */
@@ -108,11 +108,8 @@ typedef struct icp_gpu_stats {
     uint64_t n_queries;        /* source points submitted to matching, summed over iterations      */
     uint64_t n_matched;        /* correspondences that survived threshold + rejection              */
     uint64_t n_distance_evals; /* point-to-point squared distances evaluated by the search         */
-    uint64_t n_nodes_visited;  /* grid nodes (cells at any level) whose bound was tested           */
+    uint64_t n_nodes_visited;  /* BVH nodes entered (internal nodes and leaves)                    */
     uint64_t n_kernel_launches;/* kernels launched by this library in the call                     */
-    uint64_t n_points_staged;  /* target points staged in shared memory by the tiled search        */
-    uint64_t n_deferred;       /* queries the tiled search handed to the packet tree search        */
-    uint64_t n_tiles;          /* source tiles (blocks of the tiled search)                        */
 } icp_gpu_stats;
 
 typedef struct icp_gpu_ctx icp_gpu_ctx;
