@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
     const int top_level = bvh.n_levels - 1;
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
     unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
+    const unsigned int lt_mask = (1u << lane) - 1u;
     for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < a.n_src; p += warps) {
         Query q; float snx, sny, snz; unsigned int s_rgba;
         if (!prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {            // warp-uniform
@@ -210,7 +211,29 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
         if (finite3(q.x, q.y, q.z) && bvh.n_leaves > 0) {
             seed_best<COLOR>(a, q, p, b);                                       // uniform: every lane starts from the seed
-            float bound = b.d;
+            if (b.pos < 0 && top_level > 0) {
+                // No neighbour remembered (first iteration): follow the nearest child down to one leaf and take its best
+                // point as the starting bound, so that the walk below prunes from its first step on.
+                int j = 0;
+                for (int lvl = top_level; lvl > 0; --lvl) {
+                    const int cl = lvl - 1, c = j * 32 + lane;
+                    unsigned int key = 0xFFFFFFFFu;
+                    if (c < bvh.count[cl]) {
+                        const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c) + 1]);
+                        key = __float_as_uint(box_dist2(q, lo, hi));
+                    }
+                    const unsigned int kmin = __reduce_min_sync(FULL, key);
+                    j = j * 32 + (__ffs((int)__ballot_sync(FULL, key == kmin)) - 1);
+                }
+                const unsigned int i = __ldg(&a.leaf_start[j]) + lane;
+                if (i < __ldg(&a.leaf_start[j + 1])) {
+                    const float4 c = __ldg(&a.tgt_pts[i]);
+                    const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
+                    const int idx = __float_as_int(c.w);
+                    if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                }
+            }
+            float bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
             int top = 1;
             if (lane == 0) { st_node[0] = (unsigned int)top_level << 27; st_lb[0] = 0.0f; }
             __syncwarp();
@@ -266,14 +289,10 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                     }
                     continue;
                 }
-                // push far children first and the children that contain q last (popped first)
-                const bool near = keep && clb == 0.0f, far = keep && clb > 0.0f;
-                const unsigned int mf = __ballot_sync(FULL, far), mn = __ballot_sync(FULL, near);
-                const unsigned int lt = (1u << lane) - 1u;
-                if (far) { const int s = top + __popc(mf & lt); st_node[s] = ((unsigned int)cl << 27) | (unsigned int)c; st_lb[s] = clb; }
-                top += __popc(mf);
-                if (near) { const int s = top + __popc(mn & lt); st_node[s] = ((unsigned int)cl << 27) | (unsigned int)c; st_lb[s] = clb; }
-                top += __popc(mn);
+                // push the surviving children (any order is correct; the bound is already tight, see below)
+                const unsigned int mk = __ballot_sync(FULL, keep);
+                if (keep) { const int s = top + __popc(mk & lt_mask); st_node[s] = ((unsigned int)cl << 27) | (unsigned int)c; st_lb[s] = clb; }
+                top += __popc(mk);
                 __syncwarp();
             }
             // warp arg-min on (d, idx)
