@@ -109,10 +109,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(ns, nt, max_d2):
+    """The workload both arms run (BASELINE.json configs[1])."""
+    return {"workload": WORKLOAD, "n_source": ns, "n_target": nt, "iterations": N_ITER, "max_distance_sq": max_d2,
+            "pairs_per_gpu_per_step": 1, "includes_index_build": True}
+
+
 def cpu_sample(src, tgt, max_d2, iters):
     """The oracle's whole registration loop for `iters` iterations on all host threads."""
     from oracle import oracle as orc
     orc.build()
+    orc.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
     cfg = orc.Config(metric=1, minimizer=0, max_distance_sq=max_d2, n_iterations=iters)
     t0 = time.perf_counter()
     rc, pose, hist, nq = orc.estimate_pose(cfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
@@ -138,7 +145,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "icp_registrations_per_s", "value": value, "unit": "reg/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_reg * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_source": len(src), "n_target": len(tgt), "iterations": N_ITER, "max_distance_sq": args.max_dist2},
+            "config": workload_config(len(src), len(tgt), args.max_dist2),
             "mcorr_per_s": nq / statistics.mean(times) / 1e6,
             "cpu_baseline": {"value": value, "unit": "reg/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "reg/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -279,9 +286,8 @@ def main():
             "metric": "icp_registrations_per_s", "value": value, "unit": "reg/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_source": ns, "n_target": nt, "iterations": N_ITER, "max_distance_sq": args.max_dist2,
-                       "pairs_per_gpu_per_step": 1, "l2": "flushed between timed steps (256 MB write)" if flush is not None else "not flushed",
-                       "includes_index_build": True},
+            "config": dict(workload_config(ns, nt, args.max_dist2),
+                           l2="flushed between timed steps (256 MB write)" if flush is not None else "not flushed"),
             "ms_per_registration": total_ms / args.steps,
             "mcorr_per_s": (st.n_queries * regs) / (total_ms * 1e-3) / 1e6,
             "e2e": {"value": regs / (e2e_ms * 1e-3), "unit": "reg/s", "ms_per_step": e2e_ms / args.steps,
@@ -299,7 +305,7 @@ def main():
             "clocks": clocks,
             "pose_checksum": float(np.abs(pose).sum()),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             dt, nq, cores = cpu_sample(src, tgt, args.max_dist2, args.cpu_iters)
             per_reg = dt / args.cpu_iters * N_ITER
             line["cpu_baseline"] = {"value": 1.0 / per_reg, "unit": "reg/s", "cores": cores, "kind": "port",
