@@ -371,3 +371,105 @@ def test_point_sharded_equals_single(bunny, metric):
         pa, pb = a.iteration_end(), b.iteration_end()
         assert np.array_equal(pa, pb)
         assert pose_close(pa, ref_pose, 1e-6, 1e-6)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json full sizes
+@pytest.fixture(scope="module")
+def full_eth_pair():
+    """configs[1]: 344 sweeps x 1077 beams = 370 488 points per scan."""
+    return synth.eth_pair(seed=1234)
+
+
+def test_full_size_eth_correspondences_bit_exact(ctx, full_eth_pair):
+    """At the benchmark's size the device search must still return exactly the oracle's (kd-tree, == brute force)
+    correspondences, at the start pose and -- warm-started from its own previous answer -- at a later pose."""
+    src, tgt, _ = full_eth_pair
+    assert len(src) == 370488 and len(tgt) == 370488
+    ocfg = orc.Config(metric=1, max_distance_sq=10.0)
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, nn_algorithm=2))
+    tree = orc.KdTree(tgt.points)
+    later = synth.make_pose([-0.02, -0.015, -0.004], [-0.15, -0.08, -0.4])
+    for pose in (np.eye(4, dtype=np.float32), later, np.eye(4, dtype=np.float32)):
+        om = orc.match_pipeline(ocfg, pose, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors, tree=tree)
+        idx, w = ctx.query_matches(pose)
+        assert_matches_equal(idx, w, om)
+    assert (om["idx"] >= 0).mean() > 0.5
+
+
+def test_full_size_eth_registration(ctx, full_eth_pair):
+    """The benchmark's registration at full size: the pose after 10 iterations agrees with the oracle's within the
+    tolerance, repeating it gives the same bits (deterministic reductions, graph replay), and the graph and
+    launch-by-launch paths agree."""
+    src, tgt, pert = full_eth_pair
+    ocfg = orc.Config(metric=1, max_distance_sq=10.0, n_iterations=10)
+    rc, opose, _, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    cfg = gpu_config(ocfg, nn_algorithm=2)
+    ctx.set_config(cfg)
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == 10 and ctx.stats().n_queries == nq
+    assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
+    # the registration moves the source back towards the frame the perturbation took it from
+    before = np.linalg.norm(pert[:3, 3])
+    after = np.linalg.norm((pose.astype(np.float64) @ pert.astype(np.float64))[:3, 3])
+    assert after < before * 3.5      # (biased by the ~18 % of points without a counterpart; the oracle shows the same)
+    pose2, _, _ = ctx.estimate_pose()
+    assert np.array_equal(pose, pose2)
+    cfg.use_graph = 0
+    ctx.set_config(cfg)
+    pose3, _, _ = ctx.estimate_pose()
+    assert np.array_equal(pose, pose3)
+
+
+def test_full_size_tum_projective_bit_exact(ctx):
+    """configs[2]: 640x480 frames, projective matching, normals weighting: correspondences bit-exact vs the oracle."""
+    src, tgt, k, _ = synth.tum_pair(seed=1234, frame_gap=10)
+    assert len(src) == 307200
+    ocfg = orc.Config(metric=2, matching=1, weighting=2, max_distance_sq=0.1, n_iterations=1,
+                      fx=float(k[0, 0]), fy=float(k[1, 1]), cx=float(k[0, 2]), cy=float(k[1, 2]), width=640, height=480)
+    load(ctx, src, tgt)
+    ctx.set_camera(k, 640, 480)
+    ctx.set_config(gpu_config(ocfg))
+    om = orc.match_pipeline(ocfg, np.eye(4, dtype=np.float32), src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    idx, w = ctx.query_matches(np.eye(4, dtype=np.float32))
+    assert_matches_equal(idx, w, om)
+    assert (om["idx"] > 0).sum() > 100000
+
+
+def test_config4_multires_symmetric_lm_color(ctx):
+    """configs[3]: multi-resolution + symmetric metric + LM + 6-D colour k-NN + colour weighting (reduced size so that
+    the oracle's LM with its per-residual jets stays in seconds)."""
+    src, tgt, _ = synth.eth_pair(seed=77, n_sweeps=86, n_beams=270, colors="texture")
+    ocfg = orc.Config(metric=2, minimizer=1, weighting=3, color_icp=True, multires=True, max_distance_sq=0.1, n_iterations=6)
+    rc, opose, ohist, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, nn_algorithm=2))
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == len(ohist) and ctx.stats().n_queries == nq
+    assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
+
+
+def test_async_pair_queue_two_contexts(bunny, small_eth_pair):
+    """The pair queue of section 8(e): registrations enqueued on two contexts without waiting, fetched later."""
+    bs, bt, _, _ = bunny
+    es, et, _ = small_eth_pair
+    with capi.Context(0) as c1, capi.Context(0) as c2:
+        cfg = capi.default_config()
+        cfg.metric = 1
+        c1.set_config(cfg)
+        cfg.max_distance_sq = 0.1
+        c2.set_config(cfg)
+        c1.set_target(bt.points, bt.normals, bt.colors); c1.set_source(bs.points, bs.normals, bs.colors)
+        c2.set_target(et.points, et.normals, et.colors); c2.set_source(es.points, es.normals, es.colors)
+        ref1, _, _ = c1.estimate_pose()
+        ref2, _, _ = c2.estimate_pose()
+        c1.estimate_pose_async(); c2.estimate_pose_async()
+        with pytest.raises(capi.IcpGpuError) as e:          # one registration per context at a time
+            c1.estimate_pose_async()
+        assert e.value.code == capi.E_STATE
+        p2, n2 = c2.estimate_pose_finish()
+        p1, n1 = c1.estimate_pose_finish()
+        assert n1 == 20 and n2 == 20 and np.array_equal(p1, ref1) and np.array_equal(p2, ref2)
