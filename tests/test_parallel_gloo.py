@@ -1,0 +1,65 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: pair dealing, point shards, the partial-row
+all-reduce and the max-over-ranks timing reduction."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from icp_variants_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # one large pair: partial normal-equation rows of the two shards sum to the row of the whole
+        rng = np.random.default_rng(5)
+        rows = rng.normal(size=(1000, 28))
+        sl = parallel.shard_points(len(rows), world, rank)
+        total = parallel.allreduce_sum(rows[sl].sum(0))
+        ok_sum = np.allclose(total, rows.sum(0), rtol=1e-12, atol=1e-12)
+        # pair queue: every pair goes to exactly one rank
+        mine = parallel.shard_pairs(44, world, rank)
+        counts = parallel.allreduce_sum(np.bincount(mine, minlength=44).astype(np.float64))
+        ok_pairs = np.array_equal(counts, np.ones(44))
+        # timing reduction
+        ok_max = parallel.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+        q.put((rank, bool(ok_sum), bool(ok_pairs), bool(ok_max), len(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_two_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1:4] for r in res] == [(True, True, True)] * world
+    assert sum(r[4] for r in res) == 44
+
+
+def test_shards_cover_everything():
+    for n in (0, 1, 7, 44, 370488):
+        for world in (1, 2, 4, 8):
+            sl = [parallel.shard_points(n, world, r) for r in range(world)]
+            assert sl[0].start == 0 and sl[-1].stop == n
+            assert all(a.stop == b.start for a, b in zip(sl, sl[1:]))
+            assert max(s.stop - s.start for s in sl) - min(s.stop - s.start for s in sl) <= 1
+            pairs = sorted(i for r in range(world) for i in parallel.shard_pairs(n % 100, world, r))
+            assert pairs == list(range(n % 100))
