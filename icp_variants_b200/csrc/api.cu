@@ -77,7 +77,7 @@ struct icp_gpu_ctx {
     std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
     bool src_rank_valid = false;
     // target grid
-    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box, bvh_desc, leaf_start;
+    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, pstart;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
     // source grid: only its sort order is used (consecutive queries are spatial neighbours: coherent tree walks)
     DeviceBuf sgrid, scell_start, order_dev;
@@ -182,8 +182,10 @@ int build_grid(icp_gpu_ctx* ctx) {
     if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) ||
         ensure(ctx, ctx->keys, (n1 + 2) * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->cell_start, cells1 * 4) ||
         ensure(ctx, ctx->block_sums, (scan_len / 4096 + 2) * 4) || ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64) ||
-        ensure(ctx, ctx->leaf_start, (n1 + 2) * 4) || ensure(ctx, ctx->bvh_desc, sizeof(BvhDesc)) ||
-        ensure(ctx, ctx->bvh_box, icp_bvh_max_nodes(n) * 2 * sizeof(float4)))
+        ensure(ctx, ctx->leaf_start, (n1 + 2) * 4) || ensure(ctx, ctx->leaf_rank, (n1 + 2) * 4) || ensure(ctx, ctx->bvh_desc, sizeof(BvhDesc)) ||
+        ensure(ctx, ctx->bvh_box, icp_bvh_max_nodes(n) * 2 * sizeof(float4)) ||
+        ensure(ctx, ctx->node_rank, (icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS) * 4) ||
+        ensure(ctx, ctx->child_start, (icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS) * 4) || ensure(ctx, ctx->pstart, icp_bvh_max_nodes(n) * 4))
         return ICP_GPU_E_CUDA;
     int launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -192,7 +194,8 @@ int build_grid(icp_gpu_ctx* ctx) {
                              (unsigned int*)ctx->cell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->tgt_pts_sorted.p,
                              (float4*)ctx->tgt_nrm_sorted.p, 0, ctx->stream, &launches));
     CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, n, (const GridParams*)ctx->grid.p, (const unsigned int*)ctx->cell_start.p, ctx->T,
-                            (unsigned int*)ctx->keys.p, (unsigned int*)ctx->block_sums.p, (unsigned int*)ctx->leaf_start.p,
+                            (unsigned int*)ctx->leaf_rank.p, (unsigned int*)ctx->block_sums.p, (unsigned int*)ctx->leaf_start.p,
+                            (unsigned int*)ctx->node_rank.p, (unsigned int*)ctx->child_start.p, (unsigned int*)ctx->pstart.p,
                             (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ctx->stream, &launches));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
@@ -352,6 +355,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.tgt_nrm = (const float4*)(grid_order ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
     a.n_tgt = c->n_tgt;
     a.bvh_box = (const float4*)c->bvh_box.p; a.bvh = (const BvhDesc*)c->bvh_desc.p; a.leaf_start = (const unsigned int*)c->leaf_start.p;
+    a.leaf_rank = (const unsigned int*)c->leaf_rank.p; a.child_start = (const unsigned int*)c->child_start.p;
     if (c->have_camera) { a.fx = c->K[0]; a.fy = c->K[4]; a.cx = c->K[6]; a.cy = c->K[7]; }   // column-major Matrix3f
     a.width = c->width; a.height = c->height;
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
@@ -564,7 +568,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start};
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);

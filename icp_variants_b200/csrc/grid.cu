@@ -275,23 +275,105 @@ __global__ void leaf_starts_kernel(const unsigned int* __restrict__ rank, int n,
         const int L = (int)rank[n_finite];
         leaf_start[L] = n_finite;
         BvhDesc b;
-        b.n_leaves = L;
-        int cnt = L > 0 ? L : 1, off = 0, l = 0;
-        for (;;) {
-            b.count[l] = cnt; b.offset[l] = off; off += cnt; ++l;
-            if (cnt == 1 || l == ICP_BVH_MAX_LEVELS) break;
-            cnt = (cnt + 31) / 32;
-        }
-        b.n_levels = l;
-        for (int k = l; k < ICP_BVH_MAX_LEVELS; ++k) { b.count[k] = 0; b.offset[k] = off; }
+        b.n_leaves = L; b.n_levels = 1;
+        for (int k = 0; k < ICP_BVH_MAX_LEVELS; ++k) { b.count[k] = 0; b.offset[k] = 0; b.coffset[k] = 0; }
+        b.count[0] = L;
         *bvh = b;
     }
 }
 
-// one warp per node (grid-stride): level 0 reads the leaf's points, level l > 0 reads 32 child boxes; an empty
-// node gets the box [+inf, -inf], which no search enters
+// Number of level-`lvl` nodes that start before sorted point position s (s is a boundary of a cell-tree node at or
+// above the level's nodes): leaves by leaf_rank, upper levels by the chain of per-level ranks.
+__device__ __forceinline__ unsigned int nodes_before(const BvhDesc& b, const unsigned int* __restrict__ leaf_rank,
+                                                     const unsigned int* __restrict__ node_rank, int lvl, unsigned int s) {
+    unsigned int a = leaf_rank[s];
+    for (int j = 1; j <= lvl; ++j) a = node_rank[b.coffset[j] + a];
+    return a;
+}
+
+// Level `lvl` (>= 1) from level lvl-1, step 1: node k of level lvl-1 starts a level-lvl node iff it is the first node of
+// the shallowest cell-tree node around it that holds <= 32 nodes of level lvl-1.  flags -> node_rank[coffset[lvl] + k].
+__global__ void mark_level_kernel(const float4* __restrict__ pts, const GridParams* __restrict__ gp, const unsigned int* __restrict__ cs,
+                                  int T, const unsigned int* __restrict__ leaf_start, const unsigned int* __restrict__ leaf_rank,
+                                  const unsigned int* __restrict__ pstart, unsigned int* __restrict__ node_rank,
+                                  const BvhDesc* __restrict__ bvh, int lvl) {
+    const BvhDesc b = *bvh;
+    if (b.n_levels != lvl) return;                         // the level below is not the current top, or the tree is complete
+    const int prev = lvl - 1, n_prev = b.count[prev];
+    if (n_prev <= 32) return;                              // the level below already is the top
+    const GridParams g = *gp;
+    unsigned int* flags = node_rank + b.coffset[lvl];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_prev; k += gridDim.x * blockDim.x) {
+        if (k == n_prev) { flags[k] = 0u; continue; }
+        const unsigned int pos = prev == 0 ? leaf_start[k] : pstart[b.offset[prev] + k];
+        const float4 p = pts[pos];
+        const unsigned int c = cell_code(g, p.x, p.y, p.z);
+        const unsigned int sT = cs[c], eT = cs[(size_t)c + 1];
+        const unsigned int aT = nodes_before(b, leaf_rank, node_rank, prev, sT), bT = nodes_before(b, leaf_rank, node_rank, prev, eT);
+        if (bT - aT > 32u) { flags[k] = ((unsigned int)k - aT) % 32u == 0u ? 1u : 0u; continue; }   // over-full finest cell: runs of 32
+        int lo = 0, hi = T;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1, sh = T - mid;
+            const unsigned int pre = c >> sh;
+            const unsigned int cnt = nodes_before(b, leaf_rank, node_rank, prev, cs[((size_t)pre + 1) << sh]) -
+                                     nodes_before(b, leaf_rank, node_rank, prev, cs[(size_t)pre << sh]);
+            if (cnt <= 32u) hi = mid; else lo = mid + 1;
+        }
+        const int sh = T - lo;
+        flags[k] = (unsigned int)k == nodes_before(b, leaf_rank, node_rank, prev, cs[(size_t)(c >> sh) << sh]) ? 1u : 0u;
+    }
+}
+
+// step 2 (one block): exclusive scan of the level's flags in place; the descriptor gains the level
+__global__ void scan_level_kernel(unsigned int* __restrict__ node_rank, BvhDesc* __restrict__ bvh, int lvl) {
+    __shared__ unsigned int carry_s;
+    __shared__ unsigned int total;
+    const BvhDesc b = *bvh;
+    if (b.n_levels != lvl || b.count[lvl - 1] <= 32) return;
+    const int n = b.count[lvl - 1] + 1;
+    unsigned int* data = node_rank + b.coffset[lvl];
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < n ? data[i] : 0u;
+        const unsigned int ex = block_exclusive_scan(v, &total);
+        const unsigned int carry = carry_s;
+        if (i < n) data[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int cnt = (int)carry_s;
+        bvh->count[lvl] = cnt;
+        bvh->offset[lvl] = b.offset[lvl - 1] + b.count[lvl - 1];
+        if (lvl + 1 < ICP_BVH_MAX_LEVELS) bvh->coffset[lvl + 1] = b.coffset[lvl] + n;     // this level used n rank entries and cnt+1 <= n child entries
+        bvh->n_levels = lvl + 1;
+    }
+}
+
+// step 3: children ranges and start positions of the level's nodes
+__global__ void level_children_kernel(const unsigned int* __restrict__ leaf_start, const unsigned int* __restrict__ node_rank,
+                                      unsigned int* __restrict__ child_start, unsigned int* __restrict__ pstart,
+                                      const BvhDesc* __restrict__ bvh, int lvl) {
+    const BvhDesc b = *bvh;
+    if (b.n_levels != lvl + 1) return;                     // the level was not created
+    const int prev = lvl - 1, n_prev = b.count[prev];
+    const unsigned int* rank = node_rank + b.coffset[lvl];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_prev; k += gridDim.x * blockDim.x) {
+        if (k == n_prev) { child_start[b.coffset[lvl] + b.count[lvl]] = (unsigned int)n_prev; continue; }
+        if (rank[k + 1] != rank[k]) {
+            child_start[b.coffset[lvl] + rank[k]] = (unsigned int)k;
+            pstart[b.offset[lvl] + rank[k]] = prev == 0 ? leaf_start[k] : pstart[b.offset[prev] + k];
+        }
+    }
+}
+
+// one warp per node (grid-stride): level 0 reads the leaf's points, level l > 0 reads its (<= 32) child boxes
 __global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ leaf_start,
-                                 const BvhDesc* __restrict__ bvh, float4* __restrict__ box, int level) {
+                                 const unsigned int* __restrict__ child_start, const BvhDesc* __restrict__ bvh, float4* __restrict__ box,
+                                 int level) {
     const BvhDesc b = *bvh;
     if (level >= b.n_levels) return;
     const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
@@ -299,13 +381,11 @@ __global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned 
     for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < count; node += warps) {
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         if (level == 0) {
-            if (node < b.n_leaves) {
-                const unsigned int i = leaf_start[node] + lane;
-                if (i < leaf_start[node + 1]) { const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
-            }
+            const unsigned int i = leaf_start[node] + lane;
+            if (i < leaf_start[node + 1]) { const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
         } else {
-            const int c = node * 32 + lane;
-            if (c < b.count[level - 1]) {
+            const unsigned int c = child_start[b.coffset[level] + node] + lane;
+            if (c < child_start[b.coffset[level] + node + 1]) {
                 const float4 u = box[2 * (size_t)(b.offset[level - 1] + c)], v = box[2 * (size_t)(b.offset[level - 1] + c) + 1];
                 lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; hi[0] = v.x; hi[1] = v.y; hi[2] = v.z;
             }
@@ -322,28 +402,31 @@ __global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned 
 }
 
 size_t icp_bvh_max_nodes(int n) {
-    // worst case: every point its own leaf
-    size_t cnt = (size_t)(n > 0 ? n : 1), tot = 0;
-    for (int l = 0; l < ICP_BVH_MAX_LEVELS; ++l) { tot += cnt; if (cnt == 1) break; cnt = (cnt + 31) / 32; }
-    return tot + 8;
+    // worst case: every point its own leaf, and every upper level only halves the node count until the cap
+    return (size_t)(n > 0 ? n : 1) * 2 + 64;
 }
 
-static cudaError_t launch_exclusive_scan(unsigned int* data, int n, unsigned int* block_sums, cudaStream_t s, int* launches);
-
 cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
-                                 unsigned int* flags_scratch, unsigned int* block_sums, unsigned int* leaf_start, BvhDesc* bvh_dev,
-                                 float4* box, int n_sms, cudaStream_t s, int* n_launches) {
+                                 unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
+                                 unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
+                                 cudaStream_t s, int* n_launches) {
     int launches = 0;
-    mark_leaves_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(pts_sorted, n, grid, cell_start, T, flags_scratch); ++launches;
-    cudaError_t e = launch_exclusive_scan(flags_scratch, n + 1, block_sums, s, &launches);
+    mark_leaves_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(pts_sorted, n, grid, cell_start, T, leaf_rank); ++launches;
+    cudaError_t e = launch_exclusive_scan(leaf_rank, n + 1, block_sums, s, &launches);
     if (e != cudaSuccess) return e;
-    leaf_starts_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(flags_scratch, n, cell_start, T, leaf_start, bvh_dev); ++launches;
-    // number of levels an n-point cloud can need (the real count is on the device; surplus launches return at once)
-    int max_levels = 1; { long long c = n > 0 ? n : 1; while (c > 1 && max_levels < ICP_BVH_MAX_LEVELS) { c = (c + 31) / 32; ++max_levels; } }
-    for (int l = 0; l < max_levels; ++l) {
-        long long nodes = n > 0 ? n : 1; for (int k = 0; k < l; ++k) nodes = (nodes + 31) / 32;
-        long long nb = (nodes + 7) / 8; if (nb > 8ll * n_sms) nb = 8ll * n_sms; if (nb < 1) nb = 1;
-        bvh_level_kernel<<<(int)nb, 256, 0, s>>>(pts_sorted, leaf_start, bvh_dev, box, l); ++launches;
+    leaf_starts_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(leaf_rank, n, cell_start, T, leaf_start, bvh_dev); ++launches;
+    long long nb0 = ((long long)(n > 0 ? n : 1) + 7) / 8; if (nb0 > 8ll * n_sms) nb0 = 8ll * n_sms;
+    bvh_level_kernel<<<(int)nb0, 256, 0, s>>>(pts_sorted, leaf_start, child_start, bvh_dev, box, 0); ++launches;
+    // Upper levels: the node counts live on the device, so every possible level gets its (tiny) launches; the ones
+    // past the top return at once.  An n-point cloud with healthy fill needs log_16(n / 16) levels; cap the launches there + 2.
+    int max_levels = 2; { long long c = (n > 0 ? n : 1) / 16; while (c > 32 && max_levels < ICP_BVH_MAX_LEVELS) { c /= 8; ++max_levels; } }
+    if (max_levels > ICP_BVH_MAX_LEVELS) max_levels = ICP_BVH_MAX_LEVELS;
+    for (int l = 1; l < max_levels; ++l) {
+        const int nb = l == 1 ? 2 * n_sms : n_sms / 2;
+        mark_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, grid, cell_start, T, leaf_start, leaf_rank, pstart, node_rank, bvh_dev, l); ++launches;
+        scan_level_kernel<<<1, 1024, 0, s>>>(node_rank, bvh_dev, l); ++launches;
+        level_children_kernel<<<nb, 256, 0, s>>>(leaf_start, node_rank, child_start, pstart, bvh_dev, l); ++launches;
+        bvh_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, leaf_start, child_start, bvh_dev, box, l); ++launches;
     }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();

@@ -41,17 +41,21 @@ struct GridParams {
     int pad;
 };
 
-// 32-ary bounding-volume hierarchy over the cell-sorted target (grid.cu).  Level 0 = leaves: the nodes of
-// the implicit cell tree with <= 32 points (disjoint, cell-aligned runs of the sorted array, leaf j =
-// [leaf_start[j], leaf_start[j+1])); level l+1 groups 32 consecutive nodes of level l.  Every node stores the
-// TIGHT axis-aligned box of its points as two float4 {lo.xyz,_} {hi.xyz,_} at box[2*(offset[l]+j)].
-// The number of leaves is only known on the device, so the descriptor lives in device memory.
+// Bounding-volume hierarchy over the cell-sorted target (grid.cu), fan-out <= 32.  Every node of every level is
+// a node of the implicit cell tree (an aligned box of the grid), so the nodes of one level are pairwise disjoint
+// in space: level 0 = leaves = cell-tree nodes with <= 32 points (leaf j = sorted points [leaf_start[j],
+// leaf_start[j+1])); a level-l node = a cell-tree node with <= 32 nodes of level l-1 (its children are the
+// consecutive nodes [child_start[coffset[l]+j], child_start[coffset[l]+j+1]) of level l-1).  Every node stores the
+// TIGHT axis-aligned box of its points as two float4 {lo.xyz,_} {hi.xyz,_} at box[2*(offset[l]+j)].  The top level
+// is the first one with <= 32 nodes (a search tests all of them in one step).  Node counts are only known on the
+// device, so the descriptor lives in device memory.
 #define ICP_BVH_MAX_LEVELS 7
 struct BvhDesc {
-    int n_levels;                      // levels 0 .. n_levels-1; the top level has one node
+    int n_levels;                      // levels 0 .. n_levels-1
     int n_leaves;
     int count[ICP_BVH_MAX_LEVELS];     // nodes per level
-    int offset[ICP_BVH_MAX_LEVELS];    // first node of the level in the box array
+    int offset[ICP_BVH_MAX_LEVELS];    // first node of the level in the box array and in pstart[]
+    int coffset[ICP_BVH_MAX_LEVELS];   // first entry of the level in child_start[] (count+1 entries per level >= 1)
 };
 
 // One ICP iteration's query set.  Queries are addressed by p = position in the Morton-sorted source
@@ -107,6 +111,8 @@ struct MatchArgs {
     const float4* bvh_box;   // tight boxes of the BVH nodes (grid order only)
     const BvhDesc* bvh;      // device-resident
     const unsigned int* leaf_start;
+    const unsigned int* child_start; // children ranges of the levels >= 1
+    const unsigned int* leaf_rank;   // [n_tgt + 2] number of leaf starts before sorted position i: leaf of point i = leaf_rank[i + 1] - 1
     // projective
     float fx, fy, cx, cy; unsigned int width, height;
     // config
@@ -141,11 +147,13 @@ cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, in
                                   unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
                                   unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
                                   cudaStream_t s, int* n_launches);
-// Tight-box 32-ary BVH over the cell-sorted cloud (uses keys / ranks as scratch; leaf_start has n + 2 entries).
+// Tight-box BVH over the cell-sorted cloud.  leaf_rank: n + 2 entries (kept: maps a sorted position to its leaf);
+// leaf_start: n + 2; node_scratch / child_start / pstart: icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS entries each.
 size_t icp_bvh_max_nodes(int n);
 cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
-                                 unsigned int* flags_scratch, unsigned int* block_sums, unsigned int* leaf_start, BvhDesc* bvh_dev,
-                                 float4* box, int n_sms, cudaStream_t s, int* n_launches);
+                                 unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
+                                 unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
+                                 cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective

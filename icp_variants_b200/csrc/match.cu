@@ -173,7 +173,7 @@ __device__ __forceinline__ void seed_best(const MatchArgs& a, const Query& q, in
 
 // ---------------------------------------------------------------------------- BVH search, one warp per query
 #define BVH_WARPS 4
-#define BVH_STACK (32 * ICP_BVH_MAX_LEVELS)   // <= 32 pushed children per level below the top
+#define BVH_STACK (32 * ICP_BVH_MAX_LEVELS)   // <= 32 pushed children per level
 
 // fp32 lower bound (under D1's rounding and association, by monotonicity) of the squared distance from q
 // to any point inside the box
@@ -182,6 +182,49 @@ __device__ __forceinline__ float box_dist2(const Query& q, const float4 lo, cons
     const float gy = fmaxf(fmaxf(psub(lo.y, q.y), psub(q.y, hi.y)), 0.0f);
     const float gz = fmaxf(fmaxf(psub(lo.z, q.z), psub(q.z, hi.z)), 0.0f);
     return padd(padd(pmul(gx, gx), pmul(gy, gy)), pmul(gz, gz));
+}
+
+// Tests the nodes [first, last) (last - first <= 32) of level L against the query, lane = node.  Leaves that can still
+// matter are scanned at once, nearest first (lane = point); internal nodes are pushed.
+template <bool COLOR>
+__device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh, const Query& q, Best& b, float& bound, int L,
+                                          unsigned int first, unsigned int last, unsigned int* st_node, float* st_lb, int& top, int lane,
+                                          unsigned int lt_mask, unsigned int& ev, unsigned int& nd) {
+    const unsigned int FULL = 0xFFFFFFFFu;
+    const unsigned int c = first + lane;
+    float clb = FLT_BIG; bool keep = false;
+    if (c < last) {
+        const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
+        clb = box_dist2(q, lo, hi);
+        keep = !(clb > bound);
+    }
+    if (L == 0) {
+        unsigned int ls = 0, le = 0;
+        if (keep) { ls = __ldg(&a.leaf_start[c]); le = __ldg(&a.leaf_start[c + 1]); }
+        unsigned int key = keep ? __float_as_uint(clb) : 0xFFFFFFFFu;
+        for (;;) {
+            const unsigned int kmin = __reduce_min_sync(FULL, key);
+            if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bound) break;
+            const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
+            const unsigned int s0 = __shfl_sync(FULL, ls, src), e0 = __shfl_sync(FULL, le, src);
+            if (lane == src) key = 0xFFFFFFFFu;
+            const unsigned int i = s0 + lane;
+            if (i < e0) {
+                const float4 pt = __ldg(&a.tgt_pts[i]);
+                const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
+                const int idx = __float_as_int(pt.w);
+                if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                ++ev;
+            }
+            if (lane == 0) ++nd;
+            bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));   // d >= 0: bit order = value order
+        }
+        return;
+    }
+    const unsigned int mk = __ballot_sync(FULL, keep);
+    if (keep) { const int s = top + __popc(mk & lt_mask); st_node[s] = ((unsigned int)L << 27) | c; st_lb[s] = clb; }
+    top += __popc(mk);
+    __syncwarp();
 }
 
 template <bool COLOR>
@@ -198,6 +241,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const BvhDesc& bvh = s_bvh;
     const int top_level = bvh.n_levels - 1;
+    const unsigned int n_top = (unsigned int)bvh.count[top_level];
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
     unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -210,97 +254,74 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         if (lane == 0) ++nq;
         Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
         if (finite3(q.x, q.y, q.z) && bvh.n_leaves > 0) {
-            seed_best<COLOR>(a, q, p, b);                                       // uniform: every lane starts from the seed
-            if (b.pos < 0 && top_level > 0) {
-                // No neighbour remembered (first iteration): follow the nearest child down to one leaf and take its best
-                // point as the starting bound, so that the walk below prunes from its first step on.
-                int j = 0;
-                for (int lvl = top_level; lvl > 0; --lvl) {
-                    const int cl = lvl - 1, c = j * 32 + lane;
-                    unsigned int key = 0xFFFFFFFFu;
-                    if (c < bvh.count[cl]) {
-                        const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c) + 1]);
-                        key = __float_as_uint(box_dist2(q, lo, hi));
-                    }
-                    const unsigned int kmin = __reduce_min_sync(FULL, key);
-                    j = j * 32 + (__ffs((int)__ballot_sync(FULL, key == kmin)) - 1);
-                }
-                const unsigned int i = __ldg(&a.leaf_start[j]) + lane;
-                if (i < __ldg(&a.leaf_start[j + 1])) {
-                    const float4 c = __ldg(&a.tgt_pts[i]);
-                    const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
-                    const int idx = __float_as_int(c.w);
-                    if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
-                }
-            }
-            float bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
-            int top = 1;
-            if (lane == 0) { st_node[0] = (unsigned int)top_level << 27; st_lb[0] = 0.0f; }
-            __syncwarp();
-            while (top > 0) {
-                --top;
-                const unsigned int nd_id = st_node[top]; const float nlb = st_lb[top];
-                __syncwarp();
-                if (nlb > bound) continue;
-                const int lvl = (int)(nd_id >> 27), j = (int)(nd_id & 0x7FFFFFFu);
-                if (lane == 0) ++nd;
-                if (lvl == 0) {                                                 // only when the whole tree is one leaf
-                    const unsigned int ls = __ldg(&a.leaf_start[j]), le = __ldg(&a.leaf_start[j + 1]);
-                    const unsigned int i = ls + lane;
-                    if (i < le) {
+            // Start from the neighbour this query had before: scan that neighbour's whole leaf (lane = point).  After a
+            // small pose change the new neighbour is almost always in it, so the walk starts with a (nearly) final bound.
+            {
+                const int sp = a.use_seed ? a.nn_pos[p] : -1;
+                if (sp >= 0 && sp < a.n_tgt) {
+                    const unsigned int j = __ldg(&a.leaf_rank[sp + 1]) - 1u;
+                    const unsigned int i = __ldg(&a.leaf_start[j]) + lane;
+                    if (i < __ldg(&a.leaf_start[j + 1])) {
                         const float4 c = __ldg(&a.tgt_pts[i]);
                         const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
                         const int idx = __float_as_int(c.w);
                         if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
                         ++ev;
                     }
-                    bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));   // d >= 0: bit order = value order
-                    continue;
                 }
-                // lane = child
-                const int cl = lvl - 1, c = j * 32 + lane;
-                float clb = FLT_BIG; bool keep = false;
-                if (c < bvh.count[cl]) {
-                    const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[cl] + c) + 1]);
-                    clb = box_dist2(q, lo, hi);
-                    keep = !(clb > bound);
-                }
-                if (cl == 0) {
-                    // the children are leaves: scan the ones that can still matter, nearest first
-                    unsigned int ls = 0, le = 0;
-                    if (keep) { ls = __ldg(&a.leaf_start[c]); le = __ldg(&a.leaf_start[c + 1]); }
-                    unsigned int key = keep ? __float_as_uint(clb) : 0xFFFFFFFFu;
-                    for (;;) {
-                        const unsigned int kmin = __reduce_min_sync(FULL, key);
-                        if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bound) break;
-                        const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
-                        const unsigned int s0 = __shfl_sync(FULL, ls, src), e0 = __shfl_sync(FULL, le, src);
-                        if (lane == src) key = 0xFFFFFFFFu;
-                        const unsigned int i = s0 + lane;
-                        if (i < e0) {
-                            const float4 pt = __ldg(&a.tgt_pts[i]);
-                            const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
-                            const int idx = __float_as_int(pt.w);
-                            if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
-                            ++ev;
+            }
+            if (!__any_sync(FULL, b.pos >= 0) && top_level > 0) {
+                // No neighbour remembered (first iteration): follow the nearest node down to one leaf and take its best
+                // point as the starting bound, so that the walk below prunes from its first step on.
+                int L = top_level; unsigned int first = 0, last = n_top;
+                unsigned int best_node = 0;
+                for (;;) {
+                    unsigned int kbest = 0xFFFFFFFFu; best_node = first;
+                    for (unsigned int base = first; base < last; base += 32) {
+                        const unsigned int c = base + lane;
+                        unsigned int key = 0xFFFFFFFFu;
+                        if (c < last) {
+                            const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
+                            key = __float_as_uint(box_dist2(q, lo, hi));
                         }
-                        if (lane == 0) ++nd;
-                        bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
+                        const unsigned int kmin = __reduce_min_sync(FULL, key);
+                        if (kmin < kbest) { kbest = kmin; best_node = base + (unsigned int)(__ffs((int)__ballot_sync(FULL, key == kmin)) - 1); }
                     }
-                    continue;
+                    if (L == 0) break;
+                    first = __ldg(&a.child_start[bvh.coffset[L] + best_node]); last = __ldg(&a.child_start[bvh.coffset[L] + best_node + 1]);
+                    --L;
                 }
-                // push the surviving children (any order is correct; the bound is already tight, see below)
-                const unsigned int mk = __ballot_sync(FULL, keep);
-                if (keep) { const int s = top + __popc(mk & lt_mask); st_node[s] = ((unsigned int)cl << 27) | (unsigned int)c; st_lb[s] = clb; }
-                top += __popc(mk);
-                __syncwarp();
+                const unsigned int i = __ldg(&a.leaf_start[best_node]) + lane;
+                if (i < __ldg(&a.leaf_start[best_node + 1])) {
+                    const float4 c = __ldg(&a.tgt_pts[i]);
+                    const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
+                    const int idx = __float_as_int(c.w);
+                    if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                    ++ev;
+                }
+            }
+            float bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
+            int top = 0;
+            // the nodes of the top level (<= 32 unless the level cap was hit), 32 at a time, each batch followed depth-first
+            for (unsigned int base = 0; base < n_top; base += 32) {
+                bvh_visit<COLOR>(a, bvh, q, b, bound, top_level, base, min(base + 32u, n_top), st_node, st_lb, top, lane, lt_mask, ev, nd);
+                if (lane == 0) ++nd;
+                while (top > 0) {
+                    --top;
+                    const unsigned int nd_id = st_node[top]; const float nlb = st_lb[top];
+                    __syncwarp();
+                    if (nlb > bound) continue;
+                    const int lvl = (int)(nd_id >> 27); const unsigned int j = nd_id & 0x7FFFFFFu;
+                    if (lane == 0) ++nd;
+                    const unsigned int first = __ldg(&a.child_start[bvh.coffset[lvl] + j]), last = __ldg(&a.child_start[bvh.coffset[lvl] + j + 1]);
+                    bvh_visit<COLOR>(a, bvh, q, b, bound, lvl - 1, first, last, st_node, st_lb, top, lane, lt_mask, ev, nd);
+                }
             }
             // warp arg-min on (d, idx)
             const unsigned int dmin = __reduce_min_sync(FULL, __float_as_uint(b.d));
             const int cand = (__float_as_uint(b.d) == dmin) ? b.idx : INT_MAX;
             const int imin = __reduce_min_sync(FULL, cand);
-            const unsigned int who = __ballot_sync(FULL, cand == imin);
-            const int src_lane = __ffs((int)who) - 1;
+            const int src_lane = __ffs((int)__ballot_sync(FULL, cand == imin)) - 1;
             b.d = __uint_as_float(dmin); b.idx = imin; b.pos = __shfl_sync(FULL, b.pos, src_lane);
             if (b.idx == INT_MAX) b.pos = -1;
         }
