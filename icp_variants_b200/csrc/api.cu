@@ -83,7 +83,7 @@ struct icp_gpu_ctx {
     DeviceBuf sgrid, scell_start, order_dev;
     int Ts = 0;
     // loop state
-    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, partials, pose_dev, history;
+    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, qbuf, partials, pose_dev, history;
     float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
     IterDesc* h_desc = nullptr;                                                       // pinned, DESC_TOTAL
     int n_reduce_blocks = 1;
@@ -247,7 +247,7 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
         }
         const size_t n1 = (size_t)(n > 0 ? n : 1);
         if (ensure(ctx, ctx->match_pos, n1 * 4) || ensure(ctx, ctx->match_w, n1 * 4) || ensure(ctx, ctx->match_idx, n1 * 4) ||
-            ensure(ctx, ctx->nn_pos, n1 * 4)) return ICP_GPU_E_CUDA;
+            ensure(ctx, ctx->nn_pos, n1 * 4) || ensure(ctx, ctx->qbuf, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
         ctx->n_reduce_blocks = icp_reduce_blocks((int)n, ctx->n_sms);
         if (ensure(ctx, ctx->partials, (size_t)ctx->n_reduce_blocks * ICP_NRED * sizeof(double))) return ICP_GPU_E_CUDA;
         if (build_source(ctx)) return ICP_GPU_E_CUDA;
@@ -361,7 +361,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
     a.max_d2 = c->cfg.max_distance_sq;
     a.match_pos = (int*)c->match_pos.p; a.match_w = (float*)c->match_w.p; a.match_idx = want_idx ? (int*)c->match_idx.p : nullptr;
-    a.nn_pos = (int*)c->nn_pos.p;
+    a.nn_pos = (int*)c->nn_pos.p; a.qbuf = (float4*)c->qbuf.p;
     a.desc_index = desc_index;
     a.use_seed = grid_order ? 1 : 0;
     a.collect_stats = c->cfg.collect_stats;
@@ -475,8 +475,9 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         float idx_ms = 0.f;
         if (ctx->grid_built && cudaEventElapsedTime(&idx_ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->index_ms = idx_ms; else cudaGetLastError();
         timings->total_ms = tot; timings->index_ms = ctx->index_ms; timings->n_iterations = plan.n_iters;
-        timings->n_match_launches = plan.n_iters;
-        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters;
+        const int per_match = algo == 0 ? 3 : 1;
+        timings->n_match_launches = plan.n_iters * per_match;
+        timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters * per_match;
         for (auto& e : marks) cudaEventDestroy(e);
     }
     return ICP_GPU_OK;
@@ -568,7 +569,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart};
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);

@@ -123,6 +123,7 @@ struct MatchArgs {
     float* match_w;
     int* match_idx;          // original target index (API output), may be null
     int* nn_pos;             // nearest neighbour found the last time p was a query (-1 none): seeds the next search
+    float4* qbuf;            // transformed query points of the current iteration {x,y,z,rgba}; x = NaN: not searched
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
     int use_seed;
     int collect_stats;       // work counters in DevState (atomics); off in timed runs

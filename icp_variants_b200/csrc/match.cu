@@ -227,72 +227,59 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
     __syncwarp();
 }
 
+// The BVH search is split in three launches so that only the walk itself pays the one-warp-per-query price:
+//   knn_prep_kernel     thread per query: selection predicate + transformPoints -> qbuf {x,y,z,rgba}; x = NaN: not searched
+//   knn_bvh_kernel      warp per query: seed leaf, walk, arg-min -> nn_pos[p]
+//   match_finish_kernel thread per query: transformNormals, weighting, rejection -> the match records
+__global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
+    __shared__ PoseSm sm;
+    load_pose(sm, a.state_ro);
+    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_src) return;
+    const float4 p4 = __ldg(&a.src_pts[p]);
+    const float4 n4 = __ldg(&a.src_nrm[p]);
+    float4 o = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, n4.w);
+    if (query_active(d, a.mask, p4, n4)) {
+        float x, y, z;
+        xform_point(sm.P, p4.x, p4.y, p4.z, x, y, z);
+        if (finite3(x, y, z)) { o.x = x; o.y = y; o.z = z; }
+    }
+    a.qbuf[p] = o;
+}
+
 template <bool COLOR>
 __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs a) {
-    __shared__ PoseSm sm;
     __shared__ unsigned int s_node[BVH_WARPS][BVH_STACK];
     __shared__ float s_lb[BVH_WARPS][BVH_STACK];
     __shared__ BvhDesc s_bvh;
     if (threadIdx.x < sizeof(BvhDesc) / 4) reinterpret_cast<int*>(&s_bvh)[threadIdx.x] = reinterpret_cast<const int*>(a.bvh)[threadIdx.x];
-    load_pose(sm, a.state_ro);      // __syncthreads inside
+    __syncthreads();
     const unsigned int FULL = 0xFFFFFFFFu;
-    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const BvhDesc& bvh = s_bvh;
     const int top_level = bvh.n_levels - 1;
     const unsigned int n_top = (unsigned int)bvh.count[top_level];
-    unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
+    unsigned int ev = 0, nd = 0;
     unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
     const unsigned int lt_mask = (1u << lane) - 1u;
+    if (bvh.n_leaves <= 0) return;                 // empty target: match_finish_kernel sees nn_pos = -1 (set_target reset it)
     for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < a.n_src; p += warps) {
-        Query q; float snx, sny, snz; unsigned int s_rgba;
-        if (!prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {            // warp-uniform
-            if (lane == 0) write_no_query(a, p);
-            continue;
-        }
-        if (lane == 0) ++nq;
+        const float4 q4 = __ldg(&a.qbuf[p]);
+        if (!(q4.x == q4.x)) continue;                                          // not a (searchable) query this iteration
+        Query q; q.x = q4.x; q.y = q4.y; q.z = q4.z;
+        const unsigned int s_rgba = __float_as_uint(q4.w);
+        q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
         Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
-        if (finite3(q.x, q.y, q.z) && bvh.n_leaves > 0) {
-            // Start from the neighbour this query had before: scan that neighbour's whole leaf (lane = point).  After a
-            // small pose change the new neighbour is almost always in it, so the walk starts with a (nearly) final bound.
-            {
-                const int sp = a.use_seed ? a.nn_pos[p] : -1;
-                if (sp >= 0 && sp < a.n_tgt) {
-                    const unsigned int j = __ldg(&a.leaf_rank[sp + 1]) - 1u;
-                    const unsigned int i = __ldg(&a.leaf_start[j]) + lane;
-                    if (i < __ldg(&a.leaf_start[j + 1])) {
-                        const float4 c = __ldg(&a.tgt_pts[i]);
-                        const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
-                        const int idx = __float_as_int(c.w);
-                        if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
-                        ++ev;
-                    }
-                }
-            }
-            if (!__any_sync(FULL, b.pos >= 0) && top_level > 0) {
-                // No neighbour remembered (first iteration): follow the nearest node down to one leaf and take its best
-                // point as the starting bound, so that the walk below prunes from its first step on.
-                int L = top_level; unsigned int first = 0, last = n_top;
-                unsigned int best_node = 0;
-                for (;;) {
-                    unsigned int kbest = 0xFFFFFFFFu; best_node = first;
-                    for (unsigned int base = first; base < last; base += 32) {
-                        const unsigned int c = base + lane;
-                        unsigned int key = 0xFFFFFFFFu;
-                        if (c < last) {
-                            const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
-                            key = __float_as_uint(box_dist2(q, lo, hi));
-                        }
-                        const unsigned int kmin = __reduce_min_sync(FULL, key);
-                        if (kmin < kbest) { kbest = kmin; best_node = base + (unsigned int)(__ffs((int)__ballot_sync(FULL, key == kmin)) - 1); }
-                    }
-                    if (L == 0) break;
-                    first = __ldg(&a.child_start[bvh.coffset[L] + best_node]); last = __ldg(&a.child_start[bvh.coffset[L] + best_node + 1]);
-                    --L;
-                }
-                const unsigned int i = __ldg(&a.leaf_start[best_node]) + lane;
-                if (i < __ldg(&a.leaf_start[best_node + 1])) {
+        // Start from the neighbour this query had before: scan that neighbour's whole leaf (lane = point).  After a
+        // small pose change the new neighbour is almost always in it, so the walk starts with a (nearly) final bound.
+        {
+            const int sp = a.use_seed ? a.nn_pos[p] : -1;
+            if (sp >= 0 && sp < a.n_tgt) {
+                const unsigned int j = __ldg(&a.leaf_rank[sp + 1]) - 1u;
+                const unsigned int i = __ldg(&a.leaf_start[j]) + lane;
+                if (i < __ldg(&a.leaf_start[j + 1])) {
                     const float4 c = __ldg(&a.tgt_pts[i]);
                     const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
                     const int idx = __float_as_int(c.w);
@@ -300,37 +287,84 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                     ++ev;
                 }
             }
-            float bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
-            int top = 0;
-            // the nodes of the top level (<= 32 unless the level cap was hit), 32 at a time, each batch followed depth-first
-            for (unsigned int base = 0; base < n_top; base += 32) {
-                bvh_visit<COLOR>(a, bvh, q, b, bound, top_level, base, min(base + 32u, n_top), st_node, st_lb, top, lane, lt_mask, ev, nd);
-                if (lane == 0) ++nd;
-                while (top > 0) {
-                    --top;
-                    const unsigned int nd_id = st_node[top]; const float nlb = st_lb[top];
-                    __syncwarp();
-                    if (nlb > bound) continue;
-                    const int lvl = (int)(nd_id >> 27); const unsigned int j = nd_id & 0x7FFFFFFu;
-                    if (lane == 0) ++nd;
-                    const unsigned int first = __ldg(&a.child_start[bvh.coffset[lvl] + j]), last = __ldg(&a.child_start[bvh.coffset[lvl] + j + 1]);
-                    bvh_visit<COLOR>(a, bvh, q, b, bound, lvl - 1, first, last, st_node, st_lb, top, lane, lt_mask, ev, nd);
-                }
-            }
-            // warp arg-min on (d, idx)
-            const unsigned int dmin = __reduce_min_sync(FULL, __float_as_uint(b.d));
-            const int cand = (__float_as_uint(b.d) == dmin) ? b.idx : INT_MAX;
-            const int imin = __reduce_min_sync(FULL, cand);
-            const int src_lane = __ffs((int)__ballot_sync(FULL, cand == imin)) - 1;
-            b.d = __uint_as_float(dmin); b.idx = imin; b.pos = __shfl_sync(FULL, b.pos, src_lane);
-            if (b.idx == INT_MAX) b.pos = -1;
         }
-        if (lane == 0) {
-            a.nn_pos[p] = b.pos;
-            finish_match(a, p, b.pos >= 0, 1.0f, b.idx, b.pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+        if (!__any_sync(FULL, b.pos >= 0) && top_level > 0) {
+            // No neighbour remembered (first iteration): follow the nearest node down to one leaf and take its best
+            // point as the starting bound, so that the walk below prunes from its first step on.
+            int L = top_level; unsigned int first = 0, last = n_top;
+            unsigned int best_node = 0;
+            for (;;) {
+                unsigned int kbest = 0xFFFFFFFFu; best_node = first;
+                for (unsigned int base = first; base < last; base += 32) {
+                    const unsigned int c = base + lane;
+                    unsigned int key = 0xFFFFFFFFu;
+                    if (c < last) {
+                        const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
+                        key = __float_as_uint(box_dist2(q, lo, hi));
+                    }
+                    const unsigned int kmin = __reduce_min_sync(FULL, key);
+                    if (kmin < kbest) { kbest = kmin; best_node = base + (unsigned int)(__ffs((int)__ballot_sync(FULL, key == kmin)) - 1); }
+                }
+                if (L == 0) break;
+                first = __ldg(&a.child_start[bvh.coffset[L] + best_node]); last = __ldg(&a.child_start[bvh.coffset[L] + best_node + 1]);
+                --L;
+            }
+            const unsigned int i = __ldg(&a.leaf_start[best_node]) + lane;
+            if (i < __ldg(&a.leaf_start[best_node + 1])) {
+                const float4 c = __ldg(&a.tgt_pts[i]);
+                const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
+                const int idx = __float_as_int(c.w);
+                if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                ++ev;
+            }
+        }
+        float bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
+        int top = 0;
+        // the nodes of the top level (<= 32 unless the level cap was hit), 32 at a time, each batch followed depth-first
+        for (unsigned int base = 0; base < n_top; base += 32) {
+            bvh_visit<COLOR>(a, bvh, q, b, bound, top_level, base, min(base + 32u, n_top), st_node, st_lb, top, lane, lt_mask, ev, nd);
+            if (lane == 0) ++nd;
+            while (top > 0) {
+                --top;
+                const unsigned int nd_id = st_node[top]; const float nlb = st_lb[top];
+                __syncwarp();
+                if (nlb > bound) continue;
+                const int lvl = (int)(nd_id >> 27); const unsigned int j = nd_id & 0x7FFFFFFu;
+                if (lane == 0) ++nd;
+                const unsigned int first = __ldg(&a.child_start[bvh.coffset[lvl] + j]), last = __ldg(&a.child_start[bvh.coffset[lvl] + j + 1]);
+                bvh_visit<COLOR>(a, bvh, q, b, bound, lvl - 1, first, last, st_node, st_lb, top, lane, lt_mask, ev, nd);
+            }
+        }
+        // warp arg-min on (d, idx)
+        const unsigned int dmin = __reduce_min_sync(FULL, __float_as_uint(b.d));
+        const int cand = (__float_as_uint(b.d) == dmin) ? b.idx : INT_MAX;
+        const int imin = __reduce_min_sync(FULL, cand);
+        const int src_lane = __ffs((int)__ballot_sync(FULL, cand == imin)) - 1;
+        const int pos = imin == INT_MAX ? -1 : __shfl_sync(FULL, b.pos, src_lane);
+        if (lane == 0) a.nn_pos[p] = pos;
+    }
+    flush_stats(a, 0u, 0u, ev, nd);
+}
+
+__global__ void __launch_bounds__(256) match_finish_kernel(const MatchArgs a) {
+    __shared__ PoseSm sm;
+    load_pose(sm, a.state_ro);
+    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int nq = 0, nm = 0;
+    if (p < a.n_src) {
+        Query q; float snx, sny, snz; unsigned int s_rgba;
+        if (prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {
+            ++nq;
+            int pos = finite3(q.x, q.y, q.z) ? a.nn_pos[p] : -1;
+            if (pos >= a.n_tgt) pos = -1;
+            const int idx = pos >= 0 ? __float_as_int(__ldg(&a.tgt_pts[pos].w)) : -1;
+            finish_match(a, p, pos >= 0, 1.0f, idx, pos, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
+        } else {
+            write_no_query(a, p);
         }
     }
-    flush_stats(a, nq, nm, ev, nd);
+    flush_stats(a, nq, nm, 0u, 0u);
 }
 
 // Small targets: one warp per query, lanes stride over the target (original order, L1-resident),
@@ -422,10 +456,12 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
         ++launches;
     } else {
+        knn_prep_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches;
         int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
         if (nb > 64 * n_sms) nb = 64 * n_sms;
         if (a.color_icp) knn_bvh_kernel<true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
         ++launches;
+        match_finish_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches;
     }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();
