@@ -401,6 +401,82 @@ __global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned 
     }
 }
 
+// ---------------------------------------------------------------------------- leaf adjacency
+// One warp per leaf l: all other leaves whose box meets box(l) inflated by R, found by a box query on the BVH
+// (lane = child).  R starts at twice the leaf's largest extent and is halved until the list fits in 32 entries.
+#define ADJ_WARPS 4
+__device__ __forceinline__ bool boxes_meet(const float* lo, const float* hi, const float4 blo, const float4 bhi) {
+    return blo.x <= hi[0] && bhi.x >= lo[0] && blo.y <= hi[1] && bhi.y >= lo[1] && blo.z <= hi[2] && bhi.z >= lo[2];
+}
+
+__global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const BvhDesc* __restrict__ bvh, const float4* __restrict__ box,
+                                                                         const unsigned int* __restrict__ child_start,
+                                                                         unsigned int* __restrict__ adj, int* __restrict__ adj_n,
+                                                                         float* __restrict__ adj_r, int capacity) {
+    __shared__ unsigned int s_node[ADJ_WARPS][32 * ICP_BVH_MAX_LEVELS];
+    __shared__ unsigned int s_list[ADJ_WARPS][64];
+    const BvhDesc b = *bvh;
+    const unsigned int FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_leaves = min(b.n_leaves, capacity);
+    const int top_level = b.n_levels - 1;
+    unsigned int* st = s_node[wid]; unsigned int* list = s_list[wid];
+    const unsigned int lt = (1u << lane) - 1u;
+    for (int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < n_leaves; l += warps) {
+        const float4 mlo = box[2 * (size_t)l], mhi = box[2 * (size_t)l + 1];      // level 0 has offset 0
+        float R = 2.0f * fmaxf(fmaxf(mhi.x - mlo.x, mhi.y - mlo.y), mhi.z - mlo.z);
+        int count = 0; bool ok = false;
+        for (int attempt = 0; attempt < 5 && !ok; ++attempt, R *= 0.5f) {
+            const float lo[3] = {__fsub_rd(mlo.x, R), __fsub_rd(mlo.y, R), __fsub_rd(mlo.z, R)};
+            const float hi[3] = {__fadd_ru(mhi.x, R), __fadd_ru(mhi.y, R), __fadd_ru(mhi.z, R)};
+            count = 0; ok = true;
+            int top = 0;
+            // virtual root over the top level, then depth-first; leaves are appended to the list
+            for (unsigned int base = 0; base < (unsigned int)b.count[top_level] && ok; base += 32) {
+                int L = top_level; unsigned int first = base, last = min(base + 32u, (unsigned int)b.count[top_level]);
+                for (;;) {
+                    const unsigned int c = first + lane;
+                    bool keep = false;
+                    if (c < last) keep = boxes_meet(lo, hi, box[2 * (size_t)(b.offset[L] + c)], box[2 * (size_t)(b.offset[L] + c) + 1]);
+                    if (L == 0) keep = keep && c != (unsigned int)l;
+                    const unsigned int mk = __ballot_sync(FULL, keep);
+                    if (L == 0) {
+                        if (count + __popc(mk) > 32) { ok = false; break; }
+                        if (keep) list[count + __popc(mk & lt)] = c;
+                        count += __popc(mk);
+                    } else {
+                        if (keep) st[top + __popc(mk & lt)] = ((unsigned int)L << 27) | c;
+                        top += __popc(mk);
+                    }
+                    __syncwarp();
+                    if (top == 0) break;
+                    --top;
+                    const unsigned int id = st[top];
+                    __syncwarp();
+                    const int lvl = (int)(id >> 27); const unsigned int j = id & 0x7FFFFFFu;
+                    first = child_start[b.coffset[lvl] + j]; last = child_start[b.coffset[lvl] + j + 1];
+                    L = lvl - 1;
+                }
+            }
+            if (ok) break;
+        }
+        __syncwarp();
+        if (lane < count && ok) adj[(size_t)l * 32 + lane] = list[lane];
+        if (lane == 0) { adj_n[l] = ok ? count : 0; adj_r[l] = ok ? R : -1.0f; }
+        __syncwarp();
+    }
+}
+
+cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
+                                      int* adj_n, float* adj_r, int capacity, int n_sms, cudaStream_t s, int* n_launches) {
+    long long nb = ((long long)capacity + ADJ_WARPS - 1) / ADJ_WARPS;
+    if (nb > 16ll * n_sms) nb = 16ll * n_sms;
+    if (nb < 1) nb = 1;
+    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_n, adj_r, capacity);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
 size_t icp_bvh_max_nodes(int n) {
     // worst case: every point its own leaf, and every upper level only halves the node count until the cap
     return (size_t)(n > 0 ? n : 1) * 2 + 64;

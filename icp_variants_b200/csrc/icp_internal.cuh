@@ -113,6 +113,9 @@ struct MatchArgs {
     const unsigned int* leaf_start;
     const unsigned int* child_start; // children ranges of the levels >= 1
     const unsigned int* leaf_rank;   // [n_tgt + 2] number of leaf starts before sorted position i: leaf of point i = leaf_rank[i + 1] - 1
+    // Leaf adjacency (grid.cu): adj[32*l .. 32*l + adj_n[l]) = every other leaf whose box meets box(l) inflated by adj_r[l];
+    // adj_r[l] < 0: no list.  A query whose search ball lies inside that inflated box needs no tree walk.
+    const unsigned int* adj; const int* adj_n; const float* adj_r; int adj_capacity;
     // projective
     float fx, fy, cx, cy; unsigned int width, height;
     // config
@@ -155,6 +158,9 @@ cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridPara
                                  unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
                                  unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
                                  cudaStream_t s, int* n_launches);
+// Leaf adjacency lists for the leaves [0, min(n_leaves, capacity)).
+cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
+                                      int* adj_n, float* adj_r, int capacity, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective

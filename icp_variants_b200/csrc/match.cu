@@ -184,6 +184,34 @@ __device__ __forceinline__ float box_dist2(const Query& q, const float4 lo, cons
     return padd(padd(pmul(gx, gx), pmul(gy, gy)), pmul(gz, gz));
 }
 
+// Lane l proposes leaf `leaf` with box distance clb (keep = it can still matter): the proposed leaves are scanned
+// nearest first (lane = point) for as long as their box distance does not exceed the shrinking bound.
+template <bool COLOR>
+__device__ __forceinline__ void bvh_scan_leaves(const MatchArgs& a, const Query& q, Best& b, float& bound, unsigned int leaf, float clb,
+                                                bool keep, int lane, unsigned int& ev, unsigned int& nd) {
+    const unsigned int FULL = 0xFFFFFFFFu;
+    unsigned int ls = 0, le = 0;
+    if (keep) { ls = __ldg(&a.leaf_start[leaf]); le = __ldg(&a.leaf_start[leaf + 1]); }
+    unsigned int key = keep ? __float_as_uint(clb) : 0xFFFFFFFFu;
+    for (;;) {
+        const unsigned int kmin = __reduce_min_sync(FULL, key);
+        if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bound) break;
+        const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
+        const unsigned int s0 = __shfl_sync(FULL, ls, src), e0 = __shfl_sync(FULL, le, src);
+        if (lane == src) key = 0xFFFFFFFFu;
+        const unsigned int i = s0 + lane;
+        if (i < e0) {
+            const float4 pt = __ldg(&a.tgt_pts[i]);
+            const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
+            const int idx = __float_as_int(pt.w);
+            if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+            ++ev;
+        }
+        if (lane == 0) ++nd;
+        bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));   // d >= 0: bit order = value order
+    }
+}
+
 // Tests the nodes [first, last) (last - first <= 32) of level L against the query, lane = node.  Leaves that can still
 // matter are scanned at once, nearest first (lane = point); internal nodes are pushed.
 template <bool COLOR>
@@ -198,29 +226,7 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
         clb = box_dist2(q, lo, hi);
         keep = !(clb > bound);
     }
-    if (L == 0) {
-        unsigned int ls = 0, le = 0;
-        if (keep) { ls = __ldg(&a.leaf_start[c]); le = __ldg(&a.leaf_start[c + 1]); }
-        unsigned int key = keep ? __float_as_uint(clb) : 0xFFFFFFFFu;
-        for (;;) {
-            const unsigned int kmin = __reduce_min_sync(FULL, key);
-            if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bound) break;
-            const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
-            const unsigned int s0 = __shfl_sync(FULL, ls, src), e0 = __shfl_sync(FULL, le, src);
-            if (lane == src) key = 0xFFFFFFFFu;
-            const unsigned int i = s0 + lane;
-            if (i < e0) {
-                const float4 pt = __ldg(&a.tgt_pts[i]);
-                const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
-                const int idx = __float_as_int(pt.w);
-                if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
-                ++ev;
-            }
-            if (lane == 0) ++nd;
-            bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));   // d >= 0: bit order = value order
-        }
-        return;
-    }
+    if (L == 0) { bvh_scan_leaves<COLOR>(a, q, b, bound, c, clb, keep, lane, ev, nd); return; }
     const unsigned int mk = __ballot_sync(FULL, keep);
     if (keep) { const int s = top + __popc(mk & lt_mask); st_node[s] = ((unsigned int)L << 27) | c; st_lb[s] = clb; }
     top += __popc(mk);
@@ -273,22 +279,50 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
         Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
         // Start from the neighbour this query had before: scan that neighbour's whole leaf (lane = point).  After a
-        // small pose change the new neighbour is almost always in it, so the walk starts with a (nearly) final bound.
+        // small pose change the new neighbour is almost always in it, so the search starts with a (nearly) final bound.
+        int seed_leaf = -1;
         {
             const int sp = a.use_seed ? a.nn_pos[p] : -1;
             if (sp >= 0 && sp < a.n_tgt) {
-                const unsigned int j = __ldg(&a.leaf_rank[sp + 1]) - 1u;
-                const unsigned int i = __ldg(&a.leaf_start[j]) + lane;
-                if (i < __ldg(&a.leaf_start[j + 1])) {
+                seed_leaf = (int)(__ldg(&a.leaf_rank[sp + 1]) - 1u);
+                const unsigned int i = __ldg(&a.leaf_start[seed_leaf]) + lane;
+                if (i < __ldg(&a.leaf_start[seed_leaf + 1])) {
                     const float4 c = __ldg(&a.tgt_pts[i]);
                     const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
                     const int idx = __float_as_int(c.w);
                     if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
                     ++ev;
                 }
+                if (lane == 0) ++nd;
             }
         }
-        if (!__any_sync(FULL, b.pos >= 0) && top_level > 0) {
+        bool done = false;
+        if (seed_leaf >= 0 && seed_leaf < a.adj_capacity) {
+            // Shortcut without the tree: if the search ball lies inside the seed leaf's box inflated by R, every leaf
+            // that meets the ball is in that leaf's adjacency list (built with the same inflated box, grid.cu).
+            const float R = __ldg(&a.adj_r[seed_leaf]);
+            float bnd = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
+            if (R >= 0.0f && bnd < FLT_BIG) {
+                const float r = __fmul_ru(__fsqrt_ru(bnd), 1.00001f);
+                const float4 mlo = __ldg(&a.bvh_box[2 * (size_t)seed_leaf]), mhi = __ldg(&a.bvh_box[2 * (size_t)seed_leaf + 1]);
+                const bool inside = __fsub_rd(q.x, r) >= __fsub_rd(mlo.x, R) && __fadd_ru(q.x, r) <= __fadd_ru(mhi.x, R) &&
+                                    __fsub_rd(q.y, r) >= __fsub_rd(mlo.y, R) && __fadd_ru(q.y, r) <= __fadd_ru(mhi.y, R) &&
+                                    __fsub_rd(q.z, r) >= __fsub_rd(mlo.z, R) && __fadd_ru(q.z, r) <= __fadd_ru(mhi.z, R);
+                if (inside) {
+                    const int na = __ldg(&a.adj_n[seed_leaf]);
+                    unsigned int leaf = 0; float clb = FLT_BIG; bool keep = false;
+                    if (lane < na) {
+                        leaf = __ldg(&a.adj[(size_t)seed_leaf * 32 + lane]);
+                        clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                        keep = !(clb > bnd);
+                    }
+                    if (lane == 0) ++nd;
+                    bvh_scan_leaves<COLOR>(a, q, b, bnd, leaf, clb, keep, lane, ev, nd);
+                    done = true;
+                }
+            }
+        }
+        if (!done && !__any_sync(FULL, b.pos >= 0) && top_level > 0) {
             // No neighbour remembered (first iteration): follow the nearest node down to one leaf and take its best
             // point as the starting bound, so that the walk below prunes from its first step on.
             int L = top_level; unsigned int first = 0, last = n_top;
@@ -321,7 +355,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         float bound = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
         int top = 0;
         // the nodes of the top level (<= 32 unless the level cap was hit), 32 at a time, each batch followed depth-first
-        for (unsigned int base = 0; base < n_top; base += 32) {
+        for (unsigned int base = 0; base < n_top && !done; base += 32) {
             bvh_visit<COLOR>(a, bvh, q, b, bound, top_level, base, min(base + 32u, n_top), st_node, st_lb, top, lane, lt_mask, ev, nd);
             if (lane == 0) ++nd;
             while (top > 0) {
