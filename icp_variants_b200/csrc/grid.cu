@@ -12,6 +12,7 @@
 // keys+count -> scan (3) -> scatter.
 #include "icp_internal.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------- pack AoS3 -> float4
 __global__ void pack_cloud_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const uint8_t* __restrict__ rgba,
@@ -412,7 +413,7 @@ __device__ __forceinline__ bool boxes_meet(const float* lo, const float* hi, con
 __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const BvhDesc* __restrict__ bvh, const float4* __restrict__ box,
                                                                          const unsigned int* __restrict__ child_start,
                                                                          unsigned int* __restrict__ adj, int* __restrict__ adj_n,
-                                                                         float* __restrict__ adj_r, int capacity) {
+                                                                         float* __restrict__ adj_r, int capacity, float r_factor) {
     __shared__ unsigned int s_node[ADJ_WARPS][32 * ICP_BVH_MAX_LEVELS];
     __shared__ unsigned int s_list[ADJ_WARPS][64];
     const BvhDesc b = *bvh;
@@ -424,9 +425,9 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
     const unsigned int lt = (1u << lane) - 1u;
     for (int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < n_leaves; l += warps) {
         const float4 mlo = box[2 * (size_t)l], mhi = box[2 * (size_t)l + 1];      // level 0 has offset 0
-        float R = 2.0f * fmaxf(fmaxf(mhi.x - mlo.x, mhi.y - mlo.y), mhi.z - mlo.z);
+        float R = r_factor * fmaxf(fmaxf(mhi.x - mlo.x, mhi.y - mlo.y), mhi.z - mlo.z);
         int count = 0; bool ok = false;
-        for (int attempt = 0; attempt < 5 && !ok; ++attempt, R *= 0.5f) {
+        for (int attempt = 0; attempt < 6 && !ok; ++attempt, R *= 0.5f) {
             const float lo[3] = {__fsub_rd(mlo.x, R), __fsub_rd(mlo.y, R), __fsub_rd(mlo.z, R)};
             const float hi[3] = {__fadd_ru(mhi.x, R), __fadd_ru(mhi.y, R), __fadd_ru(mhi.z, R)};
             count = 0; ok = true;
@@ -472,7 +473,9 @@ cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box,
     long long nb = ((long long)capacity + ADJ_WARPS - 1) / ADJ_WARPS;
     if (nb > 16ll * n_sms) nb = 16ll * n_sms;
     if (nb < 1) nb = 1;
-    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_n, adj_r, capacity);
+    float r_factor = 2.0f;
+    if (const char* e = getenv("ICP_GPU_ADJ_FACTOR")) r_factor = (float)atof(e);   // tuning knob
+    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_n, adj_r, capacity, r_factor);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
