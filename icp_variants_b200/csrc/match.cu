@@ -437,42 +437,86 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
     flush_stats(a, nq, nm, ev, nd);
 }
 
-// Projective matching (NearestNeighbor.h:333-421): literal restatement of the window scan, unsigned
-// wrap-around included, one thread per query; neighbouring threads read neighbouring target pixels.
-__global__ void __launch_bounds__(ICP_MATCH_THREADS) projective_kernel(const MatchArgs a) {
+// Projective matching (NearestNeighbor.h:333-421): restatement of the window scan, unsigned wrap-around included
+// (a query whose projection is closer than 12 px to the low image border wraps and scans nothing).  One thread per
+// query; a block's 256 queries are consecutive in the Morton-sorted source, i.e. a compact patch that projects to a
+// compact image region: the block stages the union of its search windows (target points, row by row, coalesced) in
+// shared memory and every thread scans its own 25x25 window there.  Blocks whose union does not fit fall back to
+// reading the (L2-resident) target map directly.
+#define PROJ_THREADS 256
+#define PROJ_TILE_MAX 3000     // float4 entries (48 KB static shared memory)
+__global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
+    __shared__ float4 tile[PROJ_TILE_MAX];
+    __shared__ unsigned int s_box[4][PROJ_THREADS / 32];
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int searchWindow = 12u;                                 // NearestNeighbor.h:319
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
-    if (p < a.n_src) {
-        Query q; float snx, sny, snz; unsigned int s_rgba;
-        if (prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba)) {
+    Query q; float snx = 0.f, sny = 0.f, snz = 0.f; unsigned int s_rgba = 0;
+    q.x = q.y = q.z = 0.f; q.cr = q.cg = q.cb = 0.f;
+    const bool in = p < a.n_src;
+    const bool is_query = in && prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba);
+    const bool scans = is_query && !(q.x == MINF_F);                       // :372-373
+    unsigned int uP = 0, vP = 0, u0 = 0xFFFFFFFFu, v0 = 0xFFFFFFFFu, u1 = 0, v1 = 0;
+    bool has_window = false;
+    if (scans) {
+        uP = x86_float_to_u32(roundf(padd(pdiv(pmul(q.x, a.fx), q.z), a.cx)));   // :378-379
+        vP = x86_float_to_u32(roundf(padd(pdiv(pmul(q.y, a.fy), q.z), a.cy)));
+        // the loops of :385-386 start at vP-12 / uP-12 (unsigned) and stop at the high border or vP+12 / uP+12
+        const unsigned int vs = vP - searchWindow, us = uP - searchWindow;
+        if (vs < a.height && us < a.width && vs <= vP + searchWindow && us <= uP + searchWindow) {
+            has_window = true;
+            u0 = us; v0 = vs;
+            u1 = min(uP + searchWindow, a.width - 1u); v1 = min(vP + searchWindow, a.height - 1u);
+        }
+    }
+    // union of the block's windows
+    unsigned int bu0 = __reduce_min_sync(0xFFFFFFFFu, u0), bv0 = __reduce_min_sync(0xFFFFFFFFu, v0);
+    unsigned int bu1 = __reduce_max_sync(0xFFFFFFFFu, has_window ? u1 : 0u), bv1 = __reduce_max_sync(0xFFFFFFFFu, has_window ? v1 : 0u);
+    if (lane == 0) { s_box[0][wid] = bu0; s_box[1][wid] = bv0; s_box[2][wid] = bu1; s_box[3][wid] = bv1; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < PROJ_THREADS / 32; ++w) { bu0 = min(bu0, s_box[0][w]); bv0 = min(bv0, s_box[1][w]); bu1 = max(bu1, s_box[2][w]); bv1 = max(bv1, s_box[3][w]); }
+    const bool any_window = bu0 != 0xFFFFFFFFu;
+    const unsigned int tw = any_window ? bu1 - bu0 + 1u : 0u, th = any_window ? bv1 - bv0 + 1u : 0u;
+    const bool staged = any_window && (unsigned long long)tw * th <= PROJ_TILE_MAX;      // block-uniform
+    if (staged) {
+        for (unsigned int k = threadIdx.x; k < tw * th; k += PROJ_THREADS) {
+            const unsigned int ty = k / tw, tx = k - ty * tw;
+            tile[k] = __ldg(&a.tgt_pts[(size_t)a.width * (bv0 + ty) + bu0 + tx]);
+        }
+    }
+    __syncthreads();
+    if (in) {
+        if (!is_query) write_no_query(a, p);
+        else {
             ++nq;
-            if (q.x == MINF_F) {
+            if (!scans) {
                 // :372-373 `continue` leaves the value-initialised Match{0, 0.f} (:353)
                 finish_match(a, p, true, 0.0f, 0, 0, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
             } else {
-                const unsigned int searchWindow = 12u;                         // NearestNeighbor.h:319
-                const unsigned int uP = x86_float_to_u32(roundf(padd(pdiv(pmul(q.x, a.fx), q.z), a.cx)));
-                const unsigned int vP = x86_float_to_u32(roundf(padd(pdiv(pmul(q.y, a.fy), q.z), a.cy)));
                 float minDist = FLT_BIG; unsigned int idx = 0xFFFFFFFFu;
-                for (unsigned int v = vP - searchWindow; (v < a.height && v <= vP + searchWindow); v++) {
-                    for (unsigned int u = uP - searchWindow; (u < a.width && u <= uP + searchWindow); u++) {
-                        const unsigned int ni = a.width * v + u;
-                        const float4 t = __ldg(&a.tgt_pts[ni]);
-                        if (t.x == MINF_F) continue;
-                        const float dx = psub(q.x, t.x), dy = psub(q.y, t.y), dz = psub(q.z, t.z);
-                        const float dist = padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));
-                        ++ev;
-                        if (minDist > dist) { idx = ni; minDist = dist; }
+                if (has_window) {
+                    for (unsigned int v = v0; v <= v1; v++) {
+                        const float4* row = staged ? &tile[(v - bv0) * tw + (u0 - bu0)] : &a.tgt_pts[(size_t)a.width * v + u0];
+                        const unsigned int n_u = u1 - u0 + 1u;
+#pragma unroll 5
+                        for (unsigned int k = 0; k < n_u; k++) {
+                            const float4 t = staged ? row[k] : __ldg(&row[k]);
+                            if (t.x == MINF_F) continue;                                   // :392
+                            const float dx = psub(q.x, t.x), dy = psub(q.y, t.y), dz = psub(q.z, t.z);
+                            const float dist = padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));
+                            ++ev;
+                            if (minDist > dist) { idx = a.width * v + u0 + k; minDist = dist; }   // :399 strict: first minimum in scan order
+                        }
                     }
                 }
-                const bool ok = minDist <= a.max_d2 && idx != 0xFFFFFFFFu;
+                const bool ok = minDist <= a.max_d2 && idx != 0xFFFFFFFFu;               // :407
                 finish_match(a, p, ok, 1.0f, (int)idx, (int)idx, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
             }
-        } else {
-            write_no_query(a, p);
         }
     }
     flush_stats(a, nq, nm, ev, nd);
@@ -483,7 +527,7 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
     const int T = ICP_MATCH_THREADS;
     int launches = 0;
     if (algorithm == 2) {
-        projective_kernel<<<(a.n_src + T - 1) / T, T, 0, s>>>(a); ++launches;
+        projective_kernel<<<(a.n_src + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, s>>>(a); ++launches;
     } else if (algorithm == 1) {
         const long long threads = (long long)a.n_src * 32;
         const int nb = (int)((threads + T - 1) / T);
