@@ -323,9 +323,18 @@ __device__ __forceinline__ bool grid_reduce_row(double (&v)[32], double* __restr
     __threadfence();
     {
         const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-        double s = 0.0;
-        for (int b = g; b < (int)gridDim.x; b += THREADS / 32) s += __ldcg(&partials[(size_t)b * ICP_NRED + c]);
-        fin[g][c] = s;
+        // fixed order (deterministic); four independent chains so that the loads overlap
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const int step = THREADS / 32, nb = (int)gridDim.x;
+        int b = g;
+        for (; b + 3 * step < nb; b += 4 * step) {
+            s0 += __ldcg(&partials[(size_t)b * ICP_NRED + c]);
+            s1 += __ldcg(&partials[(size_t)(b + step) * ICP_NRED + c]);
+            s2 += __ldcg(&partials[(size_t)(b + 2 * step) * ICP_NRED + c]);
+            s3 += __ldcg(&partials[(size_t)(b + 3 * step) * ICP_NRED + c]);
+        }
+        for (; b < nb; b += step) s0 += __ldcg(&partials[(size_t)b * ICP_NRED + c]);
+        fin[g][c] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
     if (threadIdx.x < 32) {

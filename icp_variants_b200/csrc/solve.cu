@@ -10,6 +10,7 @@
 // (ICPOptimizer.h:666-674, ProcrustesAligner.h:6-70), estimatePosePointToPlane (:676-782),
 // estimatePoseSymmetricICP (:784-898), pose accumulation (:614-620).
 #include "icp_internal.cuh"
+#include <stdlib.h>
 
 struct PoseSmR { float P[16]; };
 
@@ -277,8 +278,10 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
 }
 
 int icp_reduce_blocks(int n_src, int n_sms) {
-    int nb = (n_src + ICP_REDUCE_THREADS * 4 - 1) / (ICP_REDUCE_THREADS * 4);   // ~4 points per thread
-    if (nb > 2 * n_sms) nb = 2 * n_sms;
+    int nb = (n_src + ICP_REDUCE_THREADS - 1) / ICP_REDUCE_THREADS;
+    int per_sm = 2;
+    if (const char* e = getenv("ICP_GPU_REDUCE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 32) per_sm = v; }   // tuning knob
+    if (nb > per_sm * n_sms) nb = per_sm * n_sms;
     if (nb < 1) nb = 1;
     return nb;
 }
