@@ -60,6 +60,7 @@ struct Plan {
     int n_iters = 0;
     std::vector<IterDesc> desc;         // n_iters entries
     std::vector<uint32_t> mask;         // concatenated selection masks, one bit per original source index (mt19937 mode)
+    std::vector<int> voxel_depth;       // voxel pyramid: grid depth of every mask slot built on the device
 };
 
 }  // namespace
@@ -81,7 +82,7 @@ struct icp_gpu_ctx {
     int adj_capacity = 0;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
     // source grid: only its sort order is used (consecutive queries are spatial neighbours: coherent tree walks)
-    DeviceBuf sgrid, scell_start, order_dev;
+    DeviceBuf sgrid, scell_start, order_dev, voxel_table;
     int Ts = 0;
     // loop state
     DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, qbuf, partials, pose_dev, history;
@@ -134,9 +135,11 @@ int bind(icp_gpu_ctx* ctx) {
 }
 
 int pick_T(int n) {
-    // ~2-4 points per occupied cell for surface-like clouds: cells = 4..8 x points
+    // cells = ICP_CELLS_PER_POINT x points (surface-like clouds occupy a small fraction of them)
+    long long factor = ICP_CELLS_PER_POINT;
+    if (const char* e = getenv("ICP_GPU_CELLS_PER_POINT")) { const long long v = atoll(e); if (v >= 1 && v <= 64) factor = v; }   // tuning knob
     int T = 3;
-    while (T < 24 && (1ll << T) < 8ll * (long long)(n > 0 ? n : 1)) ++T;
+    while (T < 24 && (1ll << T) < factor * (long long)(n > 0 ? n : 1)) ++T;
     if (T > 3 * ICP_MAX_BITS_PER_AXIS) T = 3 * ICP_MAX_BITS_PER_AXIS;
     return T;
 }
@@ -310,6 +313,7 @@ int make_plan(icp_gpu_ctx* ctx, Plan& plan) {
     const bool dev_rng = cfg.selection == ICP_GPU_SELECT_RANDOM && cfg.selection_rng == ICP_GPU_RNG_DEVICE;
     if (host_rng && cfg.multires && fetch_src_finite(ctx)) return ICP_GPU_E_CUDA;
     const size_t mask_words = ((size_t)(n > 0 ? n : 1) + 31) / 32;
+    const bool voxel = cfg.multires && cfg.pyramid_mode == ICP_GPU_PYRAMID_VOXEL;
     int stride = cfg.multires ? coarsest_stride(n) : 1;
     Mt19937 rng; uint32_t n_selections = 0;
     if (host_rng) rng.seed(cfg.seed + n_selections++);      // PointSelection ctor -> initSampler
@@ -318,6 +322,15 @@ int make_plan(icp_gpu_ctx* ctx, Plan& plan) {
         if (plan.n_iters >= ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "more than %d iterations", ICP_MAX_ITERS);
         IterDesc d; memset(&d, 0, sizeof(d));
         d.stride = stride; d.mask_word_offset = -1; d.filter_finite = cfg.multires ? 1 : 0; d.proba = -1.0f;
+        if (voxel && stride > 1) {
+            // level = one point per occupied source-grid cell at depth Ts' - ceil(1.5 log2 stride)
+            int k = 0; while ((1 << k) < stride) ++k;
+            int D = (ctx->Ts < 22 ? ctx->Ts : 22) - (3 * k + 1) / 2; if (D < 0) D = 0;
+            int slot = -1;
+            for (size_t j = 0; j < plan.voxel_depth.size(); ++j) if (plan.voxel_depth[j] == D) slot = (int)j;
+            if (slot < 0) { slot = (int)plan.voxel_depth.size(); plan.voxel_depth.push_back(D); }
+            d.stride = 1; d.mask_word_offset = (int)((size_t)slot * mask_words);
+        }
         if (dev_rng) { d.proba = (float)cfg.proba; d.rng_key = cfg.seed * 2654435761u + (uint32_t)(i + 1) * 0x9E3779B9u; }
         if (host_rng) {
             // resample(): one draw per point of the current level's cloud, in order (selection.h:88-104)
@@ -421,6 +434,18 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     // descriptors + selection lists + pose up (pinned staging, stream-ordered)
     memcpy(ctx->h_desc, plan.desc.data(), sizeof(IterDesc) * (size_t)plan.n_iters);
     if (plan.n_iters > 0) CU(cudaMemcpyAsync(ctx->desc.p, ctx->h_desc, sizeof(IterDesc) * (size_t)plan.n_iters, cudaMemcpyHostToDevice, ctx->stream));
+    if (!plan.voxel_depth.empty()) {
+        const size_t mask_words = ((size_t)(ctx->n_src > 0 ? ctx->n_src : 1) + 31) / 32;
+        int dmax = 0; for (int D : plan.voxel_depth) dmax = D > dmax ? D : dmax;
+        if (ensure(ctx, ctx->mask, plan.voxel_depth.size() * mask_words * sizeof(uint32_t)) ||
+            ensure(ctx, ctx->voxel_table, sizeof(unsigned int) * ((size_t)1 << dmax))) return ICP_GPU_E_CUDA;
+        int launches = 0;
+        for (size_t j = 0; j < plan.voxel_depth.size(); ++j)
+            CU(icp_launch_voxel_level((const float4*)ctx->src_pts.p, (const float4*)ctx->src_nrm.p, ctx->n_src, (const GridParams*)ctx->sgrid.p,
+                                      ctx->Ts, plan.voxel_depth[j], (unsigned int*)ctx->voxel_table.p, (unsigned int*)ctx->mask.p + j * mask_words,
+                                      mask_words, ctx->stream, &launches));
+        ctx->stats.n_kernel_launches += (uint64_t)launches;
+    }
     if (!plan.mask.empty()) {
         if (ensure(ctx, ctx->mask, plan.mask.size() * sizeof(uint32_t))) return ICP_GPU_E_CUDA;
         CU(cudaMemcpyAsync(ctx->mask.p, plan.mask.data(), plan.mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -580,7 +605,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_n, &ctx->adj_r};
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_n, &ctx->adj_r, &ctx->voxel_table};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);
@@ -619,7 +644,9 @@ int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
     if (c->selection_rng < 0 || c->selection_rng > 1) return fail(ctx, ICP_GPU_E_ARG, "selection_rng %d", c->selection_rng);
     if (c->weighting < 0 || c->weighting > 3) return fail(ctx, ICP_GPU_E_ARG, "weighting %d", c->weighting);
     if (c->nn_algorithm < 0 || c->nn_algorithm > 2) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
-    if (c->pyramid_mode != ICP_GPU_PYRAMID_STRIDE) return fail(ctx, ICP_GPU_E_ARG, "pyramid_mode %d", c->pyramid_mode);
+    if (c->pyramid_mode != ICP_GPU_PYRAMID_STRIDE && c->pyramid_mode != ICP_GPU_PYRAMID_VOXEL) return fail(ctx, ICP_GPU_E_ARG, "pyramid_mode %d", c->pyramid_mode);
+    if (c->multires && c->pyramid_mode == ICP_GPU_PYRAMID_VOXEL && c->selection == ICP_GPU_SELECT_RANDOM && c->selection_rng == ICP_GPU_RNG_MT19937)
+        return fail(ctx, ICP_GPU_E_ARG, "voxel pyramid levels are built on the device: use the device selection stream with them");
     if (c->n_iterations < 0 || c->n_iterations > ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "n_iterations %d (max %d)", c->n_iterations, ICP_MAX_ITERS);
     if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);
     if (c->matching == ICP_GPU_MATCH_PROJECTIVE && c->color_icp) return fail(ctx, ICP_GPU_E_ARG, "colour ICP is a k-NN variant (main.cpp:240-243)");

@@ -69,7 +69,7 @@ __global__ void grid_params_kernel(const unsigned int* __restrict__ bbox, int T,
         const float lo = empty ? 0.f : dec_f(bbox[a]), hi = empty ? 0.f : dec_f(bbox[3 + a]);
         P.o[a] = lo;
         maxabs[a] = fmaxf(fabsf(lo), fabsf(hi));
-        e[a] = fmaxf(hi - lo, 1e-20f + 1e-6f * maxabs[a]);   // zero-extent axes stay well defined
+        e[a] = fmaxf(psub(hi, lo), padd(1e-20f, pmul(1e-6f, maxabs[a])));   // zero-extent axes stay well defined (no FMA: the oracle restates this)
         P.bits[a] = 0;
     }
     // Level k of the implicit tree halves the axis whose cells are currently the longest.
@@ -80,11 +80,11 @@ __global__ void grid_params_kernel(const unsigned int* __restrict__ bbox, int T,
         for (int c = 0; c < 3; ++c) if (P.bits[c] < ICP_MAX_BITS_PER_AXIS && cur[c] > best) { best = cur[c]; a = c; }
         if (a < 0) a = 0;   // unreachable for T <= 3*ICP_MAX_BITS_PER_AXIS
         seq |= (unsigned long long)a << (2 * k);
-        P.bits[a] += 1; cur[a] *= 0.5f;
+        P.bits[a] += 1; cur[a] = pmul(cur[a], 0.5f);
     }
     for (int a = 0; a < 3; ++a) {
-        P.h[a] = e[a] * (1.0f + 1e-5f) / (float)(1 << P.bits[a]);
-        P.inv_h[a] = 1.0f / P.h[a];
+        P.h[a] = pdiv(pmul(e[a], 1.00001f), (float)(1 << P.bits[a]));
+        P.inv_h[a] = pdiv(1.0f, P.h[a]);
         P.delta[a] = 1e-3f * P.h[a] + 1e-6f * maxabs[a];
     }
     P.T = T; P.axis_seq = seq; P.n_finite = 0; P.pad = 0;
@@ -400,6 +400,43 @@ __global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned 
             box[2 * (size_t)(offset + node) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
+}
+
+// ---------------------------------------------------------------------------- voxel pyramid levels
+// ICP_GPU_PYRAMID_VOXEL: a pyramid level keeps ONE point per occupied cell of the source grid at depth D -- the valid
+// (finite point and normal) point with the lowest original index -- instead of every f-th point of the scan order
+// (PointCloud.h:325-343).  The level is delivered as a selection mask (bit per original index).
+__global__ void voxel_min_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, const GridParams* __restrict__ gp,
+                                 int T, int D, unsigned int* __restrict__ table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i], m = nrm[i];
+    if (!finite3(p.x, p.y, p.z) || !finite3(m.x, m.y, m.z)) return;
+    const GridParams g = *gp;
+    atomicMin(&table[cell_code(g, p.x, p.y, p.z) >> (T - D)], (unsigned int)__float_as_int(p.w));
+}
+__global__ void voxel_mask_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, const GridParams* __restrict__ gp,
+                                  int T, int D, const unsigned int* __restrict__ table, unsigned int* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i], m = nrm[i];
+    if (!finite3(p.x, p.y, p.z) || !finite3(m.x, m.y, m.z)) return;
+    const GridParams g = *gp;
+    const unsigned int o = (unsigned int)__float_as_int(p.w);
+    if (table[cell_code(g, p.x, p.y, p.z) >> (T - D)] == o) atomicOr(&mask[o >> 5], 1u << (o & 31u));
+}
+
+cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, int T, int D,
+                                   unsigned int* table, unsigned int* mask, size_t mask_words, cudaStream_t s, int* n_launches) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(table, 0xFF, sizeof(unsigned int) * ((size_t)1 << D), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(mask, 0, sizeof(unsigned int) * mask_words, s)) != cudaSuccess) return e;
+    if (n > 0) {
+        voxel_min_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_sorted, nrm_sorted, n, grid, T, D, table);
+        voxel_mask_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_sorted, nrm_sorted, n, grid, T, D, table, mask);
+        if (n_launches) *n_launches += 2;
+    }
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------- leaf adjacency

@@ -20,6 +20,7 @@
 #define ICP_REDUCE_THREADS 256
 #define ICP_MATCH_THREADS 128
 #define ICP_LEAF_MAX 8             // a grid node with <= this many points is scanned, not split
+#define ICP_CELLS_PER_POINT 32      // grid cells per point (2^T >= this x N); oracle/icp_oracle.c:orc_pick_T restates it
 #define ICP_MAX_BITS_PER_AXIS 10   // keeps the cell-index rounding error << the bound margin
 
 __device__ __forceinline__ float pmul(float a, float b) { return __fmul_rn(a, b); }
@@ -158,6 +159,9 @@ cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridPara
                                  unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
                                  unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
                                  cudaStream_t s, int* n_launches);
+// One voxel pyramid level (depth D of the source grid) as a selection mask; table: scratch of 2^D entries.
+cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, int T, int D,
+                                   unsigned int* table, unsigned int* mask, size_t mask_words, cudaStream_t s, int* n_launches);
 // Leaf adjacency lists for the leaves [0, min(n_leaves, capacity)).
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
                                       int* adj_n, float* adj_r, int capacity, int n_sms, cudaStream_t s, int* n_launches);

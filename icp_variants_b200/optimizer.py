@@ -140,6 +140,7 @@ class ICPOptimizer:
         self.selection_rng = 0        # 0 mt19937 (reference-compatible), 1 device stream
         self.nn_algorithm = 0         # 0 auto, 1 brute force, 2 tiled grid search, 3 per-query tree search
         self.use_graph = True
+        self.pyramid_mode = 0         # 0 the reference's stride pyramid, 1 voxel levels (extension)
         self.m_timeMeasure: TimeMeasure | None = None
         self.m_convergenceMeasure: ConvergenceMeasure | None = None
         self._camera = None
@@ -189,7 +190,7 @@ class ICPOptimizer:
         c.selection, c.proba, c.seed, c.selection_rng = self.selectionMethod, self.proba, self.seed & 0xFFFFFFFF, self.selection_rng
         c.weighting, c.rejection, c.max_distance_sq = self.weightingMethod, self.rejectionMethod, self.maxDistance
         c.color_icp, c.multires, c.n_iterations = int(self.colorICP), int(self.multiResolutionICP), self.m_nIterations
-        c.nn_algorithm, c.use_graph = self.nn_algorithm, int(self.use_graph)
+        c.nn_algorithm, c.use_graph, c.pyramid_mode = self.nn_algorithm, int(self.use_graph), self.pyramid_mode
         return c
 
     def setTarget(self, target: PointCloud):

@@ -25,7 +25,7 @@ public:
     ICPOptimizer()
         : metric{0}, colorICP{false}, multiResolutionICP{false}, selectionMethod{0}, proba{1.0}, rejectionMethod{1}, weightingMethod{0},
           matchingMethod{0}, m_nIterations{20}, m_timeMeasure{nullptr}, m_convergenceMeasure{nullptr}, maxDistance{0.0003f},
-          m_ctx{nullptr}, m_haveCamera{false}, m_seed{0}, m_selectionRng{ICP_GPU_RNG_MT19937}, m_width{0}, m_height{0} {
+          m_ctx{nullptr}, m_haveCamera{false}, m_seed{0}, m_selectionRng{ICP_GPU_RNG_MT19937}, m_width{0}, m_height{0}, m_pyramidMode{ICP_GPU_PYRAMID_STRIDE} {
         if (icp_gpu_create(&m_ctx, 0) != ICP_GPU_OK) { m_ctx = nullptr; std::cout << "icp_gpu: no usable CUDA device (there is no CPU fallback)." << std::endl; }
     }
     virtual ~ICPOptimizer() { if (m_ctx) icp_gpu_destroy(m_ctx); }
@@ -33,6 +33,8 @@ public:
     void setMatchingMaxDistance(float maxDistance) { this->maxDistance = maxDistance; }
     void setMetric(unsigned int metric) { this->metric = metric; }
     void enableMultiResolution(bool enableMultiResolution) { this->multiResolutionICP = enableMultiResolution; }
+    // extension: ICP_GPU_PYRAMID_VOXEL builds the levels by voxel downsampling instead of the reference's index stride
+    void setPyramidMode(int pyramidMode) { m_pyramidMode = pyramidMode; }
     void enableColorICP(bool colorICP) { this->colorICP = colorICP; }
     void setSelectionMethod(unsigned int selectionMethod, double proba = 1.0) { this->selectionMethod = selectionMethod; this->proba = proba; }
     void setRejectionMethod(unsigned int rejectionMethod) { this->rejectionMethod = rejectionMethod; }
@@ -79,7 +81,7 @@ protected:
     ConvergenceMeasure* m_convergenceMeasure;
     float maxDistance;   // squared distance
     icp_gpu_ctx* m_ctx;
-    Eigen::Matrix3f m_K; bool m_haveCamera; unsigned m_seed; int m_selectionRng; unsigned m_width, m_height;
+    Eigen::Matrix3f m_K; bool m_haveCamera; unsigned m_seed; int m_selectionRng; unsigned m_width, m_height; int m_pyramidMode;
 
     // body of estimatePose shared by both minimisers (ICPOptimizer.h:185-349 / :493-663)
     void run(int minimizer, const PointCloud& source, const PointCloud& target, Matrix4f& initialPose, bool calculateRMSE) {
@@ -89,7 +91,7 @@ protected:
         cfg.metric = (int32_t)metric; cfg.minimizer = minimizer; cfg.matching = (int32_t)matchingMethod;
         cfg.selection = (int32_t)selectionMethod; cfg.proba = proba; cfg.seed = m_seed; cfg.selection_rng = m_selectionRng;
         cfg.weighting = (int32_t)weightingMethod; cfg.rejection = (int32_t)rejectionMethod; cfg.max_distance_sq = maxDistance;
-        cfg.color_icp = colorICP ? 1 : 0; cfg.multires = multiResolutionICP ? 1 : 0; cfg.n_iterations = (int32_t)m_nIterations;
+        cfg.color_icp = colorICP ? 1 : 0; cfg.multires = multiResolutionICP ? 1 : 0; cfg.n_iterations = (int32_t)m_nIterations; cfg.pyramid_mode = m_pyramidMode;
         int rc = icp_gpu_set_config(m_ctx, &cfg);
         if (rc == ICP_GPU_OK && m_haveCamera) rc = icp_gpu_set_camera(m_ctx, m_K.data(), m_width, m_height);
         const auto& tp = target.getPoints(); const auto& tn = target.getNormals(); const auto& tc = target.getColors();

@@ -62,9 +62,12 @@ enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2 };
  * exactly as selection.h:88-104 does (reference-compatible for a given seed); 1 = counter-based
  * hash drawn on the device (fast, not reference-compatible).                                      */
 enum { ICP_GPU_RNG_MT19937 = 0, ICP_GPU_RNG_DEVICE = 1 };
-/* Multi-resolution level construction: 0 = index stride with finite filter, the reference's
- * PointCloud::getCoarseResolution (PointCloud.h:325-343).                                        */
-enum { ICP_GPU_PYRAMID_STRIDE = 0 };
+/* Multi-resolution level construction.  STRIDE: every f-th point of the scan order with finite point and
+ * normal, the reference's PointCloud::getCoarseResolution (PointCloud.h:325-343).  VOXEL: one point per occupied
+ * cell of a uniform grid over the source (the valid point with the lowest index; cell depth = grid depth -
+ * ceil(1.5 * log2 f)) -- spatially uniform levels; NOT what the reference computes, results differ.  Level count
+ * and iteration schedule are the reference's in both modes (ICPOptimizer.h:503-525,634-655).                  */
+enum { ICP_GPU_PYRAMID_STRIDE = 0, ICP_GPU_PYRAMID_VOXEL = 1 };
 
 typedef struct icp_gpu_config {
     int32_t  metric;            /* setMetric                 default 0      (ICPOptimizer.h:29)      */

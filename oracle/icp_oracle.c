@@ -44,7 +44,7 @@ void orc_default_config(orc_config* c) {
     memset(c, 0, sizeof(*c));
     c->metric = 0; c->minimizer = 0; c->matching = 0; c->selection = 0; c->proba = 1.0; c->seed = 0;
     c->weighting = 0; c->rejection = 1; c->max_distance_sq = 0.0003f; c->color_icp = 0; c->multires = 0;
-    c->n_iterations = 20; c->nn_mode = ORC_NN_KDTREE; c->lm_max_iterations = 10;
+    c->n_iterations = 20; c->nn_mode = ORC_NN_KDTREE; c->lm_max_iterations = 10; c->pyramid_mode = 0;
 }
 
 static inline int finite3(const float* p) { return isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]); }
@@ -799,6 +799,95 @@ int orc_coarsest_stride(int64_t n) {
     return (int)currentResolution;
 }
 
+/* ------------------------------------------------------------------ voxel pyramid levels (extension; restates csrc/grid.cu) */
+
+typedef struct { float o[3], h[3], inv_h[3]; int bits[3]; int T; int axis[64]; } orc_grid;
+
+static int orc_pick_T(int64_t n) {
+    int T = 3;
+    while (T < 24 && ((int64_t)1 << T) < 32 * (n > 0 ? n : 1)) ++T;   /* ICP_CELLS_PER_POINT */
+    return T;
+}
+
+static void orc_grid_params(const float* pts, int64_t n, int T, orc_grid* g) {
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; int any = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!finite3(pts + 3 * i)) continue;
+        for (int a = 0; a < 3; ++a) {
+            const float v = pts[3 * i + a];
+            if (!any || v < lo[a]) lo[a] = v;
+            if (!any || v > hi[a]) hi[a] = v;
+        }
+        any = 1;
+    }
+    float e[3], cur[3];
+    for (int a = 0; a < 3; ++a) {
+        g->o[a] = lo[a];
+        const float maxabs = fmaxf(fabsf(lo[a]), fabsf(hi[a]));
+        const float floor_ = 1e-20f + 1e-6f * maxabs;
+        const float ext = hi[a] - lo[a];
+        e[a] = ext > floor_ ? ext : floor_;
+        cur[a] = e[a]; g->bits[a] = 0;
+    }
+    for (int k = 0; k < T; ++k) {
+        int ax = -1; float best = -1.f;
+        for (int c = 0; c < 3; ++c) if (g->bits[c] < 10 && cur[c] > best) { best = cur[c]; ax = c; }
+        if (ax < 0) ax = 0;
+        g->axis[k] = ax; g->bits[ax] += 1; cur[ax] = cur[ax] * 0.5f;
+    }
+    for (int a = 0; a < 3; ++a) {
+        g->h[a] = (e[a] * 1.00001f) / (float)(1 << g->bits[a]);
+        g->inv_h[a] = 1.0f / g->h[a];
+    }
+    g->T = T;
+}
+
+static uint32_t orc_cell_code(const orc_grid* g, const float* p) {
+    int c[3], r[3];
+    for (int a = 0; a < 3; ++a) {
+        const float u = (p[a] - g->o[a]) * g->inv_h[a];
+        int i = (int)floorf(u);
+        const int hi = (1 << g->bits[a]) - 1;
+        c[a] = i < 0 ? 0 : (i > hi ? hi : i);
+        r[a] = g->bits[a];
+    }
+    uint32_t code = 0;
+    for (int k = 0; k < g->T; ++k) {
+        const int a = g->axis[k];
+        r[a] -= 1;
+        code = (code << 1) | (uint32_t)((c[a] >> r[a]) & 1);
+    }
+    return code;
+}
+
+typedef struct { uint32_t prefix; int32_t idx; } orc_vox;
+static int orc_vox_cmp(const void* a, const void* b) {
+    const orc_vox* x = (const orc_vox*)a; const orc_vox* y = (const orc_vox*)b;
+    if (x->prefix != y->prefix) return x->prefix < y->prefix ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+static int orc_i32_cmp(const void* a, const void* b) { const int32_t x = *(const int32_t*)a, y = *(const int32_t*)b; return x < y ? -1 : (x > y ? 1 : 0); }
+
+int64_t orc_voxel_indices(const float* pts, const float* nrm, int64_t n, int stride, int32_t* out) {
+    if (stride <= 1) return orc_coarse_indices(pts, nrm, n, 1, out);
+    const int T = orc_pick_T(n);
+    orc_grid g; orc_grid_params(pts, n, T, &g);
+    int k = 0; while ((1 << k) < stride) ++k;
+    int D = (T < 22 ? T : 22) - (3 * k + 1) / 2; if (D < 0) D = 0;
+    orc_vox* v = (orc_vox*)malloc(sizeof(orc_vox) * (size_t)(n > 0 ? n : 1));
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!finite3(pts + 3 * i) || !finite3(nrm + 3 * i)) continue;
+        v[m].prefix = orc_cell_code(&g, pts + 3 * i) >> (T - D); v[m].idx = (int32_t)i; ++m;
+    }
+    qsort(v, (size_t)m, sizeof(orc_vox), orc_vox_cmp);
+    int64_t c = 0;
+    for (int64_t j = 0; j < m; ++j) if (j == 0 || v[j].prefix != v[j - 1].prefix) out[c++] = v[j].idx;   /* lowest index of the cell */
+    free(v);
+    qsort(out, (size_t)c, sizeof(int32_t), orc_i32_cmp);
+    return c;
+}
+
 /* ------------------------------------------------------------------ pipeline */
 
 int orc_match_pipeline(const orc_config* cfg, const float pose[16],
@@ -851,7 +940,7 @@ int orc_estimate_pose(const orc_config* cfg,
     int32_t* level = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1));
     int32_t* sel = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1));
     int64_t n_level;
-    if (cfg->multires) n_level = orc_coarse_indices(src, src_n, n_src, stride, level);
+    if (cfg->multires) n_level = cfg->pyramid_mode == 1 ? orc_voxel_indices(src, src_n, n_src, stride, level) : orc_coarse_indices(src, src_n, n_src, stride, level);
     else { n_level = n_src; for (int64_t i = 0; i < n_src; ++i) level[i] = (int32_t)i; }
     orc_mt19937 rng; uint32_t n_selections = 0;
     orc_mt_seed(&rng, cfg->seed + n_selections++); /* PointSelection ctor -> initSampler */
@@ -905,7 +994,7 @@ int orc_estimate_pose(const orc_config* cfg,
             if (stride == 1 && i >= cfg->n_iterations - 1) break;
             if (stride == 1) continue;
             stride /= 2; if (stride < 1) stride = 1;
-            n_level = orc_coarse_indices(src, src_n, n_src, stride, level);
+            n_level = cfg->pyramid_mode == 1 ? orc_voxel_indices(src, src_n, n_src, stride, level) : orc_coarse_indices(src, src_n, n_src, stride, level);
             orc_mt_seed(&rng, cfg->seed + n_selections++);
         }
     }

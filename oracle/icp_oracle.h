@@ -50,6 +50,8 @@ typedef struct {
     uint32_t width, height;
     int32_t nn_mode;         /* ORC_NN_BRUTE (literal O(N*M)) or ORC_NN_KDTREE (same answers, fast) */
     int32_t lm_max_iterations; /* Ceres options.max_num_iterations = 10 (ICPOptimizer.h:358) */
+    int32_t pyramid_mode;    /* 0 = the reference's stride pyramid (PointCloud.h:325-343); 1 = voxel levels (extension of
+                                this repository, include/icp_gpu.h ICP_GPU_PYRAMID_VOXEL; not reference behaviour) */
 } orc_config;
 
 void orc_default_config(orc_config* c);
@@ -110,6 +112,10 @@ double orc_mt_canonical(orc_mt19937* r);
 int64_t orc_coarse_indices(const float* pts, const float* nrm, int64_t n, int stride, int32_t* out_idx);
 /* ICPOptimizer.h:503-516 */
 int orc_coarsest_stride(int64_t n);
+/* Voxel pyramid level (extension, not in the reference): the valid point with the lowest index of every occupied cell of
+ * the uniform source grid at depth min(T,22) - ceil(1.5 log2 stride).  Restates icp_variants_b200/csrc/grid.cu
+ * (grid_params_kernel, cell_code, voxel_*_kernel) operation by operation in fp32.  Ascending indices; returns the count. */
+int64_t orc_voxel_indices(const float* pts, const float* nrm, int64_t n, int stride, int32_t* out_idx);
 
 /* Whole registration: LinearICPOptimizer::estimatePose (ICPOptimizer.h:493-663) or
  * CeresICPOptimizer::estimatePose (:185-349).  pose_history (nullable) receives 16 floats per

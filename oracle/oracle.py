@@ -29,7 +29,8 @@ class _Config(C.Structure):
                 ("proba", C.c_double), ("seed", C.c_uint32), ("weighting", C.c_int32), ("rejection", C.c_int32),
                 ("max_distance_sq", C.c_float), ("color_icp", C.c_int32), ("multires", C.c_int32),
                 ("n_iterations", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
-                ("width", C.c_uint32), ("height", C.c_uint32), ("nn_mode", C.c_int32), ("lm_max_iterations", C.c_int32)]
+                ("width", C.c_uint32), ("height", C.c_uint32), ("nn_mode", C.c_int32), ("lm_max_iterations", C.c_int32),
+                ("pyramid_mode", C.c_int32)]
 
 
 MATCH_DTYPE = np.dtype([("idx", np.int32), ("weight", np.float32)])
@@ -71,12 +72,13 @@ class Config:
     height: int = 0
     nn_mode: int = 1            # 0 brute force, 1 exact kd-tree (same answers)
     lm_max_iterations: int = 10
+    pyramid_mode: int = 0       # 0 stride pyramid (reference), 1 voxel levels (extension)
 
     def c(self) -> _Config:
         return _Config(self.metric, self.minimizer, self.matching, self.selection, float(self.proba), self.seed & 0xFFFFFFFF,
                        self.weighting, self.rejection, float(self.max_distance_sq), int(self.color_icp), int(self.multires),
                        self.n_iterations, self.fx, self.fy, self.cx, self.cy, self.width, self.height, self.nn_mode,
-                       self.lm_max_iterations)
+                       self.lm_max_iterations, self.pyramid_mode)
 
 
 def _f32(a, cols=3):
@@ -232,6 +234,14 @@ def rmse(pose, src, ref):
 
 def coarsest_stride(n):
     return int(lib().orc_coarsest_stride(C.c_int64(n)))
+
+
+def voxel_indices(pts, nrm, stride):
+    pts, nrm = _f32(pts), _f32(nrm)
+    out = np.empty(len(pts), np.int32)
+    lib().orc_voxel_indices.restype = C.c_int64
+    c = lib().orc_voxel_indices(_p(pts), _p(nrm), C.c_int64(len(pts)), C.c_int(stride), _p(out))
+    return out[:c].copy()
 
 
 def coarse_indices(pts, nrm, stride):

@@ -36,6 +36,7 @@ def gpu_config(ocfg: orc.Config, **kw) -> capi.Config:
     c.proba, c.seed, c.weighting, c.rejection = ocfg.proba, ocfg.seed, ocfg.weighting, ocfg.rejection
     c.max_distance_sq, c.color_icp, c.multires = ocfg.max_distance_sq, int(ocfg.color_icp), int(ocfg.multires)
     c.n_iterations, c.lm_max_iterations = ocfg.n_iterations, ocfg.lm_max_iterations
+    c.pyramid_mode = ocfg.pyramid_mode
     for k, v in kw.items():
         setattr(c, k, v)
     return c
@@ -233,6 +234,29 @@ def test_bunny_multires(ctx, bunny, minimizer, metric):
     assert n_it == len(ohist)
     assert ctx.stats().n_queries == nq
     assert pose_close(pose, opose)
+
+
+@pytest.mark.parametrize("minimizer,metric", [(0, 1), (0, 2), (1, 1)])
+def test_voxel_pyramid(ctx, small_eth_pair, minimizer, metric):
+    """ICP_GPU_PYRAMID_VOXEL (extension): levels = one point per occupied source-grid cell; the oracle restates the
+    device grid operation by operation, so level membership -- and hence query counts and poses -- must agree."""
+    src, tgt, _ = small_eth_pair
+    src = synth.Cloud(src.points.copy(), src.normals.copy(), src.colors.copy())
+    src.normals[5::97] = np.nan                     # invalid normals are never level representatives
+    src.points[11::501] = -np.inf
+    ocfg = orc.Config(metric=metric, minimizer=minimizer, multires=True, pyramid_mode=1, max_distance_sq=0.1, n_iterations=10)
+    rc, opose, ohist, nq = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, nn_algorithm=2))
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == len(ohist)
+    assert ctx.stats().n_queries == nq
+    assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
+    cfg = gpu_config(ocfg, nn_algorithm=2, selection=1, proba=0.5, selection_rng=0)
+    with pytest.raises(capi.IcpGpuError) as e:      # host-drawn masks cannot follow device-built levels
+        ctx.set_config(cfg)
+    assert e.value.code == capi.E_ARG
 
 
 def test_multires_more_levels_than_iterations(ctx, small_eth_pair):

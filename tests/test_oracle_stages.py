@@ -159,3 +159,23 @@ def test_projective_quirks():
     # invalid source pixel keeps the value-initialised Match{0, 0.f} (NearestNeighbor.h:353,372-373)
     bad = np.where(q[:len(tgt), 0] == -np.inf)[0]
     assert (got["idx"][bad] == 0).all() and (got["weight"][bad] == 0).all()
+
+
+def test_voxel_levels_properties(small_eth_pair):
+    """Voxel pyramid levels (extension): every level is a subset of the valid points, holds the lowest index of each
+    occupied cell, is nested (a coarser level's representatives survive in the finer ones) and grows with depth."""
+    import numpy as np
+    from oracle import oracle as orc
+    src, _, _ = small_eth_pair
+    pts, nrm = src.points.copy(), src.normals.copy()
+    nrm[3::50] = np.nan
+    valid = np.isfinite(pts).all(1) & np.isfinite(nrm).all(1)
+    prev = None
+    for stride in (64, 32, 16, 8, 4, 2):
+        lv = orc.voxel_indices(pts, nrm, stride)
+        assert np.all(np.diff(lv) > 0) and valid[lv].all()
+        if prev is not None:
+            assert len(lv) >= len(prev) and np.isin(prev, lv).all()
+        prev = lv
+    assert np.array_equal(orc.voxel_indices(pts, nrm, 1), np.nonzero(valid)[0])
+    assert 0 in orc.voxel_indices(pts, nrm, 64) or not valid[0]     # the lowest index always represents its cell
