@@ -239,6 +239,69 @@ cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------- refinement of over-full finest cells
+// The dense table caps the sort key at T <= 24 bits; where the cloud is much denser than the grid (near the sensor) a
+// finest cell still holds dozens of points in arbitrary order.  Those cells get a local counting sort by 6 more bits
+// (2 per axis: the position inside the cell), so that the runs of 32 the leaves are cut from are compact.
+#define REFINE_MAX 1024
+__global__ void find_overfull_cells_kernel(const unsigned int* __restrict__ cs, int T, unsigned int* __restrict__ list,
+                                           unsigned int* __restrict__ n_list, unsigned int capacity) {
+    const unsigned long long n_cells = 1ull << T;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int cnt = cs[c + 1] - cs[c];
+        if (cnt > 32u && cnt <= REFINE_MAX) { const unsigned int k = atomicAdd(n_list, 1u); if (k < capacity) list[k] = (unsigned int)c; }
+    }
+}
+
+__global__ void __launch_bounds__(128) refine_cells_kernel(const unsigned int* __restrict__ cs, const GridParams* __restrict__ gp,
+                                                           const unsigned int* __restrict__ list, const unsigned int* __restrict__ n_list,
+                                                           unsigned int capacity, float4* __restrict__ pts, float4* __restrict__ nrm) {
+    __shared__ float4 sp[REFINE_MAX];
+    __shared__ float4 sn[REFINE_MAX];
+    __shared__ unsigned short skey[REFINE_MAX];
+    __shared__ unsigned int hist[64];
+    const GridParams g = *gp;
+    const unsigned int n = min(*n_list, capacity);
+    for (unsigned int w = blockIdx.x; w < n; w += gridDim.x) {
+        const unsigned int c = list[w], s = cs[c], cnt = cs[c + 1] - s;
+        if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
+        __syncthreads();
+        for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            const float4 p = pts[s + k];
+            sp[k] = p; sn[k] = nrm[s + k];
+            unsigned int key = 0;
+            const float x[3] = {p.x, p.y, p.z};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float u = pmul(psub(x[a], g.o[a]), g.inv_h[a]);
+                const float f = u - floorf(u);                      // position inside the cell (clamped cells: any value is fine)
+                const int q = min(max((int)(f * 4.0f), 0), 3);
+                key |= (unsigned int)(((q >> 1) & 1) << (5 - a)) | (unsigned int)((q & 1) << (2 - a));
+            }
+            skey[k] = (unsigned short)key;
+            atomicAdd(&hist[key], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int acc = 0; for (int b = 0; b < 64; ++b) { const unsigned int v = hist[b]; hist[b] = acc; acc += v; } }
+        __syncthreads();
+        for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            const unsigned int pos = atomicAdd(&hist[skey[k]], 1u);
+            pts[s + pos] = sp[k]; nrm[s + pos] = sn[k];
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t icp_launch_refine_cells(const unsigned int* cell_start, int T, const GridParams* grid, unsigned int* list, unsigned int capacity,
+                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n_sms, cudaStream_t s, int* n_launches) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(n_list, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+    find_overfull_cells_kernel<<<n_sms * 16, 256, 0, s>>>(cell_start, T, list, n_list, capacity);
+    refine_cells_kernel<<<n_sms * 4, 128, 0, s>>>(cell_start, grid, list, n_list, capacity, pts_sorted, nrm_sorted);
+    if (n_launches) *n_launches += 2;
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------- BVH over the sorted cloud
 // Leaves = nodes of the implicit cell tree with <= 32 points whose parent has more (an over-full finest cell is
 // cut into runs of 32): cell-aligned, hence pairwise disjoint in space -- a search ball meets only the few
