@@ -66,12 +66,67 @@ __device__ void svd3_dev(const double* A, double* U, double* S, double* V) {
 // Row layouts.  PLANE / SYMMETRIC: [0..20] A^T A upper triangle row-major, [21..26] A^T b, [27] count.
 //               P2P: [0] count, [1..3] sum s, [4..6] sum d, [7] sum w, [8..10] sum w s, [11..13] sum w d, [14..22] sum w d s^T.
 //               SUMS: [0] count, [1..3] sum s, [4..6] sum d.
-__device__ int expand_and_solve(const double* row, double lambda2, double* x) {
+// 6x6 Cholesky solve of the normal equations (symmetric positive definite by construction), every loop fully
+// unrolled so that the factor lives in registers -- one thread runs this on the critical path of every iteration,
+// and a local-memory (dynamically indexed) elimination costs ~10 us there.  A non-positive pivot (degenerate
+// geometry) falls back to Gaussian elimination with partial pivoting, the solver the oracle uses.
+__device__ __forceinline__ bool chol6_solve(const double* row, double lambda2, double* x) {
+    double L[6][6];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) { L[j][i] = row[k]; ++k; }        // lower triangle
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L[i][i] += lambda2;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = L[j][j];
+#pragma unroll
+        for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m];
+        if (!(d > 0.0)) ok = false;
+        const double ljj = sqrt(d), inv = 1.0 / ljj;
+        L[j][j] = ljj;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = L[i][j];
+#pragma unroll
+            for (int m = 0; m < j; ++m) v -= L[i][m] * L[j][m];
+            L[i][j] = v * inv;
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = row[21 + i];
+#pragma unroll
+        for (int m = 0; m < i; ++m) v -= L[i][m] * y[m];
+        y[i] = v / L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int m = i + 1; m < 6; ++m) v -= L[m][i] * x[m];
+        x[i] = v / L[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) ok = false;
+    return ok;
+}
+
+__device__ __noinline__ int expand_and_solve_pivoted(const double* row, double lambda2, double* x) {
     double A[36], b[6];
     int k = 0;
     for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { A[i * 6 + j] = row[k]; A[j * 6 + i] = row[k]; ++k; }
     for (int i = 0; i < 6; ++i) { A[i * 6 + i] += lambda2; b[i] = row[21 + i]; }
     return solve6_dev(A, b, x);
+}
+
+__device__ int expand_and_solve(const double* row, double lambda2, double* x) {
+    if (chol6_solve(row, lambda2, x)) return 0;
+    return expand_and_solve_pivoted(row, lambda2, x);
 }
 
 __device__ int finish_p2plane(const double* row, float* inc) {
@@ -186,16 +241,34 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = 0.0;
     const double LP = (double)0.1f, LQ = (double)1.0f;   // LAMBDA_POINT / LAMBDA_PLANE|SYMMETRIC (ICPOptimizer.h:737-738, :840-841)
-    // queries are addressed by their position in the Morton-sorted source; a query without a surviving match has pos -1
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += gridDim.x * blockDim.x) {
-        const int pos = a.match_pos[i];
+    // queries are addressed by their position in the Morton-sorted source; a query without a surviving match has pos -1.
+    // Two points per trip with all loads issued before any arithmetic: the gathers of the matched target points are
+    // dependent loads, and with ~120 registers per thread there are few warps to hide them behind.
+    const int gstride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < a.n_src; base += 2 * gstride) {
+        int posv[2]; float4 spv[2], tpv[2], tnv[2], snv[2]; float wv[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { const int i = base + q * gstride; posv[q] = i < a.n_src ? a.match_pos[i] : -1; }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = base + q * gstride;
+            spv[q] = tpv[q] = tnv[q] = snv[q] = make_float4(0.f, 0.f, 0.f, 0.f); wv[q] = 0.f;
+            if (posv[q] >= 0) {
+                spv[q] = __ldg(&a.src_pts[i]); wv[q] = a.match_w[i]; tpv[q] = __ldg(&a.tgt_pts[posv[q]]);
+                if (MODE == 1 || MODE == 2) tnv[q] = __ldg(&a.tgt_nrm[posv[q]]);
+                if (MODE == 2) snv[q] = __ldg(&a.src_nrm[i]);
+            }
+        }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int pos = posv[q];
         if (pos < 0) continue;
-        const float4 sp = __ldg(&a.src_pts[i]);
+        const float4 sp = spv[q];
         float sxf, syf, szf;
         xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
-        const float4 tp = __ldg(&a.tgt_pts[pos]);
+        const float4 tp = tpv[q];
         if (!finite3(sxf, syf, szf) || !finite3(tp.x, tp.y, tp.z)) continue;        // ICPOptimizer.h:590-592
-        const double w = (double)a.match_w[i];
+        const double w = (double)wv[q];
         if (MODE == 3) {
             v[0] += 1.0; v[1] += sxf; v[2] += syf; v[3] += szf; v[4] += tp.x; v[5] += tp.y; v[6] += tp.z;
         } else if (MODE == 0) {
@@ -209,12 +282,12 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
                 for (int c = 0; c < 3; ++c) v[14 + r * 3 + c] += w * t[r] * s[c];
         } else {
             double s[3] = {sxf, syf, szf}, t[3] = {tp.x, tp.y, tp.z};
-            const float4 tn = __ldg(&a.tgt_nrm[pos]);
+            const float4 tn = tnv[q];
             double n[3] = {tn.x, tn.y, tn.z};
             bool use_row = finite3(tn.x, tn.y, tn.z);
             double u[3] = {s[0], s[1], s[2]};
             if (MODE == 2) {
-                const float4 sn4 = __ldg(&a.src_nrm[i]);
+                const float4 sn4 = snv[q];
                 // the source normal is transformed by the current pose's inverse-transpose (ICPOptimizer.h:554)
                 float nx, ny, nz;
                 xform_normal(Nm, sn4.x, sn4.y, sn4.z, nx, ny, nz);
@@ -268,6 +341,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
             v[26] += a2 * r * c[5] + b2 * e[2];
             v[27] += 1.0;
         }
+      }
     }
     if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last)) return;
     if (threadIdx.x == 0) {
