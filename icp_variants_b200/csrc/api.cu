@@ -134,10 +134,10 @@ int bind(icp_gpu_ctx* ctx) {
     return 0;
 }
 
-int pick_T(int n) {
+int pick_T(int n, bool source = false) {
     // cells = ICP_CELLS_PER_POINT x points (surface-like clouds occupy a small fraction of them)
-    long long factor = ICP_CELLS_PER_POINT;
-    if (const char* e = getenv("ICP_GPU_CELLS_PER_POINT")) { const long long v = atoll(e); if (v >= 1 && v <= 64) factor = v; }   // tuning knob
+    long long factor = source ? ICP_SOURCE_CELLS_PER_POINT : ICP_CELLS_PER_POINT;
+    if (!source) if (const char* e = getenv("ICP_GPU_CELLS_PER_POINT")) { const long long v = atoll(e); if (v >= 1 && v <= 64) factor = v; }   // tuning knob
     int T = 3;
     while (T < 24 && (1ll << T) < factor * (long long)(n > 0 ? n : 1)) ++T;
     if (T > 3 * ICP_MAX_BITS_PER_AXIS) T = 3 * ICP_MAX_BITS_PER_AXIS;
@@ -222,7 +222,7 @@ int build_grid(icp_gpu_ctx* ctx) {
 // Sorts the source into the cell order of its own grid (Morton order).
 int build_source(icp_gpu_ctx* ctx) {
     const int n = ctx->n_src;
-    ctx->Ts = pick_T(n);
+    ctx->Ts = pick_T(n, true);
     const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->Ts) + 1;
     if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4)) ||
         ensure(ctx, ctx->keys, (n1 + 2) * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->scell_start, cells1 * 4) ||

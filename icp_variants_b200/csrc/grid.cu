@@ -54,9 +54,19 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, unsigned int*
         mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
         mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one atomic per block and value (thousands of same-address atomics from every warp cost tens of microseconds)
+    __shared__ unsigned int s_mn[3][8], s_mx[3][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { atomicMin(&bbox[a], mn[a]); atomicMax(&bbox[3 + a], mx[a]); }
+        for (int a = 0; a < 3; ++a) { s_mn[a][wid] = mn[a]; s_mx[a][wid] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int a = threadIdx.x % 3; const bool is_max = threadIdx.x >= 3;
+        unsigned int v = is_max ? 0u : 0xFFFFFFFFu;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v = is_max ? max(v, s_mx[a][w]) : min(v, s_mn[a][w]);
+        if (is_max) atomicMax(&bbox[3 + a], v); else atomicMin(&bbox[a], v);
     }
 }
 

@@ -20,7 +20,8 @@
 #define ICP_REDUCE_THREADS 256
 #define ICP_MATCH_THREADS 128
 #define ICP_LEAF_MAX 8             // a grid node with <= this many points is scanned, not split
-#define ICP_CELLS_PER_POINT 32      // grid cells per point (2^T >= this x N); oracle/icp_oracle.c:orc_pick_T restates it
+#define ICP_CELLS_PER_POINT 32      // target grid: cells per point (2^T >= this x N); the finer, the more compact the BVH leaves
+#define ICP_SOURCE_CELLS_PER_POINT 4 // source grid (sort order + voxel pyramid only); oracle/icp_oracle.c:orc_pick_T restates it
 #define ICP_MAX_BITS_PER_AXIS 10   // keeps the cell-index rounding error << the bound margin
 
 __device__ __forceinline__ float pmul(float a, float b) { return __fmul_rn(a, b); }

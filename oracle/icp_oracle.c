@@ -805,7 +805,7 @@ typedef struct { float o[3], h[3], inv_h[3]; int bits[3]; int T; int axis[64]; }
 
 static int orc_pick_T(int64_t n) {
     int T = 3;
-    while (T < 24 && ((int64_t)1 << T) < 32 * (n > 0 ? n : 1)) ++T;   /* ICP_CELLS_PER_POINT */
+    while (T < 24 && ((int64_t)1 << T) < 4 * (n > 0 ? n : 1)) ++T;   /* ICP_SOURCE_CELLS_PER_POINT */
     return T;
 }
 
