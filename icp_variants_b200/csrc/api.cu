@@ -405,6 +405,9 @@ void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     r.match_pos = (const int*)c->match_pos.p; r.match_w = (const float*)c->match_w.p;
     r.partials = (double*)c->partials.p; r.pose_history = (float*)c->history.p;
     r.metric = c->cfg.metric; r.solve = solve;
+    r.fused = 0; r.nn_pos = (const int*)c->nn_pos.p; r.n_tgt = c->n_tgt; r.mask = (const unsigned int*)c->mask.p;
+    r.desc = (const IterDesc*)c->desc.p; r.desc_index = -1;
+    r.weighting = c->cfg.weighting; r.rejection = c->cfg.rejection; r.max_d2 = c->cfg.max_distance_sq;
 }
 
 // Enqueue the whole loop.  ev_marks (nullable): events recorded around each stage for the timings report.
@@ -412,6 +415,9 @@ int enqueue_iterations(icp_gpu_ctx* ctx, const Plan& plan, int algo, std::vector
     MatchArgs ma; ReduceArgs ra;
     fill_match_args(ctx, ma, algo, -1, false);
     fill_reduce_args(ctx, ra, algo, 1);
+    // Without work counters the linear minimiser reads the search result directly: weighting and rejection are
+    // evaluated inside the reduction and the match records (and their launch) are skipped.
+    if (algo == 0 && ctx->cfg.minimizer == ICP_GPU_MIN_LINEAR && !ctx->cfg.collect_stats) { ma.skip_finish = 1; ra.fused = 1; }
     int launches = 0;
     const int nb = ctx->n_reduce_blocks;
     for (int i = 0; i < plan.n_iters; ++i) {
@@ -515,7 +521,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         float idx_ms = 0.f;
         if (ctx->grid_built && cudaEventElapsedTime(&idx_ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->index_ms = idx_ms; else cudaGetLastError();
         timings->total_ms = tot; timings->index_ms = ctx->index_ms; timings->n_iterations = plan.n_iters;
-        const int per_match = algo == 0 ? 3 : 1;
+        const int per_match = algo == 0 ? ((ctx->cfg.minimizer == ICP_GPU_MIN_LINEAR && !ctx->cfg.collect_stats) ? 2 : 3) : 1;
         timings->n_match_launches = plan.n_iters * per_match;
         timings->n_solver_launches = (int)ctx->stats.n_kernel_launches - 1 - plan.n_iters * per_match;
         for (auto& e : marks) cudaEventDestroy(e);

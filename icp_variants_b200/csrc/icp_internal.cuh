@@ -132,6 +132,7 @@ struct MatchArgs {
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
     int use_seed;
     int collect_stats;       // work counters in DevState (atomics); off in timed runs
+    int skip_finish;         // BVH path: the reduction evaluates stages 3-4 itself (ReduceArgs::fused), no match records
 };
 
 struct ReduceArgs {
@@ -142,6 +143,10 @@ struct ReduceArgs {
     double* partials;        // [grid][ICP_NRED]
     float* pose_history;     // [ICP_MAX_ITERS][16] or null
     int metric; int solve;   // solve=0: leave the summed row in state->shard_partials
+    // fused = 1: stages 3-4 (selection predicate, weighting, rejection) are evaluated here from the search result nn_pos
+    // instead of being read back from the match records (saves the match_finish launch); linear minimiser only
+    int fused; const int* nn_pos; int n_tgt; const unsigned int* mask; const IterDesc* desc; int desc_index;
+    int weighting, rejection; float max_d2;
 };
 
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
@@ -235,6 +240,49 @@ __device__ __forceinline__ bool query_active(const IterDesc& d, const unsigned i
     if (d.filter_finite && !(finite3(p4.x, p4.y, p4.z) && finite3(n4.x, n4.y, n4.z))) return false;
     if (d.mask_word_offset >= 0 && !((__ldg(&mask[d.mask_word_offset + (orig >> 5)]) >> (orig & 31u)) & 1u)) return false;
     if (d.proba >= 0.0f && !(unit_hash(d.rng_key, orig) < d.proba)) return false;
+    return true;
+}
+
+// Stages 3-4 for one matched pair: WeightingMethod::applyWeights (weighting.h:39-99) and
+// ICPOptimizer::pruneCorrespondences (ICPOptimizer.h:157-174).  w comes in as the matcher's weight (1, or 0 for the
+// projective matcher's skipped queries) and leaves as the match weight; returns false when the pair is rejected.
+// (sx,sy,sz) / (snx,sny,snz): transformed source point / normal; tp / tn: target point {x,y,z,_} / normal {x,y,z,rgba}.
+__device__ __forceinline__ bool match_weight_and_reject(int weighting, int rejection, float max_d2, float sx, float sy, float sz,
+                                                        float snx, float sny, float snz, unsigned int s_rgba, const float4 tp,
+                                                        const float4 tn, float& w) {
+    if (weighting != ICP_GPU_WEIGHT_CONSTANT) {                               // weighting.h:44 early return
+        w = 0.0f;
+        if (weighting == ICP_GPU_WEIGHT_DISTANCES || weighting == ICP_GPU_WEIGHT_COLORS) {
+            if (finite3(sx, sy, sz) && finite3(tp.x, tp.y, tp.z)) {            // weighting.h:58-59
+                const float d0 = psub(sx, tp.x), d1 = psub(sy, tp.y), d2 = psub(sz, tp.z);
+                const float q = pdiv(padd(padd(pmul(d0, d0), pmul(d1, d1)), pmul(d2, d2)), max_d2);
+                w = (float)(1.0 - (double)q);                                  // weighting.h:16-20
+            }
+        }
+        if (weighting == ICP_GPU_WEIGHT_NORMALS) {
+            if (finite3(snx, sny, snz) && finite3(tn.x, tn.y, tn.z))           // weighting.h:72-73
+                w = padd(padd(pmul(snx, tn.x), pmul(sny, tn.y)), pmul(snz, tn.z));   // weighting.h:22-25 (unclamped)
+        }
+        if (weighting == ICP_GPU_WEIGHT_COLORS) {
+            // weighting.h:27-30: Vector4uc difference wraps modulo 256 before squaring
+            const unsigned int t_rgba = __float_as_uint(tn.w);
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int e = (int)((((s_rgba >> (8 * k)) & 0xFFu) - ((t_rgba >> (8 * k)) & 0xFFu)) & 0xFFu);
+                s += e * e;
+            }
+            const float cw = (float)(1.0 - (double)pdiv((float)s, 195075.0f));
+            w = pmul(w, cw);
+        }
+    }
+    if (rejection == 1) {                                                      // ICPOptimizer.h:157-174
+        const float dot = padd(padd(pmul(snx, tn.x), pmul(sny, tn.y)), pmul(snz, tn.z));
+        const float na = __fsqrt_rn(padd(padd(pmul(snx, snx), pmul(sny, sny)), pmul(snz, snz)));
+        const float nb = __fsqrt_rn(padd(padd(pmul(tn.x, tn.x), pmul(tn.y, tn.y)), pmul(tn.z, tn.z)));
+        const float c = pdiv(dot, pmul(na, nb));
+        if (c <= 0.5f && c >= -1.0f) return false;                             // D6; NaN and |c|>1 are kept like acos()'s NaN
+    }
     return true;
 }
 

@@ -82,43 +82,13 @@ __device__ __forceinline__ void finish_match(const MatchArgs& a, int p, bool mat
                                              unsigned int& n_matched) {
     int out_idx = -1, out_pos = -1; float w = 0.0f;
     if (matched) {
-        out_idx = t_idx; out_pos = t_pos; w = w_const;
         const float4 tn = __ldg(&a.tgt_nrm[t_pos]);
-        if (a.weighting != ICP_GPU_WEIGHT_CONSTANT) {                         // weighting.h:44 early return
-            const float4 tp = __ldg(&a.tgt_pts[t_pos]);
-            w = 0.0f;
-            if (a.weighting == ICP_GPU_WEIGHT_DISTANCES || a.weighting == ICP_GPU_WEIGHT_COLORS) {
-                if (finite3(sx, sy, sz) && finite3(tp.x, tp.y, tp.z)) {        // weighting.h:58-59
-                    const float d0 = psub(sx, tp.x), d1 = psub(sy, tp.y), d2 = psub(sz, tp.z);
-                    const float q = pdiv(padd(padd(pmul(d0, d0), pmul(d1, d1)), pmul(d2, d2)), a.max_d2);
-                    w = (float)(1.0 - (double)q);                              // weighting.h:16-20
-                }
-            }
-            if (a.weighting == ICP_GPU_WEIGHT_NORMALS) {
-                if (finite3(snx, sny, snz) && finite3(tn.x, tn.y, tn.z))       // weighting.h:72-73
-                    w = padd(padd(pmul(snx, tn.x), pmul(sny, tn.y)), pmul(snz, tn.z));   // weighting.h:22-25 (unclamped)
-            }
-            if (a.weighting == ICP_GPU_WEIGHT_COLORS) {
-                // weighting.h:27-30: Vector4uc difference wraps modulo 256 before squaring
-                const unsigned int t_rgba = __float_as_uint(tn.w);
-                int s = 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int e = (int)((((s_rgba >> (8 * k)) & 0xFFu) - ((t_rgba >> (8 * k)) & 0xFFu)) & 0xFFu);
-                    s += e * e;
-                }
-                const float cw = (float)(1.0 - (double)pdiv((float)s, 195075.0f));
-                w = pmul(w, cw);
-            }
+        float4 tp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.weighting != ICP_GPU_WEIGHT_CONSTANT) tp = __ldg(&a.tgt_pts[t_pos]);
+        w = w_const;
+        if (match_weight_and_reject(a.weighting, a.rejection, a.max_d2, sx, sy, sz, snx, sny, snz, s_rgba, tp, tn, w)) {
+            out_idx = t_idx; out_pos = t_pos; ++n_matched;
         }
-        if (a.rejection == 1) {                                                // ICPOptimizer.h:157-174
-            const float dot = padd(padd(pmul(snx, tn.x), pmul(sny, tn.y)), pmul(snz, tn.z));
-            const float na = __fsqrt_rn(padd(padd(pmul(snx, snx), pmul(sny, sny)), pmul(snz, snz)));
-            const float nb = __fsqrt_rn(padd(padd(pmul(tn.x, tn.x), pmul(tn.y, tn.y)), pmul(tn.z, tn.z)));
-            const float c = pdiv(dot, pmul(na, nb));
-            if (c <= 0.5f && c >= -1.0f) { out_idx = -1; out_pos = -1; }       // D6; NaN and |c|>1 are kept like acos()'s NaN
-        }
-        if (out_pos >= 0) ++n_matched;
     }
     a.match_pos[p] = out_pos;
     a.match_w[p] = w;
@@ -539,7 +509,7 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         if (nb > 64 * n_sms) nb = 64 * n_sms;
         if (a.color_icp) knn_bvh_kernel<true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
         ++launches;
-        match_finish_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches;
+        if (!a.skip_finish) { match_finish_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches; }
     }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();

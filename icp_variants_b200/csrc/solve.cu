@@ -226,7 +226,7 @@ __device__ void finish_sums(DevState* st, const double* row) {
 
 // ---------------------------------------------------------------------------- the reduction kernel
 // MODE 0 p2p moments, 1 point-to-plane, 2 symmetric (needs means in state), 3 sums only
-template <int MODE>
+template <int MODE, bool FUSED>
 __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const ReduceArgs a) {
     __shared__ float P[16];
     __shared__ float mS[3], mD[3], Nm[9];
@@ -241,34 +241,36 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = 0.0;
     const double LP = (double)0.1f, LQ = (double)1.0f;   // LAMBDA_POINT / LAMBDA_PLANE|SYMMETRIC (ICPOptimizer.h:737-738, :840-841)
-    // queries are addressed by their position in the Morton-sorted source; a query without a surviving match has pos -1.
-    // Two points per trip with all loads issued before any arithmetic: the gathers of the matched target points are
-    // dependent loads, and with ~120 registers per thread there are few warps to hide them behind.
-    const int gstride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < a.n_src; base += 2 * gstride) {
-        int posv[2]; float4 spv[2], tpv[2], tnv[2], snv[2]; float wv[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { const int i = base + q * gstride; posv[q] = i < a.n_src ? a.match_pos[i] : -1; }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int i = base + q * gstride;
-            spv[q] = tpv[q] = tnv[q] = snv[q] = make_float4(0.f, 0.f, 0.f, 0.f); wv[q] = 0.f;
-            if (posv[q] >= 0) {
-                spv[q] = __ldg(&a.src_pts[i]); wv[q] = a.match_w[i]; tpv[q] = __ldg(&a.tgt_pts[posv[q]]);
-                if (MODE == 1 || MODE == 2) tnv[q] = __ldg(&a.tgt_nrm[posv[q]]);
-                if (MODE == 2) snv[q] = __ldg(&a.src_nrm[i]);
-            }
-        }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int pos = posv[q];
-        if (pos < 0) continue;
-        const float4 sp = spv[q];
+    // queries are addressed by their position in the Morton-sorted source
+    IterDesc d; d.stride = 1; d.filter_finite = 0; d.mask_word_offset = -1; d.rng_key = 0u; d.proba = -1.0f;
+    if (FUSED) d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state->iter];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += gridDim.x * blockDim.x) {
+        int pos; float wf; float4 sp, tp, tn = make_float4(0.f, 0.f, 0.f, 0.f), sn4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float sxf, syf, szf;
-        xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
-        const float4 tp = tpv[q];
+        if (FUSED) {
+            // stages 3-4 evaluated here from the search result (same code path as match_finish_kernel)
+            pos = a.nn_pos[i];
+            sp = __ldg(&a.src_pts[i]); sn4 = __ldg(&a.src_nrm[i]);
+            if (pos < 0 || pos >= a.n_tgt || !query_active(d, a.mask, sp, sn4)) continue;
+            xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
+            if (!finite3(sxf, syf, szf)) continue;
+            tp = __ldg(&a.tgt_pts[pos]); tn = __ldg(&a.tgt_nrm[pos]);
+            float nx, ny, nz;
+            xform_normal(Nm, sn4.x, sn4.y, sn4.z, nx, ny, nz);
+            wf = 1.0f;
+            if (!match_weight_and_reject(a.weighting, a.rejection, a.max_d2, sxf, syf, szf, nx, ny, nz, __float_as_uint(sn4.w), tp, tn, wf)) continue;
+        } else {
+            pos = a.match_pos[i];                       // a query without a surviving match has pos -1
+            if (pos < 0) continue;
+            sp = __ldg(&a.src_pts[i]);
+            xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
+            tp = __ldg(&a.tgt_pts[pos]);
+            wf = a.match_w[i];
+            if (MODE == 1 || MODE == 2) tn = __ldg(&a.tgt_nrm[pos]);
+            if (MODE == 2) sn4 = __ldg(&a.src_nrm[i]);
+        }
         if (!finite3(sxf, syf, szf) || !finite3(tp.x, tp.y, tp.z)) continue;        // ICPOptimizer.h:590-592
-        const double w = (double)wv[q];
+        const double w = (double)wf;
         if (MODE == 3) {
             v[0] += 1.0; v[1] += sxf; v[2] += syf; v[3] += szf; v[4] += tp.x; v[5] += tp.y; v[6] += tp.z;
         } else if (MODE == 0) {
@@ -282,12 +284,10 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
                 for (int c = 0; c < 3; ++c) v[14 + r * 3 + c] += w * t[r] * s[c];
         } else {
             double s[3] = {sxf, syf, szf}, t[3] = {tp.x, tp.y, tp.z};
-            const float4 tn = tnv[q];
             double n[3] = {tn.x, tn.y, tn.z};
             bool use_row = finite3(tn.x, tn.y, tn.z);
             double u[3] = {s[0], s[1], s[2]};
             if (MODE == 2) {
-                const float4 sn4 = snv[q];
                 // the source normal is transformed by the current pose's inverse-transpose (ICPOptimizer.h:554)
                 float nx, ny, nz;
                 xform_normal(Nm, sn4.x, sn4.y, sn4.z, nx, ny, nz);
@@ -341,7 +341,6 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
             v[26] += a2 * r * c[5] + b2 * e[2];
             v[27] += 1.0;
         }
-      }
     }
     if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last)) return;
     if (threadIdx.x == 0) {
@@ -360,23 +359,29 @@ int icp_reduce_blocks(int n_src, int n_sms) {
     return nb;
 }
 
+template <int MODE>
+static void launch_reduce_mode(const ReduceArgs& a, int n_blocks, cudaStream_t s) {
+    if (a.fused) reduce_kernel<MODE, true><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+    else reduce_kernel<MODE, false><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+}
+
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches) {
     int launches = 0;
-    if (a.metric == ICP_GPU_METRIC_P2P) { reduce_kernel<0><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches; }
-    else if (a.metric == ICP_GPU_METRIC_P2PLANE) { reduce_kernel<1><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches; }
+    if (a.metric == ICP_GPU_METRIC_P2P) { launch_reduce_mode<0>(a, n_blocks, s); ++launches; }
+    else if (a.metric == ICP_GPU_METRIC_P2PLANE) { launch_reduce_mode<1>(a, n_blocks, s); ++launches; }
     else {
-        reduce_kernel<3><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches;
-        reduce_kernel<2><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a); ++launches;
+        launch_reduce_mode<3>(a, n_blocks, s); ++launches;
+        launch_reduce_mode<2>(a, n_blocks, s); ++launches;
     }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }
 
 cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase, cudaStream_t s, int* n_launches) {
-    if (a.metric == ICP_GPU_METRIC_P2P) reduce_kernel<0><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
-    else if (a.metric == ICP_GPU_METRIC_P2PLANE) reduce_kernel<1><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
-    else if (phase == 0) reduce_kernel<3><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
-    else reduce_kernel<2><<<n_blocks, ICP_REDUCE_THREADS, 0, s>>>(a);
+    if (a.metric == ICP_GPU_METRIC_P2P) launch_reduce_mode<0>(a, n_blocks, s);
+    else if (a.metric == ICP_GPU_METRIC_P2PLANE) launch_reduce_mode<1>(a, n_blocks, s);
+    else if (phase == 0) launch_reduce_mode<3>(a, n_blocks, s);
+    else launch_reduce_mode<2>(a, n_blocks, s);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

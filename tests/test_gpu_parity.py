@@ -313,6 +313,24 @@ def test_projective_free_running(ctx, small_tum):
     assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
 
 
+@pytest.mark.parametrize("metric,weighting,multires", [(0, 0, False), (1, 1, False), (2, 2, False), (1, 3, True), (2, 0, True)])
+def test_fused_reduction_equals_match_records(ctx, small_eth_pair, metric, weighting, multires):
+    """collect_stats = 0 lets the linear minimiser evaluate weighting + rejection inside the reduction instead of reading
+    match records: same arithmetic, so the poses must be bit-identical to the unfused path."""
+    src, tgt, _ = small_eth_pair
+    c = capi.default_config()
+    c.metric, c.weighting, c.multires, c.max_distance_sq, c.n_iterations, c.nn_algorithm = metric, weighting, int(multires), 0.1, 8, 2
+    c.selection, c.proba, c.selection_rng, c.seed = 1, 0.7, 1, 5
+    load(ctx, src, tgt)
+    poses = []
+    for stats in (1, 0):
+        c.collect_stats = stats
+        ctx.set_config(c)
+        pose, hist, _ = ctx.estimate_pose()
+        poses.append(hist)
+    assert np.array_equal(poses[0], poses[1])
+
+
 def test_bunny_known_answer(ctx, bunny):
     """bunny_part2_trans maps onto bunny_part1 by Rz(12.2348 deg), t=(-0.0151362,-0.0032822,0)."""
     src, tgt, gs, gt = bunny
