@@ -515,3 +515,49 @@ def test_async_pair_queue_two_contexts(bunny, small_eth_pair):
         p2, n2 = c2.estimate_pose_finish()
         p1, n1 = c1.estimate_pose_finish()
         assert n1 == 20 and n2 == 20 and np.array_equal(p1, ref1) and np.array_equal(p2, ref2)
+
+
+# ----------------------------------------------------------------------------- adversarial shapes for the index
+def _cloud(kind, n, rng):
+    if kind == "uniform":
+        return rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+    if kind == "clustered":      # a few very dense blobs far apart: deep over-full cells, empty space in between
+        c = rng.uniform(-50, 50, size=(4, 3))
+        return (c[rng.integers(0, 4, n)] + rng.normal(0, 1e-3, size=(n, 3))).astype(np.float32)
+    if kind == "identical":      # every point the same: one finest cell holds everything, ties everywhere
+        return np.tile(np.array([[0.25, -3.0, 7.5]], np.float32), (n, 1))
+    if kind == "line":           # zero extent on two axes
+        t = rng.uniform(0, 1, n).astype(np.float32)
+        return np.stack([t, np.zeros_like(t), np.full_like(t, 2.0)], 1)
+    if kind == "plane_dups":     # quantised plane with many exact duplicates
+        p = np.zeros((n, 3), np.float32)
+        p[:, :2] = rng.integers(0, 20, size=(n, 2)) * 0.05
+        return p
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "identical", "line", "plane_dups"])
+@pytest.mark.parametrize("n_tgt", [1, 2, 31, 32, 33, 100, 1025, 5000, 40000])
+def test_index_edge_shapes_against_brute_force(ctx, kind, n_tgt):
+    """The grid / BVH / adjacency construction on degenerate target shapes and sizes, checked against the oracle's literal
+    brute-force scan (lowest index on ties), cold and warm-started, with and without a distance threshold."""
+    rng = np.random.default_rng(n_tgt * 7 + len(kind))
+    tgt = _cloud(kind, n_tgt, rng)
+    qry = np.concatenate([_cloud(kind, 300, rng) + rng.normal(0, 0.01, size=(300, 3)).astype(np.float32),
+                          rng.uniform(-60, 60, size=(100, 3)).astype(np.float32), tgt[:min(50, n_tgt)]]).astype(np.float32)
+    zt, zq = np.zeros_like(tgt), np.zeros_like(qry)
+    for max_d2 in (1e30, 0.5):
+        ref = orc.knn_brute(tgt, qry, max_d2)
+        c = capi.default_config()
+        c.nn_algorithm, c.max_distance_sq, c.rejection = 2, max_d2, 0
+        ctx.set_config(c)
+        ctx.set_target(tgt, zt, None)
+        ctx.set_source(qry, zq, None)
+        for attempt in range(2):                      # second call is warm-started from the first one's neighbours
+            idx, w = ctx.query_matches(np.eye(4, dtype=np.float32))
+            assert_matches_equal(idx, w, ref, f"{kind} n={n_tgt} max_d2={max_d2} attempt {attempt}")
+        shifted = synth.make_pose([0.01, -0.02, 0.005], [0.3, -0.2, 0.4])      # warm start after a small motion
+        q2 = orc.transform_points(shifted, qry)
+        ref2 = orc.knn_brute(tgt, q2, max_d2)
+        idx, w = ctx.query_matches(shifted)
+        assert_matches_equal(idx, w, ref2, f"{kind} n={n_tgt} max_d2={max_d2} shifted")
