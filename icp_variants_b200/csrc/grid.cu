@@ -166,7 +166,12 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
 __global__ void scan_tile_sums_kernel(const unsigned int* __restrict__ data, int n, unsigned int* __restrict__ tile_sums) {
     const int base = blockIdx.x * SCAN_TILE;
     unsigned int s = 0;
-    for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_THREADS) { const int i = base + k; if (i < n) s += data[i]; }
+    if (base + SCAN_TILE <= n) {                      // full tile: 16-byte loads (base is a multiple of 4096 entries)
+        const uint4* d4 = reinterpret_cast<const uint4*>(data + base);
+        for (int k = threadIdx.x; k < SCAN_TILE / 4; k += SCAN_THREADS) { const uint4 v = d4[k]; s += (v.x + v.y) + (v.z + v.w); }
+    } else {
+        for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_THREADS) { const int i = base + k; if (i < n) s += data[i]; }
+    }
     s = __reduce_add_sync(0xFFFFFFFFu, s);
     __shared__ unsigned int ws[SCAN_THREADS / 32];
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
@@ -195,11 +200,30 @@ __global__ void scan_tile_offsets_kernel(unsigned int* __restrict__ tile_sums, i
 __global__ void scan_apply_kernel(unsigned int* __restrict__ data, int n, const unsigned int* __restrict__ tile_offsets) {
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned int v[SCAN_ITEMS]; unsigned int s = 0;
+    const bool full = blockIdx.x * SCAN_TILE + SCAN_TILE <= n;      // 16-byte accesses on full tiles
+    if (full) {
+        const uint4* d4 = reinterpret_cast<const uint4*>(data + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; v[k] = i < n ? data[i] : 0u; s += v[k]; }
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) { const uint4 q = d4[k]; v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; v[k] = i < n ? data[i] : 0u; s += v[k]; }
+    }
     unsigned int ex = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
+    if (full) {
+        uint4* d4 = reinterpret_cast<uint4*>(data + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; if (i < n) data[i] = ex; ex += v[k]; }
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+            uint4 q;
+            q.x = ex; ex += v[4 * k]; q.y = ex; ex += v[4 * k + 1]; q.z = ex; ex += v[4 * k + 2]; q.w = ex; ex += v[4 * k + 3];
+            d4[k] = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; if (i < n) data[i] = ex; ex += v[k]; }
+    }
 }
 
 static cudaError_t launch_exclusive_scan(unsigned int* data, int n, unsigned int* block_sums, cudaStream_t s, int* launches) {
@@ -254,13 +278,17 @@ cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
 // finest cell still holds dozens of points in arbitrary order.  Those cells get a local counting sort by 6 more bits
 // (2 per axis: the position inside the cell), so that the runs of 32 the leaves are cut from are compact.
 #define REFINE_MAX 1024
-__global__ void find_overfull_cells_kernel(const unsigned int* __restrict__ cs, int T, unsigned int* __restrict__ list,
+// thread per sorted point: the first point of a finest cell with 33 .. REFINE_MAX points registers the cell
+__global__ void find_overfull_cells_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
+                                           const unsigned int* __restrict__ cs, int T, unsigned int* __restrict__ list,
                                            unsigned int* __restrict__ n_list, unsigned int capacity) {
-    const unsigned long long n_cells = 1ull << T;
-    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned int cnt = cs[c + 1] - cs[c];
-        if (cnt > 32u && cnt <= REFINE_MAX) { const unsigned int k = atomicAdd(n_list, 1u); if (k < capacity) list[k] = (unsigned int)c; }
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (unsigned int)i >= cs[(size_t)1 << T]) return;
+    const GridParams g = *gp;
+    const float4 p = pts[i];
+    const unsigned int c = cell_code(g, p.x, p.y, p.z);
+    const unsigned int s = cs[c], cnt = cs[(size_t)c + 1] - s;
+    if ((unsigned int)i == s && cnt > 32u && cnt <= REFINE_MAX) { const unsigned int k = atomicAdd(n_list, 1u); if (k < capacity) list[k] = c; }
 }
 
 __global__ void __launch_bounds__(128) refine_cells_kernel(const unsigned int* __restrict__ cs, const GridParams* __restrict__ gp,
@@ -303,10 +331,12 @@ __global__ void __launch_bounds__(128) refine_cells_kernel(const unsigned int* _
 }
 
 cudaError_t icp_launch_refine_cells(const unsigned int* cell_start, int T, const GridParams* grid, unsigned int* list, unsigned int capacity,
-                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n_sms, cudaStream_t s, int* n_launches) {
+                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n, int n_sms, cudaStream_t s,
+                                    int* n_launches) {
     cudaError_t e;
     if ((e = cudaMemsetAsync(n_list, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
-    find_overfull_cells_kernel<<<n_sms * 16, 256, 0, s>>>(cell_start, T, list, n_list, capacity);
+    if (n <= 0) return cudaSuccess;
+    find_overfull_cells_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_sorted, n, grid, cell_start, T, list, n_list, capacity);
     refine_cells_kernel<<<n_sms * 4, 128, 0, s>>>(cell_start, grid, list, n_list, capacity, pts_sorted, nrm_sorted);
     if (n_launches) *n_launches += 2;
     return cudaGetLastError();

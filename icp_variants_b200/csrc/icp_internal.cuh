@@ -160,7 +160,8 @@ cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, in
                                   cudaStream_t s, int* n_launches);
 // Local 6-bit counting sort inside the finest cells that hold more than 32 points (list: scratch of `capacity` cell ids).
 cudaError_t icp_launch_refine_cells(const unsigned int* cell_start, int T, const GridParams* grid, unsigned int* list, unsigned int capacity,
-                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n_sms, cudaStream_t s, int* n_launches);
+                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n, int n_sms, cudaStream_t s,
+                                    int* n_launches);
 // Tight-box BVH over the cell-sorted cloud.  leaf_rank: n + 2 entries (kept: maps a sorted position to its leaf);
 // leaf_start: n + 2; node_scratch / child_start / pstart: icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS entries each.
 size_t icp_bvh_max_nodes(int n);
