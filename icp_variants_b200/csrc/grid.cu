@@ -552,8 +552,8 @@ __device__ __forceinline__ bool boxes_meet(const float* lo, const float* hi, con
 
 __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const BvhDesc* __restrict__ bvh, const float4* __restrict__ box,
                                                                          const unsigned int* __restrict__ child_start,
-                                                                         unsigned int* __restrict__ adj, int* __restrict__ adj_n,
-                                                                         float* __restrict__ adj_r, int capacity, float r_factor) {
+                                                                         unsigned int* __restrict__ adj, float4* __restrict__ adj_box,
+                                                                         int capacity, float r_factor) {
     __shared__ unsigned int s_node[ADJ_WARPS][32 * ICP_BVH_MAX_LEVELS];
     __shared__ unsigned int s_list[ADJ_WARPS][64];
     const BvhDesc b = *bvh;
@@ -603,19 +603,29 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
         }
         __syncwarp();
         if (lane < count && ok) adj[(size_t)l * 32 + lane] = list[lane];
-        if (lane == 0) { adj_n[l] = ok ? count : 0; adj_r[l] = ok ? R : -1.0f; }
+        if (lane == 0) {
+            // the inflated box exactly as the query above used it (so that "ball inside this box" implies "every leaf the
+            // ball meets is in the list"); inverted when there is no list
+            if (ok) {
+                adj_box[2 * (size_t)l] = make_float4(__fsub_rd(mlo.x, R), __fsub_rd(mlo.y, R), __fsub_rd(mlo.z, R), __int_as_float(count));
+                adj_box[2 * (size_t)l + 1] = make_float4(__fadd_ru(mhi.x, R), __fadd_ru(mhi.y, R), __fadd_ru(mhi.z, R), 0.f);
+            } else {
+                adj_box[2 * (size_t)l] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0));
+                adj_box[2 * (size_t)l + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+            }
+        }
         __syncwarp();
     }
 }
 
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
-                                      int* adj_n, float* adj_r, int capacity, int n_sms, cudaStream_t s, int* n_launches) {
+                                      float4* adj_box, int capacity, int n_sms, cudaStream_t s, int* n_launches) {
     long long nb = ((long long)capacity + ADJ_WARPS - 1) / ADJ_WARPS;
     if (nb > 16ll * n_sms) nb = 16ll * n_sms;
     if (nb < 1) nb = 1;
     float r_factor = 2.0f;
     if (const char* e = getenv("ICP_GPU_ADJ_FACTOR")) r_factor = (float)atof(e);   // tuning knob
-    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_n, adj_r, capacity, r_factor);
+    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_box, capacity, r_factor);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -115,9 +115,11 @@ struct MatchArgs {
     const unsigned int* leaf_start;
     const unsigned int* child_start; // children ranges of the levels >= 1
     const unsigned int* leaf_rank;   // [n_tgt + 2] number of leaf starts before sorted position i: leaf of point i = leaf_rank[i + 1] - 1
-    // Leaf adjacency (grid.cu): adj[32*l .. 32*l + adj_n[l]) = every other leaf whose box meets box(l) inflated by adj_r[l];
-    // adj_r[l] < 0: no list.  A query whose search ball lies inside that inflated box needs no tree walk.
-    const unsigned int* adj; const int* adj_n; const float* adj_r; int adj_capacity;
+    // Leaf adjacency (grid.cu): adj[32*l .. 32*l + n) = every other leaf whose box meets box(l) inflated by R;
+    // adj_box[2*l] = {lo - R, n as int bits}, adj_box[2*l+1] = {hi + R, _}; an inverted box (lo > hi) means "no list".
+    // A query whose search ball lies inside the inflated box needs no tree walk.
+    const unsigned int* adj; const float4* adj_box; int adj_capacity;
+    int* nn_leaf;            // leaf of nn_pos (or -1): saves the position -> leaf lookup at the start of the next search
     // projective
     float fx, fy, cx, cy; unsigned int width, height;
     // config
@@ -174,7 +176,7 @@ cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_s
                                    unsigned int* table, unsigned int* mask, size_t mask_words, cudaStream_t s, int* n_launches);
 // Leaf adjacency lists for the leaves [0, min(n_leaves, capacity)).
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
-                                      int* adj_n, float* adj_r, int capacity, int n_sms, cudaStream_t s, int* n_launches);
+                                      float4* adj_box, int capacity, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         {
             const int sp = a.use_seed ? a.nn_pos[p] : -1;
             if (sp >= 0 && sp < a.n_tgt) {
-                seed_leaf = (int)(__ldg(&a.leaf_rank[sp + 1]) - 1u);
+                seed_leaf = a.nn_leaf[p];
                 const unsigned int i = __ldg(&a.leaf_start[seed_leaf]) + lane;
                 if (i < __ldg(&a.leaf_start[seed_leaf + 1])) {
                     const float4 c = __ldg(&a.tgt_pts[i]);
@@ -268,18 +268,16 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         }
         bool done = false;
         if (seed_leaf >= 0 && seed_leaf < a.adj_capacity) {
-            // Shortcut without the tree: if the search ball lies inside the seed leaf's box inflated by R, every leaf
-            // that meets the ball is in that leaf's adjacency list (built with the same inflated box, grid.cu).
-            const float R = __ldg(&a.adj_r[seed_leaf]);
+            // Shortcut without the tree: if the search ball lies inside the seed leaf's inflated box, every leaf that
+            // meets the ball is in that leaf's adjacency list (built with the same inflated box, grid.cu).
             float bnd = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
-            if (R >= 0.0f && bnd < FLT_BIG) {
+            if (bnd < FLT_BIG) {
                 const float r = __fmul_ru(__fsqrt_ru(bnd), 1.00001f);
-                const float4 mlo = __ldg(&a.bvh_box[2 * (size_t)seed_leaf]), mhi = __ldg(&a.bvh_box[2 * (size_t)seed_leaf + 1]);
-                const bool inside = __fsub_rd(q.x, r) >= __fsub_rd(mlo.x, R) && __fadd_ru(q.x, r) <= __fadd_ru(mhi.x, R) &&
-                                    __fsub_rd(q.y, r) >= __fsub_rd(mlo.y, R) && __fadd_ru(q.y, r) <= __fadd_ru(mhi.y, R) &&
-                                    __fsub_rd(q.z, r) >= __fsub_rd(mlo.z, R) && __fadd_ru(q.z, r) <= __fadd_ru(mhi.z, R);
-                if (inside) {
-                    const int na = __ldg(&a.adj_n[seed_leaf]);
+                const float4 ilo = __ldg(&a.adj_box[2 * (size_t)seed_leaf]), ihi = __ldg(&a.adj_box[2 * (size_t)seed_leaf + 1]);
+                const bool inside = __fsub_rd(q.x, r) >= ilo.x && __fadd_ru(q.x, r) <= ihi.x && __fsub_rd(q.y, r) >= ilo.y &&
+                                    __fadd_ru(q.y, r) <= ihi.y && __fsub_rd(q.z, r) >= ilo.z && __fadd_ru(q.z, r) <= ihi.z;
+                if (inside) {                                                   // never true for the inverted "no list" box
+                    const int na = __float_as_int(ilo.w);
                     unsigned int leaf = 0; float clb = FLT_BIG; bool keep = false;
                     if (lane < na) {
                         leaf = __ldg(&a.adj[(size_t)seed_leaf * 32 + lane]);
@@ -345,7 +343,10 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         const int imin = __reduce_min_sync(FULL, cand);
         const int src_lane = __ffs((int)__ballot_sync(FULL, cand == imin)) - 1;
         const int pos = imin == INT_MAX ? -1 : __shfl_sync(FULL, b.pos, src_lane);
-        if (lane == 0) a.nn_pos[p] = pos;
+        if (lane == 0) {
+            a.nn_pos[p] = pos;
+            a.nn_leaf[p] = pos >= 0 ? (int)(__ldg(&a.leaf_rank[pos + 1]) - 1u) : -1;      // off the critical path: nothing waits for it
+        }
     }
     flush_stats(a, 0u, 0u, ev, nd);
 }
