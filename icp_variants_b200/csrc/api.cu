@@ -68,6 +68,11 @@ struct Plan {
 struct icp_gpu_ctx {
     int device = 0, n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                      // host uploads run here and overlap the previous cloud's build
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};           // [target, source]: staging filled
+    cudaEvent_t ev_packed[2] = {nullptr, nullptr};           // staging consumed by the pack kernel
+    bool packed_once[2] = {false, false};
+    DeviceBuf stage2;                                        // the source's staging area (the target uses `stage`)
     icp_gpu_config cfg;
     float K[9]; uint32_t width = 0, height = 0; bool have_camera = false;
     // clouds
@@ -122,7 +127,7 @@ int fail(icp_gpu_ctx* c, int code, const char* fmt, ...) {
 int ensure(icp_gpu_ctx* ctx, DeviceBuf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return 0;
     if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
-    if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    if (b.p) { cudaStreamSynchronize(ctx->stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8 + 256;
     CU(cudaMalloc(&b.p, want));
     b.cap = want;
@@ -158,22 +163,29 @@ int coarsest_stride(long long n) {   // ICPOptimizer.h:503-516
 }
 
 int upload_cloud(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n, bool device_ptrs,
-                 DeviceBuf& pts, DeviceBuf& nrmb) {
+                 DeviceBuf& pts, DeviceBuf& nrmb, int kind /*0 target, 1 source*/) {
     const size_t n1 = (size_t)(n > 0 ? n : 1);
     if (ensure(ctx, pts, n1 * sizeof(float4)) || ensure(ctx, nrmb, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
     if (n == 0) return 0;
     const float* dx = xyz; const float* dn = nrm; const uint8_t* dc = rgba;
     if (!device_ptrs) {
+        // Host arrays go through a per-cloud staging area on the copy stream, so that the upload of one cloud overlaps
+        // the index build of the other on the compute stream.
+        DeviceBuf& stage = kind == 0 ? ctx->stage : ctx->stage2;
         const size_t bx = (size_t)n * 12, bc = (size_t)n * 4;
         const size_t ox = 0, on = (bx + 255) / 256 * 256, oc = on + (nrm ? (bx + 255) / 256 * 256 : 0);
-        if (ensure(ctx, ctx->stage, oc + (rgba ? bc : 0) + 256)) return ICP_GPU_E_CUDA;
-        char* st = (char*)ctx->stage.p;
-        CU(cudaMemcpyAsync(st + ox, xyz, bx, cudaMemcpyHostToDevice, ctx->stream));
+        if (ensure(ctx, stage, oc + (rgba ? bc : 0) + 256)) return ICP_GPU_E_CUDA;
+        char* st = (char*)stage.p;
+        if (ctx->packed_once[kind]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[kind], 0));   // staging still being read?
+        CU(cudaMemcpyAsync(st + ox, xyz, bx, cudaMemcpyHostToDevice, ctx->copy_stream));
         dx = (const float*)(st + ox);
-        if (nrm) { CU(cudaMemcpyAsync(st + on, nrm, bx, cudaMemcpyHostToDevice, ctx->stream)); dn = (const float*)(st + on); }
-        if (rgba) { CU(cudaMemcpyAsync(st + oc, rgba, bc, cudaMemcpyHostToDevice, ctx->stream)); dc = (const uint8_t*)(st + oc); }
+        if (nrm) { CU(cudaMemcpyAsync(st + on, nrm, bx, cudaMemcpyHostToDevice, ctx->copy_stream)); dn = (const float*)(st + on); }
+        if (rgba) { CU(cudaMemcpyAsync(st + oc, rgba, bc, cudaMemcpyHostToDevice, ctx->copy_stream)); dc = (const uint8_t*)(st + oc); }
+        CU(cudaEventRecord(ctx->ev_copied[kind], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[kind], 0));
     }
     CU(icp_launch_pack_cloud(dx, dn, dc, (int)n, (float4*)pts.p, (float4*)nrmb.p, ctx->stream));
+    if (!device_ptrs) { CU(cudaEventRecord(ctx->ev_packed[kind], ctx->stream)); ctx->packed_once[kind] = true; }
     ctx->stats.n_kernel_launches += 1;
     return 0;
 }
@@ -243,23 +255,14 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     if (target) {
-        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->tgt_pts, ctx->tgt_nrm)) return ICP_GPU_E_CUDA;
+        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->tgt_pts, ctx->tgt_nrm, 0)) return ICP_GPU_E_CUDA;
         ctx->n_tgt = (int)n;
         // buildIndex: the grid is always built (cheap), the matcher choice is made per call
         if (build_grid(ctx)) return ICP_GPU_E_CUDA;
     } else {
-        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->src_raw_pts, ctx->src_raw_nrm)) return ICP_GPU_E_CUDA;
+        if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->src_raw_pts, ctx->src_raw_nrm, 1)) return ICP_GPU_E_CUDA;
         ctx->n_src = (int)n;
-        ctx->src_finite_valid = false; ctx->src_rank_valid = false;
-        if (!dev) {
-            ctx->src_finite.resize((size_t)n);
-            for (int64_t i = 0; i < n; ++i) {
-                bool f = isfinite(xyz[3 * i]) && isfinite(xyz[3 * i + 1]) && isfinite(xyz[3 * i + 2]);
-                if (nrm) f = f && isfinite(nrm[3 * i]) && isfinite(nrm[3 * i + 1]) && isfinite(nrm[3 * i + 2]);
-                ctx->src_finite[(size_t)i] = f ? 1 : 0;
-            }
-            ctx->src_finite_valid = true;
-        }
+        ctx->src_finite_valid = false; ctx->src_rank_valid = false;     // fetched lazily from the device when a plan needs them
         const size_t n1 = (size_t)(n > 0 ? n : 1);
         if (ensure(ctx, ctx->match_pos, n1 * 4) || ensure(ctx, ctx->match_w, n1 * 4) || ensure(ctx, ctx->match_idx, n1 * 4) ||
             ensure(ctx, ctx->nn_pos, n1 * 4) || ensure(ctx, ctx->nn_leaf, n1 * 4) || ensure(ctx, ctx->qbuf, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
@@ -269,9 +272,9 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
     }
     // a new cloud invalidates the neighbours remembered from earlier searches
     if (ctx->n_src > 0 && ctx->nn_pos.p) { CU(icp_launch_fill_int((int*)ctx->nn_pos.p, ctx->n_src, -1, ctx->stream)); ctx->stats.n_kernel_launches += 1; }
-    // Host arrays are only borrowed for the duration of the call: wait for the copies.  The device-pointer
-    // forms stay asynchronous (stream-ordered with everything that follows).
-    if (!dev) CU(cudaStreamSynchronize(ctx->stream));
+    // Host arrays are only borrowed for the duration of the call: wait for the copies (not for the index build, which
+    // keeps running on the compute stream).  The device-pointer forms are fully asynchronous.
+    if (!dev && n > 0) CU(cudaEventSynchronize(ctx->ev_copied[target ? 0 : 1]));
     return ICP_GPU_OK;
 }
 
@@ -592,7 +595,10 @@ int icp_gpu_create(icp_gpu_ctx** out, int device) {
     if (ok) ctx->n_sms = prop.multiProcessorCount;
     ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->stream = ctx->own_stream;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+                                           cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_pose, 16 * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_history, 16 * sizeof(float) * ICP_MAX_ITERS) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_state, sizeof(DevState)) == cudaSuccess;
@@ -610,8 +616,9 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     if (!ctx) return ICP_GPU_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
-    DeviceBuf* bufs[] = {&ctx->stage, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
+    DeviceBuf* bufs[] = {&ctx->stage, &ctx->stage2, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
@@ -622,6 +629,8 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ICP_GPU_OK;
