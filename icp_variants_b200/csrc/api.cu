@@ -83,7 +83,8 @@ struct icp_gpu_ctx {
     std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
     bool src_rank_valid = false;
     // target grid
-    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, pstart, adj, adj_box;
+    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, pstart, adj, adj_box, adj1, adj1_box;
+    int adj1_capacity = 0;
     int adj_capacity = 0;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
     // source grid: only its sort order is used (consecutive queries are spatial neighbours: coherent tree walks)
@@ -205,7 +206,9 @@ int build_grid(icp_gpu_ctx* ctx) {
         return ICP_GPU_E_CUDA;
     // adjacency lists for up to n/4 leaves (a healthy tree has ~n/20); a cloud with more leaves simply gets no shortcut for the rest
     ctx->adj_capacity = (int)(n1 / 4 + 64);
-    if (ensure(ctx, ctx->adj, (size_t)ctx->adj_capacity * 32 * 4) || ensure(ctx, ctx->adj_box, (size_t)ctx->adj_capacity * 2 * sizeof(float4)))
+    ctx->adj1_capacity = (int)(n1 / 32 + 64);
+    if (ensure(ctx, ctx->adj, (size_t)ctx->adj_capacity * 32 * 4) || ensure(ctx, ctx->adj_box, (size_t)ctx->adj_capacity * 2 * sizeof(float4)) ||
+        ensure(ctx, ctx->adj1, (size_t)ctx->adj1_capacity * 32 * 4) || ensure(ctx, ctx->adj1_box, (size_t)ctx->adj1_capacity * 2 * sizeof(float4)))
         return ICP_GPU_E_CUDA;
     int launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -222,7 +225,10 @@ int build_grid(icp_gpu_ctx* ctx) {
                             (unsigned int*)ctx->node_rank.p, (unsigned int*)ctx->child_start.p, (unsigned int*)ctx->pstart.p,
                             (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ctx->stream, &launches));
     CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
-                                 (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, ctx->n_sms,
+                                 (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, 0, ctx->n_sms,
+                                 ctx->stream, &launches));
+    CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
+                                 (unsigned int*)ctx->adj1.p, (float4*)ctx->adj1_box.p, ctx->adj1_capacity, 1, ctx->n_sms,
                                  ctx->stream, &launches));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
@@ -386,6 +392,9 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.leaf_rank = (const unsigned int*)c->leaf_rank.p; a.child_start = (const unsigned int*)c->child_start.p;
     a.adj = (const unsigned int*)c->adj.p; a.adj_box = (const float4*)c->adj_box.p; a.adj_capacity = c->adj_capacity;
     a.nn_leaf = (int*)c->nn_leaf.p;
+    a.adj1 = (const unsigned int*)c->adj1.p; a.adj1_box = (const float4*)c->adj1_box.p; a.adj1_capacity = c->adj1_capacity;
+    a.node_rank = (const unsigned int*)c->node_rank.p;
+    if (getenv("ICP_GPU_NO_ADJACENCY1")) a.adj1_capacity = 0;   // tuning knob
     if (getenv("ICP_GPU_NO_ADJACENCY")) a.adj_capacity = 0;   // tuning knob
     if (c->have_camera) { a.fx = c->K[0]; a.fy = c->K[4]; a.cx = c->K[6]; a.cy = c->K[7]; }   // column-major Matrix3f
     a.width = c->width; a.height = c->height;
@@ -622,7 +631,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->voxel_table, &ctx->nn_leaf};
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);

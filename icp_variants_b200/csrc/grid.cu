@@ -553,18 +553,21 @@ __device__ __forceinline__ bool boxes_meet(const float* lo, const float* hi, con
 __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const BvhDesc* __restrict__ bvh, const float4* __restrict__ box,
                                                                          const unsigned int* __restrict__ child_start,
                                                                          unsigned int* __restrict__ adj, float4* __restrict__ adj_box,
-                                                                         int capacity, float r_factor) {
+                                                                         int capacity, float r_factor, int lv) {
     __shared__ unsigned int s_node[ADJ_WARPS][32 * ICP_BVH_MAX_LEVELS];
     __shared__ unsigned int s_list[ADJ_WARPS][64];
     const BvhDesc b = *bvh;
     const unsigned int FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = (gridDim.x * blockDim.x) >> 5;
-    const int n_leaves = min(b.n_leaves, capacity);
+    // lv = 0: lists of leaves (the node itself excluded: a search has scanned it already); lv = 1: lists of level-1 nodes
+    // (the node itself included)
+    if (lv >= b.n_levels) return;
+    const int n_leaves = min(b.count[lv], capacity);
     const int top_level = b.n_levels - 1;
     unsigned int* st = s_node[wid]; unsigned int* list = s_list[wid];
     const unsigned int lt = (1u << lane) - 1u;
     for (int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < n_leaves; l += warps) {
-        const float4 mlo = box[2 * (size_t)l], mhi = box[2 * (size_t)l + 1];      // level 0 has offset 0
+        const float4 mlo = box[2 * (size_t)(b.offset[lv] + l)], mhi = box[2 * (size_t)(b.offset[lv] + l) + 1];
         float R = r_factor * fmaxf(fmaxf(mhi.x - mlo.x, mhi.y - mlo.y), mhi.z - mlo.z);
         int count = 0; bool ok = false;
         for (int attempt = 0; attempt < 6 && !ok; ++attempt, R *= 0.5f) {
@@ -579,9 +582,9 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
                     const unsigned int c = first + lane;
                     bool keep = false;
                     if (c < last) keep = boxes_meet(lo, hi, box[2 * (size_t)(b.offset[L] + c)], box[2 * (size_t)(b.offset[L] + c) + 1]);
-                    if (L == 0) keep = keep && c != (unsigned int)l;
+                    if (L == lv && lv == 0) keep = keep && c != (unsigned int)l;
                     const unsigned int mk = __ballot_sync(FULL, keep);
-                    if (L == 0) {
+                    if (L == lv) {
                         if (count + __popc(mk) > 32) { ok = false; break; }
                         if (keep) list[count + __popc(mk & lt)] = c;
                         count += __popc(mk);
@@ -619,13 +622,13 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
 }
 
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
-                                      float4* adj_box, int capacity, int n_sms, cudaStream_t s, int* n_launches) {
+                                      float4* adj_box, int capacity, int level, int n_sms, cudaStream_t s, int* n_launches) {
     long long nb = ((long long)capacity + ADJ_WARPS - 1) / ADJ_WARPS;
     if (nb > 16ll * n_sms) nb = 16ll * n_sms;
     if (nb < 1) nb = 1;
     float r_factor = 2.0f;
     if (const char* e = getenv("ICP_GPU_ADJ_FACTOR")) r_factor = (float)atof(e);   // tuning knob
-    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_box, capacity, r_factor);
+    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_box, capacity, r_factor, level);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

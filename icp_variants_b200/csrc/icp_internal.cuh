@@ -119,6 +119,9 @@ struct MatchArgs {
     // adj_box[2*l] = {lo - R, n as int bits}, adj_box[2*l+1] = {hi + R, _}; an inverted box (lo > hi) means "no list".
     // A query whose search ball lies inside the inflated box needs no tree walk.
     const unsigned int* adj; const float4* adj_box; int adj_capacity;
+    // the same one level up: adj1[32*m ..] = the level-1 nodes (m itself included) whose box meets box(m) inflated; node_rank
+    // maps a leaf to its level-1 node (node_rank[coffset[1] + leaf + 1] - 1)
+    const unsigned int* adj1; const float4* adj1_box; int adj1_capacity; const unsigned int* node_rank;
     int* nn_leaf;            // leaf of nn_pos (or -1): saves the position -> leaf lookup at the start of the next search
     // projective
     float fx, fy, cx, cy; unsigned int width, height;
@@ -176,7 +179,7 @@ cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_s
                                    unsigned int* table, unsigned int* mask, size_t mask_words, cudaStream_t s, int* n_launches);
 // Leaf adjacency lists for the leaves [0, min(n_leaves, capacity)).
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
-                                      float4* adj_box, int capacity, int n_sms, cudaStream_t s, int* n_launches);
+                                      float4* adj_box, int capacity, int level, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective

@@ -290,6 +290,40 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                 }
             }
         }
+        if (!done && seed_leaf >= 0 && top_level >= 1 && a.adj1_capacity > 0) {
+            // The same shortcut one level up: the ball inside the inflated box of the seed leaf's level-1 node => every
+            // level-1 node that meets the ball is in that node's list; their leaves are tested 32 at a time.
+            const int m = (int)(__ldg(&a.node_rank[bvh.coffset[1] + seed_leaf + 1]) - 1u);
+            float bnd = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
+            if (m < a.adj1_capacity && bnd < FLT_BIG) {
+                const float r = __fmul_ru(__fsqrt_ru(bnd), 1.00001f);
+                const float4 ilo = __ldg(&a.adj1_box[2 * (size_t)m]), ihi = __ldg(&a.adj1_box[2 * (size_t)m + 1]);
+                const bool inside = __fsub_rd(q.x, r) >= ilo.x && __fadd_ru(q.x, r) <= ihi.x && __fsub_rd(q.y, r) >= ilo.y &&
+                                    __fadd_ru(q.y, r) <= ihi.y && __fsub_rd(q.z, r) >= ilo.z && __fadd_ru(q.z, r) <= ihi.z;
+                if (inside) {
+                    const int na = __float_as_int(ilo.w);
+                    unsigned int node = 0; unsigned int key = 0xFFFFFFFFu;
+                    if (lane < na) {
+                        node = __ldg(&a.adj1[(size_t)m * 32 + lane]);
+                        const float clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node)]), __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node) + 1]));
+                        if (!(clb > bnd)) key = __float_as_uint(clb);
+                    }
+                    if (lane == 0) ++nd;
+                    int top = 0;
+                    for (;;) {                                                   // the level-1 nodes that can matter, nearest first
+                        const unsigned int kmin = __reduce_min_sync(FULL, key);
+                        if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bnd) break;
+                        const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
+                        const unsigned int j = __shfl_sync(FULL, node, src);
+                        if (lane == src) key = 0xFFFFFFFFu;
+                        const unsigned int first = __ldg(&a.child_start[bvh.coffset[1] + j]), last = __ldg(&a.child_start[bvh.coffset[1] + j + 1]);
+                        if (lane == 0) ++nd;
+                        bvh_visit<COLOR>(a, bvh, q, b, bnd, 0, first, last, st_node, st_lb, top, lane, lt_mask, ev, nd);
+                    }
+                    done = true;
+                }
+            }
+        }
         if (!done && !__any_sync(FULL, b.pos >= 0) && top_level > 0) {
             // No neighbour remembered (first iteration): follow the nearest node down to one leaf and take its best
             // point as the starting bound, so that the walk below prunes from its first step on.
