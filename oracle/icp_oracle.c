@@ -1,8 +1,9 @@
 /*
  * icp_oracle.c -- CPU restatement of the ICP-Variants registration inner loop (see icp_oracle.h).
  *
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (no reference tests / golden vectors exist and the
- * reference does not compile here -- see the header).  Build: oracle/Makefile
+ * TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own headers compiled in place
+ * (oracle/_ref, tests/test_oracle_vs_reference.py, tests/golden/reference_outputs.npz); the absent
+ * third-party libraries' last bits stay a stated contract -- see the header.  Build: oracle/Makefile
  *   gcc -std=c11 -O2 -ffp-contract=off -fopenmp -shared -fPIC
  * -ffp-contract=off is part of the numerics contract: every fp32 expression below is evaluated
  * exactly as written (no FMA), left to right.

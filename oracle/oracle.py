@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product (icp_variants_b200/) never imports this.
-PARITY UNPINNED: see oracle/icp_oracle.h.
+Pinned against the reference's own code through oracle/ref.py (see oracle/icp_oracle.h).
 """
 from __future__ import annotations
 
@@ -157,6 +157,22 @@ def projective(tgt, width, height, fx, fy, cx, cy, qry, max_d2):
     lib().orc_projective(_p(tgt), C.c_uint32(width), C.c_uint32(height), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
                          _p(qry), C.c_int64(len(qry)), C.c_float(max_d2), _p(out))
     return out
+
+
+def apply_weights(method, max_d2, sp, sn, sc, tp, tn, tc, matches):
+    """weighting.h:39-99 on per-source arrays + matches (copy returned)."""
+    sp, sn, tp, tn = _f32(sp), _f32(sn), _f32(tp), _f32(tn); sc, tc = _u8(sc), _u8(tc)
+    m = np.ascontiguousarray(matches, MATCH_DTYPE).copy()
+    lib().orc_apply_weights(C.c_int(method), C.c_float(max_d2), _p(sp), _p(tp), _p(sn), _p(tn), _p(sc), _p(tc), C.c_int64(len(m)), _p(m))
+    return m
+
+
+def prune(sn, tn, matches):
+    """ICPOptimizer.h:157-174 (copy returned)."""
+    sn, tn = _f32(sn), _f32(tn)
+    m = np.ascontiguousarray(matches, MATCH_DTYPE).copy()
+    lib().orc_prune(_p(sn), _p(tn), C.c_int64(len(m)), _p(m))
+    return m
 
 
 def match_pipeline(cfg: Config, pose, src, src_n, src_c, tgt, tgt_n, tgt_c, sel_idx=None, tree: KdTree | None = None,
