@@ -404,6 +404,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.nn_pos = (int*)c->nn_pos.p; a.qbuf = (float4*)c->qbuf.p;
     a.desc_index = desc_index;
     a.use_seed = grid_order ? 1 : 0;
+    a.fast_path = getenv("ICP_GPU_NO_FASTPATH") ? 0 : 1;   // tuning knob (A/B measurement)
     a.collect_stats = c->cfg.collect_stats;
 }
 

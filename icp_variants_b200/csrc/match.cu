@@ -207,21 +207,84 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
 //   knn_prep_kernel     thread per query: selection predicate + transformPoints -> qbuf {x,y,z,rgba}; x = NaN: not searched
 //   knn_bvh_kernel      warp per query: seed leaf, walk, arg-min -> nn_pos[p]
 //   match_finish_kernel thread per query: transformNormals, weighting, rejection -> the match records
+// One thread scans one leaf for its own query (fast path of knn_prep_kernel).
+template <bool COLOR>
+__device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query& q, Best& b, int& bleaf, unsigned int leaf, unsigned int& ev) {
+    const unsigned int ls = __ldg(&a.leaf_start[leaf]), le = __ldg(&a.leaf_start[leaf + 1]);
+    for (unsigned int i = ls; i < le; ++i) {
+        const float4 pt = __ldg(&a.tgt_pts[i]);
+        const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
+        const int idx = __float_as_int(pt.w);
+        if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; bleaf = (int)leaf; }
+    }
+    ev += le - ls;
+}
+
+// Thread per query: selection predicate + transformPoints -> qbuf, and the FAST PATH of the search.  A query that
+// remembers a neighbour scans that neighbour's leaf by itself; if its search ball then lies inside the leaf's inflated box,
+// the leaves that can still matter are all in the leaf's adjacency list (grid.cu) and the thread tests and scans them
+// itself -- same candidates, same (d, idx) order, hence the same answer as the walk -- and marks the query as done
+// (qbuf.x = NaN).  The 32 queries of a warp are spatial neighbours (sorted source), so their leaves coincide and the
+// loads are mostly broadcasts.  Everything else (no neighbour yet, ball leaving the box) is left to knn_bvh_kernel.
+template <bool COLOR>
 __global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n_src) return;
-    const float4 p4 = __ldg(&a.src_pts[p]);
-    const float4 n4 = __ldg(&a.src_nrm[p]);
-    float4 o = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, n4.w);
-    if (query_active(d, a.mask, p4, n4)) {
-        float x, y, z;
-        xform_point(sm.P, p4.x, p4.y, p4.z, x, y, z);
-        if (finite3(x, y, z)) { o.x = x; o.y = y; o.z = z; }
+    unsigned int ev = 0, nd = 0;
+    if (p < a.n_src) {
+        const float4 p4 = __ldg(&a.src_pts[p]);
+        const float4 n4 = __ldg(&a.src_nrm[p]);
+        float4 o = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, n4.w);
+        if (query_active(d, a.mask, p4, n4)) {
+            float x, y, z;
+            xform_point(sm.P, p4.x, p4.y, p4.z, x, y, z);
+            if (finite3(x, y, z)) {
+                o.x = x; o.y = y; o.z = z;
+                const int sp = (a.fast_path && a.use_seed) ? a.nn_pos[p] : -1;
+                const int seed_leaf = (sp >= 0 && sp < a.n_tgt) ? a.nn_leaf[p] : -1;
+                if (seed_leaf >= 0 && seed_leaf < a.adj_capacity) {
+                    Query q; q.x = x; q.y = y; q.z = z;
+                    const unsigned int s_rgba = __float_as_uint(n4.w);
+                    q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
+                    Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
+                    int bleaf = -1;
+                    thread_scan_leaf<COLOR>(a, q, b, bleaf, (unsigned int)seed_leaf, ev); ++nd;
+                    if (b.d < FLT_BIG) {
+                        const float r = __fmul_ru(__fsqrt_ru(b.d), 1.00001f);
+                        const float4 ilo = __ldg(&a.adj_box[2 * (size_t)seed_leaf]), ihi = __ldg(&a.adj_box[2 * (size_t)seed_leaf + 1]);
+                        const bool inside = __fsub_rd(x, r) >= ilo.x && __fadd_ru(x, r) <= ihi.x && __fsub_rd(y, r) >= ilo.y &&
+                                            __fadd_ru(y, r) <= ihi.y && __fsub_rd(z, r) >= ilo.z && __fadd_ru(z, r) <= ihi.z;
+                        if (inside) {                                           // never true for the inverted "no list" box
+                            const int na = __float_as_int(ilo.w);
+                            const unsigned int* list = a.adj + (size_t)seed_leaf * 32;
+                            // two phases, so that the lanes of a warp scan their leaves side by side instead of one
+                            // list position at a time: first the box tests, then the scans of the leaves that passed
+                            unsigned int todo = 0;
+                            for (int j = 0; j < na; ++j) {
+                                const unsigned int leaf = __ldg(&list[j]);
+                                const float clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                                if (!(clb > b.d)) todo |= 1u << j;
+                            }
+                            while (todo) {
+                                const int j = __ffs((int)todo) - 1; todo &= todo - 1u;
+                                const unsigned int leaf = __ldg(&list[j]);
+                                const float clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                                if (!(clb > b.d)) { thread_scan_leaf<COLOR>(a, q, b, bleaf, leaf, ev); ++nd; }
+                            }
+                            ++nd;
+                            a.nn_pos[p] = b.idx == INT_MAX ? -1 : b.pos;
+                            a.nn_leaf[p] = b.idx == INT_MAX ? -1 : bleaf;
+                            o.x = __int_as_float(0x7fc00000);                   // searched: nothing left for the walk
+                        }
+                    }
+                }
+            }
+        }
+        a.qbuf[p] = o;
     }
-    a.qbuf[p] = o;
+    flush_stats(a, 0u, 0u, ev, nd);
 }
 
 template <bool COLOR>
@@ -539,7 +602,8 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
         ++launches;
     } else {
-        knn_prep_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches;
+        if (a.color_icp) knn_prep_kernel<true><<<(a.n_src + 255) / 256, 256, 0, s>>>(a); else knn_prep_kernel<false><<<(a.n_src + 255) / 256, 256, 0, s>>>(a);
+        ++launches;
         int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
         if (nb > 64 * n_sms) nb = 64 * n_sms;
         if (a.color_icp) knn_bvh_kernel<true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
