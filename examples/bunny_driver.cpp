@@ -30,7 +30,12 @@ int main(int argc, char** argv) {
     optimizer->setNbOfIterations((unsigned)std::atoi(argv[5]));
     optimizer->setSelectionMethod(SELECT_ALL);
     optimizer->setWeightingMethod(CONSTANT_WEIGHTING);
-    TimeMeasure timeMeasure; ConvergenceMeasure convergenceMeasure;
+    // the hand-picked ground-truth correspondences of the bunny pair (main.cpp:105-120), when the clouds are large enough
+    const int gtSource[4] = {215, 424, 640, 1023}, gtTarget[4] = {294, 258, 1238, 1310};
+    std::vector<Vector3f> gs, gt;
+    if (source.getPoints().size() > 1023 && target.getPoints().size() > 1310)
+        for (int i = 0; i < 4; ++i) { gs.push_back(source.getPoints()[(size_t)gtSource[i]]); gt.push_back(target.getPoints()[(size_t)gtTarget[i]]); }
+    TimeMeasure timeMeasure; ConvergenceMeasure convergenceMeasure(gs, gt, true);
     optimizer->setTimeMeasure(timeMeasure);
     optimizer->setConvergenceMeasure(convergenceMeasure);
     Matrix4f estimatedPose = Matrix4f::Identity();
@@ -38,6 +43,9 @@ int main(int argc, char** argv) {
     std::printf("POSE");
     for (int i = 0; i < 16; ++i) std::printf(" %.9g", estimatedPose.data()[i]);
     std::printf("\n");
+    if (!convergenceMeasure.getRMSE().empty())
+        std::printf("RMSE %.9g BENCHMARK %.9g ITERATIONS %d\n", convergenceMeasure.getFinalErrorRMSE(), convergenceMeasure.getFinalErrorBenchmark(),
+                    (int)convergenceMeasure.getRMSE().size());
     delete optimizer;
     return 0;
 }

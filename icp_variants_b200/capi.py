@@ -104,6 +104,9 @@ def lib():
             "icp_gpu_estimate_pose_async": (C.c_int, [vp, pf]),
             "icp_gpu_estimate_pose_finish": (C.c_int, [vp, pf, pf, C.POINTER(i32)]),
             "icp_gpu_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+            "icp_gpu_cloud_from_depth": (C.c_int, [vp, pf, pf, pf, pf, u32, u32, C.c_int, u32, C.c_float, C.c_int, pf, pf, pf, C.POINTER(i64)]),
+            "icp_gpu_set_correspondences": (C.c_int, [vp, pf, pf, i64]),
+            "icp_gpu_convergence_errors": (C.c_int, [vp, pf, pf, i32, C.POINTER(i32)]),
             "icp_gpu_iteration_phases": (C.c_int, [vp]),
             "icp_gpu_iteration_begin": (C.c_int, [vp, pf]),
             "icp_gpu_iteration_local": (C.c_int, [vp, C.c_int, pf, C.POINTER(i32)]),
@@ -268,6 +271,41 @@ class Context:
         n_it = C.c_int32(0)
         self._check(lib().icp_gpu_estimate_pose_finish(self._h, _ptr(p), None, C.byref(n_it)))
         return pose_from_c(p), n_it.value
+
+    def cloud_from_depth(self, depth, rgbx, K, extrinsics=None, keep_original_size=False, downsample=1, max_distance=0.1,
+                         role: int = 2, download: bool = True):
+        """PointCloud(depthMap, colorFrame, ...) (PointCloud.h:78-165) on the device.  role 0: the cloud becomes the
+        target (buildIndex), 1: the source, 2: only returned.  Returns (points, normals, colours) or the point count."""
+        depth = np.ascontiguousarray(depth, np.float32); h, w = depth.shape
+        col = None if rgbx is None else np.ascontiguousarray(rgbx, np.uint8).reshape(-1)
+        if col is not None and col.size < h * w + 3:
+            raise ValueError("rgbx must hold the RGBX frame (4*w*h bytes)")
+        Kc = np.ascontiguousarray(np.asarray(K, np.float32).T.reshape(9))
+        Ec = None if extrinsics is None else pose_to_c(extrinsics)
+        cap = (h * w + downsample - 1) // downsample if downsample > 0 else h * w
+        n = C.c_int64(0)
+        if download:
+            po = np.empty((cap, 3), np.float32); no = np.empty((cap, 3), np.float32); co = np.empty((cap, 4), np.uint8)
+        else:
+            po = no = co = None
+        self._check(lib().icp_gpu_cloud_from_depth(self._h, _ptr(depth), _ptr(col), _ptr(Kc), _ptr(Ec), w, h, int(keep_original_size),
+                                                   int(downsample), float(max_distance), int(role), _ptr(po), _ptr(no), _ptr(co), C.byref(n)))
+        if not download:
+            return n.value
+        return po[:n.value].copy(), no[:n.value].copy(), co[:n.value].copy()
+
+    def set_correspondences(self, src_xyz, ref_xyz):
+        s = _f32(src_xyz, 3); r = _f32(ref_xyz, 3)
+        assert len(s) == len(r)
+        self._check(lib().icp_gpu_set_correspondences(self._h, _ptr(s), _ptr(r), len(s)))
+
+    def convergence_errors(self, benchmark: bool = False):
+        """(rmse per iteration, benchmark error per iteration | None) of the last registration, computed on the device."""
+        cap = self.max_iterations()
+        rm = np.zeros(cap, np.float32); be = np.zeros(cap, np.float64) if benchmark else None
+        n = C.c_int32(0)
+        self._check(lib().icp_gpu_convergence_errors(self._h, _ptr(rm), _ptr(be), cap, C.byref(n)))
+        return rm[:n.value].copy(), (be[:n.value].copy() if benchmark else None)
 
     def stats(self) -> Stats:
         s = Stats()

@@ -92,6 +92,8 @@ struct icp_gpu_ctx {
     int Ts = 0;
     // loop state
     DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, nn_leaf, qbuf, partials, pose_dev, history;
+    DeviceBuf prep_in, prep_tmp, prep_out, gt_src, gt_ref, met_partial, met_out;
+    long long n_gt = 0; int last_iters = 0;
     float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
     IterDesc* h_desc = nullptr;                                                       // pinned, DESC_TOTAL
     int n_reduce_blocks = 1;
@@ -558,6 +560,7 @@ int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_histor
     if (pose_out) memcpy(pose_out, st.pose, 16 * sizeof(float));
     if (pose_history && st.iters_done > 0) memcpy(pose_history, ctx->h_history, sizeof(float) * 16 * (size_t)st.iters_done);
     if (n_iterations_out) *n_iterations_out = st.iters_done;
+    ctx->last_iters = st.iters_done;
     copy_counters(ctx);
     if (st.status == ICP_GPU_E_NO_MATCHES)
         return fail(ctx, ICP_GPU_E_NO_MATCHES, "iteration %d had no surviving correspondence (the reference hangs in ASSERT here)", st.iters_done);
@@ -632,7 +635,8 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf};
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf,
+                         &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);
@@ -680,6 +684,109 @@ int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
     if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);
     if (c->matching == ICP_GPU_MATCH_PROJECTIVE && c->color_icp) return fail(ctx, ICP_GPU_E_ARG, "colour ICP is a k-NN variant (main.cpp:240-243)");
     ctx->cfg = *c;
+    return ICP_GPU_OK;
+}
+
+// PointCloud(depthMap, colorFrame, depthIntrinsics, depthExtrinsics, width, height, keepOriginalSize, downsampleFactor,
+// maxDistance) -- PointCloud.h:78-165 -- on the device; the result can become the context's target or source directly.
+int icp_gpu_cloud_from_depth(icp_gpu_ctx* ctx, const float* depth, const uint8_t* rgbx, const float K[9], const float E[16],
+                             uint32_t width, uint32_t height, int keep_original_size, uint32_t downsample, float max_distance, int role,
+                             float* xyz_out, float* nrm_out, uint8_t* rgba_out, int64_t* n_out) {
+    if (!ctx || !K) return ICP_GPU_E_ARG;
+    if (!depth || width == 0 || height == 0 || downsample == 0 || (long long)width * height > 0x7fffffff / 4)
+        return fail(ctx, ICP_GPU_E_ARG, "bad depth map (%p, %ux%u, downsample %u)", (const void*)depth, width, height, downsample);
+    if (role < ICP_GPU_CLOUD_TARGET || role > ICP_GPU_CLOUD_ONLY) return fail(ctx, ICP_GPU_E_ARG, "role %d", role);
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    const long long npx = (long long)width * height;
+    DepthArgs a; memset(&a, 0, sizeof(a));
+    a.width = width; a.height = height; a.downsample = downsample; a.keep_original_size = keep_original_size ? 1 : 0;
+    a.n_candidates = (npx + downsample - 1) / downsample;
+    a.fovX = K[0]; a.fovY = K[4]; a.cX = K[6]; a.cY = K[7];          // column-major Matrix3f: (0,0), (1,1), (0,2), (1,2)
+    a.half_max_distance = max_distance / 2.f;
+    for (int i = 0; i < 16; ++i) a.Einv[i] = (i % 5 == 0) ? 1.f : 0.f;
+    if (E) {   // inverse in fp64, rounded to fp32 (the reference's drivers only pass the identity, VirtualSensor.h:52)
+        double m[4][8];
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { m[r][c] = E[r + 4 * c]; m[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+        for (int k = 0; k < 4; ++k) {
+            int p = k; for (int i = k + 1; i < 4; ++i) if (fabs(m[i][k]) > fabs(m[p][k])) p = i;
+            if (m[p][k] == 0.0) return fail(ctx, ICP_GPU_E_ARG, "singular depth extrinsics");
+            if (p != k) for (int j = 0; j < 8; ++j) { const double t = m[k][j]; m[k][j] = m[p][j]; m[p][j] = t; }
+            const double d = m[k][k];
+            for (int j = 0; j < 8; ++j) m[k][j] /= d;
+            for (int i = 0; i < 4; ++i) if (i != k) { const double f = m[i][k]; if (f != 0.0) for (int j = 0; j < 8; ++j) m[i][j] -= f * m[k][j]; }
+        }
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) a.Einv[r + 4 * c] = (float)m[r][4 + c];
+    }
+    const size_t nc = (size_t)a.n_candidates, nb = (nc + 255) / 256;
+    const size_t depth_bytes = (size_t)npx * 4, color_bytes = rgbx ? (size_t)npx + 3 : 0;
+    const size_t o_color = (depth_bytes + 255) / 256 * 256;
+    // staging: points, normals, colours, flags, block counts (+ total) ; outputs: points, normals, colours
+    const size_t t_nrm = (nc * 12 + 255) / 256 * 256, t_rgba = 2 * t_nrm, t_flag = t_rgba + (nc * 4 + 255) / 256 * 256,
+                 t_cnt = t_flag + (nc * 4 + 255) / 256 * 256, t_end = t_cnt + (nb + 2) * 4;
+    if (ensure(ctx, ctx->prep_in, o_color + color_bytes + 256) || ensure(ctx, ctx->prep_tmp, t_end + 256) || ensure(ctx, ctx->prep_out, 2 * t_nrm + nc * 4 + 256))
+        return ICP_GPU_E_CUDA;
+    char* in = (char*)ctx->prep_in.p; char* tmp = (char*)ctx->prep_tmp.p; char* out = (char*)ctx->prep_out.p;
+    CU(cudaMemcpyAsync(in, depth, depth_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (rgbx) CU(cudaMemcpyAsync(in + o_color, rgbx, color_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int launches = 0;
+    unsigned int* total = (unsigned int*)(tmp + t_cnt) + nb;
+    CU(icp_launch_depth_cloud((const float*)in, rgbx ? (const unsigned char*)(in + o_color) : nullptr, a, (float*)tmp, (float*)(tmp + t_nrm),
+                              (unsigned char*)(tmp + t_rgba), (unsigned int*)(tmp + t_flag), (unsigned int*)(tmp + t_cnt), total,
+                              (float*)out, (float*)(out + t_nrm), (unsigned char*)(out + 2 * t_nrm), ctx->stream, &launches));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    unsigned int n = 0;
+    CU(cudaMemcpyAsync(&n, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));    // the host arrays were pageable: all copies are done; n is known
+    if (n_out) *n_out = (int64_t)n;
+    if (n > 0) {
+        if (xyz_out) CU(cudaMemcpyAsync(xyz_out, out, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        if (nrm_out) CU(cudaMemcpyAsync(nrm_out, out + t_nrm, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        if (rgba_out) CU(cudaMemcpyAsync(rgba_out, out + 2 * t_nrm, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int rc = ICP_GPU_OK;
+    if (role != ICP_GPU_CLOUD_ONLY)
+        rc = set_cloud(ctx, role == ICP_GPU_CLOUD_TARGET, (const float*)out, (const float*)(out + t_nrm), (const uint8_t*)(out + 2 * t_nrm), (int64_t)n, true);
+    if (xyz_out || nrm_out || rgba_out) CU(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// ConvergenceMeasure(sourcePoints, unchangedPoints) (ConvergenceMeasure.h:32-41): the known correspondences.
+int icp_gpu_set_correspondences(icp_gpu_ctx* ctx, const float* src_xyz, const float* ref_xyz, int64_t m) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (m < 0 || (m > 0 && (!src_xyz || !ref_xyz))) return fail(ctx, ICP_GPU_E_ARG, "bad correspondences (m=%lld)", (long long)m);
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    ctx->n_gt = 0;
+    if (m == 0) return ICP_GPU_OK;
+    if (ensure(ctx, ctx->gt_src, (size_t)m * 12) || ensure(ctx, ctx->gt_ref, (size_t)m * 12)) return ICP_GPU_E_CUDA;
+    CU(cudaMemcpyAsync(ctx->gt_src.p, src_xyz, (size_t)m * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->gt_ref.p, ref_xyz, (size_t)m * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->n_gt = m;
+    return ICP_GPU_OK;
+}
+
+// recordAlignmentError after every iteration of the last registration (ICPOptimizer.h:629-631), evaluated on the device
+// from the per-iteration poses the loop left there.
+int icp_gpu_convergence_errors(icp_gpu_ctx* ctx, float* rmse_out, double* benchmark_out, int32_t capacity, int32_t* n_out) {
+    if (!ctx || !rmse_out) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
+    if (ctx->n_gt <= 0) return fail(ctx, ICP_GPU_E_STATE, "no correspondences set (icp_gpu_set_correspondences)");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    const int n = ctx->last_iters < capacity ? ctx->last_iters : capacity;
+    if (n_out) *n_out = n;
+    if (n <= 0) return ICP_GPU_OK;
+    const int nb = icp_metrics_blocks(ctx->n_gt, ctx->n_sms);
+    if (ensure(ctx, ctx->met_partial, (size_t)n * nb * 6 * sizeof(double)) || ensure(ctx, ctx->met_out, (size_t)n * (4 + 12 + 8) + 64)) return ICP_GPU_E_CUDA;
+    double* bench = (double*)ctx->met_out.p;                       // n doubles, then n rmse floats, then 3n centroid floats
+    float* rmse = (float*)(bench + n); float* centroid = rmse + n;
+    int launches = 0;
+    CU(icp_launch_metrics((const float*)ctx->gt_src.p, (const float*)ctx->gt_ref.p, ctx->n_gt, (const float*)ctx->history.p, n, nb,
+                          (double*)ctx->met_partial.p, rmse, centroid, benchmark_out ? bench : nullptr, ctx->stream, &launches));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    CU(cudaMemcpyAsync(rmse_out, rmse, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (benchmark_out) CU(cudaMemcpyAsync(benchmark_out, bench, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return ICP_GPU_OK;
 }
 

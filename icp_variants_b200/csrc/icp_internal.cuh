@@ -184,6 +184,19 @@ cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box,
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective
+// prep.cu: depth map -> cloud (PointCloud.h:78-165) and convergence metrics (ConvergenceMeasure.h:50-66,104-151)
+struct DepthArgs {
+    unsigned int width, height, downsample; int keep_original_size;
+    long long n_candidates;            // ceil(width*height / downsample)
+    float fovX, fovY, cX, cY, half_max_distance;
+    float Einv[16];                    // inverse depth extrinsics, column-major
+};
+cudaError_t icp_launch_depth_cloud(const float* depth, const unsigned char* color, const DepthArgs& a, float* pts_tmp, float* nrm_tmp,
+                                   unsigned char* rgba_tmp, unsigned int* flag, unsigned int* block_count, unsigned int* total,
+                                   float* pts_out, float* nrm_out, unsigned char* rgba_out, cudaStream_t s, int* n_launches);
+int icp_metrics_blocks(long long m, int n_sms);
+cudaError_t icp_launch_metrics(const float* src, const float* ref, long long m, const float* history, int n_iters, int n_blocks, double* partial,
+                               float* rmse, float* centroid, double* bench, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);

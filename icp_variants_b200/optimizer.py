@@ -50,6 +50,8 @@ class ConvergenceMeasure:
     sourceCorrespondences: np.ndarray | None = None   # [M,3]
     targetCorrespondences: np.ndarray | None = None   # [M,3]
     rmseErrors: list = field(default_factory=list)
+    runBenchmark: bool = False                        # ConvergenceMeasure.h:32: also the Fontana benchmark error (:104-151)
+    benchmarkErrors: list = field(default_factory=list)
 
     def recordAlignmentError(self, pose):
         if self.sourceCorrespondences is None:
@@ -229,10 +231,28 @@ class ICPOptimizer:
             tm.convergenceTime += t.total_ms * 1e-3
             tm.indexTime += t.index_ms * 1e-3
             tm.nIterations = n_it
-        if want_hist:
-            for h in hist:
-                self.m_convergenceMeasure.recordAlignmentError(h)
+        if want_hist and n_it > 0 and self.m_convergenceMeasure.sourceCorrespondences is not None:
+            # recordAlignmentError after every iteration (ICPOptimizer.h:629-631), evaluated on the device from the pose history
+            cm = self.m_convergenceMeasure
+            self._ctx.set_correspondences(cm.sourceCorrespondences, cm.targetCorrespondences)
+            rmse, bench = self._ctx.convergence_errors(benchmark=cm.runBenchmark)
+            cm.rmseErrors.extend(float(r) for r in rmse)
+            if cm.runBenchmark:
+                cm.benchmarkErrors.extend(float(b) for b in bench)
         return pose
+
+    def setTargetFromDepth(self, depthMap, colorFrame, depthIntrinsics, depthExtrinsics=None, keepOriginalSize=False, downsampleFactor=1,
+                           maxDistance=0.1):
+        """PointCloud(depthMap, colorFrame, ...) (PointCloud.h:78-165) built on the device and indexed as the target
+        (reconstructRoom, main.cpp:202-206); returns the number of points."""
+        return self._ctx.cloud_from_depth(depthMap, colorFrame, depthIntrinsics, depthExtrinsics, keepOriginalSize, downsampleFactor,
+                                          maxDistance, role=0, download=False)
+
+    def setSourceFromDepth(self, depthMap, colorFrame, depthIntrinsics, depthExtrinsics=None, keepOriginalSize=False, downsampleFactor=1,
+                           maxDistance=0.1):
+        """The same for the source frame (main.cpp:295-298)."""
+        return self._ctx.cloud_from_depth(depthMap, colorFrame, depthIntrinsics, depthExtrinsics, keepOriginalSize, downsampleFactor,
+                                          maxDistance, role=1, download=False)
 
 
 class LinearICPOptimizer(ICPOptimizer):

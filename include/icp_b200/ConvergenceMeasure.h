@@ -1,14 +1,25 @@
 // ConvergenceMeasure.h -- RMSE over known correspondences after every iteration
 // (reference: icp-variants/ConvergenceMeasure.h:15-78; fed from the loop at ICPOptimizer.h:629-631).
-// The device loop returns its per-iteration poses; recordAlignmentError is evaluated on them on the host.
+// Inside estimatePose the errors of all iterations are evaluated on the device from the loop's pose history
+// (icp_gpu_set_correspondences / icp_gpu_convergence_errors) and stored here; recordAlignmentError(pose) remains
+// for callers that evaluate a pose of their own.
 #pragma once
 #include "Eigen.h"
 
 class ConvergenceMeasure {
 public:
     ConvergenceMeasure() {}
-    ConvergenceMeasure(const std::vector<Vector3f>& sourceCorrespondences, const std::vector<Vector3f>& targetCorrespondences)
-        : m_source(sourceCorrespondences), m_target(targetCorrespondences) {}
+    ConvergenceMeasure(const std::vector<Vector3f>& sourceCorrespondences, const std::vector<Vector3f>& targetCorrespondences, const bool runBenchmark = false)
+        : m_source(sourceCorrespondences), m_target(targetCorrespondences), m_runBenchmark(runBenchmark) {}
+
+    // used by ICPOptimizer::run to hand the correspondences to the device and to store what it computed
+    const std::vector<Vector3f>& sourcePoints() const { return m_source; }
+    const std::vector<Vector3f>& unchangedPoints() const { return m_target; }
+    bool runBenchmark() const { return m_runBenchmark; }
+    void recordDeviceErrors(float rmse, double benchmark) { m_rmse.push_back(rmse); if (m_runBenchmark) m_benchmark.push_back((float)benchmark); }
+    float getFinalErrorRMSE() const { return m_rmse.back(); }                 // ConvergenceMeasure.h:176-178
+    float getFinalErrorBenchmark() const { return m_benchmark.back(); }       // ConvergenceMeasure.h:180-182
+    const std::vector<float>& getBenchmark() const { return m_benchmark; }
 
     void recordAlignmentError(const Matrix4f& pose) {   // ConvergenceMeasure.h:50-78
         int counter = 0; float rmse = 0.f;
@@ -28,5 +39,6 @@ public:
 
 private:
     std::vector<Vector3f> m_source, m_target;
-    std::vector<float> m_rmse;
+    std::vector<float> m_rmse, m_benchmark;
+    bool m_runBenchmark = false;
 };

@@ -113,11 +113,16 @@ protected:
             m_timeMeasure->matchingTime += tm.matching_ms * 1e-3; m_timeMeasure->solverTime += tm.solver_ms * 1e-3;
             m_timeMeasure->convergenceTime += tm.total_ms * 1e-3; m_timeMeasure->indexTime += tm.index_ms * 1e-3;
         }
-        if (calculateRMSE && m_convergenceMeasure)
-            for (int32_t i = 0; i < nIt; ++i) {
-                Matrix4f p; std::memcpy(p.data(), history.data() + 16 * (size_t)i, 16 * sizeof(float));
-                m_convergenceMeasure->recordAlignmentError(p);   // ICPOptimizer.h:629-631
-            }
+        if (calculateRMSE && m_convergenceMeasure && nIt > 0) {
+            // recordAlignmentError after every iteration (ICPOptimizer.h:629-631), evaluated on the device from the pose history
+            const auto& gs = m_convergenceMeasure->sourcePoints(); const auto& gu = m_convergenceMeasure->unchangedPoints();
+            std::vector<float> rmse((size_t)nIt); std::vector<double> bench((size_t)nIt); int32_t nErr = 0;
+            int rc2 = gs.empty() || gs.size() != gu.size() ? ICP_GPU_E_ARG
+                      : icp_gpu_set_correspondences(m_ctx, reinterpret_cast<const float*>(gs.data()), reinterpret_cast<const float*>(gu.data()), (int64_t)gs.size());
+            if (rc2 == ICP_GPU_OK) rc2 = icp_gpu_convergence_errors(m_ctx, rmse.data(), m_convergenceMeasure->runBenchmark() ? bench.data() : nullptr, nIt, &nErr);
+            if (rc2 == ICP_GPU_OK) for (int32_t i = 0; i < nErr; ++i) m_convergenceMeasure->recordDeviceErrors(rmse[(size_t)i], bench[(size_t)i]);
+            else std::cout << "icp_gpu: convergence errors unavailable (" << (gs.empty() ? "no correspondences" : icp_gpu_last_error(m_ctx)) << ")" << std::endl;
+        }
     }
 };
 

@@ -1,8 +1,13 @@
 // PointCloud.h -- the container estimatePose receives (reference: icp-variants/PointCloud.h).
-// Only the storage and its accessors are part of the hot path's boundary; construction from meshes,
-// PCD files and depth maps (PointCloud.h:12-165) is input preparation and stays with the caller.
+// The storage and its accessors are the hot path's boundary.  Of the reference's constructors the depth-map
+// one (PointCloud.h:78-165, the step right before the loop in reconstructRoom) is provided, computed on the
+// device through icp_gpu_cloud_from_depth; construction from meshes and PCD files (PointCloud.h:12-76) stays
+// with the caller (file I/O and PCL).
 #pragma once
 #include "Eigen.h"
+#include "../icp_gpu.h"
+
+typedef unsigned char BYTE;   // VirtualSensor.h:11
 
 class PointCloud {
 public:
@@ -12,6 +17,23 @@ public:
     }
     PointCloud(const std::vector<Vector3f>& points, const std::vector<Vector3f>& normals, const std::vector<Vector4uc>& colors)
         : m_points(points), m_normals(normals), m_colors(colors) {}
+
+    // PointCloud.h:78-165, same signature and defaults.  colorFrame is the RGBX frame (4*width*height bytes) or null.
+    PointCloud(float* depthMap, BYTE* colorFrame, const Matrix3f& depthIntrinsics, const Matrix4f& depthExtrinsics, const unsigned width,
+               const unsigned height, bool keepOriginalSize = false, unsigned downsampleFactor = 1, float maxDistance = 0.1f) {
+        icp_gpu_ctx* ctx = nullptr;
+        if (icp_gpu_create(&ctx, 0) != ICP_GPU_OK) { std::cout << "icp_gpu: no usable CUDA device (there is no CPU fallback)" << std::endl; return; }
+        const size_t cap = downsampleFactor ? ((size_t)width * height + downsampleFactor - 1) / downsampleFactor : 0;
+        m_points.resize(cap); m_normals.resize(cap); m_colors.resize(cap);
+        int64_t n = 0;
+        const int rc = icp_gpu_cloud_from_depth(ctx, depthMap, colorFrame, depthIntrinsics.data(), depthExtrinsics.data(), width, height,
+                                                keepOriginalSize ? 1 : 0, downsampleFactor, maxDistance, ICP_GPU_CLOUD_ONLY,
+                                                cap ? reinterpret_cast<float*>(m_points.data()) : nullptr, cap ? reinterpret_cast<float*>(m_normals.data()) : nullptr,
+                                                cap ? reinterpret_cast<uint8_t*>(m_colors.data()) : nullptr, &n);
+        if (rc != ICP_GPU_OK) { std::cout << "icp_gpu: " << icp_gpu_last_error(ctx) << std::endl; n = 0; }
+        m_points.resize((size_t)n); m_normals.resize((size_t)n); m_colors.resize((size_t)n);
+        icp_gpu_destroy(ctx);
+    }
 
     std::vector<Vector3f>& getPoints() { return m_points; }
     const std::vector<Vector3f>& getPoints() const { return m_points; }

@@ -172,6 +172,29 @@ int icp_gpu_estimate_pose_finish(icp_gpu_ctx* ctx, float pose_out[16], float* po
 
 int icp_gpu_get_stats(icp_gpu_ctx* ctx, icp_gpu_stats* out);
 
+/* ---- either side of the loop -------------------------------------------------------
+ * icp_gpu_cloud_from_depth = PointCloud(float* depthMap, BYTE* colorFrame, const Matrix3f& depthIntrinsics,
+ *   const Matrix4f& depthExtrinsics, width, height, keepOriginalSize, downsampleFactor, maxDistance)
+ *   (PointCloud.h:78-165): back-projection, central-difference normals (MINF where invalid), the
+ *   "point and normal finite" filter, every downsample-th pixel.  depth: width*height floats (MINF =
+ *   invalid, VirtualSensor.h:119-124); rgbx: the RGBX frame (4*width*height bytes, nullable) -- the colour
+ *   of kept pixel i is bytes rgbx[i .. i+3], exactly as PointCloud.h:151-152 indexes it; K: column-major
+ *   3x3 intrinsics; E: column-major 4x4 depth extrinsics (nullable = identity).  role: the cloud becomes the
+ *   context's target (= buildIndex), its source, or is only returned.  xyz_out / nrm_out / rgba_out
+ *   (nullable, host) need room for ceil(width*height / downsample) points; *n_out = points produced. */
+enum { ICP_GPU_CLOUD_TARGET = 0, ICP_GPU_CLOUD_SOURCE = 1, ICP_GPU_CLOUD_ONLY = 2 };
+int icp_gpu_cloud_from_depth(icp_gpu_ctx* ctx, const float* depth, const uint8_t* rgbx, const float K_colmajor[9],
+                             const float E_colmajor[16], uint32_t width, uint32_t height, int keep_original_size,
+                             uint32_t downsample, float max_distance, int role,
+                             float* xyz_out, float* nrm_out, uint8_t* rgba_out, int64_t* n_out);
+/* ConvergenceMeasure(sourcePoints, unchangedPoints) (ConvergenceMeasure.h:32-41): m known correspondences
+ * (source point i of the UNTRANSFORMED source <-> reference point i). */
+int icp_gpu_set_correspondences(icp_gpu_ctx* ctx, const float* src_xyz, const float* ref_xyz, int64_t m);
+/* recordAlignmentError after every iteration of the last finished registration (ICPOptimizer.h:629-631):
+ * rmse_out[k] = rmseAlignmentError(pose after iteration k) (ConvergenceMeasure.h:50-66); benchmark_out[k]
+ * (nullable) = benchmarkError (ConvergenceMeasure.h:104-151).  Evaluated on the device from the pose history. */
+int icp_gpu_convergence_errors(icp_gpu_ctx* ctx, float* rmse_out, double* benchmark_out, int32_t capacity, int32_t* n_out);
+
 /* Point-sharded registration of one very large pair across ranks (one context per rank, each
  * holding the whole target and its shard of the source).  Per iteration:
  *   icp_gpu_iteration_local   -> this rank's partial sums (linear metrics: the normal equations,

@@ -1019,3 +1019,85 @@ float orc_rmse(const float pose[16], const float* src, const float* ref, int64_t
     rmse /= counter;
     return sqrtf(rmse);
 }
+
+/* ------------------------------------------------------------------ input preparation */
+
+/* Inverse of a rigid/affine 4x4 (column-major) in double, rounded to fp32.  The reference calls Eigen's
+ * Matrix4f::inverse() (PointCloud.h:88); its drivers only ever pass the identity (VirtualSensor.h:52), for which
+ * every implementation returns the identity exactly.  For other extrinsics the contract is "inverse in fp64". */
+static void inv4_f64_to_f32(const float M[16], float out[16]) {
+    double a[4][8];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { a[r][c] = M[r + 4 * c]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+    for (int k = 0; k < 4; ++k) {
+        int p = k; for (int i = k + 1; i < 4; ++i) if (fabs(a[i][k]) > fabs(a[p][k])) p = i;
+        if (p != k) for (int j = 0; j < 8; ++j) { const double t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
+        const double d = a[k][k];
+        for (int j = 0; j < 8; ++j) a[k][j] /= d;
+        for (int i = 0; i < 4; ++i) if (i != k) { const double f = a[i][k]; if (f != 0.0) for (int j = 0; j < 8; ++j) a[i][j] -= f * a[k][j]; }
+    }
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[r + 4 * c] = (float)a[r][4 + c];
+}
+
+/* PointCloud(float* depthMap, BYTE* colorFrame, intrinsics, extrinsics, width, height, keepOriginalSize,
+ * downsampleFactor, maxDistance) -- PointCloud.h:78-165.  Returns the number of points written.
+ * colour of kept pixel i = bytes colorFrame[i .. i+3] (the reference indexes the RGBX frame with the PIXEL index,
+ * PointCloud.h:151-152), so color must hold width*height + 3 bytes at least. */
+int64_t orc_cloud_from_depth(const float* depth, const uint8_t* color, const float K[9] /* column-major */, const float E[16] /* nullable */,
+                             uint32_t width, uint32_t height, int keep_original_size, uint32_t downsample, float max_distance,
+                             float* pts_out, float* nrm_out, uint8_t* rgba_out) {
+    const float fovX = K[0], fovY = K[4], cX = K[6], cY = K[7];      /* depthIntrinsics(0,0),(1,1),(0,2),(1,2) */
+    const float half = max_distance / 2.f;
+    float Einv[16];
+    if (E) inv4_f64_to_f32(E, Einv); else mat4_identity(Einv);
+    const int64_t n = (int64_t)width * height;
+    const float minf = -INFINITY;
+    int64_t m = 0;
+    if (downsample == 0) return -1;
+    for (int64_t i = 0; i < n; i += downsample) {
+        const int u = (int)(i % width), v = (int)(i / width);
+        float p[3], nr[3] = {minf, minf, minf};
+        const float d = depth[i];
+        if (d == minf) { p[0] = p[1] = p[2] = minf; }
+        else {
+            const float c[3] = {(u - cX) / fovX * d, (v - cY) / fovY * d, d};
+            for (int r = 0; r < 3; ++r) p[r] = ((Einv[r] * c[0] + Einv[r + 4] * c[1]) + Einv[r + 8] * c[2]) + Einv[r + 12];
+        }
+        if (u >= 1 && v >= 1 && u < (int)width - 1 && v < (int)height - 1) {
+            const float du = 0.5f * (depth[i + 1] - depth[i - 1]);
+            const float dv = 0.5f * (depth[i + width] - depth[i - width]);
+            if (isfinite(du) && isfinite(dv) && !(fabsf(du) > half) && !(fabsf(dv) > half)) {
+                const float a = -du, b = -dv, c1 = 1.0f;
+                const float nn = sqrtf((a * a + b * b) + c1 * c1);
+                nr[0] = a / nn; nr[1] = b / nn; nr[2] = c1 / nn;
+            }
+        }
+        if (keep_original_size || (finite3(p) && finite3(nr))) {
+            for (int r = 0; r < 3; ++r) { pts_out[3 * m + r] = p[r]; nrm_out[3 * m + r] = nr[r]; }
+            if (rgba_out) for (int r = 0; r < 4; ++r) rgba_out[4 * m + r] = color ? color[i + r] : 0;
+            ++m;
+        }
+    }
+    return m;
+}
+
+/* ConvergenceMeasure::benchmarkError / calculate_error (ConvergenceMeasure.h:104-151): mean over i of
+ * |T s_i - u_i| / |T s_i - centroid(T s)|, pcl::euclideanDistance in fp32, centroid accumulated in double
+ * (pcl::compute3DCentroid into Eigen::Vector4d) and narrowed to float (pcl::PointXYZ), the sum in double. */
+double orc_benchmark_error(const float pose[16], const float* src, const float* ref, int64_t n) {
+    float* t = (float*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(float));
+    orc_transform_points(pose, src, n, t);
+    double c[3] = {0, 0, 0}; int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) if (finite3(t + 3 * i)) { c[0] += t[3 * i]; c[1] += t[3 * i + 1]; c[2] += t[3 * i + 2]; ++cnt; }
+    if (cnt) { c[0] /= (double)cnt; c[1] /= (double)cnt; c[2] /= (double)cnt; }
+    const float cf[3] = {(float)c[0], (float)c[1], (float)c[2]};
+    double err = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* a = t + 3 * i; const float* b = ref + 3 * i;
+        const float ex = a[0] - cf[0], ey = a[1] - cf[1], ez = a[2] - cf[2];
+        const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        const double centroid_distance = sqrtf((ex * ex + ey * ey) + ez * ez);
+        err += sqrtf((dx * dx + dy * dy) + dz * dz) / centroid_distance;
+    }
+    free(t);
+    return n ? err / (double)n : 0.0;
+}

@@ -131,6 +131,14 @@ int orc_estimate_pose(const orc_config* cfg,
 
 /* ConvergenceMeasure.h:50-66 */
 float orc_rmse(const float pose[16], const float* src, const float* ref, int64_t n);
+/* ConvergenceMeasure.h:104-151 (Fontana benchmark error) */
+double orc_benchmark_error(const float pose[16], const float* src, const float* ref, int64_t n);
+
+/* PointCloud.h:78-165: depth map (+ RGBX frame) -> points, central-difference normals, colours; returns the count.
+ * K column-major 3x3, E (nullable = identity) column-major 4x4 depth extrinsics. */
+int64_t orc_cloud_from_depth(const float* depth, const uint8_t* color, const float K[9], const float E[16],
+                             uint32_t width, uint32_t height, int keep_original_size, uint32_t downsample, float max_distance,
+                             float* pts_out, float* nrm_out, uint8_t* rgba_out);
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

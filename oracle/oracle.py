@@ -46,6 +46,8 @@ def lib():
         _lib.orc_kdtree_build.restype = C.c_void_p
         _lib.orc_mt_canonical.restype = C.c_double
         _lib.orc_coarse_indices.restype = C.c_int64
+        _lib.orc_cloud_from_depth.restype = C.c_int64
+        _lib.orc_benchmark_error.restype = C.c_double
     return _lib
 
 
@@ -246,6 +248,24 @@ def estimate_pose(cfg: Config, src, src_n, src_c, tgt, tgt_n, tgt_c, init_pose=N
 def rmse(pose, src, ref):
     src, ref = _f32(src), _f32(ref)
     return float(lib().orc_rmse(_p(_pose(pose)), _p(src), _p(ref), C.c_int64(len(src))))
+
+
+def benchmark_error(pose, src, ref):
+    src, ref = _f32(src), _f32(ref)
+    return float(lib().orc_benchmark_error(_p(_pose(pose)), _p(src), _p(ref), C.c_int64(len(src))))
+
+
+def cloud_from_depth(depth, rgbx, fx, fy, cx, cy, extrinsics=None, keep_original_size=False, downsample=1, max_distance=0.1):
+    """PointCloud(depthMap, colorFrame, ...) (PointCloud.h:78-165).  rgbx: flat uint8 RGBX frame (>= w*h + 3 bytes) or None."""
+    depth = np.ascontiguousarray(depth, np.float32); h, w = depth.shape
+    col = None if rgbx is None else np.ascontiguousarray(rgbx, np.uint8).reshape(-1)
+    assert col is None or col.size >= h * w + 3
+    K = np.ascontiguousarray(np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32).T.reshape(9))
+    E = None if extrinsics is None else _pose(extrinsics)
+    po = np.empty((h * w, 3), np.float32); no = np.empty((h * w, 3), np.float32); co = np.zeros((h * w, 4), np.uint8)
+    n = lib().orc_cloud_from_depth(_p(depth), _p(col), _p(K), _p(E), C.c_uint32(w), C.c_uint32(h), C.c_int(int(keep_original_size)),
+                                   C.c_uint32(downsample), C.c_float(max_distance), _p(po), _p(no), _p(co))
+    return po[:n].copy(), no[:n].copy(), co[:n].copy()
 
 
 def coarsest_stride(n):

@@ -66,3 +66,10 @@ def test_cpp_driver_matches_python_binding(bunny, linear, metric):
         c.set_source(src.points, src.normals, src.colors)
         pose_py, _, _ = c.estimate_pose()
     assert np.allclose(pose_cpp, pose_py, rtol=0, atol=1e-7)
+    # ConvergenceMeasure filled from the device (icp_gpu_convergence_errors): main.cpp:105-120's 4 correspondences
+    from oracle import oracle as orc
+    _, _, gs, gt = bunny
+    f = [l for l in r.stdout.splitlines() if l.startswith("RMSE")][0].split()
+    assert int(f[5]) == 20
+    assert float(f[1]) == pytest.approx(orc.rmse(pose_py, src.points[gs], tgt.points[gt]), rel=1e-6)
+    assert float(f[3]) == pytest.approx(orc.benchmark_error(pose_py, src.points[gs], tgt.points[gt]), rel=1e-6)

@@ -1,0 +1,146 @@
+"""GPU parity of the steps either side of the loop, through the C ABI:
+depth map -> cloud (PointCloud.h:78-165) bit-exact against the oracle (itself pinned against the reference's
+constructor in tests/test_oracle_vs_reference.py), and the per-iteration convergence metrics
+(ConvergenceMeasure.h:50-66, :104-151) evaluated on the device."""
+import numpy as np
+import pytest
+
+from icp_variants_b200 import capi, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _frame(w, h, seed):
+    fx = fy = 525.0 * w / 640; cx, cy = (319.5 + 0.5) * w / 640 - 0.5, (239.5 + 0.5) * w / 640 - 0.5
+    depth, _ = synth.render_depth(synth.make_room(seed), np.array([3.0, 5.0, 1.4]), 10.0, 0.0, w, h, fx, fy, cx, cy, seed=seed)
+    rgbx = np.random.default_rng(seed).integers(0, 256, 4 * h * w, dtype=np.uint8)
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    return depth, rgbx, K
+
+
+@pytest.mark.parametrize("w,h", [(96, 72), (640, 480), (33, 17)])
+def test_cloud_from_depth_bit_exact(ctx, w, h):
+    depth, rgbx, K = _frame(w, h, 3)
+    E = synth.make_pose([0.1, -0.2, 0.05], [5, -3, 10])
+    for keep, ds, md, ext in ((True, 1, 0.1, None), (False, 1, 0.1, None), (False, 8, 0.1, None), (False, 3, 0.05, None), (False, 1, 0.1, E), (True, 5, 0.1, E)):
+        po, no, co = orc.cloud_from_depth(depth, rgbx, K[0, 0], K[1, 1], K[0, 2], K[1, 2], ext, keep, ds, md)
+        pg, ng, cg = ctx.cloud_from_depth(depth, rgbx, K, ext, keep, ds, md)
+        assert pg.shape == po.shape, (keep, ds, md)
+        assert np.array_equal(pg, po, equal_nan=True) and np.array_equal(ng, no, equal_nan=True) and np.array_equal(cg, co)
+    pg, ng, cg = ctx.cloud_from_depth(depth, None, K, None, True, 1, 0.1)
+    assert (cg == 0).all() and len(pg) == w * h
+
+
+def test_cloud_from_depth_empty_and_errors(ctx):
+    depth = np.full((8, 8), -np.inf, np.float32)
+    K = np.eye(3, dtype=np.float32)
+    p, n, c = ctx.cloud_from_depth(depth, None, K, None, False, 1, 0.1)
+    assert len(p) == 0
+    p, n, c = ctx.cloud_from_depth(depth, None, K, None, True, 1, 0.1)
+    assert len(p) == 64 and np.isneginf(p).all() and np.isneginf(n).all()
+    with pytest.raises(capi.IcpGpuError):
+        ctx.cloud_from_depth(depth, None, K, np.zeros((4, 4), np.float32), False, 1, 0.1)      # singular extrinsics
+    with pytest.raises(capi.IcpGpuError):
+        ctx.cloud_from_depth(depth, None, K, None, False, 0, 0.1)                               # downsample 0
+
+
+def test_projective_registration_from_depth_maps_equals_host_clouds(ctx):
+    """reconstructRoom's path (main.cpp:183-341): both frames go up as depth maps and become target / source on the device."""
+    w, h = 160, 120
+    src, tgt, K, gt = synth.tum_pair(seed=9, width=w, height=h)
+    room = synth.make_room(9)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    pos0 = np.array([3.0, 5.0, 1.4]); pos1 = pos0 + 10 * np.array([0.0015, 0.0006, 0.0002])
+    d0, _ = synth.render_depth(room, pos0, 10.0, 0.0, w, h, fx, fy, cx, cy, seed=9, dropout=0.15)
+    d1, _ = synth.render_depth(room, pos1, 11.0, 0.0, w, h, fx, fy, cx, cy, seed=10, dropout=0.15)
+    c = capi.default_config()
+    c.metric, c.matching, c.weighting, c.n_iterations, c.max_distance_sq = 2, 1, 2, 8, 0.1
+    ctx.set_config(c); ctx.set_camera(K, w, h)
+    ctx.set_target(tgt.points, tgt.normals, tgt.colors); ctx.set_source(src.points, src.normals, src.colors)
+    pose_a, hist_a, n_a = ctx.estimate_pose()
+    assert ctx.cloud_from_depth(d0, None, K, None, True, 1, 0.1, role=0, download=False) == w * h
+    assert ctx.cloud_from_depth(d1, None, K, None, True, 1, 0.1, role=1, download=False) == w * h
+    pose_b, hist_b, n_b = ctx.estimate_pose()
+    assert n_a == n_b == 8 and np.array_equal(pose_a, pose_b) and np.array_equal(hist_a, hist_b)
+
+
+@pytest.mark.parametrize("minimizer,metric", [(0, 1), (1, 2)])
+def test_convergence_errors_bunny(ctx, bunny, minimizer, metric):
+    src, tgt, gs, gt = bunny
+    c = capi.default_config()
+    c.metric, c.minimizer, c.n_iterations, c.max_distance_sq = metric, minimizer, 12, 0.0003
+    ctx.set_config(c)
+    ctx.set_target(tgt.points, tgt.normals, tgt.colors); ctx.set_source(src.points, src.normals, src.colors)
+    ctx.set_correspondences(src.points[gs], tgt.points[gt])
+    pose, hist, n_it = ctx.estimate_pose()
+    rmse, bench = ctx.convergence_errors(benchmark=True)
+    assert len(rmse) == len(bench) == n_it == 12
+    for k in range(n_it):
+        # the reference accumulates the 4 squared distances in fp32, the device in fp64: 1 ulp of the float result
+        assert rmse[k] == pytest.approx(orc.rmse(hist[k], src.points[gs], tgt.points[gt]), rel=3e-7)
+        assert bench[k] == pytest.approx(orc.benchmark_error(hist[k], src.points[gs], tgt.points[gt]), rel=1e-12)
+    assert rmse[-1] < rmse[0]
+
+
+def test_convergence_errors_all_points(ctx, small_eth_pair):
+    """ETH / TUM runs use every point as a known correspondence (experiment.cpp): M = N, with non-finite points skipped."""
+    src, tgt, gt_pose = small_eth_pair
+    ref = orc.transform_points(gt_pose, src.points)
+    s = src.points.copy(); s[17, 1] = np.nan; s[4000, 0] = -np.inf
+    c = capi.default_config()
+    c.metric, c.n_iterations, c.max_distance_sq = 1, 6, 0.5
+    ctx.set_config(c)
+    ctx.set_target(tgt.points, tgt.normals, tgt.colors); ctx.set_source(src.points, src.normals, src.colors)
+    ctx.set_correspondences(s, ref)
+    pose, hist, n_it = ctx.estimate_pose()
+    rmse, _ = ctx.convergence_errors()
+    assert len(rmse) == n_it == 6
+    for k in range(n_it):
+        assert rmse[k] == pytest.approx(orc.rmse(hist[k], s, ref), rel=2e-5)      # fp32 sequential sum of ~10^4 terms in the reference
+    ok = np.isfinite(s).all(1)
+    rmse2, bench2 = None, None
+    ctx.set_correspondences(s[ok], ref[ok])
+    rmse2, bench2 = ctx.convergence_errors(benchmark=True)
+    for k in range(n_it):
+        assert bench2[k] == pytest.approx(orc.benchmark_error(hist[k], s[ok], ref[ok]), rel=1e-9)
+
+
+def test_convergence_errors_need_correspondences(bunny):
+    src, tgt, _, _ = bunny
+    with capi.Context(0) as c:
+        c.set_target(tgt.points, tgt.normals, tgt.colors); c.set_source(src.points, src.normals, src.colors)
+        c.estimate_pose()
+        with pytest.raises(capi.IcpGpuError):
+            c.convergence_errors()
+
+
+def test_optimizer_mirror_fills_convergence_measure_from_the_device(bunny):
+    """The reference-style driver flow (main.cpp:43-181) through the Python mirror of the operator API."""
+    from icp_variants_b200.optimizer import ConvergenceMeasure, LinearICPOptimizer, TimeMeasure
+    src, tgt, gs, gt = bunny
+    opt = LinearICPOptimizer(device=0)
+    opt.setMatchingMethod(0); opt.setMatchingMaxDistance(0.0003); opt.setMetric(2); opt.setNbOfIterations(20)
+    cm = ConvergenceMeasure(src.points[gs], tgt.points[gt], runBenchmark=True); tm = TimeMeasure()
+    opt.setConvergenceMeasure(cm); opt.setTimeMeasure(tm)
+    pose = opt.estimatePose(src, tgt, np.eye(4, dtype=np.float32))
+    assert len(cm.rmseErrors) == len(cm.benchmarkErrors) == 20
+    assert cm.rmseErrors[-1] == pytest.approx(orc.rmse(pose, src.points[gs], tgt.points[gt]), rel=1e-6)
+    assert 1.5e-4 < cm.rmseErrors[-1] < 2.5e-4 and tm.nIterations == 20
+
+
+def test_optimizer_mirror_depth_frames(ctx):
+    from icp_variants_b200.optimizer import LinearICPOptimizer
+    w, h = 96, 72
+    depth, rgbx, K = _frame(w, h, 5)
+    opt = LinearICPOptimizer(device=0)
+    assert opt.setTargetFromDepth(depth, rgbx, K, None, True) == w * h
+    n = opt.setSourceFromDepth(depth, rgbx, K, None, False, 2)
+    assert n == len(orc.cloud_from_depth(depth, rgbx, K[0, 0], K[1, 1], K[0, 2], K[1, 2], None, False, 2, 0.1)[0])

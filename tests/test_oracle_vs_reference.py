@@ -345,3 +345,32 @@ def test_projective_symmetric_registration_tum_shaped():
         else:
             assert rc == 0 and n == len(hist)
             assert rot_err(pr, po) < ROT_TOL and np.abs(pr[:3, 3] - po[:3, 3]).max() < TRANS_TOL
+
+
+def test_oracle_cloud_from_depth_equals_reference_constructor():
+    """PointCloud.h:78-165: the C oracle against the reference's own constructor."""
+    from icp_variants_b200 import synth
+    w, h = 96, 72
+    fx = fy = 525.0 * w / 640; cx, cy = w / 2 - 0.5, h / 2 - 0.5
+    depth, _ = synth.render_depth(synth.make_room(3), np.array([3.0, 5.0, 1.4]), 10.0, 0.0, w, h, fx, fy, cx, cy, seed=3)
+    rgbx = np.random.default_rng(0).integers(0, 256, 4 * h * w, dtype=np.uint8)
+    for keep, ds, md in ((True, 1, 0.1), (False, 1, 0.1), (False, 8, 0.1), (False, 3, 0.05)):
+        pr, nr, cr = R.cloud_from_depth(depth, rgbx, fx, fy, cx, cy, None, keep, ds, md)
+        po, no, co = O.cloud_from_depth(depth, rgbx, fx, fy, cx, cy, None, keep, ds, md)
+        assert pr.shape == po.shape and len(pr) > 20, (keep, ds, md, len(pr))
+        assert np.array_equal(pr, po) and np.array_equal(nr, no) and np.array_equal(cr, co)
+    # non-identity depth extrinsics (never used by the reference's drivers): the 4x4 inverse is Eigen's in the reference
+    # and an fp64 elimination in the oracle / product, so points agree to rounding only
+    E = _pose(4, 0.3, 20.0)
+    pr, nr, cr = R.cloud_from_depth(depth, rgbx, fx, fy, cx, cy, E, False, 1, 0.1)
+    po, no, co = O.cloud_from_depth(depth, rgbx, fx, fy, cx, cy, E, False, 1, 0.1)
+    assert pr.shape == po.shape and np.allclose(pr, po, atol=2e-6) and np.array_equal(nr, no) and np.array_equal(cr, co)
+
+
+def test_benchmark_error_equals_reference(bunny, small_eth_pair):
+    src, tgt, gs, gt = bunny
+    for s in range(3):
+        pose = _pose(s)
+        assert R.benchmark_error(pose, src.points[gs], tgt.points[gt]) == O.benchmark_error(pose, src.points[gs], tgt.points[gt])
+    a, b = small_eth_pair[0].points[:3000], small_eth_pair[1].points[:3000]
+    assert R.benchmark_error(_pose(1), a, b) == pytest.approx(O.benchmark_error(_pose(1), a, b), rel=1e-9)
