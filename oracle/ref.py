@@ -229,5 +229,10 @@ def estimate_pose(minimizer, metric, src, src_n, src_c, tgt, tgt_n, tgt_c, gt_sr
     return n, _unpose(pose), hist[:max(n, 0)].copy()
 
 
+def set_flann_exhaustive(on: bool):
+    """Answer the FLANN stand-in's searches by the literal O(N*M) scan instead of its exact kd-tree (same results)."""
+    lib().ref_set_flann_exhaustive(C.c_int(int(on)))
+
+
 def describe():
     return lib().ref_describe().decode()

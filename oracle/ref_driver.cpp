@@ -271,6 +271,9 @@ int ref_estimate_pose(const ref_config* cfg,
     } catch (const ref_assert_failure&) { return -2; }
 }
 
+// test hook: answer FLANN searches by the literal O(N*M) scan instead of the exact kd-tree (identical results)
+void ref_set_flann_exhaustive(int on) { flann::exhaustive() = on != 0; }
+
 const char* ref_describe(void) {
     return "reference headers from /root/reference/icp-variants compiled in place against oracle/ref_shim stand-ins "
            "(Eigen/FLANN/Ceres/PCL are not installed): pins the reference's own code, not the third-party numerics";

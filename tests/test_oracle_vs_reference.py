@@ -82,6 +82,21 @@ def test_knn3_indices_bit_exact(quant):
         assert (idx >= 0).any() and (idx < 0).any() or max_d2 == 10.0
 
 
+def test_flann_stand_in_kdtree_equals_exhaustive_scan():
+    tgt, _, tc = _cloud(4000, 21, quant=16, nonfinite=4)
+    qry, _, qc = _cloud(3000, 22, quant=16, nonfinite=4)
+    try:
+        for colours in (False, True):
+            a = (tc, qc) if colours else (None, None)
+            R.set_flann_exhaustive(True)
+            i0, w0 = R.knn_flann(tgt, qry, 0.05, *a)
+            R.set_flann_exhaustive(False)
+            i1, w1 = R.knn_flann(tgt, qry, 0.05, *a)
+            assert np.array_equal(i0, i1) and np.array_equal(w0, w1) and (i0 >= 0).sum() > 300
+    finally:
+        R.set_flann_exhaustive(False)
+
+
 def test_knn6_colour_indices_bit_exact():
     tgt, _, tc = _cloud(3000, 4, quant=8)
     qry, _, qc = _cloud(2000, 5, quant=8)
