@@ -60,6 +60,20 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu --set full capture
+    (profiles/r1_ncu_traffic.json, produced by profiles/final_measure.sh); None when the summary is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            k = json.load(f)["kernels"]
+        for name, v in k.items():
+            if kernel_substr in name:
+                return v["dram_bytes_read"] + v["dram_bytes_write"]
+    except Exception:   # noqa: BLE001
+        pass
+    return None
+
+
 def make_pair(pair_index=0, n_sweeps=344, n_beams=1077):
     """Synthetic ETH-shaped pair; cached under /tmp because k=5 PCA normals of 370k points take seconds."""
     from icp_variants_b200 import synth
@@ -320,6 +334,8 @@ def main():
     st_t = ctx.stats()
     st = st_t
     match_ms = tm.matching_ms / N_ITER
+    prep_ms = tm.search_prep_ms / N_ITER
+    walk_ms = max(match_ms - prep_ms, 1e-6)          # knn_bvh_kernel alone (the dominant kernel)
     solve_ms = tm.solver_ms / N_ITER
 
     if rank == 0:
@@ -329,7 +345,7 @@ def main():
         # algorithmic bytes of the fused match kernel per query: source point 12 + source normal 12 +
         # matched target point 12 + target normal 12 = 48 B
         alg_bytes = 48.0 * ns
-        achieved = alg_bytes / (match_ms * 1e-3) / 1e9
+        achieved = alg_bytes / (walk_ms * 1e-3) / 1e9
         evals_per_launch = st_t.n_distance_evals / N_ITER
         line = {
             "metric": "icp_registrations_per_s", "value": value, "unit": "reg/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -343,14 +359,14 @@ def main():
                     "h2d_bytes_per_step": int((ns + nt) * 28 + 64 + 32 * N_ITER), "d2h_bytes_per_step": int(64 + 16 * 4 * N_ITER + 1024)},
             "gpu_launches": launches,
             "roofline": {"kernel": "knn_bvh_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": match_ms,
+                         "frac": achieved / peak, "traffic": ncu_traffic("knn_bvh_kernel"), "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": walk_ms,
                          "note": "issue-bound tree search over L2-resident clouds; see roofline_fp32"},
             "roofline_fp32": {"kernel": "knn_bvh_kernel<false>", "distance_evals_per_launch": evals_per_launch,
                               "gevals_per_s": evals_per_launch / (match_ms * 1e-3) / 1e9, "flop_per_eval": 8,
-                              "tflops": evals_per_launch * 8 / (match_ms * 1e-3) / 1e12, "nodes_per_launch": st_t.n_nodes_visited / N_ITER,
+                              "tflops": evals_per_launch * 8 / (match_ms * 1e-3) / 1e12, "kernels": "knn_prep_kernel (fast path) + knn_bvh_kernel (walk)", "nodes_per_launch": st_t.n_nodes_visited / N_ITER,
                               "matched_per_launch": st_t.n_matched / N_ITER},
-            "stage_ms_per_iteration": {"match": match_ms, "reduce_solve": solve_ms, "index_build": tm.index_ms},
+            "stage_ms_per_iteration": {"match": match_ms, "match_prep_fast_path": prep_ms, "match_tree_walk": walk_ms, "reduce_solve": solve_ms, "index_build": tm.index_ms},
             "clocks": clocks,
             "pose_checksum": float(np.abs(pose).sum()),
         }

@@ -41,7 +41,8 @@ class Config(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("selection_ms", C.c_double), ("matching_ms", C.c_double), ("weighting_ms", C.c_double),
                 ("rejection_ms", C.c_double), ("solver_ms", C.c_double), ("index_ms", C.c_double), ("total_ms", C.c_double),
-                ("n_iterations", C.c_int32), ("n_match_launches", C.c_int32), ("n_solver_launches", C.c_int32)]
+                ("n_iterations", C.c_int32), ("n_match_launches", C.c_int32), ("n_solver_launches", C.c_int32), ("reserved_", C.c_int32),
+                ("search_prep_ms", C.c_double)]
 
 
 class Stats(C.Structure):

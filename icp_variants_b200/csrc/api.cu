@@ -437,7 +437,7 @@ int enqueue_iterations(icp_gpu_ctx* ctx, const Plan& plan, int algo, std::vector
     const int nb = ctx->n_reduce_blocks;
     for (int i = 0; i < plan.n_iters; ++i) {
         if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * i], ctx->stream));
-        CU(icp_launch_match(ma, algo, ctx->n_sms, ctx->stream, &launches));
+        CU(icp_launch_match(ma, algo, ctx->n_sms, ctx->stream, &launches, (ev_marks && algo == 0) ? (*ev_marks)[2 * plan.n_iters + 1 + i] : nullptr));
         if (ev_marks) CU(cudaEventRecord((*ev_marks)[2 * i + 1], ctx->stream));
         if (ctx->cfg.minimizer == ICP_GPU_MIN_LM) CU(icp_launch_lm(ra, nb, ctx->cfg.lm_max_iterations, ctx->stream, &launches));
         else CU(icp_launch_reduce(ra, nb, ctx->stream, &launches));
@@ -484,7 +484,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     std::vector<cudaEvent_t> marks;
     if (timings) {
         memset(timings, 0, sizeof(*timings));
-        marks.resize((size_t)2 * plan.n_iters + 1);
+        marks.resize((size_t)3 * plan.n_iters + 1);   // 2 per iteration + end, then one per iteration between the two search kernels
         for (auto& e : marks) CU(cudaEventCreate(&e));
         rc = enqueue_iterations(ctx, plan, algo, &marks);
     } else if (ctx->cfg.use_graph && plan.n_iters > 0) {
@@ -530,6 +530,8 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
             cudaEventElapsedTime(&a, marks[2 * i], marks[2 * i + 1]);
             cudaEventElapsedTime(&b, marks[2 * i + 1], marks[2 * i + 2]);
             timings->matching_ms += a; timings->solver_ms += b;
+            float c = 0.f;
+            if (algo == 0 && cudaEventElapsedTime(&c, marks[2 * i], marks[2 * plan.n_iters + 1 + i]) == cudaSuccess) timings->search_prep_ms += c; else cudaGetLastError();
         }
         float tot = 0.f;
         if (plan.n_iters > 0) cudaEventElapsedTime(&tot, marks[0], marks[2 * plan.n_iters]);

@@ -197,7 +197,7 @@ cudaError_t icp_launch_depth_cloud(const float* depth, const unsigned char* colo
 int icp_metrics_blocks(long long m, int n_sms);
 cudaError_t icp_launch_metrics(const float* src, const float* ref, long long m, const float* history, int n_iters, int n_blocks, double* partial,
                                float* rmse, float* centroid, double* bench, cudaStream_t s, int* n_launches);
-cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches);
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep = nullptr);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);
 // one phase of the point-sharded iteration: the summed row is left in state->shard_partials

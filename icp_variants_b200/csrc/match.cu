@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
     flush_stats(a, nq, nm, ev, nd);
 }
 
-cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches) {
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep) {
     if (a.n_src <= 0) return cudaSuccess;
     const int T = ICP_MATCH_THREADS;
     int launches = 0;
@@ -604,6 +604,7 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
     } else {
         if (a.color_icp) knn_prep_kernel<true><<<(a.n_src + 255) / 256, 256, 0, s>>>(a); else knn_prep_kernel<false><<<(a.n_src + 255) / 256, 256, 0, s>>>(a);
         ++launches;
+        if (after_prep) cudaEventRecord(after_prep, s);
         int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
         if (nb > 64 * n_sms) nb = 64 * n_sms;
         if (a.color_icp) knn_bvh_kernel<true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false><<<nb, BVH_WARPS * 32, 0, s>>>(a);

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ICP_GPU_ABI_VERSION 1
+#define ICP_GPU_ABI_VERSION 2
 
 enum {
     ICP_GPU_OK = 0,
@@ -104,6 +104,9 @@ typedef struct icp_gpu_timings {
     double total_ms;       /* TimeMeasure::convergenceTime                                         */
     int32_t n_iterations;  /* iterations executed                                                   */
     int32_t n_match_launches, n_solver_launches;
+    int32_t reserved_;
+    double search_prep_ms; /* part of matching_ms spent in the thread-per-query kernel (transform + fast-path search);
+                              the rest is the warp-per-query tree walk                              */
 } icp_gpu_timings;
 
 /* Work counters of the last estimate_pose / query_matches (for roofline accounting). */
