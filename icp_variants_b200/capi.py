@@ -107,6 +107,7 @@ def lib():
             "icp_gpu_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
             "icp_gpu_cloud_from_depth": (C.c_int, [vp, pf, pf, pf, pf, u32, u32, C.c_int, u32, C.c_float, C.c_int, pf, pf, pf, C.POINTER(i64)]),
             "icp_gpu_set_correspondences": (C.c_int, [vp, pf, pf, i64]),
+            "icp_gpu_set_correspondences_pose": (C.c_int, [vp, pf]),
             "icp_gpu_convergence_errors": (C.c_int, [vp, pf, pf, i32, C.POINTER(i32)]),
             "icp_gpu_iteration_phases": (C.c_int, [vp]),
             "icp_gpu_iteration_begin": (C.c_int, [vp, pf]),
@@ -299,6 +300,10 @@ class Context:
         s = _f32(src_xyz, 3); r = _f32(ref_xyz, 3)
         assert len(s) == len(r)
         self._check(lib().icp_gpu_set_correspondences(self._h, _ptr(s), _ptr(r), len(s)))
+
+    def set_correspondences_pose(self, gt_pose):
+        """Every point of the resident source against itself under a ground-truth pose (main.cpp:300-307)."""
+        self._check(lib().icp_gpu_set_correspondences_pose(self._h, _ptr(pose_to_c(gt_pose))))
 
     def convergence_errors(self, benchmark: bool = False):
         """(rmse per iteration, benchmark error per iteration | None) of the last registration, computed on the device."""

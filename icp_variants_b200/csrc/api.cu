@@ -768,6 +768,24 @@ int icp_gpu_set_correspondences(icp_gpu_ctx* ctx, const float* src_xyz, const fl
     return ICP_GPU_OK;
 }
 
+// The same with the correspondences reconstructRoom builds (main.cpp:300-307): every point of the resident source
+// against itself under a ground-truth pose, gtTargetPoints = transformPoints(source.getPoints(), gt_pose).
+int icp_gpu_set_correspondences_pose(icp_gpu_ctx* ctx, const float gt_pose[16]) {
+    if (!ctx || !gt_pose) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
+    if (ctx->n_src <= 0 || !ctx->src_raw_pts.p) return fail(ctx, ICP_GPU_E_STATE, "no source cloud set");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    ctx->n_gt = 0;
+    const size_t m = (size_t)ctx->n_src;
+    if (ensure(ctx, ctx->gt_src, m * 12) || ensure(ctx, ctx->gt_ref, m * 12) || ensure(ctx, ctx->met_out, 256)) return ICP_GPU_E_CUDA;
+    CU(cudaMemcpyAsync(ctx->met_out.p, gt_pose, 64, cudaMemcpyHostToDevice, ctx->stream));
+    CU(icp_launch_gt_from_source((const float4*)ctx->src_raw_pts.p, (long long)m, (const float*)ctx->met_out.p, (float*)ctx->gt_src.p, (float*)ctx->gt_ref.p, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+    CU(cudaStreamSynchronize(ctx->stream));     // gt_pose is the caller's (pageable) memory; met_out is reused by icp_gpu_convergence_errors
+    ctx->n_gt = (long long)m;
+    return ICP_GPU_OK;
+}
+
 // recordAlignmentError after every iteration of the last registration (ICPOptimizer.h:629-631), evaluated on the device
 // from the per-iteration poses the loop left there.
 int icp_gpu_convergence_errors(icp_gpu_ctx* ctx, float* rmse_out, double* benchmark_out, int32_t capacity, int32_t* n_out) {

@@ -194,6 +194,7 @@ struct DepthArgs {
 cudaError_t icp_launch_depth_cloud(const float* depth, const unsigned char* color, const DepthArgs& a, float* pts_tmp, float* nrm_tmp,
                                    unsigned char* rgba_tmp, unsigned int* flag, unsigned int* block_count, unsigned int* total,
                                    float* pts_out, float* nrm_out, unsigned char* rgba_out, cudaStream_t s, int* n_launches);
+cudaError_t icp_launch_gt_from_source(const float4* src_raw, long long n, const float* pose16_dev, float* gt_src, float* gt_ref, cudaStream_t s);
 int icp_metrics_blocks(long long m, int n_sms);
 cudaError_t icp_launch_metrics(const float* src, const float* ref, long long m, const float* history, int n_iters, int n_blocks, double* partial,
                                float* rmse, float* centroid, double* bench, cudaStream_t s, int* n_launches);

@@ -118,6 +118,27 @@ cudaError_t icp_launch_depth_cloud(const float* depth, const unsigned char* colo
 }
 
 // ---------------------------------------------------------------------------- convergence metrics
+// The correspondences reconstructRoom uses (main.cpp:300-307): every source point against itself under a ground-truth
+// pose, gtTargetPoints = transformPoints(source.getPoints(), currentToZeroCoordinates), built from the resident source.
+__global__ void __launch_bounds__(256) gt_from_source_kernel(const float4* __restrict__ src_raw, long long n, const float* __restrict__ pose16,
+                                                             float* __restrict__ gt_src, float* __restrict__ gt_ref) {
+    __shared__ float P[16];
+    if (threadIdx.x < 16) P[threadIdx.x] = pose16[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(&src_raw[i]);
+    float x, y, z;
+    xform_point(P, p.x, p.y, p.z, x, y, z);
+    gt_src[3 * i] = p.x; gt_src[3 * i + 1] = p.y; gt_src[3 * i + 2] = p.z;
+    gt_ref[3 * i] = x; gt_ref[3 * i + 1] = y; gt_ref[3 * i + 2] = z;
+}
+cudaError_t icp_launch_gt_from_source(const float4* src_raw, long long n, const float* pose16_dev, float* gt_src, float* gt_ref, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    gt_from_source_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(src_raw, n, pose16_dev, gt_src, gt_ref);
+    return cudaGetLastError();
+}
+
 // grid (blocks, iterations).  partial[(it * blocks + b) * 6 + ..] = {sum |T s - u|^2, pairs, sum x, sum y, sum z, finite T s}
 #define MET_THREADS 256
 __device__ __forceinline__ double block_sum(double v, double* sm) {

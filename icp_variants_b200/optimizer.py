@@ -51,6 +51,7 @@ class ConvergenceMeasure:
     targetCorrespondences: np.ndarray | None = None   # [M,3]
     rmseErrors: list = field(default_factory=list)
     runBenchmark: bool = False                        # ConvergenceMeasure.h:32: also the Fontana benchmark error (:104-151)
+    groundTruthPose: np.ndarray | None = None         # instead of the arrays: every source point under this pose (main.cpp:300-307)
     benchmarkErrors: list = field(default_factory=list)
 
     def recordAlignmentError(self, pose):
@@ -231,10 +232,13 @@ class ICPOptimizer:
             tm.convergenceTime += t.total_ms * 1e-3
             tm.indexTime += t.index_ms * 1e-3
             tm.nIterations = n_it
-        if want_hist and n_it > 0 and self.m_convergenceMeasure.sourceCorrespondences is not None:
+        cm = self.m_convergenceMeasure
+        if want_hist and n_it > 0 and (cm.sourceCorrespondences is not None or cm.groundTruthPose is not None):
             # recordAlignmentError after every iteration (ICPOptimizer.h:629-631), evaluated on the device from the pose history
-            cm = self.m_convergenceMeasure
-            self._ctx.set_correspondences(cm.sourceCorrespondences, cm.targetCorrespondences)
+            if cm.groundTruthPose is not None:
+                self._ctx.set_correspondences_pose(cm.groundTruthPose)
+            else:
+                self._ctx.set_correspondences(cm.sourceCorrespondences, cm.targetCorrespondences)
             rmse, bench = self._ctx.convergence_errors(benchmark=cm.runBenchmark)
             cm.rmseErrors.extend(float(r) for r in rmse)
             if cm.runBenchmark:

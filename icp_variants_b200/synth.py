@@ -295,3 +295,23 @@ def tum_pair(seed=1234, frame_gap=10, width=TUM_W, height=TUM_H, dropout=0.15):
     t1 = np.eye(4); t1[:3, :3] = r1; t1[:3, 3] = pos1
     gt = np.linalg.inv(t0) @ t1
     return src, tgt, k, gt.astype(np.float32)
+
+
+def tum_sequence(n_frames=11, seed=1234, frame_step=10, width=TUM_W, height=TUM_H, dropout=0.15):
+    """A TUM-freiburg1-shaped RGB-D sequence as reconstructRoom replays it (main.cpp:183-341): frame 0 plus every
+    `frame_step`-th frame (1.5 mm / 0.1 deg of motion per frame).  Returns (depth frames [n,h,w] float32 with MINF holes,
+    K 3x3, gt poses [n,4,4] mapping frame i's camera space to frame 0's = targetTrajectory * trajectory_i^-1)."""
+    room = make_room(seed)
+    sx = width / TUM_W
+    fx, fy, cx, cy = TUM_FX * sx, TUM_FY * sx, (TUM_CX + 0.5) * sx - 0.5, (TUM_CY + 0.5) * sx - 0.5
+    pos0 = np.array([3.0, 5.0, 1.4])
+    frames, cams = [], []
+    for i in range(n_frames):
+        k = i * frame_step
+        pos = pos0 + k * np.array([0.0015, 0.0006, 0.0002])
+        d, r = render_depth(room, pos, 10.0 + 0.1 * k, 0.0, width, height, fx, fy, cx, cy, seed=seed + i, dropout=dropout)
+        t = np.eye(4); t[:3, :3] = r; t[:3, 3] = pos
+        frames.append(d); cams.append(t)
+    gt = np.stack([np.linalg.inv(cams[0]) @ c for c in cams]).astype(np.float32)
+    k3 = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    return np.stack(frames), k3, gt

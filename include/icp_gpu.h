@@ -193,6 +193,9 @@ int icp_gpu_cloud_from_depth(icp_gpu_ctx* ctx, const float* depth, const uint8_t
 /* ConvergenceMeasure(sourcePoints, unchangedPoints) (ConvergenceMeasure.h:32-41): m known correspondences
  * (source point i of the UNTRANSFORMED source <-> reference point i). */
 int icp_gpu_set_correspondences(icp_gpu_ctx* ctx, const float* src_xyz, const float* ref_xyz, int64_t m);
+/* The correspondences of reconstructRoom (main.cpp:300-307): every point of the current source against itself under a
+ * ground-truth pose, unchangedPoints = transformPoints(source.getPoints(), gt_pose); built on the device. */
+int icp_gpu_set_correspondences_pose(icp_gpu_ctx* ctx, const float gt_pose[16]);
 /* recordAlignmentError after every iteration of the last finished registration (ICPOptimizer.h:629-631):
  * rmse_out[k] = rmseAlignmentError(pose after iteration k) (ConvergenceMeasure.h:50-66); benchmark_out[k]
  * (nullable) = benchmarkError (ConvergenceMeasure.h:104-151).  Evaluated on the device from the pose history. */

@@ -144,3 +144,41 @@ def test_optimizer_mirror_depth_frames(ctx):
     assert opt.setTargetFromDepth(depth, rgbx, K, None, True) == w * h
     n = opt.setSourceFromDepth(depth, rgbx, K, None, False, 2)
     assert n == len(orc.cloud_from_depth(depth, rgbx, K[0, 0], K[1, 1], K[0, 2], K[1, 2], None, False, 2, 0.1)[0])
+
+
+@pytest.mark.parametrize("projective,multires,minimizer", [(True, False, 0), (False, False, 0), (False, True, 1)])
+def test_sequence_driver_equals_oracle_loop(projective, multires, minimizer):
+    """reconstructRoom (main.cpp:183-341): target fixed at frame 0, pose carried over from frame to frame, RMSE against the
+    ground-truth trajectory after every iteration -- the device pipeline against the same loop written with the oracle."""
+    from icp_variants_b200.optimizer import CeresICPOptimizer, LinearICPOptimizer
+    from icp_variants_b200.sequence import reconstructRoom
+    w, h, n_it = 160, 120, 6
+    frames, K, gt = synth.tum_sequence(n_frames=4, seed=21, width=w, height=h)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    opt = (CeresICPOptimizer if minimizer else LinearICPOptimizer)(device=0)
+    opt.setMetric(2); opt.setNbOfIterations(n_it)
+    if projective:
+        opt.setMatchingMethod(1)
+    opt.setMatchingMaxDistance(0.1)
+    opt.setWeightingMethod(2 if projective else 0)
+    opt.enableMultiResolution(multires)
+    res = reconstructRoom(opt, frames, K, groundTruthPoses=gt)
+    # the same loop with the oracle
+    tp, tn, tc = orc.cloud_from_depth(frames[0], None, fx, fy, cx, cy, None, projective, 1, 0.1)
+    cur = np.eye(4, dtype=np.float32)
+    for i in range(1, 4):
+        sp, sn, sc = orc.cloud_from_depth(frames[i], None, fx, fy, cx, cy, None, multires, 1 if multires else 8, 0.1)
+        cfg = orc.Config(metric=2, minimizer=minimizer, matching=int(projective), weighting=2 if projective else 0, multires=multires,
+                         n_iterations=n_it, max_distance_sq=0.1, fx=fx, fy=fy, cx=cx, cy=cy, width=w, height=h)
+        rc, cur, hist, _ = orc.estimate_pose(cfg, sp, sn, sc, tp, tn, tc, init_pose=cur)
+        assert rc == 0
+        assert res.nSourcePoints[i - 1] == len(sp)
+        got = res.cameraToWorld[i - 1]
+        rot = 2.0 * np.arcsin(min(1.0, np.linalg.norm(got[:3, :3].astype(np.float64) - cur[:3, :3]) / (2.0 * np.sqrt(2.0))))
+        assert rot < 1e-5 and np.abs(got[:3, 3] - cur[:3, 3]).max() < 1e-5, (i, rot)
+        ref = orc.transform_points(gt[i], sp)
+        r = np.array([orc.rmse(hh, sp, ref) for hh in hist])
+        assert len(res.rmsePerIteration[i - 1]) == len(hist)
+        assert np.allclose(res.rmsePerIteration[i - 1], r, rtol=3e-5)
+        cur = got      # continue from the device's pose so that rounding differences do not accumulate across frames
+    assert np.isfinite(res.finalRMSE).all() and len(res.estimatedPoses) == 4
