@@ -380,6 +380,12 @@ int check_ready(icp_gpu_ctx* ctx) {
     return 0;
 }
 
+// Projective matching of a full-frame source (one point per pixel of the camera the target was taken with): the kernels
+// then address the source in its original pixel order (the unsorted upload) instead of the Morton order.
+bool proj_tiled(const icp_gpu_ctx* c, int algo) {
+    return algo == 2 && c->n_src > 0 && (long long)c->width * c->height == (long long)c->n_src && !getenv("ICP_GPU_NO_PROJ_TILES");
+}
+
 void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, bool want_idx) {
     memset(&a, 0, sizeof(a));
     const bool grid_order = (algo == 0);
@@ -406,6 +412,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.nn_pos = (int*)c->nn_pos.p; a.qbuf = (float4*)c->qbuf.p;
     a.desc_index = desc_index;
     a.use_seed = grid_order ? 1 : 0;
+    if (proj_tiled(c, algo)) { a.src_pts = (const float4*)c->src_raw_pts.p; a.src_nrm = (const float4*)c->src_raw_nrm.p; a.proj_tiled = 1; }
     a.fast_path = getenv("ICP_GPU_NO_FASTPATH") ? 0 : 1;   // tuning knob (A/B measurement)
     a.collect_stats = c->cfg.collect_stats;
 }
@@ -423,6 +430,7 @@ void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     r.fused = 0; r.nn_pos = (const int*)c->nn_pos.p; r.n_tgt = c->n_tgt; r.mask = (const unsigned int*)c->mask.p;
     r.desc = (const IterDesc*)c->desc.p; r.desc_index = -1;
     r.weighting = c->cfg.weighting; r.rejection = c->cfg.rejection; r.max_d2 = c->cfg.max_distance_sq;
+    if (proj_tiled(c, algo)) { r.src_pts = (const float4*)c->src_raw_pts.p; r.src_nrm = (const float4*)c->src_raw_nrm.p; }
 }
 
 // Enqueue the whole loop.  ev_marks (nullable): events recorded around each stage for the timings report.
@@ -870,7 +878,8 @@ int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t*
     CU(cudaStreamSynchronize(ctx->stream));
     // device results are in sorted-source order; the caller gets its own order back
     for (int k = 0; k < nq; ++k) {
-        const int p = ctx->src_rank[(size_t)(sel_idx ? sel_idx[k] : k)];
+        const int o = sel_idx ? sel_idx[k] : k;
+        const int p = ma.proj_tiled ? o : ctx->src_rank[(size_t)o];
         idx_out[k] = idx_s[(size_t)p]; weight_out[k] = w_s[(size_t)p];
     }
     copy_counters(ctx);

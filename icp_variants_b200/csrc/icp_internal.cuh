@@ -136,6 +136,7 @@ struct MatchArgs {
     float4* qbuf;            // transformed query points of the current iteration {x,y,z,rgba}; x = NaN: not searched
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
     int use_seed;
+    int proj_tiled;          // projective matching of a full-frame source: src arrays are in ORIGINAL (pixel) order, one 32x8 tile per block
     int fast_path;           // knn_prep_kernel answers the queries whose search ball stays inside their seed leaf's inflated box
     int collect_stats;       // work counters in DevState (atomics); off in timed runs
     int skip_finish;         // BVH path: the reduction evaluates stages 3-4 itself (ReduceArgs::fused), no match records

@@ -519,13 +519,25 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
     __shared__ unsigned int s_box[4][PROJ_THREADS / 32];
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // Which query this thread answers.  A full-frame source (one point per pixel, original order: a.proj_tiled) is cut
+    // into 32 x 8 pixel tiles, one per block: the windows of a tile overlap in a (32+24) x (8+24) region (plus the
+    // inter-frame motion), which always fits the shared-memory stage, and the lanes of a warp read consecutive entries
+    // of it (no bank conflicts).  Any other source is taken 256 consecutive points of its Morton order at a time.
+    int p; bool in;
+    if (a.proj_tiled) {
+        const unsigned int tiles_x = (a.width + 31u) / 32u;
+        const unsigned int u = (blockIdx.x % tiles_x) * 32u + (unsigned int)lane, v = (blockIdx.x / tiles_x) * (PROJ_THREADS / 32) + (unsigned int)wid;
+        in = u < a.width && v < a.height;
+        p = (int)(v * a.width + u);
+    } else {
+        p = blockIdx.x * blockDim.x + threadIdx.x;
+        in = p < a.n_src;
+    }
     const unsigned int searchWindow = 12u;                                 // NearestNeighbor.h:319
     unsigned int nq = 0, nm = 0, ev = 0, nd = 0;
     Query q; float snx = 0.f, sny = 0.f, snz = 0.f; unsigned int s_rgba = 0;
     q.x = q.y = q.z = 0.f; q.cr = q.cg = q.cb = 0.f;
-    const bool in = p < a.n_src;
     const bool is_query = in && prepare_query(a, d, sm, p, q, snx, sny, snz, s_rgba);
     const bool scans = is_query && !(q.x == MINF_F);                       // :372-373
     unsigned int uP = 0, vP = 0, u0 = 0xFFFFFFFFu, v0 = 0xFFFFFFFFu, u1 = 0, v1 = 0;
@@ -551,6 +563,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
     const bool any_window = bu0 != 0xFFFFFFFFu;
     const unsigned int tw = any_window ? bu1 - bu0 + 1u : 0u, th = any_window ? bv1 - bv0 + 1u : 0u;
     const bool staged = any_window && (unsigned long long)tw * th <= PROJ_TILE_MAX;      // block-uniform
+    if (any_window && !staged && threadIdx.x == 0) ++nd;                                // work counter: blocks that fall back to global reads
     if (staged) {
         for (unsigned int k = threadIdx.x; k < tw * th; k += PROJ_THREADS) {
             const unsigned int ty = k / tw, tx = k - ty * tw;
@@ -568,19 +581,37 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
             } else {
                 float minDist = FLT_BIG; unsigned int idx = 0xFFFFFFFFu;
                 if (has_window) {
-                    for (unsigned int v = v0; v <= v1; v++) {
-                        const float4* row = staged ? &tile[(v - bv0) * tw + (u0 - bu0)] : &a.tgt_pts[(size_t)a.width * v + u0];
-                        const unsigned int n_u = u1 - u0 + 1u;
+                    // Scan order = the reference's (rows, then columns): the strict '>' of :399 keeps the first minimum.  A MINF
+                    // target (:392 `continue`) needs no test of its own: its distance is +inf (or NaN), which never passes the
+                    // strict comparison against a minDist that starts at FLT_MAX.  The winner is remembered as a running
+                    // candidate number and decoded after the loops.
+                    const unsigned int n_u = u1 - u0 + 1u;
+                    unsigned int cnt = 0u, best = 0xFFFFFFFFu;
+                    if (staged) {
+                        const float4* row = &tile[(v0 - bv0) * tw + (u0 - bu0)];          // shared-memory pointer: LDS.128
+                        for (unsigned int v = v0; v <= v1; ++v, row += tw) {
 #pragma unroll 5
-                        for (unsigned int k = 0; k < n_u; k++) {
-                            const float4 t = staged ? row[k] : __ldg(&row[k]);
-                            if (t.x == MINF_F) continue;                                   // :392
-                            const float dx = psub(q.x, t.x), dy = psub(q.y, t.y), dz = psub(q.z, t.z);
-                            const float dist = padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));
-                            ++ev;
-                            if (minDist > dist) { idx = a.width * v + u0 + k; minDist = dist; }   // :399 strict: first minimum in scan order
+                            for (unsigned int k = 0; k < n_u; ++k, ++cnt) {
+                                const float4 t = row[k];
+                                const float dx = psub(q.x, t.x), dy = psub(q.y, t.y), dz = psub(q.z, t.z);
+                                const float dist = padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));
+                                if (minDist > dist) { best = cnt; minDist = dist; }
+                            }
+                        }
+                    } else {
+                        const float4* row = &a.tgt_pts[(size_t)a.width * v0 + u0];
+                        for (unsigned int v = v0; v <= v1; ++v, row += a.width) {
+#pragma unroll 5
+                            for (unsigned int k = 0; k < n_u; ++k, ++cnt) {
+                                const float4 t = __ldg(&row[k]);
+                                const float dx = psub(q.x, t.x), dy = psub(q.y, t.y), dz = psub(q.z, t.z);
+                                const float dist = padd(padd(pmul(dx, dx), pmul(dy, dy)), pmul(dz, dz));
+                                if (minDist > dist) { best = cnt; minDist = dist; }
+                            }
                         }
                     }
+                    ev += cnt;                                                            // candidates scanned (MINF ones included)
+                    if (best != 0xFFFFFFFFu) idx = a.width * (v0 + best / n_u) + u0 + best % n_u;
                 }
                 const bool ok = minDist <= a.max_d2 && idx != 0xFFFFFFFFu;               // :407
                 finish_match(a, p, ok, 1.0f, (int)idx, (int)idx, q.x, q.y, q.z, snx, sny, snz, s_rgba, nm);
@@ -595,7 +626,9 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
     const int T = ICP_MATCH_THREADS;
     int launches = 0;
     if (algorithm == 2) {
-        projective_kernel<<<(a.n_src + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, s>>>(a); ++launches;
+        const unsigned int nb = a.proj_tiled ? ((a.width + 31u) / 32u) * ((a.height + PROJ_THREADS / 32 - 1u) / (PROJ_THREADS / 32))
+                                             : (unsigned int)((a.n_src + PROJ_THREADS - 1) / PROJ_THREADS);
+        projective_kernel<<<nb, PROJ_THREADS, 0, s>>>(a); ++launches;
     } else if (algorithm == 1) {
         const long long threads = (long long)a.n_src * 32;
         const int nb = (int)((threads + T - 1) / T);
