@@ -65,3 +65,58 @@ def reconstructRoom(optimizer: ICPOptimizer, depthFrames, depthIntrinsics, color
         res.nSourcePoints.append(int(ns))
         res.secondsPerFrame.append(time.perf_counter() - t0)
     return res
+
+
+@dataclass
+class PairResult:
+    pose: np.ndarray
+    nIterations: int
+    rmseErrors: list = field(default_factory=list)
+    benchmarkErrors: list = field(default_factory=list)
+    error: str | None = None
+
+
+def alignPairs(contexts, pairs, config, calculateErrors: bool = False):
+    """The pair loop of alignETH (main.cpp:343-514; experiment.cpp:276-412): independent (source, target[, unchanged source])
+    registrations, identity start pose, dealt round-robin to the given contexts (one or two per GPU, any number of GPUs).
+    Registration k+1 is uploaded and enqueued on the next context before registration k is waited for
+    (icp_gpu_estimate_pose_async / _finish), so uploads, index builds and loops of different contexts overlap.
+    pairs: iterable of (source Cloud, target Cloud) or (source, target, unchangedSourcePoints [N,3]) -- the third entry feeds
+    ConvergenceMeasure(source points, unchanged points, runBenchmark=true) as main.cpp:439 does.  Returns [PairResult]."""
+    from . import capi
+    pairs = list(pairs)
+    results: list = [None] * len(pairs)
+    pending: list = []                      # (pair index, context)
+
+    def finish(k, ctx):
+        try:
+            pose, n_it = ctx.estimate_pose_finish()
+            r = PairResult(pose, n_it)
+        except capi.IcpGpuError as e:
+            if e.code not in (capi.E_NO_MATCHES, capi.E_NUMERIC):
+                raise
+            # the reference spins in ASSERT / returns a NaN pose here; the drop-in reports it and goes on with the next pair
+            r = PairResult(getattr(e, "pose", np.eye(4, dtype=np.float32)), 0, error=str(e))
+        if calculateErrors and len(pairs[k]) > 2 and r.nIterations > 0:
+            ctx.set_correspondences(pairs[k][0].points, pairs[k][2])
+            rm, be = ctx.convergence_errors(benchmark=True)
+            r.rmseErrors, r.benchmarkErrors = [float(x) for x in rm], [float(x) for x in be]
+        results[k] = r
+
+    for k, pr in enumerate(pairs):
+        ctx = contexts[k % len(contexts)]
+        # a context still busy with an earlier pair must be drained first
+        for j, (kk, cc) in enumerate(pending):
+            if cc is ctx:
+                finish(kk, cc)
+                pending.pop(j)
+                break
+        src, tgt = pr[0], pr[1]
+        ctx.set_config(config)
+        ctx.set_target(tgt.points, tgt.normals, tgt.colors)
+        ctx.set_source(src.points, src.normals, src.colors)
+        ctx.estimate_pose_async(np.eye(4, dtype=np.float32))
+        pending.append((k, ctx))
+    for kk, cc in pending:
+        finish(kk, cc)
+    return results

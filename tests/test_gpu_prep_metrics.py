@@ -182,3 +182,31 @@ def test_sequence_driver_equals_oracle_loop(projective, multires, minimizer):
         assert np.allclose(res.rmsePerIteration[i - 1], r, rtol=3e-5)
         cur = got      # continue from the device's pose so that rounding differences do not accumulate across frames
     assert np.isfinite(res.finalRMSE).all() and len(res.estimatedPoses) == 4
+
+
+def test_pair_queue_equals_sequential(small_eth_pair, bunny):
+    """alignETH's pair loop (main.cpp:411-498) as a queue over two contexts of one GPU: same poses as one pair at a time,
+    ConvergenceMeasure(source, unchanged source, runBenchmark=true) filled per pair (main.cpp:439)."""
+    from icp_variants_b200.sequence import alignPairs
+    src, tgt, pert = small_eth_pair
+    bs, bt, _, _ = bunny
+    unchanged = orc.transform_points(np.linalg.inv(pert).astype(np.float32), src.points)
+    pairs = [(src, tgt, unchanged), (bs, bt), (src, tgt, unchanged), (tgt, src), (bs, bt)]
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations, cfg.max_distance_sq = 1, 8, 10.0
+    with capi.Context(0) as a, capi.Context(0) as b:
+        res = alignPairs([a, b], pairs, cfg, calculateErrors=True)
+    assert len(res) == 5 and all(r is not None for r in res)
+    with capi.Context(0) as c:
+        for k, pr in enumerate(pairs):
+            c.set_config(cfg); c.set_target(pr[1].points, pr[1].normals, pr[1].colors); c.set_source(pr[0].points, pr[0].normals, pr[0].colors)
+            try:
+                pose, hist, n_it = c.estimate_pose()
+            except capi.IcpGpuError:
+                assert res[k].error is not None
+                continue
+            assert np.array_equal(res[k].pose, pose) and res[k].nIterations == n_it
+            if len(pr) > 2:
+                assert len(res[k].rmseErrors) == len(res[k].benchmarkErrors) == n_it
+                assert res[k].rmseErrors[-1] == pytest.approx(orc.rmse(pose, src.points, unchanged), rel=2e-5)
+                assert res[k].benchmarkErrors[-1] == pytest.approx(orc.benchmark_error(pose, src.points, unchanged), rel=1e-9)
