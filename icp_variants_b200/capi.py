@@ -106,6 +106,7 @@ def lib():
             "icp_gpu_estimate_pose_finish": (C.c_int, [vp, pf, pf, C.POINTER(i32)]),
             "icp_gpu_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
             "icp_gpu_cloud_from_depth": (C.c_int, [vp, pf, pf, pf, pf, u32, u32, C.c_int, u32, C.c_float, C.c_int, pf, pf, pf, C.POINTER(i64)]),
+            "icp_gpu_target_normals": (C.c_int, [vp, i32, pf, pf, pf]),
             "icp_gpu_set_correspondences": (C.c_int, [vp, pf, pf, i64]),
             "icp_gpu_set_correspondences_pose": (C.c_int, [vp, pf]),
             "icp_gpu_convergence_errors": (C.c_int, [vp, pf, pf, i32, C.POINTER(i32)]),
@@ -295,6 +296,16 @@ class Context:
         if not download:
             return n.value
         return po[:n.value].copy(), no[:n.value].copy(), co[:n.value].copy()
+
+    def target_normals(self, k: int = 5, viewpoint=None, n: int | None = None, curvature: bool = False):
+        """PointCloud(pcl cloud) (PointCloud.h:41-76): k-NN PCA normals of the resident target (n = its size); they also
+        replace the target's normals on the device.  Returns normals [n,3] (and curvature [n])."""
+        if n is None:
+            raise ValueError("pass n = number of target points")
+        vp = None if viewpoint is None else np.ascontiguousarray(viewpoint, np.float32)
+        nrm = np.empty((n, 3), np.float32); cur = np.empty(n, np.float32) if curvature else None
+        self._check(lib().icp_gpu_target_normals(self._h, int(k), _ptr(vp), _ptr(nrm), _ptr(cur)))
+        return (nrm, cur) if curvature else nrm
 
     def set_correspondences(self, src_xyz, ref_xyz):
         s = _f32(src_xyz, 3); r = _f32(ref_xyz, 3)

@@ -92,6 +92,7 @@ struct icp_gpu_ctx {
     int Ts = 0;
     // loop state
     DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, nn_leaf, qbuf, partials, pose_dev, history;
+    DeviceBuf nrm_out_dev;
     DeviceBuf prep_in, prep_tmp, prep_out, gt_src, gt_ref, met_partial, met_out;
     long long n_gt = 0; int last_iters = 0;
     float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
@@ -646,7 +647,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
                          &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf,
-                         &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
+                         &ctx->nrm_out_dev, &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);
@@ -759,6 +760,36 @@ int icp_gpu_cloud_from_depth(icp_gpu_ctx* ctx, const float* depth, const uint8_t
         rc = set_cloud(ctx, role == ICP_GPU_CLOUD_TARGET, (const float*)out, (const float*)(out + t_nrm), (const uint8_t*)(out + 2 * t_nrm), (int64_t)n, true);
     if (xyz_out || nrm_out || rgba_out) CU(cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+// PointCloud(pcl::PointCloud<pcl::PointXYZ>::Ptr) (PointCloud.h:41-76): k-NN PCA normals (pcl::NormalEstimation, setKSearch(k)) of the
+// context's TARGET cloud, computed with the index set_target built.  The normals replace the target's own (used by the next
+// registrations) and are returned in the caller's point order.
+int icp_gpu_target_normals(icp_gpu_ctx* ctx, int32_t k, const float viewpoint[3], float* nrm_out, float* curvature_out) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (k < 3 || k > 8) return fail(ctx, ICP_GPU_E_ARG, "k %d (3..8)", k);
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
+    if (!ctx->grid_built) return fail(ctx, ICP_GPU_E_STATE, "no target cloud set");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    const int n = ctx->n_tgt;
+    if (n <= 0) return ICP_GPU_OK;
+    if (ensure(ctx, ctx->nrm_out_dev, (size_t)n * 16 + 256)) return ICP_GPU_E_CUDA;
+    NormalArgs a; memset(&a, 0, sizeof(a));
+    a.pts = (const float4*)ctx->tgt_pts_sorted.p; a.n = n;
+    a.bvh_box = (const float4*)ctx->bvh_box.p; a.bvh = (const BvhDesc*)ctx->bvh_desc.p; a.leaf_start = (const unsigned int*)ctx->leaf_start.p;
+    a.leaf_rank = (const unsigned int*)ctx->leaf_rank.p; a.child_start = (const unsigned int*)ctx->child_start.p;
+    a.adj = (const unsigned int*)ctx->adj.p; a.adj_box = (const float4*)ctx->adj_box.p; a.adj_capacity = ctx->adj_capacity;
+    a.k = k;
+    for (int i = 0; i < 3; ++i) a.vp[i] = viewpoint ? viewpoint[i] : 0.f;
+    a.out_nrm = (float*)ctx->nrm_out_dev.p; a.out_curv = (float*)ctx->nrm_out_dev.p + 3 * (size_t)n;
+    a.nrm_sorted = (float4*)ctx->tgt_nrm_sorted.p; a.nrm_orig = (float4*)ctx->tgt_nrm.p;
+    CU(cudaMemsetAsync(ctx->nrm_out_dev.p, 0xFF, (size_t)n * 16, ctx->stream));     // NaN: points the index does not hold (non-finite ones)
+    CU(icp_launch_pca_normals(a, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+    if (nrm_out) CU(cudaMemcpyAsync(nrm_out, a.out_nrm, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (curvature_out) CU(cudaMemcpyAsync(curvature_out, a.out_curv, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nrm_out || curvature_out) CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
 }
 
 // ConvergenceMeasure(sourcePoints, unchangedPoints) (ConvergenceMeasure.h:32-41): the known correspondences.

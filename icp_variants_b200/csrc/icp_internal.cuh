@@ -199,6 +199,16 @@ cudaError_t icp_launch_gt_from_source(const float4* src_raw, long long n, const 
 int icp_metrics_blocks(long long m, int n_sms);
 cudaError_t icp_launch_metrics(const float* src, const float* ref, long long m, const float* history, int n_iters, int n_blocks, double* partial,
                                float* rmse, float* centroid, double* bench, cudaStream_t s, int* n_launches);
+// normals.cu: k-NN PCA normals of the indexed cloud (PointCloud.h:41-76)
+struct NormalArgs {
+    const float4* pts; int n;                // cell-sorted cloud {x,y,z,orig idx}
+    const float4* bvh_box; const BvhDesc* bvh; const unsigned int* leaf_start; const unsigned int* leaf_rank; const unsigned int* child_start;
+    const unsigned int* adj; const float4* adj_box; int adj_capacity;
+    int k; float vp[3];
+    float* out_nrm; float* out_curv;         // original order: 3n, n
+    float4* nrm_sorted; float4* nrm_orig;    // the cloud's own normal arrays {nx,ny,nz,rgba}: x,y,z overwritten
+};
+cudaError_t icp_launch_pca_normals(const NormalArgs& a, cudaStream_t s);
 cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep = nullptr);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);

@@ -245,6 +245,13 @@ class ICPOptimizer:
                 cm.benchmarkErrors.extend(float(b) for b in bench)
         return pose
 
+    def estimateNormals(self, points, k: int = 5, viewpoint=None):
+        """PointCloud(pcl cloud) (PointCloud.h:41-76): k-NN PCA normals of a cloud, computed on the device.  The cloud is
+        indexed as the target to do so (set the registration's target afterwards if it is another cloud)."""
+        pts = np.ascontiguousarray(points, np.float32)
+        self._ctx.set_target(pts, None, None)
+        return self._ctx.target_normals(k, viewpoint, n=len(pts))
+
     def setTargetFromDepth(self, depthMap, colorFrame, depthIntrinsics, depthExtrinsics=None, keepOriginalSize=False, downsampleFactor=1,
                            maxDistance=0.1):
         """PointCloud(depthMap, colorFrame, ...) (PointCloud.h:78-165) built on the device and indexed as the target

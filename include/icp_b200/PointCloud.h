@@ -35,6 +35,22 @@ public:
         icp_gpu_destroy(ctx);
     }
 
+    // PointCloud(pcl::PointCloud<pcl::PointXYZ>::Ptr) (PointCloud.h:41-76) without the PCL types: points in, k = 5 PCA normals
+    // (pcl::NormalEstimation, viewpoint at the origin) computed on the device, colours (255, 255, 255, 1) (:74).
+    static PointCloud fromPoints(const std::vector<Vector3f>& points, int kSearch = 5) {
+        PointCloud c;
+        c.m_points = points;
+        c.m_normals.resize(points.size());
+        c.m_colors.assign(points.size(), Vector4uc(255, 255, 255, 1));
+        icp_gpu_ctx* ctx = nullptr;
+        if (icp_gpu_create(&ctx, 0) != ICP_GPU_OK) { std::cout << "icp_gpu: no usable CUDA device (there is no CPU fallback)" << std::endl; return c; }
+        int rc = points.empty() ? ICP_GPU_OK : icp_gpu_set_target(ctx, reinterpret_cast<const float*>(points.data()), nullptr, nullptr, (int64_t)points.size());
+        if (rc == ICP_GPU_OK && !points.empty()) rc = icp_gpu_target_normals(ctx, kSearch, nullptr, reinterpret_cast<float*>(c.m_normals.data()), nullptr);
+        if (rc != ICP_GPU_OK) std::cout << "icp_gpu: " << icp_gpu_last_error(ctx) << std::endl;
+        icp_gpu_destroy(ctx);
+        return c;
+    }
+
     std::vector<Vector3f>& getPoints() { return m_points; }
     const std::vector<Vector3f>& getPoints() const { return m_points; }
     std::vector<Vector3f>& getNormals() { return m_normals; }

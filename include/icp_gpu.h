@@ -190,6 +190,13 @@ int icp_gpu_cloud_from_depth(icp_gpu_ctx* ctx, const float* depth, const uint8_t
                              const float E_colmajor[16], uint32_t width, uint32_t height, int keep_original_size,
                              uint32_t downsample, float max_distance, int role,
                              float* xyz_out, float* nrm_out, uint8_t* rgba_out, int64_t* n_out);
+/* PointCloud(pcl::PointCloud<pcl::PointXYZ>::Ptr) (PointCloud.h:41-76): pcl::NormalEstimation with setKSearch(k) (the
+ * reference uses k = 5) and viewpoint (nullable = the origin) on the context's TARGET cloud, with the index
+ * icp_gpu_set_target built: the k nearest neighbours of every point (itself included), the eigenvector of the smallest
+ * eigenvalue of their covariance, flipped towards the viewpoint; NaN for non-finite points.  The normals replace the
+ * target's own for the following registrations and are returned in the caller's point order (nrm_out: 3*n floats,
+ * curvature_out: n floats, both nullable).  3 <= k <= 8. */
+int icp_gpu_target_normals(icp_gpu_ctx* ctx, int32_t k, const float viewpoint[3], float* nrm_out, float* curvature_out);
 /* ConvergenceMeasure(sourcePoints, unchangedPoints) (ConvergenceMeasure.h:32-41): m known correspondences
  * (source point i of the UNTRANSFORMED source <-> reference point i). */
 int icp_gpu_set_correspondences(icp_gpu_ctx* ctx, const float* src_xyz, const float* ref_xyz, int64_t m);

@@ -1101,3 +1101,81 @@ double orc_benchmark_error(const float pose[16], const float* src, const float* 
     free(t);
     return n ? err / (double)n : 0.0;
 }
+
+/* ------------------------------------------------------------------ k-NN PCA normals (second half) */
+
+/* Jacobi eigen-decomposition of a symmetric 3x3 (row-major) in double, eigenvalues ascending; column k of V
+ * (V[3*i+k]) is the k-th eigenvector.  Cyclic sweeps (0,1), (0,2), (1,2) until the off-diagonal sum is below 1e-300 or 64
+ * sweeps.  The device kernel (csrc/normals.cu) executes exactly these operations in this order, without FMA contraction. */
+static void orc_eig3(const double A_[9], double evals[3], double V[9]) {
+    double A[9];
+    for (int i = 0; i < 9; ++i) { A[i] = A_[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double off = (fabs(A[1]) + fabs(A[2])) + fabs(A[5]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            const double apq = A[p * 3 + q];
+            if (apq == 0.0) continue;
+            const double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            for (int k = 0; k < 3; ++k) { const double akp = A[k * 3 + p], akq = A[k * 3 + q]; A[k * 3 + p] = c * akp - s * akq; A[k * 3 + q] = s * akp + c * akq; }
+            for (int k = 0; k < 3; ++k) { const double apk = A[p * 3 + k], aqk = A[q * 3 + k]; A[p * 3 + k] = c * apk - s * aqk; A[q * 3 + k] = s * apk + c * aqk; }
+            for (int k = 0; k < 3; ++k) { const double vkp = V[k * 3 + p], vkq = V[k * 3 + q]; V[k * 3 + p] = c * vkp - s * vkq; V[k * 3 + q] = s * vkp + c * vkq; }
+        }
+    }
+    int ord[3] = {0, 1, 2};   /* stable ascending order of the diagonal */
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j) if (A[ord[j + 1] * 4] < A[ord[j] * 4]) { const int t = ord[j]; ord[j] = ord[j + 1]; ord[j + 1] = t; }
+    double Vs[9];
+    for (int k = 0; k < 3; ++k) { evals[k] = A[ord[k] * 4]; for (int i = 0; i < 3; ++i) Vs[i * 3 + k] = V[i * 3 + ord[k]]; }
+    for (int i = 0; i < 9; ++i) V[i] = Vs[i];
+}
+
+/* PointCloud(pcl::PointCloud<PointXYZ>::Ptr) (PointCloud.h:41-76): pcl::NormalEstimation with setKSearch(k = 5) and the
+ * default viewpoint (0,0,0).  PCL is an un-vendored dependency; restated from its published algorithm
+ * (features/normal_3d.h): the k nearest neighbours of every point (itself included; exact, (d2, index) order under contract
+ * D1), the covariance of the neighbourhood about its mean (double), the eigenvector of the smallest eigenvalue, flipped
+ * towards the viewpoint; curvature = |l0 / (l0 + l1 + l2)|.  Non-finite points, and points with fewer than 3 finite
+ * neighbours, get NaN normals.  out_nrm: 3n floats, out_curv (nullable): n floats. */
+void orc_pca_normals(const float* pts, int64_t n, int k, const float vp[3], float* out_nrm, float* out_curv) {
+    if (k > 16) k = 16;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        const float nanf_ = NAN;
+        float* o = out_nrm + 3 * i;
+        o[0] = o[1] = o[2] = nanf_; if (out_curv) out_curv[i] = nanf_;
+        const float* q = pts + 3 * i;
+        if (!finite3(q)) continue;
+        float bd[16]; int64_t bi[16]; int m = 0;
+        for (int64_t j = 0; j < n; ++j) {
+            const float* p = pts + 3 * j;
+            const float d = d2_3(q, p);
+            if (!isfinite(d)) continue;
+            /* insert (d, j) into the ascending list; equal distances keep index order because j ascends */
+            if (m < k || d < bd[m - 1]) {
+                int pos = m < k ? m : k - 1;
+                while (pos > 0 && d < bd[pos - 1]) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; --pos; }
+                bd[pos] = d; bi[pos] = j;
+                if (m < k) ++m;
+            }
+        }
+        if (m < 3) continue;
+        double mean[3] = {0, 0, 0};
+        for (int a = 0; a < m; ++a) { mean[0] += pts[3 * bi[a]]; mean[1] += pts[3 * bi[a] + 1]; mean[2] += pts[3 * bi[a] + 2]; }
+        for (int a = 0; a < 3; ++a) mean[a] /= (double)m;
+        double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int a = 0; a < m; ++a) {
+            const double d[3] = {pts[3 * bi[a]] - mean[0], pts[3 * bi[a] + 1] - mean[1], pts[3 * bi[a] + 2] - mean[2]};
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r * 3 + c] += d[r] * d[c];
+        }
+        for (int a = 0; a < 9; ++a) C[a] /= (double)m;
+        double ev[3], V[9];
+        orc_eig3(C, ev, V);
+        double nx = V[0], ny = V[3], nz = V[6];
+        const double sum = (ev[0] + ev[1]) + ev[2];
+        const double vx = (double)vp[0] - q[0], vy = (double)vp[1] - q[1], vz = (double)vp[2] - q[2];
+        if ((vx * nx + vy * ny) + vz * nz < 0) { nx = -nx; ny = -ny; nz = -nz; }          /* flipNormalTowardsViewpoint */
+        o[0] = (float)nx; o[1] = (float)ny; o[2] = (float)nz;
+        if (out_curv) out_curv[i] = sum != 0 ? (float)fabs(ev[0] / sum) : 0.f;
+    }
+}

@@ -131,6 +131,8 @@ int orc_estimate_pose(const orc_config* cfg,
 
 /* ConvergenceMeasure.h:50-66 */
 float orc_rmse(const float pose[16], const float* src, const float* ref, int64_t n);
+/* PointCloud(pcl cloud) (PointCloud.h:41-76): k-NN PCA normals (PCL NormalEstimation restated), viewpoint vp. */
+void orc_pca_normals(const float* pts, int64_t n, int k, const float vp[3], float* out_nrm, float* out_curv);
 /* ConvergenceMeasure.h:104-151 (Fontana benchmark error) */
 double orc_benchmark_error(const float pose[16], const float* src, const float* ref, int64_t n);
 

@@ -250,6 +250,14 @@ def rmse(pose, src, ref):
     return float(lib().orc_rmse(_p(_pose(pose)), _p(src), _p(ref), C.c_int64(len(src))))
 
 
+def pca_normals(pts, k=5, viewpoint=(0.0, 0.0, 0.0)):
+    """PointCloud(pcl cloud) (PointCloud.h:41-76): (normals [N,3], curvature [N])."""
+    pts = _f32(pts); nrm = np.empty_like(pts); cur = np.empty(len(pts), np.float32)
+    vp = np.ascontiguousarray(viewpoint, np.float32)
+    lib().orc_pca_normals(_p(pts), C.c_int64(len(pts)), C.c_int(k), _p(vp), _p(nrm), _p(cur))
+    return nrm, cur
+
+
 def benchmark_error(pose, src, ref):
     src, ref = _f32(src), _f32(ref)
     return float(lib().orc_benchmark_error(_p(_pose(pose)), _p(src), _p(ref), C.c_int64(len(src))))

@@ -39,7 +39,7 @@ inline void eig3(const double A_[9], double evals[3], double evecs[9] /* column 
     double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int i = 0; i < 9; ++i) A[i] = A_[i];
     for (int sweep = 0; sweep < 64; ++sweep) {
-        const double off = std::fabs(A[1]) + std::fabs(A[2]) + std::fabs(A[5]);
+        const double off = (std::fabs(A[1]) + std::fabs(A[2])) + std::fabs(A[5]);
         if (off < 1e-300) break;
         for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
             const double apq = A[p * 3 + q];
@@ -52,8 +52,8 @@ inline void eig3(const double A_[9], double evals[3], double evecs[9] /* column 
             for (int k = 0; k < 3; ++k) { const double vkp = V[k * 3 + p], vkq = V[k * 3 + q]; V[k * 3 + p] = c * vkp - s * vkq; V[k * 3 + q] = s * vkp + c * vkq; }
         }
     }
-    int ord[3] = {0, 1, 2};
-    std::sort(ord, ord + 3, [&](int a, int b) { return A[a * 3 + a] < A[b * 3 + b]; });
+    int ord[3] = {0, 1, 2};   // stable ascending order of the diagonal
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j) if (A[ord[j + 1] * 4] < A[ord[j] * 4]) std::swap(ord[j], ord[j + 1]);
     for (int k = 0; k < 3; ++k) { evals[k] = A[ord[k] * 3 + ord[k]]; for (int i = 0; i < 3; ++i) evecs[i * 3 + k] = V[i * 3 + ord[k]]; }
 }
 }  // namespace shim
@@ -99,10 +99,10 @@ public:
             for (int a = 0; a < 9; ++a) C[a] /= (double)best.size();
             double ev[3], V[9]; shim::eig3(C, ev, V);
             double nx = V[0], ny = V[3], nz = V[6];
-            const double sum = ev[0] + ev[1] + ev[2];
+            const double sum = (ev[0] + ev[1]) + ev[2];
             // flipNormalTowardsViewpoint
             const double vx = vpx_ - P[i].x, vy = vpy_ - P[i].y, vz = vpz_ - P[i].z;
-            if (vx * nx + vy * ny + vz * nz < 0) { nx = -nx; ny = -ny; nz = -nz; }
+            if ((vx * nx + vy * ny) + vz * nz < 0) { nx = -nx; ny = -ny; nz = -nz; }
             o.normal_x = (float)nx; o.normal_y = (float)ny; o.normal_z = (float)nz;
             o.curvature = sum != 0 ? (float)std::fabs(ev[0] / sum) : 0.f;
         }

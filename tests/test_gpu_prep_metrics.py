@@ -210,3 +210,57 @@ def test_pair_queue_equals_sequential(small_eth_pair, bunny):
                 assert len(res[k].rmseErrors) == len(res[k].benchmarkErrors) == n_it
                 assert res[k].rmseErrors[-1] == pytest.approx(orc.rmse(pose, src.points, unchanged), rel=2e-5)
                 assert res[k].benchmarkErrors[-1] == pytest.approx(orc.benchmark_error(pose, src.points, unchanged), rel=1e-9)
+
+
+def test_pca_normals_bit_exact(ctx, small_eth_pair, bunny):
+    """PointCloud(pcl cloud) (PointCloud.h:41-76): k = 5 PCA normals on the device against the oracle's restatement of
+    pcl::NormalEstimation (itself equal, bit for bit, to the reference constructor running over the PCL stand-in)."""
+    src, tgt, _ = small_eth_pair
+    bs, bt, _, _ = bunny
+    rng = np.random.default_rng(3)
+    quant = (np.round(rng.uniform(-1, 1, (3000, 3)) * 16) / 16).astype(np.float32)       # many ties and duplicates
+    holes = tgt.points.copy(); holes[11, 0] = np.nan; holes[500, 2] = -np.inf
+    for pts, k, vp in ((tgt.points, 5, None), (bt.points, 5, None), (holes, 5, (1.0, -2.0, 0.5)), (quant, 5, None), (src.points, 8, None), (bt.points, 3, None)):
+        ctx.set_target(pts, None, None)
+        n_g, c_g = ctx.target_normals(k, vp, n=len(pts), curvature=True)
+        n_o, c_o = orc.pca_normals(pts, k, vp if vp is not None else (0.0, 0.0, 0.0))
+        assert np.array_equal(n_g, n_o, equal_nan=True), (k, np.nanmax(np.abs(n_g - n_o)), (n_g != n_o).any(1).sum())
+        assert np.array_equal(c_g, c_o, equal_nan=True)
+    assert np.isnan(n_g).sum() == 0
+
+
+def test_pca_normals_become_the_target_normals(ctx, small_eth_pair):
+    """The computed normals replace the target's: a point-to-plane registration then equals one with the normals uploaded."""
+    src, tgt, _ = small_eth_pair
+    c = capi.default_config(); c.metric, c.n_iterations, c.max_distance_sq = 1, 5, 0.5
+    ctx.set_config(c)
+    ctx.set_target(tgt.points, None, None); ctx.set_source(src.points, src.normals, None)
+    nrm = ctx.target_normals(5, None, n=len(tgt.points))
+    pose_a, _, _ = ctx.estimate_pose()
+    ctx.set_target(tgt.points, nrm, None)
+    pose_b, _, _ = ctx.estimate_pose()
+    assert np.array_equal(pose_a, pose_b)
+
+
+def test_pca_normals_full_size_properties(ctx):
+    """370k points: unit length, oriented towards the viewpoint, and equal to an independent fp64 PCA (scipy k-NN + numpy
+    eigh) on a random subset wherever the smallest eigenvalue is well separated."""
+    from scipy.spatial import cKDTree
+    _, tgt, _ = synth.eth_pair(seed=1234)
+    pts = tgt.points
+    ctx.set_target(pts, None, None)
+    nrm = ctx.target_normals(5, None, n=len(pts))
+    assert np.isfinite(nrm).all()
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-6)
+    assert ((-pts * nrm).sum(1) >= -1e-6).all()                      # flipNormalTowardsViewpoint, viewpoint = origin
+    sel = np.random.default_rng(0).choice(len(pts), 3000, replace=False)
+    p64 = pts.astype(np.float64)
+    _, nb = cKDTree(p64).query(p64[sel], k=5)
+    ok = 0
+    for s, idx in zip(sel, nb):
+        q = p64[idx]; C = np.cov((q - q.mean(0)).T, bias=True)
+        w, v = np.linalg.eigh(C)
+        if w[1] - w[0] > 1e-3 * w[2]:
+            assert abs(v[:, 0] @ nrm[s]) > 1 - 1e-6
+            ok += 1
+    assert ok > 1000

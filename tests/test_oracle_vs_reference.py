@@ -389,3 +389,20 @@ def test_benchmark_error_equals_reference(bunny, small_eth_pair):
         assert R.benchmark_error(pose, src.points[gs], tgt.points[gt]) == O.benchmark_error(pose, src.points[gs], tgt.points[gt])
     a, b = small_eth_pair[0].points[:3000], small_eth_pair[1].points[:3000]
     assert R.benchmark_error(_pose(1), a, b) == pytest.approx(O.benchmark_error(_pose(1), a, b), rel=1e-9)
+
+
+def test_pca_normals_equal_reference_constructor(small_eth_pair, bunny):
+    """PointCloud(pcl::PointCloud<PointXYZ>::Ptr) (PointCloud.h:41-76): k = 5 normals, colours (255,255,255,1).  PCL is
+    absent; the reference constructor runs over the PCL stand-in (exhaustive neighbours, published NormalEstimation
+    algorithm), so this pins the constructor's own logic and the oracle's restatement, not PCL's numerics."""
+    pts = small_eth_pair[1].points[::2].copy()
+    pts[7, 1] = np.nan
+    n_r, c_r = R.cloud_from_xyz(pts)
+    n_o, _ = O.pca_normals(pts, 5)
+    assert np.array_equal(n_r, n_o, equal_nan=True)
+    assert (c_r == [255, 255, 255, 1]).all() and np.isnan(n_o[7]).all()
+    ok = np.isfinite(n_o).all(1)
+    assert np.allclose(np.linalg.norm(n_o[ok], axis=1), 1.0, atol=1e-6)
+    assert ((-pts[ok] * n_o[ok]).sum(1) >= -1e-6).all()                # flipped towards the viewpoint (the origin)
+    n_b, _ = O.pca_normals(bunny[1].points, 5)
+    assert np.array_equal(R.cloud_from_xyz(bunny[1].points)[0], n_b, equal_nan=True)
