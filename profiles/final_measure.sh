@@ -9,3 +9,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"knn_prep|knn_bvh|reduce_kernel" -s 60 -c 3 -f -o gpurun_out/final/prof_hot python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/final/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"depth_cloud|metrics_pass1" -c 2 -f -o gpurun_out/final/prof_prep python -m pytest tests/test_gpu_prep_metrics.py -m gpu -q -k "bit_exact and 640 or all_points" > gpurun_out/final/ncu_prep.log 2>&1
 tail -2 gpurun_out/final/bench_n1.json | cut -c1-300
+python profiles/measure_sequence.py > gpurun_out/final/sequence.json 2> gpurun_out/final/sequence.err
+python profiles/measure_normals.py > gpurun_out/final/normals_depth.json 2> gpurun_out/final/normals_depth.err
+ncu --set full --clock-control none --import-source on -k regex:"projective|pca_normals" -s 10 -c 1 -f -o gpurun_out/final/prof_projective python profiles/profile_projective.py > gpurun_out/final/ncu_proj.log 2>&1
