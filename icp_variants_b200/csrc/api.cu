@@ -223,7 +223,7 @@ int build_grid(icp_gpu_ctx* ctx) {
     CU(icp_launch_refine_cells((const unsigned int*)ctx->cell_start.p, ctx->T, (const GridParams*)ctx->grid.p, (unsigned int*)ctx->keys.p,
                                (unsigned int)(n / 33 + 1), (unsigned int*)ctx->bbox.p + 8, (float4*)ctx->tgt_pts_sorted.p,
                                (float4*)ctx->tgt_nrm_sorted.p, n, ctx->n_sms, ctx->stream, &launches));
-    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, n, (const GridParams*)ctx->grid.p, (const unsigned int*)ctx->cell_start.p, ctx->T,
+    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, (const float4*)ctx->tgt_nrm_sorted.p, n, (const GridParams*)ctx->grid.p, (const unsigned int*)ctx->cell_start.p, ctx->T,
                             (unsigned int*)ctx->leaf_rank.p, (unsigned int*)ctx->block_sums.p, (unsigned int*)ctx->leaf_start.p,
                             (unsigned int*)ctx->node_rank.p, (unsigned int*)ctx->child_start.p, (unsigned int*)ctx->pstart.p,
                             (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ctx->stream, &launches));

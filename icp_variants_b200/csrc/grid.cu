@@ -475,7 +475,9 @@ __global__ void level_children_kernel(const unsigned int* __restrict__ leaf_star
 }
 
 // one warp per node (grid-stride): level 0 reads the leaf's points, level l > 0 reads its (<= 32) child boxes
-__global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ leaf_start,
+// The w components of the two box entries carry the node's COLOUR range (min / max of r, g, b as packed bytes), which the
+// 6-D colour search adds to its lower bounds (match.cu: box_dist2c).
+__global__ void bvh_level_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, const unsigned int* __restrict__ leaf_start,
                                  const unsigned int* __restrict__ child_start, const BvhDesc* __restrict__ bvh, float4* __restrict__ box,
                                  int level) {
     const BvhDesc b = *bvh;
@@ -484,23 +486,34 @@ __global__ void bvh_level_kernel(const float4* __restrict__ pts, const unsigned 
     const int count = b.count[level], offset = b.offset[level];
     for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < count; node += warps) {
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        unsigned int clo[3] = {255u, 255u, 255u}, chi[3] = {0u, 0u, 0u};
         if (level == 0) {
             const unsigned int i = leaf_start[node] + lane;
-            if (i < leaf_start[node + 1]) { const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
+            if (i < leaf_start[node + 1]) {
+                const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
+                const unsigned int c = __float_as_uint(nrm[i].w);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) clo[k] = chi[k] = (c >> (8 * k)) & 0xFFu;
+            }
         } else {
             const unsigned int c = child_start[b.coffset[level] + node] + lane;
             if (c < child_start[b.coffset[level] + node + 1]) {
                 const float4 u = box[2 * (size_t)(b.offset[level - 1] + c)], v = box[2 * (size_t)(b.offset[level - 1] + c) + 1];
                 lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; hi[0] = v.x; hi[1] = v.y; hi[2] = v.z;
+                const unsigned int cu = __float_as_uint(u.w), cv = __float_as_uint(v.w);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { clo[k] = (cu >> (8 * k)) & 0xFFu; chi[k] = (cv >> (8 * k)) & 0xFFu; }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { clo[k] = __reduce_min_sync(0xFFFFFFFFu, clo[k]); chi[k] = __reduce_max_sync(0xFFFFFFFFu, chi[k]); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
             for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
         if (lane == 0) {
-            box[2 * (size_t)(offset + node)] = make_float4(lo[0], lo[1], lo[2], 0.f);
-            box[2 * (size_t)(offset + node) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+            box[2 * (size_t)(offset + node)] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(clo[0] | (clo[1] << 8) | (clo[2] << 16)));
+            box[2 * (size_t)(offset + node) + 1] = make_float4(hi[0], hi[1], hi[2], __uint_as_float(chi[0] | (chi[1] << 8) | (chi[2] << 16)));
         }
     }
 }
@@ -638,7 +651,7 @@ size_t icp_bvh_max_nodes(int n) {
     return (size_t)(n > 0 ? n : 1) * 2 + 64;
 }
 
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
                                  unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
                                  unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
                                  cudaStream_t s, int* n_launches) {
@@ -648,7 +661,7 @@ cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridPara
     if (e != cudaSuccess) return e;
     leaf_starts_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(leaf_rank, n, cell_start, T, leaf_start, bvh_dev); ++launches;
     long long nb0 = ((long long)(n > 0 ? n : 1) + 7) / 8; if (nb0 > 8ll * n_sms) nb0 = 8ll * n_sms;
-    bvh_level_kernel<<<(int)nb0, 256, 0, s>>>(pts_sorted, leaf_start, child_start, bvh_dev, box, 0); ++launches;
+    bvh_level_kernel<<<(int)nb0, 256, 0, s>>>(pts_sorted, nrm_sorted, leaf_start, child_start, bvh_dev, box, 0); ++launches;
     // Upper levels: the node counts live on the device, so every possible level gets its (tiny) launches; the ones
     // past the top return at once.  An n-point cloud with healthy fill needs log_16(n / 16) levels; cap the launches there + 2.
     int max_levels = 2; { long long c = (n > 0 ? n : 1) / 16; while (c > 32 && max_levels < ICP_BVH_MAX_LEVELS) { c /= 8; ++max_levels; } }
@@ -658,7 +671,7 @@ cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridPara
         mark_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, grid, cell_start, T, leaf_start, leaf_rank, pstart, node_rank, bvh_dev, l); ++launches;
         scan_level_kernel<<<1, 1024, 0, s>>>(node_rank, bvh_dev, l); ++launches;
         level_children_kernel<<<nb, 256, 0, s>>>(leaf_start, node_rank, child_start, pstart, bvh_dev, l); ++launches;
-        bvh_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, leaf_start, child_start, bvh_dev, box, l); ++launches;
+        bvh_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, nrm_sorted, leaf_start, child_start, bvh_dev, box, l); ++launches;
     }
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();

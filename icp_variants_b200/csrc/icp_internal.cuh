@@ -172,7 +172,7 @@ cudaError_t icp_launch_refine_cells(const unsigned int* cell_start, int T, const
 // Tight-box BVH over the cell-sorted cloud.  leaf_rank: n + 2 entries (kept: maps a sorted position to its leaf);
 // leaf_start: n + 2; node_scratch / child_start / pstart: icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS entries each.
 size_t icp_bvh_max_nodes(int n);
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
                                  unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
                                  unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
                                  cudaStream_t s, int* n_launches);

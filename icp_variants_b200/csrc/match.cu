@@ -154,6 +154,22 @@ __device__ __forceinline__ float box_dist2(const Query& q, const float4 lo, cons
     return padd(padd(pmul(gx, gx), pmul(gy, gy)), pmul(gz, gz));
 }
 
+// The same for the 6-D colour search: the node's colour range (packed bytes in lo.w / hi.w, grid.cu) adds the squared gap
+// of every colour feature, accumulated in the order of dist6_tail, so the bound stays below the D1 distance of every point
+// of the node (the feature map and every rounding involved are monotone).
+template <bool COLOR>
+__device__ __forceinline__ float box_dist2c(const Query& q, const float4 lo, const float4 hi) {
+    float d = box_dist2(q, lo, hi);
+    if (COLOR) {
+        const unsigned int cl = __float_as_uint(lo.w), ch = __float_as_uint(hi.w);
+        const float gr = fmaxf(fmaxf(psub(color_feature(cl, 0), q.cr), psub(q.cr, color_feature(ch, 0))), 0.0f);
+        const float gg = fmaxf(fmaxf(psub(color_feature(cl, 1), q.cg), psub(q.cg, color_feature(ch, 1))), 0.0f);
+        const float gb = fmaxf(fmaxf(psub(color_feature(cl, 2), q.cb), psub(q.cb, color_feature(ch, 2))), 0.0f);
+        d = padd(d, pmul(gr, gr)); d = padd(d, pmul(gg, gg)); d = padd(d, pmul(gb, gb));
+    }
+    return d;
+}
+
 // Lane l proposes leaf `leaf` with box distance clb (keep = it can still matter): the proposed leaves are scanned
 // nearest first (lane = point) for as long as their box distance does not exceed the shrinking bound.
 template <bool COLOR>
@@ -193,7 +209,7 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
     float clb = FLT_BIG; bool keep = false;
     if (c < last) {
         const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
-        clb = box_dist2(q, lo, hi);
+        clb = box_dist2c<COLOR>(q, lo, hi);
         keep = !(clb > bound);
     }
     if (L == 0) { bvh_scan_leaves<COLOR>(a, q, b, bound, c, clb, keep, lane, ev, nd); return; }
@@ -264,13 +280,13 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
                             unsigned int todo = 0;
                             for (int j = 0; j < na; ++j) {
                                 const unsigned int leaf = __ldg(&list[j]);
-                                const float clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                                const float clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
                                 if (!(clb > b.d)) todo |= 1u << j;
                             }
                             while (todo) {
                                 const int j = __ffs((int)todo) - 1; todo &= todo - 1u;
                                 const unsigned int leaf = __ldg(&list[j]);
-                                const float clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                                const float clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
                                 if (!(clb > b.d)) { thread_scan_leaf<COLOR>(a, q, b, bleaf, leaf, ev); ++nd; }
                             }
                             ++nd;
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                     unsigned int leaf = 0; float clb = FLT_BIG; bool keep = false;
                     if (lane < na) {
                         leaf = __ldg(&a.adj[(size_t)seed_leaf * 32 + lane]);
-                        clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                        clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
                         keep = !(clb > bnd);
                     }
                     if (lane == 0) ++nd;
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                     unsigned int node = 0; unsigned int key = 0xFFFFFFFFu;
                     if (lane < na) {
                         node = __ldg(&a.adj1[(size_t)m * 32 + lane]);
-                        const float clb = box_dist2(q, __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node)]), __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node) + 1]));
+                        const float clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node)]), __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node) + 1]));
                         if (!(clb > bnd)) key = __float_as_uint(clb);
                     }
                     if (lane == 0) ++nd;
@@ -399,7 +415,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                     unsigned int key = 0xFFFFFFFFu;
                     if (c < last) {
                         const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
-                        key = __float_as_uint(box_dist2(q, lo, hi));
+                        key = __float_as_uint(box_dist2c<COLOR>(q, lo, hi));
                     }
                     const unsigned int kmin = __reduce_min_sync(FULL, key);
                     if (kmin < kbest) { kbest = kmin; best_node = base + (unsigned int)(__ffs((int)__ballot_sync(FULL, key == kmin)) - 1); }
