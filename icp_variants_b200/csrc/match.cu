@@ -10,7 +10,10 @@
 // NearestNeighborSearchBruteForce's scan order (NearestNeighbor.h:81-97) yields on squared distances.
 //
 // k-NN kernels:
-//   knn_bvh_kernel    one warp per query walks a 32-ary bounding-volume hierarchy over the cell-sorted target
+//   knn_prep_kernel   one thread per query: selection predicate + transform, and the FAST PATH: a query that remembers a
+//                     neighbour scans that neighbour's leaf and, if its search ball stays inside the leaf's inflated box,
+//                     the leaves of the leaf's adjacency list -- ~75 % of the queries end here.
+//   knn_bvh_kernel    the rest: one warp per query walks a 32-ary bounding-volume hierarchy over the cell-sorted target
 //                     (grid.cu) depth-first with an explicit shared-memory stack.  Leaves are the nodes of the
 //                     implicit cell tree with <= 32 points (disjoint aligned cells, TIGHT boxes); an internal
 //                     node groups 32 consecutive nodes of the level below.  One step tests the 32 children of a
@@ -18,7 +21,10 @@
 //                     32 lanes in parallel (lane = point, one coalesced 512 B read) with a warp arg-min at the end.
 //                     Every query starts from an upper bound: the neighbour it had the last time it was matched
 //                     (the pose moves little between ICP iterations), else the distance threshold.
+//                     In the 6-D colour search every node also carries its colour range, added to the lower bounds.
 //   knn_brute_kernel  small targets: one warp per query over the whole target, warp-shuffle arg-min.
+//   projective_kernel one thread per query over its 25 x 25 pixel window, staged in shared memory per block
+//                     (32 x 8 pixel tiles of a full-frame source, else 256 Morton-consecutive points).
 #include "icp_internal.cuh"
 #include <limits.h>
 
@@ -124,21 +130,6 @@ __device__ __forceinline__ bool prepare_query(const MatchArgs& a, const IterDesc
     s_rgba = __float_as_uint(n4.w);
     q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
     return true;
-}
-
-// Initial bound of a search: the distance threshold (D3), tightened by the neighbour this query had before.
-template <bool COLOR>
-__device__ __forceinline__ void seed_best(const MatchArgs& a, const Query& q, int p, Best& b) {
-    b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
-    if (a.use_seed) {
-        const int sp = a.nn_pos[p];
-        if (sp >= 0 && sp < a.n_tgt) {
-            const float4 c = __ldg(&a.tgt_pts[sp]);
-            const float d = dist2<COLOR>(q, c, b.d, a.tgt_nrm, (unsigned int)sp);
-            const int idx = __float_as_int(c.w);
-            if (better(d, idx, b)) { b.d = d; b.idx = idx; b.pos = sp; }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------- BVH search, one warp per query
