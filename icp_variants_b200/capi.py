@@ -19,8 +19,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libicp_gpu.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "icp_gpu.h")
 
-OK, E_CUDA, E_ARG, E_STATE, E_NO_MATCHES, E_NUMERIC = 0, -1, -2, -3, -4, -5
+OK, E_CUDA, E_ARG, E_STATE, E_NO_MATCHES, E_NUMERIC, E_PEER = 0, -1, -2, -3, -4, -5, -6
 MAX_PARTIALS = 32
+MAX_PEERS, PEER_HANDLE_BYTES = 8, 64
 
 
 class IcpGpuError(RuntimeError):
@@ -47,7 +48,7 @@ class Timings(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_queries", C.c_uint64), ("n_matched", C.c_uint64), ("n_distance_evals", C.c_uint64),
-                ("n_nodes_visited", C.c_uint64), ("n_kernel_launches", C.c_uint64)]
+                ("n_nodes_visited", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("reduce_profile_ns", C.c_uint64 * 6)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -117,6 +118,11 @@ def lib():
             "icp_gpu_iteration_end": (C.c_int, [vp, pf]),
             "icp_gpu_iteration_local_dev": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(i32)]),
             "icp_gpu_iteration_apply_dev": (C.c_int, [vp, C.c_int]),
+            "icp_gpu_peer_export": (C.c_int, [vp, pf]),
+            "icp_gpu_peer_attach": (C.c_int, [vp, i32, i32, pf]),
+            "icp_gpu_peer_address": (C.c_int, [vp, C.POINTER(vp)]),
+            "icp_gpu_peer_attach_ptrs": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),
+            "icp_gpu_peer_detach": (C.c_int, [vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -361,3 +367,30 @@ class Context:
         p = np.empty(16, np.float32)
         self._check(lib().icp_gpu_iteration_end(self._h, _ptr(p)))
         return pose_from_c(p)
+
+    # -- point-sharded registration with the exchange inside the reduction kernel (peer memory)
+    def peer_export(self) -> bytes:
+        """(Re)creates this context's mailbox; returns its 64-byte CUDA IPC handle for the other ranks."""
+        h = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._check(lib().icp_gpu_peer_export(self._h, h))
+        return h.raw
+
+    def peer_attach(self, rank: int, world: int, handles):
+        """handles: the `world` handles in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != world * PEER_HANDLE_BYTES:
+            raise ValueError(f"expected {world} handles of {PEER_HANDLE_BYTES} bytes")
+        self._check(lib().icp_gpu_peer_attach(self._h, rank, world, C.c_char_p(blob)))
+
+    def peer_address(self) -> int:
+        """(Re)creates this context's mailbox; returns its device address (contexts of one process)."""
+        p = C.c_void_p()
+        self._check(lib().icp_gpu_peer_address(self._h, C.byref(p)))
+        return int(p.value)
+
+    def peer_attach_ptrs(self, rank: int, world: int, addresses):
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(a)) for a in addresses])
+        self._check(lib().icp_gpu_peer_attach_ptrs(self._h, rank, world, arr))
+
+    def peer_detach(self):
+        self._check(lib().icp_gpu_peer_detach(self._h))

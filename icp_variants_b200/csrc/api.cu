@@ -106,6 +106,12 @@ struct icp_gpu_ctx {
     bool pending = false; int pending_iters = 0;
     // shard iteration state
     bool shard_open = false; int shard_algo = 0, shard_iters = 0;
+    // point-sharded registration over peer memory (icp_gpu_peer_*)
+    void* peer_box = nullptr;                               // own mailbox (plain cudaMalloc: exportable through CUDA IPC)
+    void* peer_ptr[ICP_MAX_PEERS] = {nullptr};              // every rank's mailbox as mapped here
+    bool peer_ipc[ICP_MAX_PEERS] = {false};                 // opened with cudaIpcOpenMemHandle (to be closed)
+    int peer_world = 0, peer_rank = 0;
+    uint64_t peer_epoch = 0;                                // part of the graph key: a new attachment is a new graph
     icp_gpu_stats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     char err[512];
@@ -432,6 +438,14 @@ void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     r.desc = (const IterDesc*)c->desc.p; r.desc_index = -1;
     r.weighting = c->cfg.weighting; r.rejection = c->cfg.rejection; r.max_d2 = c->cfg.max_distance_sq;
     if (proj_tiled(c, algo)) { r.src_pts = (const float4*)c->src_raw_pts.p; r.src_nrm = (const float4*)c->src_raw_nrm.p; }
+    r.profile = getenv("ICP_GPU_REDUCE_PROFILE") ? 1 : 0;   // diagnostic
+    if (solve && c->peer_world > 1) {
+        r.peer.world = c->peer_world; r.peer.rank = c->peer_rank;
+        unsigned long long ms = 2000;
+        if (const char* e = getenv("ICP_GPU_PEER_TIMEOUT_MS")) { const long long v = atoll(e); if (v >= 1 && v <= 600000) ms = (unsigned long long)v; }
+        r.peer.timeout_ns = ms * 1000000ull;
+        for (int j = 0; j < c->peer_world; ++j) r.peer.box[j] = (PeerBox*)c->peer_ptr[j];
+    }
 }
 
 // Enqueue the whole loop.  ev_marks (nullable): events recorded around each stage for the timings report.
@@ -506,6 +520,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         for (int k = 0; k < 9; ++k) key.push_back((long long)__float_as_int_host(ctx->have_camera ? ctx->K[k] : 0.f));
         key.push_back((long long)(uintptr_t)ctx->mask.p); key.push_back((long long)(uintptr_t)ctx->stream);
         key.push_back(plan.n_iters);
+        key.push_back(ctx->peer_world); key.push_back(ctx->peer_rank); key.push_back((long long)ctx->peer_epoch);
         if (!ctx->graph_exec || key != ctx->graph_key) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -559,6 +574,7 @@ void copy_counters(icp_gpu_ctx* ctx) {
     const DevState& st = *ctx->h_state;
     ctx->stats.n_queries = st.n_queries; ctx->stats.n_matched = st.n_matched;
     ctx->stats.n_distance_evals = st.n_evals; ctx->stats.n_nodes_visited = st.n_nodes;
+    for (int k = 0; k < 6; ++k) ctx->stats.reduce_profile_ns[k] = st.prof[k];
 }
 
 int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out) {
@@ -575,8 +591,29 @@ int finish_registration(icp_gpu_ctx* ctx, float pose_out[16], float* pose_histor
     copy_counters(ctx);
     if (st.status == ICP_GPU_E_NO_MATCHES)
         return fail(ctx, ICP_GPU_E_NO_MATCHES, "iteration %d had no surviving correspondence (the reference hangs in ASSERT here)", st.iters_done);
+    if (st.status == ICP_GPU_E_PEER)
+        return fail(ctx, ICP_GPU_E_PEER, "point-sharded registration: a peer's row did not arrive in time (iteration %d; rank %d of %d)", st.iters_done, ctx->peer_rank, ctx->peer_world);
     if (st.status != 0) return fail(ctx, st.status, "iteration %d: singular / non-finite normal equations", st.iters_done);
     return ICP_GPU_OK;
+}
+
+void peer_close(icp_gpu_ctx* ctx) {
+    for (int j = 0; j < ICP_MAX_PEERS; ++j) {
+        if (ctx->peer_ipc[j] && ctx->peer_ptr[j]) { if (cudaIpcCloseMemHandle(ctx->peer_ptr[j]) != cudaSuccess) cudaGetLastError(); }
+        ctx->peer_ptr[j] = nullptr; ctx->peer_ipc[j] = false;
+    }
+    ctx->peer_world = 0; ctx->peer_rank = 0; ctx->peer_epoch += 1;
+}
+
+// (Re)creates the mailbox in its initial state: no row received, exchange counter 0.
+int peer_reset_box(icp_gpu_ctx* ctx) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    peer_close(ctx);
+    if (!ctx->peer_box) CU(cudaMalloc(&ctx->peer_box, sizeof(PeerBox)));
+    CU(cudaMemsetAsync(ctx->peer_box, 0, sizeof(PeerBox), ctx->stream));
+    CU(cudaMemsetAsync(&((DevState*)ctx->state.p)->xchg_seq, 0, sizeof(unsigned int), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 }  // namespace
@@ -642,6 +679,8 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    peer_close(ctx);
+    if (ctx->peer_box) cudaFree(ctx->peer_box);
     DeviceBuf* bufs[] = {&ctx->stage, &ctx->stage2, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
@@ -959,6 +998,7 @@ int icp_gpu_iteration_begin(icp_gpu_ctx* ctx, const float pose_in[16]) {
     if (!ctx || !pose_in) return ICP_GPU_E_ARG;
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
     if (ctx->cfg.minimizer != ICP_GPU_MIN_LINEAR) return fail(ctx, ICP_GPU_E_ARG, "the point-sharded path supports the linear minimiser only");
+    if (ctx->peer_world > 1) return fail(ctx, ICP_GPU_E_STATE, "peers are attached: icp_gpu_estimate_pose is the point-sharded registration (icp_gpu_peer_detach first)");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
     IterDesc d; memset(&d, 0, sizeof(d));
@@ -1034,6 +1074,73 @@ int icp_gpu_iteration_end(icp_gpu_ctx* ctx, float pose_out[16]) {
     memcpy(pose_out, ctx->h_state->pose, 16 * sizeof(float));
     if (ctx->h_state->status == ICP_GPU_E_NO_MATCHES) return fail(ctx, ICP_GPU_E_NO_MATCHES, "no surviving correspondence on any rank");
     if (ctx->h_state->status != 0) return fail(ctx, ctx->h_state->status, "singular / non-finite normal equations");
+    return ICP_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------- point-sharded registration over peer memory
+int icp_gpu_peer_export(icp_gpu_ctx* ctx, void* handle_out) {
+    if (!ctx || !handle_out) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    static_assert(sizeof(cudaIpcMemHandle_t) == ICP_GPU_PEER_HANDLE_BYTES, "handle size");
+    if (peer_reset_box(ctx)) return ICP_GPU_E_CUDA;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->peer_box));
+    memcpy(handle_out, &h, sizeof(h));
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_peer_address(icp_gpu_ctx* ctx, void** mailbox_dev) {
+    if (!ctx || !mailbox_dev) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    if (peer_reset_box(ctx)) return ICP_GPU_E_CUDA;
+    *mailbox_dev = ctx->peer_box;
+    return ICP_GPU_OK;
+}
+
+static int peer_attach_common(icp_gpu_ctx* ctx, int32_t rank, int32_t world, const void* handles, void* const* ptrs) {
+    if (!ctx || (!handles && !ptrs)) return ICP_GPU_E_ARG;
+    if (world < 1 || world > ICP_MAX_PEERS || rank < 0 || rank >= world) return fail(ctx, ICP_GPU_E_ARG, "rank %d of world %d (max %d)", rank, world, ICP_MAX_PEERS);
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (!ctx->peer_box) return fail(ctx, ICP_GPU_E_STATE, "icp_gpu_peer_export / icp_gpu_peer_address not called");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    CU(cudaStreamSynchronize(ctx->stream));
+    peer_close(ctx);
+    for (int j = 0; j < world; ++j) {
+        if (j == rank) { ctx->peer_ptr[j] = ctx->peer_box; continue; }
+        if (ptrs) {
+            if (!ptrs[j]) { peer_close(ctx); return fail(ctx, ICP_GPU_E_ARG, "mailbox %d is null", j); }
+            ctx->peer_ptr[j] = ptrs[j];
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles + (size_t)j * ICP_GPU_PEER_HANDLE_BYTES, sizeof(h));
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); peer_close(ctx); return fail(ctx, ICP_GPU_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", j, cudaGetErrorString(e)); }
+            ctx->peer_ptr[j] = p; ctx->peer_ipc[j] = true;
+        }
+    }
+    ctx->peer_world = world; ctx->peer_rank = rank;
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_peer_attach(icp_gpu_ctx* ctx, int32_t rank, int32_t world, const void* handles) {
+    if (!handles) return ICP_GPU_E_ARG;
+    return peer_attach_common(ctx, rank, world, handles, nullptr);
+}
+
+int icp_gpu_peer_attach_ptrs(icp_gpu_ctx* ctx, int32_t rank, int32_t world, void* const* mailboxes_dev) {
+    if (!mailboxes_dev) return ICP_GPU_E_ARG;
+    return peer_attach_common(ctx, rank, world, nullptr, mailboxes_dev);
+}
+
+int icp_gpu_peer_detach(icp_gpu_ctx* ctx) {
+    if (!ctx) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    CU(cudaStreamSynchronize(ctx->stream));
+    peer_close(ctx);
     return ICP_GPU_OK;
 }
 

@@ -18,6 +18,7 @@
 #define ICP_MAX_ITERS 256          // upper bound on iterations per estimate_pose call
 #define ICP_NRED 32                // doubles per partial-sum row (27..30 used)
 #define ICP_REDUCE_THREADS 256
+#define ICP_MAX_PEERS 8            // ranks of one point-sharded registration (one B200 box); <= ICP_REDUCE_THREADS / 32
 #define ICP_MATCH_THREADS 128
 #define ICP_LEAF_MAX 8             // a grid node with <= this many points is scanned, not split
 #define ICP_CELLS_PER_POINT 32      // target grid: cells per point (2^T >= this x N); the finer, the more compact the BVH leaves
@@ -93,6 +94,25 @@ struct DevState {
     double lm_radius, lm_decrease, lm_model_change;
     int lm_iter, lm_done, lm_reuse_diag, lm_invalid, lm_step_ok, lm_have_cand;
     double shard_partials[ICP_NRED];
+    unsigned int xchg_seq;   // peer exchanges completed since the mailboxes were attached (never reset by pose_init)
+    int pad_xchg;
+    unsigned long long prof[6];   // ReduceArgs::profile: %globaltimer marks of the last reduction launch (icp_gpu_stats)
+};
+
+// Point-sharded registration over peer memory (NVLink): every rank owns one mailbox; the last block of a reduction
+// STORES its summed row straight into every peer's mailbox and waits for the peers' rows in its own -- the all-reduce of
+// the <= 32 doubles is part of the reduction kernel, nothing returns to the host between iterations.
+// Two slots (exchange number & 1): a rank can be at most one exchange ahead of a peer, because finishing exchange k
+// needs every peer's row k, which a peer only sends after it has read all rows of exchange k-1.
+struct PeerBox {
+    double row[2][ICP_MAX_PEERS][ICP_NRED];
+    unsigned int flag[2][ICP_MAX_PEERS];       // exchange number whose row is complete
+};
+
+struct PeerXchg {
+    int world, rank;                   // world <= 1: no exchange
+    unsigned long long timeout_ns;     // a peer that does not show up raises ICP_GPU_E_PEER instead of hanging the GPU
+    PeerBox* box[ICP_MAX_PEERS];       // box[j] = rank j's mailbox as mapped into this process (box[rank] = own)
 };
 
 struct MatchArgs {
@@ -154,6 +174,8 @@ struct ReduceArgs {
     // instead of being read back from the match records (saves the match_finish launch); linear minimiser only
     int fused; const int* nn_pos; int n_tgt; const unsigned int* mask; const IterDesc* desc; int desc_index;
     int weighting, rejection; float max_d2;
+    int profile;             // write DevState::prof (diagnostic, ICP_GPU_REDUCE_PROFILE=1)
+    PeerXchg peer;           // world > 1: the summed row is all-reduced over the peers' mailboxes before the solve
 };
 
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
@@ -387,9 +409,70 @@ static __device__ void apply_increment(DevState* st, const float* inc, int rc, f
 // partials[block][32]; the block that draws the last ticket sums all rows in a fixed order
 // (deterministic, no floating-point atomics).  Returns true in every thread of that last block,
 // with the total in fin[0][0..31].  red: [THREADS/32][32], fin: [THREADS/32][32] shared scratch.
+// ---- all-reduce of the summed row over the peers' mailboxes (NVLink peer memory), run by the last block ----
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Called by every thread of the last block with the local total in fin[0][0..31]; returns with the sum over all ranks
+// there, added in rank order on every rank (=> bit-identical rows, identical solves, identical poses: no broadcast).
+// Warp j (j < world, j != rank) serves peer j: it pushes the local row into rank j's mailbox (remote stores, then a
+// system-scope fence and a release store of the exchange number) and then polls its own mailbox for rank j's row.
+template <int THREADS>
+__device__ __forceinline__ void peer_exchange_row(const PeerXchg& px, DevState* st, double (*red)[32], double (*fin)[32]) {
+    static_assert(THREADS / 32 >= ICP_MAX_PEERS, "one warp per peer");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned int seq = st->xchg_seq + 1u;     // written back by thread 0 after the last read below
+    const int slot = (int)(seq & 1u);
+    bool timed_out = false;
+    if (w < px.world) {
+        if (w != px.rank) {
+            PeerBox* theirs = px.box[w];
+            theirs->row[slot][px.rank][lane] = fin[0][lane];
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) st_release_sys_u32(&theirs->flag[slot][px.rank], seq);
+            const PeerBox* mine = px.box[px.rank];
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys_u32(&mine->flag[slot][w]) != seq) {
+                if (global_timer_ns() - t0 > px.timeout_ns) { timed_out = true; break; }
+                __nanosleep(64);
+            }
+            red[w][lane] = ld_relaxed_sys_f64(&mine->row[slot][w][lane]);
+        } else {
+            red[w][lane] = fin[0][lane];
+        }
+    }
+    if (timed_out && lane == 0) atomicCAS(&st->status, 0, ICP_GPU_E_PEER);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int j = 0; j < px.world; ++j) s += red[j][threadIdx.x];
+        fin[0][threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) st->xchg_seq = seq;
+    __syncthreads();
+}
+
 template <int THREADS>
 __device__ __forceinline__ bool grid_reduce_row(double (&v)[32], double* __restrict__ partials, unsigned int* ticket,
-                                                double (*red)[32], double (*fin)[32], bool* is_last) {
+                                                double (*red)[32], double (*fin)[32], bool* is_last,
+                                                const PeerXchg* px = nullptr, DevState* px_state = nullptr) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     warp_reduce_scatter32(v, lane);
     red[wid][lane] = v[0];
@@ -411,18 +494,24 @@ __device__ __forceinline__ bool grid_reduce_row(double (&v)[32], double* __restr
     __threadfence();
     {
         const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-        // fixed order (deterministic); four independent chains so that the loads overlap
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        // fixed order (deterministic); eight independent chains so that the loads of a whole pass are in flight at
+        // once -- the last block is alone on the critical path of every iteration, each pass costs one L2 round trip
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
         const int step = THREADS / 32, nb = (int)gridDim.x;
         int b = g;
-        for (; b + 3 * step < nb; b += 4 * step) {
-            s0 += __ldcg(&partials[(size_t)b * ICP_NRED + c]);
-            s1 += __ldcg(&partials[(size_t)(b + step) * ICP_NRED + c]);
-            s2 += __ldcg(&partials[(size_t)(b + 2 * step) * ICP_NRED + c]);
-            s3 += __ldcg(&partials[(size_t)(b + 3 * step) * ICP_NRED + c]);
+        for (; b + 7 * step < nb; b += 8 * step) {
+            const double x0 = __ldcg(&partials[(size_t)b * ICP_NRED + c]);
+            const double x1 = __ldcg(&partials[(size_t)(b + step) * ICP_NRED + c]);
+            const double x2 = __ldcg(&partials[(size_t)(b + 2 * step) * ICP_NRED + c]);
+            const double x3 = __ldcg(&partials[(size_t)(b + 3 * step) * ICP_NRED + c]);
+            const double x4 = __ldcg(&partials[(size_t)(b + 4 * step) * ICP_NRED + c]);
+            const double x5 = __ldcg(&partials[(size_t)(b + 5 * step) * ICP_NRED + c]);
+            const double x6 = __ldcg(&partials[(size_t)(b + 6 * step) * ICP_NRED + c]);
+            const double x7 = __ldcg(&partials[(size_t)(b + 7 * step) * ICP_NRED + c]);
+            s0 += x0; s1 += x1; s2 += x2; s3 += x3; s4 += x4; s5 += x5; s6 += x6; s7 += x7;
         }
         for (; b < nb; b += step) s0 += __ldcg(&partials[(size_t)b * ICP_NRED + c]);
-        fin[g][c] = (s0 + s1) + (s2 + s3);
+        fin[g][c] = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -433,5 +522,6 @@ __device__ __forceinline__ bool grid_reduce_row(double (&v)[32], double* __restr
     }
     __syncthreads();
     if (threadIdx.x == 0) *ticket = 0;
+    if (px && px->world > 1) peer_exchange_row<THREADS>(*px, px_state, red, fin);
     return true;
 }

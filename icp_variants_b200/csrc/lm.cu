@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) lm_eval_kernel(const Reduc
             }
         }
     }
-    if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last)) return;
+    if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last, &a.peer, a.state)) return;
     if (threadIdx.x == 0) lm_advance(a.state, fin[0], step_index, max_iterations, a.pose_history);
 }
 

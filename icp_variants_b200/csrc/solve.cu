@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     __shared__ double red[ICP_REDUCE_THREADS / 32][32];
     __shared__ double fin[ICP_REDUCE_THREADS / 32][32];
     __shared__ bool is_last;
+    unsigned long long t_start = 0, t_loop = 0;
+    if (a.profile && threadIdx.x == 0) { t_start = global_timer_ns(); if (blockIdx.x == 0) a.state->prof[0] = t_start; }
     if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
     if (threadIdx.x >= 64 && threadIdx.x < 73) Nm[threadIdx.x - 64] = a.state->nrm[threadIdx.x - 64];
@@ -244,30 +246,50 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     // queries are addressed by their position in the Morton-sorted source
     IterDesc d; d.stride = 1; d.filter_finite = 0; d.mask_word_offset = -1; d.rng_key = 0u; d.proba = -1.0f;
     if (FUSED) d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state->iter];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += gridDim.x * blockDim.x) {
-        int pos; float wf; float4 sp, tp, tn = make_float4(0.f, 0.f, 0.f, 0.f), sn4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Software pipeline over the thread's points: the loads that depend on nothing (search result / match record,
+    // source point and normal) are issued one point ahead, so the only latency a point exposes is its gather of the
+    // matched target point -- the kernel is latency-bound (4 warps per scheduler at 128 registers), not HBM-bound.
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int pos_n = -1; float wf_n = 0.f;
+    float4 sp_n = make_float4(0.f, 0.f, 0.f, 0.f), sn_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < a.n_src) {
+        pos_n = FUSED ? a.nn_pos[i] : a.match_pos[i];
+        sp_n = __ldg(&a.src_pts[i]);
+        if (FUSED || MODE == 2) sn_n = __ldg(&a.src_nrm[i]);
+        if (!FUSED) wf_n = a.match_w[i];
+    }
+    for (; i < a.n_src; i += stride) {
+        const int pos = pos_n; float wf = wf_n; const float4 sp = sp_n, sn4 = sn_n;
+        // a query without a (surviving) match has pos -1
+        const bool gather = pos >= 0 && (!FUSED || pos < a.n_tgt);
+        float4 tp = make_float4(0.f, 0.f, 0.f, 0.f), tn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gather) {
+            tp = __ldg(&a.tgt_pts[pos]);
+            if (FUSED || MODE == 1 || MODE == 2) tn = __ldg(&a.tgt_nrm[pos]);
+        }
+        {
+            const int i2 = i + stride;
+            if (i2 < a.n_src) {
+                pos_n = FUSED ? a.nn_pos[i2] : a.match_pos[i2];
+                sp_n = __ldg(&a.src_pts[i2]);
+                if (FUSED || MODE == 2) sn_n = __ldg(&a.src_nrm[i2]);
+                if (!FUSED) wf_n = a.match_w[i2];
+            }
+        }
+        if (!gather) continue;
         float sxf, syf, szf;
         if (FUSED) {
             // stages 3-4 evaluated here from the search result (same code path as match_finish_kernel)
-            pos = a.nn_pos[i];
-            sp = __ldg(&a.src_pts[i]); sn4 = __ldg(&a.src_nrm[i]);
-            if (pos < 0 || pos >= a.n_tgt || !query_active(d, a.mask, sp, sn4)) continue;
+            if (!query_active(d, a.mask, sp, sn4)) continue;
             xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
             if (!finite3(sxf, syf, szf)) continue;
-            tp = __ldg(&a.tgt_pts[pos]); tn = __ldg(&a.tgt_nrm[pos]);
             float nx, ny, nz;
             xform_normal(Nm, sn4.x, sn4.y, sn4.z, nx, ny, nz);
             wf = 1.0f;
             if (!match_weight_and_reject(a.weighting, a.rejection, a.max_d2, sxf, syf, szf, nx, ny, nz, __float_as_uint(sn4.w), tp, tn, wf)) continue;
         } else {
-            pos = a.match_pos[i];                       // a query without a surviving match has pos -1
-            if (pos < 0) continue;
-            sp = __ldg(&a.src_pts[i]);
             xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
-            tp = __ldg(&a.tgt_pts[pos]);
-            wf = a.match_w[i];
-            if (MODE == 1 || MODE == 2) tn = __ldg(&a.tgt_nrm[pos]);
-            if (MODE == 2) sn4 = __ldg(&a.src_nrm[i]);
         }
         if (!finite3(sxf, syf, szf) || !finite3(tp.x, tp.y, tp.z)) continue;        // ICPOptimizer.h:590-592
         const double w = (double)wf;
@@ -342,11 +364,14 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
             v[27] += 1.0;
         }
     }
-    if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last)) return;
+    if (a.profile && threadIdx.x == 0) t_loop = global_timer_ns();
+    if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last, a.solve ? &a.peer : nullptr, a.state)) return;
     if (threadIdx.x == 0) {
+        if (a.profile) { a.state->prof[1] = t_start; a.state->prof[2] = t_loop; a.state->prof[3] = global_timer_ns(); }
         if (!a.solve) { for (int k = 0; k < ICP_NRED; ++k) a.state->shard_partials[k] = fin[0][k]; }
         else if (MODE == 3) finish_sums(a.state, fin[0]);
         else finish_row(a.state, fin[0], MODE, a.pose_history);
+        if (a.profile) { __threadfence(); a.state->prof[4] = global_timer_ns(); }
     }
 }
 

@@ -4,8 +4,11 @@ partitioned.  No kernel lives here.
   * a SEQUENCE of independent scan pairs (alignETH's loop, main.cpp:411-498): pairs are dealt to ranks, every
     rank runs its own queue on its own context -- no collective on the data path;
   * ONE very large pair: every rank holds the whole target and a contiguous shard of the source; per iteration
-    the ranks' partial normal-equation rows (<= 28 doubles) are summed with one all-reduce and every rank solves
-    the identical system (icp_gpu_iteration_local / _apply).
+    the ranks' partial normal-equation rows (<= 28 doubles) are summed and every rank solves the identical system.
+    Two transports: (a) `attach_peers` + the ordinary `estimate_pose` -- the exchange runs INSIDE the reduction
+    kernel over NVLink peer memory (icp_gpu_peer_*; the loop stays one CUDA graph, nothing returns to the host
+    between iterations); (b) `register_sharded` -- one NCCL / gloo all-reduce per iteration through the host
+    (icp_gpu_iteration_local / _apply), kept as the portable baseline the fused path is measured against.
 """
 from __future__ import annotations
 
@@ -54,3 +57,20 @@ def register_sharded(ctx, n_iterations: int, init_pose=None) -> np.ndarray:
         for phase in range(ctx.iteration_phases()):
             ctx.iteration_apply(phase, allreduce_sum(ctx.iteration_local(phase)))
     return ctx.iteration_end()
+
+
+def gather_peer_handles(handle: bytes) -> list[bytes]:
+    """Every rank's mailbox handle in rank order (the collective that doubles as the export -> attach barrier)."""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, bytes(handle))
+    return [bytes(h) for h in out]
+
+
+def attach_peers(ctx) -> None:
+    """Collective: after it, `ctx.estimate_pose()` on every rank is ONE point-sharded registration (each rank holds
+    the whole target and its shard of the source) whose per-iteration all-reduce is fused into the reduction kernel."""
+    import torch.distributed as dist
+    handles = gather_peer_handles(ctx.peer_export())
+    ctx.peer_attach(dist.get_rank(), dist.get_world_size(), handles)
+    dist.barrier()      # nobody starts a registration before every rank has opened every mailbox

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ICP_GPU_ABI_VERSION 2
+#define ICP_GPU_ABI_VERSION 3
 
 enum {
     ICP_GPU_OK = 0,
@@ -41,7 +41,8 @@ enum {
     ICP_GPU_E_STATE = -3,      /* call order: no target / source / camera set for what was asked    */
     ICP_GPU_E_NO_MATCHES = -4, /* an iteration had no surviving correspondence (reference: hangs in
                                   ASSERT, ICPOptimizer.h:668,680,788); pose is the last good one    */
-    ICP_GPU_E_NUMERIC = -5     /* singular normal equations                                         */
+    ICP_GPU_E_NUMERIC = -5,    /* singular normal equations                                         */
+    ICP_GPU_E_PEER = -6        /* point-sharded registration: a peer's row did not arrive in time   */
 };
 
 /* ICPOptimizer::setMetric (ICPOptimizer.h:46): 0 point-to-point, 1 point-to-plane, 2 symmetric   */
@@ -116,6 +117,10 @@ typedef struct icp_gpu_stats {
     uint64_t n_distance_evals; /* point-to-point squared distances evaluated by the search         */
     uint64_t n_nodes_visited;  /* BVH nodes entered (internal nodes and leaves)                    */
     uint64_t n_kernel_launches;/* kernels launched by this library in the call                     */
+    uint64_t reduce_profile_ns[6]; /* ICP_GPU_REDUCE_PROFILE=1 (environment): device timestamps (%globaltimer, ns) of the LAST
+                                      reduction launch -- [0] first block starts, [1] the block that ends up last starts,
+                                      [2] its point loop is done, [3] all rows summed (and exchanged with the peers),
+                                      [4] system solved and pose written; else 0                        */
 } icp_gpu_stats;
 
 typedef struct icp_gpu_ctx icp_gpu_ctx;
@@ -226,6 +231,31 @@ int icp_gpu_iteration_end(icp_gpu_ctx* ctx, float pose_out[16]);
  * returns the device address of the context's partial-sum buffer (ICP_GPU_MAX_PARTIALS doubles). */
 int icp_gpu_iteration_local_dev(icp_gpu_ctx* ctx, int phase, double** partials_dev, int32_t* n_values);
 int icp_gpu_iteration_apply_dev(icp_gpu_ctx* ctx, int phase);
+
+
+/* The same registration with the exchange INSIDE the reduction kernel (no NCCL call, no host round trip per
+ * iteration): every rank owns a small mailbox in device memory; the last block of each reduction stores its summed
+ * row into every peer's mailbox over NVLink peer memory, waits for the peers' rows in its own, adds the rows in
+ * rank order (bit-identical totals, hence identical poses on every rank) and solves.  Once the peers are attached,
+ * icp_gpu_estimate_pose[_async] IS the point-sharded registration: a collective call -- every rank makes it with
+ * the same configuration, the whole target and its own shard of the source -- whose loop is one CUDA graph.
+ *   icp_gpu_peer_export       allocates (or resets) this context's mailbox and returns a 64-byte handle
+ *                             (cudaIpcMemHandle_t) the caller hands to the other ranks (MPI / torch.distributed);
+ *   icp_gpu_peer_attach       handles = world x 64 bytes in rank order; opens the peers' mailboxes;
+ *   icp_gpu_peer_address / icp_gpu_peer_attach_ptrs
+ *                             the same for contexts of ONE process (device addresses instead of handles; devices
+ *                             other than the context's own need peer access enabled by the caller);
+ *   icp_gpu_peer_detach       back to a single-context registration.
+ * Every rank must export before any rank attaches, and all ranks attach before the first registration (the handle
+ * exchange is that barrier).  A rank whose peer does not arrive within ICP_GPU_PEER_TIMEOUT_MS (environment,
+ * default 2000) finishes with ICP_GPU_E_PEER instead of hanging.  world <= ICP_GPU_MAX_PEERS. */
+#define ICP_GPU_MAX_PEERS 8
+#define ICP_GPU_PEER_HANDLE_BYTES 64
+int icp_gpu_peer_export(icp_gpu_ctx* ctx, void* handle_out);
+int icp_gpu_peer_attach(icp_gpu_ctx* ctx, int32_t rank, int32_t world, const void* handles);
+int icp_gpu_peer_address(icp_gpu_ctx* ctx, void** mailbox_dev);
+int icp_gpu_peer_attach_ptrs(icp_gpu_ctx* ctx, int32_t rank, int32_t world, void* const* mailboxes_dev);
+int icp_gpu_peer_detach(icp_gpu_ctx* ctx);
 
 #ifdef __cplusplus
 }

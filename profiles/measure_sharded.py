@@ -1,5 +1,6 @@
 """Config 5b: one very large pair (default 1720 sweeps x 1744 beams ~ 3 M points) registered (a) by one GPU alone and
-(b) point-sharded over all ranks with one all-reduce of <= 28 doubles per iteration.  Run under torchrun:
+(b) point-sharded over all ranks with one all-reduce of <= 28 doubles per iteration (NCCL through the host, and fused
+into the reduction kernel over peer memory).  Run under torchrun:
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 profiles/measure_sharded.py
 Rank 0 prints one JSON object.  ("used only where it is measured to win": this is that measurement.)"""
 import json
@@ -44,10 +45,25 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         dt = time.perf_counter() - t0
     dt = parallel.max_over_ranks(dt)
+    # (c) the same shards, exchange fused into the reduction kernel over NVLink peer memory (icp_gpu_peer_*): the
+    # ordinary estimate_pose, one CUDA graph, no host round trip and no NCCL call per iteration
+    parallel.attach_peers(ctx)
+    for _ in range(3):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pose_fused, _, _ = ctx.estimate_pose(want_history=False)
+        dtf = time.perf_counter() - t0
+    dtf = parallel.max_over_ranks(dtf)
+    poses = [None] * world
+    dist.all_gather_object(poses, pose_fused.tobytes())
+    ctx.peer_detach()
     if rank == 0:
-        out.update(sharded_ms=dt * 1e3, world=world, n_points=len(src), iterations=iters,
-                   max_abs_pose_diff=float(np.abs(pose_sharded - pose_single).max()),
-                   note="sharded path stages the 28-double row through the host each iteration (D2H, NCCL all-reduce, H2D)")
+        out.update(sharded_nccl_host_staged_ms=dt * 1e3, sharded_fused_peer_memory_ms=dtf * 1e3, world=world, n_points=len(src), iterations=iters,
+                   max_abs_pose_diff_nccl=float(np.abs(pose_sharded - pose_single).max()),
+                   max_abs_pose_diff_fused=float(np.abs(pose_fused - pose_single).max()),
+                   fused_pose_identical_on_all_ranks=bool(all(p == poses[0] for p in poses)),
+                   note="nccl: the 28-double row goes D2H, NCCL all-reduce, H2D every iteration; fused: the last block of the reduction "
+                        "kernel stores its row into the peers' mailboxes (NVLink) and sums what it receives")
         print(json.dumps(out))
     ctx.close()
     dist.destroy_process_group()

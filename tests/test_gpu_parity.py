@@ -415,6 +415,95 @@ def test_point_sharded_equals_single(bunny, metric):
         assert pose_close(pa, ref_pose, 1e-6, 1e-6)
 
 
+# ----------------------------------------------------------------------------- the same with the exchange inside the reduction kernel
+def _peer_pair(tgt, src, cfg, n_ctx=2):
+    """n contexts on this GPU, each with the whole target and a contiguous shard of the source, mailboxes attached."""
+    from icp_variants_b200 import parallel
+    ctxs = [capi.Context(0) for _ in range(n_ctx)]
+    for r, c in enumerate(ctxs):
+        sl = parallel.shard_points(len(src), n_ctx, r)
+        c.set_config(cfg)
+        c.set_target(tgt.points, tgt.normals, tgt.colors)
+        c.set_source(src.points[sl], src.normals[sl], src.colors[sl])
+    addr = [c.peer_address() for c in ctxs]              # every mailbox exists (zeroed) before anybody attaches
+    for r, c in enumerate(ctxs):
+        c.peer_attach_ptrs(r, n_ctx, addr)
+    return ctxs
+
+
+@pytest.mark.parametrize("metric,minimizer,n_ctx,graph", [(0, 0, 2, 1), (1, 0, 2, 1), (2, 0, 2, 1), (1, 0, 3, 1), (1, 0, 2, 0), (1, 1, 2, 1), (2, 1, 2, 1)])
+def test_peer_memory_sharded_registration_equals_single(bunny, monkeypatch, metric, minimizer, n_ctx, graph):
+    """icp_gpu_peer_*: the last block of every reduction stores its row into the peers' mailboxes and sums the rows
+    it receives, so each context's ordinary estimate_pose runs the point-sharded registration without the host.
+    All contexts must end with the bit-identical pose, equal to the single-context one within the pose tolerance."""
+    monkeypatch.setenv("ICP_GPU_PEER_TIMEOUT_MS", "20000")
+    src, tgt, _, _ = bunny
+    cfg = capi.default_config()
+    cfg.metric, cfg.minimizer, cfg.n_iterations, cfg.use_graph, cfg.collect_stats = metric, minimizer, 5, graph, 0
+    with capi.Context(0) as full:
+        full.set_config(cfg)
+        full.set_target(tgt.points, tgt.normals, tgt.colors)
+        full.set_source(src.points, src.normals, src.colors)
+        ref_pose, _, _ = full.estimate_pose()
+    ctxs = _peer_pair(tgt, src, cfg, n_ctx)
+    try:
+        for rep in range(2):                              # twice: the exchange counter runs on across registrations
+            for c in ctxs:
+                c.estimate_pose_async()                   # enqueue only: the kernels of the contexts wait for each other
+            poses = [c.estimate_pose_finish()[0] for c in ctxs]
+            for q in poses[1:]:
+                assert np.array_equal(poses[0], q)
+            assert pose_close(poses[0], ref_pose, 1e-6, 1e-6)
+        ctxs[0].peer_detach()                             # detached: a single-context registration of its own shard again
+        alone, _, _ = ctxs[0].estimate_pose()
+        assert np.isfinite(alone).all()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_memory_sharded_grid_search_fused_reduction(small_eth_pair, monkeypatch):
+    """The same on the BVH search path, where the reduction evaluates weighting / rejection itself (fused stages 3-4):
+    10 point-to-plane iterations of an ETH-shaped pair split over two contexts."""
+    monkeypatch.setenv("ICP_GPU_PEER_TIMEOUT_MS", "20000")
+    src, tgt, _ = small_eth_pair
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = 1, 10, 10.0, 2, 0
+    with capi.Context(0) as full:
+        full.set_config(cfg)
+        full.set_target(tgt.points, tgt.normals, tgt.colors)
+        full.set_source(src.points, src.normals, src.colors)
+        ref_pose, _, _ = full.estimate_pose()
+    ctxs = _peer_pair(tgt, src, cfg, 2)
+    try:
+        for c in ctxs:
+            c.estimate_pose_async()
+        (pa, na), (pb, nb) = [c.estimate_pose_finish() for c in ctxs]
+        assert na == nb == 10 and np.array_equal(pa, pb)
+        assert pose_close(pa, ref_pose, 1e-6, 1e-6)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_memory_missing_peer_times_out_with_an_error(bunny, monkeypatch):
+    """A rank whose peer never arrives must finish with ICP_GPU_E_PEER, not hang the GPU."""
+    monkeypatch.setenv("ICP_GPU_PEER_TIMEOUT_MS", "50")
+    src, tgt, _, _ = bunny
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations = 1, 2
+    ctxs = _peer_pair(tgt, src, cfg, 2)
+    try:
+        with pytest.raises(capi.IcpGpuError) as e:
+            ctxs[0].estimate_pose()                       # rank 1 never runs
+        assert e.value.code == capi.E_PEER
+        with pytest.raises(capi.IcpGpuError):             # the NCCL-style split iteration is refused while peers are attached
+            ctxs[1].iteration_begin(np.eye(4, dtype=np.float32))
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 # ----------------------------------------------------------------------------- BASELINE.json full sizes
 @pytest.fixture(scope="module")
 def full_eth_pair():

@@ -34,6 +34,19 @@ def _worker(rank, world, port, q):
         ok_pairs = np.array_equal(counts, np.ones(44))
         # timing reduction
         ok_max = parallel.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+        # mailbox handles of the fused (peer-memory) exchange arrive in rank order on every rank
+        handles = parallel.gather_peer_handles(bytes([rank]) * 64)
+        ok_max = ok_max and handles == [bytes([r]) * 64 for r in range(world)]
+
+        class FakeCtx:                                   # attach_peers drives export -> gather -> attach -> barrier
+            def peer_export(self):
+                return bytes([100 + rank]) * 64
+
+            def peer_attach(self, r, w, hs):
+                self.got = (r, w, list(hs))
+        fc = FakeCtx()
+        parallel.attach_peers(fc)
+        ok_max = ok_max and fc.got == (rank, world, [bytes([100 + r]) * 64 for r in range(world)])
         q.put((rank, bool(ok_sum), bool(ok_pairs), bool(ok_max), len(mine)))
     finally:
         dist.destroy_process_group()
