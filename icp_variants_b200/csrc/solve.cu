@@ -80,14 +80,17 @@ __device__ __forceinline__ bool chol6_solve(const double* row, double lambda2, d
 #pragma unroll
     for (int i = 0; i < 6; ++i) L[i][i] += lambda2;
     bool ok = true;
+    double Linv[6];          // 1 / L[j][j]: one rsqrt per column instead of a sqrt and 3 divisions (this is the serial tail
+                             // of every iteration: one thread, every dependent fp64 division costs ~100 cycles)
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double d = L[j][j];
 #pragma unroll
         for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m];
         if (!(d > 0.0)) ok = false;
-        const double ljj = sqrt(d), inv = 1.0 / ljj;
-        L[j][j] = ljj;
+        const double inv = rsqrt(d);
+        Linv[j] = inv;
+        L[j][j] = d * inv;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = L[i][j];
@@ -102,14 +105,14 @@ __device__ __forceinline__ bool chol6_solve(const double* row, double lambda2, d
         double v = row[21 + i];
 #pragma unroll
         for (int m = 0; m < i; ++m) v -= L[i][m] * y[m];
-        y[i] = v / L[i][i];
+        y[i] = v * Linv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double v = y[i];
 #pragma unroll
         for (int m = i + 1; m < 6; ++m) v -= L[m][i] * x[m];
-        x[i] = v / L[i][i];
+        x[i] = v * Linv[i];
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) ok = false;
@@ -136,8 +139,10 @@ __device__ int finish_p2plane(const double* row, float* inc) {
     if (expand_and_solve(row, 0.0, x) != 0) return ICP_GPU_E_NUMERIC;
     // ICPOptimizer.h:768-779: R = Rx(alpha) * Ry(beta) * Rz(gamma) in fp32, t = x[3..5]
     const float al = (float)x[0], be = (float)x[1], ga = (float)x[2];
-    const float ca = (float)cos((double)al), sa = (float)sin((double)al), cb = (float)cos((double)be), sb = (float)sin((double)be),
-                cg = (float)cos((double)ga), sg = (float)sin((double)ga);
+    double sd, cd;
+    sincos((double)al, &sd, &cd); const float ca = (float)cd, sa = (float)sd;
+    sincos((double)be, &sd, &cd); const float cb = (float)cd, sb = (float)sd;
+    sincos((double)ga, &sd, &cd); const float cg = (float)cd, sg = (float)sd;
     float Rx[16], Ry[16], Rz[16], T[16];
     mat4_identity_dev(Rx); mat4_identity_dev(Ry); mat4_identity_dev(Rz);
     Rx[5] = ca; Rx[9] = -sa; Rx[6] = sa; Rx[10] = ca;
@@ -215,6 +220,37 @@ __device__ void finish_row(DevState* st, const double* row, int mode, float* his
     apply_increment(st, inc, rc, history);
 }
 
+// The same for the last block of reduce_kernel: the current pose and the means come from the block's shared-memory copies and
+// the three loop counters from registers (loaded at kernel start), so the serial tail makes no dependent global-memory round
+// trip; everything is written once at the end.
+struct LoopRegs { int status, iters_done, iter; };
+
+__device__ __forceinline__ void finish_row_local(DevState* st, const double* row, int mode, float* history, const float* P, const float* mS,
+                                                 const float* mD, const LoopRegs lr) {
+    float inc[16]; int rc;
+    if (mode == 0) rc = finish_p2p(row, inc);
+    else if (mode == 1) rc = finish_p2plane(row, inc);
+    else rc = finish_symmetric(row, mS, mD, inc);
+    if (lr.status == 0) {
+        if (rc != 0) st->status = rc;
+        else {
+            float np[16], nm[9];
+            mat4_mul_pinned(inc, P, np);                       // ICPOptimizer.h:614-620
+            inv_transpose3_pinned(np, nm);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) st->pose[i] = np[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) st->nrm[i] = nm[i];
+            if (history) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) history[16 * lr.iters_done + i] = np[i];
+            }
+            st->iters_done = lr.iters_done + 1;
+        }
+    }
+    st->iter = lr.iter + 1;
+}
+
 __device__ void finish_sums(DevState* st, const double* row) {
     // unweighted means of the kept matches, rounded to fp32 (ICPOptimizer.h:797-798)
     const double M = row[0];
@@ -235,6 +271,8 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     __shared__ bool is_last;
     unsigned long long t_start = 0, t_loop = 0;
     if (a.profile && threadIdx.x == 0) { t_start = global_timer_ns(); if (blockIdx.x == 0) a.state->prof[0] = t_start; }
+    LoopRegs lr; lr.status = 0; lr.iters_done = 0; lr.iter = 0;
+    if (threadIdx.x == 0) { lr.status = a.state->status; lr.iters_done = a.state->iters_done; lr.iter = a.state->iter; }
     if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
     if (threadIdx.x >= 64 && threadIdx.x < 73) Nm[threadIdx.x - 64] = a.state->nrm[threadIdx.x - 64];
@@ -370,7 +408,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
         if (a.profile) { a.state->prof[1] = t_start; a.state->prof[2] = t_loop; a.state->prof[3] = global_timer_ns(); }
         if (!a.solve) { for (int k = 0; k < ICP_NRED; ++k) a.state->shard_partials[k] = fin[0][k]; }
         else if (MODE == 3) finish_sums(a.state, fin[0]);
-        else finish_row(a.state, fin[0], MODE, a.pose_history);
+        else finish_row_local(a.state, fin[0], MODE, a.pose_history, P, mS, mD, lr);
         if (a.profile) { __threadfence(); a.state->prof[4] = global_timer_ns(); }
     }
 }
