@@ -91,7 +91,7 @@ struct icp_gpu_ctx {
     DeviceBuf sgrid, scell_start, order_dev, voxel_table;
     int Ts = 0;
     // loop state
-    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, nn_leaf, qbuf, partials, pose_dev, history;
+    DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, nn_leaf, qbuf, seedbuf, partials, pose_dev, history;
     DeviceBuf nrm_out_dev;
     DeviceBuf prep_in, prep_tmp, prep_out, gt_src, gt_ref, met_partial, met_out;
     long long n_gt = 0; int last_iters = 0;
@@ -280,7 +280,8 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
         ctx->src_finite_valid = false; ctx->src_rank_valid = false;     // fetched lazily from the device when a plan needs them
         const size_t n1 = (size_t)(n > 0 ? n : 1);
         if (ensure(ctx, ctx->match_pos, n1 * 4) || ensure(ctx, ctx->match_w, n1 * 4) || ensure(ctx, ctx->match_idx, n1 * 4) ||
-            ensure(ctx, ctx->nn_pos, n1 * 4) || ensure(ctx, ctx->nn_leaf, n1 * 4) || ensure(ctx, ctx->qbuf, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
+            ensure(ctx, ctx->nn_pos, n1 * 4) || ensure(ctx, ctx->nn_leaf, n1 * 4) || ensure(ctx, ctx->qbuf, n1 * sizeof(float4)) ||
+            ensure(ctx, ctx->seedbuf, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
         ctx->n_reduce_blocks = icp_reduce_blocks((int)n, ctx->n_sms);
         if (ensure(ctx, ctx->partials, (size_t)ctx->n_reduce_blocks * ICP_NRED * sizeof(double))) return ICP_GPU_E_CUDA;
         if (build_source(ctx)) return ICP_GPU_E_CUDA;
@@ -416,7 +417,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
     a.max_d2 = c->cfg.max_distance_sq;
     a.match_pos = (int*)c->match_pos.p; a.match_w = (float*)c->match_w.p; a.match_idx = want_idx ? (int*)c->match_idx.p : nullptr;
-    a.nn_pos = (int*)c->nn_pos.p; a.qbuf = (float4*)c->qbuf.p;
+    a.nn_pos = (int*)c->nn_pos.p; a.qbuf = (float4*)c->qbuf.p; a.seedbuf = (float4*)c->seedbuf.p;
     a.desc_index = desc_index;
     a.use_seed = grid_order ? 1 : 0;
     if (proj_tiled(c, algo)) { a.src_pts = (const float4*)c->src_raw_pts.p; a.src_nrm = (const float4*)c->src_raw_nrm.p; a.proj_tiled = 1; }
@@ -685,7 +686,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf,
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
                          &ctx->nrm_out_dev, &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);

@@ -153,6 +153,8 @@ struct MatchArgs {
     float* match_w;
     int* match_idx;          // original target index (API output), may be null
     int* nn_pos;             // nearest neighbour found the last time p was a query (-1 none): seeds the next search
+    float4* seedbuf;         // knn_prep_kernel -> knn_bvh_kernel, per deferred query: {best d2, best idx, best pos, seed leaf} of the seed-leaf
+                             // scan the fast path already made (w = -2: not scanned, the walk starts from nn_pos itself)
     float4* qbuf;            // transformed query points of the current iteration {x,y,z,rgba}; x = NaN: not searched
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
     int use_seed;

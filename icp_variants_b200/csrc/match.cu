@@ -233,8 +233,11 @@ __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query
 // itself -- same candidates, same (d, idx) order, hence the same answer as the walk -- and marks the query as done
 // (qbuf.x = NaN).  The 32 queries of a warp are spatial neighbours (sorted source), so their leaves coincide and the
 // loads are mostly broadcasts.  Everything else (no neighbour yet, ball leaving the box) is left to knn_bvh_kernel.
+#ifndef PREP_MIN_BLOCKS
+#define PREP_MIN_BLOCKS 5          // measured 5 / 6 / 7 / 8 blocks per SM: 60 / 67 / 78 / 79 us per launch (more blocks = spills)
+#endif
 template <bool COLOR>
-__global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
+__global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
         const float4 p4 = __ldg(&a.src_pts[p]);
         const float4 n4 = __ldg(&a.src_nrm[p]);
         float4 o = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, n4.w);
+        float4 seed = make_float4(0.f, 0.f, 0.f, __int_as_float(-2));      // nothing to hand over
         if (query_active(d, a.mask, p4, n4)) {
             float x, y, z;
             xform_point(sm.P, p4.x, p4.y, p4.z, x, y, z);
@@ -258,6 +262,8 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
                     Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
                     int bleaf = -1;
                     thread_scan_leaf<COLOR>(a, q, b, bleaf, (unsigned int)seed_leaf, ev); ++nd;
+                    // if this query is left to the walk, the walk starts from this scan instead of repeating it
+                    seed = make_float4(b.d, __int_as_float(b.idx), __int_as_float(b.pos), __int_as_float(seed_leaf));
                     if (b.d < FLT_BIG) {
                         const float r = __fmul_ru(__fsqrt_ru(b.d), 1.00001f);
                         const float4 ilo = __ldg(&a.adj_box[2 * (size_t)seed_leaf]), ihi = __ldg(&a.adj_box[2 * (size_t)seed_leaf + 1]);
@@ -290,12 +296,16 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const MatchArgs a) {
             }
         }
         a.qbuf[p] = o;
+        if (o.x == o.x) a.seedbuf[p] = seed;
     }
     flush_stats(a, 0u, 0u, ev, nd);
 }
 
+#ifndef WALK_MIN_BLOCKS
+#define WALK_MIN_BLOCKS 16         // 32 registers: all 64 warp slots of an SM (the walk is latency-bound: 11 / 8 / 5 resident blocks
+#endif                             // measured 150 / 196 / 241 us per launch against 118 at 16)
 template <bool COLOR>
-__global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs a) {
+__global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kernel(const MatchArgs a) {
     __shared__ unsigned int s_node[BVH_WARPS][BVH_STACK];
     __shared__ float s_lb[BVH_WARPS][BVH_STACK];
     __shared__ BvhDesc s_bvh;
@@ -321,7 +331,12 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
         // Start from the neighbour this query had before: scan that neighbour's whole leaf (lane = point).  After a
         // small pose change the new neighbour is almost always in it, so the search starts with a (nearly) final bound.
         int seed_leaf = -1;
-        {
+        const float4 sb = __ldg(&a.seedbuf[p]);
+        const bool handed = __float_as_int(sb.w) >= 0;      // the fast path scanned the seed leaf and found the ball leaving its inflated box
+        if (handed) {
+            seed_leaf = __float_as_int(sb.w);
+            if (lane == 0) { b.d = sb.x; b.idx = __float_as_int(sb.y); b.pos = __float_as_int(sb.z); }
+        } else {
             const int sp = a.use_seed ? a.nn_pos[p] : -1;
             if (sp >= 0 && sp < a.n_tgt) {
                 seed_leaf = a.nn_leaf[p];
@@ -337,7 +352,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
             }
         }
         bool done = false;
-        if (seed_leaf >= 0 && seed_leaf < a.adj_capacity) {
+        if (!handed && seed_leaf >= 0 && seed_leaf < a.adj_capacity) {
             // Shortcut without the tree: if the search ball lies inside the seed leaf's inflated box, every leaf that
             // meets the ball is in that leaf's adjacency list (built with the same inflated box, grid.cu).
             float bnd = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
@@ -373,8 +388,10 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                 if (inside) {
                     const int na = __float_as_int(ilo.w);
                     unsigned int node = 0; unsigned int key = 0xFFFFFFFFu;
+                    unsigned int cfirst = 0u, clast = 0u;                        // the node's children, loaded with the boxes (not after the pick)
                     if (lane < na) {
                         node = __ldg(&a.adj1[(size_t)m * 32 + lane]);
+                        cfirst = __ldg(&a.child_start[bvh.coffset[1] + node]); clast = __ldg(&a.child_start[bvh.coffset[1] + node + 1]);
                         const float clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node)]), __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[1] + node) + 1]));
                         if (!(clb > bnd)) key = __float_as_uint(clb);
                     }
@@ -384,9 +401,8 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knn_bvh_kernel(const MatchArgs
                         const unsigned int kmin = __reduce_min_sync(FULL, key);
                         if (kmin == 0xFFFFFFFFu || __uint_as_float(kmin) > bnd) break;
                         const int src = __ffs((int)__ballot_sync(FULL, key == kmin)) - 1;
-                        const unsigned int j = __shfl_sync(FULL, node, src);
+                        const unsigned int first = __shfl_sync(FULL, cfirst, src), last = __shfl_sync(FULL, clast, src);
                         if (lane == src) key = 0xFFFFFFFFu;
-                        const unsigned int first = __ldg(&a.child_start[bvh.coffset[1] + j]), last = __ldg(&a.child_start[bvh.coffset[1] + j + 1]);
                         if (lane == 0) ++nd;
                         bvh_visit<COLOR>(a, bvh, q, b, bnd, 0, first, last, st_node, st_lb, top, lane, lt_mask, ev, nd);
                     }
