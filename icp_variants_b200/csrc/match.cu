@@ -161,14 +161,14 @@ __device__ __forceinline__ float box_dist2c(const Query& q, const float4 lo, con
     return d;
 }
 
-// Lane l proposes leaf `leaf` with box distance clb (keep = it can still matter): the proposed leaves are scanned
-// nearest first (lane = point) for as long as their box distance does not exceed the shrinking bound.
+// Lane l proposes the leaf with points [ls, le) and box distance clb (keep = it can still matter): the proposed leaves are
+// scanned nearest first (lane = point) for as long as their box distance does not exceed the shrinking bound.  The callers
+// load the point ranges together with the boxes (one dependent memory round trip less per visited node: the walk is
+// bound by the length of its chain of dependent loads).
 template <bool COLOR>
-__device__ __forceinline__ void bvh_scan_leaves(const MatchArgs& a, const Query& q, Best& b, float& bound, unsigned int leaf, float clb,
-                                                bool keep, int lane, unsigned int& ev, unsigned int& nd) {
+__device__ __forceinline__ void bvh_scan_leaves(const MatchArgs& a, const Query& q, Best& b, float& bound, unsigned int ls, unsigned int le,
+                                                float clb, bool keep, int lane, unsigned int& ev, unsigned int& nd) {
     const unsigned int FULL = 0xFFFFFFFFu;
-    unsigned int ls = 0, le = 0;
-    if (keep) { ls = __ldg(&a.leaf_start[leaf]); le = __ldg(&a.leaf_start[leaf + 1]); }
     unsigned int key = keep ? __float_as_uint(clb) : 0xFFFFFFFFu;
     for (;;) {
         const unsigned int kmin = __reduce_min_sync(FULL, key);
@@ -198,12 +198,14 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
     const unsigned int FULL = 0xFFFFFFFFu;
     const unsigned int c = first + lane;
     float clb = FLT_BIG; bool keep = false;
+    unsigned int ls = 0u, le = 0u;
     if (c < last) {
         const float4 lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c)]), hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[L] + c) + 1]);
+        if (L == 0) { ls = __ldg(&a.leaf_start[c]); le = __ldg(&a.leaf_start[c + 1]); }
         clb = box_dist2c<COLOR>(q, lo, hi);
         keep = !(clb > bound);
     }
-    if (L == 0) { bvh_scan_leaves<COLOR>(a, q, b, bound, c, clb, keep, lane, ev, nd); return; }
+    if (L == 0) { bvh_scan_leaves<COLOR>(a, q, b, bound, ls, le, clb, keep, lane, ev, nd); return; }
     const unsigned int mk = __ballot_sync(FULL, keep);
     if (keep) { const int s = top + __popc(mk & lt_mask); st_node[s] = ((unsigned int)L << 27) | c; st_lb[s] = clb; }
     top += __popc(mk);
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
                     int bleaf = -1;
                     thread_scan_leaf<COLOR>(a, q, b, bleaf, (unsigned int)seed_leaf, ev); ++nd;
                     // if this query is left to the walk, the walk starts from this scan instead of repeating it
-                    seed = make_float4(b.d, __int_as_float(b.idx), __int_as_float(b.pos), __int_as_float(seed_leaf));
+                    seed = make_float4(b.d, __int_as_float(b.idx), __int_as_float(b.pos), __int_as_float(-1));
                     if (b.d < FLT_BIG) {
                         const float r = __fmul_ru(__fsqrt_ru(b.d), 1.00001f);
                         const float4 ilo = __ldg(&a.adj_box[2 * (size_t)seed_leaf]), ihi = __ldg(&a.adj_box[2 * (size_t)seed_leaf + 1]);
@@ -290,6 +292,15 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
                             a.nn_pos[p] = b.idx == INT_MAX ? -1 : b.pos;
                             a.nn_leaf[p] = b.idx == INT_MAX ? -1 : bleaf;
                             o.x = __int_as_float(0x7fc00000);                   // searched: nothing left for the walk
+                        } else if (a.adj1_capacity > 0 && a.bvh->n_levels >= 2) {
+                            // left to the walk: does the ball at least stay inside the inflated box of the seed leaf's level-1 node?
+                            // Then the walk starts from that node's list (lanes of deferred queries are otherwise idle here).
+                            const int m = (int)(__ldg(&a.node_rank[a.bvh->coffset[1] + seed_leaf + 1]) - 1u);
+                            if (m < a.adj1_capacity) {
+                                const float4 jlo = __ldg(&a.adj1_box[2 * (size_t)m]), jhi = __ldg(&a.adj1_box[2 * (size_t)m + 1]);
+                                if (__fsub_rd(x, r) >= jlo.x && __fadd_ru(x, r) <= jhi.x && __fsub_rd(y, r) >= jlo.y &&
+                                    __fadd_ru(y, r) <= jhi.y && __fsub_rd(z, r) >= jlo.z && __fadd_ru(z, r) <= jhi.z) seed.w = __int_as_float(m);
+                            }
                         }
                     }
                 }
@@ -332,9 +343,10 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
         // small pose change the new neighbour is almost always in it, so the search starts with a (nearly) final bound.
         int seed_leaf = -1;
         const float4 sb = __ldg(&a.seedbuf[p]);
-        const bool handed = __float_as_int(sb.w) >= 0;      // the fast path scanned the seed leaf and found the ball leaving its inflated box
+        // handed over: the fast path scanned the seed leaf, found the ball leaving its inflated box, and looked one level up
+        // (sb.w = the level-1 node whose list covers the ball, or -1)
+        const bool handed = __float_as_int(sb.w) >= -1;
         if (handed) {
-            seed_leaf = __float_as_int(sb.w);
             if (lane == 0) { b.d = sb.x; b.idx = __float_as_int(sb.y); b.pos = __float_as_int(sb.z); }
         } else {
             const int sp = a.use_seed ? a.nn_pos[p] : -1;
@@ -363,28 +375,34 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
                                     __fadd_ru(q.y, r) <= ihi.y && __fsub_rd(q.z, r) >= ilo.z && __fadd_ru(q.z, r) <= ihi.z;
                 if (inside) {                                                   // never true for the inverted "no list" box
                     const int na = __float_as_int(ilo.w);
-                    unsigned int leaf = 0; float clb = FLT_BIG; bool keep = false;
+                    unsigned int ls = 0u, le = 0u; float clb = FLT_BIG; bool keep = false;
                     if (lane < na) {
-                        leaf = __ldg(&a.adj[(size_t)seed_leaf * 32 + lane]);
-                        clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
+                        const unsigned int leaf = __ldg(&a.adj[(size_t)seed_leaf * 32 + lane]);
+                        const float4 lo = __ldg(&a.bvh_box[2 * (size_t)leaf]), hi = __ldg(&a.bvh_box[2 * (size_t)leaf + 1]);
+                        ls = __ldg(&a.leaf_start[leaf]); le = __ldg(&a.leaf_start[leaf + 1]);
+                        clb = box_dist2c<COLOR>(q, lo, hi);
                         keep = !(clb > bnd);
                     }
                     if (lane == 0) ++nd;
-                    bvh_scan_leaves<COLOR>(a, q, b, bnd, leaf, clb, keep, lane, ev, nd);
+                    bvh_scan_leaves<COLOR>(a, q, b, bnd, ls, le, clb, keep, lane, ev, nd);
                     done = true;
                 }
             }
         }
-        if (!done && seed_leaf >= 0 && top_level >= 1 && a.adj1_capacity > 0) {
+        if (!done && (handed ? __float_as_int(sb.w) >= 0 : seed_leaf >= 0) && top_level >= 1 && a.adj1_capacity > 0) {
             // The same shortcut one level up: the ball inside the inflated box of the seed leaf's level-1 node => every
             // level-1 node that meets the ball is in that node's list; their leaves are tested 32 at a time.
-            const int m = (int)(__ldg(&a.node_rank[bvh.coffset[1] + seed_leaf + 1]) - 1u);
+            const int m = handed ? __float_as_int(sb.w) : (int)(__ldg(&a.node_rank[bvh.coffset[1] + seed_leaf + 1]) - 1u);
             float bnd = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(b.d)));
             if (m < a.adj1_capacity && bnd < FLT_BIG) {
-                const float r = __fmul_ru(__fsqrt_ru(bnd), 1.00001f);
-                const float4 ilo = __ldg(&a.adj1_box[2 * (size_t)m]), ihi = __ldg(&a.adj1_box[2 * (size_t)m + 1]);
-                const bool inside = __fsub_rd(q.x, r) >= ilo.x && __fadd_ru(q.x, r) <= ihi.x && __fsub_rd(q.y, r) >= ilo.y &&
-                                    __fadd_ru(q.y, r) <= ihi.y && __fsub_rd(q.z, r) >= ilo.z && __fadd_ru(q.z, r) <= ihi.z;
+                const float4 ilo = __ldg(&a.adj1_box[2 * (size_t)m]);
+                bool inside = true;                                             // handed over: tested by the fast path
+                if (!handed) {
+                    const float r = __fmul_ru(__fsqrt_ru(bnd), 1.00001f);
+                    const float4 ihi = __ldg(&a.adj1_box[2 * (size_t)m + 1]);
+                    inside = __fsub_rd(q.x, r) >= ilo.x && __fadd_ru(q.x, r) <= ihi.x && __fsub_rd(q.y, r) >= ilo.y &&
+                             __fadd_ru(q.y, r) <= ihi.y && __fsub_rd(q.z, r) >= ilo.z && __fadd_ru(q.z, r) <= ihi.z;
+                }
                 if (inside) {
                     const int na = __float_as_int(ilo.w);
                     unsigned int node = 0; unsigned int key = 0xFFFFFFFFu;
