@@ -241,13 +241,20 @@ __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query
 template <bool COLOR>
 __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
-    load_pose(sm, a.state_ro);
-    const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // Everything that depends on nothing is requested first, so that the pose, the descriptor and the query's own state
+    // arrive together (the kernel is bound by its chain of dependent loads, not by bandwidth).
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = p4;
+    int sp_raw = -1, leaf_raw = -1;
+    if (p < a.n_src) {
+        p4 = __ldg(&a.src_pts[p]); n4 = __ldg(&a.src_nrm[p]);
+        sp_raw = a.nn_pos[p]; leaf_raw = a.nn_leaf[p];          // leaf_raw is meaningless unless sp_raw is a position
+    }
+    const int desc_i = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
+    load_pose(sm, a.state_ro);
+    const IterDesc d = a.desc[desc_i];
     unsigned int ev = 0, nd = 0;
     if (p < a.n_src) {
-        const float4 p4 = __ldg(&a.src_pts[p]);
-        const float4 n4 = __ldg(&a.src_nrm[p]);
         float4 o = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, n4.w);
         float4 seed = make_float4(0.f, 0.f, 0.f, __int_as_float(-2));      // nothing to hand over
         if (query_active(d, a.mask, p4, n4)) {
@@ -255,8 +262,8 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
             xform_point(sm.P, p4.x, p4.y, p4.z, x, y, z);
             if (finite3(x, y, z)) {
                 o.x = x; o.y = y; o.z = z;
-                const int sp = (a.fast_path && a.use_seed) ? a.nn_pos[p] : -1;
-                const int seed_leaf = (sp >= 0 && sp < a.n_tgt) ? a.nn_leaf[p] : -1;
+                const int sp = (a.fast_path && a.use_seed) ? sp_raw : -1;
+                const int seed_leaf = (sp >= 0 && sp < a.n_tgt) ? leaf_raw : -1;
                 if (seed_leaf >= 0 && seed_leaf < a.adj_capacity) {
                     Query q; q.x = x; q.y = y; q.z = z;
                     const unsigned int s_rgba = __float_as_uint(n4.w);

@@ -271,22 +271,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     __shared__ bool is_last;
     unsigned long long t_start = 0, t_loop = 0;
     if (a.profile && threadIdx.x == 0) { t_start = global_timer_ns(); if (blockIdx.x == 0) a.state->prof[0] = t_start; }
-    LoopRegs lr; lr.status = 0; lr.iters_done = 0; lr.iter = 0;
-    if (threadIdx.x == 0) { lr.status = a.state->status; lr.iters_done = a.state->iters_done; lr.iter = a.state->iter; }
-    if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
-    if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
-    if (threadIdx.x >= 64 && threadIdx.x < 73) Nm[threadIdx.x - 64] = a.state->nrm[threadIdx.x - 64];
-    __syncthreads();
-    double v[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = 0.0;
-    const double LP = (double)0.1f, LQ = (double)1.0f;   // LAMBDA_POINT / LAMBDA_PLANE|SYMMETRIC (ICPOptimizer.h:737-738, :840-841)
-    // queries are addressed by their position in the Morton-sorted source
-    IterDesc d; d.stride = 1; d.filter_finite = 0; d.mask_word_offset = -1; d.rng_key = 0u; d.proba = -1.0f;
-    if (FUSED) d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state->iter];
-    // Software pipeline over the thread's points: the loads that depend on nothing (search result / match record,
-    // source point and normal) are issued one point ahead, so the only latency a point exposes is its gather of the
-    // matched target point -- the kernel is latency-bound (4 warps per scheduler at 128 registers), not HBM-bound.
+    // the first point's independent loads are requested before the pose / descriptor loads and the barrier
     const int stride = gridDim.x * blockDim.x;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int pos_n = -1; float wf_n = 0.f;
@@ -297,6 +282,23 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
         if (FUSED || MODE == 2) sn_n = __ldg(&a.src_nrm[i]);
         if (!FUSED) wf_n = a.match_w[i];
     }
+    const int state_iter = a.state->iter;
+    LoopRegs lr; lr.status = 0; lr.iters_done = 0; lr.iter = state_iter;
+    if (threadIdx.x == 0) { lr.status = a.state->status; lr.iters_done = a.state->iters_done; }
+    if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 35) { mS[threadIdx.x - 32] = a.state->mean_s[threadIdx.x - 32]; mD[threadIdx.x - 32] = a.state->mean_d[threadIdx.x - 32]; }
+    if (threadIdx.x >= 64 && threadIdx.x < 73) Nm[threadIdx.x - 64] = a.state->nrm[threadIdx.x - 64];
+    __syncthreads();
+    double v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.0;
+    const double LP = (double)0.1f, LQ = (double)1.0f;   // LAMBDA_POINT / LAMBDA_PLANE|SYMMETRIC (ICPOptimizer.h:737-738, :840-841)
+    // queries are addressed by their position in the Morton-sorted source
+    IterDesc d; d.stride = 1; d.filter_finite = 0; d.mask_word_offset = -1; d.rng_key = 0u; d.proba = -1.0f;
+    if (FUSED) d = a.desc[a.desc_index >= 0 ? a.desc_index : state_iter];
+    // Software pipeline over the thread's points: the loads that depend on nothing (search result / match record,
+    // source point and normal) are issued one point ahead, so the only latency a point exposes is its gather of the
+    // matched target point -- the kernel is latency-bound (4 warps per scheduler at 128 registers), not HBM-bound.
     for (; i < a.n_src; i += stride) {
         const int pos = pos_n; float wf = wf_n; const float4 sp = sp_n, sn4 = sn_n;
         // a query without a (surviving) match has pos -1
