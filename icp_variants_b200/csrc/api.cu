@@ -504,6 +504,13 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
     ctx->stats.n_kernel_launches += 1;
+    if (algo == 0 && ctx->n_src > 0 && ctx->n_tgt > 0 && ctx->grid_built && !getenv("ICP_GPU_NO_GRID_SEED")) {
+        // queries without a remembered neighbour start from a point of their own grid cell's neighbourhood (grid.cu)
+        CU(icp_launch_seed_from_grid((const float4*)ctx->src_pts.p, ctx->n_src, (const DevState*)ctx->state.p, (const GridParams*)ctx->grid.p,
+                                     (const unsigned int*)ctx->cell_start.p, ctx->T, (const unsigned int*)ctx->leaf_rank.p,
+                                     (int*)ctx->nn_pos.p, (int*)ctx->nn_leaf.p, ctx->stream));
+        ctx->stats.n_kernel_launches += 1;
+    }
 
     std::vector<cudaEvent_t> marks;
     if (timings) {

@@ -268,6 +268,50 @@ __global__ void fill_int_kernel(int* __restrict__ p, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// First-iteration seeds from the cell table: a query that remembers no neighbour yet (nn_pos < 0) gets a point of the
+// smallest cell-tree node around its transformed position that holds any point (binary search over the depth: the count
+// of the node around a position is monotone in the depth).  The search uses a seed only as its starting bound and first
+// leaf, so any target point is a valid seed -- a near one lets the first iteration run like the later ones (fast path
+// for most queries) instead of walking the tree from the root for every query.
+__global__ void seed_from_grid_kernel(const float4* __restrict__ src_pts, int n_src, const DevState* __restrict__ st,
+                                      const GridParams* __restrict__ gp, const unsigned int* __restrict__ cs, int T,
+                                      const unsigned int* __restrict__ leaf_rank, int* __restrict__ nn_pos, int* __restrict__ nn_leaf) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_src) return;
+    if (nn_pos[p] >= 0) return;
+    const unsigned int n_finite = cs[(size_t)1 << T];
+    if (n_finite == 0u) return;
+    const float4 s = src_pts[p];
+    float P[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) P[k] = st->pose[k];
+    float x, y, z;
+    xform_point(P, s.x, s.y, s.z, x, y, z);
+    if (!finite3(x, y, z)) return;
+    const GridParams g = *gp;
+    const unsigned int c = cell_code(g, x, y, z);
+    int lo = 0, hi = T;                                  // smallest shift whose node is not empty (shift T = the whole cloud)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned int pre = c >> mid;
+        const unsigned int cnt = cs[((size_t)pre + 1) << mid] - cs[(size_t)pre << mid];
+        if (cnt > 0u) hi = mid; else lo = mid + 1;
+    }
+    const unsigned int pre = c >> lo;
+    const unsigned int s0 = cs[(size_t)pre << lo], e0 = cs[((size_t)pre + 1) << lo];
+    if (e0 <= s0) return;
+    const unsigned int pos = s0 + ((e0 - s0) >> 1);
+    nn_pos[p] = (int)pos;
+    nn_leaf[p] = (int)(leaf_rank[pos + 1] - 1u);
+}
+
+cudaError_t icp_launch_seed_from_grid(const float4* src_pts, int n_src, const DevState* st, const GridParams* grid, const unsigned int* cell_start,
+                                      int T, const unsigned int* leaf_rank, int* nn_pos, int* nn_leaf, cudaStream_t s) {
+    if (n_src <= 0) return cudaSuccess;
+    seed_from_grid_kernel<<<(n_src + 255) / 256, 256, 0, s>>>(src_pts, n_src, st, grid, cell_start, T, leaf_rank, nn_pos, nn_leaf);
+    return cudaGetLastError();
+}
+
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
     if (n > 0) fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
     return cudaGetLastError();

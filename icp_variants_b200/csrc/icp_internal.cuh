@@ -208,6 +208,9 @@ cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box,
                                       float4* adj_box, int capacity, int level, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
+// Seeds (nn_pos / nn_leaf) for the queries that have none, from the target's cell table at the pose in `st`.
+cudaError_t icp_launch_seed_from_grid(const float4* src_pts_sorted, int n_src, const DevState* st, const GridParams* grid, const unsigned int* cell_start,
+                                      int T, const unsigned int* leaf_rank, int* nn_pos, int* nn_leaf, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective
 // prep.cu: depth map -> cloud (PointCloud.h:78-165) and convergence metrics (ConvergenceMeasure.h:50-66,104-151)
 struct DepthArgs {
