@@ -238,7 +238,7 @@ __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query
 #ifndef PREP_MIN_BLOCKS
 #define PREP_MIN_BLOCKS 5          // measured 5 / 6 / 7 / 8 blocks per SM: 60 / 67 / 78 / 79 us per launch (more blocks = spills)
 #endif
-template <bool COLOR>
+template <bool COLOR, bool STATS>
 __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,13 +316,13 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
         a.qbuf[p] = o;
         if (o.x == o.x) a.seedbuf[p] = seed;
     }
-    flush_stats(a, 0u, 0u, ev, nd);
+    if (STATS) flush_stats(a, 0u, 0u, ev, nd);     // STATS = false: the counters are dead code (2.6 % of the walk's instructions)
 }
 
 #ifndef WALK_MIN_BLOCKS
 #define WALK_MIN_BLOCKS 16         // 32 registers: all 64 warp slots of an SM (the walk is latency-bound: 11 / 8 / 5 resident blocks
 #endif                             // measured 150 / 196 / 241 us per launch against 118 at 16)
-template <bool COLOR>
+template <bool COLOR, bool STATS>
 __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kernel(const MatchArgs a) {
     __shared__ unsigned int s_node[BVH_WARPS][BVH_STACK];
     __shared__ float s_lb[BVH_WARPS][BVH_STACK];
@@ -339,9 +339,19 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
     unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
     const unsigned int lt_mask = (1u << lane) - 1u;
     if (bvh.n_leaves <= 0) return;                 // empty target: match_finish_kernel sees nn_pos = -1 (set_target reset it)
-    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < a.n_src; p += warps) {
-        const float4 q4 = __ldg(&a.qbuf[p]);
-        if (!(q4.x == q4.x)) continue;                                          // not a (searchable) query this iteration
+    // The warp's positions are p0, p0 + warps, p0 + 2 warps, ...; three quarters of them were answered by the fast path.
+    // Lane k fetches the transformed query of position p0 + k * warps, so that one round of loads (instead of one
+    // dependent load per position) tells the warp which positions it has to search.
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int pb = p0; pb < a.n_src; pb += 32 * warps) {
+      const long long pl = (long long)pb + (long long)lane * warps;
+      float qx = __int_as_float(0x7fc00000);
+      if (pl < (long long)a.n_src) qx = __ldg(&a.qbuf[pl].x);
+      unsigned int todo = __ballot_sync(FULL, qx == qx);                        // NaN: not a (searchable) query this iteration
+      while (todo) {
+        const int k = __ffs((int)todo) - 1; todo &= todo - 1u;
+        const int p = pb + k * warps;
+        const float4 q4 = __ldg(&a.qbuf[p]);                                    // its sector was fetched a moment ago
         Query q; q.x = q4.x; q.y = q4.y; q.z = q4.z;
         const unsigned int s_rgba = __float_as_uint(q4.w);
         q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
@@ -492,8 +502,9 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
             a.nn_pos[p] = pos;
             a.nn_leaf[p] = pos >= 0 ? (int)(__ldg(&a.leaf_rank[pos + 1]) - 1u) : -1;      // off the critical path: nothing waits for it
         }
+      }
     }
-    flush_stats(a, 0u, 0u, ev, nd);
+    if (STATS) flush_stats(a, 0u, 0u, ev, nd);     // STATS = false: the counters are dead code (2.6 % of the walk's instructions)
 }
 
 __global__ void __launch_bounds__(256) match_finish_kernel(const MatchArgs a) {
@@ -683,12 +694,15 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
         ++launches;
     } else {
-        if (a.color_icp) knn_prep_kernel<true><<<(a.n_src + 255) / 256, 256, 0, s>>>(a); else knn_prep_kernel<false><<<(a.n_src + 255) / 256, 256, 0, s>>>(a);
+        const int np = (a.n_src + 255) / 256;
+        if (a.collect_stats) { if (a.color_icp) knn_prep_kernel<true, true><<<np, 256, 0, s>>>(a); else knn_prep_kernel<false, true><<<np, 256, 0, s>>>(a); }
+        else { if (a.color_icp) knn_prep_kernel<true, false><<<np, 256, 0, s>>>(a); else knn_prep_kernel<false, false><<<np, 256, 0, s>>>(a); }
         ++launches;
         if (after_prep) cudaEventRecord(after_prep, s);
         int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
         if (nb > 64 * n_sms) nb = 64 * n_sms;
-        if (a.color_icp) knn_bvh_kernel<true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false><<<nb, BVH_WARPS * 32, 0, s>>>(a);
+        if (a.collect_stats) { if (a.color_icp) knn_bvh_kernel<true, true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, true><<<nb, BVH_WARPS * 32, 0, s>>>(a); }
+        else { if (a.color_icp) knn_bvh_kernel<true, false><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, false><<<nb, BVH_WARPS * 32, 0, s>>>(a); }
         ++launches;
         if (!a.skip_finish) { match_finish_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches; }
     }
