@@ -220,12 +220,20 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
 template <bool COLOR>
 __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query& q, Best& b, int& bleaf, unsigned int leaf, unsigned int& ev) {
     const unsigned int ls = __ldg(&a.leaf_start[leaf]), le = __ldg(&a.leaf_start[leaf + 1]);
+    // (d, idx) lexicographic '<' (contract D2) as ONE 64-bit unsigned comparison: d >= 0, so the bit pattern of d orders
+    // like d, and 0 <= idx <= INT_MAX.  This loop is a third of the kernel's instructions; the two-float-compares-and-an-
+    // integer-compare form of better() plus four selects cost more than the distance itself.
+    if (b.d < 0.f) return;                          // a negative threshold admits nothing (and its bit pattern would order last)
+    unsigned long long key = ((unsigned long long)__float_as_uint(b.d) << 32) | (unsigned int)b.idx;
+    int pos = b.pos;
     for (unsigned int i = ls; i < le; ++i) {
         const float4 pt = __ldg(&a.tgt_pts[i]);
-        const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
-        const int idx = __float_as_int(pt.w);
-        if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; bleaf = (int)leaf; }
+        const float dd = dist2<COLOR>(q, pt, __uint_as_float((unsigned int)(key >> 32)), a.tgt_nrm, i);
+        const unsigned long long k = ((unsigned long long)__float_as_uint(dd) << 32) | __float_as_uint(pt.w);
+        if (k < key) { key = k; pos = (int)i; }
     }
+    if (pos != b.pos) bleaf = (int)leaf;            // positions are unique: a new best position means this leaf holds it
+    b.d = __uint_as_float((unsigned int)(key >> 32)); b.idx = (int)(unsigned int)key; b.pos = pos;
     ev += le - ls;
 }
 
