@@ -11,10 +11,11 @@ from icp_variants_b200 import capi, synth  # noqa: E402
 
 
 def main():
-    src, tgt, _ = synth.eth_pair(seed=1234)
+    sweeps, beams = int(os.environ.get("SWEEPS", "344")), int(os.environ.get("BEAMS", "1077"))     # 1720 x 1744: the 3 M-point pair
+    src, tgt, _ = synth.eth_pair(seed=1234, n_sweeps=sweeps, n_beams=beams)
     cfg = capi.default_config()
     cfg.metric, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = 1, 30, 10.0, 2, 0
-    out = {"runs": []}
+    out = {"n_points": len(src), "algorithmic_bytes_per_launch": 48 * len(src), "runs": []}
     with capi.Context(0) as ctx:
         ctx.set_config(cfg)
         ctx.set_target(tgt.points, tgt.normals, tgt.colors)
@@ -24,7 +25,8 @@ def main():
             t = [int(x) for x in ctx.stats().reduce_profile_ns]
             out["runs"].append({"first_block_to_last_block_start_us": (t[1] - t[0]) / 1e3, "point_loop_us": (t[2] - t[1]) / 1e3,
                                 "block_reduce_ticket_final_sum_us": (t[3] - t[2]) / 1e3, "solve_pose_update_us": (t[4] - t[3]) / 1e3,
-                                "first_block_start_to_pose_written_us": (t[4] - t[0]) / 1e3})
+                                "first_block_start_to_pose_written_us": (t[4] - t[0]) / 1e3,
+                                "algorithmic_GBps_in_kernel": 48 * len(src) / max(t[4] - t[0], 1)})
     print(json.dumps(out))
 
 
