@@ -41,6 +41,20 @@ struct Best { float d; int idx; int pos; };
 // (d, idx) lexicographic '<' : contract D2
 __device__ __forceinline__ bool better(float d, int idx, const Best& b) { return d < b.d || (d == b.d && idx < b.idx); }
 
+// The same order as ONE 64-bit unsigned comparison of bits(d) || idx, valid while both distances are >= +0 (the bit pattern of a
+// non-negative float orders like its value; a NaN distance orders last) and 0 <= idx <= INT_MAX.  best_init keeps b.d
+// non-negative: a negative threshold admits nothing, which the smallest key (0, 0) expresses.  Used by the grid search
+// kernels; the brute-force kernel keeps better().
+__device__ __forceinline__ bool better_key(float d, int idx, const Best& b) {
+    return (((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)idx) <
+           (((unsigned long long)__float_as_uint(b.d) << 32) | (unsigned int)b.idx);
+}
+__device__ __forceinline__ void best_init(Best& b, float max_d2) {
+    if (max_d2 < 0.f) { b.d = 0.f; b.idx = 0; }
+    else { b.d = fminf(max_d2, FLT_BIG); b.idx = INT_MAX; }
+    b.pos = -1;
+}
+
 __device__ __forceinline__ float color_feature(unsigned int rgba, int k) {
     // NearestNeighbor.h:212-221,245-254: color_scale(1) * color_normalize(1/float(255)) * uchar
     return pmul(1.0f / 255.0f, (float)((rgba >> (8 * k)) & 0xFFu));
@@ -181,7 +195,7 @@ __device__ __forceinline__ void bvh_scan_leaves(const MatchArgs& a, const Query&
             const float4 pt = __ldg(&a.tgt_pts[i]);
             const float dd = dist2<COLOR>(q, pt, b.d, a.tgt_nrm, i);
             const int idx = __float_as_int(pt.w);
-            if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+            if (better_key(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
             ++ev;
         }
         if (lane == 0) ++nd;
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
                     Query q; q.x = x; q.y = y; q.z = z;
                     const unsigned int s_rgba = __float_as_uint(n4.w);
                     q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
-                    Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
+                    Best b; best_init(b, a.max_d2);
                     int bleaf = -1;
                     thread_scan_leaf<COLOR>(a, q, b, bleaf, (unsigned int)seed_leaf, ev); ++nd;
                     // if this query is left to the walk, the walk starts from this scan instead of repeating it
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
         Query q; q.x = q4.x; q.y = q4.y; q.z = q4.z;
         const unsigned int s_rgba = __float_as_uint(q4.w);
         q.cr = color_feature(s_rgba, 0); q.cg = color_feature(s_rgba, 1); q.cb = color_feature(s_rgba, 2);
-        Best b; b.d = fminf(a.max_d2, FLT_BIG); b.idx = INT_MAX; b.pos = -1;
+        Best b; best_init(b, a.max_d2);
         // Start from the neighbour this query had before: scan that neighbour's whole leaf (lane = point).  After a
         // small pose change the new neighbour is almost always in it, so the search starts with a (nearly) final bound.
         int seed_leaf = -1;
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
                     const float4 c = __ldg(&a.tgt_pts[i]);
                     const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
                     const int idx = __float_as_int(c.w);
-                    if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                    if (better_key(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
                     ++ev;
                 }
                 if (lane == 0) ++nd;
@@ -479,7 +493,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
                 const float4 c = __ldg(&a.tgt_pts[i]);
                 const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, i);
                 const int idx = __float_as_int(c.w);
-                if (better(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
+                if (better_key(dd, idx, b)) { b.d = dd; b.idx = idx; b.pos = (int)i; }
                 ++ev;
             }
         }
