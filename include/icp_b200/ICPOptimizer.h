@@ -52,6 +52,11 @@ public:
     // The reference seeds its sampler from std::random_device (selection.h:76-79); here the seed is explicit.
     void setSelectionSeed(unsigned seed, bool deviceStream = false) { m_seed = seed; m_selectionRng = deviceStream ? ICP_GPU_RNG_DEVICE : ICP_GPU_RNG_MT19937; }
 
+    // extension: the C-ABI handle behind this optimizer, for what the reference's interface has no name for (icp_gpu_set_stream,
+    // icp_gpu_peer_export / icp_gpu_peer_attach: after attaching, estimatePose of every rank is one point-sharded registration --
+    // the source handed to it is the rank's shard, the target the whole cloud)
+    icp_gpu_ctx* context() const { return m_ctx; }
+
     void printICPConfiguration() {   // ICPOptimizer.h:97-138
         std::cout << "\n\n*-*-*-*-*-*-*-*-*-*-*-*-*-*-*-*-*\nStarting ICP with the following configuration:\n";
         if (colorICP) std::cout << "Color-ICP enabled\n";
