@@ -56,3 +56,14 @@ def test_pose_layout_roundtrip():
     v = capi.pose_to_c(p)
     assert v[12] == p[0, 3] and v[1] == p[1, 0]       # column-major like Eigen::Matrix4f::data()
     assert np.array_equal(capi.pose_from_c(v), p)
+
+
+def test_header_constants_match_the_python_mirror():
+    """Error codes and the peer-exchange constants as the C compiler sees them == capi.py."""
+    src = ('#include "icp_gpu.h"\n#include <stdio.h>\nint main(){printf("%d %d %d %d %d %d %d %d %d", ICP_GPU_E_CUDA, ICP_GPU_E_ARG, ICP_GPU_E_STATE, '
+           'ICP_GPU_E_NO_MATCHES, ICP_GPU_E_NUMERIC, ICP_GPU_E_PEER, ICP_GPU_MAX_PEERS, ICP_GPU_PEER_HANDLE_BYTES, ICP_GPU_MAX_PARTIALS);return 0;}')
+    exe = "/tmp/icp_gpu_consts"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.dirname(capi.HEADER_PATH), "-o", exe], input=src, text=True, check=True)
+    vals = [int(x) for x in subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    assert vals == [capi.E_CUDA, capi.E_ARG, capi.E_STATE, capi.E_NO_MATCHES, capi.E_NUMERIC, capi.E_PEER, capi.MAX_PEERS,
+                    capi.PEER_HANDLE_BYTES, capi.MAX_PARTIALS]
