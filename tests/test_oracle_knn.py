@@ -86,3 +86,24 @@ def test_6d_colour_search():
     # quantised positions + colours can tie in fp64 only by exact duplicates; allow equal-distance alternates
     da = np.linalg.norm(tf[a["idx"]] - qf, axis=1)
     assert np.allclose(da, d, rtol=1e-5, atol=1e-7), diff.sum()
+
+
+def test_packed_key_order_equals_lexicographic_distance_index_order():
+    """The grid search kernels compare candidates as ONE unsigned 64-bit key bits(d2) << 32 | idx (match.cu: better_key,
+    thread_scan_leaf).  That is the (d2, idx) lexicographic order of contract D2 for every non-negative fp32 distance --
+    +0, denormals, FLT_MAX, +inf -- and puts NaN distances after every number, as the strict comparisons of
+    NearestNeighbor.h:81-97 do."""
+    rng = np.random.default_rng(11)
+    special = np.array([0.0, 1e-45, 1.1754944e-38, 1.0, 10.0, 3.4028235e38, np.inf], np.float32)
+    d = np.concatenate([special, rng.random(2000).astype(np.float32) * 5.0, rng.choice(special, 500)]).astype(np.float32)
+    idx = rng.integers(0, 2**31 - 1, size=len(d)).astype(np.int64)
+    idx[: len(special)] = [0, 2**31 - 2, 5, 5, 0, 1, 7]
+    key = (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | idx.astype(np.uint64)
+    i, j = rng.integers(0, len(d), 20000), rng.integers(0, len(d), 20000)
+    lex = (d[i] < d[j]) | ((d[i] == d[j]) & (idx[i] < idx[j]))
+    assert np.array_equal(key[i] < key[j], lex)
+    nan_key = (np.array([np.nan], np.float32).view(np.uint32).astype(np.uint64) << np.uint64(32))
+    assert (nan_key[0] > key).all()          # a NaN distance never wins
+    # the initial bound (min(max_d2, FLT_MAX), INT_MAX) loses exactly to the candidates the reference accepts: d2 <= max_d2
+    init = (np.array([10.0], np.float32).view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(2**31 - 1)
+    assert np.array_equal(key < init[0], (d <= np.float32(10.0)) & ~((d == np.float32(10.0)) & (idx >= 2**31 - 1)))
