@@ -248,7 +248,8 @@ int icp_gpu_iteration_apply_dev(icp_gpu_ctx* ctx, int phase);
  *   icp_gpu_peer_detach       back to a single-context registration.
  * Every rank must export before any rank attaches, and all ranks attach before the first registration (the handle
  * exchange is that barrier).  A rank whose peer does not arrive within ICP_GPU_PEER_TIMEOUT_MS (environment,
- * default 2000) finishes with ICP_GPU_E_PEER instead of hanging.  world <= ICP_GPU_MAX_PEERS. */
+ * default 2000) finishes with ICP_GPU_E_PEER instead of hanging; the ranks' exchange counters are then out of step, so
+ * every rank has to export and attach again before the next registration.  world <= ICP_GPU_MAX_PEERS. */
 #define ICP_GPU_MAX_PEERS 8
 #define ICP_GPU_PEER_HANDLE_BYTES 64
 int icp_gpu_peer_export(icp_gpu_ctx* ctx, void* handle_out);
