@@ -69,6 +69,11 @@ struct icp_gpu_ctx {
     int device = 0, n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;                      // host uploads run here and overlap the previous cloud's build
+    // The part of buildIndex that reads only the library's own data (tree levels, boxes, adjacency lists) runs on aux_stream, so that
+    // whatever the caller enqueues next on `stream` (normally the source's pack + sort) overlaps it; consumers of the index join first.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_index_ready = nullptr;
+    bool index_pending = false;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};           // [target, source]: staging filled
     cudaEvent_t ev_packed[2] = {nullptr, nullptr};           // staging consumed by the pack kernel
     bool packed_once[2] = {false, false};
@@ -83,12 +88,17 @@ struct icp_gpu_ctx {
     std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
     bool src_rank_valid = false;
     // target grid
-    DeviceBuf grid, bbox, keys, ranks, cell_start, block_sums, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, pstart, adj, adj_box, adj1, adj1_box;
+    DeviceBuf grid, bbox, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, adj, adj_box, adj1, adj1_box;
+    // sort / tree scratch, one set per cloud (the two builds run on different streams)
+    struct SortBufs { DeviceBuf keys_a, keys_b, idx_a, idx_b, tile_hist, msd; unsigned int* keys_sorted = nullptr; int msd_shift = 0; };
+    SortBufs tsort, ssort;
+    DeviceBuf lv_flags, lv_tiles, delta_a, delta_b;
     int adj1_capacity = 0;
     int adj_capacity = 0;
     int T = 0; bool grid_built = false; double index_ms = 0.0;
+    bool nn_stale = true;                                    // a new cloud made the remembered neighbours (nn_pos / nn_leaf) meaningless
     // source grid: only its sort order is used (consecutive queries are spatial neighbours: coherent tree walks)
-    DeviceBuf sgrid, scell_start, order_dev, voxel_table;
+    DeviceBuf sgrid, sbbox, order_dev, voxel_table;
     int Ts = 0;
     // loop state
     DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, nn_leaf, qbuf, seedbuf, partials, pose_dev, history;
@@ -137,7 +147,7 @@ int fail(icp_gpu_ctx* c, int code, const char* fmt, ...) {
 int ensure(icp_gpu_ctx* ctx, DeviceBuf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return 0;
     if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
-    if (b.p) { cudaStreamSynchronize(ctx->stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    if (b.p) { cudaStreamSynchronize(ctx->stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8 + 256;
     CU(cudaMalloc(&b.p, want));
     b.cap = want;
@@ -150,11 +160,16 @@ int bind(icp_gpu_ctx* ctx) {
 }
 
 int pick_T(int n, bool source = false) {
-    // cells = ICP_CELLS_PER_POINT x points (surface-like clouds occupy a small fraction of them)
-    long long factor = source ? ICP_SOURCE_CELLS_PER_POINT : ICP_CELLS_PER_POINT;
-    if (!source) if (const char* e = getenv("ICP_GPU_CELLS_PER_POINT")) { const long long v = atoll(e); if (v >= 1 && v <= 64) factor = v; }   // tuning knob
+    // Target: the finest grid the 32-bit keys hold (10 bits per axis) -- the radix sort costs the same for any T, and fine
+    // cells give compact leaves.  Source: 4 cells per point; its grid also defines the voxel pyramid levels, which the
+    // oracle restates (oracle/icp_oracle.c:orc_pick_T).
+    if (!source) {
+        int T = 3 * ICP_MAX_BITS_PER_AXIS;
+        if (const char* e = getenv("ICP_GPU_TARGET_GRID_BITS")) { const int v = atoi(e); if (v >= 3 && v <= 3 * ICP_MAX_BITS_PER_AXIS) T = v; }   // tuning knob
+        return T;
+    }
     int T = 3;
-    while (T < 24 && (1ll << T) < factor * (long long)(n > 0 ? n : 1)) ++T;
+    while (T < 24 && (1ll << T) < (long long)ICP_SOURCE_CELLS_PER_POINT * (long long)(n > 0 ? n : 1)) ++T;
     if (T > 3 * ICP_MAX_BITS_PER_AXIS) T = 3 * ICP_MAX_BITS_PER_AXIS;
     return T;
 }
@@ -175,8 +190,9 @@ int coarsest_stride(long long n) {   // ICPOptimizer.h:503-516
 int upload_cloud(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n, bool device_ptrs,
                  DeviceBuf& pts, DeviceBuf& nrmb, int kind /*0 target, 1 source*/) {
     const size_t n1 = (size_t)(n > 0 ? n : 1);
-    if (ensure(ctx, pts, n1 * sizeof(float4)) || ensure(ctx, nrmb, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
-    if (n == 0) return 0;
+    DeviceBuf& bbox = kind == 0 ? ctx->bbox : ctx->sbbox;
+    if (ensure(ctx, pts, n1 * sizeof(float4)) || ensure(ctx, nrmb, n1 * sizeof(float4)) || ensure(ctx, bbox, 64)) return ICP_GPU_E_CUDA;
+    if (n == 0) { CU(icp_launch_pack_cloud(nullptr, nullptr, nullptr, 0, (float4*)pts.p, (float4*)nrmb.p, (unsigned int*)bbox.p, ctx->stream)); return 0; }
     const float* dx = xyz; const float* dn = nrm; const uint8_t* dc = rgba;
     if (!device_ptrs) {
         // Host arrays go through a per-cloud staging area on the copy stream, so that the upload of one cloud overlaps
@@ -194,24 +210,39 @@ int upload_cloud(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uin
         CU(cudaEventRecord(ctx->ev_copied[kind], ctx->copy_stream));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[kind], 0));
     }
-    CU(icp_launch_pack_cloud(dx, dn, dc, (int)n, (float4*)pts.p, (float4*)nrmb.p, ctx->stream));
+    CU(icp_launch_pack_cloud(dx, dn, dc, (int)n, (float4*)pts.p, (float4*)nrmb.p, (unsigned int*)bbox.p, ctx->stream));
     if (!device_ptrs) { CU(cudaEventRecord(ctx->ev_packed[kind], ctx->stream)); ctx->packed_once[kind] = true; }
     ctx->stats.n_kernel_launches += 1;
     return 0;
 }
 
+// Consumers of the target index (and anything that overwrites it) first wait for the part of its build that runs on aux_stream.
+int join_index(icp_gpu_ctx* ctx) {
+    if (!ctx->index_pending) return 0;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_index_ready, 0));
+    ctx->index_pending = false;
+    return 0;
+}
+
+int ensure_sort(icp_gpu_ctx* ctx, icp_gpu_ctx::SortBufs& sb, int n, int T) {
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    if (ensure(ctx, sb.keys_a, n1 * 4) || ensure(ctx, sb.keys_b, n1 * 4) || ensure(ctx, sb.idx_a, n1 * 4) || ensure(ctx, sb.idx_b, n1 * 4) ||
+        ensure(ctx, sb.tile_hist, icp_radix_hist_words(n, T) * 4) || ensure(ctx, sb.msd, ICP_MSD_WORDS * 4)) return ICP_GPU_E_CUDA;
+    return 0;
+}
+
+// buildIndex: radix sort by cell code, leaves and upper levels from the sorted keys, tight boxes, adjacency lists.
 int build_grid(icp_gpu_ctx* ctx) {
     const int n = ctx->n_tgt;
     ctx->T = pick_T(n);
-    const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->T) + 1;
-    const size_t scan_len = cells1 > n1 + 2 ? cells1 : n1 + 2;
-    if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) ||
-        ensure(ctx, ctx->keys, (n1 + 2) * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->cell_start, cells1 * 4) ||
-        ensure(ctx, ctx->block_sums, (scan_len / 4096 + 2) * 4) || ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->bbox, 64) ||
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) || ensure_sort(ctx, ctx->tsort, n, ctx->T) ||
+        ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->lv_flags, n1 + 64) || ensure(ctx, ctx->lv_tiles, (n1 / 1024 + 2) * 4) ||
+        ensure(ctx, ctx->delta_a, (n1 + 2) * 4) || ensure(ctx, ctx->delta_b, (n1 + 2) * 4) ||
         ensure(ctx, ctx->leaf_start, (n1 + 2) * 4) || ensure(ctx, ctx->leaf_rank, (n1 + 2) * 4) || ensure(ctx, ctx->bvh_desc, sizeof(BvhDesc)) ||
         ensure(ctx, ctx->bvh_box, icp_bvh_max_nodes(n) * 2 * sizeof(float4)) ||
         ensure(ctx, ctx->node_rank, (icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS) * 4) ||
-        ensure(ctx, ctx->child_start, (icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS) * 4) || ensure(ctx, ctx->pstart, icp_bvh_max_nodes(n) * 4))
+        ensure(ctx, ctx->child_start, (icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS) * 4))
         return ICP_GPU_E_CUDA;
     // adjacency lists for up to n/4 leaves (a healthy tree has ~n/20); a cloud with more leaves simply gets no shortcut for the rest
     ctx->adj_capacity = (int)(n1 / 4 + 64);
@@ -220,46 +251,42 @@ int build_grid(icp_gpu_ctx* ctx) {
         ensure(ctx, ctx->adj1, (size_t)ctx->adj1_capacity * 32 * 4) || ensure(ctx, ctx->adj1_box, (size_t)ctx->adj1_capacity * 2 * sizeof(float4)))
         return ICP_GPU_E_CUDA;
     int launches = 0;
+    if (join_index(ctx)) return ICP_GPU_E_CUDA;              // a build still running on aux_stream reads what this one overwrites
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(icp_launch_grid_build((const float4*)ctx->tgt_pts.p, (const float4*)ctx->tgt_nrm.p, n, ctx->T, (GridParams*)ctx->grid.p,
-                             (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
-                             (unsigned int*)ctx->cell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->tgt_pts_sorted.p,
-                             (float4*)ctx->tgt_nrm_sorted.p, 0, ctx->stream, &launches));
-    // the source-sort scratch (keys: n+2 entries, bbox[8]) is free here: list of over-full cells and its counter
-    CU(icp_launch_refine_cells((const unsigned int*)ctx->cell_start.p, ctx->T, (const GridParams*)ctx->grid.p, (unsigned int*)ctx->keys.p,
-                               (unsigned int)(n / 33 + 1), (unsigned int*)ctx->bbox.p + 8, (float4*)ctx->tgt_pts_sorted.p,
-                               (float4*)ctx->tgt_nrm_sorted.p, n, ctx->n_sms, ctx->stream, &launches));
-    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, (const float4*)ctx->tgt_nrm_sorted.p, n, (const GridParams*)ctx->grid.p, (const unsigned int*)ctx->cell_start.p, ctx->T,
-                            (unsigned int*)ctx->leaf_rank.p, (unsigned int*)ctx->block_sums.p, (unsigned int*)ctx->leaf_start.p,
-                            (unsigned int*)ctx->node_rank.p, (unsigned int*)ctx->child_start.p, (unsigned int*)ctx->pstart.p,
-                            (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ctx->stream, &launches));
+    CU(icp_launch_cloud_sort((const float4*)ctx->tgt_pts.p, (const float4*)ctx->tgt_nrm.p, n, ctx->T, (GridParams*)ctx->grid.p, (unsigned int*)ctx->bbox.p,
+                             (unsigned int*)ctx->tsort.keys_a.p, (unsigned int*)ctx->tsort.keys_b.p, (unsigned int*)ctx->tsort.idx_a.p,
+                             (unsigned int*)ctx->tsort.idx_b.p, (unsigned int*)ctx->tsort.tile_hist.p, (float4*)ctx->tgt_pts_sorted.p,
+                             (float4*)ctx->tgt_nrm_sorted.p, (unsigned int*)ctx->tsort.msd.p, &ctx->tsort.keys_sorted, &ctx->tsort.msd_shift, ctx->stream, &launches));
+    cudaStream_t ts = getenv("ICP_GPU_NO_AUX_STREAM") ? ctx->stream : ctx->aux_stream;       // tuning knob (A/B measurement)
+    if (ts != ctx->stream) { CU(cudaEventRecord(ctx->ev_fork, ctx->stream)); CU(cudaStreamWaitEvent(ts, ctx->ev_fork, 0)); }
+    CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, (const float4*)ctx->tgt_nrm_sorted.p, n, ctx->T, ctx->tsort.keys_sorted,
+                            (const unsigned int*)ctx->bbox.p + 7, (unsigned char*)ctx->lv_flags.p, (unsigned int*)ctx->lv_tiles.p, (int*)ctx->delta_a.p,
+                            (int*)ctx->delta_b.p, (unsigned int*)ctx->leaf_rank.p, (unsigned int*)ctx->leaf_start.p, (unsigned int*)ctx->node_rank.p,
+                            (unsigned int*)ctx->child_start.p, (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ts, &launches));
     CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
-                                 (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, 0, ctx->n_sms,
-                                 ctx->stream, &launches));
+                                 (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, 0, ctx->n_sms, ts, &launches));
     CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
-                                 (unsigned int*)ctx->adj1.p, (float4*)ctx->adj1_box.p, ctx->adj1_capacity, 1, ctx->n_sms,
-                                 ctx->stream, &launches));
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+                                 (unsigned int*)ctx->adj1.p, (float4*)ctx->adj1_box.p, ctx->adj1_capacity, 1, ctx->n_sms, ts, &launches));
+    CU(cudaEventRecord(ctx->ev[1], ts));
+    if (ts != ctx->stream) { CU(cudaEventRecord(ctx->ev_index_ready, ts)); ctx->index_pending = true; }
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     ctx->grid_built = true;
     return 0;
 }
 
-// Sorts the source into the cell order of its own grid (Morton order).
+// Sorts the source into the cell order of its own grid (Morton order); points with a non-finite coordinate keep a slot at the end.
 int build_source(icp_gpu_ctx* ctx) {
     const int n = ctx->n_src;
     ctx->Ts = pick_T(n, true);
-    const size_t n1 = (size_t)(n > 0 ? n : 1), cells1 = ((size_t)1 << ctx->Ts) + 1;
-    if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4)) ||
-        ensure(ctx, ctx->keys, (n1 + 2) * 4) || ensure(ctx, ctx->ranks, n1 * 4) || ensure(ctx, ctx->scell_start, cells1 * 4) ||
-        ensure(ctx, ctx->block_sums, ((cells1 > n1 + 2 ? cells1 : n1 + 2) / 4096 + 2) * 4) || ensure(ctx, ctx->sgrid, sizeof(GridParams)) ||
-        ensure(ctx, ctx->bbox, 64))
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4)) || ensure_sort(ctx, ctx->ssort, n, ctx->Ts) ||
+        ensure(ctx, ctx->sgrid, sizeof(GridParams)))
         return ICP_GPU_E_CUDA;
     int launches = 0;
-    CU(icp_launch_grid_build((const float4*)ctx->src_raw_pts.p, (const float4*)ctx->src_raw_nrm.p, n, ctx->Ts, (GridParams*)ctx->sgrid.p,
-                             (unsigned int*)ctx->bbox.p, (unsigned int*)ctx->keys.p, (unsigned int*)ctx->ranks.p,
-                             (unsigned int*)ctx->scell_start.p, (unsigned int*)ctx->block_sums.p, (float4*)ctx->src_pts.p,
-                             (float4*)ctx->src_nrm.p, 1, ctx->stream, &launches));
+    CU(icp_launch_cloud_sort((const float4*)ctx->src_raw_pts.p, (const float4*)ctx->src_raw_nrm.p, n, ctx->Ts, (GridParams*)ctx->sgrid.p, (unsigned int*)ctx->sbbox.p,
+                             (unsigned int*)ctx->ssort.keys_a.p, (unsigned int*)ctx->ssort.keys_b.p, (unsigned int*)ctx->ssort.idx_a.p,
+                             (unsigned int*)ctx->ssort.idx_b.p, (unsigned int*)ctx->ssort.tile_hist.p, (float4*)ctx->src_pts.p,
+                             (float4*)ctx->src_nrm.p, nullptr, &ctx->ssort.keys_sorted, &ctx->ssort.msd_shift, ctx->stream, &launches));
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     return 0;
 }
@@ -270,6 +297,7 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     if (target) {
+        if (join_index(ctx)) return ICP_GPU_E_CUDA;      // the previous build's tail (aux_stream) still reads the scratch this upload resets
         if (upload_cloud(ctx, xyz, nrm, rgba, n, dev, ctx->tgt_pts, ctx->tgt_nrm, 0)) return ICP_GPU_E_CUDA;
         ctx->n_tgt = (int)n;
         // buildIndex: the grid is always built (cheap), the matcher choice is made per call
@@ -286,8 +314,8 @@ int set_cloud(icp_gpu_ctx* ctx, bool target, const float* xyz, const float* nrm,
         if (ensure(ctx, ctx->partials, (size_t)ctx->n_reduce_blocks * ICP_NRED * sizeof(double))) return ICP_GPU_E_CUDA;
         if (build_source(ctx)) return ICP_GPU_E_CUDA;
     }
-    // a new cloud invalidates the neighbours remembered from earlier searches
-    if (ctx->n_src > 0 && ctx->nn_pos.p) { CU(icp_launch_fill_int((int*)ctx->nn_pos.p, ctx->n_src, -1, ctx->stream)); ctx->stats.n_kernel_launches += 1; }
+    // a new cloud invalidates the neighbours remembered from earlier searches: the next search resets them (seed kernel or fill)
+    ctx->nn_stale = true;
     // Host arrays are only borrowed for the duration of the call: wait for the copies (not for the index build, which
     // keeps running on the compute stream).  The device-pointer forms are fully asynchronous.
     if (!dev && n > 0) CU(cudaEventSynchronize(ctx->ev_copied[target ? 0 : 1]));
@@ -400,7 +428,6 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.src_pts = (const float4*)c->src_pts.p; a.src_nrm = (const float4*)c->src_nrm.p; a.n_src = c->n_src;
     a.mask = (const unsigned int*)c->mask.p; a.desc = (const IterDesc*)c->desc.p;
     a.state_ro = (const DevState*)c->state.p; a.state = (DevState*)c->state.p;
-    a.grid = (const GridParams*)c->grid.p; a.cell_start = (const unsigned int*)c->cell_start.p;
     a.tgt_pts = (const float4*)(grid_order ? c->tgt_pts_sorted.p : c->tgt_pts.p);
     a.tgt_nrm = (const float4*)(grid_order ? c->tgt_nrm_sorted.p : c->tgt_nrm.p);
     a.n_tgt = c->n_tgt;
@@ -449,6 +476,26 @@ void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     }
 }
 
+// Every query starts its search from the neighbour it had the last time it was searched (nn_pos / nn_leaf).  After a new
+// cloud those are meaningless (nn_stale): they are replaced by seeds read off the target's sorted keys at the current pose
+// (grid.cu; queries that still have a neighbour keep it), or reset to "none".
+int refresh_seeds(icp_gpu_ctx* ctx, int algo, bool allow_seed) {
+    if (algo != 0 || ctx->n_src <= 0 || !ctx->nn_pos.p) return 0;
+    const bool seed = allow_seed && ctx->n_tgt > 0 && ctx->grid_built && !getenv("ICP_GPU_NO_GRID_SEED");
+    if (seed) {
+        CU(icp_launch_seed_from_keys((const float4*)ctx->src_pts.p, ctx->n_src, (const DevState*)ctx->state.p, (const GridParams*)ctx->grid.p,
+                                     ctx->tsort.keys_sorted, ctx->n_tgt, (const unsigned int*)ctx->bbox.p + 7, (const unsigned int*)ctx->tsort.msd.p,
+                                     ctx->tsort.msd_shift, (const unsigned int*)ctx->leaf_rank.p, (int*)ctx->nn_pos.p, (int*)ctx->nn_leaf.p,
+                                     ctx->nn_stale ? 1 : 0, ctx->stream));
+        ctx->stats.n_kernel_launches += 1;
+    } else if (ctx->nn_stale) {
+        CU(icp_launch_fill_int((int*)ctx->nn_pos.p, ctx->n_src, -1, ctx->stream));
+        ctx->stats.n_kernel_launches += 1;
+    }
+    ctx->nn_stale = false;
+    return 0;
+}
+
 // Enqueue the whole loop.  ev_marks (nullable): events recorded around each stage for the timings report.
 int enqueue_iterations(icp_gpu_ctx* ctx, const Plan& plan, int algo, std::vector<cudaEvent_t>* ev_marks) {
     MatchArgs ma; ReduceArgs ra;
@@ -476,6 +523,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is already pending");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
+    if (join_index(ctx)) return ICP_GPU_E_CUDA;
     Plan plan;
     rc = make_plan(ctx, plan); if (rc) return rc;
     const int algo = choose_algorithm(ctx);
@@ -504,13 +552,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
     ctx->stats.n_kernel_launches += 1;
-    if (algo == 0 && ctx->n_src > 0 && ctx->n_tgt > 0 && ctx->grid_built && !getenv("ICP_GPU_NO_GRID_SEED")) {
-        // queries without a remembered neighbour start from a point of their own grid cell's neighbourhood (grid.cu)
-        CU(icp_launch_seed_from_grid((const float4*)ctx->src_pts.p, ctx->n_src, (const DevState*)ctx->state.p, (const GridParams*)ctx->grid.p,
-                                     (const unsigned int*)ctx->cell_start.p, ctx->T, (const unsigned int*)ctx->leaf_rank.p,
-                                     (int*)ctx->nn_pos.p, (int*)ctx->nn_leaf.p, ctx->stream));
-        ctx->stats.n_kernel_launches += 1;
-    }
+    rc = refresh_seeds(ctx, algo, true); if (rc) return rc;
 
     std::vector<cudaEvent_t> marks;
     if (timings) {
@@ -665,6 +707,8 @@ int icp_gpu_create(icp_gpu_ctx** out, int device) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->stream = ctx->own_stream;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_index_ready, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
                                            cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -686,14 +730,15 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     peer_close(ctx);
     if (ctx->peer_box) cudaFree(ctx->peer_box);
     DeviceBuf* bufs[] = {&ctx->stage, &ctx->stage2, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
-                         &ctx->grid, &ctx->bbox, &ctx->keys, &ctx->ranks, &ctx->cell_start, &ctx->block_sums, &ctx->state, &ctx->desc, &ctx->mask,
+                         &ctx->grid, &ctx->bbox, &ctx->sbbox, &ctx->lv_flags, &ctx->lv_tiles, &ctx->delta_a, &ctx->delta_b, &ctx->tsort.keys_a, &ctx->tsort.keys_b, &ctx->tsort.idx_a, &ctx->tsort.idx_b, &ctx->tsort.tile_hist, &ctx->tsort.msd, &ctx->ssort.keys_a, &ctx->ssort.keys_b, &ctx->ssort.idx_a, &ctx->ssort.idx_b, &ctx->ssort.tile_hist, &ctx->ssort.msd, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
-                         &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->scell_start, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->pstart, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
+                         &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->order_dev,
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
                          &ctx->nrm_out_dev, &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
@@ -702,6 +747,9 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_index_ready) cudaEventDestroy(ctx->ev_index_ready);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -715,6 +763,8 @@ int icp_gpu_set_stream(icp_gpu_ctx* ctx, void* cuda_stream) {
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->aux_stream));
+    ctx->index_pending = false;
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return ICP_GPU_OK;
 }
@@ -722,6 +772,7 @@ int icp_gpu_set_stream(icp_gpu_ctx* ctx, void* cuda_stream) {
 int icp_gpu_synchronize(icp_gpu_ctx* ctx) {
     if (!ctx) return ICP_GPU_E_ARG;
     if (bind(ctx)) return ICP_GPU_E_CUDA;
+    if (join_index(ctx)) return ICP_GPU_E_CUDA;
     CU(cudaStreamSynchronize(ctx->stream));
     return ICP_GPU_OK;
 }
@@ -820,6 +871,7 @@ int icp_gpu_target_normals(icp_gpu_ctx* ctx, int32_t k, const float viewpoint[3]
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     const int n = ctx->n_tgt;
     if (n <= 0) return ICP_GPU_OK;
+    if (join_index(ctx)) return ICP_GPU_E_CUDA;
     if (ensure(ctx, ctx->nrm_out_dev, (size_t)n * 16 + 256)) return ICP_GPU_E_CUDA;
     NormalArgs a; memset(&a, 0, sizeof(a));
     a.pts = (const float4*)ctx->tgt_pts_sorted.p; a.n = n;
@@ -919,6 +971,7 @@ int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t*
     if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
+    if (join_index(ctx)) return ICP_GPU_E_CUDA;
     const int n = ctx->n_src;
     const int nq = sel_idx ? (int)n_sel : n;
     if (sel_idx && (n_sel < 0 || n_sel > n)) return fail(ctx, ICP_GPU_E_ARG, "n_sel %lld", (long long)n_sel);
@@ -943,6 +996,7 @@ int icp_gpu_query_matches(icp_gpu_ctx* ctx, const float pose[16], const int32_t*
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
     const int algo = choose_algorithm(ctx);
+    rc = refresh_seeds(ctx, algo, false); if (rc) return rc;       // stages 2-4 at one pose: an unseeded search unless a registration left neighbours
     MatchArgs ma; fill_match_args(ctx, ma, algo, DESC_QUERY, true);
     int launches = 1;
     CU(icp_launch_match(ma, algo, ctx->n_sms, ctx->stream, &launches));
@@ -1009,6 +1063,7 @@ int icp_gpu_iteration_begin(icp_gpu_ctx* ctx, const float pose_in[16]) {
     if (ctx->peer_world > 1) return fail(ctx, ICP_GPU_E_STATE, "peers are attached: icp_gpu_estimate_pose is the point-sharded registration (icp_gpu_peer_detach first)");
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
+    if (join_index(ctx)) return ICP_GPU_E_CUDA;
     IterDesc d; memset(&d, 0, sizeof(d));
     d.stride = 1; d.mask_word_offset = -1; d.filter_finite = 0; d.proba = -1.0f;
     for (int i = 0; i < ICP_MAX_ITERS; ++i) ctx->h_desc[i] = d;      // every iteration of the shard loop: all points
@@ -1017,6 +1072,7 @@ int icp_gpu_iteration_begin(icp_gpu_ctx* ctx, const float pose_in[16]) {
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
     ctx->shard_open = true; ctx->shard_algo = choose_algorithm(ctx); ctx->shard_iters = 0;
+    rc = refresh_seeds(ctx, ctx->shard_algo, true); if (rc) return rc;
     return ICP_GPU_OK;
 }
 

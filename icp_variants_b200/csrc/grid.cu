@@ -1,53 +1,44 @@
 // grid.cu -- buildIndex: the on-device search structure that replaces FLANN's kd-tree
 // (reference: NearestNeighborSearchFlann::buildIndex, NearestNeighbor.h:122-141 / :209-232).
 //
-// Structure: a uniform grid of 2^T cells whose cell codes are Morton-style bit interleavings of
-// the per-axis cell indices (the axis taken at each bit is chosen so that cells end up near-cubic).
-// Points are counting-sorted by cell code (one radix pass, radix 2^T), and the exclusive prefix sum
-// of the per-cell counts, cell_start[0..2^T], doubles as an implicit binary tree: the node at depth d
-// with code prefix p owns points [cell_start[p << (T-d)], cell_start[(p+1) << (T-d)]).  No node
-// storage, no pointers; empty subtrees are recognised by an empty range.
+// Structure: a uniform grid of 2^T cells (T = 30 for a target: 10 bits per axis) whose cell codes are Morton-style
+// bit interleavings of the per-axis cell indices (the axis taken at each bit is the currently longest one, so cells end up
+// near-cubic).  The cloud is sorted by (cell code, original index) with a stable LSD RADIX SORT -- 3 passes of 10-11 bits,
+// every pass = per-tile digit histograms + a ranking scatter (warp-level multi-split with match.any, no atomics in the
+// ranking: the order inside a cell is the original index order, so two uploads of the same cloud give the same structure
+// bit for bit).  There is no dense cell table: the implicit binary tree over the cells is read off the SORTED KEYS -- the
+// node of depth d around point i is the maximal run of points around i whose neighbouring keys share >= d leading bits
+// (delta(i) = common-prefix length of key[i-1] and key[i]).  Leaves = the shallowest such nodes with <= 32 points, level-l
+// nodes = the shallowest with <= 32 nodes of level l-1; both are found per element from a +-32 window of delta values.
 //
-// Launches (all on one stream, no host synchronisation): pack -> bbox -> params -> memset ->
-// keys+count -> scan (3) -> scatter.
+// Launches of one target build (one stream, no host synchronisation): pack+bbox, keys+hist, (scatter, hist) x passes,
+// leaf flags, leaf ranks, leaf boxes, level-1 flags / ranks / boxes, one single-block kernel for all levels above,
+// two adjacency kernels.
 #include "icp_internal.cuh"
 #include <string.h>
 #include <stdlib.h>
 
-// ---------------------------------------------------------------------------- pack AoS3 -> float4
-__global__ void pack_cloud_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const uint8_t* __restrict__ rgba,
-                                  int n, float4* __restrict__ pts, float4* __restrict__ nrmo) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // Layout in HBM: points {x,y,z,original index bits}, normals {nx,ny,nz,rgba bits}.
-    unsigned int c = 0;
-    if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
-    float4 p; p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2]; p.w = __int_as_float(i);
-    float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
-    if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
-    pts[i] = p; nrmo[i] = m;
-}
-
-cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
-                                  cudaStream_t s) {
-    if (n <= 0) return cudaSuccess;
-    pack_cloud_kernel<<<(n + 255) / 256, 256, 0, s>>>(xyz, nrm, rgba, n, pts, nrmo);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------- bounding box
+// ---------------------------------------------------------------------------- pack AoS3 -> float4, bounding box
 __device__ __forceinline__ unsigned int enc_f(float f) { unsigned int b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float dec_f(unsigned int e) { return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e); }
 
-// bbox[0..2] = encoded min, bbox[3..5] = encoded max (initialised to 0xFFFFFFFF / 0)
-__global__ void bbox_kernel(const float4* __restrict__ pts, int n, unsigned int* __restrict__ bbox) {
+// Layout in HBM: points {x,y,z,original index bits}, normals {nx,ny,nz,rgba bits}.
+// bbox[0..2] = encoded min, bbox[3..5] = encoded max of the finite points (initialised to 0xFFFFFFFF / 0).
+__global__ void __launch_bounds__(256) pack_bbox_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const uint8_t* __restrict__ rgba,
+                                                        int n, float4* __restrict__ pts, float4* __restrict__ nrmo, unsigned int* __restrict__ bbox) {
     unsigned int mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = pts[i];
-        if (!finite3(p.x, p.y, p.z)) continue;
-        const unsigned int e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
+        unsigned int c = 0;
+        if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
+        float4 p; p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2]; p.w = __int_as_float(i);
+        float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
+        if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
+        pts[i] = p; nrmo[i] = m;
+        if (finite3(p.x, p.y, p.z)) {
+            const unsigned int e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], e[a]); mx[a] = max(mx[a], e[a]); }
+            for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], e[a]); mx[a] = max(mx[a], e[a]); }
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -70,16 +61,28 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, unsigned int*
     }
 }
 
-__global__ void grid_params_kernel(const unsigned int* __restrict__ bbox, int T, GridParams* __restrict__ g) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    GridParams P;
+cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
+                                  unsigned int* bbox, cudaStream_t s) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(bbox, 0xFF, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bbox + 3, 0x00, 5 * sizeof(unsigned int), s)) != cudaSuccess) return e;   // max[3], spare, non-finite counter
+    if (n <= 0) return cudaSuccess;
+    const int nb = min((n + 255) / 256, 148 * 4);
+    pack_bbox_kernel<<<nb, 256, 0, s>>>(xyz, nrm, rgba, n, pts, nrmo, bbox);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- grid parameters and cell codes
+// A pure function of the bounding box: every block that needs the parameters derives them itself (no launch of its own);
+// the oracle restates this arithmetic (oracle/icp_oracle.c: voxel levels), hence no FMA.
+__device__ void grid_params_from_bbox(const unsigned int* __restrict__ bbox, int T, GridParams& P) {
     float e[3], maxabs[3];
     const bool empty = bbox[0] == 0xFFFFFFFFu && bbox[3] == 0u;
     for (int a = 0; a < 3; ++a) {
         const float lo = empty ? 0.f : dec_f(bbox[a]), hi = empty ? 0.f : dec_f(bbox[3 + a]);
         P.o[a] = lo;
         maxabs[a] = fmaxf(fabsf(lo), fabsf(hi));
-        e[a] = fmaxf(psub(hi, lo), padd(1e-20f, pmul(1e-6f, maxabs[a])));   // zero-extent axes stay well defined (no FMA: the oracle restates this)
+        e[a] = fmaxf(psub(hi, lo), padd(1e-20f, pmul(1e-6f, maxabs[a])));   // zero-extent axes stay well defined
         P.bits[a] = 0;
     }
     // Level k of the implicit tree halves the axis whose cells are currently the longest.
@@ -98,7 +101,6 @@ __global__ void grid_params_kernel(const unsigned int* __restrict__ bbox, int T,
         P.delta[a] = 1e-3f * P.h[a] + 1e-6f * maxabs[a];
     }
     P.T = T; P.axis_seq = seq; P.n_finite = 0; P.pad = 0;
-    *g = P;
 }
 
 __device__ __forceinline__ int cell_index(const GridParams& g, int a, float x) {
@@ -124,23 +126,64 @@ __device__ __forceinline__ unsigned int cell_code(const GridParams& g, float x, 
     return code;
 }
 
-// key per point + rank within its cell (the count array becomes cell_start after the scan)
-__global__ void keys_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
-                            unsigned int* __restrict__ keys, unsigned int* __restrict__ ranks, unsigned int* __restrict__ counts) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const GridParams g = *gp;
-    const float4 p = pts[i];
-    if (!finite3(p.x, p.y, p.z)) { keys[i] = 0xFFFFFFFFu; return; }   // can never win the strict '>' scan of NearestNeighbor.h:87
-    const unsigned int c = cell_code(g, p.x, p.y, p.z);
-    keys[i] = c;
-    ranks[i] = atomicAdd(&counts[c], 1u);
+// ---------------------------------------------------------------------------- stable LSD radix sort of (key, index)
+// key = cell code (T bits); a point with a non-finite coordinate gets 1 << T: it sorts after every cell (sources keep such
+// points at the end -- every point needs a slot; targets simply never look past n_finite).  T + 1 bits are sorted in
+// passes of <= 11 bits.  A pass: every tile (256 threads x ipt items, contiguous) publishes its digit histogram; the scatter
+// kernel of the pass derives a tile's first output slot per digit from those rows (digits before it, the same digit in earlier
+// tiles), ranks the tile's items per warp (contiguous chunk per warp, rounds of 32 in order; match.any groups equal
+// digits, the group's lowest lane advances the warp's running count) and writes each item to its slot: stable, no
+// atomics, deterministic.  The histogram of pass 0 is produced by the key kernel; the last pass moves the payload
+// (point and normal records) instead of the index.
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_MAX_BITS 11
+#define RS_MAX_BINS (1 << RS_MAX_BITS)
+
+__global__ void __launch_bounds__(RS_THREADS) keys_kernel(const float4* __restrict__ pts, int n, int T, const unsigned int* __restrict__ bbox,
+                                                          GridParams* __restrict__ gp_out, unsigned int* __restrict__ keys, int tile_items, int shift,
+                                                          int bits, unsigned int* __restrict__ tile_hist, unsigned int* __restrict__ nonfinite_counter) {
+    __shared__ GridParams g;
+    __shared__ unsigned int hist[RS_MAX_BINS];
+    const int bins = 1 << bits;
+    for (int d = threadIdx.x; d < bins; d += RS_THREADS) hist[d] = 0u;
+    if (threadIdx.x == 0) { grid_params_from_bbox(bbox, T, g); if (blockIdx.x == 0) *gp_out = g; }
+    __syncthreads();
+    const unsigned int mask = (unsigned int)bins - 1u;
+    const long long base = (long long)blockIdx.x * tile_items;
+    unsigned int bad = 0;
+    for (int k = threadIdx.x; k < tile_items; k += RS_THREADS) {
+        const long long i = base + k;
+        if (i >= n) break;
+        const float4 p = pts[i];
+        unsigned int key;
+        if (finite3(p.x, p.y, p.z)) key = cell_code(g, p.x, p.y, p.z);
+        else { key = 1u << T; ++bad; }                    // can never win the strict '>' scan of NearestNeighbor.h:87
+        keys[i] = key;
+        atomicAdd(&hist[(key >> shift) & mask], 1u);
+    }
+    bad = __reduce_add_sync(0xFFFFFFFFu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite_counter, bad);
+    __syncthreads();
+    for (int d = threadIdx.x; d < bins; d += RS_THREADS) tile_hist[(size_t)blockIdx.x * RS_MAX_BINS + d] = hist[d];
 }
 
-// ---------------------------------------------------------------------------- exclusive scan over 2^T+1 counters
-#define SCAN_THREADS 256
-#define SCAN_ITEMS 16
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const unsigned int* __restrict__ keys, int n, int tile_items, int shift, int bits,
+                                                                unsigned int* __restrict__ tile_hist) {
+    __shared__ unsigned int hist[RS_MAX_BINS];
+    const int bins = 1 << bits;
+    for (int d = threadIdx.x; d < bins; d += RS_THREADS) hist[d] = 0u;
+    __syncthreads();
+    const unsigned int mask = (unsigned int)bins - 1u;
+    const long long base = (long long)blockIdx.x * tile_items;
+    for (int k = threadIdx.x; k < tile_items; k += RS_THREADS) {
+        const long long i = base + k;
+        if (i >= n) break;
+        atomicAdd(&hist[(keys[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < bins; d += RS_THREADS) tile_hist[(size_t)blockIdx.x * RS_MAX_BINS + d] = hist[d];
+}
 
 __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total) {
     __shared__ unsigned int warp_sums[32];
@@ -163,96 +206,157 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
     return r;
 }
 
-__global__ void scan_tile_sums_kernel(const unsigned int* __restrict__ data, int n, unsigned int* __restrict__ tile_sums) {
-    const int base = blockIdx.x * SCAN_TILE;
-    unsigned int s = 0;
-    if (base + SCAN_TILE <= n) {                      // full tile: 16-byte loads (base is a multiple of 4096 entries)
-        const uint4* d4 = reinterpret_cast<const uint4*>(data + base);
-        for (int k = threadIdx.x; k < SCAN_TILE / 4; k += SCAN_THREADS) { const uint4 v = d4[k]; s += (v.x + v.y) + (v.z + v.w); }
-    } else {
-        for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_THREADS) { const int i = base + k; if (i < n) s += data[i]; }
-    }
-    s = __reduce_add_sync(0xFFFFFFFFu, s);
-    __shared__ unsigned int ws[SCAN_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+// idx_in == nullptr: the identity (pass 0).  pts_in != nullptr: last pass -- the payload is moved instead of the index.
+// msd_start (nullable, last pass): first output slot of every digit of the pass, bins + 1 entries.
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ idx_in,
+                                                                   unsigned int* __restrict__ keys_out, unsigned int* __restrict__ idx_out, int n,
+                                                                   int tile_items, int n_tiles, int shift, int bits,
+                                                                   const unsigned int* __restrict__ tile_hist, const float4* __restrict__ pts_in,
+                                                                   const float4* __restrict__ nrm_in, float4* __restrict__ pts_out,
+                                                                   float4* __restrict__ nrm_out, unsigned int* __restrict__ msd_start) {
+    __shared__ unsigned short wcnt[RS_WARPS][RS_MAX_BINS];     // per warp and digit: count, then tile-relative first slot, then running slot
+    __shared__ unsigned int base[RS_MAX_BINS];                 // per digit: first output slot of this tile
+    const unsigned int FULL = 0xFFFFFFFFu;
+    const int bins = 1 << bits;
+    const unsigned int mask = (unsigned int)bins - 1u;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    for (int d = threadIdx.x; d < RS_WARPS * bins; d += RS_THREADS) wcnt[d / bins][d % bins] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) { unsigned int t = 0; for (int w = 0; w < SCAN_THREADS / 32; ++w) t += ws[w]; tile_sums[blockIdx.x] = t; }
-}
-
-// single block: exclusive scan of up to 1024*8 tile sums in place
-__global__ void scan_tile_offsets_kernel(unsigned int* __restrict__ tile_sums, int n_tiles) {
-    __shared__ unsigned int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n_tiles; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const unsigned int v = i < n_tiles ? tile_sums[i] : 0u;
-        __shared__ unsigned int total;
-        const unsigned int ex = block_exclusive_scan(v, &total);
-        const unsigned int carry = carry_s;
-        if (i < n_tiles) tile_sums[i] = ex + carry;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
-    }
-}
-
-__global__ void scan_apply_kernel(unsigned int* __restrict__ data, int n, const unsigned int* __restrict__ tile_offsets) {
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    unsigned int v[SCAN_ITEMS]; unsigned int s = 0;
-    const bool full = blockIdx.x * SCAN_TILE + SCAN_TILE <= n;      // 16-byte accesses on full tiles
-    if (full) {
-        const uint4* d4 = reinterpret_cast<const uint4*>(data + base);
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 4; ++k) { const uint4 q = d4[k]; v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
-    } else {
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; v[k] = i < n ? data[i] : 0u; s += v[k]; }
-    }
-    unsigned int ex = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
-    if (full) {
-        uint4* d4 = reinterpret_cast<uint4*>(data + base);
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
-            uint4 q;
-            q.x = ex; ex += v[4 * k]; q.y = ex; ex += v[4 * k + 1]; q.z = ex; ex += v[4 * k + 2]; q.w = ex; ex += v[4 * k + 3];
-            d4[k] = q;
+    const int chunk = tile_items / RS_WARPS;                   // a multiple of 32
+    const long long w0 = (long long)blockIdx.x * tile_items + (long long)w * chunk;
+    // phase A: digit counts of the warp's chunk
+    for (int r = 0; r < chunk; r += 32) {
+        const long long i = w0 + r + lane;
+        const bool valid = i < n;
+        const unsigned int vm = __ballot_sync(FULL, valid);
+        if (valid) {
+            const unsigned int dg = (keys_in[i] >> shift) & mask;
+            const unsigned int peers = __match_any_sync(vm, dg);
+            if ((peers & lt) == 0u) wcnt[w][dg] = (unsigned short)(wcnt[w][dg] + __popc(peers));
         }
-    } else {
+        __syncwarp();
+        if (vm != FULL) break;
+    }
+    __syncthreads();
+    // per digit: warp counts -> exclusive prefix over the warps; the same digit in earlier tiles; the digit's total
+    unsigned int before[RS_MAX_BINS / RS_THREADS];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) { const int i = base + k; if (i < n) data[i] = ex; ex += v[k]; }
+    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
+        const int d = k * RS_THREADS + threadIdx.x;
+        before[k] = 0u;
+        if (d < bins) {
+            unsigned int acc = 0;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ++ww) { const unsigned int c = wcnt[ww][d]; wcnt[ww][d] = (unsigned short)acc; acc += c; }
+            unsigned int b0 = 0, a0 = 0, b1 = 0, a1 = 0;
+            int t = 0;
+            for (; t + 1 < n_tiles; t += 2) {                  // two independent chains of (L2-resident) loads
+                const unsigned int h0 = __ldg(&tile_hist[(size_t)t * RS_MAX_BINS + d]), h1 = __ldg(&tile_hist[(size_t)(t + 1) * RS_MAX_BINS + d]);
+                a0 += h0; a1 += h1;
+                if (t < (int)blockIdx.x) b0 += h0;
+                if (t + 1 < (int)blockIdx.x) b1 += h1;
+            }
+            if (t < n_tiles) { const unsigned int h0 = __ldg(&tile_hist[(size_t)t * RS_MAX_BINS + d]); a0 += h0; if (t < (int)blockIdx.x) b0 += h0; }
+            before[k] = b0 + b1;
+            base[d] = a0 + a1;                                 // the digit's total, scanned below
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the totals in digit order: every thread owns `per` consecutive digits
+        const int per = (bins + RS_THREADS - 1) / RS_THREADS;
+        unsigned int loc[RS_MAX_BINS / RS_THREADS]; unsigned int s = 0;
+#pragma unroll
+        for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
+            const int d = threadIdx.x * per + k;
+            loc[k] = (k < per && d < bins) ? base[d] : 0u;
+            s += loc[k];
+        }
+        unsigned int ex = block_exclusive_scan(s, nullptr);    // ends with a barrier: every total has been read
+#pragma unroll
+        for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
+            const int d = threadIdx.x * per + k;
+            if (k < per && d < bins) { base[d] = ex; ex += loc[k]; }
+        }
+    }
+    __syncthreads();
+    if (msd_start && blockIdx.x == 0) {
+        for (int d = threadIdx.x; d < bins; d += RS_THREADS) msd_start[d] = base[d];
+        if (threadIdx.x == 0) msd_start[bins] = (unsigned int)n;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
+        const int d = k * RS_THREADS + threadIdx.x;
+        if (d < bins) base[d] += before[k];
+    }
+    __syncthreads();
+    // phase B: the same rounds again; the group's lowest lane advances the warp's running slot of the digit
+    for (int r = 0; r < chunk; r += 32) {
+        const long long i = w0 + r + lane;
+        const bool valid = i < n;
+        const unsigned int vm = __ballot_sync(FULL, valid);
+        if (valid) {
+            const unsigned int key = keys_in[i];
+            const unsigned int dg = (key >> shift) & mask;
+            const unsigned int peers = __match_any_sync(vm, dg);
+            const int leader = __ffs((int)peers) - 1;
+            unsigned int old = 0;
+            if (lane == leader) { old = wcnt[w][dg]; wcnt[w][dg] = (unsigned short)(old + __popc(peers)); }
+            old = __shfl_sync(peers, old, leader);
+            const unsigned int pos = base[dg] + old + (unsigned int)__popc(peers & lt);
+            const unsigned int src = idx_in ? idx_in[i] : (unsigned int)i;
+            keys_out[pos] = key;
+            if (pts_in) { pts_out[pos] = pts_in[src]; nrm_out[pos] = nrm_in[src]; }
+            else idx_out[pos] = src;
+        }
+        __syncwarp();
+        if (vm != FULL) break;
     }
 }
 
-static cudaError_t launch_exclusive_scan(unsigned int* data, int n, unsigned int* block_sums, cudaStream_t s, int* launches) {
-    const int n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    scan_tile_sums_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(data, n, block_sums);
-    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(block_sums, n_tiles);
-    scan_apply_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(data, n, block_sums);
-    if (launches) *launches += 3;
+void icp_radix_plan(int n, int T, IcpRadixPlan* p) {
+    const int total = T + 1;
+    p->n_pass = (total + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    const int lo = total / p->n_pass, extra = total % p->n_pass;
+    int shift = 0;
+    for (int k = 0; k < p->n_pass; ++k) { p->bits[k] = lo + (k < extra ? 1 : 0); p->shift[k] = shift; shift += p->bits[k]; }
+    // 16 items per thread; larger clouds get larger tiles so that the per-tile histogram rows every scatter block sums stay few
+    long long ipt = 16;
+    while ((long long)n > ipt * RS_THREADS * 160 && ipt < 224) ipt += 16;
+    p->tile_items = (int)(ipt * RS_THREADS);
+    p->n_tiles = n > 0 ? (int)(((long long)n + p->tile_items - 1) / p->tile_items) : 0;
+}
+
+size_t icp_radix_hist_words(int n, int T) { IcpRadixPlan p; icp_radix_plan(n, T, &p); return (size_t)(p.n_tiles > 0 ? p.n_tiles : 1) * RS_MAX_BINS; }
+
+// Sorts a packed cloud into (cell code, original index) order.  keys_a / keys_b: n entries each (keys_sorted ends up in
+// *keys_sorted_out, one of the two); idx_a / idx_b: n entries each; bbox: filled by icp_launch_pack_cloud (bbox[7] = number of
+// non-finite points afterwards); msd_start: RS_MAX_BINS + 1 entries (nullable).
+cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid, unsigned int* bbox,
+                                  unsigned int* keys_a, unsigned int* keys_b, unsigned int* idx_a, unsigned int* idx_b,
+                                  unsigned int* tile_hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
+                                  unsigned int** keys_sorted_out, int* msd_shift_out, cudaStream_t s, int* n_launches) {
+    IcpRadixPlan p; icp_radix_plan(n, T, &p);
+    int launches = 0;
+    if (msd_shift_out) *msd_shift_out = p.shift[p.n_pass - 1];
+    unsigned int* kin = keys_a; unsigned int* kout = keys_b;
+    unsigned int* iin = nullptr; unsigned int* iout = idx_a;
+    // n == 0: one block still writes the (empty-cloud) grid parameters
+    keys_kernel<<<p.n_tiles > 0 ? p.n_tiles : 1, RS_THREADS, 0, s>>>(pts_in, n, T, bbox, grid, kin, p.tile_items, p.shift[0], p.bits[0], tile_hist, bbox + 7);
+    ++launches;
+    for (int k = 0; k < p.n_pass && n > 0; ++k) {
+        const bool last = k == p.n_pass - 1;
+        if (k > 0) { radix_hist_kernel<<<p.n_tiles, RS_THREADS, 0, s>>>(kin, n, p.tile_items, p.shift[k], p.bits[k], tile_hist); ++launches; }
+        radix_scatter_kernel<<<p.n_tiles, RS_THREADS, 0, s>>>(kin, iin, kout, iout, n, p.tile_items, p.n_tiles, p.shift[k], p.bits[k], tile_hist,
+                                                             last ? pts_in : nullptr, nrm_in, pts_sorted, nrm_sorted, last ? msd_start : nullptr);
+        ++launches;
+        unsigned int* t = kin; kin = kout; kout = t;
+        iin = iout; iout = (iout == idx_a) ? idx_b : idx_a;
+    }
+    if (keys_sorted_out) *keys_sorted_out = kin;
+    if (n_launches) *n_launches += launches;
     return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------- scatter into cell order
-__global__ void scatter_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n,
-                               const unsigned int* __restrict__ keys, const unsigned int* __restrict__ ranks,
-                               const unsigned int* __restrict__ cell_start, unsigned int n_cells, int keep_nonfinite,
-                               unsigned int* __restrict__ nonfinite_counter, float4* __restrict__ pts_sorted,
-                               float4* __restrict__ nrm_sorted) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned int k = keys[i];
-    unsigned int pos;
-    if (k == 0xFFFFFFFFu) {
-        if (!keep_nonfinite) return;
-        pos = cell_start[n_cells] + atomicAdd(nonfinite_counter, 1u);   // after the last cell; never part of any search
-    } else {
-        pos = cell_start[k] + ranks[i];
-    }
-    pts_sorted[pos] = pts[i];                        // .w already holds the original index: tie-break + API output
-    nrm_sorted[pos] = nrm[i];
 }
 
 __global__ void extract_order_kernel(const float4* __restrict__ pts_sorted, int n, int* __restrict__ order) {
@@ -268,253 +372,309 @@ __global__ void fill_int_kernel(int* __restrict__ p, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// First-iteration seeds from the cell table: a query that remembers no neighbour yet (nn_pos < 0) gets a point of the
-// smallest cell-tree node around its transformed position that holds any point (binary search over the depth: the count
-// of the node around a position is monotone in the depth).  The search uses a seed only as its starting bound and first
-// leaf, so any target point is a valid seed -- a near one lets the first iteration run like the later ones (fast path
-// for most queries) instead of walking the tree from the root for every query.
-__global__ void seed_from_grid_kernel(const float4* __restrict__ src_pts, int n_src, const DevState* __restrict__ st,
-                                      const GridParams* __restrict__ gp, const unsigned int* __restrict__ cs, int T,
-                                      const unsigned int* __restrict__ leaf_rank, int* __restrict__ nn_pos, int* __restrict__ nn_leaf) {
+cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
+    if (n > 0) fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- first-iteration seeds from the sorted keys
+// A query that remembers no neighbour (nn_pos < 0, or `reset`: a new cloud made every remembered neighbour stale) gets a
+// point of the smallest cell-tree node around its transformed position that holds any point: the keys are sorted, so that
+// is the lower bound of the query's cell code or its predecessor -- whichever shares the longer prefix with the code.  The
+// lower bound is searched inside the bucket of the code's most significant digit (msd_start, a by-product of the last
+// sorting pass).  The search uses a seed only as its starting bound and first leaf, so any target point is a valid seed -- a
+// near one lets the first iteration run like the later ones (fast path for most queries).
+__global__ void seed_from_keys_kernel(const float4* __restrict__ src_pts, int n_src, const DevState* __restrict__ st,
+                                      const GridParams* __restrict__ gp, const unsigned int* __restrict__ keys, int n_tgt,
+                                      const unsigned int* __restrict__ nonfinite, const unsigned int* __restrict__ msd_start, int msd_shift,
+                                      const unsigned int* __restrict__ leaf_rank, int* __restrict__ nn_pos, int* __restrict__ nn_leaf, int reset) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_src) return;
-    if (nn_pos[p] >= 0) return;
-    const unsigned int n_finite = cs[(size_t)1 << T];
-    if (n_finite == 0u) return;
+    if (!reset && nn_pos[p] >= 0) return;
+    int out_pos = -1, out_leaf = -1;
+    const int n_finite = n_tgt - (int)*nonfinite;
     const float4 s = src_pts[p];
     float P[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) P[k] = st->pose[k];
     float x, y, z;
     xform_point(P, s.x, s.y, s.z, x, y, z);
-    if (!finite3(x, y, z)) return;
-    const GridParams g = *gp;
-    const unsigned int c = cell_code(g, x, y, z);
-    int lo = 0, hi = T;                                  // smallest shift whose node is not empty (shift T = the whole cloud)
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const unsigned int pre = c >> mid;
-        const unsigned int cnt = cs[((size_t)pre + 1) << mid] - cs[(size_t)pre << mid];
-        if (cnt > 0u) hi = mid; else lo = mid + 1;
+    if (n_finite > 0 && finite3(x, y, z)) {
+        const GridParams g = *gp;
+        const unsigned int c = cell_code(g, x, y, z);
+        int lo = (int)msd_start[c >> msd_shift], hi = (int)msd_start[(c >> msd_shift) + 1];
+        if (hi > n_finite) hi = n_finite;
+        if (lo > hi) lo = hi;
+        while (lo < hi) {                                   // lower bound of c
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        int pos = lo;
+        if (pos >= n_finite) pos = n_finite - 1;
+        else if (pos > 0) {
+            const unsigned int xa = keys[pos] ^ c, xb = keys[pos - 1] ^ c;
+            if (xb < xa) pos = pos - 1;                     // smaller xor = longer common prefix
+        }
+        out_pos = pos; out_leaf = (int)(leaf_rank[pos + 1] - 1u);
     }
-    const unsigned int pre = c >> lo;
-    const unsigned int s0 = cs[(size_t)pre << lo], e0 = cs[((size_t)pre + 1) << lo];
-    if (e0 <= s0) return;
-    const unsigned int pos = s0 + ((e0 - s0) >> 1);
-    nn_pos[p] = (int)pos;
-    nn_leaf[p] = (int)(leaf_rank[pos + 1] - 1u);
+    if (reset || out_pos >= 0) { nn_pos[p] = out_pos; nn_leaf[p] = out_leaf; }
 }
 
-cudaError_t icp_launch_seed_from_grid(const float4* src_pts, int n_src, const DevState* st, const GridParams* grid, const unsigned int* cell_start,
-                                      int T, const unsigned int* leaf_rank, int* nn_pos, int* nn_leaf, cudaStream_t s) {
+cudaError_t icp_launch_seed_from_keys(const float4* src_pts, int n_src, const DevState* st, const GridParams* grid, const unsigned int* keys, int n_tgt,
+                                      const unsigned int* nonfinite, const unsigned int* msd_start, int msd_shift, const unsigned int* leaf_rank,
+                                      int* nn_pos, int* nn_leaf, int reset, cudaStream_t s) {
     if (n_src <= 0) return cudaSuccess;
-    seed_from_grid_kernel<<<(n_src + 255) / 256, 256, 0, s>>>(src_pts, n_src, st, grid, cell_start, T, leaf_rank, nn_pos, nn_leaf);
-    return cudaGetLastError();
-}
-
-cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s) {
-    if (n > 0) fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------- refinement of over-full finest cells
-// The dense table caps the sort key at T <= 24 bits; where the cloud is much denser than the grid (near the sensor) a
-// finest cell still holds dozens of points in arbitrary order.  Those cells get a local counting sort by 6 more bits
-// (2 per axis: the position inside the cell), so that the runs of 32 the leaves are cut from are compact.
-#define REFINE_MAX 1024
-// thread per sorted point: the first point of a finest cell with 33 .. REFINE_MAX points registers the cell
-__global__ void find_overfull_cells_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
-                                           const unsigned int* __restrict__ cs, int T, unsigned int* __restrict__ list,
-                                           unsigned int* __restrict__ n_list, unsigned int capacity) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || (unsigned int)i >= cs[(size_t)1 << T]) return;
-    const GridParams g = *gp;
-    const float4 p = pts[i];
-    const unsigned int c = cell_code(g, p.x, p.y, p.z);
-    const unsigned int s = cs[c], cnt = cs[(size_t)c + 1] - s;
-    if ((unsigned int)i == s && cnt > 32u && cnt <= REFINE_MAX) { const unsigned int k = atomicAdd(n_list, 1u); if (k < capacity) list[k] = c; }
-}
-
-__global__ void __launch_bounds__(128) refine_cells_kernel(const unsigned int* __restrict__ cs, const GridParams* __restrict__ gp,
-                                                           const unsigned int* __restrict__ list, const unsigned int* __restrict__ n_list,
-                                                           unsigned int capacity, float4* __restrict__ pts, float4* __restrict__ nrm) {
-    __shared__ float4 sp[REFINE_MAX];
-    __shared__ float4 sn[REFINE_MAX];
-    __shared__ unsigned short skey[REFINE_MAX];
-    __shared__ unsigned int hist[64];
-    const GridParams g = *gp;
-    const unsigned int n = min(*n_list, capacity);
-    for (unsigned int w = blockIdx.x; w < n; w += gridDim.x) {
-        const unsigned int c = list[w], s = cs[c], cnt = cs[c + 1] - s;
-        if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
-        __syncthreads();
-        for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
-            const float4 p = pts[s + k];
-            sp[k] = p; sn[k] = nrm[s + k];
-            unsigned int key = 0;
-            const float x[3] = {p.x, p.y, p.z};
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float u = pmul(psub(x[a], g.o[a]), g.inv_h[a]);
-                const float f = u - floorf(u);                      // position inside the cell (clamped cells: any value is fine)
-                const int q = min(max((int)(f * 4.0f), 0), 3);
-                key |= (unsigned int)(((q >> 1) & 1) << (5 - a)) | (unsigned int)((q & 1) << (2 - a));
-            }
-            skey[k] = (unsigned short)key;
-            atomicAdd(&hist[key], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { unsigned int acc = 0; for (int b = 0; b < 64; ++b) { const unsigned int v = hist[b]; hist[b] = acc; acc += v; } }
-        __syncthreads();
-        for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
-            const unsigned int pos = atomicAdd(&hist[skey[k]], 1u);
-            pts[s + pos] = sp[k]; nrm[s + pos] = sn[k];
-        }
-        __syncthreads();
-    }
-}
-
-cudaError_t icp_launch_refine_cells(const unsigned int* cell_start, int T, const GridParams* grid, unsigned int* list, unsigned int capacity,
-                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n, int n_sms, cudaStream_t s,
-                                    int* n_launches) {
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(n_list, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
-    if (n <= 0) return cudaSuccess;
-    find_overfull_cells_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_sorted, n, grid, cell_start, T, list, n_list, capacity);
-    refine_cells_kernel<<<n_sms * 4, 128, 0, s>>>(cell_start, grid, list, n_list, capacity, pts_sorted, nrm_sorted);
-    if (n_launches) *n_launches += 2;
+    seed_from_keys_kernel<<<(n_src + 255) / 256, 256, 0, s>>>(src_pts, n_src, st, grid, keys, n_tgt, nonfinite, msd_start, msd_shift, leaf_rank,
+                                                             nn_pos, nn_leaf, reset);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------- BVH over the sorted cloud
-// Leaves = nodes of the implicit cell tree with <= 32 points whose parent has more (an over-full finest cell is
-// cut into runs of 32): cell-aligned, hence pairwise disjoint in space -- a search ball meets only the few
-// leaves around it, unlike fixed runs of the Z-curve, whose boxes straddle the curve's jumps.
-__global__ void mark_leaves_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
-                                   const unsigned int* __restrict__ cs, int T, unsigned int* __restrict__ flags) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    const unsigned int n_finite = cs[(size_t)1 << T];
-    if ((unsigned int)i >= n_finite) { flags[i] = 0u; return; }
-    const GridParams g = *gp;
-    const float4 p = pts[i];
-    const unsigned int c = cell_code(g, p.x, p.y, p.z);
-    // smallest depth whose node holds <= 32 points (the count is monotone in the depth)
-    const unsigned int sT = cs[c], eT = cs[(size_t)c + 1];
-    if (eT - sT > 32u) { flags[i] = ((unsigned int)i - sT) % 32u == 0u ? 1u : 0u; return; }
-    int lo = 0, hi = T;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1, sh = T - mid;
-        const unsigned int pre = c >> sh;
-        const unsigned int cnt = cs[((size_t)pre + 1) << sh] - cs[(size_t)pre << sh];
-        if (cnt <= 32u) hi = mid; else lo = mid + 1;
-    }
-    const int sh = T - lo;
-    flags[i] = (unsigned int)i == cs[(size_t)(c >> sh) << sh] ? 1u : 0u;
+// Level 0 (leaves): elements = sorted points, delta(i) = number of leading bits (of T) key[i-1] and key[i] share
+// (T when equal; -1 before the first and after the last finite point).  Level l >= 1: elements = nodes of level l-1,
+// delta(k) = delta of the first element of node k one level down (the boundary between node k-1 and node k).  The cell-tree
+// node of depth d around element i is the maximal run around i whose inner boundaries all have delta >= d; an element starts
+// a node of the level iff it is the first element of the SHALLOWEST such run with <= 32 elements.  A finest cell (run of
+// equal keys) with more than 32 elements is cut at the positions divisible by 32.  Cell-aligned nodes are pairwise disjoint
+// in space -- a search ball meets only the few leaves around it, unlike fixed runs of the Z-curve, whose boxes straddle the
+// curve's jumps.
+#define LV_THREADS 256
+#define LV_ITEMS 4
+#define LV_TILE (LV_THREADS * LV_ITEMS)
+#define LV_HALO 32
+
+__device__ __forceinline__ int key_delta(unsigned int a, unsigned int b, int T) {
+    const unsigned int x = a ^ b;
+    return x ? __clz((int)x) - (32 - T) : T;
 }
 
-// flags have been exclusive-scanned in place: rank[i] = number of leaf starts before i
-__global__ void leaf_starts_kernel(const unsigned int* __restrict__ rank, int n, const unsigned int* __restrict__ cs, int T,
-                                   unsigned int* __restrict__ leaf_start, BvhDesc* __restrict__ bvh) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int n_finite = cs[(size_t)1 << T];
-    if (i < n && (unsigned int)i < n_finite && rank[i + 1] != rank[i]) leaf_start[rank[i]] = (unsigned int)i;
-    if (i == 0) {
-        const int L = (int)rank[n_finite];
-        leaf_start[L] = n_finite;
-        BvhDesc b;
-        b.n_leaves = L; b.n_levels = 1;
-        for (int k = 0; k < ICP_BVH_MAX_LEVELS; ++k) { b.count[k] = 0; b.offset[k] = 0; b.coffset[k] = 0; }
-        b.count[0] = L;
-        *bvh = b;
-    }
-}
-
-// Number of level-`lvl` nodes that start before sorted point position s (s is a boundary of a cell-tree node at or
-// above the level's nodes): leaves by leaf_rank, upper levels by the chain of per-level ranks.
-__device__ __forceinline__ unsigned int nodes_before(const BvhDesc& b, const unsigned int* __restrict__ leaf_rank,
-                                                     const unsigned int* __restrict__ node_rank, int lvl, unsigned int s) {
-    unsigned int a = leaf_rank[s];
-    for (int j = 1; j <= lvl; ++j) a = node_rank[b.coffset[j] + a];
-    return a;
-}
-
-// Level `lvl` (>= 1) from level lvl-1, step 1: node k of level lvl-1 starts a level-lvl node iff it is the first node of
-// the shallowest cell-tree node around it that holds <= 32 nodes of level lvl-1.  flags -> node_rank[coffset[lvl] + k].
-__global__ void mark_level_kernel(const float4* __restrict__ pts, const GridParams* __restrict__ gp, const unsigned int* __restrict__ cs,
-                                  int T, const unsigned int* __restrict__ leaf_start, const unsigned int* __restrict__ leaf_rank,
-                                  const unsigned int* __restrict__ pstart, unsigned int* __restrict__ node_rank,
-                                  const BvhDesc* __restrict__ bvh, int lvl) {
-    const BvhDesc b = *bvh;
-    if (b.n_levels != lvl) return;                         // the level below is not the current top, or the tree is complete
-    const int prev = lvl - 1, n_prev = b.count[prev];
-    if (n_prev <= 32) return;                              // the level below already is the top
-    const GridParams g = *gp;
-    unsigned int* flags = node_rank + b.coffset[lvl];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_prev; k += gridDim.x * blockDim.x) {
-        if (k == n_prev) { flags[k] = 0u; continue; }
-        const unsigned int pos = prev == 0 ? leaf_start[k] : pstart[b.offset[prev] + k];
-        const float4 p = pts[pos];
-        const unsigned int c = cell_code(g, p.x, p.y, p.z);
-        const unsigned int sT = cs[c], eT = cs[(size_t)c + 1];
-        const unsigned int aT = nodes_before(b, leaf_rank, node_rank, prev, sT), bT = nodes_before(b, leaf_rank, node_rank, prev, eT);
-        if (bT - aT > 32u) { flags[k] = ((unsigned int)k - aT) % 32u == 0u ? 1u : 0u; continue; }   // over-full finest cell: runs of 32
-        int lo = 0, hi = T;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1, sh = T - mid;
-            const unsigned int pre = c >> sh;
-            const unsigned int cnt = nodes_before(b, leaf_rank, node_rank, prev, cs[((size_t)pre + 1) << sh]) -
-                                     nodes_before(b, leaf_rank, node_rank, prev, cs[(size_t)pre << sh]);
-            if (cnt <= 32u) hi = mid; else lo = mid + 1;
-        }
-        const int sh = T - lo;
-        flags[k] = (unsigned int)k == nodes_before(b, leaf_rank, node_rank, prev, cs[(size_t)(c >> sh) << sh]) ? 1u : 0u;
-    }
-}
-
-// step 2 (one block): exclusive scan of the level's flags in place; the descriptor gains the level
-__global__ void scan_level_kernel(unsigned int* __restrict__ node_rank, BvhDesc* __restrict__ bvh, int lvl) {
-    __shared__ unsigned int carry_s;
-    __shared__ unsigned int total;
-    const BvhDesc b = *bvh;
-    if (b.n_levels != lvl || b.count[lvl - 1] <= 32) return;
-    const int n = b.count[lvl - 1] + 1;
-    unsigned int* data = node_rank + b.coffset[lvl];
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const unsigned int v = i < n ? data[i] : 0u;
-        const unsigned int ex = block_exclusive_scan(v, &total);
-        const unsigned int carry = carry_s;
-        if (i < n) data[i] = ex + carry;
+// flags[i] = 1 iff element i starts a node; tile_count[tile] = flags set in the tile.  count = *count_ptr - *minus_ptr.
+template <bool FROM_KEYS>
+__global__ void __launch_bounds__(LV_THREADS) level_flags_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ delta_in,
+                                                                 const int* count_ptr, int count_host, const unsigned int* __restrict__ minus_ptr,
+                                                                 int min_count, int T, unsigned char* __restrict__ flags,
+                                                                 unsigned int* __restrict__ tile_count) {
+    __shared__ int sd[LV_TILE + 2 * LV_HALO + 1];
+    __shared__ unsigned int wsum[LV_THREADS / 32];
+    const int count = (count_ptr ? *count_ptr : count_host) - (minus_ptr ? (int)*minus_ptr : 0);
+    if (count <= min_count) return;                            // the level below already is the top
+    const int n_tiles = (count + LV_TILE - 1) / LV_TILE;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = (long long)tile * LV_TILE;
         __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
+        // sd[j] = delta(base - LV_HALO + j), j = 0 .. LV_TILE + 2 * LV_HALO
+        for (int j = threadIdx.x; j < LV_TILE + 2 * LV_HALO + 1; j += LV_THREADS) {
+            const long long i = base - LV_HALO + j;
+            int d = -1;
+            if (i > 0 && i < count) d = FROM_KEYS ? key_delta(keys[i - 1], keys[i], T) : delta_in[i];
+            sd[j] = d;
+        }
         __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const int cnt = (int)carry_s;
-        bvh->count[lvl] = cnt;
-        bvh->offset[lvl] = b.offset[lvl - 1] + b.count[lvl - 1];
-        if (lvl + 1 < ICP_BVH_MAX_LEVELS) bvh->coffset[lvl + 1] = b.coffset[lvl] + n;     // this level used n rank entries and cnt+1 <= n child entries
-        bvh->n_levels = lvl + 1;
+        unsigned int mine = 0;
+#pragma unroll
+        for (int k = 0; k < LV_ITEMS; ++k) {
+            const int t = k * LV_THREADS + threadIdx.x;
+            const long long i = base + t;
+            if (i >= count) continue;
+            const int* dl = sd + LV_HALO + t;                  // dl[o] = delta(i + o)
+            int l = 0, r = 0;                                  // the run [i + l, i + r]
+            bool overfull_cell = false;
+            for (;;) {
+                const int d = max(dl[l], dl[r + 1]);
+                if (d < 0) break;                              // the whole level is one run
+                int nl = l, nr = r;
+                while (nr - nl + 1 <= 32 && dl[nl] >= d) --nl;
+                while (nr - nl + 1 <= 32 && dl[nr + 1] >= d) ++nr;
+                if (nr - nl + 1 > 32) { overfull_cell = (d == T && l == 0 && r == 0); break; }
+                l = nl; r = nr;
+            }
+            const bool f = overfull_cell ? (dl[0] < T || (i & 31) == 0) : (l == 0);
+            flags[i] = f ? 1 : 0;
+            mine += f ? 1u : 0u;
+        }
+        mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int s = 0; for (int w = 0; w < LV_THREADS / 32; ++w) s += wsum[w]; tile_count[tile] = s; }
     }
 }
 
-// step 3: children ranges and start positions of the level's nodes
-__global__ void level_children_kernel(const unsigned int* __restrict__ leaf_start, const unsigned int* __restrict__ node_rank,
-                                      unsigned int* __restrict__ child_start, unsigned int* __restrict__ pstart,
-                                      const BvhDesc* __restrict__ bvh, int lvl) {
-    const BvhDesc b = *bvh;
-    if (b.n_levels != lvl + 1) return;                     // the level was not created
-    const int prev = lvl - 1, n_prev = b.count[prev];
-    const unsigned int* rank = node_rank + b.coffset[lvl];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_prev; k += gridDim.x * blockDim.x) {
-        if (k == n_prev) { child_start[b.coffset[lvl] + b.count[lvl]] = (unsigned int)n_prev; continue; }
-        if (rank[k + 1] != rank[k]) {
-            child_start[b.coffset[lvl] + rank[k]] = (unsigned int)k;
-            pstart[b.offset[lvl] + rank[k]] = prev == 0 ? leaf_start[k] : pstart[b.offset[prev] + k];
+// Exclusive scan of the flags: rank[i] = nodes starting before element i (count + 1 entries), start[rank] = i for every flagged element (and start[total] = count), delta_out[rank] = delta of the
+// flagged element; the descriptor gains the level.  level 0: rank = leaf_rank, start = leaf_start.
+template <bool FROM_KEYS>
+__global__ void __launch_bounds__(LV_THREADS) level_rank_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ delta_in,
+                                                                const int* count_ptr, int count_host, const unsigned int* __restrict__ minus_ptr,
+                                                                int min_count, int T, const unsigned char* __restrict__ flags,
+                                                                const unsigned int* __restrict__ tile_count, unsigned int* __restrict__ rank_base,
+                                                                unsigned int* __restrict__ start_base, int* __restrict__ delta_out,
+                                                                BvhDesc* bvh, int level, int n_alloc) {
+    __shared__ unsigned int s_red[LV_THREADS / 32];
+    __shared__ unsigned int s_before, s_total;
+    const int count = (count_ptr ? *count_ptr : count_host) - (minus_ptr ? (int)*minus_ptr : 0);
+    if (level == 0) {
+        if (count <= 0) {                                      // empty cloud: a descriptor with no leaves
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                BvhDesc b; b.n_leaves = 0; b.n_levels = 1;
+                for (int k = 0; k < ICP_BVH_MAX_LEVELS; ++k) { b.count[k] = 0; b.offset[k] = 0; b.coffset[k] = 0; }
+                *bvh = b; start_base[0] = 0u;
+            }
+            for (int i = blockIdx.x * LV_THREADS + threadIdx.x; i < n_alloc + 2; i += gridDim.x * LV_THREADS) rank_base[i] = 0u;
+            return;
         }
+    } else if (count <= min_count) return;
+    // level >= 1: the level's rank / child arrays start at coffset[level] (set when the level below was finished)
+    const int coff = level == 0 ? 0 : bvh->coffset[level];
+    unsigned int* rank = rank_base + coff;
+    unsigned int* start = start_base + coff;
+    const int n_tiles = (count + LV_TILE - 1) / LV_TILE;
+    {   // nodes of the whole level
+        unsigned int a = 0;
+        for (int t = threadIdx.x; t < n_tiles; t += LV_THREADS) a += tile_count[t];
+        a = __reduce_add_sync(0xFFFFFFFFu, a);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int s = 0; for (int w = 0; w < LV_THREADS / 32; ++w) s += s_red[w]; s_total = s; }
+        __syncthreads();
+    }
+    const unsigned int total = s_total;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = (long long)tile * LV_TILE;
+        __syncthreads();
+        unsigned int b = 0;                                    // nodes before this tile
+        for (int t = threadIdx.x; t < tile; t += LV_THREADS) b += tile_count[t];
+        b = __reduce_add_sync(0xFFFFFFFFu, b);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int s = 0; for (int w = 0; w < LV_THREADS / 32; ++w) s += s_red[w]; s_before = s; }
+        __syncthreads();
+        const unsigned int before = s_before;
+        // every thread owns LV_ITEMS consecutive elements
+        const long long i0 = base + (long long)threadIdx.x * LV_ITEMS;
+        unsigned int f[LV_ITEMS]; unsigned int s = 0;
+#pragma unroll
+        for (int k = 0; k < LV_ITEMS; ++k) { f[k] = (i0 + k < count) ? flags[i0 + k] : 0u; s += f[k]; }
+        unsigned int ex = block_exclusive_scan(s, nullptr) + before;
+#pragma unroll
+        for (int k = 0; k < LV_ITEMS; ++k) {
+            const long long i = i0 + k;
+            if (i < count) {
+                rank[i] = ex;
+                if (f[k]) {
+                    start[ex] = (unsigned int)i;
+                    if (delta_out) delta_out[ex] = i == 0 ? -1 : (FROM_KEYS ? key_delta(keys[i - 1], keys[i], T) : delta_in[i]);
+                }
+            }
+            ex += f[k];
+        }
+    }
+    // rank[count] = the number of nodes; level 0 keeps leaf_rank defined for every sorted position up to n_alloc + 1
+    // (the non-finite points at the end included)
+    const long long tail_end = level == 0 ? (long long)n_alloc + 2 : (long long)count + 1;
+    for (long long i = (long long)count + blockIdx.x * LV_THREADS + threadIdx.x; i < tail_end; i += (long long)gridDim.x * LV_THREADS) rank[i] = total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        start[total] = (unsigned int)count;
+        if (level == 0) {
+            BvhDesc d;
+            d.n_leaves = (int)total; d.n_levels = 1;
+            for (int k = 0; k < ICP_BVH_MAX_LEVELS; ++k) { d.count[k] = 0; d.offset[k] = 0; d.coffset[k] = 0; }
+            d.count[0] = (int)total;
+            *bvh = d;
+        } else {
+            const int n_prev = count;
+            bvh->count[level] = (int)total;
+            bvh->offset[level] = bvh->offset[level - 1] + n_prev;
+            if (level + 1 < ICP_BVH_MAX_LEVELS) bvh->coffset[level + 1] = coff + n_prev + 1;
+            bvh->n_levels = level + 1;
+        }
+    }
+}
+
+// All levels above level 1 in ONE single-block launch (a 370k-point cloud has ~1.5k level-1 nodes, then ~90, then ~6):
+// per level the flags (same window rule, delta values read from global memory), the scan, the children ranges, the next
+// level's delta values and the boxes.  delta_a holds the deltas of level `first_level - 1`'s nodes; the levels ping-pong
+// between delta_a and delta_b.
+#define UP_THREADS 1024
+__global__ void __launch_bounds__(UP_THREADS) upper_levels_kernel(int* delta_a, int* delta_b, unsigned int* node_rank,
+                                                                  unsigned int* child_start, BvhDesc* bvh,
+                                                                  float4* box, int T, int first_level) {
+    __shared__ unsigned int s_carry, s_total;
+    __shared__ BvhDesc sb;
+    const int lane = threadIdx.x & 31;
+    int* din = delta_a; int* dout = delta_b;
+    for (int lvl = first_level; lvl < ICP_BVH_MAX_LEVELS; ++lvl) {
+        __syncthreads();
+        if (threadIdx.x < sizeof(BvhDesc) / 4) reinterpret_cast<int*>(&sb)[threadIdx.x] = reinterpret_cast<volatile int*>(bvh)[threadIdx.x];
+        if (threadIdx.x == 0) s_carry = 0u;
+        __syncthreads();
+        if (sb.n_levels != lvl) return;                        // the level below was not created
+        const int n_prev = sb.count[lvl - 1];
+        if (n_prev <= 32) return;                              // the level below already is the top
+        const int coff = sb.coffset[lvl];
+        unsigned int* rank = node_rank + coff;
+        unsigned int* start = child_start + coff;
+        for (int base = 0; base < n_prev; base += UP_THREADS) {
+            const int i = base + threadIdx.x;
+            unsigned int f = 0u;
+            if (i < n_prev) {
+                // delta(j) of this level's elements; -1 outside (1 .. n_prev - 1)
+                auto dl = [&](int o) -> int { const int j = i + o; return (j > 0 && j < n_prev) ? din[j] : -1; };
+                int l = 0, r = 0; bool overfull_cell = false;
+                for (;;) {
+                    const int d = max(dl(l), dl(r + 1));
+                    if (d < 0) break;
+                    int nl = l, nr = r;
+                    while (nr - nl + 1 <= 32 && dl(nl) >= d) --nl;
+                    while (nr - nl + 1 <= 32 && dl(nr + 1) >= d) ++nr;
+                    if (nr - nl + 1 > 32) { overfull_cell = (d == T && l == 0 && r == 0); break; }
+                    l = nl; r = nr;
+                }
+                f = (overfull_cell ? (dl(0) < T || (i & 31) == 0) : (l == 0)) ? 1u : 0u;
+            }
+            const unsigned int ex = block_exclusive_scan(f, &s_total) + s_carry;
+            if (i < n_prev) {
+                rank[i] = ex;
+                if (f) { start[ex] = (unsigned int)i; dout[ex] = i == 0 ? -1 : din[i]; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry += s_total;
+            __syncthreads();
+        }
+        const int total = (int)s_carry;
+        if (threadIdx.x == 0) {
+            rank[n_prev] = (unsigned int)total;
+            start[total] = (unsigned int)n_prev;
+            bvh->count[lvl] = total;
+            bvh->offset[lvl] = sb.offset[lvl - 1] + n_prev;
+            if (lvl + 1 < ICP_BVH_MAX_LEVELS) bvh->coffset[lvl + 1] = coff + n_prev + 1;
+            bvh->n_levels = lvl + 1;
+            __threadfence();
+        }
+        __syncthreads();
+        // boxes of the new level: one warp per node over its (<= 32) child boxes
+        const int off_prev = sb.offset[lvl - 1], off = sb.offset[lvl - 1] + n_prev;
+        for (int node = threadIdx.x >> 5; node < total; node += UP_THREADS / 32) {
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            unsigned int clo[3] = {255u, 255u, 255u}, chi[3] = {0u, 0u, 0u};
+            const unsigned int c = start[node] + lane;
+            if (c < start[node + 1]) {
+                const float4 u = box[2 * (size_t)(off_prev + c)], v = box[2 * (size_t)(off_prev + c) + 1];
+                lo[0] = u.x; lo[1] = u.y; lo[2] = u.z; hi[0] = v.x; hi[1] = v.y; hi[2] = v.z;
+                const unsigned int cu = __float_as_uint(u.w), cv = __float_as_uint(v.w);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { clo[k] = (cu >> (8 * k)) & 0xFFu; chi[k] = (cv >> (8 * k)) & 0xFFu; }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { clo[k] = __reduce_min_sync(0xFFFFFFFFu, clo[k]); chi[k] = __reduce_max_sync(0xFFFFFFFFu, chi[k]); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o)); }
+            if (lane == 0) {
+                box[2 * (size_t)(off + node)] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(clo[0] | (clo[1] << 8) | (clo[2] << 16)));
+                box[2 * (size_t)(off + node) + 1] = make_float4(hi[0], hi[1], hi[2], __uint_as_float(chi[0] | (chi[1] << 8) | (chi[2] << 16)));
+            }
+        }
+        int* t = din; din = dout; dout = t;
     }
 }
 
@@ -695,57 +855,32 @@ size_t icp_bvh_max_nodes(int n) {
     return (size_t)(n > 0 ? n : 1) * 2 + 64;
 }
 
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
-                                 unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
-                                 unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
-                                 cudaStream_t s, int* n_launches) {
+// Tight-box BVH over the sorted cloud.  keys: the sorted keys; nonfinite: device count of the points past the last cell.
+// leaf_rank: n + 2 entries (kept: maps a sorted position to its leaf); leaf_start: n + 2; node_rank / child_start:
+// icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS entries each; flags: n bytes; tile_count: n / 1024 + 2; delta_a / delta_b: n + 2 each.
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, int T, const unsigned int* keys,
+                                 const unsigned int* nonfinite, unsigned char* flags, unsigned int* tile_count,
+                                 int* delta_a, int* delta_b, unsigned int* leaf_rank, unsigned int* leaf_start, unsigned int* node_rank,
+                                 unsigned int* child_start, BvhDesc* bvh_dev, float4* box, int n_sms, cudaStream_t s, int* n_launches) {
     int launches = 0;
-    mark_leaves_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(pts_sorted, n, grid, cell_start, T, leaf_rank); ++launches;
-    cudaError_t e = launch_exclusive_scan(leaf_rank, n + 1, block_sums, s, &launches);
-    if (e != cudaSuccess) return e;
-    leaf_starts_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(leaf_rank, n, cell_start, T, leaf_start, bvh_dev); ++launches;
-    long long nb0 = ((long long)(n > 0 ? n : 1) + 7) / 8; if (nb0 > 8ll * n_sms) nb0 = 8ll * n_sms;
+    const int n1 = n > 0 ? n : 1;
+    const int tiles0 = (n1 + LV_TILE - 1) / LV_TILE;
+    // level 0: leaves
+    level_flags_kernel<true><<<tiles0, LV_THREADS, 0, s>>>(keys, nullptr, nullptr, n, nonfinite, 0, T, flags, tile_count); ++launches;
+    level_rank_kernel<true><<<tiles0, LV_THREADS, 0, s>>>(keys, nullptr, nullptr, n, nonfinite, 0, T, flags, tile_count, leaf_rank, leaf_start, delta_a,
+                                                          bvh_dev, 0, n); ++launches;
+    long long nb0 = ((long long)n1 + 7) / 8; if (nb0 > 8ll * n_sms) nb0 = 8ll * n_sms;
     bvh_level_kernel<<<(int)nb0, 256, 0, s>>>(pts_sorted, nrm_sorted, leaf_start, child_start, bvh_dev, box, 0); ++launches;
-    // Upper levels: the node counts live on the device, so every possible level gets its (tiny) launches; the ones
-    // past the top return at once.  An n-point cloud with healthy fill needs log_16(n / 16) levels; cap the launches there + 2.
-    int max_levels = 2; { long long c = (n > 0 ? n : 1) / 16; while (c > 32 && max_levels < ICP_BVH_MAX_LEVELS) { c /= 8; ++max_levels; } }
-    if (max_levels > ICP_BVH_MAX_LEVELS) max_levels = ICP_BVH_MAX_LEVELS;
-    for (int l = 1; l < max_levels; ++l) {
-        const int nb = l == 1 ? 2 * n_sms : n_sms / 2;
-        mark_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, grid, cell_start, T, leaf_start, leaf_rank, pstart, node_rank, bvh_dev, l); ++launches;
-        scan_level_kernel<<<1, 1024, 0, s>>>(node_rank, bvh_dev, l); ++launches;
-        level_children_kernel<<<nb, 256, 0, s>>>(leaf_start, node_rank, child_start, pstart, bvh_dev, l); ++launches;
-        bvh_level_kernel<<<nb, 256, 0, s>>>(pts_sorted, nrm_sorted, leaf_start, child_start, bvh_dev, box, l); ++launches;
-    }
-    if (n_launches) *n_launches += launches;
-    return cudaGetLastError();
-}
-
-cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid,
-                                  unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
-                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
-                                  cudaStream_t s, int* n_launches) {
-    cudaError_t e;
-    const int n_cells1 = (1 << T) + 1;
-    if ((e = cudaMemsetAsync(bbox_scratch, 0xFF, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(bbox_scratch + 3, 0x00, 5 * sizeof(unsigned int), s)) != cudaSuccess) return e;   // max[3], spare, non-finite counter
-    if ((e = cudaMemsetAsync(cell_start, 0, sizeof(unsigned int) * (size_t)n_cells1, s)) != cudaSuccess) return e;
-    int launches = 0;
-    if (n > 0) {
-        const int nb = min((n + 255) / 256, 148 * 8);
-        bbox_kernel<<<nb, 256, 0, s>>>(pts_in, n, bbox_scratch); ++launches;
-    }
-    grid_params_kernel<<<1, 32, 0, s>>>(bbox_scratch, T, grid); ++launches;
-    if (n > 0) { keys_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_in, n, grid, keys, ranks, cell_start); ++launches; }
-    const int n_tiles = (n_cells1 + SCAN_TILE - 1) / SCAN_TILE;
-    scan_tile_sums_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(cell_start, n_cells1, block_sums); ++launches;
-    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(block_sums, n_tiles); ++launches;
-    scan_apply_kernel<<<n_tiles, SCAN_THREADS, 0, s>>>(cell_start, n_cells1, block_sums); ++launches;
-    if (n > 0) {
-        scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts_in, nrm_in, n, keys, ranks, cell_start, 1u << T, keep_nonfinite, bbox_scratch + 7,
-                                                       pts_sorted, nrm_sorted);
-        ++launches;
-    }
+    // level 1: elements = leaves (a healthy cloud has ~n/16 of them; the kernels loop if there are more)
+    int tiles1 = (n1 / 8 + LV_TILE - 1) / LV_TILE; if (tiles1 < 1) tiles1 = 1; if (tiles1 > 4 * n_sms) tiles1 = 4 * n_sms;
+    const int* leaves_dev = &bvh_dev->count[0];
+    level_flags_kernel<false><<<tiles1, LV_THREADS, 0, s>>>(nullptr, delta_a, leaves_dev, 0, nullptr, 32, T, flags, tile_count); ++launches;
+    level_rank_kernel<false><<<tiles1, LV_THREADS, 0, s>>>(nullptr, delta_a, leaves_dev, 0, nullptr, 32, T, flags, tile_count, node_rank, child_start, delta_b,
+                                                           bvh_dev, 1, 0); ++launches;
+    const int nb1 = 2 * n_sms;
+    bvh_level_kernel<<<nb1, 256, 0, s>>>(pts_sorted, nrm_sorted, leaf_start, child_start, bvh_dev, box, 1); ++launches;
+    // levels >= 2: one block
+    upper_levels_kernel<<<1, UP_THREADS, 0, s>>>(delta_b, delta_a, node_rank, child_start, bvh_dev, box, T, 2); ++launches;
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }

@@ -125,8 +125,6 @@ struct MatchArgs {
     const DevState* state_ro;
     DevState* state;
     // target
-    const GridParams* grid;
-    const unsigned int* cell_start;
     const float4* tgt_pts;   // grid order {x,y,z,orig idx bits}; brute / projective: original order
     const float4* tgt_nrm;   // same order {nx,ny,nz,rgba bits}
     int n_tgt;
@@ -181,25 +179,25 @@ struct ReduceArgs {
 };
 
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
+// AoS3 -> float4 records and the bounding box of the finite points (bbox: 8 words, [7] becomes the non-finite count of the sort)
 cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
-                                  cudaStream_t s);
-// Sorts a cloud into grid-cell (Morton) order and builds the dense cell table.  keep_nonfinite: points
-// with a non-finite coordinate are appended after the last cell (source clouds: every point needs a slot).
-cudaError_t icp_launch_grid_build(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid,
-                                  unsigned int* bbox_scratch, unsigned int* keys, unsigned int* ranks, unsigned int* cell_start,
-                                  unsigned int* block_sums, float4* pts_sorted, float4* nrm_sorted, int keep_nonfinite,
-                                  cudaStream_t s, int* n_launches);
-// Local 6-bit counting sort inside the finest cells that hold more than 32 points (list: scratch of `capacity` cell ids).
-cudaError_t icp_launch_refine_cells(const unsigned int* cell_start, int T, const GridParams* grid, unsigned int* list, unsigned int capacity,
-                                    unsigned int* n_list, float4* pts_sorted, float4* nrm_sorted, int n, int n_sms, cudaStream_t s,
-                                    int* n_launches);
-// Tight-box BVH over the cell-sorted cloud.  leaf_rank: n + 2 entries (kept: maps a sorted position to its leaf);
-// leaf_start: n + 2; node_scratch / child_start / pstart: icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS entries each.
+                                  unsigned int* bbox, cudaStream_t s);
+// Stable LSD radix sort of a packed cloud into (cell code, original index) order; points with a non-finite coordinate end up
+// after the last cell.  T + 1 key bits in passes of <= 11 bits.
+struct IcpRadixPlan { int n_pass; int shift[3]; int bits[3]; int tile_items; int n_tiles; };
+void icp_radix_plan(int n, int T, IcpRadixPlan* p);
+size_t icp_radix_hist_words(int n, int T);
+#define ICP_MSD_WORDS 2049
+cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid, unsigned int* bbox,
+                                  unsigned int* keys_a, unsigned int* keys_b, unsigned int* idx_a, unsigned int* idx_b,
+                                  unsigned int* tile_hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
+                                  unsigned int** keys_sorted_out, int* msd_shift_out, cudaStream_t s, int* n_launches);
+// Tight-box BVH over the sorted cloud, read off the common-prefix lengths of neighbouring sorted keys.
 size_t icp_bvh_max_nodes(int n);
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, const unsigned int* cell_start, int T,
-                                 unsigned int* leaf_rank, unsigned int* block_sums, unsigned int* leaf_start, unsigned int* node_rank,
-                                 unsigned int* child_start, unsigned int* pstart, BvhDesc* bvh_dev, float4* box, int n_sms,
-                                 cudaStream_t s, int* n_launches);
+cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, int T, const unsigned int* keys,
+                                 const unsigned int* nonfinite, unsigned char* flags, unsigned int* tile_count,
+                                 int* delta_a, int* delta_b, unsigned int* leaf_rank, unsigned int* leaf_start, unsigned int* node_rank,
+                                 unsigned int* child_start, BvhDesc* bvh_dev, float4* box, int n_sms, cudaStream_t s, int* n_launches);
 // One voxel pyramid level (depth D of the source grid) as a selection mask; table: scratch of 2^D entries.
 cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, int T, int D,
                                    unsigned int* table, unsigned int* mask, size_t mask_words, cudaStream_t s, int* n_launches);
@@ -208,9 +206,10 @@ cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box,
                                       float4* adj_box, int capacity, int level, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
-// Seeds (nn_pos / nn_leaf) for the queries that have none, from the target's cell table at the pose in `st`.
-cudaError_t icp_launch_seed_from_grid(const float4* src_pts_sorted, int n_src, const DevState* st, const GridParams* grid, const unsigned int* cell_start,
-                                      int T, const unsigned int* leaf_rank, int* nn_pos, int* nn_leaf, cudaStream_t s);
+// Seeds (nn_pos / nn_leaf) for the queries that have none (reset: for every query), from the target's sorted keys at the pose in `st`.
+cudaError_t icp_launch_seed_from_keys(const float4* src_pts, int n_src, const DevState* st, const GridParams* grid, const unsigned int* keys, int n_tgt,
+                                      const unsigned int* nonfinite, const unsigned int* msd_start, int msd_shift, const unsigned int* leaf_rank,
+                                      int* nn_pos, int* nn_leaf, int reset, cudaStream_t s);
 // algorithm: 0 BVH search (one warp per query), 1 brute force, 2 projective
 // prep.cu: depth map -> cloud (PointCloud.h:78-165) and convergence metrics (ConvergenceMeasure.h:50-66,104-151)
 struct DepthArgs {
