@@ -36,7 +36,8 @@ class Config(C.Structure):
                 ("proba", C.c_double), ("seed", C.c_uint32), ("selection_rng", C.c_int32), ("weighting", C.c_int32),
                 ("rejection", C.c_int32), ("max_distance_sq", C.c_float), ("color_icp", C.c_int32), ("multires", C.c_int32),
                 ("pyramid_mode", C.c_int32), ("n_iterations", C.c_int32), ("lm_max_iterations", C.c_int32),
-                ("nn_algorithm", C.c_int32), ("use_graph", C.c_int32), ("collect_stats", C.c_int32)]
+                ("nn_algorithm", C.c_int32), ("use_graph", C.c_int32), ("collect_stats", C.c_int32),
+                ("weight_max_distance_sq", C.c_float)]
 
 
 class Timings(C.Structure):

@@ -75,6 +75,8 @@ struct icp_gpu_ctx {
     cudaEvent_t ev_fork = nullptr, ev_index_ready = nullptr;
     bool index_pending = false;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};           // [target, source]: staging filled
+    cudaEvent_t ev_xyz[2] = {nullptr, nullptr};              // the points of the upload are there (normals and colours follow)
+    IcpLatePack late[2]; bool late_pending[2] = {false, false};   // normal records still to be packed by the sort
     cudaEvent_t ev_packed[2] = {nullptr, nullptr};           // staging consumed by the pack kernel
     bool packed_once[2] = {false, false};
     DeviceBuf stage2;                                        // the source's staging area (the target uses `stage`)
@@ -90,7 +92,7 @@ struct icp_gpu_ctx {
     // target grid
     DeviceBuf grid, bbox, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, adj, adj_box, adj1, adj1_box;
     // sort / tree scratch, one set per cloud (the two builds run on different streams)
-    struct SortBufs { DeviceBuf keys_a, keys_b, idx_a, idx_b, tile_hist, msd; unsigned int* keys_sorted = nullptr; int msd_shift = 0; };
+    struct SortBufs { DeviceBuf keys_a, keys_b, idx_a, idx_b, hist, msd; unsigned int* keys_sorted = nullptr; int msd_shift = 0; };
     SortBufs tsort, ssort;
     DeviceBuf lv_flags, lv_tiles, delta_a, delta_b;
     int adj1_capacity = 0;
@@ -120,7 +122,7 @@ struct icp_gpu_ctx {
     void* peer_box = nullptr;                               // own mailbox (plain cudaMalloc: exportable through CUDA IPC)
     void* peer_ptr[ICP_MAX_PEERS] = {nullptr};              // every rank's mailbox as mapped here
     bool peer_ipc[ICP_MAX_PEERS] = {false};                 // opened with cudaIpcOpenMemHandle (to be closed)
-    int peer_world = 0, peer_rank = 0;
+    int peer_world = 0, peer_rank = 0, peer_plan_check = 0;
     uint64_t peer_epoch = 0;                                // part of the graph key: a new attachment is a new graph
     icp_gpu_stats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -176,7 +178,7 @@ int pick_T(int n, bool source = false) {
 
 int choose_algorithm(const icp_gpu_ctx* c) {   // 0 grid, 1 brute, 2 projective
     if (c->cfg.matching == ICP_GPU_MATCH_PROJECTIVE) return 2;
-    if (c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE) return 1;
+    if (c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE || c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE_NORM) return 1;
     if (c->cfg.nn_algorithm == ICP_GPU_NN_GRID) return 0;
     return c->n_tgt <= 2048 ? 1 : 0;
 }
@@ -185,35 +187,6 @@ int coarsest_stride(long long n) {   // ICPOptimizer.h:503-516
     float res = 1.0f; int sz = (int)n;
     for (;;) { sz = (int)(sz / 2.0); if (sz < 100) break; res *= 2.0f; }
     return (int)res;
-}
-
-int upload_cloud(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n, bool device_ptrs,
-                 DeviceBuf& pts, DeviceBuf& nrmb, int kind /*0 target, 1 source*/) {
-    const size_t n1 = (size_t)(n > 0 ? n : 1);
-    DeviceBuf& bbox = kind == 0 ? ctx->bbox : ctx->sbbox;
-    if (ensure(ctx, pts, n1 * sizeof(float4)) || ensure(ctx, nrmb, n1 * sizeof(float4)) || ensure(ctx, bbox, 64)) return ICP_GPU_E_CUDA;
-    if (n == 0) { CU(icp_launch_pack_cloud(nullptr, nullptr, nullptr, 0, (float4*)pts.p, (float4*)nrmb.p, (unsigned int*)bbox.p, ctx->stream)); return 0; }
-    const float* dx = xyz; const float* dn = nrm; const uint8_t* dc = rgba;
-    if (!device_ptrs) {
-        // Host arrays go through a per-cloud staging area on the copy stream, so that the upload of one cloud overlaps
-        // the index build of the other on the compute stream.
-        DeviceBuf& stage = kind == 0 ? ctx->stage : ctx->stage2;
-        const size_t bx = (size_t)n * 12, bc = (size_t)n * 4;
-        const size_t ox = 0, on = (bx + 255) / 256 * 256, oc = on + (nrm ? (bx + 255) / 256 * 256 : 0);
-        if (ensure(ctx, stage, oc + (rgba ? bc : 0) + 256)) return ICP_GPU_E_CUDA;
-        char* st = (char*)stage.p;
-        if (ctx->packed_once[kind]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[kind], 0));   // staging still being read?
-        CU(cudaMemcpyAsync(st + ox, xyz, bx, cudaMemcpyHostToDevice, ctx->copy_stream));
-        dx = (const float*)(st + ox);
-        if (nrm) { CU(cudaMemcpyAsync(st + on, nrm, bx, cudaMemcpyHostToDevice, ctx->copy_stream)); dn = (const float*)(st + on); }
-        if (rgba) { CU(cudaMemcpyAsync(st + oc, rgba, bc, cudaMemcpyHostToDevice, ctx->copy_stream)); dc = (const uint8_t*)(st + oc); }
-        CU(cudaEventRecord(ctx->ev_copied[kind], ctx->copy_stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[kind], 0));
-    }
-    CU(icp_launch_pack_cloud(dx, dn, dc, (int)n, (float4*)pts.p, (float4*)nrmb.p, (unsigned int*)bbox.p, ctx->stream));
-    if (!device_ptrs) { CU(cudaEventRecord(ctx->ev_packed[kind], ctx->stream)); ctx->packed_once[kind] = true; }
-    ctx->stats.n_kernel_launches += 1;
-    return 0;
 }
 
 // Consumers of the target index (and anything that overwrites it) first wait for the part of its build that runs on aux_stream.
@@ -227,17 +200,61 @@ int join_index(icp_gpu_ctx* ctx) {
 int ensure_sort(icp_gpu_ctx* ctx, icp_gpu_ctx::SortBufs& sb, int n, int T) {
     const size_t n1 = (size_t)(n > 0 ? n : 1);
     if (ensure(ctx, sb.keys_a, n1 * 4) || ensure(ctx, sb.keys_b, n1 * 4) || ensure(ctx, sb.idx_a, n1 * 4) || ensure(ctx, sb.idx_b, n1 * 4) ||
-        ensure(ctx, sb.tile_hist, icp_radix_hist_words(n, T) * 4) || ensure(ctx, sb.msd, ICP_MSD_WORDS * 4)) return ICP_GPU_E_CUDA;
+        ensure(ctx, sb.hist, icp_radix_hist_words(n, T) * 4) || ensure(ctx, sb.msd, ICP_MSD_WORDS * 4)) return ICP_GPU_E_CUDA;
+    return 0;
+}
+
+int upload_cloud(icp_gpu_ctx* ctx, const float* xyz, const float* nrm, const uint8_t* rgba, int64_t n, bool device_ptrs,
+                 DeviceBuf& pts, DeviceBuf& nrmb, int kind /*0 target, 1 source*/) {
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    DeviceBuf& bbox = kind == 0 ? ctx->bbox : ctx->sbbox;
+    DeviceBuf& grid = kind == 0 ? ctx->grid : ctx->sgrid;
+    icp_gpu_ctx::SortBufs& sb = kind == 0 ? ctx->tsort : ctx->ssort;
+    // the pack kernel also derives the grid parameters and clears the histograms of the sort that follows
+    const int T = pick_T((int)n, kind == 1);
+    if (kind == 0) ctx->T = T; else ctx->Ts = T;
+    if (ensure(ctx, pts, n1 * sizeof(float4)) || ensure(ctx, nrmb, n1 * sizeof(float4)) || ensure(ctx, bbox, 64) || ensure(ctx, grid, sizeof(GridParams)) ||
+        ensure_sort(ctx, sb, (int)n, T)) return ICP_GPU_E_CUDA;
+    const long long hist_words = (long long)icp_radix_hist_words((int)n, T);
+    if (n == 0) {
+        CU(icp_launch_pack_cloud(nullptr, nullptr, nullptr, 0, (float4*)pts.p, (float4*)nrmb.p, (unsigned int*)bbox.p, T, (GridParams*)grid.p,
+                                 (unsigned int*)sb.hist.p, hist_words, 1, ctx->stream));
+        ctx->late_pending[kind] = false;
+        return 0;
+    }
+    const float* dx = xyz; const float* dn = nrm; const uint8_t* dc = rgba;
+    if (!device_ptrs) {
+        // Host arrays go through a per-cloud staging area on the copy stream, so that the upload of one cloud overlaps
+        // the index build of the other on the compute stream.
+        DeviceBuf& stage = kind == 0 ? ctx->stage : ctx->stage2;
+        const size_t bx = (size_t)n * 12, bc = (size_t)n * 4;
+        const size_t ox = 0, on = (bx + 255) / 256 * 256, oc = on + (nrm ? (bx + 255) / 256 * 256 : 0);
+        if (ensure(ctx, stage, oc + (rgba ? bc : 0) + 256)) return ICP_GPU_E_CUDA;
+        char* st = (char*)stage.p;
+        if (ctx->packed_once[kind]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[kind], 0));   // staging still being read?
+        CU(cudaMemcpyAsync(st + ox, xyz, bx, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_xyz[kind], ctx->copy_stream));       // the sort starts from the points alone
+        dx = (const float*)(st + ox);
+        if (nrm) { CU(cudaMemcpyAsync(st + on, nrm, bx, cudaMemcpyHostToDevice, ctx->copy_stream)); dn = (const float*)(st + on); }
+        if (rgba) { CU(cudaMemcpyAsync(st + oc, rgba, bc, cudaMemcpyHostToDevice, ctx->copy_stream)); dc = (const uint8_t*)(st + oc); }
+        CU(cudaEventRecord(ctx->ev_copied[kind], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_xyz[kind], 0));
+        // the normal / colour records are packed by the sort just before its last pass (the only one that moves them)
+        ctx->late[kind].nrm = dn; ctx->late[kind].rgba = dc; ctx->late[kind].nrmo = (float4*)nrmb.p; ctx->late[kind].ready = ctx->ev_copied[kind];
+    }
+    ctx->late_pending[kind] = !device_ptrs;
+    CU(icp_launch_pack_cloud(dx, dn, dc, (int)n, (float4*)pts.p, (float4*)nrmb.p, (unsigned int*)bbox.p, T, (GridParams*)grid.p,
+                             (unsigned int*)sb.hist.p, hist_words, device_ptrs ? 1 : 0, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
     return 0;
 }
 
 // buildIndex: radix sort by cell code, leaves and upper levels from the sorted keys, tight boxes, adjacency lists.
 int build_grid(icp_gpu_ctx* ctx) {
     const int n = ctx->n_tgt;
-    ctx->T = pick_T(n);
     const size_t n1 = (size_t)(n > 0 ? n : 1);
-    if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) || ensure_sort(ctx, ctx->tsort, n, ctx->T) ||
-        ensure(ctx, ctx->grid, sizeof(GridParams)) || ensure(ctx, ctx->lv_flags, n1 + 64) || ensure(ctx, ctx->lv_tiles, (n1 / 1024 + 2) * 4) ||
+    if (ensure(ctx, ctx->tgt_pts_sorted, n1 * sizeof(float4)) || ensure(ctx, ctx->tgt_nrm_sorted, n1 * sizeof(float4)) ||
+        ensure(ctx, ctx->lv_flags, n1 + 64) || ensure(ctx, ctx->lv_tiles, (n1 / 1024 + 2) * 4) ||
         ensure(ctx, ctx->delta_a, (n1 + 2) * 4) || ensure(ctx, ctx->delta_b, (n1 + 2) * 4) ||
         ensure(ctx, ctx->leaf_start, (n1 + 2) * 4) || ensure(ctx, ctx->leaf_rank, (n1 + 2) * 4) || ensure(ctx, ctx->bvh_desc, sizeof(BvhDesc)) ||
         ensure(ctx, ctx->bvh_box, icp_bvh_max_nodes(n) * 2 * sizeof(float4)) ||
@@ -253,20 +270,24 @@ int build_grid(icp_gpu_ctx* ctx) {
     int launches = 0;
     if (join_index(ctx)) return ICP_GPU_E_CUDA;              // a build still running on aux_stream reads what this one overwrites
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(icp_launch_cloud_sort((const float4*)ctx->tgt_pts.p, (const float4*)ctx->tgt_nrm.p, n, ctx->T, (GridParams*)ctx->grid.p, (unsigned int*)ctx->bbox.p,
+    CU(icp_launch_cloud_sort((const float4*)ctx->tgt_pts.p, (const float4*)ctx->tgt_nrm.p, n, ctx->T, (const GridParams*)ctx->grid.p,
                              (unsigned int*)ctx->tsort.keys_a.p, (unsigned int*)ctx->tsort.keys_b.p, (unsigned int*)ctx->tsort.idx_a.p,
-                             (unsigned int*)ctx->tsort.idx_b.p, (unsigned int*)ctx->tsort.tile_hist.p, (float4*)ctx->tgt_pts_sorted.p,
-                             (float4*)ctx->tgt_nrm_sorted.p, (unsigned int*)ctx->tsort.msd.p, &ctx->tsort.keys_sorted, &ctx->tsort.msd_shift, ctx->stream, &launches));
+                             (unsigned int*)ctx->tsort.idx_b.p, (unsigned int*)ctx->tsort.hist.p, (float4*)ctx->tgt_pts_sorted.p,
+                             (float4*)ctx->tgt_nrm_sorted.p, (unsigned int*)ctx->tsort.msd.p, &ctx->tsort.keys_sorted, &ctx->tsort.msd_shift,
+                             ctx->late_pending[0] ? &ctx->late[0] : nullptr, ctx->stream, &launches));
+    if (ctx->late_pending[0]) { CU(cudaEventRecord(ctx->ev_packed[0], ctx->stream)); ctx->packed_once[0] = true; ctx->late_pending[0] = false; }
     cudaStream_t ts = getenv("ICP_GPU_NO_AUX_STREAM") ? ctx->stream : ctx->aux_stream;       // tuning knob (A/B measurement)
     if (ts != ctx->stream) { CU(cudaEventRecord(ctx->ev_fork, ctx->stream)); CU(cudaStreamWaitEvent(ts, ctx->ev_fork, 0)); }
     CU(icp_launch_bvh_build((const float4*)ctx->tgt_pts_sorted.p, (const float4*)ctx->tgt_nrm_sorted.p, n, ctx->T, ctx->tsort.keys_sorted,
                             (const unsigned int*)ctx->bbox.p + 7, (unsigned char*)ctx->lv_flags.p, (unsigned int*)ctx->lv_tiles.p, (int*)ctx->delta_a.p,
                             (int*)ctx->delta_b.p, (unsigned int*)ctx->leaf_rank.p, (unsigned int*)ctx->leaf_start.p, (unsigned int*)ctx->node_rank.p,
                             (unsigned int*)ctx->child_start.p, (BvhDesc*)ctx->bvh_desc.p, (float4*)ctx->bvh_box.p, ctx->n_sms, ts, &launches));
+    const bool bottom_up = !getenv("ICP_GPU_ADJ_FROM_ROOT");                                  // tuning knob (A/B measurement)
     CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
-                                 (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, 0, ctx->n_sms, ts, &launches));
+                                 (unsigned int*)ctx->adj1.p, (float4*)ctx->adj1_box.p, ctx->adj1_capacity, 1, nullptr, nullptr, nullptr, 0, ctx->n_sms, ts, &launches));
     CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
-                                 (unsigned int*)ctx->adj1.p, (float4*)ctx->adj1_box.p, ctx->adj1_capacity, 1, ctx->n_sms, ts, &launches));
+                                 (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, 0, (const unsigned int*)ctx->node_rank.p,
+                                 bottom_up ? (const unsigned int*)ctx->adj1.p : nullptr, (const float4*)ctx->adj1_box.p, ctx->adj1_capacity, ctx->n_sms, ts, &launches));
     CU(cudaEventRecord(ctx->ev[1], ts));
     if (ts != ctx->stream) { CU(cudaEventRecord(ctx->ev_index_ready, ts)); ctx->index_pending = true; }
     ctx->stats.n_kernel_launches += (uint64_t)launches;
@@ -277,16 +298,15 @@ int build_grid(icp_gpu_ctx* ctx) {
 // Sorts the source into the cell order of its own grid (Morton order); points with a non-finite coordinate keep a slot at the end.
 int build_source(icp_gpu_ctx* ctx) {
     const int n = ctx->n_src;
-    ctx->Ts = pick_T(n, true);
     const size_t n1 = (size_t)(n > 0 ? n : 1);
-    if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4)) || ensure_sort(ctx, ctx->ssort, n, ctx->Ts) ||
-        ensure(ctx, ctx->sgrid, sizeof(GridParams)))
-        return ICP_GPU_E_CUDA;
+    if (ensure(ctx, ctx->src_pts, n1 * sizeof(float4)) || ensure(ctx, ctx->src_nrm, n1 * sizeof(float4))) return ICP_GPU_E_CUDA;
     int launches = 0;
-    CU(icp_launch_cloud_sort((const float4*)ctx->src_raw_pts.p, (const float4*)ctx->src_raw_nrm.p, n, ctx->Ts, (GridParams*)ctx->sgrid.p, (unsigned int*)ctx->sbbox.p,
+    CU(icp_launch_cloud_sort((const float4*)ctx->src_raw_pts.p, (const float4*)ctx->src_raw_nrm.p, n, ctx->Ts, (const GridParams*)ctx->sgrid.p,
                              (unsigned int*)ctx->ssort.keys_a.p, (unsigned int*)ctx->ssort.keys_b.p, (unsigned int*)ctx->ssort.idx_a.p,
-                             (unsigned int*)ctx->ssort.idx_b.p, (unsigned int*)ctx->ssort.tile_hist.p, (float4*)ctx->src_pts.p,
-                             (float4*)ctx->src_nrm.p, nullptr, &ctx->ssort.keys_sorted, &ctx->ssort.msd_shift, ctx->stream, &launches));
+                             (unsigned int*)ctx->ssort.idx_b.p, (unsigned int*)ctx->ssort.hist.p, (float4*)ctx->src_pts.p,
+                             (float4*)ctx->src_nrm.p, nullptr, &ctx->ssort.keys_sorted, &ctx->ssort.msd_shift,
+                             ctx->late_pending[1] ? &ctx->late[1] : nullptr, ctx->stream, &launches));
+    if (ctx->late_pending[1]) { CU(cudaEventRecord(ctx->ev_packed[1], ctx->stream)); ctx->packed_once[1] = true; ctx->late_pending[1] = false; }
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     return 0;
 }
@@ -443,10 +463,12 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.width = c->width; a.height = c->height;
     a.weighting = c->cfg.weighting; a.rejection = c->cfg.rejection; a.color_icp = c->cfg.color_icp;
     a.max_d2 = c->cfg.max_distance_sq;
+    a.weight_max_d2 = c->cfg.weight_max_distance_sq > 0.f ? c->cfg.weight_max_distance_sq : c->cfg.max_distance_sq;
     a.match_pos = (int*)c->match_pos.p; a.match_w = (float*)c->match_w.p; a.match_idx = want_idx ? (int*)c->match_idx.p : nullptr;
     a.nn_pos = (int*)c->nn_pos.p; a.qbuf = (float4*)c->qbuf.p; a.seedbuf = (float4*)c->seedbuf.p;
     a.desc_index = desc_index;
     a.use_seed = grid_order ? 1 : 0;
+    a.brute_norm = c->cfg.nn_algorithm == ICP_GPU_NN_BRUTE_NORM ? 1 : 0;
     if (proj_tiled(c, algo)) { a.src_pts = (const float4*)c->src_raw_pts.p; a.src_nrm = (const float4*)c->src_raw_nrm.p; a.proj_tiled = 1; }
     a.fast_path = getenv("ICP_GPU_NO_FASTPATH") ? 0 : 1;   // tuning knob (A/B measurement)
     a.collect_stats = c->cfg.collect_stats;
@@ -465,6 +487,7 @@ void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
     r.fused = 0; r.nn_pos = (const int*)c->nn_pos.p; r.n_tgt = c->n_tgt; r.mask = (const unsigned int*)c->mask.p;
     r.desc = (const IterDesc*)c->desc.p; r.desc_index = -1;
     r.weighting = c->cfg.weighting; r.rejection = c->cfg.rejection; r.max_d2 = c->cfg.max_distance_sq;
+    r.weight_max_d2 = c->cfg.weight_max_distance_sq > 0.f ? c->cfg.weight_max_distance_sq : c->cfg.max_distance_sq;
     if (proj_tiled(c, algo)) { r.src_pts = (const float4*)c->src_raw_pts.p; r.src_nrm = (const float4*)c->src_raw_nrm.p; }
     r.profile = getenv("ICP_GPU_REDUCE_PROFILE") ? 1 : 0;   // diagnostic
     if (solve && c->peer_world > 1) {
@@ -473,6 +496,7 @@ void fill_reduce_args(icp_gpu_ctx* c, ReduceArgs& r, int algo, int solve) {
         if (const char* e = getenv("ICP_GPU_PEER_TIMEOUT_MS")) { const long long v = atoll(e); if (v >= 1 && v <= 600000) ms = (unsigned long long)v; }
         r.peer.timeout_ns = ms * 1000000ull;
         for (int j = 0; j < c->peer_world; ++j) r.peer.box[j] = (PeerBox*)c->peer_ptr[j];
+        r.peer.plan_check = c->peer_plan_check;
     }
 }
 
@@ -524,8 +548,13 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     int rc = check_ready(ctx); if (rc) return rc;
     if (join_index(ctx)) return ICP_GPU_E_CUDA;
+    if (ctx->peer_world > 1 && ctx->cfg.multires)
+        return fail(ctx, ICP_GPU_E_ARG, "point-sharded registration: the multi-resolution schedule is derived from the local shard (level strides and count "
+                                        "differ between ranks and from the unsharded cloud); run it with multires off");
     Plan plan;
     rc = make_plan(ctx, plan); if (rc) return rc;
+    // what every rank must agree on for the exchanges to pair up; checked inside the first exchange (icp_internal.cuh: peer_exchange_row)
+    ctx->peer_plan_check = plan.n_iters * 64 + ctx->cfg.metric * 16 + ctx->cfg.minimizer * 8 + (ctx->cfg.lm_max_iterations & 7);
     const int algo = choose_algorithm(ctx);
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     // descriptors + selection lists + pose up (pinned staging, stream-ordered)
@@ -565,7 +594,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         std::vector<long long> key;
         key.push_back(algo); key.push_back(ctx->cfg.metric); key.push_back(ctx->cfg.minimizer); key.push_back(ctx->cfg.lm_max_iterations);
         key.push_back(ctx->cfg.weighting); key.push_back(ctx->cfg.rejection); key.push_back(ctx->cfg.color_icp); key.push_back(ctx->cfg.collect_stats);
-        key.push_back((long long)__float_as_int_host(ctx->cfg.max_distance_sq));
+        key.push_back((long long)__float_as_int_host(ctx->cfg.max_distance_sq)); key.push_back((long long)__float_as_int_host(ctx->cfg.weight_max_distance_sq));
         key.push_back(ctx->n_src); key.push_back(ctx->n_tgt); key.push_back(ctx->T); key.push_back(ctx->width); key.push_back(ctx->height);
         for (int k = 0; k < 9; ++k) key.push_back((long long)__float_as_int_host(ctx->have_camera ? ctx->K[k] : 0.f));
         key.push_back((long long)(uintptr_t)ctx->mask.p); key.push_back((long long)(uintptr_t)ctx->stream);
@@ -687,6 +716,7 @@ void icp_gpu_default_config(icp_gpu_config* cfg) {
     cfg->weighting = ICP_GPU_WEIGHT_CONSTANT; cfg->rejection = 1; cfg->max_distance_sq = 0.0003f;
     cfg->color_icp = 0; cfg->multires = 0; cfg->pyramid_mode = ICP_GPU_PYRAMID_STRIDE; cfg->n_iterations = 20;
     cfg->lm_max_iterations = 10; cfg->nn_algorithm = ICP_GPU_NN_AUTO; cfg->use_graph = 1; cfg->collect_stats = 1;
+    cfg->weight_max_distance_sq = 0.0f;
 }
 
 int icp_gpu_create(icp_gpu_ctx** out, int device) {
@@ -710,7 +740,7 @@ int icp_gpu_create(icp_gpu_ctx** out, int device) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_index_ready, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-    for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+    for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_xyz[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
                                            cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_pose, 16 * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_history, 16 * sizeof(float) * ICP_MAX_ITERS) == cudaSuccess;
@@ -735,7 +765,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     peer_close(ctx);
     if (ctx->peer_box) cudaFree(ctx->peer_box);
     DeviceBuf* bufs[] = {&ctx->stage, &ctx->stage2, &ctx->src_pts, &ctx->src_nrm, &ctx->tgt_pts, &ctx->tgt_nrm, &ctx->tgt_pts_sorted, &ctx->tgt_nrm_sorted,
-                         &ctx->grid, &ctx->bbox, &ctx->sbbox, &ctx->lv_flags, &ctx->lv_tiles, &ctx->delta_a, &ctx->delta_b, &ctx->tsort.keys_a, &ctx->tsort.keys_b, &ctx->tsort.idx_a, &ctx->tsort.idx_b, &ctx->tsort.tile_hist, &ctx->tsort.msd, &ctx->ssort.keys_a, &ctx->ssort.keys_b, &ctx->ssort.idx_a, &ctx->ssort.idx_b, &ctx->ssort.tile_hist, &ctx->ssort.msd, &ctx->state, &ctx->desc, &ctx->mask,
+                         &ctx->grid, &ctx->bbox, &ctx->sbbox, &ctx->lv_flags, &ctx->lv_tiles, &ctx->delta_a, &ctx->delta_b, &ctx->tsort.keys_a, &ctx->tsort.keys_b, &ctx->tsort.idx_a, &ctx->tsort.idx_b, &ctx->tsort.hist, &ctx->tsort.msd, &ctx->ssort.keys_a, &ctx->ssort.keys_b, &ctx->ssort.idx_a, &ctx->ssort.idx_b, &ctx->ssort.hist, &ctx->ssort.msd, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->order_dev,
                          &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
@@ -746,7 +776,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]); }
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_xyz[i]) cudaEventDestroy(ctx->ev_xyz[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_index_ready) cudaEventDestroy(ctx->ev_index_ready);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -785,12 +815,14 @@ int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
     if (c->selection < 0 || c->selection > 1) return fail(ctx, ICP_GPU_E_ARG, "selection %d", c->selection);
     if (c->selection_rng < 0 || c->selection_rng > 1) return fail(ctx, ICP_GPU_E_ARG, "selection_rng %d", c->selection_rng);
     if (c->weighting < 0 || c->weighting > 3) return fail(ctx, ICP_GPU_E_ARG, "weighting %d", c->weighting);
-    if (c->nn_algorithm < 0 || c->nn_algorithm > 2) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
+    if (c->nn_algorithm < 0 || c->nn_algorithm > 3) return fail(ctx, ICP_GPU_E_ARG, "nn_algorithm %d", c->nn_algorithm);
+    if (c->nn_algorithm == ICP_GPU_NN_BRUTE_NORM && c->color_icp) return fail(ctx, ICP_GPU_E_ARG, "the norm-thresholded brute-force matcher is 3-D only (NearestNeighbor.h:63-69)");
     if (c->pyramid_mode != ICP_GPU_PYRAMID_STRIDE && c->pyramid_mode != ICP_GPU_PYRAMID_VOXEL) return fail(ctx, ICP_GPU_E_ARG, "pyramid_mode %d", c->pyramid_mode);
     if (c->multires && c->pyramid_mode == ICP_GPU_PYRAMID_VOXEL && c->selection == ICP_GPU_SELECT_RANDOM && c->selection_rng == ICP_GPU_RNG_MT19937)
         return fail(ctx, ICP_GPU_E_ARG, "voxel pyramid levels are built on the device: use the device selection stream with them");
     if (c->n_iterations < 0 || c->n_iterations > ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "n_iterations %d (max %d)", c->n_iterations, ICP_MAX_ITERS);
     if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);
+    if (!(c->weight_max_distance_sq >= 0.f)) return fail(ctx, ICP_GPU_E_ARG, "weight_max_distance_sq %g", (double)c->weight_max_distance_sq);
     if (c->matching == ICP_GPU_MATCH_PROJECTIVE && c->color_icp) return fail(ctx, ICP_GPU_E_ARG, "colour ICP is a k-NN variant (main.cpp:240-243)");
     ctx->cfg = *c;
     return ICP_GPU_OK;

@@ -23,34 +23,48 @@ __device__ __forceinline__ unsigned int enc_f(float f) { unsigned int b = __floa
 __device__ __forceinline__ float dec_f(unsigned int e) { return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e); }
 
 // Layout in HBM: points {x,y,z,original index bits}, normals {nx,ny,nz,rgba bits}.
-// bbox[0..2] = encoded min, bbox[3..5] = encoded max of the finite points (initialised to 0xFFFFFFFF / 0).
+// scratch words: [0..2] encoded min, [3..5] encoded max of the finite points (initialised to 0xFFFFFFFF / 0), [6] block ticket,
+// [7] number of points with a non-finite coordinate.  The kernel also clears the radix sort's histograms (zero / zero_words)
+// and its last block derives the grid parameters from the finished bounding box -- no launch of their own.
+__device__ void grid_params_from_bbox(const unsigned int* bbox, int T, GridParams& P);
+
 __global__ void __launch_bounds__(256) pack_bbox_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const uint8_t* __restrict__ rgba,
-                                                        int n, float4* __restrict__ pts, float4* __restrict__ nrmo, unsigned int* __restrict__ bbox) {
+                                                        int n, float4* __restrict__ pts, float4* __restrict__ nrmo, unsigned int* bbox, int T,
+                                                        GridParams* __restrict__ gp_out, unsigned int* __restrict__ zero, long long zero_words,
+                                                        int with_normals) {
+    for (long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x; z < zero_words; z += (long long)gridDim.x * blockDim.x) zero[z] = 0u;
     unsigned int mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+    unsigned int bad = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        unsigned int c = 0;
-        if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
         float4 p; p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2]; p.w = __int_as_float(i);
-        float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
-        if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
-        pts[i] = p; nrmo[i] = m;
+        pts[i] = p;
+        if (with_normals) {
+            unsigned int c = 0;
+            if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
+            float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
+            if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
+            nrmo[i] = m;
+        }
         if (finite3(p.x, p.y, p.z)) {
             const unsigned int e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
 #pragma unroll
             for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], e[a]); mx[a] = max(mx[a], e[a]); }
-        }
+        } else ++bad;
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
         mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
     }
+    bad = __reduce_add_sync(0xFFFFFFFFu, bad);
     // one atomic per block and value (thousands of same-address atomics from every warp cost tens of microseconds)
-    __shared__ unsigned int s_mn[3][8], s_mx[3][8];
+    __shared__ unsigned int s_mn[3][8], s_mx[3][8], s_bad[8];
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { s_mn[a][wid] = mn[a]; s_mx[a][wid] = mx[a]; }
+        s_bad[wid] = bad;
     }
     __syncthreads();
     if (threadIdx.x < 6) {
@@ -58,24 +72,52 @@ __global__ void __launch_bounds__(256) pack_bbox_kernel(const float* __restrict_
         unsigned int v = is_max ? 0u : 0xFFFFFFFFu;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v = is_max ? max(v, s_mx[a][w]) : min(v, s_mn[a][w]);
         if (is_max) atomicMax(&bbox[3 + a], v); else atomicMin(&bbox[a], v);
+    } else if (threadIdx.x == 6) {
+        unsigned int v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += s_bad[w];
+        if (v) atomicAdd(&bbox[7], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&bbox[6], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        unsigned int bb[6];
+        for (int k = 0; k < 6; ++k) bb[k] = *reinterpret_cast<volatile unsigned int*>(&bbox[k]);
+        GridParams P;
+        grid_params_from_bbox(bb, T, P);
+        *gp_out = P;
     }
 }
 
+// The normal / colour records alone: host uploads deliver them after the points, and only the last pass of the sort reads them.
+__global__ void __launch_bounds__(256) pack_normals_kernel(const float* __restrict__ nrm, const uint8_t* __restrict__ rgba, int n, float4* __restrict__ nrmo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned int c = 0;
+    if (rgba) c = reinterpret_cast<const unsigned int*>(rgba)[i];
+    float4 m = make_float4(0.f, 0.f, 0.f, __uint_as_float(c));
+    if (nrm) { m.x = nrm[3 * (size_t)i]; m.y = nrm[3 * (size_t)i + 1]; m.z = nrm[3 * (size_t)i + 2]; }
+    nrmo[i] = m;
+}
+
+// with_normals = 0: only the point records (the normal records follow through IcpLatePack / icp_launch_cloud_sort)
 cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
-                                  unsigned int* bbox, cudaStream_t s) {
+                                  unsigned int* bbox, int T, GridParams* grid, unsigned int* zero, long long zero_words, int with_normals,
+                                  cudaStream_t s) {
     cudaError_t e;
     if ((e = cudaMemsetAsync(bbox, 0xFF, 3 * sizeof(unsigned int), s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(bbox + 3, 0x00, 5 * sizeof(unsigned int), s)) != cudaSuccess) return e;   // max[3], spare, non-finite counter
-    if (n <= 0) return cudaSuccess;
-    const int nb = min((n + 255) / 256, 148 * 4);
-    pack_bbox_kernel<<<nb, 256, 0, s>>>(xyz, nrm, rgba, n, pts, nrmo, bbox);
+    if ((e = cudaMemsetAsync(bbox + 3, 0x00, 5 * sizeof(unsigned int), s)) != cudaSuccess) return e;   // max[3], ticket, non-finite counter
+    int nb = min((n + 255) / 256, 148 * 4); if (nb < 1) nb = 1;           // n == 0: one block still writes the (empty-cloud) grid parameters
+    pack_bbox_kernel<<<nb, 256, 0, s>>>(xyz, nrm, rgba, n, pts, nrmo, bbox, T, grid, zero, zero_words, with_normals);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------- grid parameters and cell codes
 // A pure function of the bounding box: every block that needs the parameters derives them itself (no launch of its own);
 // the oracle restates this arithmetic (oracle/icp_oracle.c: voxel levels), hence no FMA.
-__device__ void grid_params_from_bbox(const unsigned int* __restrict__ bbox, int T, GridParams& P) {
+__device__ void grid_params_from_bbox(const unsigned int* bbox, int T, GridParams& P) {
     float e[3], maxabs[3];
     const bool empty = bbox[0] == 0xFFFFFFFFu && bbox[3] == 0u;
     for (int a = 0; a < 3; ++a) {
@@ -101,6 +143,11 @@ __device__ void grid_params_from_bbox(const unsigned int* __restrict__ bbox, int
         P.delta[a] = 1e-3f * P.h[a] + 1e-6f * maxabs[a];
     }
     P.T = T; P.axis_seq = seq; P.n_finite = 0; P.pad = 0;
+    // where the bits of an axis' cell index go in the code: level k (root split = most significant code bit) takes the
+    // highest not yet used bit of its axis
+    int r[3] = {P.bits[0], P.bits[1], P.bits[2]};
+    for (int a = 0; a < 3; ++a) for (int j = 0; j < ICP_MAX_BITS_PER_AXIS; ++j) P.bitpos[a][j] = 0;
+    for (int k = 0; k < T; ++k) { const int a = (int)((seq >> (2 * k)) & 3ull); --r[a]; P.bitpos[a][r[a]] = (unsigned char)(T - 1 - k); }
 }
 
 __device__ __forceinline__ int cell_index(const GridParams& g, int a, float x) {
@@ -110,79 +157,65 @@ __device__ __forceinline__ int cell_index(const GridParams& g, int a, float x) {
     return min(max(i, 0), hi);
 }
 
-__device__ __forceinline__ unsigned int cell_code(const GridParams& g, float x, float y, float z) {
-    const int c0 = cell_index(g, 0, x), c1 = cell_index(g, 1, y), c2 = cell_index(g, 2, z);
-    int r0 = g.bits[0], r1 = g.bits[1], r2 = g.bits[2];
+// The code bits an axis contributes for cell index c: bit j of c lands at bitpos[a][j].
+__device__ __forceinline__ unsigned int axis_spread(const GridParams& g, int a, int c) {
     unsigned int code = 0;
-    unsigned long long seq = g.axis_seq;
-    for (int k = 0; k < g.T; ++k) {
-        const int a = (int)(seq & 3ull); seq >>= 2;
-        int bit;
-        if (a == 0) { --r0; bit = (c0 >> r0) & 1; }
-        else if (a == 1) { --r1; bit = (c1 >> r1) & 1; }
-        else { --r2; bit = (c2 >> r2) & 1; }
-        code = (code << 1) | (unsigned int)bit;
-    }
+#pragma unroll
+    for (int j = 0; j < ICP_MAX_BITS_PER_AXIS; ++j)
+        if (j < g.bits[a]) code |= (((unsigned int)c >> j) & 1u) << g.bitpos[a][j];
     return code;
+}
+
+__device__ __forceinline__ unsigned int cell_code(const GridParams& g, float x, float y, float z) {
+    return axis_spread(g, 0, cell_index(g, 0, x)) | axis_spread(g, 1, cell_index(g, 1, y)) | axis_spread(g, 2, cell_index(g, 2, z));
 }
 
 // ---------------------------------------------------------------------------- stable LSD radix sort of (key, index)
 // key = cell code (T bits); a point with a non-finite coordinate gets 1 << T: it sorts after every cell (sources keep such
 // points at the end -- every point needs a slot; targets simply never look past n_finite).  T + 1 bits are sorted in
-// passes of <= 11 bits.  A pass: every tile (256 threads x ipt items, contiguous) publishes its digit histogram; the scatter
-// kernel of the pass derives a tile's first output slot per digit from those rows (digits before it, the same digit in earlier
-// tiles), ranks the tile's items per warp (contiguous chunk per warp, rounds of 32 in order; match.any groups equal
-// digits, the group's lowest lane advances the warp's running count) and writes each item to its slot: stable, no
-// atomics, deterministic.  The histogram of pass 0 is produced by the key kernel; the last pass moves the payload
-// (point and normal records) instead of the index.
+// passes of <= 11 bits over tiles of 256 threads x ipt contiguous items.  Per pass:
+//   digit histograms per tile, digit-major (hist[d * tiles_pad + tile]): pass 0's by the key kernel; pass p+1's by the
+//     scatter kernel of pass p (an item's next tile is known once its slot is: one L2 atomic per item);
+//   radix_scan_kernel: one warp per digit turns the digit's row into exclusive prefixes over the tiles (+ the digit's total);
+//   radix_scatter_kernel: a tile's first slot per digit = digits before it (block scan of the totals) + the same digit in
+//     earlier tiles; the tile's items are ranked per warp (contiguous chunk per warp, rounds of 32 in order; match.any groups
+//     equal digits, the group's lowest lane advances the warp's running slot) and written to their slots: stable,
+//     deterministic -- no atomics decide any position.  The last pass moves the payload (point and normal records).
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_BITS 11
 #define RS_MAX_BINS (1 << RS_MAX_BITS)
 
-__global__ void __launch_bounds__(RS_THREADS) keys_kernel(const float4* __restrict__ pts, int n, int T, const unsigned int* __restrict__ bbox,
-                                                          GridParams* __restrict__ gp_out, unsigned int* __restrict__ keys, int tile_items, int shift,
-                                                          int bits, unsigned int* __restrict__ tile_hist, unsigned int* __restrict__ nonfinite_counter) {
+// Thread per point: key + the point's count in pass 0's histogram (cleared by the pack kernel).
+__global__ void __launch_bounds__(RS_THREADS) keys_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
+                                                          unsigned int* __restrict__ keys, int tile_items, int tiles_pad, int shift, int bits,
+                                                          unsigned int* __restrict__ hist0) {
     __shared__ GridParams g;
-    __shared__ unsigned int hist[RS_MAX_BINS];
-    const int bins = 1 << bits;
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) hist[d] = 0u;
-    if (threadIdx.x == 0) { grid_params_from_bbox(bbox, T, g); if (blockIdx.x == 0) *gp_out = g; }
+    if (threadIdx.x < sizeof(GridParams) / 4) reinterpret_cast<unsigned int*>(&g)[threadIdx.x] = reinterpret_cast<const unsigned int*>(gp)[threadIdx.x];
     __syncthreads();
-    const unsigned int mask = (unsigned int)bins - 1u;
-    const long long base = (long long)blockIdx.x * tile_items;
-    unsigned int bad = 0;
-    for (int k = threadIdx.x; k < tile_items; k += RS_THREADS) {
-        const long long i = base + k;
-        if (i >= n) break;
-        const float4 p = pts[i];
-        unsigned int key;
-        if (finite3(p.x, p.y, p.z)) key = cell_code(g, p.x, p.y, p.z);
-        else { key = 1u << T; ++bad; }                    // can never win the strict '>' scan of NearestNeighbor.h:87
-        keys[i] = key;
-        atomicAdd(&hist[(key >> shift) & mask], 1u);
-    }
-    bad = __reduce_add_sync(0xFFFFFFFFu, bad);
-    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite_counter, bad);
-    __syncthreads();
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) tile_hist[(size_t)blockIdx.x * RS_MAX_BINS + d] = hist[d];
+    const int i = blockIdx.x * RS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    const unsigned int key = finite3(p.x, p.y, p.z) ? cell_code(g, p.x, p.y, p.z) : (1u << g.T);   // non-finite: can never win the strict '>' scan of NearestNeighbor.h:87
+    keys[i] = key;
+    atomicAdd(&hist0[(size_t)((key >> shift) & ((1u << bits) - 1u)) * tiles_pad + (unsigned int)i / (unsigned int)tile_items], 1u);
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const unsigned int* __restrict__ keys, int n, int tile_items, int shift, int bits,
-                                                                unsigned int* __restrict__ tile_hist) {
-    __shared__ unsigned int hist[RS_MAX_BINS];
-    const int bins = 1 << bits;
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) hist[d] = 0u;
-    __syncthreads();
-    const unsigned int mask = (unsigned int)bins - 1u;
-    const long long base = (long long)blockIdx.x * tile_items;
-    for (int k = threadIdx.x; k < tile_items; k += RS_THREADS) {
-        const long long i = base + k;
-        if (i >= n) break;
-        atomicAdd(&hist[(keys[i] >> shift) & mask], 1u);
+// One warp per digit: the digit's per-tile counts -> exclusive prefixes over the tiles; totals[d] = the digit's count.
+__global__ void __launch_bounds__(RS_THREADS) radix_scan_kernel(unsigned int* __restrict__ hist, int bins, int n_tiles, int tiles_pad, unsigned int* __restrict__ totals) {
+    const int d = (blockIdx.x * RS_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (d >= bins) return;
+    unsigned int* row = hist + (size_t)d * tiles_pad;
+    unsigned int carry = 0;
+    for (int c = 0; c < tiles_pad; c += 32) {
+        const unsigned int v = c + lane < n_tiles ? row[c + lane] : 0u;      // the pad columns are never written
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        row[c + lane] = carry + inc - v;
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
-    __syncthreads();
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) tile_hist[(size_t)blockIdx.x * RS_MAX_BINS + d] = hist[d];
+    if (lane == 0) totals[d] = carry;
 }
 
 __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total) {
@@ -207,13 +240,30 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
 }
 
 // idx_in == nullptr: the identity (pass 0).  pts_in != nullptr: last pass -- the payload is moved instead of the index.
-// msd_start (nullable, last pass): first output slot of every digit of the pass, bins + 1 entries.
+// hist: this pass's scanned histogram; hist_next (nullable): the next pass's, counted here.  msd_start (nullable, last pass):
+// first output slot of every digit of the pass, bins + 1 entries.  ipt <= RS_REG_IPT: a thread's keys, indices and slots stay
+// in registers between the phases (all loads of a phase in flight at once: with one 8-warp block per SM the kernel is bound by
+// the length of its chain of dependent memory round trips, not by bandwidth).
+#define RS_REG_IPT 16
+// The lanes of the (converged, `vm`) warp whose digit equals mine: match.any, or `bits` ballots combined (one per digit bit).
+__device__ __forceinline__ unsigned int digit_peers(unsigned int vm, unsigned int dg, int bits, int use_ballot) {
+    if (!use_ballot) return __match_any_sync(vm, dg);
+    unsigned int peers = vm;
+    for (int k = 0; k < bits; ++k) {
+        const unsigned int b = __ballot_sync(vm, (dg >> k) & 1u);
+        peers &= ((dg >> k) & 1u) ? b : ~b;
+    }
+    return peers;
+}
+template <bool REG>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ idx_in,
                                                                    unsigned int* __restrict__ keys_out, unsigned int* __restrict__ idx_out, int n,
-                                                                   int tile_items, int n_tiles, int shift, int bits,
-                                                                   const unsigned int* __restrict__ tile_hist, const float4* __restrict__ pts_in,
-                                                                   const float4* __restrict__ nrm_in, float4* __restrict__ pts_out,
-                                                                   float4* __restrict__ nrm_out, unsigned int* __restrict__ msd_start) {
+                                                                   int ipt, int tiles_pad, int shift, int bits,
+                                                                   const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals,
+                                                                   unsigned int* __restrict__ hist_next, int shift_next, int bits_next,
+                                                                   const float4* __restrict__ pts_in, const float4* __restrict__ nrm_in,
+                                                                   float4* __restrict__ pts_out, float4* __restrict__ nrm_out,
+                                                                   unsigned int* __restrict__ msd_start, int use_ballot) {
     __shared__ unsigned short wcnt[RS_WARPS][RS_MAX_BINS];     // per warp and digit: count, then tile-relative first slot, then running slot
     __shared__ unsigned int base[RS_MAX_BINS];                 // per digit: first output slot of this tile
     const unsigned int FULL = 0xFFFFFFFFu;
@@ -221,48 +271,74 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
     const unsigned int mask = (unsigned int)bins - 1u;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    for (int d = threadIdx.x; d < RS_WARPS * bins; d += RS_THREADS) wcnt[d / bins][d % bins] = 0;
-    __syncthreads();
-    const int chunk = tile_items / RS_WARPS;                   // a multiple of 32
+    const int tile_items = ipt * RS_THREADS;
+    const int chunk = ipt * 32;                                // the warp's contiguous share of the tile
     const long long w0 = (long long)blockIdx.x * tile_items + (long long)w * chunk;
-    // phase A: digit counts of the warp's chunk
-    for (int r = 0; r < chunk; r += 32) {
-        const long long i = w0 + r + lane;
-        const bool valid = i < n;
-        const unsigned int vm = __ballot_sync(FULL, valid);
-        if (valid) {
-            const unsigned int dg = (keys_in[i] >> shift) & mask;
-            const unsigned int peers = __match_any_sync(vm, dg);
-            if ((peers & lt) == 0u) wcnt[w][dg] = (unsigned short)(wcnt[w][dg] + __popc(peers));
+    unsigned int kreg[RS_REG_IPT], ireg[RS_REG_IPT];
+    if (REG) {
+#pragma unroll
+        for (int r = 0; r < RS_REG_IPT; ++r) {
+            const long long i = w0 + r * 32 + lane;
+            const bool valid = r < ipt && i < n;
+            kreg[r] = valid ? keys_in[i] : 0u;
+            ireg[r] = valid ? (idx_in ? idx_in[i] : (unsigned int)i) : 0u;
         }
-        __syncwarp();
-        if (vm != FULL) break;
     }
-    __syncthreads();
-    // per digit: warp counts -> exclusive prefix over the warps; the same digit in earlier tiles; the digit's total
-    unsigned int before[RS_MAX_BINS / RS_THREADS];
+    {
+        unsigned int* z = reinterpret_cast<unsigned int*>(&wcnt[0][0]);
+        for (int d = threadIdx.x; d < RS_WARPS * RS_MAX_BINS / 2; d += RS_THREADS) z[d] = 0u;
+    }
+    // the loads of the offsets below depend on nothing: issue them before the counting phase
+    unsigned int before[RS_MAX_BINS / RS_THREADS], tot[RS_MAX_BINS / RS_THREADS];
 #pragma unroll
     for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
         const int d = k * RS_THREADS + threadIdx.x;
-        before[k] = 0u;
+        before[k] = d < bins ? __ldg(&hist[(size_t)d * tiles_pad + blockIdx.x]) : 0u;
+        tot[k] = d < bins ? __ldg(&totals[d]) : 0u;
+    }
+    __syncthreads();
+    // phase A: digit counts of the warp's chunk, rounds of 32 items
+    if (REG) {
+#pragma unroll
+        for (int r = 0; r < RS_REG_IPT; ++r) {
+            if (r < ipt) {
+                const bool valid = w0 + r * 32 + lane < n;
+                const unsigned int vm = __ballot_sync(FULL, valid);
+                if (valid) {
+                    const unsigned int dg = (kreg[r] >> shift) & mask;
+                    const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                    if ((peers & lt) == 0u) wcnt[w][dg] = (unsigned short)(wcnt[w][dg] + __popc(peers));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        for (int r = 0; r < chunk; r += 32) {
+            const long long i = w0 + r + lane;
+            const bool valid = i < n;
+            const unsigned int vm = __ballot_sync(FULL, valid);
+            if (valid) {
+                const unsigned int dg = (keys_in[i] >> shift) & mask;
+                const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                if ((peers & lt) == 0u) wcnt[w][dg] = (unsigned short)(wcnt[w][dg] + __popc(peers));
+            }
+            __syncwarp();
+            if (vm != FULL) break;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) { const int d = k * RS_THREADS + threadIdx.x; if (d < bins) base[d] = tot[k]; }
+    __syncthreads();
+    // per digit: warp counts -> exclusive prefix over the warps (tile-relative first slot of the warp's items with the digit)
+#pragma unroll
+    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
+        const int d = k * RS_THREADS + threadIdx.x;
         if (d < bins) {
             unsigned int acc = 0;
 #pragma unroll
             for (int ww = 0; ww < RS_WARPS; ++ww) { const unsigned int c = wcnt[ww][d]; wcnt[ww][d] = (unsigned short)acc; acc += c; }
-            unsigned int b0 = 0, a0 = 0, b1 = 0, a1 = 0;
-            int t = 0;
-            for (; t + 1 < n_tiles; t += 2) {                  // two independent chains of (L2-resident) loads
-                const unsigned int h0 = __ldg(&tile_hist[(size_t)t * RS_MAX_BINS + d]), h1 = __ldg(&tile_hist[(size_t)(t + 1) * RS_MAX_BINS + d]);
-                a0 += h0; a1 += h1;
-                if (t < (int)blockIdx.x) b0 += h0;
-                if (t + 1 < (int)blockIdx.x) b1 += h1;
-            }
-            if (t < n_tiles) { const unsigned int h0 = __ldg(&tile_hist[(size_t)t * RS_MAX_BINS + d]); a0 += h0; if (t < (int)blockIdx.x) b0 += h0; }
-            before[k] = b0 + b1;
-            base[d] = a0 + a1;                                 // the digit's total, scanned below
         }
     }
-    __syncthreads();
     {   // exclusive scan of the totals in digit order: every thread owns `per` consecutive digits
         const int per = (bins + RS_THREADS - 1) / RS_THREADS;
         unsigned int loc[RS_MAX_BINS / RS_THREADS]; unsigned int s = 0;
@@ -292,26 +368,60 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
     }
     __syncthreads();
     // phase B: the same rounds again; the group's lowest lane advances the warp's running slot of the digit
-    for (int r = 0; r < chunk; r += 32) {
-        const long long i = w0 + r + lane;
-        const bool valid = i < n;
-        const unsigned int vm = __ballot_sync(FULL, valid);
-        if (valid) {
-            const unsigned int key = keys_in[i];
-            const unsigned int dg = (key >> shift) & mask;
-            const unsigned int peers = __match_any_sync(vm, dg);
-            const int leader = __ffs((int)peers) - 1;
-            unsigned int old = 0;
-            if (lane == leader) { old = wcnt[w][dg]; wcnt[w][dg] = (unsigned short)(old + __popc(peers)); }
-            old = __shfl_sync(peers, old, leader);
-            const unsigned int pos = base[dg] + old + (unsigned int)__popc(peers & lt);
-            const unsigned int src = idx_in ? idx_in[i] : (unsigned int)i;
-            keys_out[pos] = key;
-            if (pts_in) { pts_out[pos] = pts_in[src]; nrm_out[pos] = nrm_in[src]; }
-            else idx_out[pos] = src;
+    const unsigned int mask_next = (1u << bits_next) - 1u;
+    if (REG) {
+        unsigned int pos[RS_REG_IPT];
+#pragma unroll
+        for (int r = 0; r < RS_REG_IPT; ++r) {
+            pos[r] = 0xFFFFFFFFu;
+            if (r < ipt) {
+                const bool valid = w0 + r * 32 + lane < n;
+                const unsigned int vm = __ballot_sync(FULL, valid);
+                if (valid) {
+                    const unsigned int dg = (kreg[r] >> shift) & mask;
+                    const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                    const int leader = __ffs((int)peers) - 1;
+                    unsigned int old = 0;
+                    if (lane == leader) { old = wcnt[w][dg]; wcnt[w][dg] = (unsigned short)(old + __popc(peers)); }
+                    old = __shfl_sync(peers, old, leader);
+                    pos[r] = base[dg] + old + (unsigned int)__popc(peers & lt);
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
-        if (vm != FULL) break;
+        // every slot is known: the moves are independent of each other
+#pragma unroll
+        for (int r = 0; r < RS_REG_IPT; ++r) {
+            if (pos[r] != 0xFFFFFFFFu) {
+                keys_out[pos[r]] = kreg[r];
+                if (pts_in) { pts_out[pos[r]] = __ldg(&pts_in[ireg[r]]); nrm_out[pos[r]] = __ldg(&nrm_in[ireg[r]]); }
+                else idx_out[pos[r]] = ireg[r];
+                if (hist_next) atomicAdd(&hist_next[(size_t)((kreg[r] >> shift_next) & mask_next) * tiles_pad + pos[r] / (unsigned int)tile_items], 1u);
+            }
+        }
+    } else {
+        for (int r = 0; r < chunk; r += 32) {
+            const long long i = w0 + r + lane;
+            const bool valid = i < n;
+            const unsigned int vm = __ballot_sync(FULL, valid);
+            if (valid) {
+                const unsigned int key = keys_in[i];
+                const unsigned int src = idx_in ? idx_in[i] : (unsigned int)i;
+                const unsigned int dg = (key >> shift) & mask;
+                const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                const int leader = __ffs((int)peers) - 1;
+                unsigned int old = 0;
+                if (lane == leader) { old = wcnt[w][dg]; wcnt[w][dg] = (unsigned short)(old + __popc(peers)); }
+                old = __shfl_sync(peers, old, leader);
+                const unsigned int p = base[dg] + old + (unsigned int)__popc(peers & lt);
+                keys_out[p] = key;
+                if (pts_in) { pts_out[p] = pts_in[src]; nrm_out[p] = nrm_in[src]; }
+                else idx_out[p] = src;
+                if (hist_next) atomicAdd(&hist_next[(size_t)((key >> shift_next) & mask_next) * tiles_pad + p / (unsigned int)tile_items], 1u);
+            }
+            __syncwarp();
+            if (vm != FULL) break;
+        }
     }
 }
 
@@ -321,35 +431,58 @@ void icp_radix_plan(int n, int T, IcpRadixPlan* p) {
     const int lo = total / p->n_pass, extra = total % p->n_pass;
     int shift = 0;
     for (int k = 0; k < p->n_pass; ++k) { p->bits[k] = lo + (k < extra ? 1 : 0); p->shift[k] = shift; shift += p->bits[k]; }
-    // 16 items per thread; larger clouds get larger tiles so that the per-tile histogram rows every scatter block sums stay few
-    long long ipt = 16;
-    while ((long long)n > ipt * RS_THREADS * 160 && ipt < 224) ipt += 16;
+    // One tile per SM while that keeps a thread's items in registers (4 .. 16 items per thread), more tiles beyond; only clouds
+    // of more than 16 M points get larger tiles (the histograms have one column per tile).
+    long long ipt = ((long long)n + RS_THREADS * 148 - 1) / (RS_THREADS * 148);
+    if (ipt < 4) ipt = 4;
+    if (ipt > RS_REG_IPT) ipt = RS_REG_IPT;
+    while ((long long)n > ipt * RS_THREADS * 4096 && ipt < 224) ipt += 16;
+    p->ipt = (int)ipt;
     p->tile_items = (int)(ipt * RS_THREADS);
     p->n_tiles = n > 0 ? (int)(((long long)n + p->tile_items - 1) / p->tile_items) : 0;
+    p->tiles_pad = ((p->n_tiles > 0 ? p->n_tiles : 1) + 31) / 32 * 32;
 }
 
-size_t icp_radix_hist_words(int n, int T) { IcpRadixPlan p; icp_radix_plan(n, T, &p); return (size_t)(p.n_tiles > 0 ? p.n_tiles : 1) * RS_MAX_BINS; }
+// words of histogram scratch: one digit-major matrix per pass, then the per-digit totals
+size_t icp_radix_hist_words(int n, int T) {
+    IcpRadixPlan p; icp_radix_plan(n, T, &p);
+    return (size_t)p.n_pass * RS_MAX_BINS * p.tiles_pad + RS_MAX_BINS;
+}
 
-// Sorts a packed cloud into (cell code, original index) order.  keys_a / keys_b: n entries each (keys_sorted ends up in
-// *keys_sorted_out, one of the two); idx_a / idx_b: n entries each; bbox: filled by icp_launch_pack_cloud (bbox[7] = number of
-// non-finite points afterwards); msd_start: RS_MAX_BINS + 1 entries (nullable).
-cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid, unsigned int* bbox,
+// Sorts a packed cloud into (cell code, original index) order.  grid / hist: written / cleared by icp_launch_pack_cloud on the
+// same stream before.  keys_a / keys_b: n entries each (the sorted keys end up in *keys_sorted_out, one of the two);
+// idx_a / idx_b: n entries each; hist: icp_radix_hist_words(); msd_start: ICP_MSD_WORDS entries (nullable).
+cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, const GridParams* grid,
                                   unsigned int* keys_a, unsigned int* keys_b, unsigned int* idx_a, unsigned int* idx_b,
-                                  unsigned int* tile_hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
-                                  unsigned int** keys_sorted_out, int* msd_shift_out, cudaStream_t s, int* n_launches) {
+                                  unsigned int* hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
+                                  unsigned int** keys_sorted_out, int* msd_shift_out, const IcpLatePack* late, cudaStream_t s, int* n_launches) {
     IcpRadixPlan p; icp_radix_plan(n, T, &p);
     int launches = 0;
     if (msd_shift_out) *msd_shift_out = p.shift[p.n_pass - 1];
     unsigned int* kin = keys_a; unsigned int* kout = keys_b;
     unsigned int* iin = nullptr; unsigned int* iout = idx_a;
-    // n == 0: one block still writes the (empty-cloud) grid parameters
-    keys_kernel<<<p.n_tiles > 0 ? p.n_tiles : 1, RS_THREADS, 0, s>>>(pts_in, n, T, bbox, grid, kin, p.tile_items, p.shift[0], p.bits[0], tile_hist, bbox + 7);
-    ++launches;
+    const size_t mat = (size_t)RS_MAX_BINS * p.tiles_pad;
+    unsigned int* totals = hist + (size_t)p.n_pass * mat;
+    const int use_ballot = getenv("ICP_GPU_RADIX_BALLOT") ? 1 : 0;       // tuning knob (A/B measurement)
+    if (n > 0) { keys_kernel<<<(n + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, s>>>(pts_in, n, grid, kin, p.tile_items, p.tiles_pad, p.shift[0], p.bits[0], hist); ++launches; }
     for (int k = 0; k < p.n_pass && n > 0; ++k) {
         const bool last = k == p.n_pass - 1;
-        if (k > 0) { radix_hist_kernel<<<p.n_tiles, RS_THREADS, 0, s>>>(kin, n, p.tile_items, p.shift[k], p.bits[k], tile_hist); ++launches; }
-        radix_scatter_kernel<<<p.n_tiles, RS_THREADS, 0, s>>>(kin, iin, kout, iout, n, p.tile_items, p.n_tiles, p.shift[k], p.bits[k], tile_hist,
-                                                             last ? pts_in : nullptr, nrm_in, pts_sorted, nrm_sorted, last ? msd_start : nullptr);
+        const int bins = 1 << p.bits[k];
+        radix_scan_kernel<<<(bins * 32 + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, s>>>(hist + k * mat, bins, p.n_tiles, p.tiles_pad, totals); ++launches;
+        if (last && late) {
+            // the normal records (nrm_in) are packed only now: their upload had the earlier passes to finish
+            cudaError_t e = cudaStreamWaitEvent(s, late->ready, 0);
+            if (e != cudaSuccess) return e;
+            pack_normals_kernel<<<(n + 255) / 256, 256, 0, s>>>(late->nrm, late->rgba, n, late->nrmo); ++launches;
+        }
+        unsigned int* hn = last ? nullptr : hist + (k + 1) * mat;
+        const int sn = last ? 0 : p.shift[k + 1], bn = last ? 1 : p.bits[k + 1];
+        if (p.ipt <= RS_REG_IPT)
+            radix_scatter_kernel<true><<<p.n_tiles, RS_THREADS, 0, s>>>(kin, iin, kout, iout, n, p.ipt, p.tiles_pad, p.shift[k], p.bits[k], hist + k * mat, totals, hn, sn, bn,
+                                                                       last ? pts_in : nullptr, nrm_in, pts_sorted, nrm_sorted, last ? msd_start : nullptr, use_ballot);
+        else
+            radix_scatter_kernel<false><<<p.n_tiles, RS_THREADS, 0, s>>>(kin, iin, kout, iout, n, p.ipt, p.tiles_pad, p.shift[k], p.bits[k], hist + k * mat, totals, hn, sn, bn,
+                                                                        last ? pts_in : nullptr, nrm_in, pts_sorted, nrm_sorted, last ? msd_start : nullptr, use_ballot);
         ++launches;
         unsigned int* t = kin; kin = kout; kout = t;
         iin = iout; iout = (iout == idx_a) ? idx_b : idx_a;
@@ -477,18 +610,18 @@ __global__ void __launch_bounds__(LV_THREADS) level_flags_kernel(const unsigned 
             const long long i = base + t;
             if (i >= count) continue;
             const int* dl = sd + LV_HALO + t;                  // dl[o] = delta(i + o)
-            int l = 0, r = 0;                                  // the run [i + l, i + r]
-            bool overfull_cell = false;
-            for (;;) {
-                const int d = max(dl[l], dl[r + 1]);
-                if (d < 0) break;                              // the whole level is one run
-                int nl = l, nr = r;
-                while (nr - nl + 1 <= 32 && dl[nl] >= d) --nl;
-                while (nr - nl + 1 <= 32 && dl[nr + 1] >= d) ++nr;
-                if (nr - nl + 1 > 32) { overfull_cell = (d == T && l == 0 && r == 0); break; }
-                l = nl; r = nr;
+            // Element i starts a node iff joining it with its left neighbour -- at the depth d = delta(i) where the two
+            // first share a cell -- would make a run of more than 32 elements (the shallowest run with <= 32 elements
+            // around i then starts at i).  The run of depth d around i: to the left while delta >= d, to the right alike.
+            const int di = dl[0];
+            bool f = true;
+            if (di >= 0) {
+                int size = 2, j = -1;
+                while (size <= 32 && dl[j] >= di) { ++size; --j; }
+                j = 1;
+                while (size <= 32 && dl[j] >= di) { ++size; ++j; }
+                f = size > 32 && (di < T || (i & 31) == 0);    // a finest cell with more than 32 elements is cut at multiples of 32
             }
-            const bool f = overfull_cell ? (dl[0] < T || (i & 31) == 0) : (l == 0);
             flags[i] = f ? 1 : 0;
             mine += f ? 1u : 0u;
         }
@@ -616,19 +749,17 @@ __global__ void __launch_bounds__(UP_THREADS) upper_levels_kernel(int* delta_a, 
             const int i = base + threadIdx.x;
             unsigned int f = 0u;
             if (i < n_prev) {
-                // delta(j) of this level's elements; -1 outside (1 .. n_prev - 1)
+                // the rule of level_flags_kernel; delta(j) of this level's elements, -1 outside (1 .. n_prev - 1)
                 auto dl = [&](int o) -> int { const int j = i + o; return (j > 0 && j < n_prev) ? din[j] : -1; };
-                int l = 0, r = 0; bool overfull_cell = false;
-                for (;;) {
-                    const int d = max(dl(l), dl(r + 1));
-                    if (d < 0) break;
-                    int nl = l, nr = r;
-                    while (nr - nl + 1 <= 32 && dl(nl) >= d) --nl;
-                    while (nr - nl + 1 <= 32 && dl(nr + 1) >= d) ++nr;
-                    if (nr - nl + 1 > 32) { overfull_cell = (d == T && l == 0 && r == 0); break; }
-                    l = nl; r = nr;
+                const int di = dl(0);
+                f = 1u;
+                if (di >= 0) {
+                    int size = 2, j = -1;
+                    while (size <= 32 && dl(j) >= di) { ++size; --j; }
+                    j = 1;
+                    while (size <= 32 && dl(j) >= di) { ++size; ++j; }
+                    f = (size > 32 && (di < T || (i & 31) == 0)) ? 1u : 0u;
                 }
-                f = (overfull_cell ? (dl(0) < T || (i & 31) == 0) : (l == 0)) ? 1u : 0u;
             }
             const unsigned int ex = block_exclusive_scan(f, &s_total) + s_carry;
             if (i < n_prev) {
@@ -770,7 +901,9 @@ __device__ __forceinline__ bool boxes_meet(const float* lo, const float* hi, con
 __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const BvhDesc* __restrict__ bvh, const float4* __restrict__ box,
                                                                          const unsigned int* __restrict__ child_start,
                                                                          unsigned int* __restrict__ adj, float4* __restrict__ adj_box,
-                                                                         int capacity, float r_factor, int lv) {
+                                                                         int capacity, float r_factor, int lv,
+                                                                         const unsigned int* __restrict__ node_rank, const unsigned int* __restrict__ adj1,
+                                                                         const float4* __restrict__ adj1_box, int adj1_capacity) {
     __shared__ unsigned int s_node[ADJ_WARPS][32 * ICP_BVH_MAX_LEVELS];
     __shared__ unsigned int s_list[ADJ_WARPS][64];
     const BvhDesc b = *bvh;
@@ -787,10 +920,39 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
         const float4 mlo = box[2 * (size_t)(b.offset[lv] + l)], mhi = box[2 * (size_t)(b.offset[lv] + l) + 1];
         float R = r_factor * fmaxf(fmaxf(mhi.x - mlo.x, mhi.y - mlo.y), mhi.z - mlo.z);
         int count = 0; bool ok = false;
+        // Leaves (lv = 0) with the level-1 lists already built: while the leaf's inflated box lies inside the inflated box of its
+        // level-1 node m, every leaf that meets it is a child of a node of m's list -- two rounds of box tests (the <= 32 nodes
+        // of the list, then the children of those that meet) instead of a walk from the root.
+        int pm = -1, pna = 0; float4 plo = make_float4(0.f, 0.f, 0.f, 0.f), phi = plo;
+        if (lv == 0 && adj1 && b.n_levels >= 2) {
+            pm = (int)(node_rank[b.coffset[1] + l + 1] - 1u);
+            if (pm < adj1_capacity) { plo = adj1_box[2 * (size_t)pm]; phi = adj1_box[2 * (size_t)pm + 1]; pna = __float_as_int(plo.w); } else pm = -1;
+        }
         for (int attempt = 0; attempt < 6 && !ok; ++attempt, R *= 0.5f) {
             const float lo[3] = {__fsub_rd(mlo.x, R), __fsub_rd(mlo.y, R), __fsub_rd(mlo.z, R)};
             const float hi[3] = {__fadd_ru(mhi.x, R), __fadd_ru(mhi.y, R), __fadd_ru(mhi.z, R)};
             count = 0; ok = true;
+            if (pm >= 0 && lo[0] >= plo.x && lo[1] >= plo.y && lo[2] >= plo.z && hi[0] <= phi.x && hi[1] <= phi.y && hi[2] <= phi.z) {   // never true for the inverted "no list" box
+                unsigned int cfirst = 0u, clast = 0u; bool keep1 = false;
+                if (lane < pna) {
+                    const unsigned int node = adj1[(size_t)pm * 32 + lane];
+                    keep1 = boxes_meet(lo, hi, box[2 * (size_t)(b.offset[1] + node)], box[2 * (size_t)(b.offset[1] + node) + 1]);
+                    cfirst = child_start[b.coffset[1] + node]; clast = child_start[b.coffset[1] + node + 1];
+                }
+                unsigned int m1 = __ballot_sync(FULL, keep1);
+                while (m1 && ok) {
+                    const int src = __ffs((int)m1) - 1; m1 &= m1 - 1u;
+                    const unsigned int c = __shfl_sync(FULL, cfirst, src) + lane, last = __shfl_sync(FULL, clast, src);
+                    const bool keep = c < last && c != (unsigned int)l && boxes_meet(lo, hi, box[2 * (size_t)c], box[2 * (size_t)c + 1]);
+                    const unsigned int mk = __ballot_sync(FULL, keep);
+                    if (count + __popc(mk) > 32) { ok = false; break; }
+                    if (keep) list[count + __popc(mk & lt)] = c;
+                    count += __popc(mk);
+                }
+                __syncwarp();
+                if (ok) break;                                 // R stays the one this list was built with
+                continue;
+            }
             int top = 0;
             // virtual root over the top level, then depth-first; leaves are appended to the list
             for (unsigned int base = 0; base < (unsigned int)b.count[top_level] && ok; base += 32) {
@@ -838,14 +1000,17 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
     }
 }
 
+// level 1 first; the level-0 call then takes the level-1 lists (node_rank, adj1, adj1_box; nullable = walk from the root)
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
-                                      float4* adj_box, int capacity, int level, int n_sms, cudaStream_t s, int* n_launches) {
+                                      float4* adj_box, int capacity, int level, const unsigned int* node_rank, const unsigned int* adj1,
+                                      const float4* adj1_box, int adj1_capacity, int n_sms, cudaStream_t s, int* n_launches) {
     long long nb = ((long long)capacity + ADJ_WARPS - 1) / ADJ_WARPS;
     if (nb > 16ll * n_sms) nb = 16ll * n_sms;
     if (nb < 1) nb = 1;
     float r_factor = 2.0f;
     if (const char* e = getenv("ICP_GPU_ADJ_FACTOR")) r_factor = (float)atof(e);   // tuning knob
-    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_box, capacity, r_factor, level);
+    leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_box, capacity, r_factor, level,
+                                                             node_rank, adj1, adj1_box, adj1_capacity);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

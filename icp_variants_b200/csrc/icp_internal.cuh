@@ -40,8 +40,10 @@ struct GridParams {
     int bits[3];      // bits per axis, sum = T
     int T;            // depth of the implicit tree, 2^T cells
     unsigned long long axis_seq;  // 2 bits per level, level 0 (root split) in the low bits
-    int n_finite;     // points inserted (finite coordinates)
+    int n_finite;     // unused (the sort counts the non-finite points instead)
     int pad;
+    unsigned char bitpos[3][ICP_MAX_BITS_PER_AXIS];   // bit j of axis a's cell index is bit bitpos[a][j] of the cell code
+    unsigned char pad2[2];
 };
 
 // Bounding-volume hierarchy over the cell-sorted target (grid.cu), fan-out <= 32.  Every node of every level is
@@ -112,6 +114,8 @@ struct PeerBox {
 struct PeerXchg {
     int world, rank;                   // world <= 1: no exchange
     unsigned long long timeout_ns;     // a peer that does not show up raises ICP_GPU_E_PEER instead of hanging the GPU
+    int plan_check;                    // iterations + metric / minimiser this rank planned: element 31 of every row carries it, ranks that disagree raise ICP_GPU_E_PEER
+    int pad_;
     PeerBox* box[ICP_MAX_PEERS];       // box[j] = rank j's mailbox as mapped into this process (box[rank] = own)
 };
 
@@ -145,7 +149,8 @@ struct MatchArgs {
     float fx, fy, cx, cy; unsigned int width, height;
     // config
     int weighting, rejection, color_icp;
-    float max_d2;
+    float max_d2;            // the matcher's threshold
+    float weight_max_d2;     // WeightingMethod's maxDistance (the reference keeps the two apart, ICPOptimizer.h:41-44,71-78)
     // per-query state, indexed by p
     int* match_pos;          // position in tgt_pts order, -1 = none
     float* match_w;
@@ -156,6 +161,7 @@ struct MatchArgs {
     float4* qbuf;            // transformed query points of the current iteration {x,y,z,rgba}; x = NaN: not searched
     int desc_index;          // >= 0: fixed descriptor (query_matches); -1: use state->iter
     int use_seed;
+    int brute_norm;          // brute force on rounded Euclidean norms, max_d2 = a plain distance (NearestNeighborSearchBruteForce, NearestNeighbor.h:81-97)
     int proj_tiled;          // projective matching of a full-frame source: src arrays are in ORIGINAL (pixel) order, one 32x8 tile per block
     int fast_path;           // knn_prep_kernel answers the queries whose search ball stays inside their seed leaf's inflated box
     int collect_stats;       // work counters in DevState (atomics); off in timed runs
@@ -173,25 +179,28 @@ struct ReduceArgs {
     // fused = 1: stages 3-4 (selection predicate, weighting, rejection) are evaluated here from the search result nn_pos
     // instead of being read back from the match records (saves the match_finish launch); linear minimiser only
     int fused; const int* nn_pos; int n_tgt; const unsigned int* mask; const IterDesc* desc; int desc_index;
-    int weighting, rejection; float max_d2;
+    int weighting, rejection; float max_d2, weight_max_d2;
     int profile;             // write DevState::prof (diagnostic, ICP_GPU_REDUCE_PROFILE=1)
     PeerXchg peer;           // world > 1: the summed row is all-reduced over the peers' mailboxes before the solve
 };
 
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
-// AoS3 -> float4 records and the bounding box of the finite points (bbox: 8 words, [7] becomes the non-finite count of the sort)
+// AoS3 -> float4 records, the bounding box of the finite points and from it the grid parameters; clears the sort's histograms
+// (scratch: 8 words, [7] = number of points with a non-finite coordinate afterwards)
 cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
-                                  unsigned int* bbox, cudaStream_t s);
+                                  unsigned int* scratch, int T, GridParams* grid, unsigned int* hist, long long hist_words, int with_normals, cudaStream_t s);
 // Stable LSD radix sort of a packed cloud into (cell code, original index) order; points with a non-finite coordinate end up
 // after the last cell.  T + 1 key bits in passes of <= 11 bits.
-struct IcpRadixPlan { int n_pass; int shift[3]; int bits[3]; int tile_items; int n_tiles; };
+// normal / colour records packed late (before the last pass of the sort), once `ready` has happened: host uploads
+struct IcpLatePack { const float* nrm; const uint8_t* rgba; float4* nrmo; cudaEvent_t ready; };
+struct IcpRadixPlan { int n_pass; int shift[3]; int bits[3]; int ipt; int tile_items; int n_tiles; int tiles_pad; };
 void icp_radix_plan(int n, int T, IcpRadixPlan* p);
 size_t icp_radix_hist_words(int n, int T);
 #define ICP_MSD_WORDS 2049
-cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, GridParams* grid, unsigned int* bbox,
+cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, const GridParams* grid,
                                   unsigned int* keys_a, unsigned int* keys_b, unsigned int* idx_a, unsigned int* idx_b,
-                                  unsigned int* tile_hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
-                                  unsigned int** keys_sorted_out, int* msd_shift_out, cudaStream_t s, int* n_launches);
+                                  unsigned int* hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
+                                  unsigned int** keys_sorted_out, int* msd_shift_out, const IcpLatePack* late, cudaStream_t s, int* n_launches);
 // Tight-box BVH over the sorted cloud, read off the common-prefix lengths of neighbouring sorted keys.
 size_t icp_bvh_max_nodes(int n);
 cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, int T, const unsigned int* keys,
@@ -201,9 +210,11 @@ cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sor
 // One voxel pyramid level (depth D of the source grid) as a selection mask; table: scratch of 2^D entries.
 cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_sorted, int n, const GridParams* grid, int T, int D,
                                    unsigned int* table, unsigned int* mask, size_t mask_words, cudaStream_t s, int* n_launches);
-// Leaf adjacency lists for the leaves [0, min(n_leaves, capacity)).
+// Adjacency lists of the nodes [0, min(count[level], capacity)) of `level` (0 leaves, 1 their parents).  The level-0 call can take
+// the level-1 lists (node_rank, adj1, adj1_box; nullable = every query walks from the root).
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
-                                      float4* adj_box, int capacity, int level, int n_sms, cudaStream_t s, int* n_launches);
+                                      float4* adj_box, int capacity, int level, const unsigned int* node_rank, const unsigned int* adj1,
+                                      const float4* adj1_box, int adj1_capacity, int n_sms, cudaStream_t s, int* n_launches);
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // Seeds (nn_pos / nn_leaf) for the queries that have none (reset: for every query), from the target's sorted keys at the pose in `st`.
@@ -303,7 +314,8 @@ __device__ __forceinline__ bool query_active(const IterDesc& d, const unsigned i
 
 // Stages 3-4 for one matched pair: WeightingMethod::applyWeights (weighting.h:39-99) and
 // ICPOptimizer::pruneCorrespondences (ICPOptimizer.h:157-174).  w comes in as the matcher's weight (1, or 0 for the
-// projective matcher's skipped queries) and leaves as the match weight; returns false when the pair is rejected.
+// projective matcher's skipped queries) and leaves as the match weight; returns false when the pair is rejected.  max_d2 is
+// WeightingMethod's maxDistance (weighting.h:33-37), not the matcher's threshold.
 // (sx,sy,sz) / (snx,sny,snz): transformed source point / normal; tp / tn: target point {x,y,z,_} / normal {x,y,z,rgba}.
 __device__ __forceinline__ bool match_weight_and_reject(int weighting, int rejection, float max_d2, float sx, float sy, float sz,
                                                         float snx, float sny, float snz, unsigned int s_rgba, const float4 tp,
@@ -437,33 +449,52 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // there, added in rank order on every rank (=> bit-identical rows, identical solves, identical poses: no broadcast).
 // Warp j (j < world, j != rank) serves peer j: it pushes the local row into rank j's mailbox (remote stores, then a
 // system-scope fence and a release store of the exchange number) and then polls its own mailbox for rank j's row.
+// A rank whose peer did not show up in time (ICP_GPU_E_PEER) POISONS the exchange: it stores ICP_PEER_POISON into its flag
+// words of every peer's mailbox (both slots), so that the peers fail in their current or next exchange instead of finishing
+// with sums built from a stale row, and it skips every later exchange of the registration -- a lost peer costs one time-out
+// per registration, not one per launch.  The mailboxes stay poisoned until they are exported and attached again.
+#define ICP_PEER_POISON 0xFFFFFFFFu
 template <int THREADS>
 __device__ __forceinline__ void peer_exchange_row(const PeerXchg& px, DevState* st, double (*red)[32], double (*fin)[32]) {
     static_assert(THREADS / 32 >= ICP_MAX_PEERS, "one warp per peer");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) s_failed = (*reinterpret_cast<volatile int*>(&st->status) == ICP_GPU_E_PEER) ? 1 : 0;
+    __syncthreads();
+    const bool failed_before = s_failed != 0;
     const unsigned int seq = st->xchg_seq + 1u;     // written back by thread 0 after the last read below
     const int slot = (int)(seq & 1u);
-    bool timed_out = false;
-    if (w < px.world) {
+    bool lost = false;
+    if (!failed_before && w < px.world) {
         if (w != px.rank) {
             PeerBox* theirs = px.box[w];
-            theirs->row[slot][px.rank][lane] = fin[0][lane];
+            theirs->row[slot][px.rank][lane] = lane == 31 ? (double)px.plan_check : fin[0][lane];   // element 31 is no sum: the plan check
             __threadfence_system();
             __syncwarp();
             if (lane == 0) st_release_sys_u32(&theirs->flag[slot][px.rank], seq);
             const PeerBox* mine = px.box[px.rank];
             const unsigned long long t0 = global_timer_ns();
-            while (ld_acquire_sys_u32(&mine->flag[slot][w]) != seq) {
-                if (global_timer_ns() - t0 > px.timeout_ns) { timed_out = true; break; }
+            for (;;) {
+                const unsigned int f = ld_acquire_sys_u32(&mine->flag[slot][w]);
+                if (f == seq) break;
+                if (f == ICP_PEER_POISON || global_timer_ns() - t0 > px.timeout_ns) { lost = true; break; }
                 __nanosleep(64);
             }
             red[w][lane] = ld_relaxed_sys_f64(&mine->row[slot][w][lane]);
         } else {
-            red[w][lane] = fin[0][lane];
+            red[w][lane] = lane == 31 ? (double)px.plan_check : fin[0][lane];
         }
     }
-    if (timed_out && lane == 0) atomicCAS(&st->status, 0, ICP_GPU_E_PEER);
+    // every rank must have planned the same registration (iterations, metric, minimiser): a rank with another plan would leave
+    // the others waiting for exchanges that never come
+    if (!failed_before && !lost && w < px.world && lane == 31 && red[w][31] != (double)px.plan_check) lost = true;
+    if (lost && (lane == 0 || lane == 31)) { atomicCAS(&st->status, 0, ICP_GPU_E_PEER); s_failed = 1; }
     __syncthreads();
+    if (s_failed) {
+        // tell every peer (whatever exchange it is in, or enters next); the totals of this exchange are not used: the status is set
+        if (w < px.world && w != px.rank && lane < 2) st_release_sys_u32(&px.box[w]->flag[lane][px.rank], ICP_PEER_POISON);
+        if (failed_before) return;
+    }
     if (threadIdx.x < 32) {
         double s = 0.0;
         for (int j = 0; j < px.world; ++j) s += red[j][threadIdx.x];

@@ -106,7 +106,7 @@ __device__ __forceinline__ void finish_match(const MatchArgs& a, int p, bool mat
         float4 tp = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.weighting != ICP_GPU_WEIGHT_CONSTANT) tp = __ldg(&a.tgt_pts[t_pos]);
         w = w_const;
-        if (match_weight_and_reject(a.weighting, a.rejection, a.max_d2, sx, sy, sz, snx, sny, snz, s_rgba, tp, tn, w)) {
+        if (match_weight_and_reject(a.weighting, a.rejection, a.weight_max_d2, sx, sy, sz, snx, sny, snz, s_rgba, tp, tn, w)) {
             out_idx = t_idx; out_pos = t_pos; ++n_matched;
         }
     }
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) match_finish_kernel(const MatchArgs a) {
 
 // Small targets: one warp per query, lanes stride over the target (original order, L1-resident),
 // warp-shuffle arg-min on (d, idx).
-template <bool COLOR>
+template <bool COLOR, bool NORM>
 __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     load_pose(sm, a.state_ro);
@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
             if (finite3(q.x, q.y, q.z)) {
                 for (int j = lane; j < a.n_tgt; j += 32) {
                     const float4 c = __ldg(&a.tgt_pts[j]);
-                    const float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, (unsigned int)j);
+                    float dd = dist2<COLOR>(q, c, b.d, a.tgt_nrm, (unsigned int)j);
+                    if (NORM) dd = __fsqrt_rn(dist3(q, c));                  // (p - m).norm(), NearestNeighbor.h:86
                     if (better(dd, j, b)) { b.d = dd; b.idx = j; b.pos = j; }
                 }
                 ev += (unsigned int)((a.n_tgt - lane + 31) / 32);
@@ -713,7 +714,9 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
     } else if (algorithm == 1) {
         const long long threads = (long long)a.n_src * 32;
         const int nb = (int)((threads + T - 1) / T);
-        if (a.color_icp) knn_brute_kernel<true><<<nb, T, 0, s>>>(a); else knn_brute_kernel<false><<<nb, T, 0, s>>>(a);
+        if (a.color_icp) knn_brute_kernel<true, false><<<nb, T, 0, s>>>(a);
+        else if (a.brute_norm) knn_brute_kernel<false, true><<<nb, T, 0, s>>>(a);
+        else knn_brute_kernel<false, false><<<nb, T, 0, s>>>(a);
         ++launches;
     } else {
         const int np = (a.n_src + 255) / 256;

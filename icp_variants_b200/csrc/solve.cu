@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
             float nx, ny, nz;
             xform_normal(Nm, sn4.x, sn4.y, sn4.z, nx, ny, nz);
             wf = 1.0f;
-            if (!match_weight_and_reject(a.weighting, a.rejection, a.max_d2, sxf, syf, szf, nx, ny, nz, __float_as_uint(sn4.w), tp, tn, wf)) continue;
+            if (!match_weight_and_reject(a.weighting, a.rejection, a.weight_max_d2, sxf, syf, szf, nx, ny, nz, __float_as_uint(sn4.w), tp, tn, wf)) continue;
         } else {
             xform_point(P, sp.x, sp.y, sp.z, sxf, syf, szf);
         }

@@ -119,8 +119,8 @@ class NearestNeighborSearchFlann(NearestNeighborSearch):
 
 
 class NearestNeighborSearchBruteForce(NearestNeighborSearch):
-    """NearestNeighbor.h:42-98 (scan order / tie rule); on squared distances like the FLANN class."""
-    _nn_algorithm = 1
+    """NearestNeighbor.h:42-98 as written: candidates compared on the rounded norm, m_maxDistance taken as a plain distance (:93)."""
+    _nn_algorithm = 3
 
 
 class NearestNeighborSearchProjective(NearestNeighborSearch):
@@ -137,6 +137,10 @@ class ICPOptimizer:
         # constructor defaults, ICPOptimizer.h:29-31
         self.metric, self.selectionMethod, self.rejectionMethod, self.weightingMethod = 0, SELECT_ALL, 1, CONSTANT_WEIGHTING
         self.m_nIterations, self.matchingMethod, self.maxDistance = 20, 0, 0.0003
+        # The reference keeps two distances apart: the matcher's own threshold (NearestNeighborSearch::m_maxDistance, MAX_DISTANCE
+        # until setMatchingMaxDistance, and again after every setMatchingMethod, which re-creates the matcher, ICPOptimizer.h:71-78)
+        # and ICPOptimizer::maxDistance (0.0003 until setMatchingMaxDistance), which only WeightingMethod sees (:220,:528).
+        self.matcherMaxDistance = MAX_DISTANCE
         self.colorICP, self.multiResolutionICP = False, False
         self.proba = 1.0
         self.seed = 0                 # the reference seeds from std::random_device (selection.h:76-79)
@@ -150,7 +154,8 @@ class ICPOptimizer:
         self.last_error: str | None = None
 
     def setMatchingMaxDistance(self, maxDistance):
-        self.maxDistance = float(maxDistance)
+        self.matcherMaxDistance = float(maxDistance)      # m_nearestNeighborSearch->setMatchingMaxDistance, ICPOptimizer.h:42
+        self.maxDistance = float(maxDistance)             # :43
 
     def setMetric(self, metric):
         self.metric = int(metric)
@@ -173,7 +178,7 @@ class ICPOptimizer:
     def setMatchingMethod(self, matchingMethod):
         # ICPOptimizer.h:71-78 re-creates the matcher, which resets its max distance to MAX_DISTANCE
         self.matchingMethod = int(matchingMethod)
-        self.maxDistance = MAX_DISTANCE
+        self.matcherMaxDistance = MAX_DISTANCE            # the weighting distance keeps its value
 
     def setCameraParamsMatchingMethod(self, depthIntrinsics, width, height):
         self._camera = (np.asarray(depthIntrinsics, np.float32), int(width), int(height))
@@ -191,7 +196,8 @@ class ICPOptimizer:
         c = capi.default_config()
         c.metric, c.minimizer, c.matching = self.metric, self._minimizer, self.matchingMethod
         c.selection, c.proba, c.seed, c.selection_rng = self.selectionMethod, self.proba, self.seed & 0xFFFFFFFF, self.selection_rng
-        c.weighting, c.rejection, c.max_distance_sq = self.weightingMethod, self.rejectionMethod, self.maxDistance
+        c.weighting, c.rejection, c.max_distance_sq = self.weightingMethod, self.rejectionMethod, self.matcherMaxDistance
+        c.weight_max_distance_sq = self.maxDistance
         c.color_icp, c.multires, c.n_iterations = int(self.colorICP), int(self.multiResolutionICP), self.m_nIterations
         c.nn_algorithm, c.use_graph, c.pyramid_mode = self.nn_algorithm, int(self.use_graph), self.pyramid_mode
         return c

@@ -25,12 +25,14 @@ public:
     ICPOptimizer()
         : metric{0}, colorICP{false}, multiResolutionICP{false}, selectionMethod{0}, proba{1.0}, rejectionMethod{1}, weightingMethod{0},
           matchingMethod{0}, m_nIterations{20}, m_timeMeasure{nullptr}, m_convergenceMeasure{nullptr}, maxDistance{0.0003f},
+          m_matcherMaxDistance{MAX_DISTANCE},
           m_ctx{nullptr}, m_haveCamera{false}, m_seed{0}, m_selectionRng{ICP_GPU_RNG_MT19937}, m_width{0}, m_height{0}, m_pyramidMode{ICP_GPU_PYRAMID_STRIDE} {
         if (icp_gpu_create(&m_ctx, 0) != ICP_GPU_OK) { m_ctx = nullptr; std::cout << "icp_gpu: no usable CUDA device (there is no CPU fallback)." << std::endl; }
     }
     virtual ~ICPOptimizer() { if (m_ctx) icp_gpu_destroy(m_ctx); }
 
-    void setMatchingMaxDistance(float maxDistance) { this->maxDistance = maxDistance; }
+    // ICPOptimizer.h:41-44: the matcher's threshold AND the distance WeightingMethod divides by
+    void setMatchingMaxDistance(float maxDistance) { m_matcherMaxDistance = maxDistance; this->maxDistance = maxDistance; }
     void setMetric(unsigned int metric) { this->metric = metric; }
     void enableMultiResolution(bool enableMultiResolution) { this->multiResolutionICP = enableMultiResolution; }
     // extension: ICP_GPU_PYRAMID_VOXEL builds the levels by voxel downsampling instead of the reference's index stride
@@ -41,7 +43,7 @@ public:
     void setWeightingMethod(unsigned int weightingMethod) { this->weightingMethod = weightingMethod; }
     void setMatchingMethod(unsigned int matchingMethod) {
         this->matchingMethod = matchingMethod;
-        this->maxDistance = MAX_DISTANCE;   // ICPOptimizer.h:71-78 re-creates the matcher with its default distance
+        m_matcherMaxDistance = MAX_DISTANCE;   // ICPOptimizer.h:71-78 re-creates the matcher: ITS distance is back at the default, maxDistance is not touched
     }
     void setCameraParamsMatchingMethod(const Eigen::Matrix3f& depthIntrinsics, const unsigned width, const unsigned height) {
         m_K = depthIntrinsics; m_width = width; m_height = height; m_haveCamera = true;
@@ -84,7 +86,8 @@ protected:
     unsigned m_nIterations;
     TimeMeasure* m_timeMeasure;
     ConvergenceMeasure* m_convergenceMeasure;
-    float maxDistance;   // squared distance
+    float maxDistance;   // squared distance: what WeightingMethod is constructed with (ICPOptimizer.h:220,528); default 0.0003f
+    float m_matcherMaxDistance;   // NearestNeighborSearch::m_maxDistance of the matcher the reference owns (NearestNeighbor.h:17-19,35)
     icp_gpu_ctx* m_ctx;
     Eigen::Matrix3f m_K; bool m_haveCamera; unsigned m_seed; int m_selectionRng; unsigned m_width, m_height; int m_pyramidMode;
 
@@ -95,7 +98,8 @@ protected:
         icp_gpu_config cfg; icp_gpu_default_config(&cfg);
         cfg.metric = (int32_t)metric; cfg.minimizer = minimizer; cfg.matching = (int32_t)matchingMethod;
         cfg.selection = (int32_t)selectionMethod; cfg.proba = proba; cfg.seed = m_seed; cfg.selection_rng = m_selectionRng;
-        cfg.weighting = (int32_t)weightingMethod; cfg.rejection = (int32_t)rejectionMethod; cfg.max_distance_sq = maxDistance;
+        cfg.weighting = (int32_t)weightingMethod; cfg.rejection = (int32_t)rejectionMethod;
+        cfg.max_distance_sq = m_matcherMaxDistance; cfg.weight_max_distance_sq = maxDistance;
         cfg.color_icp = colorICP ? 1 : 0; cfg.multires = multiResolutionICP ? 1 : 0; cfg.n_iterations = (int32_t)m_nIterations; cfg.pyramid_mode = m_pyramidMode;
         int rc = icp_gpu_set_config(m_ctx, &cfg);
         if (rc == ICP_GPU_OK && m_haveCamera) rc = icp_gpu_set_camera(m_ctx, m_K.data(), m_width, m_height);
@@ -111,10 +115,10 @@ protected:
         if (rc != ICP_GPU_OK) { std::cout << "icp_gpu: " << icp_gpu_last_error(m_ctx) << std::endl; return; }
         const int cap = icp_gpu_max_iterations(m_ctx);
         std::vector<float> history((size_t)(cap > 0 ? cap : 1) * 16);
-        int32_t nIt = 0; icp_gpu_timings tm;
+        int32_t nIt = 0; icp_gpu_timings tm = {};
         rc = icp_gpu_estimate_pose(m_ctx, initialPose.data(), history.data(), &nIt, m_timeMeasure ? &tm : nullptr);
         if (rc != ICP_GPU_OK) std::cout << "icp_gpu: " << icp_gpu_last_error(m_ctx) << " -- pose left at the last good estimate" << std::endl;
-        if (m_timeMeasure) {
+        if (m_timeMeasure && rc == ICP_GPU_OK) {
             m_timeMeasure->matchingTime += tm.matching_ms * 1e-3; m_timeMeasure->solverTime += tm.solver_ms * 1e-3;
             m_timeMeasure->convergenceTime += tm.total_ms * 1e-3; m_timeMeasure->indexTime += tm.index_ms * 1e-3;
         }

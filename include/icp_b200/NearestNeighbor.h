@@ -81,7 +81,8 @@ protected:
 
 class NearestNeighborSearchBruteForce : public NearestNeighborSearch {
 public:
-    NearestNeighborSearchBruteForce() : NearestNeighborSearch(ICP_GPU_MATCH_KNN, ICP_GPU_NN_BRUTE) {}
+    // NearestNeighbor.h:81-97 compares (p - m).norm() with m_maxDistance: a plain distance, not a squared one -- ICP_GPU_NN_BRUTE_NORM
+    NearestNeighborSearchBruteForce() : NearestNeighborSearch(ICP_GPU_MATCH_KNN, ICP_GPU_NN_BRUTE_NORM) {}
 };
 
 class NearestNeighborSearchFlann : public NearestNeighborSearch {

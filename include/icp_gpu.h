@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ICP_GPU_ABI_VERSION 3
+#define ICP_GPU_ABI_VERSION 4
 
 enum {
     ICP_GPU_OK = 0,
@@ -58,7 +58,12 @@ enum { ICP_GPU_WEIGHT_CONSTANT = 0, ICP_GPU_WEIGHT_DISTANCES = 1, ICP_GPU_WEIGHT
 /* Nearest-neighbour kernel choice (both exact, same answers): AUTO = by target size; BRUTE = one warp per
  * query over the whole target; GRID = one warp per query over a tight-box 32-ary BVH built on the target
  * sorted into the cell (Morton) order of a uniform grid                                               */
-enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2 };
+enum { ICP_GPU_NN_AUTO = 0, ICP_GPU_NN_BRUTE = 1, ICP_GPU_NN_GRID = 2,
+       /* NearestNeighborSearchBruteForce's own rule (NearestNeighbor.h:81-97; 3-D only): candidates are compared on the
+        * Euclidean NORM (p - m).norm() = sqrt of the D1 squared distance, rounded to fp32 -- ties are ties of the rounded
+        * norms, lowest index first -- and max_distance_sq is taken as a plain distance (the reference compares the norm with
+        * m_maxDistance, :93).  The optimizers never use this class; it exists for the reference's matcher API. */
+       ICP_GPU_NN_BRUTE_NORM = 3 };
 /* Random selection stream: 0 = std::mt19937 + uniform_real_distribution<double> drawn on the host
  * exactly as selection.h:88-104 does (reference-compatible for a given seed); 1 = counter-based
  * hash drawn on the device (fast, not reference-compatible).                                      */
@@ -80,7 +85,9 @@ typedef struct icp_gpu_config {
     int32_t  selection_rng;     /* ICP_GPU_RNG_*                                                    */
     int32_t  weighting;         /* setWeightingMethod        default constant                        */
     int32_t  rejection;         /* setRejectionMethod        default 1 = on (ICPOptimizer.h:30)      */
-    float    max_distance_sq;   /* setMatchingMaxDistance, SQUARED metres, default 0.0003 (:31)      */
+    float    max_distance_sq;   /* the matcher's threshold NearestNeighborSearch::m_maxDistance, SQUARED metres
+                                   (NearestNeighbor.h:17-19,35; valid iff d2 <= it, :182).  Default 0.0003 = what
+                                   setMatchingMaxDistance(0.0003f) leaves in both members (ICPOptimizer.h:41-44)   */
     int32_t  color_icp;         /* enableColorICP            default off                             */
     int32_t  multires;          /* enableMultiResolution     default off                             */
     int32_t  pyramid_mode;      /* ICP_GPU_PYRAMID_*                                                */
@@ -90,6 +97,11 @@ typedef struct icp_gpu_config {
     int32_t  use_graph;         /* 1 (default): replay the iteration loop as one CUDA graph          */
     int32_t  collect_stats;     /* 1 (default): fill icp_gpu_stats' work counters (device atomics);
                                    0: fastest, icp_gpu_get_stats then only reports kernel launches   */
+    float    weight_max_distance_sq; /* ICPOptimizer::maxDistance as handed to WeightingMethod (ICPOptimizer.h:220,528;
+                                   weighting.h:16-20,33-37): the divisor of the distance / colour weights.  The reference keeps
+                                   it apart from the matcher's threshold: setMatchingMethod re-creates the matcher with
+                                   MAX_DISTANCE = 0.005 (ICPOptimizer.h:71-78, NearestNeighbor.h:5) and leaves this one alone;
+                                   only setMatchingMaxDistance sets both.  0 (default) = max_distance_sq               */
 } icp_gpu_config;
 
 /* Per-stage device times of the last icp_gpu_estimate_pose call made with timings != NULL

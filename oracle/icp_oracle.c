@@ -140,6 +140,21 @@ void orc_knn3_brute(const float* tgt, int64_t nt, const float* qry, int64_t nq, 
     }
 }
 
+/* NearestNeighborSearchBruteForce::getClosestPoint as written (NearestNeighbor.h:81-97): candidates compared on the rounded
+ * Euclidean norm (strict '>' => lowest index among equal norms), the norm compared with m_maxDistance (:93). */
+void orc_knn3_brute_norm(const float* tgt, int64_t nt, const float* qry, int64_t nq, float max_d, orc_match* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nq; ++i) {
+        float best = FLT_MAX; int32_t bi = -1;
+        for (int64_t j = 0; j < nt; ++j) {
+            const float d = sqrtf(d2_3(qry + 3 * i, tgt + 3 * j));
+            if (best > d) { best = d; bi = (int32_t)j; }
+        }
+        if (best <= max_d) { out[i].idx = bi; out[i].weight = 1.f; }
+        else { out[i].idx = -1; out[i].weight = 0.f; }
+    }
+}
+
 void orc_knn6_brute(const float* tgt, const uint8_t* tc, int64_t nt, const float* qry, const uint8_t* qc, int64_t nq,
                     float max_d2, orc_match* out) {
     float* tf = (float*)malloc(sizeof(float) * 6 * (size_t)(nt > 0 ? nt : 1));
@@ -922,7 +937,8 @@ int orc_match_pipeline(const orc_config* cfg, const float pose[16],
         else orc_knn3_brute(tgt, n_tgt, tp, n_sel, cfg->max_distance_sq, out);
     }
     if (rc == 0) {
-        orc_apply_weights(cfg->weighting, cfg->max_distance_sq, tp, tgt, tn, tgt_n, sc, tgt_c, n_sel, out); /* :571-572 */
+        orc_apply_weights(cfg->weighting, cfg->weight_max_distance_sq > 0.f ? cfg->weight_max_distance_sq : cfg->max_distance_sq,
+                          tp, tgt, tn, tgt_n, sc, tgt_c, n_sel, out); /* :571-572; WeightingMethod(weightingMethod, maxDistance) :528 */
         if (cfg->rejection == 1) orc_prune(tn, tgt_n, n_sel, out);                                        /* :578-579 */
     }
     if (tp_out) memcpy(tp_out, tp, sizeof(float) * 3 * (size_t)n_sel);

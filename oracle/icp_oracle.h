@@ -45,7 +45,7 @@ typedef struct {
     uint32_t seed;           /* reference seeds from random_device (selection.h:76-79); explicit here */
     int32_t weighting;       /* setWeightingMethod                 (ICPOptimizer.h:67)  */
     int32_t rejection;       /* setRejectionMethod, default 1      (ICPOptimizer.h:30)  */
-    float   max_distance_sq; /* setMatchingMaxDistance, squared    (ICPOptimizer.h:41)  */
+    float   max_distance_sq; /* the matcher's m_maxDistance, squared (NearestNeighbor.h:17-19); setMatchingMaxDistance (ICPOptimizer.h:41) sets it */
     int32_t color_icp;       /* enableColorICP                     (ICPOptimizer.h:54)  */
     int32_t multires;        /* enableMultiResolution              (ICPOptimizer.h:50)  */
     int32_t n_iterations;    /* setNbOfIterations                  (ICPOptimizer.h:84)  */
@@ -55,6 +55,8 @@ typedef struct {
     int32_t lm_max_iterations; /* Ceres options.max_num_iterations = 10 (ICPOptimizer.h:358) */
     int32_t pyramid_mode;    /* 0 = the reference's stride pyramid (PointCloud.h:325-343); 1 = voxel levels (extension of
                                 this repository, include/icp_gpu.h ICP_GPU_PYRAMID_VOXEL; not reference behaviour) */
+    float   weight_max_distance_sq; /* ICPOptimizer::maxDistance as handed to WeightingMethod (ICPOptimizer.h:220,528): kept apart from the
+                                matcher's threshold by the reference (setMatchingMethod resets only the matcher, :71-78); 0 = max_distance_sq */
 } orc_config;
 
 void orc_default_config(orc_config* c);
@@ -65,6 +67,8 @@ void orc_transform_normals(const float pose[16], const float* nrm, int64_t n, fl
 
 /* NearestNeighbor.h:81-97 tie rule + :181-186 threshold; exact 1-NN, lowest index on ties. */
 void orc_knn3_brute(const float* tgt, int64_t nt, const float* qry, int64_t nq, float max_d2, orc_match* out);
+/* NearestNeighborSearchBruteForce as written: compared and thresholded on the rounded norm (NearestNeighbor.h:81-97) */
+void orc_knn3_brute_norm(const float* tgt, int64_t nt, const float* qry, int64_t nq, float max_d, orc_match* out);
 void orc_knn6_brute(const float* tgt, const uint8_t* tgt_rgba, int64_t nt,
                     const float* qry, const uint8_t* qry_rgba, int64_t nq, float max_d2, orc_match* out);
 /* Same answers as the brute-force versions, via an exact kd-tree (dim 3 or 6). */

@@ -30,7 +30,7 @@ class _Config(C.Structure):
                 ("max_distance_sq", C.c_float), ("color_icp", C.c_int32), ("multires", C.c_int32),
                 ("n_iterations", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("nn_mode", C.c_int32), ("lm_max_iterations", C.c_int32),
-                ("pyramid_mode", C.c_int32)]
+                ("pyramid_mode", C.c_int32), ("weight_max_distance_sq", C.c_float)]
 
 
 MATCH_DTYPE = np.dtype([("idx", np.int32), ("weight", np.float32)])
@@ -75,12 +75,13 @@ class Config:
     nn_mode: int = 1            # 0 brute force, 1 exact kd-tree (same answers)
     lm_max_iterations: int = 10
     pyramid_mode: int = 0       # 0 stride pyramid (reference), 1 voxel levels (extension)
+    weight_max_distance_sq: float = 0.0   # WeightingMethod's maxDistance when it differs from the matcher's (0 = the same)
 
     def c(self) -> _Config:
         return _Config(self.metric, self.minimizer, self.matching, self.selection, float(self.proba), self.seed & 0xFFFFFFFF,
                        self.weighting, self.rejection, float(self.max_distance_sq), int(self.color_icp), int(self.multires),
                        self.n_iterations, self.fx, self.fy, self.cx, self.cy, self.width, self.height, self.nn_mode,
-                       self.lm_max_iterations, self.pyramid_mode)
+                       self.lm_max_iterations, self.pyramid_mode, float(self.weight_max_distance_sq))
 
 
 def _f32(a, cols=3):
@@ -132,6 +133,14 @@ def knn_brute(tgt, qry, max_d2, tgt_rgba=None, qry_rgba=None):
     else:
         tc, qc = _u8(tgt_rgba), _u8(qry_rgba)
         lib().orc_knn6_brute(_p(tgt), _p(tc), C.c_int64(len(tgt)), _p(qry), _p(qc), C.c_int64(len(qry)), C.c_float(max_d2), _p(out))
+    return out
+
+
+def knn_brute_norm(tgt, qry, max_d):
+    """NearestNeighborSearchBruteForce::getClosestPoint as written: rounded norms, a plain distance threshold."""
+    tgt, qry = _f32(tgt), _f32(qry)
+    out = np.empty(len(qry), MATCH_DTYPE)
+    lib().orc_knn3_brute_norm(_p(tgt), C.c_int64(len(tgt)), _p(qry), C.c_int64(len(qry)), C.c_float(max_d), _p(out))
     return out
 
 

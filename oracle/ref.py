@@ -35,7 +35,7 @@ class _Config(C.Structure):
     _fields_ = [("minimizer", C.c_int32), ("metric", C.c_int32), ("selection", C.c_int32), ("weighting", C.c_int32),
                 ("rejection", C.c_int32), ("matching", C.c_int32), ("color_icp", C.c_int32), ("multires", C.c_int32),
                 ("n_iterations", C.c_int32), ("proba", C.c_double), ("seed", C.c_uint32), ("max_distance_sq", C.c_float),
-                ("K", C.c_float * 9), ("width", C.c_uint32), ("height", C.c_uint32)]
+                ("K", C.c_float * 9), ("width", C.c_uint32), ("height", C.c_uint32), ("setter_order", C.c_int32)]
 
 
 _lib = None
@@ -209,8 +209,10 @@ def cloud_from_xyz(pts):
 
 def estimate_pose(minimizer, metric, src, src_n, src_c, tgt, tgt_n, tgt_c, gt_src, gt_ref, *, n_iterations=20, max_distance_sq=0.0003,
                   selection=0, proba=1.0, seed=0, weighting=0, rejection=1, matching=0, color_icp=False, multires=False,
-                  camera=None, init_pose=None):
-    """Runs the reference's {Linear,Ceres}ICPOptimizer::estimatePose.  Returns (n_iterations_executed | -2, pose, rmse history)."""
+                  camera=None, init_pose=None, setter_order=0):
+    """Runs the reference's {Linear,Ceres}ICPOptimizer::estimatePose.  Returns (n_iterations_executed | -2, pose, rmse history).
+    setter_order: 0 = setMatchingMethod then setMatchingMaxDistance (main.cpp); 1 = the other way round (the matcher falls back to
+    MAX_DISTANCE, only the weighting keeps max_distance_sq); 2 = setMatchingMaxDistance never called."""
     src, src_n, tgt, tgt_n = _f32(src), _f32(src_n), _f32(tgt), _f32(tgt_n)
     src_c, tgt_c = _u8(src_c), _u8(tgt_c)
     gt_src, gt_ref = _f32(gt_src), _f32(gt_ref)
@@ -221,6 +223,7 @@ def estimate_pose(minimizer, metric, src, src_n, src_c, tgt, tgt_n, tgt_c, gt_sr
         for i, v in enumerate(_K9(fx, fy, cx, cy)):
             cfg.K[i] = float(v)
         cfg.width, cfg.height = width, height
+    cfg.setter_order = int(setter_order)
     pose = _pose(np.eye(4, dtype=np.float32) if init_pose is None else init_pose).copy()
     cap = n_iterations + 128
     hist = np.zeros(cap, np.float32)

@@ -111,6 +111,9 @@ typedef struct {
     float max_distance_sq;
     float K[9];              // column-major 3x3 (Eigen Matrix3f storage), projective only
     uint32_t width, height;
+    int32_t setter_order;    // 0: setMatchingMethod, then setMatchingMaxDistance (main.cpp's order: both distances = max_distance_sq);
+                             // 1: setMatchingMaxDistance first -- setMatchingMethod then re-creates the matcher with MAX_DISTANCE and only
+                             //    WeightingMethod keeps max_distance_sq; 2: setMatchingMaxDistance never called (0.005 / 0.0003)
 } ref_config;
 
 // utils.h:106-118 / :122-133
@@ -247,10 +250,11 @@ int ref_estimate_pose(const ref_config* cfg,
         g_ref_seed = cfg->seed;
         std::unique_ptr<ICPOptimizer> opt;
         if (cfg->minimizer == 0) opt.reset(new LinearICPOptimizer()); else opt.reset(new CeresICPOptimizer());
-        opt->setMatchingMethod((unsigned)cfg->matching);   // before setMatchingMaxDistance: it replaces the matcher (ICPOptimizer.h:71-78)
+        if (cfg->setter_order == 1) opt->setMatchingMaxDistance(cfg->max_distance_sq);
+        opt->setMatchingMethod((unsigned)cfg->matching);   // replaces the matcher (ICPOptimizer.h:71-78)
         opt->setMetric((unsigned)cfg->metric);
         opt->setNbOfIterations((unsigned)cfg->n_iterations);
-        opt->setMatchingMaxDistance(cfg->max_distance_sq);
+        if (cfg->setter_order == 0) opt->setMatchingMaxDistance(cfg->max_distance_sq);
         opt->setSelectionMethod((unsigned)cfg->selection, cfg->proba);
         opt->setRejectionMethod((unsigned)cfg->rejection);
         opt->setWeightingMethod((unsigned)cfg->weighting);

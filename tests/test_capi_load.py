@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_default_config(lib):
-    assert lib.icp_gpu_abi_version() == 3
+    assert lib.icp_gpu_abi_version() == 4
     c = capi.default_config()
     # ICPOptimizer constructor defaults, ICPOptimizer.h:29-31
     assert (c.metric, c.selection, c.rejection, c.weighting, c.n_iterations, c.matching) == (0, 0, 1, 0, 20, 0)

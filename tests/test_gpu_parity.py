@@ -7,6 +7,8 @@ Protocol:
   (ii) free-running: the pose after the fixed iteration count must agree with the oracle's within
        ROT_TOL rad / TRANS_TOL m (north_star: 1e-5 / 1e-5).
 """
+import time
+
 import numpy as np
 import pytest
 
@@ -499,6 +501,61 @@ def test_peer_memory_missing_peer_times_out_with_an_error(bunny, monkeypatch):
         assert e.value.code == capi.E_PEER
         with pytest.raises(capi.IcpGpuError):             # the NCCL-style split iteration is refused while peers are attached
             ctxs[1].iteration_begin(np.eye(4, dtype=np.float32))
+        # The rank that gave up poisoned the exchange: the late peer must fail too -- at once, not after its own time-out, and
+        # not "succeed" on the stale rows rank 0 left in its mailbox.
+        monkeypatch.setenv("ICP_GPU_PEER_TIMEOUT_MS", "20000")
+        t0 = time.perf_counter()
+        with pytest.raises(capi.IcpGpuError) as e:
+            ctxs[1].estimate_pose()
+        assert e.value.code == capi.E_PEER and time.perf_counter() - t0 < 5.0
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_memory_lost_peer_costs_one_timeout_per_registration(bunny, monkeypatch):
+    """Once a rank has raised ICP_GPU_E_PEER the remaining launches of its registration skip the exchange: 8 iterations of the
+    symmetric metric (16 exchanges) with a 300 ms time-out take about one time-out, not sixteen."""
+    monkeypatch.setenv("ICP_GPU_PEER_TIMEOUT_MS", "300")
+    src, tgt, _, _ = bunny
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations = 2, 8
+    ctxs = _peer_pair(tgt, src, cfg, 2)
+    try:
+        t0 = time.perf_counter()
+        with pytest.raises(capi.IcpGpuError) as e:
+            ctxs[0].estimate_pose()
+        assert e.value.code == capi.E_PEER
+        assert time.perf_counter() - t0 < 2.0
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_memory_ranks_must_plan_the_same_registration(bunny, monkeypatch):
+    """Ranks whose iteration counts differ would wait for exchanges that never come: the first exchange compares the plans
+    and every rank finishes with ICP_GPU_E_PEER; the multi-resolution schedule (derived from the local shard) is refused."""
+    monkeypatch.setenv("ICP_GPU_PEER_TIMEOUT_MS", "20000")
+    src, tgt, _, _ = bunny
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations = 1, 4
+    ctxs = _peer_pair(tgt, src, cfg, 2)
+    try:
+        cfg.n_iterations = 6
+        ctxs[1].set_config(cfg)
+        t0 = time.perf_counter()
+        for c in ctxs:
+            c.estimate_pose_async()
+        for c in ctxs:
+            with pytest.raises(capi.IcpGpuError) as e:
+                c.estimate_pose_finish()
+            assert e.value.code == capi.E_PEER
+        assert time.perf_counter() - t0 < 10.0
+        cfg.multires = 1
+        ctxs[0].set_config(cfg)
+        with pytest.raises(capi.IcpGpuError) as e:
+            ctxs[0].estimate_pose()
+        assert e.value.code == capi.E_ARG
     finally:
         for c in ctxs:
             c.close()

@@ -104,3 +104,43 @@ def test_depth_constructor_equals_reference(ctx):
         pr, nr, cr = R.cloud_from_depth(frames[0], rgbx, K[0, 0], K[1, 1], K[0, 2], K[1, 2], None, keep, ds, 0.1)   # PointCloud.h:78-165
         pg, ng, cg = ctx.cloud_from_depth(frames[0], rgbx, K, None, keep, ds, 0.1)
         assert np.array_equal(pg, pr, equal_nan=True) and np.array_equal(ng, nr, equal_nan=True) and np.array_equal(cg, cr)
+
+
+@pytest.mark.parametrize("setter_order", [0, 1, 2])
+def test_dropin_setters_keep_matcher_and_weighting_distances_apart(bunny, setter_order):
+    """ICPOptimizer drop-in (icp_variants_b200/optimizer.py, mirrored by include/icp_b200/ICPOptimizer.h) driven with the reference's
+    setters in three orders against the reference's own classes driven the same way: setMatchingMethod resets only the matcher's
+    distance to MAX_DISTANCE (ICPOptimizer.h:71-78), setMatchingMaxDistance sets both (:41-44), WeightingMethod sees
+    ICPOptimizer::maxDistance (:220,:528)."""
+    from icp_variants_b200.optimizer import LinearICPOptimizer, PointCloud
+    src, tgt, gs, gt = bunny
+    n, pr, _ = R.estimate_pose(0, 1, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors, src.points[gs], tgt.points[gt],
+                               n_iterations=5, max_distance_sq=0.002, weighting=1, setter_order=setter_order)
+    assert n == 5
+    opt = LinearICPOptimizer(device=0)
+    if setter_order == 1:
+        opt.setMatchingMaxDistance(0.002)
+    opt.setMatchingMethod(0)
+    opt.setMetric(1); opt.setNbOfIterations(5)
+    if setter_order == 0:
+        opt.setMatchingMaxDistance(0.002)
+    opt.setWeightingMethod(1)
+    pose = opt.estimatePose(src, tgt, np.eye(4, dtype=np.float32), calculateRMSE=False)
+    assert rot_err(pr, pose) < 1e-5 and np.abs(pr[:3, 3] - pose[:3, 3]).max() < 1e-5
+
+
+def test_brute_force_class_thresholds_the_norm_like_the_reference(ctx):
+    """ICP_GPU_NN_BRUTE_NORM = NearestNeighborSearchBruteForce as written (NearestNeighbor.h:81-97): bit-exact against the class."""
+    rng = np.random.default_rng(3)
+    tgt = (np.round(rng.uniform(-1, 1, (1500, 3)) * 8) / 8).astype(np.float32)      # quantised: many exact ties
+    qry = (np.round(rng.uniform(-1, 1, (1000, 3)) * 8) / 8 + 0.01).astype(np.float32)
+    c = capi.default_config()
+    c.nn_algorithm, c.rejection = 3, 0
+    for max_d in (0.05, 0.3):
+        c.max_distance_sq = max_d
+        ctx.set_config(c)
+        ctx.set_target(tgt, None, None); ctx.set_source(qry, None, None)
+        idx, w = ctx.query_matches(np.eye(4, dtype=np.float32))
+        i0, w0 = R.knn_brute(tgt, qry, max_d)
+        assert np.array_equal(idx, i0) and np.array_equal(w, w0)
+        assert (idx >= 0).any() and ((idx < 0).any() or max_d > 0.05)

@@ -406,3 +406,37 @@ def test_pca_normals_equal_reference_constructor(small_eth_pair, bunny):
     assert ((-pts[ok] * n_o[ok]).sum(1) >= -1e-6).all()                # flipped towards the viewpoint (the origin)
     n_b, _ = O.pca_normals(bunny[1].points, 5)
     assert np.array_equal(R.cloud_from_xyz(bunny[1].points)[0], n_b, equal_nan=True)
+
+
+@pytest.mark.parametrize("setter_order,matcher_d2,weight_d2", [(1, 0.005, 0.002), (2, 0.005, 0.0003)])
+def test_matcher_and_weighting_distances_are_separate(bunny, setter_order, matcher_d2, weight_d2):
+    """The reference keeps two distances: setMatchingMethod re-creates the matcher with MAX_DISTANCE = 0.005 (ICPOptimizer.h:71-78,
+    NearestNeighbor.h:5,35) and leaves ICPOptimizer::maxDistance -- the one WeightingMethod divides by (:220,:528) -- alone.  A driver
+    that calls setMatchingMaxDistance BEFORE setMatchingMethod (or never) therefore matches with 0.005 and weights with its own
+    value (or 0.0003): the oracle reproduces both through max_distance_sq / weight_max_distance_sq."""
+    src, tgt, gs, gt = bunny
+    for minimizer, metric in ((0, 1), (0, 2), (1, 1)):
+        n, pr, _ = R.estimate_pose(minimizer, metric, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors,
+                                   src.points[gs], tgt.points[gt], n_iterations=5, max_distance_sq=0.002, weighting=1, setter_order=setter_order)
+        assert n == 5
+        cfg = O.Config(metric=metric, minimizer=minimizer, weighting=1, n_iterations=5, max_distance_sq=matcher_d2, weight_max_distance_sq=weight_d2)
+        rc, po, _, _ = O.estimate_pose(cfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+        assert rc == 0
+        assert rot_err(pr, po) < ROT_TOL and np.abs(pr[:3, 3] - po[:3, 3]).max() < TRANS_TOL
+        # and the single-distance configuration is a different registration (the test would not notice a merged field otherwise)
+        rc, pm, _, _ = O.estimate_pose(O.Config(metric=metric, minimizer=minimizer, weighting=1, n_iterations=5, max_distance_sq=0.002),
+                                       src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+        assert rot_err(pm, po) > 10 * ROT_TOL or np.abs(pm[:3, 3] - po[:3, 3]).max() > 10 * TRANS_TOL
+
+
+def test_reference_brute_force_as_written_norm_threshold():
+    """NearestNeighborSearchBruteForce compares (p - m).norm() -- candidates AND the threshold (NearestNeighbor.h:86,93): with the
+    same number it keeps a different match set than the squared-distance matchers.  The oracle's restatement of exactly that rule
+    (what ICP_GPU_NN_BRUTE_NORM runs on the device) is bit-identical to the reference class, ties of rounded norms included."""
+    tgt, _, _ = _cloud(1500, 6, quant=8)
+    qry, _, _ = _cloud(1000, 7, quant=8)
+    for max_d in (0.05, 0.3, 1e9):
+        idx, w = R.knn_brute(tgt, qry, max_d)
+        m = O.knn_brute_norm(tgt, qry, max_d)
+        assert np.array_equal(idx, m["idx"]) and np.array_equal(w, m["weight"])
+    assert (R.knn_brute(tgt, qry, 0.05)[0] < 0).any() and (R.knn_brute(tgt, qry, 0.05)[0] >= 0).any()
