@@ -3,15 +3,15 @@
 //
 // Structure: a uniform grid of 2^T cells (T = 30 for a target: 10 bits per axis) whose cell codes are Morton-style
 // bit interleavings of the per-axis cell indices (the axis taken at each bit is the currently longest one, so cells end up
-// near-cubic).  The cloud is sorted by (cell code, original index) with a stable LSD RADIX SORT -- 3 passes of 10-11 bits,
-// every pass = per-tile digit histograms + a ranking scatter (warp-level multi-split with match.any, no atomics in the
+// near-cubic).  The cloud is sorted by (cell code, original index) with a stable LSD RADIX SORT -- 4 passes of 7-8 bits,
+// every pass = per-tile digit histograms, their scan, and a ranking scatter (warp-level multi-split with match.any, no atomics in the
 // ranking: the order inside a cell is the original index order, so two uploads of the same cloud give the same structure
 // bit for bit).  There is no dense cell table: the implicit binary tree over the cells is read off the SORTED KEYS -- the
 // node of depth d around point i is the maximal run of points around i whose neighbouring keys share >= d leading bits
 // (delta(i) = common-prefix length of key[i-1] and key[i]).  Leaves = the shallowest such nodes with <= 32 points, level-l
 // nodes = the shallowest with <= 32 nodes of level l-1; both are found per element from a +-32 window of delta values.
 //
-// Launches of one target build (one stream, no host synchronisation): pack+bbox, keys+hist, (scatter, hist) x passes,
+// Launches of one target build (no host synchronisation): pack+bbox+grid parameters, keys+hist, (scan, scatter) x passes, gather,
 // leaf flags, leaf ranks, leaf boxes, level-1 flags / ranks / boxes, one single-block kernel for all levels above,
 // two adjacency kernels.
 #include "icp_internal.cuh"
@@ -173,27 +173,31 @@ __device__ __forceinline__ unsigned int cell_code(const GridParams& g, float x, 
 // ---------------------------------------------------------------------------- stable LSD radix sort of (key, index)
 // key = cell code (T bits); a point with a non-finite coordinate gets 1 << T: it sorts after every cell (sources keep such
 // points at the end -- every point needs a slot; targets simply never look past n_finite).  T + 1 bits are sorted in
-// passes of <= 11 bits over tiles of 256 threads x ipt contiguous items.  Per pass:
+// passes of <= 8 bits over tiles of 512 threads x ipt contiguous items (one tile per SM for clouds up to ~600k points).
+// Per pass:
 //   digit histograms per tile, digit-major (hist[d * tiles_pad + tile]): pass 0's by the key kernel; pass p+1's by the
 //     scatter kernel of pass p (an item's next tile is known once its slot is: one L2 atomic per item);
 //   radix_scan_kernel: one warp per digit turns the digit's row into exclusive prefixes over the tiles (+ the digit's total);
 //   radix_scatter_kernel: a tile's first slot per digit = digits before it (block scan of the totals) + the same digit in
 //     earlier tiles; the tile's items are ranked per warp (contiguous chunk per warp, rounds of 32 in order; match.any groups
 //     equal digits, the group's lowest lane advances the warp's running slot) and written to their slots: stable,
-//     deterministic -- no atomics decide any position.  The last pass moves the payload (point and normal records).
-#define RS_THREADS 256
+//     deterministic -- no atomics decide any position.
+// A final gather moves the point and normal records into the sorted order (coalesced writes).
+#define KEY_THREADS 256
+#define RS_THREADS 512
 #define RS_WARPS (RS_THREADS / 32)
-#define RS_MAX_BITS 11
+#define RS_MAX_BITS 8
 #define RS_MAX_BINS (1 << RS_MAX_BITS)
+#define RS_REG_IPT 8
 
 // Thread per point: key + the point's count in pass 0's histogram (cleared by the pack kernel).
-__global__ void __launch_bounds__(RS_THREADS) keys_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
-                                                          unsigned int* __restrict__ keys, int tile_items, int tiles_pad, int shift, int bits,
-                                                          unsigned int* __restrict__ hist0) {
+__global__ void __launch_bounds__(KEY_THREADS) keys_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
+                                                           unsigned int* __restrict__ keys, int tile_items, int tiles_pad, int shift, int bits,
+                                                           unsigned int* __restrict__ hist0) {
     __shared__ GridParams g;
     if (threadIdx.x < sizeof(GridParams) / 4) reinterpret_cast<unsigned int*>(&g)[threadIdx.x] = reinterpret_cast<const unsigned int*>(gp)[threadIdx.x];
     __syncthreads();
-    const int i = blockIdx.x * RS_THREADS + threadIdx.x;
+    const int i = blockIdx.x * KEY_THREADS + threadIdx.x;
     if (i >= n) return;
     const float4 p = pts[i];
     const unsigned int key = finite3(p.x, p.y, p.z) ? cell_code(g, p.x, p.y, p.z) : (1u << g.T);   // non-finite: can never win the strict '>' scan of NearestNeighbor.h:87
@@ -202,8 +206,8 @@ __global__ void __launch_bounds__(RS_THREADS) keys_kernel(const float4* __restri
 }
 
 // One warp per digit: the digit's per-tile counts -> exclusive prefixes over the tiles; totals[d] = the digit's count.
-__global__ void __launch_bounds__(RS_THREADS) radix_scan_kernel(unsigned int* __restrict__ hist, int bins, int n_tiles, int tiles_pad, unsigned int* __restrict__ totals) {
-    const int d = (blockIdx.x * RS_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) radix_scan_kernel(unsigned int* __restrict__ hist, int bins, int n_tiles, int tiles_pad, unsigned int* __restrict__ totals) {
+    const int d = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (d >= bins) return;
     unsigned int* row = hist + (size_t)d * tiles_pad;
     unsigned int carry = 0;
@@ -239,31 +243,25 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
     return r;
 }
 
-// idx_in == nullptr: the identity (pass 0).  pts_in != nullptr: last pass -- the payload is moved instead of the index.
-// hist: this pass's scanned histogram; hist_next (nullable): the next pass's, counted here.  msd_start (nullable, last pass):
-// first output slot of every digit of the pass, bins + 1 entries.  ipt <= RS_REG_IPT: a thread's keys, indices and slots stay
-// in registers between the phases (all loads of a phase in flight at once: with one 8-warp block per SM the kernel is bound by
-// the length of its chain of dependent memory round trips, not by bandwidth).
-#define RS_REG_IPT 16
-// The lanes of the (converged, `vm`) warp whose digit equals mine: match.any, or `bits` ballots combined (one per digit bit).
-__device__ __forceinline__ unsigned int digit_peers(unsigned int vm, unsigned int dg, int bits, int use_ballot) {
-    if (!use_ballot) return __match_any_sync(vm, dg);
-    unsigned int peers = vm;
-    for (int k = 0; k < bits; ++k) {
-        const unsigned int b = __ballot_sync(vm, (dg >> k) & 1u);
-        peers &= ((dg >> k) & 1u) ? b : ~b;
-    }
-    return peers;
+// idx_in == nullptr: the identity (pass 0).  hist: this pass's scanned histogram; hist_next (nullable): the next pass's, counted
+// here.  msd_start (nullable, last pass): first output slot of every digit of the pass, bins + 1 entries.  ipt <= RS_REG_IPT: a
+// thread's keys, indices and slots stay in registers between the phases (all loads of a phase in flight at once: with one
+// block per SM the kernel is bound by the length of its chains of dependent instructions, not by bandwidth).
+// One count for the next pass's histogram, aggregated over the lanes of the warp that hit the same counter: sorted keys
+// put neighbours into the same (digit, tile) cell -- 32 same-address L2 atomics per warp otherwise, and the high digits of a
+// room scan take only a few dozen values.
+__device__ __forceinline__ void count_next(unsigned int* __restrict__ hist_next, unsigned int cell) {
+    const unsigned int peers = __match_any_sync(__activemask(), cell);
+    if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&hist_next[cell], (unsigned int)__popc(peers));
 }
+
 template <bool REG>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ idx_in,
                                                                    unsigned int* __restrict__ keys_out, unsigned int* __restrict__ idx_out, int n,
                                                                    int ipt, int tiles_pad, int shift, int bits,
                                                                    const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals,
                                                                    unsigned int* __restrict__ hist_next, int shift_next, int bits_next,
-                                                                   const float4* __restrict__ pts_in, const float4* __restrict__ nrm_in,
-                                                                   float4* __restrict__ pts_out, float4* __restrict__ nrm_out,
-                                                                   unsigned int* __restrict__ msd_start, int use_ballot) {
+                                                                   unsigned int* __restrict__ msd_start) {
     __shared__ unsigned short wcnt[RS_WARPS][RS_MAX_BINS];     // per warp and digit: count, then tile-relative first slot, then running slot
     __shared__ unsigned int base[RS_MAX_BINS];                 // per digit: first output slot of this tile
     const unsigned int FULL = 0xFFFFFFFFu;
@@ -288,14 +286,10 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
         unsigned int* z = reinterpret_cast<unsigned int*>(&wcnt[0][0]);
         for (int d = threadIdx.x; d < RS_WARPS * RS_MAX_BINS / 2; d += RS_THREADS) z[d] = 0u;
     }
-    // the loads of the offsets below depend on nothing: issue them before the counting phase
-    unsigned int before[RS_MAX_BINS / RS_THREADS], tot[RS_MAX_BINS / RS_THREADS];
-#pragma unroll
-    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
-        const int d = k * RS_THREADS + threadIdx.x;
-        before[k] = d < bins ? __ldg(&hist[(size_t)d * tiles_pad + blockIdx.x]) : 0u;
-        tot[k] = d < bins ? __ldg(&totals[d]) : 0u;
-    }
+    // the loads of the offsets below depend on nothing: issue them before the counting phase (thread d < bins owns digit d)
+    const int d_own = threadIdx.x;
+    unsigned int before = 0u, tot = 0u;
+    if (d_own < bins) { before = __ldg(&hist[(size_t)d_own * tiles_pad + blockIdx.x]); tot = __ldg(&totals[d_own]); }
     __syncthreads();
     // phase A: digit counts of the warp's chunk, rounds of 32 items
     if (REG) {
@@ -306,7 +300,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
                 const unsigned int vm = __ballot_sync(FULL, valid);
                 if (valid) {
                     const unsigned int dg = (kreg[r] >> shift) & mask;
-                    const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                    const unsigned int peers = __match_any_sync(vm, dg);
                     if ((peers & lt) == 0u) wcnt[w][dg] = (unsigned short)(wcnt[w][dg] + __popc(peers));
                 }
                 __syncwarp();
@@ -319,52 +313,25 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
             const unsigned int vm = __ballot_sync(FULL, valid);
             if (valid) {
                 const unsigned int dg = (keys_in[i] >> shift) & mask;
-                const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                const unsigned int peers = __match_any_sync(vm, dg);
                 if ((peers & lt) == 0u) wcnt[w][dg] = (unsigned short)(wcnt[w][dg] + __popc(peers));
             }
             __syncwarp();
             if (vm != FULL) break;
         }
     }
-#pragma unroll
-    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) { const int d = k * RS_THREADS + threadIdx.x; if (d < bins) base[d] = tot[k]; }
     __syncthreads();
     // per digit: warp counts -> exclusive prefix over the warps (tile-relative first slot of the warp's items with the digit)
+    if (d_own < bins) {
+        unsigned int acc = 0;
 #pragma unroll
-    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
-        const int d = k * RS_THREADS + threadIdx.x;
-        if (d < bins) {
-            unsigned int acc = 0;
-#pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ++ww) { const unsigned int c = wcnt[ww][d]; wcnt[ww][d] = (unsigned short)acc; acc += c; }
-        }
+        for (int ww = 0; ww < RS_WARPS; ++ww) { const unsigned int c = wcnt[ww][d_own]; wcnt[ww][d_own] = (unsigned short)acc; acc += c; }
     }
-    {   // exclusive scan of the totals in digit order: every thread owns `per` consecutive digits
-        const int per = (bins + RS_THREADS - 1) / RS_THREADS;
-        unsigned int loc[RS_MAX_BINS / RS_THREADS]; unsigned int s = 0;
-#pragma unroll
-        for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
-            const int d = threadIdx.x * per + k;
-            loc[k] = (k < per && d < bins) ? base[d] : 0u;
-            s += loc[k];
-        }
-        unsigned int ex = block_exclusive_scan(s, nullptr);    // ends with a barrier: every total has been read
-#pragma unroll
-        for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
-            const int d = threadIdx.x * per + k;
-            if (k < per && d < bins) { base[d] = ex; ex += loc[k]; }
-        }
-    }
-    __syncthreads();
-    if (msd_start && blockIdx.x == 0) {
-        for (int d = threadIdx.x; d < bins; d += RS_THREADS) msd_start[d] = base[d];
-        if (threadIdx.x == 0) msd_start[bins] = (unsigned int)n;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RS_MAX_BINS / RS_THREADS; ++k) {
-        const int d = k * RS_THREADS + threadIdx.x;
-        if (d < bins) base[d] += before[k];
+    // exclusive scan of the digits' totals: the first slot of every digit in the output
+    const unsigned int digit_base = block_exclusive_scan(d_own < bins ? tot : 0u, nullptr);
+    if (d_own < bins) {
+        base[d_own] = digit_base + before;
+        if (msd_start && blockIdx.x == 0) { msd_start[d_own] = digit_base; if (d_own == bins - 1) msd_start[bins] = (unsigned int)n; }
     }
     __syncthreads();
     // phase B: the same rounds again; the group's lowest lane advances the warp's running slot of the digit
@@ -379,7 +346,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
                 const unsigned int vm = __ballot_sync(FULL, valid);
                 if (valid) {
                     const unsigned int dg = (kreg[r] >> shift) & mask;
-                    const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                    const unsigned int peers = __match_any_sync(vm, dg);
                     const int leader = __ffs((int)peers) - 1;
                     unsigned int old = 0;
                     if (lane == leader) { old = wcnt[w][dg]; wcnt[w][dg] = (unsigned short)(old + __popc(peers)); }
@@ -394,9 +361,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
         for (int r = 0; r < RS_REG_IPT; ++r) {
             if (pos[r] != 0xFFFFFFFFu) {
                 keys_out[pos[r]] = kreg[r];
-                if (pts_in) { pts_out[pos[r]] = __ldg(&pts_in[ireg[r]]); nrm_out[pos[r]] = __ldg(&nrm_in[ireg[r]]); }
-                else idx_out[pos[r]] = ireg[r];
-                if (hist_next) atomicAdd(&hist_next[(size_t)((kreg[r] >> shift_next) & mask_next) * tiles_pad + pos[r] / (unsigned int)tile_items], 1u);
+                idx_out[pos[r]] = ireg[r];
+                if (hist_next) count_next(hist_next, ((kreg[r] >> shift_next) & mask_next) * (unsigned int)tiles_pad + pos[r] / (unsigned int)tile_items);
             }
         }
     } else {
@@ -408,21 +374,30 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigne
                 const unsigned int key = keys_in[i];
                 const unsigned int src = idx_in ? idx_in[i] : (unsigned int)i;
                 const unsigned int dg = (key >> shift) & mask;
-                const unsigned int peers = digit_peers(vm, dg, bits, use_ballot);
+                const unsigned int peers = __match_any_sync(vm, dg);
                 const int leader = __ffs((int)peers) - 1;
                 unsigned int old = 0;
                 if (lane == leader) { old = wcnt[w][dg]; wcnt[w][dg] = (unsigned short)(old + __popc(peers)); }
                 old = __shfl_sync(peers, old, leader);
                 const unsigned int p = base[dg] + old + (unsigned int)__popc(peers & lt);
                 keys_out[p] = key;
-                if (pts_in) { pts_out[p] = pts_in[src]; nrm_out[p] = nrm_in[src]; }
-                else idx_out[p] = src;
-                if (hist_next) atomicAdd(&hist_next[(size_t)((key >> shift_next) & mask_next) * tiles_pad + p / (unsigned int)tile_items], 1u);
+                idx_out[p] = src;
+                if (hist_next) count_next(hist_next, ((key >> shift_next) & mask_next) * (unsigned int)tiles_pad + p / (unsigned int)tile_items);
             }
             __syncwarp();
             if (vm != FULL) break;
         }
     }
+}
+
+// The records in sorted order: thread per output slot (coalesced writes, gathered reads).
+__global__ void __launch_bounds__(256) gather_records_kernel(const unsigned int* __restrict__ idx, int n, const float4* __restrict__ pts_in,
+                                                             const float4* __restrict__ nrm_in, float4* __restrict__ pts_out, float4* __restrict__ nrm_out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int s = idx[i];
+    pts_out[i] = __ldg(&pts_in[s]);
+    nrm_out[i] = __ldg(&nrm_in[s]);
 }
 
 void icp_radix_plan(int n, int T, IcpRadixPlan* p) {
@@ -431,12 +406,12 @@ void icp_radix_plan(int n, int T, IcpRadixPlan* p) {
     const int lo = total / p->n_pass, extra = total % p->n_pass;
     int shift = 0;
     for (int k = 0; k < p->n_pass; ++k) { p->bits[k] = lo + (k < extra ? 1 : 0); p->shift[k] = shift; shift += p->bits[k]; }
-    // One tile per SM while that keeps a thread's items in registers (4 .. 16 items per thread), more tiles beyond; only clouds
+    // One tile per SM while that keeps a thread's items in registers (2 .. 8 items per thread), more tiles beyond; only clouds
     // of more than 16 M points get larger tiles (the histograms have one column per tile).
     long long ipt = ((long long)n + RS_THREADS * 148 - 1) / (RS_THREADS * 148);
-    if (ipt < 4) ipt = 4;
+    if (ipt < 2) ipt = 2;
     if (ipt > RS_REG_IPT) ipt = RS_REG_IPT;
-    while ((long long)n > ipt * RS_THREADS * 4096 && ipt < 224) ipt += 16;
+    while ((long long)n > ipt * RS_THREADS * 4096 && ipt < 120) ipt += 8;
     p->ipt = (int)ipt;
     p->tile_items = (int)(ipt * RS_THREADS);
     p->n_tiles = n > 0 ? (int)(((long long)n + p->tile_items - 1) / p->tile_items) : 0;
@@ -463,29 +438,31 @@ cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, in
     unsigned int* iin = nullptr; unsigned int* iout = idx_a;
     const size_t mat = (size_t)RS_MAX_BINS * p.tiles_pad;
     unsigned int* totals = hist + (size_t)p.n_pass * mat;
-    const int use_ballot = getenv("ICP_GPU_RADIX_BALLOT") ? 1 : 0;       // tuning knob (A/B measurement)
-    if (n > 0) { keys_kernel<<<(n + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, s>>>(pts_in, n, grid, kin, p.tile_items, p.tiles_pad, p.shift[0], p.bits[0], hist); ++launches; }
+    if (n > 0) { keys_kernel<<<(n + KEY_THREADS - 1) / KEY_THREADS, KEY_THREADS, 0, s>>>(pts_in, n, grid, kin, p.tile_items, p.tiles_pad, p.shift[0], p.bits[0], hist); ++launches; }
     for (int k = 0; k < p.n_pass && n > 0; ++k) {
         const bool last = k == p.n_pass - 1;
         const int bins = 1 << p.bits[k];
-        radix_scan_kernel<<<(bins * 32 + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, s>>>(hist + k * mat, bins, p.n_tiles, p.tiles_pad, totals); ++launches;
-        if (last && late) {
-            // the normal records (nrm_in) are packed only now: their upload had the earlier passes to finish
-            cudaError_t e = cudaStreamWaitEvent(s, late->ready, 0);
-            if (e != cudaSuccess) return e;
-            pack_normals_kernel<<<(n + 255) / 256, 256, 0, s>>>(late->nrm, late->rgba, n, late->nrmo); ++launches;
-        }
+        radix_scan_kernel<<<(bins * 32 + 255) / 256, 256, 0, s>>>(hist + k * mat, bins, p.n_tiles, p.tiles_pad, totals); ++launches;
         unsigned int* hn = last ? nullptr : hist + (k + 1) * mat;
         const int sn = last ? 0 : p.shift[k + 1], bn = last ? 1 : p.bits[k + 1];
         if (p.ipt <= RS_REG_IPT)
             radix_scatter_kernel<true><<<p.n_tiles, RS_THREADS, 0, s>>>(kin, iin, kout, iout, n, p.ipt, p.tiles_pad, p.shift[k], p.bits[k], hist + k * mat, totals, hn, sn, bn,
-                                                                       last ? pts_in : nullptr, nrm_in, pts_sorted, nrm_sorted, last ? msd_start : nullptr, use_ballot);
+                                                                       last ? msd_start : nullptr);
         else
             radix_scatter_kernel<false><<<p.n_tiles, RS_THREADS, 0, s>>>(kin, iin, kout, iout, n, p.ipt, p.tiles_pad, p.shift[k], p.bits[k], hist + k * mat, totals, hn, sn, bn,
-                                                                        last ? pts_in : nullptr, nrm_in, pts_sorted, nrm_sorted, last ? msd_start : nullptr, use_ballot);
+                                                                        last ? msd_start : nullptr);
         ++launches;
         unsigned int* t = kin; kin = kout; kout = t;
         iin = iout; iout = (iout == idx_a) ? idx_b : idx_a;
+    }
+    if (n > 0) {
+        if (late) {
+            // the normal records (nrm_in) are packed only now: their upload had the whole sort to finish
+            cudaError_t e = cudaStreamWaitEvent(s, late->ready, 0);
+            if (e != cudaSuccess) return e;
+            pack_normals_kernel<<<(n + 255) / 256, 256, 0, s>>>(late->nrm, late->rgba, n, late->nrmo); ++launches;
+        }
+        gather_records_kernel<<<(n + 255) / 256, 256, 0, s>>>(iin, n, pts_in, nrm_in, pts_sorted, nrm_sorted); ++launches;
     }
     if (keys_sorted_out) *keys_sorted_out = kin;
     if (n_launches) *n_launches += launches;
@@ -571,8 +548,8 @@ cudaError_t icp_launch_seed_from_keys(const float4* src_pts, int n_src, const De
 // equal keys) with more than 32 elements is cut at the positions divisible by 32.  Cell-aligned nodes are pairwise disjoint
 // in space -- a search ball meets only the few leaves around it, unlike fixed runs of the Z-curve, whose boxes straddle the
 // curve's jumps.
-#define LV_THREADS 256
-#define LV_ITEMS 4
+#define LV_THREADS 1024     // one element per thread: the per-element work is a chain of dependent shared-memory loads -- many warps hide it
+#define LV_ITEMS 1
 #define LV_TILE (LV_THREADS * LV_ITEMS)
 #define LV_HALO 32
 
@@ -727,11 +704,13 @@ __global__ void __launch_bounds__(LV_THREADS) level_rank_kernel(const unsigned i
 // level's delta values and the boxes.  delta_a holds the deltas of level `first_level - 1`'s nodes; the levels ping-pong
 // between delta_a and delta_b.
 #define UP_THREADS 1024
+#define UP_STAGE 4096
 __global__ void __launch_bounds__(UP_THREADS) upper_levels_kernel(int* delta_a, int* delta_b, unsigned int* node_rank,
                                                                   unsigned int* child_start, BvhDesc* bvh,
                                                                   float4* box, int T, int first_level) {
     __shared__ unsigned int s_carry, s_total;
     __shared__ BvhDesc sb;
+    __shared__ int s_delta[UP_STAGE];                        // the level's deltas when they fit (dependent loads: shared memory is 10x nearer than L2)
     const int lane = threadIdx.x & 31;
     int* din = delta_a; int* dout = delta_b;
     for (int lvl = first_level; lvl < ICP_BVH_MAX_LEVELS; ++lvl) {
@@ -745,12 +724,15 @@ __global__ void __launch_bounds__(UP_THREADS) upper_levels_kernel(int* delta_a, 
         const int coff = sb.coffset[lvl];
         unsigned int* rank = node_rank + coff;
         unsigned int* start = child_start + coff;
+        const bool staged = n_prev <= UP_STAGE;
+        if (staged) for (int j = threadIdx.x; j < n_prev; j += UP_THREADS) s_delta[j] = din[j];
+        __syncthreads();
         for (int base = 0; base < n_prev; base += UP_THREADS) {
             const int i = base + threadIdx.x;
             unsigned int f = 0u;
             if (i < n_prev) {
                 // the rule of level_flags_kernel; delta(j) of this level's elements, -1 outside (1 .. n_prev - 1)
-                auto dl = [&](int o) -> int { const int j = i + o; return (j > 0 && j < n_prev) ? din[j] : -1; };
+                auto dl = [&](int o) -> int { const int j = i + o; return (j > 0 && j < n_prev) ? (staged ? s_delta[j] : din[j]) : -1; };
                 const int di = dl(0);
                 f = 1u;
                 if (di >= 0) {
@@ -764,7 +746,7 @@ __global__ void __launch_bounds__(UP_THREADS) upper_levels_kernel(int* delta_a, 
             const unsigned int ex = block_exclusive_scan(f, &s_total) + s_carry;
             if (i < n_prev) {
                 rank[i] = ex;
-                if (f) { start[ex] = (unsigned int)i; dout[ex] = i == 0 ? -1 : din[i]; }
+                if (f) { start[ex] = (unsigned int)i; dout[ex] = i == 0 ? -1 : (staged ? s_delta[i] : din[i]); }
             }
             __syncthreads();
             if (threadIdx.x == 0) s_carry += s_total;
@@ -940,10 +922,24 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
                     cfirst = child_start[b.coffset[1] + node]; clast = child_start[b.coffset[1] + node + 1];
                 }
                 unsigned int m1 = __ballot_sync(FULL, keep1);
-                while (m1 && ok) {
+                // the children of the nodes that meet, one node per round; the next node's boxes are requested before the
+                // current ones are used (the rounds are chains of dependent L2 loads: two in flight)
+                float4 nlo = make_float4(0.f, 0.f, 0.f, 0.f), nhi = nlo; unsigned int nc = 0u, nlast = 0u;
+                bool more = m1 != 0u;                          // warp-uniform: a node's boxes are in flight
+                if (more) {
                     const int src = __ffs((int)m1) - 1; m1 &= m1 - 1u;
-                    const unsigned int c = __shfl_sync(FULL, cfirst, src) + lane, last = __shfl_sync(FULL, clast, src);
-                    const bool keep = c < last && c != (unsigned int)l && boxes_meet(lo, hi, box[2 * (size_t)c], box[2 * (size_t)c + 1]);
+                    nc = __shfl_sync(FULL, cfirst, src) + lane; nlast = __shfl_sync(FULL, clast, src);
+                    if (nc < nlast) { nlo = box[2 * (size_t)nc]; nhi = box[2 * (size_t)nc + 1]; }
+                }
+                while (more && ok) {
+                    const float4 clo = nlo, chi = nhi; const unsigned int c = nc, last = nlast;
+                    more = m1 != 0u;
+                    if (more) {
+                        const int src = __ffs((int)m1) - 1; m1 &= m1 - 1u;
+                        nc = __shfl_sync(FULL, cfirst, src) + lane; nlast = __shfl_sync(FULL, clast, src);
+                        if (nc < nlast) { nlo = box[2 * (size_t)nc]; nhi = box[2 * (size_t)nc + 1]; }
+                    }
+                    const bool keep = c < last && c != (unsigned int)l && boxes_meet(lo, hi, clo, chi);
                     const unsigned int mk = __ballot_sync(FULL, keep);
                     if (count + __popc(mk) > 32) { ok = false; break; }
                     if (keep) list[count + __popc(mk & lt)] = c;

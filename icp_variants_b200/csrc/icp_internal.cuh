@@ -190,13 +190,13 @@ struct ReduceArgs {
 cudaError_t icp_launch_pack_cloud(const float* xyz, const float* nrm, const uint8_t* rgba, int n, float4* pts, float4* nrmo,
                                   unsigned int* scratch, int T, GridParams* grid, unsigned int* hist, long long hist_words, int with_normals, cudaStream_t s);
 // Stable LSD radix sort of a packed cloud into (cell code, original index) order; points with a non-finite coordinate end up
-// after the last cell.  T + 1 key bits in passes of <= 11 bits.
+// after the last cell.  T + 1 key bits in passes of <= 8 bits.
 // normal / colour records packed late (before the last pass of the sort), once `ready` has happened: host uploads
 struct IcpLatePack { const float* nrm; const uint8_t* rgba; float4* nrmo; cudaEvent_t ready; };
-struct IcpRadixPlan { int n_pass; int shift[3]; int bits[3]; int ipt; int tile_items; int n_tiles; int tiles_pad; };
+struct IcpRadixPlan { int n_pass; int shift[4]; int bits[4]; int ipt; int tile_items; int n_tiles; int tiles_pad; };
 void icp_radix_plan(int n, int T, IcpRadixPlan* p);
 size_t icp_radix_hist_words(int n, int T);
-#define ICP_MSD_WORDS 2049
+#define ICP_MSD_WORDS 257
 cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, int n, int T, const GridParams* grid,
                                   unsigned int* keys_a, unsigned int* keys_b, unsigned int* idx_a, unsigned int* idx_b,
                                   unsigned int* hist, float4* pts_sorted, float4* nrm_sorted, unsigned int* msd_start,
