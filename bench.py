@@ -13,22 +13,27 @@ estimatePose, ICPOptimizer.h:532-535).
   e2e      the same registration through the host-pointer C ABI call a reference user would make
            (icp_gpu_set_target / set_source / estimate_pose with host arrays): the H2D copy of both
            clouds and the D2H read of the pose are inside the timed region
-  roofline the dominant kernel (the fused k-NN match kernel), CUDA-event timed per launch
-  cpu_baseline  the reference's own LinearICPOptimizer::estimatePose (oracle/_ref: the reference headers compiled in
-           place against the stand-ins of oracle/ref_shim) on the same pair, a bounded number of iterations; the
-           oracle port (oracle/icp_oracle.c) when that library is absent
+  roofline the dominant kernel (the warp-per-query tree walk of the k-NN search), CUDA-event timed per launch;
+           roofline_fp32 relates its distance evaluations to the device's FP32 throughput MEASURED in the same run
+  cpu_baseline  (N = 1) the reference's own LinearICPOptimizer::estimatePose (oracle/_ref: the reference headers compiled in
+           place against the stand-ins of oracle/ref_shim) on the same pair: one FULL 30-iteration registration on all host
+           threads, a bounded 1-thread sample, and the FLANN-like approximate matcher (cv2.flann_Index, 1 tree, 16 checks)
+           with its match rate against the exact search
+  pair_queue_44  config 5a: a 44-pair ETH-shaped sequence dealt round-robin to the ranks (one queue per GPU, no collective),
+           host arrays in, poses out -- pairs/s over all ranks and the ceiling 44 / ceil(44 / N)
+  sharded_3m     config 5b: ONE 3 M-point pair sharded by source points over the ranks, the per-iteration all-reduce of the 28-double
+           row fused into the reduction kernel over NVLink peer memory (icp_gpu_peer_*), next to an ncclAllReduce on the stream
 
-N > 1 (torchrun): independent pairs sharded across ranks, one queue per GPU, no collective on the
-data path -> weak scaling; time = max over ranks.
+N > 1 (torchrun): `value` = independent pairs, one per rank per step -> weak scaling; time = max over ranks.
 
 --impl reference: times the reference's own code path -- LinearICPOptimizer::estimatePose from
 /root/reference/icp-variants/ICPOptimizer.h, compiled in place into oracle/_ref/libicp_ref.so -- on the box's host
-cores, on a bounded sample (a few iterations) of the same workload.  Eigen, FLANN, Ceres and PCL are neither vendored
-nor installed, so that build uses the stand-ins of oracle/ref_shim: the matcher is an EXACT kd-tree (OpenMP over the
-queries, all host threads) instead of FLANN's approximate one, the 4M x 6 least squares a Gram-matrix SVD; every other
-line (transforms with a 3x3 inverse per normal, weighting, rejection, gather, system assembly, pose composition) is
-the reference's own, single-threaded as in the reference.  Without the library the arm falls back to the oracle port
-(kind "port").
+cores: every step is one FULL 30-iteration registration of the same pair (no extrapolation).  Eigen, FLANN, Ceres and PCL
+are neither vendored nor installed, so that build uses the stand-ins of oracle/ref_shim: the matcher is an EXACT kd-tree
+(OpenMP over the queries, all host threads) instead of FLANN's approximate one, the 4M x 6 least squares a Gram-matrix
+SVD; every other line (transforms with a 3x3 inverse per normal, weighting, rejection, gather, system assembly, pose
+composition) is the reference's own, single-threaded as in the reference.  Without the library the arm falls back to the
+oracle port (kind "port").
 """
 from __future__ import annotations
 
@@ -49,6 +54,8 @@ if ROOT not in sys.path:
 
 N_ITER = 30
 WORKLOAD = "eth_apartment_shaped_pair_344x1077_knn_point_to_plane_linear_30it"
+N_SEQUENCE_PAIRS = 44
+L2_NOTE = "GPU arm: flushed between timed steps (256 MB write); CPU arm: not applicable"
 
 
 def load_peaks():
@@ -61,16 +68,17 @@ def load_peaks():
 
 
 def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu --set full capture
-    (profiles/r1_ncu_traffic.json, produced by profiles/final_measure.sh); None when the summary is absent."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            k = json.load(f)["kernels"]
-        for name, v in k.items():
-            if kernel_substr in name:
-                return v["dram_bytes_read"] + v["dram_bytes_write"]
-    except Exception:   # noqa: BLE001
-        pass
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the newest committed ncu --set full capture
+    (profiles/r2_ncu_traffic.json, else round 1's); None when the summary is absent."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                k = json.load(f)["kernels"]
+            for kn, v in k.items():
+                if kernel_substr in kn:
+                    return v["dram_bytes_read"] + v["dram_bytes_write"]
+        except Exception:   # noqa: BLE001
+            continue
     return None
 
 
@@ -82,6 +90,29 @@ def make_pair(pair_index=0, n_sweeps=344, n_beams=1077):
         z = np.load(cache)
         return (synth.Cloud(z["sp"], z["sn"], z["sc"]), synth.Cloud(z["tp"], z["tn"], z["tc"]))
     src, tgt, _ = synth.eth_pair(seed=1234, n_sweeps=n_sweeps, n_beams=n_beams, pair_index=pair_index)
+    try:
+        np.savez(cache, sp=src.points, sn=src.normals, sc=src.colors, tp=tgt.points, tn=tgt.normals, tc=tgt.colors)
+    except OSError:
+        pass
+    return src, tgt
+
+
+def device_normals_fn(ctx):
+    """k = 5 PCA normals towards the sensor on the device (icp_gpu_target_normals = PointCloud.h:41-76): input preparation of
+    the big synthetic workloads only (never inside a timed region)."""
+    def f(points, viewpoint):
+        ctx.set_target(points, None, None)
+        return ctx.target_normals(5, viewpoint, n=len(points))
+    return f
+
+
+def make_pair_device_normals(ctx, pair_index, n_sweeps, n_beams):
+    from icp_variants_b200 import synth
+    cache = f"/tmp/icp_b200_pairdn_{n_sweeps}x{n_beams}_{pair_index}.npz"
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return (synth.Cloud(z["sp"], z["sn"], z["sc"]), synth.Cloud(z["tp"], z["tn"], z["tc"]))
+    src, tgt, _ = synth.eth_pair(seed=1234, n_sweeps=n_sweeps, n_beams=n_beams, pair_index=pair_index, normals_fn=device_normals_fn(ctx))
     try:
         np.savez(cache, sp=src.points, sn=src.normals, sc=src.colors, tp=tgt.points, tn=tgt.normals, tc=tgt.colors)
     except OSError:
@@ -130,59 +161,81 @@ class ClockSampler:
 
 
 def workload_config(ns, nt, max_d2):
-    """The workload both arms run (BASELINE.json configs[1])."""
+    """The workload both arms run (BASELINE.json configs[1]); identical in both arms' lines."""
     return {"workload": WORKLOAD, "n_source": ns, "n_target": nt, "iterations": N_ITER, "max_distance_sq": max_d2,
-            "pairs_per_gpu_per_step": 1, "includes_index_build": True}
+            "pairs_per_gpu_per_step": 1, "includes_index_build": True, "l2": L2_NOTE}
 
 
-def ref_sample(src, tgt, max_d2, iters):
-    """The reference's own LinearICPOptimizer::estimatePose (oracle/_ref) for `iters` iterations; None if unavailable."""
+# ----------------------------------------------------------------------------- CPU arms
+def host_threads():
+    return os.cpu_count() or 1
+
+
+def ref_registration(src, tgt, max_d2, iters, threads):
+    """The reference's own LinearICPOptimizer::estimatePose (oracle/_ref) for `iters` iterations on `threads` matcher threads.
+    Returns seconds, or None when the library is unavailable."""
     try:
         from oracle import ref
         if ref.build() is None:
             return None
-        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+        ref.set_num_threads(threads)
         t0 = time.perf_counter()
         n, pose, _ = ref.estimate_pose(0, 1, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors,
                                        src.points[:4], tgt.points[:4], n_iterations=iters, max_distance_sq=max_d2)
         dt = time.perf_counter() - t0
-        if n != iters:
-            return None
-        return dt, iters * len(src), os.cpu_count() or 1
+        return dt if n == iters else None
     except Exception as e:   # noqa: BLE001 -- the baseline must never take the bench down
         print(f"bench: reference library unavailable ({e}); using the oracle port", file=sys.stderr)
         return None
 
 
-def cpu_baseline_sample(src, tgt, max_d2, iters):
-    """(seconds, queries, threads, kind): the reference build when present, else the oracle port."""
-    r = ref_sample(src, tgt, max_d2, iters)
-    if r is not None:
-        return r + ("reference",)
-    return cpu_sample(src, tgt, max_d2, iters) + ("port",)
-
-
-def cpu_registration_seconds(src, tgt, max_d2, iters):
-    """Seconds of one full N_ITER-iteration CPU registration, extrapolated from a 1-iteration and an `iters`-iteration run
-    of the same pair: t(1) + (N_ITER - 1) * (t(iters) - t(1)) / (iters - 1), so that the once-per-registration work (index
-    build, cloud copies) is counted once.  Returns (seconds, measured seconds, queries/iteration, threads, kind)."""
-    iters = max(int(iters), 2)
-    t1, _, cores, kind = cpu_baseline_sample(src, tgt, max_d2, 1)
-    tk, nq, cores, kind = cpu_baseline_sample(src, tgt, max_d2, iters)
-    per_iter = max(tk - t1, 0.0) / (iters - 1)
-    return t1 + (N_ITER - 1) * per_iter, t1 + tk, nq // iters, cores, kind
-
-
-def cpu_sample(src, tgt, max_d2, iters):
-    """The oracle's whole registration loop for `iters` iterations on all host threads."""
+def port_registration(src, tgt, max_d2, iters, threads):
+    """The oracle's whole registration loop (kind "port") -- only when oracle/_ref is absent."""
     from oracle import oracle as orc
     orc.build()
-    orc.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
+    orc.set_num_threads(threads)
     cfg = orc.Config(metric=1, minimizer=0, max_distance_sq=max_d2, n_iterations=iters)
     t0 = time.perf_counter()
-    rc, pose, hist, nq = orc.estimate_pose(cfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
-    dt = time.perf_counter() - t0
-    return dt, nq, orc.num_threads()
+    orc.estimate_pose(cfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    return time.perf_counter() - t0
+
+
+def cpu_registration(src, tgt, max_d2, iters, threads):
+    """(seconds, kind) of one CPU registration of `iters` iterations."""
+    dt = ref_registration(src, tgt, max_d2, iters, threads)
+    if dt is not None:
+        return dt, "reference"
+    return port_registration(src, tgt, max_d2, iters, threads), "port"
+
+
+def cpu_baseline_block(src, tgt, max_d2):
+    """cpu_baseline of the GPU arm's line: one full registration on all host threads (the value), a bounded 1-thread sample, and
+    the FLANN-like approximate matcher with its match rate."""
+    cores = host_threads()
+    dt, kind = cpu_registration(src, tgt, max_d2, N_ITER, cores)
+    out = {"value": 1.0 / dt, "unit": "reg/s", "cores": cores, "kind": kind, "seconds": dt,
+           "sample": f"one full {N_ITER}-iteration registration of the same {len(src)}-point pair (index build included), exact kd-tree matcher on "
+                     f"{cores} OpenMP threads, the rest of the loop single-threaded as in the reference"}
+    # the reference is single-threaded apart from Ceres (no OpenMP flag, CMakeLists.txt:50-63): 1-thread figure from a bounded sample
+    t1, _ = cpu_registration(src, tgt, max_d2, 1, 1)
+    t2, _ = cpu_registration(src, tgt, max_d2, 2, 1)
+    one = t1 + (N_ITER - 1) * max(t2 - t1, 0.0)
+    out["one_core"] = {"value": 1.0 / one, "unit": "reg/s", "cores": 1, "seconds_estimated": one,
+                       "sample": f"bounded: a 1-iteration ({t1:.2f} s) and a 2-iteration ({t2:.2f} s) run on one thread, extended to {N_ITER} iterations "
+                                 "(index build counted once)"}
+    try:
+        from oracle import flann_like
+        if flann_like.available():
+            r = flann_like.register_p2plane(src, tgt, max_d2, 3)
+            per_it = statistics.mean(r["seconds_per_iteration"])
+            est = r["seconds_build"] + N_ITER * per_it
+            out["flann_like"] = {"value": 1.0 / est, "unit": "reg/s", "cores": 1, "seconds_estimated": est, "seconds_per_iteration": per_it,
+                                 "match_rate_vs_exact": r["match_rate"], "matched_fraction_exact": r["matched_fraction"],
+                                 "sample": "bounded: 3 iterations of the same pair with cv2.flann_Index(KDTREE, trees=1), checks=16 -- the stand-in for "
+                                           "FLANN 1.8.4 KDTreeIndexParams(1) / SearchParams(16) (NearestNeighbor.h:136,172-174) -- extended to 30 iterations"}
+    except Exception as e:   # noqa: BLE001
+        out["flann_like"] = {"unavailable": str(e)}
+    return out
 
 
 def run_reference(args):
@@ -190,24 +243,24 @@ def run_reference(args):
     if rank != 0:
         return 0
     src, tgt = make_pair(0, args.sweeps, args.beams)
-    iters = args.cpu_iters
-    if os.environ.get("OMP_NUM_THREADS") == "1":      # torchrun exports 1; the baseline may use every host core
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_baseline_sample(src, tgt, args.max_dist2, 1)
-    times, nq, cores, kind = [], 0, 1, "port"
+    cores = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)          # torchrun exports 1; the baseline may use every host core
+    kind = "port"
+    for _ in range(args.warmup):
+        _, kind = cpu_registration(src, tgt, args.max_dist2, N_ITER, cores)
+    times = []
     for _ in range(args.steps):
-        dt, _, nq, cores, kind = cpu_registration_seconds(src, tgt, args.max_dist2, iters)
+        dt, kind = cpu_registration(src, tgt, args.max_dist2, N_ITER, cores)
         times.append(dt)
     per_reg = statistics.mean(times)
     value = 1.0 / per_reg
-    sample = (f"per step: a 1-iteration and a {max(iters, 2)}-iteration run of the same {len(src)}-point pair, extrapolated to {N_ITER} iterations "
-              f"(index build counted once)")
+    sample = (f"every step = one full {N_ITER}-iteration registration of the same {len(src)}-point pair (index build included); exact kd-tree "
+              f"matcher on {cores} OpenMP threads, the rest of the loop single-threaded as in the reference")
     line = {"impl": "reference", "metric": "icp_registrations_per_s", "value": value, "unit": "reg/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_reg * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(len(src), len(tgt), args.max_dist2),
-            "mcorr_per_s": nq * N_ITER / per_reg / 1e6,
+            "mcorr_per_s": len(src) * N_ITER / per_reg / 1e6,
             "cpu_baseline": {"value": value, "unit": "reg/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "reg/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": ("reference's own estimatePose compiled in place (oracle/_ref); Eigen/FLANN absent: exact kd-tree matcher on all host threads "
@@ -215,6 +268,130 @@ def run_reference(args):
                      if kind == "reference" else "oracle/_ref absent: oracle port, exact kd-tree instead of FLANN's approximate search")}
     print(json.dumps(line))
     return 0
+
+
+# ----------------------------------------------------------------------------- multi-GPU workloads (config 5)
+def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
+    """Config 5a: the 44 pairs of an ETH-Apartment-shaped sequence dealt round-robin (parallel.shard_pairs) to the ranks; every
+    rank runs its queue through sequence.alignPairs (host arrays in, poses out, two contexts per GPU so that the upload of pair
+    k+1 overlaps the loop of pair k).  No collective on the data path; time = CUDA events around the queue, max over ranks."""
+    from icp_variants_b200 import parallel, sequence
+    mine = parallel.shard_pairs(N_SEQUENCE_PAIRS, world, rank)
+    t0 = time.perf_counter()
+    pairs = [make_pair_device_normals(ctx, k, args.sweeps, args.beams) for k in mine]
+    t_gen = time.perf_counter() - t0
+    cfg = capi.default_config()
+    cfg.metric, cfg.minimizer, cfg.matching, cfg.n_iterations = 1, 0, 0, N_ITER
+    cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = args.max_dist2, 2, 0
+    second = capi.Context(dev.index)
+    second.set_stream(stream.cuda_stream)
+    ctxs = [ctx, second]
+    ms = None
+    for rep in range(2):                                   # the first pass warms allocations and graphs
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = sequence.alignPairs(ctxs, pairs, cfg)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+    second.close()
+    ok = all(r is not None and r.error is None and r.nIterations == N_ITER for r in res)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        o = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(o, op=dist.ReduceOp.MIN)
+        ok = bool(o.item())
+    longest = -(-N_SEQUENCE_PAIRS // world)
+    return {"pairs": N_SEQUENCE_PAIRS, "n_gpus": world, "pairs_per_s": N_SEQUENCE_PAIRS / (ms * 1e-3), "ms_total": ms,
+            "pairs_on_the_longest_queue": longest, "ideal_speedup_over_one_gpu": N_SEQUENCE_PAIRS / longest, "all_pairs_converged_30_iterations": ok,
+            "points_per_scan": len(pairs[0][0]) if pairs else None, "scaling": "strong", "collective": "none",
+            "path": "sequence.alignPairs: icp_gpu_set_target / set_source (host arrays) + icp_gpu_estimate_pose_async / _finish, two contexts per GPU",
+            "input_generation_s_rank0": t_gen}
+
+
+def sharded_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
+    """Config 5b: one 3 M-point pair, the source sharded by points over the ranks (every rank holds the whole target).  Fused: the
+    per-iteration all-reduce of the <= 28-double row runs inside reduce_kernel over NVLink peer memory (icp_gpu_peer_*), the loop
+    stays one CUDA graph.  Baseline: the same shards with ncclAllReduce on the stream between the two halves of the iteration."""
+    from icp_variants_b200 import parallel
+    sweeps, beams = args.big_sweeps, args.big_beams
+    src, tgt = make_pair_device_normals(ctx, 0, sweeps, beams)
+    cfg = capi.default_config()
+    cfg.metric, cfg.minimizer, cfg.matching, cfg.n_iterations = 1, 0, 0, N_ITER
+    cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = args.max_dist2, 2, 0
+    ctx.set_config(cfg)
+    ctx.set_target(tgt.points, tgt.normals, tgt.colors)
+    out = {"n_points": int(len(src)), "n_gpus": world, "iterations": N_ITER}
+
+    def timed(fn, reps=3):
+        best, res = None, None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            res = fn()
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            best = ms if best is None else min(best, ms)
+        return best, res
+
+    # one GPU alone (rank 0), whole source: the time the sharded forms are compared with
+    pose_single = None
+    if rank == 0:
+        ctx.set_source(src.points, src.normals, src.colors)
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            pose_single, _, _ = ctx.estimate_pose(want_history=False)
+            e1.record(stream); e1.synchronize()
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        out["ms_single_gpu"] = best
+    if world == 1:
+        out["note"] = "N = 1: the unsharded registration (index already built, clouds resident); run with --gpus 2/4/8 for the sharded forms"
+        return out
+    dist.barrier()
+    sl = parallel.shard_points(len(src), world, rank)
+    ctx.set_source(src.points[sl], src.normals[sl], src.colors[sl])
+    # baseline: ncclAllReduce of the row on the stream, no host round trip
+    ms_nccl, pose_nccl = timed(lambda: parallel.register_sharded_on_stream(ctx, N_ITER))
+    # fused: exchange inside the reduction kernel over peer memory
+    parallel.attach_peers(ctx)
+    ms_fused, r = timed(lambda: ctx.estimate_pose(want_history=False))
+    pose_fused = r[0]
+    poses = [None] * world
+    dist.all_gather_object(poses, pose_fused.tobytes())
+    ctx.peer_detach()
+    # what one exchange costs: the same loop on a tiny source (1024 points per rank), attached vs. detached
+    tiny = slice(sl.start, sl.start + 1024)
+    ctx.set_source(src.points[tiny], src.normals[tiny], src.colors[tiny])
+    ms_tiny_alone, _ = timed(lambda: ctx.estimate_pose(want_history=False))
+    parallel.attach_peers(ctx)
+    ms_tiny_fused, _ = timed(lambda: ctx.estimate_pose(want_history=False))
+    ctx.peer_detach()
+    out.update(ms_fused_peer_memory=ms_fused, ms_nccl_allreduce_on_stream=ms_nccl,
+               exchange_bytes_per_iteration_per_peer=27 * 8, exchange_us_per_iteration=(ms_tiny_fused - ms_tiny_alone) * 1e3 / N_ITER,
+               pose_identical_on_all_ranks=bool(all(p == poses[0] for p in poses)),
+               path="icp_gpu_peer_export / _attach + icp_gpu_estimate_pose (one CUDA graph per rank, exchange inside reduce_kernel)")
+    if rank == 0:
+        out["speedup_fused_over_single_gpu"] = out["ms_single_gpu"] / ms_fused
+        out["speedup_nccl_over_single_gpu"] = out["ms_single_gpu"] / ms_nccl
+        out["max_abs_pose_diff_fused_vs_single_gpu"] = float(np.abs(pose_fused - pose_single).max())
+        out["max_abs_pose_diff_nccl_vs_single_gpu"] = float(np.abs(pose_nccl - pose_single).max())
+    return out
 
 
 def main():
@@ -225,9 +402,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sweeps", type=int, default=344)
     ap.add_argument("--beams", type=int, default=1077)
+    ap.add_argument("--big-sweeps", type=int, default=1720, help="config 5b: sweeps of the point-sharded pair (1720 x 1744 ~ 3 M points)")
+    ap.add_argument("--big-beams", type=int, default=1744)
     ap.add_argument("--max-dist2", type=float, default=10.0, help="squared matching distance; alignETH uses 10 (main.cpp:361)")
-    ap.add_argument("--cpu-iters", type=int, default=3, help="iterations per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="skip the config-5 workloads (pair_queue_44, sharded_3m)")
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -318,7 +497,6 @@ def main():
     total_ms, launches, pose = timed(step_resident, args.steps, args.warmup)
     e2e_ms, _, pose_e2e = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    launches_per_step = launches // (args.steps * world)
 
     # per-kernel timing of the dominant kernel: one extra registration, launch by launch with CUDA events
     ctx.set_target_dev(d["tp"].data_ptr(), d["tn"].data_ptr(), d["tc"].data_ptr(), nt)
@@ -331,13 +509,18 @@ def main():
     ctx.set_target_dev(d["tp"].data_ptr(), d["tn"].data_ptr(), d["tc"].data_ptr(), nt)
     ctx.set_source_dev(d["sp"].data_ptr(), d["sn"].data_ptr(), d["sc"].data_ptr(), ns)
     ctx.estimate_pose(want_history=False)
-    st_t = ctx.stats()
-    st = st_t
+    st = ctx.stats()
+    cfg.collect_stats = 0
+    ctx.set_config(cfg)
     match_ms = tm.matching_ms / N_ITER
     prep_ms = tm.search_prep_ms / N_ITER
     walk_ms = max(match_ms - prep_ms, 1e-6)          # knn_bvh_kernel alone (the dominant kernel)
     solve_ms = tm.solver_ms / N_ITER
+    # the FP32 denominators, measured on this device in this run (peak.cu)
+    ffma_tflops = ctx.measure_fp32_peak(0)
+    nonfma_tflops = ctx.measure_fp32_peak(1)
 
+    line = None
     if rank == 0:
         peak, peak_kind = load_peaks()
         regs = args.steps * world
@@ -346,36 +529,47 @@ def main():
         # matched target point 12 + target normal 12 = 48 B
         alg_bytes = 48.0 * ns
         achieved = alg_bytes / (walk_ms * 1e-3) / 1e9
-        evals_per_launch = st_t.n_distance_evals / N_ITER
+        evals_per_launch = st.n_distance_evals / N_ITER
+        search_tflops = evals_per_launch * 8 / (match_ms * 1e-3) / 1e12
         line = {
             "metric": "icp_registrations_per_s", "value": value, "unit": "reg/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": dict(workload_config(ns, nt, args.max_dist2),
-                           l2="flushed between timed steps (256 MB write)" if flush is not None else "not flushed"),
+            "config": workload_config(ns, nt, args.max_dist2),
             "ms_per_registration": total_ms / args.steps,
             "mcorr_per_s": (st.n_queries * regs) / (total_ms * 1e-3) / 1e6,
             "e2e": {"value": regs / (e2e_ms * 1e-3), "unit": "reg/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int((ns + nt) * 28 + 64 + 32 * N_ITER), "d2h_bytes_per_step": int(64 + 16 * 4 * N_ITER + 1024)},
             "gpu_launches": launches,
+            "gpu_launches_per_step": launches // max(args.steps * world, 1),
             "roofline": {"kernel": "knn_bvh_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic("knn_bvh_kernel"), "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": walk_ms,
                          "note": "issue-bound tree search over L2-resident clouds; see roofline_fp32"},
-            "roofline_fp32": {"kernel": "knn_bvh_kernel<false>", "distance_evals_per_launch": evals_per_launch,
-                              "gevals_per_s": evals_per_launch / (match_ms * 1e-3) / 1e9, "flop_per_eval": 8,
-                              "tflops": evals_per_launch * 8 / (match_ms * 1e-3) / 1e12, "kernels": "knn_prep_kernel (fast path) + knn_bvh_kernel (walk)", "nodes_per_launch": st_t.n_nodes_visited / N_ITER,
-                              "matched_per_launch": st_t.n_matched / N_ITER},
-            "stage_ms_per_iteration": {"match": match_ms, "match_prep_fast_path": prep_ms, "match_tree_walk": walk_ms, "reduce_solve": solve_ms, "index_build": tm.index_ms},
+            "roofline_fp32": {"kernels": "knn_prep_kernel (fast path) + knn_bvh_kernel (walk)", "distance_evals_per_launch": evals_per_launch,
+                              "gevals_per_s": evals_per_launch / (match_ms * 1e-3) / 1e9, "flop_per_eval": 8, "tflops": search_tflops,
+                              "peak_ffma_tflops_measured": ffma_tflops, "peak_fmul_fadd_tflops_measured": nonfma_tflops,
+                              "frac_of_measured_non_fma_peak": search_tflops / nonfma_tflops if nonfma_tflops > 0 else None,
+                              "frac_of_measured_ffma_peak": search_tflops / ffma_tflops if ffma_tflops > 0 else None,
+                              "nodes_per_launch": st.n_nodes_visited / N_ITER, "matched_per_launch": st.n_matched / N_ITER,
+                              "note": "contract D1 forbids FMA contraction in the distances: the non-FMA figure is the attainable one"},
+            "stage_ms_per_iteration": {"match": match_ms, "match_prep_fast_path": prep_ms, "match_tree_walk": walk_ms, "reduce_solve": solve_ms,
+                                       "index_build": tm.index_ms},
             "clocks": clocks,
             "pose_checksum": float(np.abs(pose).sum()),
         }
         if not args.no_cpu_baseline and world == 1:
-            per_reg, dt, nq, cores, kind = cpu_registration_seconds(src, tgt, args.max_dist2, args.cpu_iters)
-            line["cpu_baseline"] = {"value": 1.0 / per_reg, "unit": "reg/s", "cores": cores, "kind": kind,
-                                    "sample": (f"a 1-iteration and a {max(args.cpu_iters, 2)}-iteration run of the same pair, extrapolated to {N_ITER} iterations "
-                                               f"(index build counted once)"),
-                                    "seconds": dt}
+            line["cpu_baseline"] = cpu_baseline_block(src, tgt, args.max_dist2)
+            fl = line["cpu_baseline"].get("flann_like", {})
+            if "match_rate_vs_exact" in fl:
+                line["flann_match_rate"] = fl["match_rate_vs_exact"][0]
+    if not args.no_multi:
+        pq = pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args)
+        sh = sharded_block(torch, dist, capi, ctx, stream, world, rank, dev, args)
+        if rank == 0:
+            line["pair_queue_44"] = pq
+            line["sharded_3m"] = sh
+    if rank == 0:
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -107,6 +107,7 @@ def lib():
             "icp_gpu_estimate_pose_async": (C.c_int, [vp, pf]),
             "icp_gpu_estimate_pose_finish": (C.c_int, [vp, pf, pf, C.POINTER(i32)]),
             "icp_gpu_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+            "icp_gpu_measure_fp32_peak": (C.c_int, [vp, i32, C.POINTER(C.c_double)]),
             "icp_gpu_cloud_from_depth": (C.c_int, [vp, pf, pf, pf, pf, u32, u32, C.c_int, u32, C.c_float, C.c_int, pf, pf, pf, C.POINTER(i64)]),
             "icp_gpu_target_normals": (C.c_int, [vp, i32, pf, pf, pf]),
             "icp_gpu_set_correspondences": (C.c_int, [vp, pf, pf, i64]),
@@ -330,6 +331,12 @@ class Context:
         n = C.c_int32(0)
         self._check(lib().icp_gpu_convergence_errors(self._h, _ptr(rm), _ptr(be), cap, C.byref(n)))
         return rm[:n.value].copy(), (be[:n.value].copy() if benchmark else None)
+
+    def measure_fp32_peak(self, mode: int = 0) -> float:
+        """Measured non-tensor FP32 throughput of the device in TFLOP/s: mode 0 FFMA, 1 FMUL+FADD pairs."""
+        t = C.c_double(0.0)
+        self._check(lib().icp_gpu_measure_fp32_peak(self._h, int(mode), C.byref(t)))
+        return float(t.value)
 
     def stats(self) -> Stats:
         s = Stats()

@@ -1070,6 +1070,14 @@ int icp_gpu_estimate_pose(icp_gpu_ctx* ctx, float pose_inout[16], float* pose_hi
     return finish_registration(ctx, pose_inout, pose_history, n_iterations_out);
 }
 
+int icp_gpu_measure_fp32_peak(icp_gpu_ctx* ctx, int32_t mode, double* tflops_out) {
+    if (!ctx || !tflops_out || mode < 0 || mode > 1) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    CU(icp_measure_fp32_peak(mode, ctx->n_sms, ctx->stream, tflops_out));
+    return ICP_GPU_OK;
+}
+
 int icp_gpu_get_stats(icp_gpu_ctx* ctx, icp_gpu_stats* out) {
     if (!ctx || !out) return ICP_GPU_E_ARG;
     *out = ctx->stats;

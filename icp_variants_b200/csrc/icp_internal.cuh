@@ -184,6 +184,8 @@ struct ReduceArgs {
     PeerXchg peer;           // world > 1: the summed row is all-reduced over the peers' mailboxes before the solve
 };
 
+// peak.cu: measured FP32 throughput of the device (mode 0 FFMA, 1 FMUL+FADD), TFLOP/s
+cudaError_t icp_measure_fp32_peak(int mode, int n_sms, cudaStream_t s, double* tflops);
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----
 // AoS3 -> float4 records, the bounding box of the finite points and from it the grid parameters; clears the sort's histograms
 // (scratch: 8 words, [7] = number of points with a non-finite coordinate afterwards)

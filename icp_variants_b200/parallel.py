@@ -59,6 +59,33 @@ def register_sharded(ctx, n_iterations: int, init_pose=None) -> np.ndarray:
     return ctx.iteration_end()
 
 
+class _DeviceRow:
+    """Zero-copy torch view of the context's partial-sum row (icp_gpu_iteration_local_dev) through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def register_sharded_on_stream(ctx, n_iterations: int, init_pose=None) -> np.ndarray:
+    """The same point-sharded registration with the all-reduce as a collective ON THE STREAM (ncclAllReduce of the row where it
+    lies in device memory): local rows -> all-reduce -> solve are enqueued back to back, nothing returns to the host between
+    iterations.  `ctx` must run on torch's current stream (ctx.set_stream).  The baseline the fused peer-memory exchange is
+    measured against."""
+    import torch
+    import torch.distributed as dist
+    pose = np.eye(4, dtype=np.float32) if init_pose is None else init_pose
+    ctx.iteration_begin(pose)
+    views = {}
+    for _ in range(n_iterations):
+        for phase in range(ctx.iteration_phases()):
+            ptr, n = ctx.iteration_local_dev(phase)
+            if (ptr, n) not in views:
+                views[(ptr, n)] = torch.as_tensor(_DeviceRow(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(views[(ptr, n)], op=dist.ReduceOp.SUM)
+            ctx.iteration_apply_dev(phase)
+    return ctx.iteration_end()
+
+
 def gather_peer_handles(handle: bytes) -> list[bytes]:
     """Every rank's mailbox handle in rank order (the collective that doubles as the export -> attach barrier)."""
     import torch.distributed as dist

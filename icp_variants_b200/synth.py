@@ -142,7 +142,7 @@ def pca_normals(points: np.ndarray, viewpoint, k=5) -> np.ndarray:
 
 
 def lidar_scan(room: Room, sensor_pos, yaw_deg=0.0, n_sweeps=344, n_beams=1077, noise=0.01, max_range=30.0,
-               seed=0, normals_k=5, colors=None) -> Cloud:
+               seed=0, normals_k=5, colors=None, normals_fn=None) -> Cloud:
     """ETH 'Challenging data sets'-like tilting 2-D lidar: n_sweeps tilt steps (-45..+45 deg) of a
     270-degree, n_beams-beam planar scan (README.md:45-46: ~370k points per scan), range noise
     N(0, noise), expressed in the world frame.  Normals: k=5 PCA towards the sensor; colours
@@ -161,7 +161,8 @@ def lidar_scan(room: Room, sensor_pos, yaw_deg=0.0, n_sweeps=344, n_beams=1077, 
     t = t + rng.normal(0.0, noise, size=t.shape)
     keep = (t > 0.05) & (t < max_range)
     pts = (np.asarray(sensor_pos, np.float64) + dirs[keep] * t[keep, None]).astype(np.float32)
-    nrm = pca_normals(pts, sensor_pos, k=normals_k)
+    # normals_fn(points, viewpoint) -> normals: e.g. the device's k = 5 PCA normals (seconds -> milliseconds for big scans)
+    nrm = normals_fn(pts, np.asarray(sensor_pos, np.float32)) if normals_fn is not None else pca_normals(pts, sensor_pos, k=normals_k)
     if colors == "texture":
         col = procedural_colors(pts)
     else:
@@ -183,7 +184,7 @@ def procedural_colors(points: np.ndarray, seed=99) -> np.ndarray:
     return col
 
 
-def eth_pair(seed=1234, n_sweeps=344, n_beams=1077, noise=0.01, pose_scaling=0.1, colors=None, pair_index=0):
+def eth_pair(seed=1234, n_sweeps=344, n_beams=1077, noise=0.01, pose_scaling=0.1, colors=None, pair_index=0, normals_fn=None):
     """One ETH-Apartment-shaped scan pair as alignETH prepares it (main.cpp:411-429): both scans in a
     common frame, the source then moved by the ground-truth perturbation scaled by 0.1.
     Returns (source Cloud, target Cloud, applied perturbation 4x4)."""
@@ -194,9 +195,9 @@ def eth_pair(seed=1234, n_sweeps=344, n_beams=1077, noise=0.01, pose_scaling=0.1
     p0 = base
     p1 = base + np.array([0.30, 0.20, 0.05])
     tgt = lidar_scan(room, p0, yaw_deg=3.0 * pair_index, n_sweeps=n_sweeps, n_beams=n_beams, noise=noise,
-                     seed=int(rng.integers(1 << 30)), colors=colors)
+                     seed=int(rng.integers(1 << 30)), colors=colors, normals_fn=normals_fn)
     src = lidar_scan(room, p1, yaw_deg=3.0 * pair_index + 5.0, n_sweeps=n_sweeps, n_beams=n_beams, noise=noise,
-                     seed=int(rng.integers(1 << 30)), colors=colors)
+                     seed=int(rng.integers(1 << 30)), colors=colors, normals_fn=normals_fn)
     full_t = np.array([0.30, 0.20, 0.05])
     full_a = np.array([2.0, 1.0, 5.0])
     pert = make_pose(pose_scaling * full_t, pose_scaling * full_a)

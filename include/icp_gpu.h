@@ -191,6 +191,10 @@ int icp_gpu_estimate_pose_async(icp_gpu_ctx* ctx, const float pose_in[16]);
 int icp_gpu_estimate_pose_finish(icp_gpu_ctx* ctx, float pose_out[16], float* pose_history, int32_t* n_iterations_out);
 
 int icp_gpu_get_stats(icp_gpu_ctx* ctx, icp_gpu_stats* out);
+/* The FP32 (non-tensor) roofline denominator of the context's device, measured with a register-resident microbenchmark on
+ * the context's stream (the reference has no counterpart): mode 0 = FFMA (2 flop / instruction), mode 1 =
+ * FMUL + FADD pairs (the un-fused arithmetic contract D1 prescribes for squared distances).  TFLOP/s. */
+int icp_gpu_measure_fp32_peak(icp_gpu_ctx* ctx, int32_t mode, double* tflops_out);
 
 /* ---- either side of the loop -------------------------------------------------------
  * icp_gpu_cloud_from_depth = PointCloud(float* depthMap, BYTE* colorFrame, const Matrix3f& depthIntrinsics,

@@ -232,6 +232,15 @@ def estimate_pose(minimizer, metric, src, src_n, src_c, tgt, tgt_n, tgt_c, gt_sr
     return n, _unpose(pose), hist[:max(n, 0)].copy()
 
 
+def set_num_threads(n: int):
+    """Threads of the stand-in matcher's OpenMP loop (everything else in the reference's loop is single-threaded)."""
+    lib().ref_set_num_threads(C.c_int(int(n)))
+
+
+def num_threads() -> int:
+    return int(lib().ref_num_threads())
+
+
 def set_flann_exhaustive(on: bool):
     """Answer the FLANN stand-in's searches by the literal O(N*M) scan instead of its exact kd-tree (same results)."""
     lib().ref_set_flann_exhaustive(C.c_int(int(on)))

@@ -11,6 +11,9 @@
 //
 // No reference source is copied: the headers are #included by path at build time.
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cassert>
 #include <cmath>
 #include <cstdint>
@@ -273,6 +276,22 @@ int ref_estimate_pose(const ref_config* cfg,
         if (stage_times_out) { stage_times_out[0] = tm.selectionTime; stage_times_out[1] = tm.matchingTime; stage_times_out[2] = tm.weighingTime; stage_times_out[3] = tm.rejectionTime; stage_times_out[4] = tm.solverTime; stage_times_out[5] = tm.convergenceTime; }
         return n_it;
     } catch (const ref_assert_failure&) { return -2; }
+}
+
+// threads of the stand-in matcher's OpenMP loop (the reference's own loop is single-threaded apart from Ceres)
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : 1);
+#else
+    (void)n;
+#endif
+}
+int ref_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }
 
 // test hook: answer FLANN searches by the literal O(N*M) scan instead of the exact kd-tree (identical results)
