@@ -273,8 +273,8 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- multi-GPU workloads (config 5)
 def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     """Config 5a: the 44 pairs of an ETH-Apartment-shaped sequence dealt round-robin (parallel.shard_pairs) to the ranks; every
-    rank runs its queue through sequence.alignPairs (host arrays in, poses out, two contexts per GPU so that the upload of pair
-    k+1 overlaps the loop of pair k).  No collective on the data path; time = CUDA events around the queue, max over ranks."""
+    rank runs its queue through sequence.alignPairs (host arrays in, poses out, three contexts per GPU so that the upload and the
+    loops of different pairs overlap).  No collective on the data path; time = CUDA events around the queue, max over ranks."""
     from icp_variants_b200 import parallel, sequence
     mine = parallel.shard_pairs(N_SEQUENCE_PAIRS, world, rank)
     t0 = time.perf_counter()
@@ -283,21 +283,25 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     cfg = capi.default_config()
     cfg.metric, cfg.minimizer, cfg.matching, cfg.n_iterations = 1, 0, 0, N_ITER
     cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = args.max_dist2, 2, 0
-    second = capi.Context(dev.index)
-    second.set_stream(stream.cuda_stream)
-    ctxs = [ctx, second]
+    # Three contexts per GPU, each on its own stream: the registrations of different pairs overlap on the device (a single
+    # registration is a chain of latency-bound launches that leaves most of the machine idle: 5.0 -> 2.7 ms per pair, measured with
+    # profiles/probe_pair_queue.py), and the upload of the next pair overlaps the loops of the others.
+    ctxs = [capi.Context(dev.index) for _ in range(3)]
     ms = None
     for rep in range(2):                                   # the first pass warms allocations and graphs
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        res = sequence.alignPairs(ctxs, pairs, cfg)
+        e0.record(stream)                                  # the stream is idle: the events bracket the queue, which ends with every
+        res = sequence.alignPairs(ctxs, pairs, cfg)        # context's stream synchronised (estimate_pose_finish)
+        torch.cuda.synchronize()
         e1.record(stream)
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-    second.close()
+    for c in ctxs:
+        c.close()
+    print(f"bench: rank {rank}: pair queue of {len(pairs)} pairs {ms:.1f} ms", file=sys.stderr)
     ok = all(r is not None and r.error is None and r.nIterations == N_ITER for r in res)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -310,7 +314,7 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     return {"pairs": N_SEQUENCE_PAIRS, "n_gpus": world, "pairs_per_s": N_SEQUENCE_PAIRS / (ms * 1e-3), "ms_total": ms,
             "pairs_on_the_longest_queue": longest, "ideal_speedup_over_one_gpu": N_SEQUENCE_PAIRS / longest, "all_pairs_converged_30_iterations": ok,
             "points_per_scan": len(pairs[0][0]) if pairs else None, "scaling": "strong", "collective": "none",
-            "path": "sequence.alignPairs: icp_gpu_set_target / set_source (host arrays) + icp_gpu_estimate_pose_async / _finish, two contexts per GPU",
+            "path": "sequence.alignPairs: icp_gpu_set_target / set_source (pageable host arrays) + icp_gpu_estimate_pose_async / _finish, three contexts (streams) per GPU",
             "input_generation_s_rank0": t_gen}
 
 
@@ -431,7 +435,10 @@ def main():
     ns, nt = len(src), len(tgt)
 
     ctx = capi.Context(local)
-    stream = torch.cuda.current_stream()
+    # One explicit stream for everything: the library's kernels, torch's fills and events, and NCCL's ordering all refer to it
+    # (torch's default stream has handle 0, which icp_gpu_set_stream reads as "the context's own stream").
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)                        # torch.cuda.Event only sees torch's current stream
     cfg = capi.default_config()
     cfg.metric, cfg.minimizer, cfg.matching, cfg.n_iterations = 1, 0, 0, N_ITER

@@ -12,7 +12,8 @@ sweeps, beams = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (
 src, tgt = bench.make_pair(0, sweeps, beams)
 dev = torch.device("cuda", 0)
 ctx = capi.Context(0)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
 d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
      (("sp", src.points), ("sn", src.normals), ("sc", src.colors), ("tp", tgt.points), ("tn", tgt.normals), ("tc", tgt.colors))}

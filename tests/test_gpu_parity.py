@@ -611,6 +611,104 @@ def test_full_size_eth_registration(ctx, full_eth_pair):
     assert np.array_equal(pose, pose3)
 
 
+def test_bench_config_as_run_370k_30_iterations(ctx, full_eth_pair):
+    """BASELINE configs[1] exactly as bench.py runs it -- 370 488 x 370 488 points, k-NN, point-to-plane linear, 30 iterations, max
+    distance^2 10, rejection on, work counters off (so the fused reduction path) -- against the oracle's free-running loop."""
+    src, tgt, _ = full_eth_pair
+    ocfg = orc.Config(metric=1, max_distance_sq=10.0, n_iterations=30)
+    rc, opose, ohist, _ = orc.estimate_pose(ocfg, src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors)
+    assert rc == 0
+    load(ctx, src, tgt)
+    ctx.set_config(gpu_config(ocfg, nn_algorithm=2, collect_stats=0))
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it == 30
+    worst = max(rot_angle(hist[k], ohist[k]) for k in range(30)), max(float(np.linalg.norm(hist[k][:3, 3] - ohist[k][:3, 3])) for k in range(30))
+    assert pose_close(pose, opose), f"rot {rot_angle(pose, opose):.2e} trans {np.linalg.norm(pose[:3, 3] - opose[:3, 3]):.2e}"
+    assert worst[0] <= ROT_TOL and worst[1] <= TRANS_TOL, worst        # every iteration of the trajectory, not only the last
+
+
+def test_reupload_of_the_same_clouds_gives_identical_bits(ctx, full_eth_pair):
+    """The index is a function of the cloud alone: the radix sort ranks by (cell code, original index) without atomics, so
+    uploading the same pair again (and into a second context) reproduces the correspondences, every pose of the trajectory and
+    hence the fp64 summation order bit for bit."""
+    src, tgt, _ = full_eth_pair
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = 1, 8, 10.0, 2, 0
+    runs = []
+    other = capi.Context(0)
+    try:
+        for c in (ctx, ctx, other):
+            c.set_config(cfg)
+            load(c, src, tgt)                               # a fresh upload + index build every time
+            pose, hist, n_it = c.estimate_pose()
+            idx, w = c.query_matches(pose)
+            runs.append((pose, hist, idx, w))
+    finally:
+        other.close()
+    for pose, hist, idx, w in runs[1:]:
+        assert np.array_equal(pose, runs[0][0]) and np.array_equal(hist, runs[0][1])
+        assert np.array_equal(idx, runs[0][2]) and np.array_equal(w, runs[0][3])
+
+
+def test_config4_full_size_teacher_forced(ctx):
+    """configs[3] at FULL size: 370k-point coloured ETH-shaped pair, multi-resolution + symmetric metric + LM + 6-D colour k-NN +
+    colour weighting.  The device runs the registration; at five poses of ITS OWN trajectory (first, three in between, last) the
+    oracle's stages 2-4 on the level cloud of that iteration must give the same correspondences and weights bit for bit."""
+    src, tgt, _ = synth.eth_pair(seed=1234, colors="texture")
+    assert len(src) == 370488
+    ocfg = orc.Config(metric=2, minimizer=1, weighting=3, color_icp=True, multires=True, max_distance_sq=0.1, n_iterations=6)
+    load(ctx, src, tgt)
+    cfg = gpu_config(ocfg, nn_algorithm=2)
+    ctx.set_config(cfg)
+    pose, hist, n_it = ctx.estimate_pose()
+    assert n_it >= 6 and np.isfinite(pose).all()
+    # the level schedule of ICPOptimizer.h:503-525,634-655: stride halves every iteration until 1
+    stride = orc.coarsest_stride(len(src))
+    strides = []
+    for i in range(n_it):
+        strides.append(stride)
+        if stride > 1:
+            stride = max(stride // 2, 1)
+    tree = orc.KdTree(tgt.points, tgt.colors)
+    poses = [np.eye(4, dtype=np.float32)] + list(hist)
+    flat = capi.default_config()
+    for k in sorted({0, n_it // 4, n_it // 2, 3 * n_it // 4, n_it - 1}):
+        sel = orc.coarse_indices(src.points, src.normals, strides[k])            # PointCloud::getCoarseResolution (PointCloud.h:325-343)
+        om = orc.match_pipeline(ocfg, poses[k], src.points, src.normals, src.colors, tgt.points, tgt.normals, tgt.colors, sel_idx=sel, tree=tree)
+        qcfg = gpu_config(ocfg, nn_algorithm=2); qcfg.multires = 0
+        ctx.set_config(qcfg)
+        idx, w = ctx.query_matches(poses[k], sel_idx=sel)
+        assert_matches_equal(idx, w, om, f"iteration {k} (stride {strides[k]}, {len(sel)} points)")
+        assert (idx >= 0).sum() > 0.3 * len(sel) or strides[k] > 64
+    ctx.set_config(cfg)
+
+
+def test_point_to_point_centred_data_within_1e_5(ctx, small_eth_pair):
+    """Point-to-point against the reference build at the north-star tolerance (1e-5 m): the 3e-5 m this suite allows for that
+    metric on 17 m coordinates is the REFERENCE's own fp32 Procrustes noise (means and the 3x3 moment accumulated in fp32,
+    t = R(mean_d - mean_s) - R mean_d + mean_d in fp32, ProcrustesAligner.h:13-70) -- with both clouds moved to the origin
+    (coordinates within a few metres of 0) it disappears and the fp64-accumulating device agrees within 1e-5."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libicp_ref.so not built")
+    src, tgt, _ = small_eth_pair
+    c0 = tgt.points[np.isfinite(tgt.points).all(1)].mean(0)
+    sp, tp = (src.points - c0).astype(np.float32)[::2], (tgt.points - c0).astype(np.float32)[::2]
+    sn, tn = src.normals[::2], tgt.normals[::2]
+    z = np.zeros((len(sp), 4), np.uint8); zt = np.zeros((len(tp), 4), np.uint8)
+    cfg = capi.default_config()
+    cfg.metric, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm = 0, 4, 0.5, 2
+    ctx.set_config(cfg)
+    ctx.set_target(tp, tn, zt); ctx.set_source(sp, sn, z)
+    pose, hist, n_it = ctx.estimate_pose()
+    prev = np.eye(4, dtype=np.float32)
+    for k in range(n_it):
+        n, pr, _ = R.estimate_pose(0, 0, sp, sn, z, tp, tn, zt, sp[:4], tp[:4], n_iterations=1, max_distance_sq=0.5, init_pose=prev)
+        assert n == 1
+        assert rot_angle(pr, hist[k]) < 1e-5 and np.abs(pr[:3, 3] - hist[k][:3, 3]).max() < 1e-5, (k, rot_angle(pr, hist[k]), np.abs(pr[:3, 3] - hist[k][:3, 3]).max())
+        prev = hist[k]
+
+
 def test_full_size_tum_projective_bit_exact(ctx):
     """configs[2]: 640x480 frames, projective matching, normals weighting: correspondences bit-exact vs the oracle."""
     src, tgt, k, _ = synth.tum_pair(seed=1234, frame_gap=10)
