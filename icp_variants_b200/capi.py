@@ -108,6 +108,11 @@ def lib():
             "icp_gpu_estimate_pose_finish": (C.c_int, [vp, pf, pf, C.POINTER(i32)]),
             "icp_gpu_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
             "icp_gpu_measure_fp32_peak": (C.c_int, [vp, i32, C.POINTER(C.c_double)]),
+            "icp_gpu_alignment_error": (C.c_int, [vp, pf, pf, C.POINTER(C.c_double)]),
+            "icp_gpu_transform_points": (C.c_int, [vp, pf, pf, i64, pf]),
+            "icp_gpu_transform_normals": (C.c_int, [vp, pf, pf, i64, pf]),
+            "icp_gpu_apply_weights": (C.c_int, [vp, i32, C.c_float, pf, pf, pf, i64, pf, pf, pf, i64, pf, pf]),
+            "icp_gpu_solve_linear": (C.c_int, [vp, i32, pf, pf, pf, pf, pf, i64, pf]),
             "icp_gpu_cloud_from_depth": (C.c_int, [vp, pf, pf, pf, pf, u32, u32, C.c_int, u32, C.c_float, C.c_int, pf, pf, pf, C.POINTER(i64)]),
             "icp_gpu_target_normals": (C.c_int, [vp, i32, pf, pf, pf]),
             "icp_gpu_set_correspondences": (C.c_int, [vp, pf, pf, i64]),
@@ -324,6 +329,12 @@ class Context:
         """Every point of the resident source against itself under a ground-truth pose (main.cpp:300-307)."""
         self._check(lib().icp_gpu_set_correspondences_pose(self._h, _ptr(pose_to_c(gt_pose))))
 
+    def alignment_error(self, pose, benchmark: bool = False):
+        """(rmse, benchmark error | None) of one pose over the correspondences set before (ConvergenceMeasure.h:50-66, :104-151)."""
+        r = np.zeros(1, np.float32); b = C.c_double(0.0)
+        self._check(lib().icp_gpu_alignment_error(self._h, _ptr(pose_to_c(pose)), _ptr(r), C.byref(b) if benchmark else None))
+        return float(r[0]), (float(b.value) if benchmark else None)
+
     def convergence_errors(self, benchmark: bool = False):
         """(rmse per iteration, benchmark error per iteration | None) of the last registration, computed on the device."""
         cap = self.max_iterations()
@@ -331,6 +342,35 @@ class Context:
         n = C.c_int32(0)
         self._check(lib().icp_gpu_convergence_errors(self._h, _ptr(rm), _ptr(be), cap, C.byref(n)))
         return rm[:n.value].copy(), (be[:n.value].copy() if benchmark else None)
+
+    # -- the reference API's value-level operations (utils.h, weighting.h, ProcrustesAligner.h / the linear solvers)
+    def transform_points(self, pose, xyz):
+        p = _f32(xyz, 3); out = np.empty_like(p)
+        self._check(lib().icp_gpu_transform_points(self._h, _ptr(pose_to_c(pose)), _ptr(p), len(p), _ptr(out)))
+        return out
+
+    def transform_normals(self, pose, nrm):
+        p = _f32(nrm, 3); out = np.empty_like(p)
+        self._check(lib().icp_gpu_transform_normals(self._h, _ptr(pose_to_c(pose)), _ptr(p), len(p), _ptr(out)))
+        return out
+
+    def apply_weights(self, weighting, max_distance_sq, src_xyz, src_nrm, src_rgba, tgt_xyz, tgt_nrm, tgt_rgba, idx, weight):
+        sp, tp = _f32(src_xyz, 3), _f32(tgt_xyz, 3)
+        sn = None if src_nrm is None else _f32(src_nrm, 3); tn = None if tgt_nrm is None else _f32(tgt_nrm, 3)
+        sc = None if src_rgba is None else np.ascontiguousarray(src_rgba, np.uint8); tc = None if tgt_rgba is None else np.ascontiguousarray(tgt_rgba, np.uint8)
+        i = np.ascontiguousarray(idx, np.int32); w = np.ascontiguousarray(weight, np.float32).copy()
+        self._check(lib().icp_gpu_apply_weights(self._h, int(weighting), float(max_distance_sq), _ptr(sp), _ptr(sn), _ptr(sc), len(sp), _ptr(tp), _ptr(tn),
+                                                _ptr(tc), len(tp), _ptr(i), _ptr(w)))
+        return w
+
+    def solve_linear(self, metric, src_xyz, tgt_xyz, src_nrm=None, tgt_nrm=None, weights=None):
+        s, t = _f32(src_xyz, 3), _f32(tgt_xyz, 3)
+        assert len(s) == len(t)
+        sn = None if src_nrm is None else _f32(src_nrm, 3); tn = None if tgt_nrm is None else _f32(tgt_nrm, 3)
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        out = np.empty(16, np.float32)
+        self._check(lib().icp_gpu_solve_linear(self._h, int(metric), _ptr(s), _ptr(sn), _ptr(t), _ptr(tn), _ptr(w), len(s), _ptr(out)))
+        return pose_from_c(out)
 
     def measure_fp32_peak(self, mode: int = 0) -> float:
         """Measured non-tensor FP32 throughput of the device in TFLOP/s: mode 0 FFMA, 1 FMUL+FADD pairs."""

@@ -106,6 +106,7 @@ struct icp_gpu_ctx {
     DeviceBuf state, desc, mask, match_pos, match_w, match_idx, nn_pos, nn_leaf, qbuf, seedbuf, partials, pose_dev, history;
     DeviceBuf nrm_out_dev;
     DeviceBuf prep_in, prep_tmp, prep_out, gt_src, gt_ref, met_partial, met_out;
+    DeviceBuf scratch[16];                                   // operands of the value-level entry points (transform, weights, solve)
     long long n_gt = 0; int last_iters = 0;
     float* h_pose = nullptr; float* h_history = nullptr; DevState* h_state = nullptr;   // pinned
     IterDesc* h_desc = nullptr;                                                       // pinned, DESC_TOTAL
@@ -771,6 +772,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
                          &ctx->nrm_out_dev, &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (DeviceBuf& b : ctx->scratch) if (b.p) cudaFree(b.p);
     if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
     if (ctx->h_history) cudaFreeHost(ctx->h_history);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -976,6 +978,27 @@ int icp_gpu_convergence_errors(icp_gpu_ctx* ctx, float* rmse_out, double* benchm
     ctx->stats.n_kernel_launches += (uint64_t)launches;
     CU(cudaMemcpyAsync(rmse_out, rmse, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (benchmark_out) CU(cudaMemcpyAsync(benchmark_out, bench, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
+}
+
+// rmseAlignmentError(pose) / benchmarkError(pose) (ConvergenceMeasure.h:50-66, :104-151) of ONE pose the caller supplies, over the
+// correspondences set before: the metrics kernels with a one-entry pose history.
+int icp_gpu_alignment_error(icp_gpu_ctx* ctx, const float pose[16], float* rmse_out, double* benchmark_out) {
+    if (!ctx || !pose || !rmse_out) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending; call icp_gpu_estimate_pose_finish first");
+    if (ctx->n_gt <= 0) return fail(ctx, ICP_GPU_E_STATE, "no correspondences set (icp_gpu_set_correspondences)");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    const int nb = icp_metrics_blocks(ctx->n_gt, ctx->n_sms);
+    if (ensure(ctx, ctx->met_partial, (size_t)nb * 6 * sizeof(double)) || ensure(ctx, ctx->met_out, (4 + 12 + 8) + 64) || ensure(ctx, ctx->scratch[15], 64)) return ICP_GPU_E_CUDA;
+    CU(cudaMemcpyAsync(ctx->scratch[15].p, pose, 64, cudaMemcpyHostToDevice, ctx->stream));
+    double* bench = (double*)ctx->met_out.p; float* rmse = (float*)(bench + 1); float* centroid = rmse + 1;
+    int launches = 0;
+    CU(icp_launch_metrics((const float*)ctx->gt_src.p, (const float*)ctx->gt_ref.p, ctx->n_gt, (const float*)ctx->scratch[15].p, 1, nb,
+                          (double*)ctx->met_partial.p, rmse, centroid, benchmark_out ? bench : nullptr, ctx->stream, &launches));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    CU(cudaMemcpyAsync(rmse_out, rmse, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (benchmark_out) CU(cudaMemcpyAsync(benchmark_out, bench, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return ICP_GPU_OK;
 }
@@ -1245,6 +1268,107 @@ int icp_gpu_peer_detach(icp_gpu_ctx* ctx) {
     if (bind(ctx)) return ICP_GPU_E_CUDA;
     CU(cudaStreamSynchronize(ctx->stream));
     peer_close(ctx);
+    return ICP_GPU_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------- value-level operations outside the loop
+namespace {
+// host array -> scratch slot k of the context (nullable in, nullptr out)
+int up(icp_gpu_ctx* ctx, int k, const void* host, size_t bytes, void** dev) {
+    *dev = nullptr;
+    if (!host || bytes == 0) return 0;
+    if (ensure(ctx, ctx->scratch[k], bytes)) return ICP_GPU_E_CUDA;
+    CU(cudaMemcpyAsync(ctx->scratch[k].p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = ctx->scratch[k].p;
+    return 0;
+}
+}  // namespace
+
+static int transform_common(icp_gpu_ctx* ctx, const float pose[16], const float* in, int64_t n, float* out, int normals) {
+    if (!ctx || !pose || n < 0 || (n > 0 && (!in || !out))) return ICP_GPU_E_ARG;
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    if (n == 0) return ICP_GPU_OK;
+    void* din = nullptr;
+    if (up(ctx, 0, in, (size_t)n * 12, &din) || ensure(ctx, ctx->scratch[1], (size_t)n * 12)) return ICP_GPU_E_CUDA;
+    CU(icp_launch_transform((const float*)din, (long long)n, pose, normals, (float*)ctx->scratch[1].p, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+    CU(cudaMemcpyAsync(out, ctx->scratch[1].p, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
+}
+
+extern "C" {
+
+int icp_gpu_transform_points(icp_gpu_ctx* ctx, const float pose[16], const float* xyz_in, int64_t n, float* xyz_out) {
+    return transform_common(ctx, pose, xyz_in, n, xyz_out, 0);
+}
+int icp_gpu_transform_normals(icp_gpu_ctx* ctx, const float pose[16], const float* nrm_in, int64_t n, float* nrm_out) {
+    return transform_common(ctx, pose, nrm_in, n, nrm_out, 1);
+}
+
+int icp_gpu_apply_weights(icp_gpu_ctx* ctx, int32_t weighting, float max_distance_sq, const float* src_xyz, const float* src_nrm, const uint8_t* src_rgba,
+                          int64_t n_src, const float* tgt_xyz, const float* tgt_nrm, const uint8_t* tgt_rgba, int64_t n_tgt, const int32_t* idx,
+                          float* weight_inout) {
+    if (!ctx || n_src < 0 || n_tgt < 0 || (n_src > 0 && (!src_xyz || !idx || !weight_inout)) || (n_tgt > 0 && !tgt_xyz)) return ICP_GPU_E_ARG;
+    if (weighting < 0 || weighting > 3) return fail(ctx, ICP_GPU_E_ARG, "weighting %d", weighting);
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    if (n_src == 0 || weighting == ICP_GPU_WEIGHT_CONSTANT) return ICP_GPU_OK;      // weighting.h:44
+    void *sp, *sn, *sc, *tp, *tn, *tc, *di, *dw;
+    if (up(ctx, 0, src_xyz, (size_t)n_src * 12, &sp) || up(ctx, 1, src_nrm, (size_t)n_src * 12, &sn) || up(ctx, 2, src_rgba, (size_t)n_src * 4, &sc) ||
+        up(ctx, 3, tgt_xyz, (size_t)n_tgt * 12, &tp) || up(ctx, 4, tgt_nrm, (size_t)n_tgt * 12, &tn) || up(ctx, 5, tgt_rgba, (size_t)n_tgt * 4, &tc) ||
+        up(ctx, 6, idx, (size_t)n_src * 4, &di) || up(ctx, 7, weight_inout, (size_t)n_src * 4, &dw)) return ICP_GPU_E_CUDA;
+    CU(icp_launch_apply_weights(weighting, max_distance_sq, (const float*)sp, (const float*)sn, (const unsigned int*)sc, (const float*)tp, (const float*)tn,
+                                (const unsigned int*)tc, (long long)n_tgt, (const int*)di, (float*)dw, (long long)n_src, ctx->stream));
+    ctx->stats.n_kernel_launches += 1;
+    CU(cudaMemcpyAsync(weight_inout, dw, (size_t)n_src * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICP_GPU_OK;
+}
+
+int icp_gpu_solve_linear(icp_gpu_ctx* ctx, int32_t metric, const float* src_xyz, const float* src_nrm, const float* tgt_xyz, const float* tgt_nrm,
+                         const float* weights, int64_t n, float pose_out[16]) {
+    if (!ctx || !pose_out || n < 0 || n > 0x7fffffff / 4 || (n > 0 && (!src_xyz || !tgt_xyz))) return ICP_GPU_E_ARG;
+    if (metric < 0 || metric > 2) return fail(ctx, ICP_GPU_E_ARG, "metric %d", metric);
+    if (metric == ICP_GPU_METRIC_P2PLANE && n > 0 && !tgt_nrm) return fail(ctx, ICP_GPU_E_ARG, "point-to-plane needs the target normals");
+    if (metric == ICP_GPU_METRIC_SYMMETRIC && n > 0 && (!tgt_nrm || !src_nrm)) return fail(ctx, ICP_GPU_E_ARG, "the symmetric metric needs both normals");
+    if (ctx->pending) return fail(ctx, ICP_GPU_E_STATE, "a registration is pending");
+    if (bind(ctx)) return ICP_GPU_E_CUDA;
+    for (int i = 0; i < 16; ++i) pose_out[i] = (i % 5 == 0) ? 1.f : 0.f;
+    if (n == 0) return fail(ctx, ICP_GPU_E_NO_MATCHES, "no correspondences (the reference hangs in ASSERT here, ICPOptimizer.h:668,680,788)");
+    void *s, *sn, *t, *tn, *w;
+    const size_t n1 = (size_t)n;
+    if (up(ctx, 0, src_xyz, n1 * 12, &s) || up(ctx, 1, src_nrm, n1 * 12, &sn) || up(ctx, 2, tgt_xyz, n1 * 12, &t) || up(ctx, 3, tgt_nrm, n1 * 12, &tn) ||
+        up(ctx, 4, weights, n1 * 4, &w)) return ICP_GPU_E_CUDA;
+    for (int k = 8; k < 14; ++k) if (ensure(ctx, ctx->scratch[k], n1 * (k < 12 ? sizeof(float4) : 4))) return ICP_GPU_E_CUDA;
+    const int nb = icp_reduce_blocks((int)n, ctx->n_sms);
+    if (ensure(ctx, ctx->scratch[14], (size_t)nb * ICP_NRED * sizeof(double))) return ICP_GPU_E_CUDA;
+    CU(icp_launch_pack_pairs((const float*)s, (const float*)sn, (const float*)t, (const float*)tn, (const float*)w, (int)n, (float4*)ctx->scratch[8].p,
+                             (float4*)ctx->scratch[9].p, (float4*)ctx->scratch[10].p, (float4*)ctx->scratch[11].p, (int*)ctx->scratch[12].p,
+                             (float*)ctx->scratch[13].p, ctx->stream));
+    // the pairs are already in a common frame: the loop state starts at the identity, the "estimated pose" it ends with is the increment
+    const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    memcpy(ctx->h_pose, eye, sizeof(eye));
+    CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
+    ReduceArgs ra; memset(&ra, 0, sizeof(ra));
+    ra.src_pts = (const float4*)ctx->scratch[8].p; ra.src_nrm = (const float4*)ctx->scratch[9].p; ra.n_src = (int)n;
+    ra.tgt_pts = (const float4*)ctx->scratch[10].p; ra.tgt_nrm = (const float4*)ctx->scratch[11].p; ra.n_tgt = (int)n;
+    ra.match_pos = (const int*)ctx->scratch[12].p; ra.match_w = (const float*)ctx->scratch[13].p;
+    ra.state = (DevState*)ctx->state.p; ra.partials = (double*)ctx->scratch[14].p; ra.pose_history = nullptr;
+    ra.metric = metric; ra.solve = 1; ra.fused = 0; ra.desc_index = -1;
+    int launches = 2;
+    CU(icp_launch_reduce(ra, nb, ctx->stream, &launches));
+    ctx->stats.n_kernel_launches += (uint64_t)launches;
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const DevState& st = *ctx->h_state;
+    if (st.status == ICP_GPU_E_NO_MATCHES) return fail(ctx, ICP_GPU_E_NO_MATCHES, "no finite correspondence");
+    if (st.status != 0) return fail(ctx, st.status, "singular / non-finite system");
+    memcpy(pose_out, st.pose, 16 * sizeof(float));
     return ICP_GPU_OK;
 }
 

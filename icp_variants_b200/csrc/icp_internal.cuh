@@ -184,6 +184,12 @@ struct ReduceArgs {
     PeerXchg peer;           // world > 1: the summed row is all-reduced over the peers' mailboxes before the solve
 };
 
+// standalone.cu: the reference API's value-level operations outside the loop
+cudaError_t icp_launch_transform(const float* in, long long n, const float pose16[16], int normals, float* out, cudaStream_t s);
+cudaError_t icp_launch_apply_weights(int method, float max_d2, const float* sp, const float* sn, const unsigned int* sc, const float* tp, const float* tn,
+                                     const unsigned int* tc, long long n_tgt, const int* idx, float* w, long long n, cudaStream_t s);
+cudaError_t icp_launch_pack_pairs(const float* s, const float* sn, const float* t, const float* tn, const float* w, int n, float4* sp4, float4* sn4,
+                                  float4* tp4, float4* tn4, int* pos, float* wo, cudaStream_t st);
 // peak.cu: measured FP32 throughput of the device (mode 0 FFMA, 1 FMUL+FADD), TFLOP/s
 cudaError_t icp_measure_fp32_peak(int mode, int n_sms, cudaStream_t s, double* tflops);
 // ---- launchers (defined in grid.cu / match.cu / solve.cu / lm.cu) ----

@@ -16,8 +16,11 @@
 #include "Eigen.h"
 #include "NearestNeighbor.h"
 #include "PointCloud.h"
+#include "ProcrustesAligner.h"
 #include "TimeMeasure.h"
+#include "constraints.h"
 #include "selection.h"
+#include "utils.h"
 #include "weighting.h"
 
 class ICPOptimizer {

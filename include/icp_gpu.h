@@ -228,6 +228,29 @@ int icp_gpu_set_correspondences_pose(icp_gpu_ctx* ctx, const float gt_pose[16]);
  * rmse_out[k] = rmseAlignmentError(pose after iteration k) (ConvergenceMeasure.h:50-66); benchmark_out[k]
  * (nullable) = benchmarkError (ConvergenceMeasure.h:104-151).  Evaluated on the device from the pose history. */
 int icp_gpu_convergence_errors(icp_gpu_ctx* ctx, float* rmse_out, double* benchmark_out, int32_t capacity, int32_t* n_out);
+/* rmseAlignmentError(pose) and (nullable) benchmarkError(pose) of one pose the caller supplies (ConvergenceMeasure.h:50-66, :104-151),
+ * over the correspondences set before. */
+int icp_gpu_alignment_error(icp_gpu_ctx* ctx, const float pose[16], float* rmse_out, double* benchmark_out);
+
+/* ---- the reference API's value-level operations, for callers that use them outside estimatePose (the loop runs the same device
+ * functions fused).  Host arrays in and out; each call synchronises the context's stream.
+ *   icp_gpu_transform_points / _normals   transformPoints / transformNormals (utils.h:106-118, :122-133): q = R p + t;
+ *                                         n' = (R^-1)^T n with the 3x3 inverse by cofactors.
+ *   icp_gpu_apply_weights                 WeightingMethod(weighting, max_distance_sq).applyWeights (weighting.h:39-99): per source
+ *                                         point i with idx[i] >= 0 the weight of the pair (i, idx[i]) replaces weight_inout[i];
+ *                                         CONSTANT leaves everything as it is.  The source arrays are the TRANSFORMED ones.
+ *   icp_gpu_solve_linear                  the closed-form minimisers on n matched pairs (source point i <-> target point i, both in
+ *                                         the target's frame): metric 0 ProcrustesAligner::estimatePose (ProcrustesAligner.h:6-29),
+ *                                         1 estimatePosePointToPlane (ICPOptimizer.h:676-782), 2 estimatePoseSymmetricICP (:784-898);
+ *                                         weights nullable (= 1).  pose_out = the increment, column-major.  ICP_GPU_E_NO_MATCHES /
+ *                                         ICP_GPU_E_NUMERIC instead of the reference's ASSERT / NaN pose. */
+int icp_gpu_transform_points(icp_gpu_ctx* ctx, const float pose[16], const float* xyz_in, int64_t n, float* xyz_out);
+int icp_gpu_transform_normals(icp_gpu_ctx* ctx, const float pose[16], const float* nrm_in, int64_t n, float* nrm_out);
+int icp_gpu_apply_weights(icp_gpu_ctx* ctx, int32_t weighting, float max_distance_sq, const float* src_xyz, const float* src_nrm,
+                          const uint8_t* src_rgba, int64_t n_src, const float* tgt_xyz, const float* tgt_nrm, const uint8_t* tgt_rgba,
+                          int64_t n_tgt, const int32_t* idx, float* weight_inout);
+int icp_gpu_solve_linear(icp_gpu_ctx* ctx, int32_t metric, const float* src_xyz, const float* src_nrm, const float* tgt_xyz, const float* tgt_nrm,
+                         const float* weights, int64_t n, float pose_out[16]);
 
 /* Point-sharded registration of one very large pair across ranks (one context per rank, each
  * holding the whole target and its shard of the source).  Per iteration:

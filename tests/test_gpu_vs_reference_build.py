@@ -144,3 +144,35 @@ def test_brute_force_class_thresholds_the_norm_like_the_reference(ctx):
         i0, w0 = R.knn_brute(tgt, qry, max_d)
         assert np.array_equal(idx, i0) and np.array_equal(w, w0)
         assert (idx >= 0).any() and ((idx < 0).any() or max_d > 0.05)
+
+
+def test_value_level_entry_points_equal_reference_functions(ctx, small_eth_pair):
+    """icp_gpu_transform_points / _normals, icp_gpu_apply_weights and icp_gpu_solve_linear -- what the drop-in's transformPoints,
+    WeightingMethod, ProcrustesAligner (include/icp_b200/utils.h, weighting.h, ProcrustesAligner.h) call -- against the reference's own
+    functions: bit-exact transforms and weights, 1e-5 rad / 1e-5 m for the solvers."""
+    src, tgt, _ = small_eth_pair
+    sc, tc = synth.procedural_colors(src.points), synth.procedural_colors(tgt.points)
+    pose = _poses(1)[1]
+    q, qn = ctx.transform_points(pose, src.points), ctx.transform_normals(pose, src.normals)
+    assert np.array_equal(q, R.transform_points(pose, src.points), equal_nan=True)                 # utils.h:106-118
+    assert np.array_equal(qn, R.transform_normals(pose, src.normals), equal_nan=True)              # utils.h:122-133
+    i0, w0 = R.knn_flann(tgt.points, q, 0.5)
+    for method in (0, 1, 2, 3):
+        _, wr = R.apply_weights(method, 0.5, q, qn, sc, tgt.points, tgt.normals, tc, i0, w0)       # weighting.h:39-99
+        wg = ctx.apply_weights(method, 0.5, q, qn, sc, tgt.points, tgt.normals, tc, i0, w0)
+        assert np.array_equal(wg, wr)
+    keep = i0 >= 0
+    s, d, ns, nt = q[keep], tgt.points[i0[keep]], qn[keep], tgt.normals[i0[keep]]
+    w = np.random.default_rng(2).uniform(0.2, 1.0, len(s)).astype(np.float32)
+    c0 = d.mean(0)
+    for metric in (0, 1, 2):
+        # metric 0 on centred coordinates: at 17 m the REFERENCE's fp32 Procrustes (means and moments accumulated in fp32) carries
+        # 3-4e-5 m of translation noise of its own, which the fp64-accumulating device does not reproduce (DESIGN.md, deviations)
+        ss, dd = ((s - c0).astype(np.float32), (d - c0).astype(np.float32)) if metric == 0 else (s, d)
+        rc, pr = R.solve_linear(metric, ss, dd, ns, nt, w)                                         # ProcrustesAligner.h / ICPOptimizer.h:676-898
+        pg = ctx.solve_linear(metric, ss, dd, ns, nt, w)
+        assert rc == 0
+        assert rot_err(pr, pg) < 1e-5 and np.abs(pr[:3, 3] - pg[:3, 3]).max() < 1e-5, (metric, rot_err(pr, pg), np.abs(pr[:3, 3] - pg[:3, 3]).max())
+    with pytest.raises(capi.IcpGpuError) as e:
+        ctx.solve_linear(1, s[:0], d[:0], ns[:0], nt[:0])
+    assert e.value.code == capi.E_NO_MATCHES
