@@ -37,7 +37,8 @@ class Config(C.Structure):
                 ("rejection", C.c_int32), ("max_distance_sq", C.c_float), ("color_icp", C.c_int32), ("multires", C.c_int32),
                 ("pyramid_mode", C.c_int32), ("n_iterations", C.c_int32), ("lm_max_iterations", C.c_int32),
                 ("nn_algorithm", C.c_int32), ("use_graph", C.c_int32), ("collect_stats", C.c_int32),
-                ("weight_max_distance_sq", C.c_float)]
+                ("weight_max_distance_sq", C.c_float), ("early_stop_rotation", C.c_float), ("early_stop_translation", C.c_float),
+                ("reserved_", C.c_int32)]
 
 
 class Timings(C.Structure):

@@ -580,7 +580,7 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
     }
     memcpy(ctx->h_pose, pose_in, 16 * sizeof(float));
     CU(cudaMemcpyAsync(ctx->pose_dev.p, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream));
+    CU(icp_launch_pose_init((DevState*)ctx->state.p, (const float*)ctx->pose_dev.p, ctx->stream, ctx->cfg.early_stop_rotation, ctx->cfg.early_stop_translation));
     ctx->stats.n_kernel_launches += 1;
     rc = refresh_seeds(ctx, algo, true); if (rc) return rc;
 
@@ -717,7 +717,7 @@ void icp_gpu_default_config(icp_gpu_config* cfg) {
     cfg->weighting = ICP_GPU_WEIGHT_CONSTANT; cfg->rejection = 1; cfg->max_distance_sq = 0.0003f;
     cfg->color_icp = 0; cfg->multires = 0; cfg->pyramid_mode = ICP_GPU_PYRAMID_STRIDE; cfg->n_iterations = 20;
     cfg->lm_max_iterations = 10; cfg->nn_algorithm = ICP_GPU_NN_AUTO; cfg->use_graph = 1; cfg->collect_stats = 1;
-    cfg->weight_max_distance_sq = 0.0f;
+    cfg->weight_max_distance_sq = 0.0f; cfg->early_stop_rotation = 0.0f; cfg->early_stop_translation = 0.0f;
 }
 
 int icp_gpu_create(icp_gpu_ctx** out, int device) {
@@ -824,6 +824,7 @@ int icp_gpu_set_config(icp_gpu_ctx* ctx, const icp_gpu_config* c) {
         return fail(ctx, ICP_GPU_E_ARG, "voxel pyramid levels are built on the device: use the device selection stream with them");
     if (c->n_iterations < 0 || c->n_iterations > ICP_MAX_ITERS) return fail(ctx, ICP_GPU_E_ARG, "n_iterations %d (max %d)", c->n_iterations, ICP_MAX_ITERS);
     if (c->lm_max_iterations < 0 || c->lm_max_iterations > 64) return fail(ctx, ICP_GPU_E_ARG, "lm_max_iterations %d", c->lm_max_iterations);
+    if (!(c->early_stop_rotation >= 0.f) || !(c->early_stop_translation >= 0.f)) return fail(ctx, ICP_GPU_E_ARG, "early-stop thresholds must be >= 0");
     if (!(c->weight_max_distance_sq >= 0.f)) return fail(ctx, ICP_GPU_E_ARG, "weight_max_distance_sq %g", (double)c->weight_max_distance_sq);
     if (c->matching == ICP_GPU_MATCH_PROJECTIVE && c->color_icp) return fail(ctx, ICP_GPU_E_ARG, "colour ICP is a k-NN variant (main.cpp:240-243)");
     ctx->cfg = *c;

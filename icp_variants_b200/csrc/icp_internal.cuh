@@ -98,6 +98,9 @@ struct DevState {
     double shard_partials[ICP_NRED];
     unsigned int xchg_seq;   // peer exchanges completed since the mailboxes were attached (never reset by pose_init)
     int pad_xchg;
+    // early stop (icp_gpu_config.early_stop_*; 0 = off): set once an applied increment is smaller than both thresholds; every
+    // later launch of the registration then returns at once
+    float stop_rot, stop_trans; int converged; int pad_stop;
     unsigned long long prof[6];   // ReduceArgs::profile: %globaltimer marks of the last reduction launch (icp_gpu_stats)
 };
 
@@ -255,7 +258,7 @@ struct NormalArgs {
 };
 cudaError_t icp_launch_pca_normals(const NormalArgs& a, cudaStream_t s);
 cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep = nullptr);
-cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s);
+cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s, float stop_rot = 0.f, float stop_trans = 0.f);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);
 // one phase of the point-sharded iteration: the summed row is left in state->shard_partials
 cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase, cudaStream_t s, int* n_launches);
@@ -411,6 +414,17 @@ __device__ __forceinline__ void mat4_identity_dev(float* M) {
 }
 
 
+// Early-stop criterion (the reference always runs all iterations): the increment just applied rotates by no
+// more than stop_rot radians and translates by no more than stop_trans metres.  Off unless both thresholds are positive.
+__device__ __forceinline__ bool increment_is_small(const float* inc, float stop_rot, float stop_trans) {
+    if (!(stop_rot > 0.f) || !(stop_trans > 0.f)) return false;
+    double f = 0.0;     // |R - I|_F = 2 sqrt(2) sin(theta / 2)
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) { const double d = (double)inc[r + 4 * c] - (r == c ? 1.0 : 0.0); f += d * d; }
+    const double theta = 2.0 * asin(fmin(sqrt(f) / (2.0 * sqrt(2.0)), 1.0));
+    const double t = sqrt((double)inc[12] * inc[12] + (double)inc[13] * inc[13] + (double)inc[14] * inc[14]);
+    return theta <= (double)stop_rot && t <= (double)stop_trans;
+}
+
 // estimatedPose = increment * estimatedPose (ICPOptimizer.h:614-620); history as handed to
 // ConvergenceMeasure::recordAlignmentError (:629-631).
 static __device__ void apply_increment(DevState* st, const float* inc, int rc, float* history) {
@@ -423,6 +437,7 @@ static __device__ void apply_increment(DevState* st, const float* inc, int rc, f
             inv_transpose3_pinned(st->pose, st->nrm);
             if (history) for (int i = 0; i < 16; ++i) history[16 * st->iters_done + i] = np[i];
             st->iters_done += 1;
+            if (increment_is_small(inc, st->stop_rot, st->stop_trans)) st->converged = 1;
         }
     }
     st->iter += 1;

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) lm_eval_kernel(const Reduc
     __shared__ double red[ICP_REDUCE_THREADS / 32][32];
     __shared__ double fin[ICP_REDUCE_THREADS / 32][32];
     __shared__ bool is_last;
+    if (a.state->converged) return;                          // early stop reached in an earlier outer iteration
     if (step_index > 0 && a.state->lm_done) return;          // converged earlier in this outer iteration (uniform across the grid)
     if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 41) Nm[threadIdx.x - 32] = a.state->nrm[threadIdx.x - 32];

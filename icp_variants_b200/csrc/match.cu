@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
         p4 = __ldg(&a.src_pts[p]); n4 = __ldg(&a.src_nrm[p]);
         sp_raw = a.nn_pos[p]; leaf_raw = a.nn_leaf[p];          // leaf_raw is meaningless unless sp_raw is a position
     }
+    if (a.desc_index < 0 && a.state_ro->converged) return;   // early stop reached: the remaining launches of the registration are no-ops
     const int desc_i = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[desc_i];
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
     __shared__ unsigned int s_node[BVH_WARPS][BVH_STACK];
     __shared__ float s_lb[BVH_WARPS][BVH_STACK];
     __shared__ BvhDesc s_bvh;
+    if (a.desc_index < 0 && a.state_ro->converged) return;
     if (threadIdx.x < sizeof(BvhDesc) / 4) reinterpret_cast<int*>(&s_bvh)[threadIdx.x] = reinterpret_cast<const int*>(a.bvh)[threadIdx.x];
     __syncthreads();
     const unsigned int FULL = 0xFFFFFFFFu;
@@ -531,6 +533,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
 
 __global__ void __launch_bounds__(256) match_finish_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
+    if (a.desc_index < 0 && a.state_ro->converged) return;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -555,6 +558,7 @@ __global__ void __launch_bounds__(256) match_finish_kernel(const MatchArgs a) {
 template <bool COLOR, bool NORM>
 __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
+    if (a.desc_index < 0 && a.state_ro->converged) return;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int lane = threadIdx.x & 31;
@@ -599,6 +603,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
     __shared__ PoseSm sm;
     __shared__ float4 tile[PROJ_TILE_MAX];
     __shared__ unsigned int s_box[4][PROJ_THREADS / 32];
+    if (a.desc_index < 0 && a.state_ro->converged) return;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

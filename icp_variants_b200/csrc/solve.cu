@@ -246,6 +246,7 @@ __device__ __forceinline__ void finish_row_local(DevState* st, const double* row
                 for (int i = 0; i < 16; ++i) history[16 * lr.iters_done + i] = np[i];
             }
             st->iters_done = lr.iters_done + 1;
+            if (increment_is_small(inc, st->stop_rot, st->stop_trans)) st->converged = 1;
         }
     }
     st->iter = lr.iter + 1;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
     __shared__ double fin[ICP_REDUCE_THREADS / 32][32];
     __shared__ bool is_last;
     unsigned long long t_start = 0, t_loop = 0;
+    if (a.state->converged) return;                          // early stop reached (uniform across the grid)
     if (a.profile && threadIdx.x == 0) { t_start = global_timer_ns(); if (blockIdx.x == 0) a.state->prof[0] = t_start; }
     // the first point's independent loads are requested before the pose / descriptor loads and the barrier
     const int stride = gridDim.x * blockDim.x;
@@ -452,7 +454,7 @@ cudaError_t icp_launch_reduce_phase(const ReduceArgs& a, int n_blocks, int phase
 }
 
 // ---------------------------------------------------------------------------- pose upload / shard apply
-__global__ void pose_init_kernel(DevState* st, const float* pose16) {
+__global__ void pose_init_kernel(DevState* st, const float* pose16, float stop_rot, float stop_trans) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int i = 0; i < 16; ++i) st->pose[i] = pose16[i];
     inv_transpose3_pinned(st->pose, st->nrm);
@@ -460,10 +462,11 @@ __global__ void pose_init_kernel(DevState* st, const float* pose16) {
     st->n_queries = 0; st->n_matched = 0; st->n_evals = 0; st->n_nodes = 0;
     for (int k = 0; k < 3; ++k) { st->mean_s[k] = 0.f; st->mean_d[k] = 0.f; }
     st->lm_done = 0; st->lm_iter = 0;
+    st->stop_rot = stop_rot; st->stop_trans = stop_trans; st->converged = 0;
 }
 
-cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s) {
-    pose_init_kernel<<<1, 32, 0, s>>>(st, pose_dev16);
+cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s, float stop_rot, float stop_trans) {
+    pose_init_kernel<<<1, 32, 0, s>>>(st, pose_dev16, stop_rot, stop_trans);
     return cudaGetLastError();
 }
 

@@ -6,8 +6,12 @@
     TUM depth scaling       VirtualSensor::processFrameIndex           VirtualSensor.h:119-124   (u16 / 5000, 0 -> MINF)
     ETH pair list           ETHDataLoader::getItem + CSVReader         ETHDataLoader.h:50-61, CSVReader.h:27-44
 
-File decoding of PNG / PCD payloads (FreeImage, PCL in the reference) is left to the caller; these functions parse the
-text formats and apply the reference's conventions to already-decoded arrays."""
+    PCD point clouds        pcl::io::loadPCDFile<pcl::PointXYZ>        ETHDataLoader.h:68,87     (ascii and uncompressed binary)
+    PLY point clouds        PointCloud::writeToFile / savePLYFile      PointCloud.h:219-236      (ascii and binary little-endian)
+    PointCloud binary dump  PointCloud::readFromFile                   PointCloud.h:167-217
+
+Decoding of PNG payloads (FreeImage in the reference) is left to the caller; these functions parse the formats and apply the
+reference's conventions to already-decoded arrays."""
 from __future__ import annotations
 
 import numpy as np
@@ -120,3 +124,145 @@ def read_eth_pairs(path: str):
         pose[:3, :4] = np.array([float(x) for x in vec[4:16]], np.float32).reshape(3, 4)
         out.append({"id": vec[0], "source": vec[1], "target": vec[2], "pose": pose})
     return out
+
+
+# --------------------------------------------------------------------------- PCD / PLY / PointCloud dump
+_PCD_NP = {("F", 4): "<f4", ("F", 8): "<f8", ("U", 1): "u1", ("U", 2): "<u2", ("U", 4): "<u4", ("I", 1): "i1", ("I", 2): "<i2", ("I", 4): "<i4"}
+
+
+def read_pcd(path: str):
+    """pcl::io::loadPCDFile<pcl::PointXYZ> (ETHDataLoader.h:68,87): the x / y / z fields of an ascii or uncompressed-binary .pcd as
+    [N,3] float32; NaN rows are kept (PCL keeps them too; the registration treats them as non-finite points).  Also returns a dict
+    of the other fields (e.g. normal_x ..., intensity) as arrays."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    header, pos = {}, 0
+    while True:
+        end = raw.index(b"\n", pos)
+        line = raw[pos:end].decode("ascii", "replace").strip()
+        pos = end + 1
+        if not line or line.startswith("#"):
+            continue
+        key, _, val = line.partition(" ")
+        header[key.upper()] = val.split()
+        if key.upper() == "DATA":
+            break
+    fields, sizes, types = header["FIELDS"], [int(v) for v in header["SIZE"]], header["TYPE"]
+    counts = [int(v) for v in header.get("COUNT", ["1"] * len(fields))]
+    n = int(header["POINTS"][0]) if "POINTS" in header else int(header["WIDTH"][0]) * int(header.get("HEIGHT", ["1"])[0])
+    mode = header["DATA"][0].lower()
+    if mode == "ascii":
+        tok = raw[pos:].split()
+        per = sum(counts)
+        a = np.array(tok[:n * per], dtype=np.float64).reshape(n, per)
+        cols, k = {}, 0
+        for name, c in zip(fields, counts):
+            cols[name] = a[:, k] if c == 1 else a[:, k:k + c]
+            k += c
+    elif mode == "binary":
+        dt = np.dtype([(name, _PCD_NP[(t.upper(), sz)], (c,) if c > 1 else ()) for name, t, sz, c in zip(fields, types, sizes, counts)])
+        rec = np.frombuffer(raw, dtype=dt, count=n, offset=pos)
+        cols = {name: rec[name] for name in fields}
+    else:
+        raise ValueError(f"unsupported PCD DATA mode {mode!r} (binary_compressed needs PCL's LZF)")
+    xyz = np.stack([np.asarray(cols[k], np.float32) for k in ("x", "y", "z")], 1)
+    return xyz, {k: np.asarray(v) for k, v in cols.items() if k not in ("x", "y", "z")}
+
+
+def write_pcd(path: str, points, binary: bool = False):
+    """An x y z .pcd (ascii or uncompressed binary) as PCL's PCDWriter lays it out (version 0.7 header)."""
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    hdr = (f"# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH {len(p)}\nHEIGHT 1\n"
+           f"VIEWPOINT 0 0 0 1 0 0 0\nPOINTS {len(p)}\nDATA {'binary' if binary else 'ascii'}\n")
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        if binary:
+            f.write(p.astype("<f4").tobytes())
+        else:
+            f.write("".join(f"{float(a)!r} {float(b)!r} {float(c)!r}\n" for a, b, c in p).encode("ascii"))
+
+
+_PLY_NP = {"float": "f4", "float32": "f4", "double": "f8", "float64": "f8", "uchar": "u1", "uint8": "u1", "char": "i1", "int8": "i1",
+           "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4"}
+
+
+def read_ply(path: str):
+    """The vertex element of a .ply (ascii, binary_little_endian or binary_big_endian) -- what PointCloud::writeToFile produces through
+    pcl::io::savePLYFile (PointCloud.h:219-236: x y z intensity normal_x normal_y normal_z curvature).  Returns (points [N,3] float32,
+    normals [N,3] float32 | None, dict of the remaining vertex properties)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    end = raw.index(b"end_header")
+    end = raw.index(b"\n", end) + 1
+    lines = raw[:end].decode("ascii", "replace").splitlines()
+    if not lines or lines[0].strip() != "ply":
+        raise ValueError("not a PLY file")
+    fmt, n, props, in_vertex, before = None, 0, [], False, 0
+    for ln in lines[1:]:
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "format":
+            fmt = t[1]
+        elif t[0] == "element":
+            in_vertex = t[1] == "vertex"
+            if in_vertex:
+                n = int(t[2])
+            elif not props:
+                before += 1          # elements before the vertex element are not supported (PCL and the reference write vertex first)
+        elif t[0] == "property" and in_vertex:
+            if t[1] == "list":
+                raise ValueError("list properties in the vertex element are not supported")
+            props.append((t[2], _PLY_NP[t[1]]))
+    if before:
+        raise ValueError("the vertex element must come first")
+    if fmt == "ascii":
+        tok = raw[end:].split()
+        a = np.array(tok[:n * len(props)], dtype=np.float64).reshape(n, len(props))
+        cols = {name: a[:, k] for k, (name, _) in enumerate(props)}
+    else:
+        order = "<" if fmt == "binary_little_endian" else ">"
+        dt = np.dtype([(name, order + t if t[-1] != "1" else t) for name, t in props])
+        rec = np.frombuffer(raw, dtype=dt, count=n, offset=end)
+        cols = {name: rec[name] for name, _ in props}
+    pts = np.stack([np.asarray(cols[k], np.float32) for k in ("x", "y", "z")], 1)
+    nk = ("normal_x", "normal_y", "normal_z") if "normal_x" in cols else (("nx", "ny", "nz") if "nx" in cols else None)
+    nrm = None if nk is None else np.stack([np.asarray(cols[k], np.float32) for k in nk], 1)
+    used = {"x", "y", "z"} | set(nk or ())
+    return pts, nrm, {k: np.asarray(v) for k, v in cols.items() if k not in used}
+
+
+def write_ply(path: str, points, normals=None, binary: bool = False):
+    """PointCloud::writeToFile (PointCloud.h:219-236): vertices with x y z [normal_x normal_y normal_z]; ascii or binary little-endian."""
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    cols = [p] + ([np.ascontiguousarray(normals, np.float32).reshape(-1, 3)] if normals is not None else [])
+    a = np.concatenate(cols, 1)
+    names = ["x", "y", "z"] + (["normal_x", "normal_y", "normal_z"] if normals is not None else [])
+    hdr = "ply\nformat " + ("binary_little_endian" if binary else "ascii") + f" 1.0\nelement vertex {len(p)}\n" + \
+          "".join(f"property float {k}\n" for k in names) + "end_header\n"
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        if binary:
+            f.write(a.astype("<f4").tobytes())
+        else:
+            f.write("".join(" ".join(repr(float(v)) for v in row) + "\n" for row in a).encode("ascii"))
+
+
+def read_pointcloud_dump(path: str):
+    """PointCloud::readFromFile (PointCloud.h:167-217): char nBytes (4 or 8), uint32 n, n points then n normals as float / double
+    triples.  Returns (points, normals) as float32."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    nbytes = raw[0]
+    n = int(np.frombuffer(raw, "<u4", 1, 1)[0])
+    dt = "<f4" if nbytes == 4 else "<f8"
+    a = np.frombuffer(raw, dt, 6 * n, 5).astype(np.float32)
+    return a[:3 * n].reshape(n, 3).copy(), a[3 * n:].reshape(n, 3).copy()
+
+
+def write_pointcloud_dump(path: str, points, normals, double: bool = False):
+    p = np.ascontiguousarray(points).reshape(-1, 3); m = np.ascontiguousarray(normals).reshape(-1, 3)
+    dt = "<f8" if double else "<f4"
+    with open(path, "wb") as f:
+        f.write(bytes([8 if double else 4])); f.write(np.uint32(len(p)).tobytes())
+        f.write(p.astype(dt).tobytes()); f.write(m.astype(dt).tobytes())

@@ -148,6 +148,7 @@ class ICPOptimizer:
         self.nn_algorithm = 0         # 0 auto, 1 brute force, 2 tiled grid search, 3 per-query tree search
         self.use_graph = True
         self.pyramid_mode = 0         # 0 the reference's stride pyramid, 1 voxel levels (extension)
+        self.early_stop = (0.0, 0.0)  # extension: (radians, metres) below which an applied increment ends the loop; 0 = run all iterations
         self.m_timeMeasure: TimeMeasure | None = None
         self.m_convergenceMeasure: ConvergenceMeasure | None = None
         self._camera = None
@@ -200,6 +201,7 @@ class ICPOptimizer:
         c.weight_max_distance_sq = self.maxDistance
         c.color_icp, c.multires, c.n_iterations = int(self.colorICP), int(self.multiResolutionICP), self.m_nIterations
         c.nn_algorithm, c.use_graph, c.pyramid_mode = self.nn_algorithm, int(self.use_graph), self.pyramid_mode
+        c.early_stop_rotation, c.early_stop_translation = float(self.early_stop[0]), float(self.early_stop[1])
         return c
 
     def setTarget(self, target: PointCloud):

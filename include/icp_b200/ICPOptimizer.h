@@ -29,7 +29,8 @@ public:
         : metric{0}, colorICP{false}, multiResolutionICP{false}, selectionMethod{0}, proba{1.0}, rejectionMethod{1}, weightingMethod{0},
           matchingMethod{0}, m_nIterations{20}, m_timeMeasure{nullptr}, m_convergenceMeasure{nullptr}, maxDistance{0.0003f},
           m_matcherMaxDistance{MAX_DISTANCE},
-          m_ctx{nullptr}, m_haveCamera{false}, m_seed{0}, m_selectionRng{ICP_GPU_RNG_MT19937}, m_width{0}, m_height{0}, m_pyramidMode{ICP_GPU_PYRAMID_STRIDE} {
+          m_ctx{nullptr}, m_haveCamera{false}, m_seed{0}, m_selectionRng{ICP_GPU_RNG_MT19937}, m_width{0}, m_height{0}, m_pyramidMode{ICP_GPU_PYRAMID_STRIDE},
+          m_stopRot{0.f}, m_stopTrans{0.f} {
         if (icp_gpu_create(&m_ctx, 0) != ICP_GPU_OK) { m_ctx = nullptr; std::cout << "icp_gpu: no usable CUDA device (there is no CPU fallback)." << std::endl; }
     }
     virtual ~ICPOptimizer() { if (m_ctx) icp_gpu_destroy(m_ctx); }
@@ -40,6 +41,8 @@ public:
     void enableMultiResolution(bool enableMultiResolution) { this->multiResolutionICP = enableMultiResolution; }
     // extension: ICP_GPU_PYRAMID_VOXEL builds the levels by voxel downsampling instead of the reference's index stride
     void setPyramidMode(int pyramidMode) { m_pyramidMode = pyramidMode; }
+    // extension: stop once an applied increment is below both thresholds (radians, metres); 0 = the reference's behaviour (all iterations)
+    void setEarlyStop(float rotation, float translation) { m_stopRot = rotation; m_stopTrans = translation; }
     void enableColorICP(bool colorICP) { this->colorICP = colorICP; }
     void setSelectionMethod(unsigned int selectionMethod, double proba = 1.0) { this->selectionMethod = selectionMethod; this->proba = proba; }
     void setRejectionMethod(unsigned int rejectionMethod) { this->rejectionMethod = rejectionMethod; }
@@ -93,6 +96,7 @@ protected:
     float m_matcherMaxDistance;   // NearestNeighborSearch::m_maxDistance of the matcher the reference owns (NearestNeighbor.h:17-19,35)
     icp_gpu_ctx* m_ctx;
     Eigen::Matrix3f m_K; bool m_haveCamera; unsigned m_seed; int m_selectionRng; unsigned m_width, m_height; int m_pyramidMode;
+    float m_stopRot, m_stopTrans;
 
     // body of estimatePose shared by both minimisers (ICPOptimizer.h:185-349 / :493-663)
     void run(int minimizer, const PointCloud& source, const PointCloud& target, Matrix4f& initialPose, bool calculateRMSE) {
@@ -104,6 +108,7 @@ protected:
         cfg.weighting = (int32_t)weightingMethod; cfg.rejection = (int32_t)rejectionMethod;
         cfg.max_distance_sq = m_matcherMaxDistance; cfg.weight_max_distance_sq = maxDistance;
         cfg.color_icp = colorICP ? 1 : 0; cfg.multires = multiResolutionICP ? 1 : 0; cfg.n_iterations = (int32_t)m_nIterations; cfg.pyramid_mode = m_pyramidMode;
+        cfg.early_stop_rotation = m_stopRot; cfg.early_stop_translation = m_stopTrans;
         int rc = icp_gpu_set_config(m_ctx, &cfg);
         if (rc == ICP_GPU_OK && m_haveCamera) rc = icp_gpu_set_camera(m_ctx, m_K.data(), m_width, m_height);
         const auto& tp = target.getPoints(); const auto& tn = target.getNormals(); const auto& tc = target.getColors();

@@ -102,6 +102,11 @@ typedef struct icp_gpu_config {
                                    it apart from the matcher's threshold: setMatchingMethod re-creates the matcher with
                                    MAX_DISTANCE = 0.005 (ICPOptimizer.h:71-78, NearestNeighbor.h:5) and leaves this one alone;
                                    only setMatchingMaxDistance sets both.  0 (default) = max_distance_sq               */
+    float    early_stop_rotation;    /* extension: stop once an applied increment rotates by <= this (radians) AND   */
+    float    early_stop_translation; /* translates by <= this (metres); the remaining iterations are skipped on the device and
+                                   n_iterations_out reports the executed ones.  0 (default, either one) = run every iteration,
+                                   as the reference does                                                                 */
+    int32_t  reserved_;
 } icp_gpu_config;
 
 /* Per-stage device times of the last icp_gpu_estimate_pose call made with timings != NULL

@@ -805,3 +805,29 @@ def test_index_edge_shapes_against_brute_force(ctx, kind, n_tgt):
         ref2 = orc.knn_brute(tgt, q2, max_d2)
         idx, w = ctx.query_matches(shifted)
         assert_matches_equal(idx, w, ref2, f"{kind} n={n_tgt} max_d2={max_d2} shifted")
+
+
+@pytest.mark.parametrize("minimizer", [0, 1])
+def test_early_stop_criterion(ctx, bunny, minimizer):
+    """with thresholds set, the loop ends (on the device, inside the replayed graph) after the first iteration whose
+    increment is below both; the poses up to there are bit for bit those of the full run, which is unchanged when the thresholds are 0."""
+    src, tgt, _, _ = bunny
+    load(ctx, src, tgt)
+    cfg = capi.default_config()
+    cfg.metric, cfg.minimizer, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm = 1, minimizer, 30, 0.0003, 2
+    ctx.set_config(cfg)
+    full, hist, n_full = ctx.estimate_pose()
+    assert n_full == 30
+    steps = [(rot_angle(hist[k], hist[k - 1]), float(np.linalg.norm(hist[k][:3, 3] - hist[k - 1][:3, 3]))) for k in range(1, 30)]
+    k_stop = next(k for k, (r, t) in enumerate(steps, start=1) if r < 2e-4 and t < 2e-5)      # an iteration well inside the run
+    assert 2 <= k_stop <= 28
+    cfg.early_stop_rotation, cfg.early_stop_translation = 1e-3, 1e-4                          # generous: the increment, not the pose difference, is tested
+    ctx.set_config(cfg)
+    pose, h2, n_it = ctx.estimate_pose()
+    assert 1 <= n_it < 30 and len(h2) == n_it
+    assert np.array_equal(np.asarray(h2), np.asarray(hist[:n_it])) and np.array_equal(pose, hist[n_it - 1])
+    for use_graph in (0, 1):
+        cfg.use_graph = use_graph
+        ctx.set_config(cfg)
+        p3, _, n3 = ctx.estimate_pose()
+        assert n3 == n_it and np.array_equal(p3, pose)

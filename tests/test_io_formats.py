@@ -87,3 +87,38 @@ def test_eth_pair_list(tmp_path):
     rows = fio.read_eth_pairs(p)
     assert len(rows) == 2 and rows[0]["source"] == "PointCloud1.pcd" and rows[0]["target"] == "PointCloud0.pcd"
     assert rows[0]["pose"][:3, 3].tolist() == [0.5, -0.25, 2.0] and rows[1]["pose"][0, 1] == -1 and rows[1]["pose"][3].tolist() == [0, 0, 0, 1]
+
+
+def test_pcd_ply_and_dump_round_trips(tmp_path):
+    """PCD (pcl::io::loadPCDFile, ETHDataLoader.h:68,87), PLY (PointCloud::writeToFile, PointCloud.h:219-236) and the PointCloud binary
+    dump (PointCloud.h:167-217): ascii and binary forms read back bit for bit, NaN points survive, extra fields come back by name."""
+    rng = np.random.default_rng(0)
+    p = rng.normal(size=(257, 3)).astype(np.float32); p[5] = np.nan
+    n = rng.normal(size=(257, 3)).astype(np.float32)
+    for binary in (False, True):
+        f = str(tmp_path / f"c{int(binary)}.pcd"); fio.write_pcd(f, p, binary)
+        q, extra = fio.read_pcd(f)
+        assert np.array_equal(q, p, equal_nan=True) and extra == {}
+        g = str(tmp_path / f"c{int(binary)}.ply"); fio.write_ply(g, p, n, binary)
+        q, m, extra = fio.read_ply(g)
+        assert np.array_equal(q, p, equal_nan=True) and np.array_equal(m, n) and extra == {}
+    # a PCD as PCL writes clouds with normals (FIELDS x y z normal_x normal_y normal_z curvature), ascii
+    f = str(tmp_path / "n.pcd")
+    with open(f, "w") as fh:
+        fh.write("# .PCD v0.7\nVERSION 0.7\nFIELDS x y z normal_x normal_y normal_z curvature\nSIZE 4 4 4 4 4 4 4\nTYPE F F F F F F F\n"
+                 "COUNT 1 1 1 1 1 1 1\nWIDTH 2\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 2\nDATA ascii\n1 2 3 0 0 1 0.5\n4 5 6 0 1 0 0.25\n")
+    q, extra = fio.read_pcd(f)
+    assert np.array_equal(q, np.array([[1, 2, 3], [4, 5, 6]], np.float32)) and np.array_equal(extra["curvature"], [0.5, 0.25])
+    # the PLY layout of pcl::io::savePLYFile for PointXYZINormal: intensity between the point and the normal, curvature after it
+    g = str(tmp_path / "pcl.ply")
+    with open(g, "w") as fh:
+        fh.write("ply\nformat ascii 1.0\ncomment PCL generated\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property float intensity\nproperty float normal_x\nproperty float normal_y\nproperty float normal_z\nproperty float curvature\n"
+                 "element camera 1\nproperty float view_px\nend_header\n1 2 3 1 0 0 1 0\n4 5 6 1 0 1 0 0\n0\n")
+    q, m, extra = fio.read_ply(g)
+    assert np.array_equal(q, np.array([[1, 2, 3], [4, 5, 6]], np.float32)) and np.array_equal(m, np.array([[0, 0, 1], [0, 1, 0]], np.float32))
+    assert np.array_equal(extra["intensity"], [1, 1])
+    for double in (False, True):
+        d = str(tmp_path / f"d{int(double)}.bin"); fio.write_pointcloud_dump(d, p, n, double)
+        q, m = fio.read_pointcloud_dump(d)
+        assert np.array_equal(q, p, equal_nan=True) and np.array_equal(m, n)
