@@ -368,7 +368,7 @@ def sharded_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
         out["note"] = "N = 1: the unsharded registration (index already built, clouds resident); run with --gpus 2/4/8 for the sharded forms"
         return out
     dist.barrier()
-    sl = parallel.shard_points(len(src), world, rank)
+    sl = parallel.shard_points_interleaved(len(src), world, rank)      # uniform subsamples: equal cost per rank and iteration
     ctx.set_source(src.points[sl], src.normals[sl], src.colors[sl])
     # baseline: ncclAllReduce of the row on the stream, no host round trip
     ms_nccl, pose_nccl = timed(lambda: parallel.register_sharded_on_stream(ctx, N_ITER))
@@ -380,7 +380,7 @@ def sharded_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     dist.all_gather_object(poses, pose_fused.tobytes())
     ctx.peer_detach()
     # what one exchange costs: the same loop on a tiny source (1024 points per rank), attached vs. detached
-    tiny = slice(sl.start, sl.start + 1024)
+    tiny = slice(rank * 1024, rank * 1024 + 1024)
     ctx.set_source(src.points[tiny], src.normals[tiny], src.colors[tiny])
     ms_tiny_alone, _ = timed(lambda: ctx.estimate_pose(want_history=False))
     parallel.attach_peers(ctx)

@@ -598,8 +598,8 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
 // shared memory and every thread scans its own 25x25 window there.  Blocks whose union does not fit fall back to
 // reading the (L2-resident) target map directly.
 #define PROJ_THREADS 256
-#define PROJ_TILE_MAX 3000     // float4 entries (48 KB static shared memory)
-__global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArgs a) {
+#define PROJ_TILE_MAX 2800     // float4 entries (44.8 KB static shared memory: five blocks per SM)
+__global__ void __launch_bounds__(PROJ_THREADS, 5) projective_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     __shared__ float4 tile[PROJ_TILE_MAX];
     __shared__ unsigned int s_box[4][PROJ_THREADS / 32];
@@ -649,12 +649,17 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
     for (int w = 0; w < PROJ_THREADS / 32; ++w) { bu0 = min(bu0, s_box[0][w]); bv0 = min(bv0, s_box[1][w]); bu1 = max(bu1, s_box[2][w]); bv1 = max(bv1, s_box[3][w]); }
     const bool any_window = bu0 != 0xFFFFFFFFu;
     const unsigned int tw = any_window ? bu1 - bu0 + 1u : 0u, th = any_window ? bv1 - bv0 + 1u : 0u;
-    const bool staged = any_window && (unsigned long long)tw * th <= PROJ_TILE_MAX;      // block-uniform
+    // Row pitch of the staged tile: a MULTIPLE OF 8 entries (128 B).  An LDS.128 is served 8 lanes at a time and is conflict-free
+    // when those lanes hit 8 different 16-byte bank groups, i.e. different (row * pitch + column) mod 8: the lanes of a warp scan
+    // neighbouring columns of possibly different rows (the frames are rotated against each other), so with pitch = 0 mod 8 the bank
+    // group is the column alone.  Round 1 used the raw union width (834 k conflicts per launch); an odd pitch measured 2.4 M.
+    const unsigned int tp = (tw + 7u) & ~7u;
+    const bool staged = any_window && (unsigned long long)tp * th <= PROJ_TILE_MAX;      // block-uniform
     if (any_window && !staged && threadIdx.x == 0) ++nd;                                // work counter: blocks that fall back to global reads
     if (staged) {
         for (unsigned int k = threadIdx.x; k < tw * th; k += PROJ_THREADS) {
             const unsigned int ty = k / tw, tx = k - ty * tw;
-            tile[k] = __ldg(&a.tgt_pts[(size_t)a.width * (bv0 + ty) + bu0 + tx]);
+            tile[ty * tp + tx] = __ldg(&a.tgt_pts[(size_t)a.width * (bv0 + ty) + bu0 + tx]);
         }
     }
     __syncthreads();
@@ -675,8 +680,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) projective_kernel(const MatchArg
                     const unsigned int n_u = u1 - u0 + 1u;
                     unsigned int cnt = 0u, best = 0xFFFFFFFFu;
                     if (staged) {
-                        const float4* row = &tile[(v0 - bv0) * tw + (u0 - bu0)];          // shared-memory pointer: LDS.128
-                        for (unsigned int v = v0; v <= v1; ++v, row += tw) {
+                        const float4* row = &tile[(v0 - bv0) * tp + (u0 - bu0)];          // shared-memory pointer: LDS.128
+                        for (unsigned int v = v0; v <= v1; ++v, row += tp) {
 #pragma unroll 5
                             for (unsigned int k = 0; k < n_u; ++k, ++cnt) {
                                 const float4 t = row[k];

@@ -27,6 +27,14 @@ def shard_points(n_points: int, world: int, rank: int) -> slice:
     return slice(start, start + base + (1 if rank < rem else 0))
 
 
+def shard_points_interleaved(n_points: int, world: int, rank: int) -> slice:
+    """Every world-th point, starting at `rank`: each shard is a uniform subsample of the scan, so the ranks' iterations cost the same.
+    The exchange synchronises the ranks once per iteration -- with contiguous shards (different parts of the scene, different shares of
+    far queries) every iteration costs the slower rank's time and the skew adds up (measured on the 3 M-point pair, 2 GPUs: 62 us per
+    iteration of waiting, profiles/r2_sharded_detail_n2.json)."""
+    return slice(rank, n_points, world)
+
+
 def allreduce_sum(row: np.ndarray) -> np.ndarray:
     """Sum of one partial row over all ranks (gloo: CPU tensor; nccl: staged through the rank's GPU)."""
     import torch

