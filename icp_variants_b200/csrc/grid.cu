@@ -794,7 +794,10 @@ __global__ void __launch_bounds__(UP_THREADS) upper_levels_kernel(int* delta_a, 
 // one warp per node (grid-stride): level 0 reads the leaf's points, level l > 0 reads its (<= 32) child boxes
 // The w components of the two box entries carry the node's COLOUR range (min / max of r, g, b as packed bytes), which the
 // 6-D colour search adds to its lower bounds (match.cu: box_dist2c).
-__global__ void bvh_level_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, const unsigned int* __restrict__ leaf_start,
+// Level 0 also re-orders every leaf's records by ORIGINAL index (they arrive in (cell code, original index) order): a scan of
+// the leaf in storage order with a strict '<' on the distance then returns the lowest original index among equal distances --
+// contract D2 inside a leaf without comparing indices per candidate (match.cu: thread_scan_leaf).
+__global__ void bvh_level_kernel(float4* __restrict__ pts, float4* __restrict__ nrm, const unsigned int* __restrict__ leaf_start,
                                  const unsigned int* __restrict__ child_start, const BvhDesc* __restrict__ bvh, float4* __restrict__ box,
                                  int level) {
     const BvhDesc b = *bvh;
@@ -805,13 +808,22 @@ __global__ void bvh_level_kernel(const float4* __restrict__ pts, const float4* _
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         unsigned int clo[3] = {255u, 255u, 255u}, chi[3] = {0u, 0u, 0u};
         if (level == 0) {
-            const unsigned int i = leaf_start[node] + lane;
-            if (i < leaf_start[node + 1]) {
-                const float4 p = pts[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
-                const unsigned int c = __float_as_uint(nrm[i].w);
+            const unsigned int ls = leaf_start[node], i = ls + lane;
+            const bool in = i < leaf_start[node + 1];
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f), m = p;
+            if (in) {
+                p = pts[i]; m = nrm[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
+                const unsigned int c = __float_as_uint(m.w);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) clo[k] = chi[k] = (c >> (8 * k)) & 0xFFu;
             }
+            // rank of this lane's record among the leaf's by original index (unique), then the in-place permutation
+            const unsigned int mine = in ? __float_as_uint(p.w) : 0xFFFFFFFFu;
+            unsigned int rank = 0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) rank += __shfl_sync(0xFFFFFFFFu, mine, l) < mine ? 1u : 0u;
+            __syncwarp();                                    // every record of the leaf is in registers before any is overwritten
+            if (in) { pts[ls + rank] = p; nrm[ls + rank] = m; }
         } else {
             const unsigned int c = child_start[b.coffset[level] + node] + lane;
             if (c < child_start[b.coffset[level] + node + 1]) {
@@ -1019,7 +1031,7 @@ size_t icp_bvh_max_nodes(int n) {
 // Tight-box BVH over the sorted cloud.  keys: the sorted keys; nonfinite: device count of the points past the last cell.
 // leaf_rank: n + 2 entries (kept: maps a sorted position to its leaf); leaf_start: n + 2; node_rank / child_start:
 // icp_bvh_max_nodes(n) + ICP_BVH_MAX_LEVELS entries each; flags: n bytes; tile_count: n / 1024 + 2; delta_a / delta_b: n + 2 each.
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, int T, const unsigned int* keys,
+cudaError_t icp_launch_bvh_build(float4* pts_sorted, float4* nrm_sorted, int n, int T, const unsigned int* keys,
                                  const unsigned int* nonfinite, unsigned char* flags, unsigned int* tile_count,
                                  int* delta_a, int* delta_b, unsigned int* leaf_rank, unsigned int* leaf_start, unsigned int* node_rank,
                                  unsigned int* child_start, BvhDesc* bvh_dev, float4* box, int n_sms, cudaStream_t s, int* n_launches) {

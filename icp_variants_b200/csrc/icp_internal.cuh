@@ -214,7 +214,7 @@ cudaError_t icp_launch_cloud_sort(const float4* pts_in, const float4* nrm_in, in
                                   unsigned int** keys_sorted_out, int* msd_shift_out, const IcpLatePack* late, cudaStream_t s, int* n_launches);
 // Tight-box BVH over the sorted cloud, read off the common-prefix lengths of neighbouring sorted keys.
 size_t icp_bvh_max_nodes(int n);
-cudaError_t icp_launch_bvh_build(const float4* pts_sorted, const float4* nrm_sorted, int n, int T, const unsigned int* keys,
+cudaError_t icp_launch_bvh_build(float4* pts_sorted, float4* nrm_sorted, int n, int T, const unsigned int* keys,
                                  const unsigned int* nonfinite, unsigned char* flags, unsigned int* tile_count,
                                  int* delta_a, int* delta_b, unsigned int* leaf_rank, unsigned int* leaf_start, unsigned int* node_rank,
                                  unsigned int* child_start, BvhDesc* bvh_dev, float4* box, int n_sms, cudaStream_t s, int* n_launches);

@@ -234,21 +234,23 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
 template <bool COLOR>
 __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query& q, Best& b, int& bleaf, unsigned int leaf, unsigned int& ev) {
     const unsigned int ls = __ldg(&a.leaf_start[leaf]), le = __ldg(&a.leaf_start[leaf + 1]);
-    // (d, idx) lexicographic '<' (contract D2) as ONE 64-bit unsigned comparison: d >= 0, so the bit pattern of d orders
-    // like d, and 0 <= idx <= INT_MAX.  This loop is a third of the kernel's instructions; the two-float-compares-and-an-
-    // integer-compare form of better() plus four selects cost more than the distance itself.
-    if (b.d < 0.f) return;                          // a negative threshold admits nothing (and its bit pattern would order last)
-    unsigned long long key = ((unsigned long long)__float_as_uint(b.d) << 32) | (unsigned int)b.idx;
-    int pos = b.pos;
+    // Contract D2 ((d, idx) lexicographic) without an index comparison per candidate: a leaf's records are stored in ORIGINAL index
+    // order (grid.cu: bvh_level_kernel), so the first minimum of the distance in storage order is the lowest original index among
+    // equal distances.  The scan accepts d <= the current best (`run` starts one ulp above it; d >= 0, so the bit pattern + 1 is the
+    // next float) and the (d, idx) rule is applied once, to the leaf's winner.  This loop is a third of the kernel's instructions.
+    if (b.d < 0.f) return;                          // a negative threshold admits nothing
+    float run = __uint_as_float(__float_as_uint(b.d) + 1u);
+    int pos = -1;
     for (unsigned int i = ls; i < le; ++i) {
         const float4 pt = __ldg(&a.tgt_pts[i]);
-        const float dd = dist2<COLOR>(q, pt, __uint_as_float((unsigned int)(key >> 32)), a.tgt_nrm, i);
-        const unsigned long long k = ((unsigned long long)__float_as_uint(dd) << 32) | __float_as_uint(pt.w);
-        if (k < key) { key = k; pos = (int)i; }
+        const float dd = dist2<COLOR>(q, pt, run, a.tgt_nrm, i);
+        if (dd < run) { run = dd; pos = (int)i; }
     }
-    if (pos != b.pos) bleaf = (int)leaf;            // positions are unique: a new best position means this leaf holds it
-    b.d = __uint_as_float((unsigned int)(key >> 32)); b.idx = (int)(unsigned int)key; b.pos = pos;
     ev += le - ls;
+    if (pos >= 0) {
+        const int idx = __float_as_int(__ldg(&a.tgt_pts[pos].w));
+        if (better_key(run, idx, b)) { b.d = run; b.idx = idx; b.pos = pos; bleaf = (int)leaf; }
+    }
 }
 
 // Thread per query: selection predicate + transformPoints -> qbuf, and the FAST PATH of the search.  A query that
