@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libicp_gpu.so")
+LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("ICP_GPU_LIB_NAME", "libicp_gpu.so"))   # the variable: A/B runs of build variants (profiles/)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "icp_gpu.h")
 
 OK, E_CUDA, E_ARG, E_STATE, E_NO_MATCHES, E_NUMERIC, E_PEER = 0, -1, -2, -3, -4, -5, -6

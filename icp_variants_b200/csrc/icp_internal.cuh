@@ -169,6 +169,17 @@ struct MatchArgs {
     int fast_path;           // knn_prep_kernel answers the queries whose search ball stays inside their seed leaf's inflated box
     int collect_stats;       // work counters in DevState (atomics); off in timed runs
     int skip_finish;         // BVH path: the reduction evaluates stages 3-4 itself (ReduceArgs::fused), no match records
+    int q_begin, q_end;      // BVH path: the sorted-source positions [q_begin, q_end) this launch searches (a chunk; the whole cloud by default)
+};
+
+// Concurrency inside one iteration (api.cu, match.cu): the queries are cut into chunks, each chunk's {prep, walk} chain runs on its own
+// stream between a fork and a join event; the per-query results do not depend on the cut.
+#define ICP_MAX_MATCH_CHUNKS 8
+struct MatchChunks {
+    int n = 1;                                         // 1 = everything on the caller's stream
+    cudaStream_t stream[ICP_MAX_MATCH_CHUNKS - 1] = {};
+    cudaEvent_t done[ICP_MAX_MATCH_CHUNKS - 1] = {};
+    cudaEvent_t fork = nullptr;
 };
 
 struct ReduceArgs {
@@ -257,7 +268,8 @@ struct NormalArgs {
     float4* nrm_sorted; float4* nrm_orig;    // the cloud's own normal arrays {nx,ny,nz,rgba}: x,y,z overwritten
 };
 cudaError_t icp_launch_pca_normals(const NormalArgs& a, cudaStream_t s);
-cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep = nullptr);
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep = nullptr,
+                             const MatchChunks* chunks = nullptr);
 cudaError_t icp_launch_pose_init(DevState* st, const float* pose_dev16, cudaStream_t s, float stop_rot = 0.f, float stop_trans = 0.f);
 cudaError_t icp_launch_reduce(const ReduceArgs& a, int n_blocks, cudaStream_t s, int* n_launches);
 // one phase of the point-sharded iteration: the summed row is left in state->shard_partials

@@ -147,7 +147,9 @@ __device__ __forceinline__ bool prepare_query(const MatchArgs& a, const IterDesc
 }
 
 // ---------------------------------------------------------------------------- BVH search, one warp per query
+#ifndef BVH_WARPS
 #define BVH_WARPS 4
+#endif
 #define BVH_STACK (32 * ICP_BVH_MAX_LEVELS)   // <= 32 pushed children per level
 
 // fp32 lower bound (under D1's rounding and association, by monotonicity) of the squared distance from q
@@ -265,12 +267,12 @@ __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query
 template <bool COLOR, bool STATS>
 __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = a.q_begin + blockIdx.x * blockDim.x + threadIdx.x;
     // Everything that depends on nothing is requested first, so that the pose, the descriptor and the query's own state
     // arrive together (the kernel is bound by its chain of dependent loads, not by bandwidth).
     float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = p4;
     int sp_raw = -1, leaf_raw = -1;
-    if (p < a.n_src) {
+    if (p < a.q_end) {
         p4 = __ldg(&a.src_pts[p]); n4 = __ldg(&a.src_nrm[p]);
         sp_raw = a.nn_pos[p]; leaf_raw = a.nn_leaf[p];          // leaf_raw is meaningless unless sp_raw is a position
     }
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[desc_i];
     unsigned int ev = 0, nd = 0;
-    if (p < a.n_src) {
+    if (p < a.q_end) {
         float4 o = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, n4.w);
         float4 seed = make_float4(0.f, 0.f, 0.f, __int_as_float(-2));      // nothing to hand over
         if (query_active(d, a.mask, p4, n4)) {
@@ -368,11 +370,11 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
     // The warp's positions are p0, p0 + warps, p0 + 2 warps, ...; three quarters of them were answered by the fast path.
     // Lane k fetches the transformed query of position p0 + k * warps, so that one round of loads (instead of one
     // dependent load per position) tells the warp which positions it has to search.
-    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    for (int pb = p0; pb < a.n_src; pb += 32 * warps) {
+    const int p0 = a.q_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    for (int pb = p0; pb < a.q_end; pb += 32 * warps) {
       const long long pl = (long long)pb + (long long)lane * warps;
       float qx = __int_as_float(0x7fc00000);
-      if (pl < (long long)a.n_src) qx = __ldg(&a.qbuf[pl].x);
+      if (pl < (long long)a.q_end) qx = __ldg(&a.qbuf[pl].x);
       unsigned int todo = __ballot_sync(FULL, qx == qx);                        // NaN: not a (searchable) query this iteration
       while (todo) {
         const int k = __ffs((int)todo) - 1; todo &= todo - 1u;
@@ -715,7 +717,8 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projective_kernel(const Match
     flush_stats(a, nq, nm, ev, nd);
 }
 
-cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep) {
+cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaStream_t s, int* n_launches, cudaEvent_t after_prep,
+                             const MatchChunks* chunks) {
     if (a.n_src <= 0) return cudaSuccess;
     const int T = ICP_MATCH_THREADS;
     int launches = 0;
@@ -731,16 +734,37 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
         else knn_brute_kernel<false, false><<<nb, T, 0, s>>>(a);
         ++launches;
     } else {
-        const int np = (a.n_src + 255) / 256;
-        if (a.collect_stats) { if (a.color_icp) knn_prep_kernel<true, true><<<np, 256, 0, s>>>(a); else knn_prep_kernel<false, true><<<np, 256, 0, s>>>(a); }
-        else { if (a.color_icp) knn_prep_kernel<true, false><<<np, 256, 0, s>>>(a); else knn_prep_kernel<false, false><<<np, 256, 0, s>>>(a); }
-        ++launches;
-        if (after_prep) cudaEventRecord(after_prep, s);
-        int nb = (a.n_src + BVH_WARPS - 1) / BVH_WARPS;
-        if (nb > 64 * n_sms) nb = 64 * n_sms;
-        if (a.collect_stats) { if (a.color_icp) knn_bvh_kernel<true, true><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, true><<<nb, BVH_WARPS * 32, 0, s>>>(a); }
-        else { if (a.color_icp) knn_bvh_kernel<true, false><<<nb, BVH_WARPS * 32, 0, s>>>(a); else knn_bvh_kernel<false, false><<<nb, BVH_WARPS * 32, 0, s>>>(a); }
-        ++launches;
+        // One chunk of queries = one {prep, walk} chain; the chains run side by side on their own streams between a fork and a
+        // join (MatchChunks): the block scheduler fills the ramps and tails of one chain's kernels with the other's blocks.
+        int K = (chunks && !after_prep) ? chunks->n : 1;
+        if (K < 1) K = 1;
+        long long per = ((long long)a.n_src + K - 1) / K;
+        per = (per + 255) / 256 * 256;                                         // whole prep blocks
+        if (K > 1) cudaEventRecord(chunks->fork, s);
+        static const int mult = getenv("ICP_GPU_WALK_GRID") ? atoi(getenv("ICP_GPU_WALK_GRID")) : 64;     // tuning knob
+        for (int c = 0; c < K; ++c) {
+            MatchArgs ac = a;
+            ac.q_begin = (int)std::min<long long>((long long)c * per, a.n_src);
+            ac.q_end = (int)std::min<long long>((long long)(c + 1) * per, a.n_src);
+            const int nq = ac.q_end - ac.q_begin;
+            if (nq <= 0) continue;
+            cudaStream_t cs = c == 0 ? s : chunks->stream[c - 1];
+            if (c > 0) cudaStreamWaitEvent(cs, chunks->fork, 0);
+            const int np = (nq + 255) / 256;
+            if (a.collect_stats) { if (a.color_icp) knn_prep_kernel<true, true><<<np, 256, 0, cs>>>(ac); else knn_prep_kernel<false, true><<<np, 256, 0, cs>>>(ac); }
+            else { if (a.color_icp) knn_prep_kernel<true, false><<<np, 256, 0, cs>>>(ac); else knn_prep_kernel<false, false><<<np, 256, 0, cs>>>(ac); }
+            ++launches;
+            if (after_prep) cudaEventRecord(after_prep, s);
+            // every chunk's walk gets the full grid (its warps then take fewer positions each): a heavy chunk left alone at the end
+            // of the iteration still fills the machine
+            int nb = (nq + BVH_WARPS - 1) / BVH_WARPS;
+            const int cap = std::max(1, mult * n_sms * 4 / BVH_WARPS);
+            if (nb > cap) nb = cap;
+            if (a.collect_stats) { if (a.color_icp) knn_bvh_kernel<true, true><<<nb, BVH_WARPS * 32, 0, cs>>>(ac); else knn_bvh_kernel<false, true><<<nb, BVH_WARPS * 32, 0, cs>>>(ac); }
+            else { if (a.color_icp) knn_bvh_kernel<true, false><<<nb, BVH_WARPS * 32, 0, cs>>>(ac); else knn_bvh_kernel<false, false><<<nb, BVH_WARPS * 32, 0, cs>>>(ac); }
+            ++launches;
+            if (c > 0) { cudaEventRecord(chunks->done[c - 1], cs); cudaStreamWaitEvent(s, chunks->done[c - 1], 0); }
+        }
         if (!a.skip_finish) { match_finish_kernel<<<(a.n_src + 255) / 256, 256, 0, s>>>(a); ++launches; }
     }
     if (n_launches) *n_launches += launches;
