@@ -146,6 +146,25 @@ __device__ __forceinline__ bool prepare_query(const MatchArgs& a, const IterDesc
     return true;
 }
 
+// ---------------------------------------------------------------------------- diagnostic build (-DICP_TIMELINE, profiles/)
+// Start and end (%globaltimer, ns) of every warp of the search kernels of ONE iteration (ICP_TL_ITER), plain stores.
+#ifdef ICP_TIMELINE
+#define ICP_TL_ITER 12
+#define ICP_TL_WARPS 40960
+__device__ unsigned long long g_timeline[2][2][ICP_TL_WARPS][2];      // [kernel][chunk][warp]{start, end}
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+extern "C" int icp_gpu_debug_timeline(unsigned long long* out, int reset) {
+    if (reset) { void* p = nullptr; cudaGetSymbolAddress(&p, g_timeline); return (int)cudaMemset(p, 0, sizeof(g_timeline)); }
+    return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline));
+}
+#define TL_BEGIN(k, it, chunk) const int tl_w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), tl_c = (chunk); \
+    const bool tl_on = (it) == ICP_TL_ITER && (threadIdx.x & 31) == 0 && tl_w < ICP_TL_WARPS; if (tl_on) g_timeline[k][tl_c][tl_w][0] = tl_now()
+#define TL_END(k) if (tl_on) g_timeline[k][tl_c][tl_w][1] = tl_now()
+#else
+#define TL_BEGIN(k, it, chunk)
+#define TL_END(k)
+#endif
+
 // ---------------------------------------------------------------------------- BVH search, one warp per query
 #ifndef BVH_WARPS
 #define BVH_WARPS 4
@@ -261,11 +280,14 @@ __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query
 // itself -- same candidates, same (d, idx) order, hence the same answer as the walk -- and marks the query as done
 // (qbuf.x = NaN).  The 32 queries of a warp are spatial neighbours (sorted source), so their leaves coincide and the
 // loads are mostly broadcasts.  Everything else (no neighbour yet, ball leaving the box) is left to knn_bvh_kernel.
+#ifndef PREP_THREADS
+#define PREP_THREADS 256
+#endif
 #ifndef PREP_MIN_BLOCKS
 #define PREP_MIN_BLOCKS 5          // measured 5 / 6 / 7 / 8 blocks per SM: 60 / 67 / 78 / 79 us per launch (more blocks = spills)
 #endif
 template <bool COLOR, bool STATS>
-__global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const MatchArgs a) {
+__global__ void __launch_bounds__(PREP_THREADS, PREP_MIN_BLOCKS * 256 / PREP_THREADS) knn_prep_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     const int p = a.q_begin + blockIdx.x * blockDim.x + threadIdx.x;
     // Everything that depends on nothing is requested first, so that the pose, the descriptor and the query's own state
@@ -278,6 +300,7 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
     }
     if (a.desc_index < 0 && a.state_ro->converged) return;   // early stop reached: the remaining launches of the registration are no-ops
     const int desc_i = a.desc_index >= 0 ? a.desc_index : a.state_ro->iter;
+    TL_BEGIN(0, a.state_ro->iter, a.q_begin > 0 ? 1 : 0);
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[desc_i];
     unsigned int ev = 0, nd = 0;
@@ -343,6 +366,7 @@ __global__ void __launch_bounds__(256, PREP_MIN_BLOCKS) knn_prep_kernel(const Ma
         a.qbuf[p] = o;
         if (o.x == o.x) a.seedbuf[p] = seed;
     }
+    TL_END(0);
     if (STATS) flush_stats(a, 0u, 0u, ev, nd);     // STATS = false: the counters are dead code (2.6 % of the walk's instructions)
 }
 
@@ -367,6 +391,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
     unsigned int* st_node = s_node[wid]; float* st_lb = s_lb[wid];
     const unsigned int lt_mask = (1u << lane) - 1u;
     if (bvh.n_leaves <= 0) return;                 // empty target: match_finish_kernel sees nn_pos = -1 (set_target reset it)
+    TL_BEGIN(1, a.state_ro->iter, a.q_begin > 0 ? 1 : 0);
     // The warp's positions are p0, p0 + warps, p0 + 2 warps, ...; three quarters of them were answered by the fast path.
     // Lane k fetches the transformed query of position p0 + k * warps, so that one round of loads (instead of one
     // dependent load per position) tells the warp which positions it has to search.
@@ -532,6 +557,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, WALK_MIN_BLOCKS) knn_bvh_kerne
         }
       }
     }
+    TL_END(1);
     if (STATS) flush_stats(a, 0u, 0u, ev, nd);     // STATS = false: the counters are dead code (2.6 % of the walk's instructions)
 }
 
@@ -750,9 +776,9 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
             if (nq <= 0) continue;
             cudaStream_t cs = c == 0 ? s : chunks->stream[c - 1];
             if (c > 0) cudaStreamWaitEvent(cs, chunks->fork, 0);
-            const int np = (nq + 255) / 256;
-            if (a.collect_stats) { if (a.color_icp) knn_prep_kernel<true, true><<<np, 256, 0, cs>>>(ac); else knn_prep_kernel<false, true><<<np, 256, 0, cs>>>(ac); }
-            else { if (a.color_icp) knn_prep_kernel<true, false><<<np, 256, 0, cs>>>(ac); else knn_prep_kernel<false, false><<<np, 256, 0, cs>>>(ac); }
+            const int np = (nq + PREP_THREADS - 1) / PREP_THREADS;
+            if (a.collect_stats) { if (a.color_icp) knn_prep_kernel<true, true><<<np, PREP_THREADS, 0, cs>>>(ac); else knn_prep_kernel<false, true><<<np, PREP_THREADS, 0, cs>>>(ac); }
+            else { if (a.color_icp) knn_prep_kernel<true, false><<<np, PREP_THREADS, 0, cs>>>(ac); else knn_prep_kernel<false, false><<<np, PREP_THREADS, 0, cs>>>(ac); }
             ++launches;
             if (after_prep) cudaEventRecord(after_prep, s);
             // every chunk's walk gets the full grid (its warps then take fewer positions each): a heavy chunk left alone at the end

@@ -261,6 +261,15 @@ __device__ void finish_sums(DevState* st, const double* row) {
     }
 }
 
+#ifdef ICP_TIMELINE   // diagnostic build (profiles/): see match.cu; per block of iteration 12 {start, loop end}, [511] = {pose written, 0}
+__device__ unsigned long long g_timeline_r[512][2];
+__device__ __forceinline__ unsigned long long tlr_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+extern "C" int icp_gpu_debug_timeline_reduce(unsigned long long* out, int reset) {
+    if (reset) { void* p = nullptr; cudaGetSymbolAddress(&p, g_timeline_r); return (int)cudaMemset(p, 0, sizeof(g_timeline_r)); }
+    return (int)cudaMemcpyFromSymbol(out, g_timeline_r, sizeof(g_timeline_r));
+}
+#endif
+
 // ---------------------------------------------------------------------------- the reduction kernel
 // MODE 0 p2p moments, 1 point-to-plane, 2 symmetric (needs means in state), 3 sums only
 template <int MODE, bool FUSED>
@@ -285,6 +294,10 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
         if (!FUSED) wf_n = a.match_w[i];
     }
     const int state_iter = a.state->iter;
+#ifdef ICP_TIMELINE
+    const bool tl_on = state_iter == 12 && threadIdx.x == 0 && blockIdx.x < 511;
+    if (tl_on) g_timeline_r[blockIdx.x][0] = tlr_now();
+#endif
     LoopRegs lr; lr.status = 0; lr.iters_done = 0; lr.iter = state_iter;
     if (threadIdx.x == 0) { lr.status = a.state->status; lr.iters_done = a.state->iters_done; }
     if (threadIdx.x < 16) P[threadIdx.x] = a.state->pose[threadIdx.x];
@@ -407,6 +420,9 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
         }
     }
     if (a.profile && threadIdx.x == 0) t_loop = global_timer_ns();
+#ifdef ICP_TIMELINE
+    if (tl_on) g_timeline_r[blockIdx.x][1] = tlr_now();
+#endif
     if (!grid_reduce_row<ICP_REDUCE_THREADS>(v, a.partials, &a.state->ticket, red, fin, &is_last, a.solve ? &a.peer : nullptr, a.state)) return;
     if (threadIdx.x == 0) {
         if (a.profile) { a.state->prof[1] = t_start; a.state->prof[2] = t_loop; a.state->prof[3] = global_timer_ns(); }
@@ -414,6 +430,9 @@ __global__ void __launch_bounds__(ICP_REDUCE_THREADS) reduce_kernel(const Reduce
         else if (MODE == 3) finish_sums(a.state, fin[0]);
         else finish_row_local(a.state, fin[0], MODE, a.pose_history, P, mS, mD, lr);
         if (a.profile) { __threadfence(); a.state->prof[4] = global_timer_ns(); }
+#ifdef ICP_TIMELINE
+        if (state_iter == 12) g_timeline_r[511][0] = tlr_now();
+#endif
     }
 }
 
