@@ -91,7 +91,7 @@ struct icp_gpu_ctx {
     std::vector<int> src_rank;         // host copy: original source index -> position in the sorted source
     bool src_rank_valid = false;
     // target grid
-    DeviceBuf grid, bbox, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, adj, adj_box, adj1, adj1_box;
+    DeviceBuf grid, bbox, bvh_box, bvh_desc, leaf_start, leaf_rank, node_rank, child_start, adj, adj_box, adj1, adj1_box, adj_gap;
     // sort / tree scratch, one set per cloud (the two builds run on different streams)
     struct SortBufs { DeviceBuf keys_a, keys_b, idx_a, idx_b, hist, msd; unsigned int* keys_sorted = nullptr; int msd_shift = 0; };
     SortBufs tsort, ssort;
@@ -266,7 +266,8 @@ int build_grid(icp_gpu_ctx* ctx) {
     // adjacency lists for up to n/4 leaves (a healthy tree has ~n/20); a cloud with more leaves simply gets no shortcut for the rest
     ctx->adj_capacity = (int)(n1 / 4 + 64);
     ctx->adj1_capacity = (int)(n1 / 32 + 64);
-    if (ensure(ctx, ctx->adj, (size_t)ctx->adj_capacity * 32 * 4) || ensure(ctx, ctx->adj_box, (size_t)ctx->adj_capacity * 2 * sizeof(float4)) ||
+    if (ensure(ctx, ctx->adj, (size_t)ctx->adj_capacity * 32 * 4) || ensure(ctx, ctx->adj_gap, (size_t)ctx->adj_capacity * 32 * 4) ||
+        ensure(ctx, ctx->adj_box, (size_t)ctx->adj_capacity * 2 * sizeof(float4)) ||
         ensure(ctx, ctx->adj1, (size_t)ctx->adj1_capacity * 32 * 4) || ensure(ctx, ctx->adj1_box, (size_t)ctx->adj1_capacity * 2 * sizeof(float4)))
         return ICP_GPU_E_CUDA;
     int launches = 0;
@@ -289,7 +290,8 @@ int build_grid(icp_gpu_ctx* ctx) {
                                  (unsigned int*)ctx->adj1.p, (float4*)ctx->adj1_box.p, ctx->adj1_capacity, 1, nullptr, nullptr, nullptr, 0, ctx->n_sms, ts, &launches));
     CU(icp_launch_leaf_adjacency((const BvhDesc*)ctx->bvh_desc.p, (const float4*)ctx->bvh_box.p, (const unsigned int*)ctx->child_start.p,
                                  (unsigned int*)ctx->adj.p, (float4*)ctx->adj_box.p, ctx->adj_capacity, 0, (const unsigned int*)ctx->node_rank.p,
-                                 bottom_up ? (const unsigned int*)ctx->adj1.p : nullptr, (const float4*)ctx->adj1_box.p, ctx->adj1_capacity, ctx->n_sms, ts, &launches));
+                                 bottom_up ? (const unsigned int*)ctx->adj1.p : nullptr, (const float4*)ctx->adj1_box.p, ctx->adj1_capacity, ctx->n_sms, ts, &launches,
+                                 (float*)ctx->adj_gap.p));
     CU(cudaEventRecord(ctx->ev[1], ts));
     if (ts != ctx->stream) { CU(cudaEventRecord(ctx->ev_index_ready, ts)); ctx->index_pending = true; }
     ctx->stats.n_kernel_launches += (uint64_t)launches;
@@ -456,6 +458,7 @@ void fill_match_args(icp_gpu_ctx* c, MatchArgs& a, int algo, int desc_index, boo
     a.bvh_box = (const float4*)c->bvh_box.p; a.bvh = (const BvhDesc*)c->bvh_desc.p; a.leaf_start = (const unsigned int*)c->leaf_start.p;
     a.leaf_rank = (const unsigned int*)c->leaf_rank.p; a.child_start = (const unsigned int*)c->child_start.p;
     a.adj = (const unsigned int*)c->adj.p; a.adj_box = (const float4*)c->adj_box.p; a.adj_capacity = c->adj_capacity;
+    a.adj_gap = getenv("ICP_GPU_NO_ADJ_GAP") ? nullptr : (const float*)c->adj_gap.p;   // tuning knob (A/B measurement)
     a.nn_leaf = (int*)c->nn_leaf.p;
     a.adj1 = (const unsigned int*)c->adj1.p; a.adj1_box = (const float4*)c->adj1_box.p; a.adj1_capacity = c->adj1_capacity;
     a.node_rank = (const unsigned int*)c->node_rank.p;
@@ -780,7 +783,7 @@ int icp_gpu_destroy(icp_gpu_ctx* ctx) {
                          &ctx->grid, &ctx->bbox, &ctx->sbbox, &ctx->lv_flags, &ctx->lv_tiles, &ctx->delta_a, &ctx->delta_b, &ctx->tsort.keys_a, &ctx->tsort.keys_b, &ctx->tsort.idx_a, &ctx->tsort.idx_b, &ctx->tsort.hist, &ctx->tsort.msd, &ctx->ssort.keys_a, &ctx->ssort.keys_b, &ctx->ssort.idx_a, &ctx->ssort.idx_b, &ctx->ssort.hist, &ctx->ssort.msd, &ctx->state, &ctx->desc, &ctx->mask,
                          &ctx->match_pos, &ctx->match_w, &ctx->match_idx, &ctx->partials, &ctx->pose_dev, &ctx->history,
                          &ctx->src_raw_pts, &ctx->src_raw_nrm, &ctx->sgrid, &ctx->order_dev,
-                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
+                         &ctx->nn_pos, &ctx->bvh_box, &ctx->bvh_desc, &ctx->leaf_start, &ctx->leaf_rank, &ctx->node_rank, &ctx->child_start, &ctx->qbuf, &ctx->adj, &ctx->adj_box, &ctx->adj_gap, &ctx->adj1, &ctx->adj1_box, &ctx->voxel_table, &ctx->nn_leaf, &ctx->seedbuf,
                          &ctx->nrm_out_dev, &ctx->prep_in, &ctx->prep_tmp, &ctx->prep_out, &ctx->gt_src, &ctx->gt_ref, &ctx->met_partial, &ctx->met_out};
     for (DeviceBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (DeviceBuf& b : ctx->scratch) if (b.p) cudaFree(b.p);

@@ -897,7 +897,7 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
                                                                          unsigned int* __restrict__ adj, float4* __restrict__ adj_box,
                                                                          int capacity, float r_factor, int lv,
                                                                          const unsigned int* __restrict__ node_rank, const unsigned int* __restrict__ adj1,
-                                                                         const float4* __restrict__ adj1_box, int adj1_capacity) {
+                                                                         const float4* __restrict__ adj1_box, int adj1_capacity, float* __restrict__ adj_gap) {
     __shared__ unsigned int s_node[ADJ_WARPS][32 * ICP_BVH_MAX_LEVELS];
     __shared__ unsigned int s_list[ADJ_WARPS][64];
     const BvhDesc b = *bvh;
@@ -992,7 +992,27 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
             if (ok) break;
         }
         __syncwarp();
-        if (lane < count && ok) adj[(size_t)l * 32 + lane] = list[lane];
+        if (adj_gap && ok) {
+            // Entries in the order of their squared box-to-box gap to this node (rounded down), the gaps stored with them: a search
+            // whose best candidate p lies in this node's box at distance r from the query needs only the entries with gap <= 2r
+            // (a point x within r of the query is within 2r of p, and gap <= |p - x|), and stops at the first one beyond.
+            float gq = INFINITY; unsigned int e = 0u;
+            if (lane < count) {
+                e = list[lane];
+                const float4 elo = box[2 * (size_t)(b.offset[lv] + e)], ehi = box[2 * (size_t)(b.offset[lv] + e) + 1];
+                const float gx = fmaxf(fmaxf(__fsub_rd(elo.x, mhi.x), __fsub_rd(mlo.x, ehi.x)), 0.f);
+                const float gy = fmaxf(fmaxf(__fsub_rd(elo.y, mhi.y), __fsub_rd(mlo.y, ehi.y)), 0.f);
+                const float gz = fmaxf(fmaxf(__fsub_rd(elo.z, mhi.z), __fsub_rd(mlo.z, ehi.z)), 0.f);
+                gq = __fadd_rd(__fadd_rd(__fmul_rd(gx, gx), __fmul_rd(gy, gy)), __fmul_rd(gz, gz));
+            }
+            int rank = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float gk = __shfl_sync(FULL, gq, k);
+                rank += (gk < gq || (gk == gq && k < lane)) ? 1 : 0;
+            }
+            if (lane < count) { adj[(size_t)l * 32 + rank] = e; adj_gap[(size_t)l * 32 + rank] = gq; }
+        } else if (lane < count && ok) adj[(size_t)l * 32 + lane] = list[lane];
         if (lane == 0) {
             // the inflated box exactly as the query above used it (so that "ball inside this box" implies "every leaf the
             // ball meets is in the list"); inverted when there is no list
@@ -1011,14 +1031,14 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) leaf_adjacency_kernel(const Bv
 // level 1 first; the level-0 call then takes the level-1 lists (node_rank, adj1, adj1_box; nullable = walk from the root)
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
                                       float4* adj_box, int capacity, int level, const unsigned int* node_rank, const unsigned int* adj1,
-                                      const float4* adj1_box, int adj1_capacity, int n_sms, cudaStream_t s, int* n_launches) {
+                                      const float4* adj1_box, int adj1_capacity, int n_sms, cudaStream_t s, int* n_launches, float* adj_gap) {
     long long nb = ((long long)capacity + ADJ_WARPS - 1) / ADJ_WARPS;
     if (nb > 16ll * n_sms) nb = 16ll * n_sms;
     if (nb < 1) nb = 1;
     float r_factor = 2.0f;
     if (const char* e = getenv("ICP_GPU_ADJ_FACTOR")) r_factor = (float)atof(e);   // tuning knob
     leaf_adjacency_kernel<<<(int)nb, ADJ_WARPS * 32, 0, s>>>(bvh_dev, box, child_start, adj, adj_box, capacity, r_factor, level,
-                                                             node_rank, adj1, adj1_box, adj1_capacity);
+                                                             node_rank, adj1, adj1_box, adj1_capacity, adj_gap);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -144,6 +144,7 @@ struct MatchArgs {
     // adj_box[2*l] = {lo - R, n as int bits}, adj_box[2*l+1] = {hi + R, _}; an inverted box (lo > hi) means "no list".
     // A query whose search ball lies inside the inflated box needs no tree walk.
     const unsigned int* adj; const float4* adj_box; int adj_capacity;
+    const float* adj_gap;    // squared box-to-box gap of every list entry to its leaf, ascending along the list (rounded down)
     // the same one level up: adj1[32*m ..] = the level-1 nodes (m itself included) whose box meets box(m) inflated; node_rank
     // maps a leaf to its level-1 node (node_rank[coffset[1] + leaf + 1] - 1)
     const unsigned int* adj1; const float4* adj1_box; int adj1_capacity; const unsigned int* node_rank;
@@ -236,7 +237,8 @@ cudaError_t icp_launch_voxel_level(const float4* pts_sorted, const float4* nrm_s
 // the level-1 lists (node_rank, adj1, adj1_box; nullable = every query walks from the root).
 cudaError_t icp_launch_leaf_adjacency(const BvhDesc* bvh_dev, const float4* box, const unsigned int* child_start, unsigned int* adj,
                                       float4* adj_box, int capacity, int level, const unsigned int* node_rank, const unsigned int* adj1,
-                                      const float4* adj1_box, int adj1_capacity, int n_sms, cudaStream_t s, int* n_launches);
+                                      const float4* adj1_box, int adj1_capacity, int n_sms, cudaStream_t s, int* n_launches,
+                                      float* adj_gap = nullptr);   // adj_gap: sort the entries by their gap to the node and store the gaps
 cudaError_t icp_launch_extract_order(const float4* pts_sorted, int n, int* order, cudaStream_t s);
 cudaError_t icp_launch_fill_int(int* p, int n, int v, cudaStream_t s);
 // Seeds (nn_pos / nn_leaf) for the queries that have none (reset: for every query), from the target's sorted keys at the pose in `st`.

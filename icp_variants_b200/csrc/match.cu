@@ -334,7 +334,13 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MIN_BLOCKS * 256 / PREP_THR
                             // two phases, so that the lanes of a warp scan their leaves side by side instead of one
                             // list position at a time: first the box tests, then the scans of the leaves that passed
                             unsigned int todo = 0;
+                            // the list is in the order of the entries' gaps to the seed leaf's box: with the best candidate inside that
+                            // box, an entry whose gap exceeds twice the search radius (4 x in squares, rounded up) cannot hold a nearer
+                            // point, nor can any entry after it
+                            const float* gap = a.adj_gap ? a.adj_gap + (size_t)seed_leaf * 32 : nullptr;
+                            const float lim = (gap && bleaf == seed_leaf) ? __fmul_ru(__fmul_ru(4.0f, b.d), 1.00001f) : FLT_BIG;
                             for (int j = 0; j < na; ++j) {
+                                if (gap && __ldg(&gap[j]) > lim) break;
                                 const unsigned int leaf = __ldg(&list[j]);
                                 const float clb = box_dist2c<COLOR>(q, __ldg(&a.bvh_box[2 * (size_t)leaf]), __ldg(&a.bvh_box[2 * (size_t)leaf + 1]));
                                 if (!(clb > b.d)) todo |= 1u << j;
