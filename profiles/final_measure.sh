@@ -11,6 +11,12 @@ SWEEPS=1720 BEAMS=1744 python profiles/measure_reduce_profile.py > $F/reduce_pro
 python profiles/measure_sequence.py > $F/sequence.json 2> $F/sequence.err
 python profiles/measure_normals.py > $F/normals_depth.json 2> $F/normals_depth.err
 python profiles/probe_pair_queue.py > $F/pair_queue_contexts.txt 2> $F/pair_queue_contexts.err
+python profiles/probe_sequence_frame.py > $F/sequence_frame_breakdown.json 2> $F/sequence_frame_breakdown.err
+# per-warp timeline of one iteration, one and two chunk chains (diagnostic build of the library, removed again afterwards)
+make -C icp_variants_b200/csrc timeline > $F/make_timeline.log 2>&1
+ICP_GPU_MATCH_CHUNKS=1 python profiles/probe_timeline.py > $F/timeline_1chunk.json 2> $F/timeline_1chunk.err
+ICP_GPU_MATCH_CHUNKS=2 python profiles/probe_timeline.py > $F/timeline_2chunks.json 2> $F/timeline_2chunks.err
+rm -f icp_variants_b200/lib/libicp_gpu_timeline.so icp_variants_b200/lib/*_timeline.o
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-multi"
 # launch lists of the bench command: caches as the program leaves them (--cache-control none: the figures that add up to the step),
 # and ncu's default (flushed before every launch: cold-cache, compare shares only)
