@@ -612,7 +612,6 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
         key.push_back(plan.n_iters);
         key.push_back(ctx->peer_world); key.push_back(ctx->peer_rank); key.push_back((long long)ctx->peer_epoch);
         if (!ctx->graph_exec || key != ctx->graph_key) {
-            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t before = ctx->stats.n_kernel_launches;
@@ -620,7 +619,15 @@ int start_registration(icp_gpu_ctx* ctx, const float pose_in[16], icp_gpu_timing
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             if (ce != cudaSuccess) return fail(ctx, ICP_GPU_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+            // A new cloud size (every frame of a sequence) changes launch shapes and arguments, not the graph's topology: the
+            // instantiated graph is updated in place, which is several times cheaper than instantiating a new one.
+            bool updated = false;
+            if (ctx->graph_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess;
+                if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            }
+            ce = updated ? cudaSuccess : cudaGraphInstantiate(&ctx->graph_exec, g, 0);
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) { ctx->graph_exec = nullptr; return fail(ctx, ICP_GPU_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
             ctx->graph_key = key;

@@ -633,8 +633,11 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
 // compact image region: the block stages the union of its search windows (target points, row by row, coalesced) in
 // shared memory and every thread scans its own 25x25 window there.  Blocks whose union does not fit fall back to
 // reading the (L2-resident) target map directly.
-#define PROJ_THREADS 256
 #define PROJ_TILE_MAX 2800     // float4 entries (44.8 KB static shared memory: five blocks per SM)
+// PROJ_THREADS = 256: full frames and large sources.  64: a small source (every 8th valid pixel of a frame, main.cpp:291-298: ~25 k
+// queries) -- 256-query blocks would be fewer than the SMs, and the window union of 256 points that lie 8 pixels apart does not fit
+// the stage (47 x 47 entries for 64 of them do).
+template <int PROJ_THREADS>
 __global__ void __launch_bounds__(PROJ_THREADS, 5) projective_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
     __shared__ float4 tile[PROJ_TILE_MAX];
@@ -755,9 +758,15 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
     const int T = ICP_MATCH_THREADS;
     int launches = 0;
     if (algorithm == 2) {
-        const unsigned int nb = a.proj_tiled ? ((a.width + 31u) / 32u) * ((a.height + PROJ_THREADS / 32 - 1u) / (PROJ_THREADS / 32))
-                                             : (unsigned int)((a.n_src + PROJ_THREADS - 1) / PROJ_THREADS);
-        projective_kernel<<<nb, PROJ_THREADS, 0, s>>>(a); ++launches;
+        static const bool no_small = getenv("ICP_GPU_NO_SMALL_PROJ_BLOCKS") != nullptr;                // tuning knob (A/B measurement)
+        if (!a.proj_tiled && a.n_src < 2 * 256 * n_sms && !no_small) {
+            projective_kernel<64><<<(unsigned int)((a.n_src + 63) / 64), 64, 0, s>>>(a);
+        } else {
+            const unsigned int nb = a.proj_tiled ? ((a.width + 31u) / 32u) * ((a.height + 256 / 32 - 1u) / (256 / 32))
+                                                 : (unsigned int)((a.n_src + 256 - 1) / 256);
+            projective_kernel<256><<<nb, 256, 0, s>>>(a);
+        }
+        ++launches;
     } else if (algorithm == 1) {
         const long long threads = (long long)a.n_src * 32;
         const int nb = (int)((threads + T - 1) / T);
