@@ -275,11 +275,16 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     """Config 5a: the 44 pairs of an ETH-Apartment-shaped sequence dealt round-robin (parallel.shard_pairs) to the ranks; every
     rank runs its queue through sequence.alignPairs (host arrays in, poses out, three contexts per GPU so that the upload and the
     loops of different pairs overlap).  No collective on the data path; time = CUDA events around the queue, max over ranks."""
-    from icp_variants_b200 import parallel, sequence
+    from icp_variants_b200 import parallel, sequence, synth
     mine = parallel.shard_pairs(N_SEQUENCE_PAIRS, world, rank)
     t0 = time.perf_counter()
     pairs = [make_pair_device_normals(ctx, k, args.sweeps, args.beams) for k in mine]
     t_gen = time.perf_counter() - t0
+    if not args.pageable_queue:
+        # the scans wait in page-locked memory, as a reader that feeds a GPU would leave them (from pageable arrays every upload is a
+        # staged copy on the host thread that drives all three contexts: 283 instead of 291 pairs/s on one GPU)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()          # noqa: E731
+        pairs = [tuple(synth.Cloud(pin(c.points), pin(c.normals), pin(c.colors)) for c in pr[:2]) + tuple(pr[2:]) for pr in pairs]
     cfg = capi.default_config()
     cfg.metric, cfg.minimizer, cfg.matching, cfg.n_iterations = 1, 0, 0, N_ITER
     cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = args.max_dist2, 2, 0
@@ -314,7 +319,7 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     return {"pairs": N_SEQUENCE_PAIRS, "n_gpus": world, "pairs_per_s": N_SEQUENCE_PAIRS / (ms * 1e-3), "ms_total": ms,
             "pairs_on_the_longest_queue": longest, "ideal_speedup_over_one_gpu": N_SEQUENCE_PAIRS / longest, "all_pairs_converged_30_iterations": ok,
             "points_per_scan": len(pairs[0][0]) if pairs else None, "scaling": "strong", "collective": "none",
-            "path": "sequence.alignPairs: icp_gpu_set_target / set_source (pageable host arrays) + icp_gpu_estimate_pose_async / _finish, three contexts (streams) per GPU",
+            "path": "sequence.alignPairs: icp_gpu_set_target / set_source (%s host arrays) + icp_gpu_estimate_pose_async / _finish, three contexts (streams) per GPU" % ("pageable" if args.pageable_queue else "page-locked"),
             "input_generation_s_rank0": t_gen}
 
 
@@ -411,6 +416,8 @@ def main():
     ap.add_argument("--max-dist2", type=float, default=10.0, help="squared matching distance; alignETH uses 10 (main.cpp:361)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multi", action="store_true", help="skip the config-5 workloads (pair_queue_44, sharded_3m)")
+    ap.add_argument("--pageable-queue", action="store_true", help="pair_queue_44 from pageable host arrays (default: page-locked)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip sharded_3m only")
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -572,10 +579,11 @@ def main():
                 line["flann_match_rate"] = fl["match_rate_vs_exact"][0]
     if not args.no_multi:
         pq = pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args)
-        sh = sharded_block(torch, dist, capi, ctx, stream, world, rank, dev, args)
+        sh = None if args.no_sharded else sharded_block(torch, dist, capi, ctx, stream, world, rank, dev, args)
         if rank == 0:
             line["pair_queue_44"] = pq
-            line["sharded_3m"] = sh
+            if sh is not None:
+                line["sharded_3m"] = sh
     if rank == 0:
         print(json.dumps(line))
     ctx.close()

@@ -22,8 +22,11 @@ B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-multi"
 # and ncu's default (flushed before every launch: cold-cache, compare shares only)
 $B > $F/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none -c 700 --csv --log-file $F/launches_hot.csv $B > $F/ncu_launches_hot.log 2>&1
 $B > $F/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $F/launches.csv $B > $F/ncu_launches.log 2>&1
-# one full capture of the iteration kernels (a steady-state iteration) and of the index-build kernels
+# one full capture of the iteration kernels (a steady-state iteration) and of the index-build kernels; the iteration kernels with ONE
+# chunk chain (ICP_GPU_MATCH_CHUNKS=1), so that a launch covers all queries like the launches bench.py's roofline object times
+export ICP_GPU_MATCH_CHUNKS=1
 $B > $F/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"knn_prep|knn_bvh|reduce_kernel" -s 300 -c 3 -f -o $F/prof_hot $B > $F/ncu_full.log 2>&1
+unset ICP_GPU_MATCH_CHUNKS
 python profiles/measure_build.py > $F/plain_build.log 2>&1 && ncu --set full --clock-control none --cache-control none --import-source on -k regex:"pack_bbox|keys_kernel|radix_|gather_records|level_|bvh_level|upper_levels|leaf_adjacency|seed_from_keys" -s 60 -c 24 -f -o $F/prof_build python profiles/measure_build.py > $F/ncu_build.log 2>&1
 python profiles/profile_projective.py > $F/plain_proj.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:projective -s 4 -c 1 -f -o $F/prof_proj python profiles/profile_projective.py > $F/ncu_proj.log 2>&1
 tail -c 400 $F/bench_n1.json
