@@ -637,17 +637,17 @@ __global__ void __launch_bounds__(ICP_MATCH_THREADS) knn_brute_kernel(const Matc
 // PROJ_THREADS = 256: full frames and large sources.  64: a small source (every 8th valid pixel of a frame, main.cpp:291-298: ~25 k
 // queries) -- 256-query blocks would be fewer than the SMs, and the window union of 256 points that lie 8 pixels apart does not fit
 // the stage (47 x 47 entries for 64 of them do).
-template <int PROJ_THREADS>
-__global__ void __launch_bounds__(PROJ_THREADS, 5) projective_kernel(const MatchArgs a) {
+template <int PROJ_THREADS, int TILE_MAX, int MIN_BLOCKS>
+__global__ void __launch_bounds__(PROJ_THREADS, MIN_BLOCKS) projective_kernel(const MatchArgs a) {
     __shared__ PoseSm sm;
-    __shared__ float4 tile[PROJ_TILE_MAX];
+    __shared__ float4 tile[TILE_MAX];
     __shared__ unsigned int s_box[4][PROJ_THREADS / 32];
     if (a.desc_index < 0 && a.state_ro->converged) return;
     load_pose(sm, a.state_ro);
     const IterDesc d = a.desc[a.desc_index >= 0 ? a.desc_index : a.state_ro->iter];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // Which query this thread answers.  A full-frame source (one point per pixel, original order: a.proj_tiled) is cut
-    // into 32 x 8 pixel tiles, one per block: the windows of a tile overlap in a (32+24) x (8+24) region (plus the
+    // into 32 x (PROJ_THREADS / 32) pixel tiles, one per block: the windows of a tile overlap in a (32+24) x (rows+24) region (plus the
     // inter-frame motion), which always fits the shared-memory stage, and the lanes of a warp read consecutive entries
     // of it (no bank conflicts).  Any other source is taken 256 consecutive points of its Morton order at a time.
     int p; bool in;
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projective_kernel(const Match
     // neighbouring columns of possibly different rows (the frames are rotated against each other), so with pitch = 0 mod 8 the bank
     // group is the column alone.  Round 1 used the raw union width (834 k conflicts per launch); an odd pitch measured 2.4 M.
     const unsigned int tp = (tw + 7u) & ~7u;
-    const bool staged = any_window && (unsigned long long)tp * th <= PROJ_TILE_MAX;      // block-uniform
+    const bool staged = any_window && (unsigned long long)tp * th <= TILE_MAX;           // block-uniform
     if (any_window && !staged && threadIdx.x == 0) ++nd;                                // work counter: blocks that fall back to global reads
     if (staged) {
         for (unsigned int k = threadIdx.x; k < tw * th; k += PROJ_THREADS) {
@@ -760,11 +760,15 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
     if (algorithm == 2) {
         static const bool no_small = getenv("ICP_GPU_NO_SMALL_PROJ_BLOCKS") != nullptr;                // tuning knob (A/B measurement)
         if (!a.proj_tiled && a.n_src < 2 * 256 * n_sms && !no_small) {
-            projective_kernel<64><<<(unsigned int)((a.n_src + 63) / 64), 64, 0, s>>>(a);
+            projective_kernel<64, PROJ_TILE_MAX, 5><<<(unsigned int)((a.n_src + 63) / 64), 64, 0, s>>>(a);
+        } else if (a.proj_tiled) {
+            // full frames: 32 x 4 pixel tiles, 2400 blocks of 128 threads at 640 x 480 over 148 x 6 slots -- with 32 x 8 tiles the 1200
+            // blocks were 1.6 waves of long blocks (C3: 4.35 -> 4.20 ms per 35 iterations).  The stage holds the (32+24) x (4+24) union
+            // plus 8 pixels of inter-frame motion either way.
+            const unsigned int nb = ((a.width + 31u) / 32u) * ((a.height + 128 / 32 - 1u) / (128 / 32));
+            projective_kernel<128, 2304, 6><<<nb, 128, 0, s>>>(a);
         } else {
-            const unsigned int nb = a.proj_tiled ? ((a.width + 31u) / 32u) * ((a.height + 256 / 32 - 1u) / (256 / 32))
-                                                 : (unsigned int)((a.n_src + 256 - 1) / 256);
-            projective_kernel<256><<<nb, 256, 0, s>>>(a);
+            projective_kernel<256, PROJ_TILE_MAX, 5><<<(unsigned int)((a.n_src + 256 - 1) / 256), 256, 0, s>>>(a);
         }
         ++launches;
     } else if (algorithm == 1) {
