@@ -28,5 +28,5 @@ export ICP_GPU_MATCH_CHUNKS=1
 $B > $F/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"knn_prep|knn_bvh|reduce_kernel" -s 300 -c 3 -f -o $F/prof_hot $B > $F/ncu_full.log 2>&1
 unset ICP_GPU_MATCH_CHUNKS
 python profiles/measure_build.py > $F/plain_build.log 2>&1 && ncu --set full --clock-control none --cache-control none --import-source on -k regex:"pack_bbox|keys_kernel|radix_|gather_records|level_|bvh_level|upper_levels|leaf_adjacency|seed_from_keys" -s 60 -c 24 -f -o $F/prof_build python profiles/measure_build.py > $F/ncu_build.log 2>&1
-python profiles/profile_projective.py > $F/plain_proj.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:projective -s 4 -c 1 -f -o $F/prof_proj python profiles/profile_projective.py > $F/ncu_proj.log 2>&1
+python profiles/profile_projective.py > $F/plain_proj.log 2>&1 && ncu --set full --clock-control none --cache-control none --import-source on -k regex:projective -s 40 -c 1 -f -o $F/prof_proj python profiles/profile_projective.py > $F/ncu_proj.log 2>&1
 tail -c 400 $F/bench_n1.json
