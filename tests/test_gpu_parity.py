@@ -627,6 +627,37 @@ def test_bench_config_as_run_370k_30_iterations(ctx, full_eth_pair):
     assert worst[0] <= ROT_TOL and worst[1] <= TRANS_TOL, worst        # every iteration of the trajectory, not only the last
 
 
+def test_chunk_chains_and_adjacency_early_exit_change_no_bit(full_eth_pair, monkeypatch):
+    """How the search is scheduled is invisible in the results: one, two or three {prep, walk} chunk chains per iteration
+    (ICP_GPU_MATCH_CHUNKS; two is the default from 131 072 queries on), launched one by one or as a graph, and the fast path with
+    or without its early exit from the gap-sorted adjacency lists (ICP_GPU_NO_ADJ_GAP) give the same trajectory and the same
+    correspondences bit for bit.  The variables are read when a registration is enqueued; a fresh context per variant keeps the
+    graph caches apart."""
+    src, tgt, _ = full_eth_pair
+    runs = []
+    for env in ({"ICP_GPU_MATCH_CHUNKS": "1"}, {}, {"ICP_GPU_MATCH_CHUNKS": "3"}, {"ICP_GPU_NO_ADJ_GAP": "1"}, {"ICP_GPU_MATCH_CHUNKS": "2", "use_graph": 0}):
+        for k in ("ICP_GPU_MATCH_CHUNKS", "ICP_GPU_NO_ADJ_GAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            if k.startswith("ICP_"):
+                monkeypatch.setenv(k, v)
+        c = capi.Context(0)
+        try:
+            cfg = capi.default_config()
+            cfg.metric, cfg.n_iterations, cfg.max_distance_sq, cfg.nn_algorithm, cfg.collect_stats = 1, 6, 10.0, 2, 0
+            cfg.use_graph = env.get("use_graph", 1)
+            c.set_config(cfg)
+            load(c, src, tgt)
+            pose, hist, n_it = c.estimate_pose()
+            idx, w = c.query_matches(pose)
+            runs.append((pose, hist, idx, w))
+        finally:
+            c.close()
+    for pose, hist, idx, w in runs[1:]:
+        assert np.array_equal(pose, runs[0][0]) and np.array_equal(hist, runs[0][1])
+        assert np.array_equal(idx, runs[0][2]) and np.array_equal(w, runs[0][3])
+
+
 def test_reupload_of_the_same_clouds_gives_identical_bits(ctx, full_eth_pair):
     """The index is a function of the cloud alone: the radix sort ranks by (cell code, original index) without atomics, so
     uploading the same pair again (and into a second context) reproduces the correspondences, every pose of the trajectory and
