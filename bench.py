@@ -19,8 +19,9 @@ estimatePose, ICPOptimizer.h:532-535).
            place against the stand-ins of oracle/ref_shim) on the same pair: one FULL 30-iteration registration on all host
            threads, a bounded 1-thread sample, and the FLANN-like approximate matcher (cv2.flann_Index, 1 tree, 16 checks)
            with its match rate against the exact search
-  pair_queue_44  config 5a: a 44-pair ETH-shaped sequence dealt round-robin to the ranks (one queue per GPU, no collective),
-           host arrays in, poses out -- pairs/s over all ranks and the ceiling 44 / ceil(44 / N)
+  pair_queue_44  config 5a: a 44-pair ETH-shaped sequence, one queue per GPU, no collective on the data path: the ranks draw pair
+           indices from a shared ticket counter (--static-deal: round-robin), host arrays in, poses out -- pairs/s over all
+           ranks and the ceiling 44 / ceil(44 / N)
   sharded_3m     config 5b: ONE 3 M-point pair sharded by source points over the ranks, the per-iteration all-reduce of the 28-double
            row fused into the reduction kernel over NVLink peer memory (icp_gpu_peer_*), next to an ncclAllReduce on the stream
 
@@ -276,10 +277,16 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     rank runs its queue through sequence.alignPairs (host arrays in, poses out, three contexts per GPU so that the upload and the
     loops of different pairs overlap).  No collective on the data path; time = CUDA events around the queue, max over ranks."""
     from icp_variants_b200 import parallel, sequence, synth
+    dynamic = world > 1 and not args.static_deal
     mine = parallel.shard_pairs(N_SEQUENCE_PAIRS, world, rank)
     t0 = time.perf_counter()
-    pairs = [make_pair_device_normals(ctx, k, args.sweeps, args.beams) for k in mine]
+    pairs = {k: make_pair_device_normals(ctx, k, args.sweeps, args.beams) for k in mine}     # (also fills the /tmp cache)
+    if dynamic:
+        # every rank must be able to read every pair: the ranks generated disjoint shares into the cache, now each loads the rest
+        dist.barrier()
+        pairs = {k: pairs[k] if k in pairs else make_pair_device_normals(ctx, k, args.sweeps, args.beams) for k in range(N_SEQUENCE_PAIRS)}
     t_gen = time.perf_counter() - t0
+    pairs = [pairs[k] for k in sorted(pairs)]
     if not args.pageable_queue:
         # the scans wait in page-locked memory, as a reader that feeds a GPU would leave them (from pageable arrays every upload is a
         # staged copy on the host thread that drives all three contexts: 283 instead of 291 pairs/s on one GPU)
@@ -292,22 +299,27 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     # registration is a chain of latency-bound launches that leaves most of the machine idle: 5.0 -> 2.7 ms per pair, measured with
     # profiles/probe_pair_queue.py), and the upload of the next pair overlaps the loops of the others.
     ctxs = [capi.Context(dev.index) for _ in range(3)]
-    ms = None
+    ms, res, n_mine = None, [], 0
     for rep in range(2):                                   # the first pass warms allocations and graphs
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        # dynamic deal: the ranks draw pair indices from one shared counter (a fresh key per pass), so a rank with cheap pairs takes more
+        tickets = parallel.PairTickets(N_SEQUENCE_PAIRS, key=f"icp_bench_pair_queue_pass{rep}") if dynamic else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)                                  # the stream is idle: the events bracket the queue, which ends with every
-        res = sequence.alignPairs(ctxs, pairs, cfg)        # context's stream synchronised (estimate_pose_finish)
+        res = sequence.alignPairs(ctxs, pairs, cfg, tickets=tickets)   # context's stream synchronised (estimate_pose_finish)
         torch.cuda.synchronize()
         e1.record(stream)
         e1.synchronize()
         ms = e0.elapsed_time(e1)
     for c in ctxs:
         c.close()
-    print(f"bench: rank {rank}: pair queue of {len(pairs)} pairs {ms:.1f} ms", file=sys.stderr)
-    ok = all(r is not None and r.error is None and r.nIterations == N_ITER for r in res)
+    done = [r for r in res if r is not None]
+    n_mine = len(done)
+    print(f"bench: rank {rank}: pair queue: {n_mine} pairs in {ms:.1f} ms ({'dynamic' if dynamic else 'static'} deal)", file=sys.stderr)
+    ok = all(r.error is None and r.nIterations == N_ITER for r in done) and (dynamic or n_mine == len(pairs))
+    longest = n_mine
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -315,9 +327,20 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
         o = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
         dist.all_reduce(o, op=dist.ReduceOp.MIN)
         ok = bool(o.item())
-    longest = -(-N_SEQUENCE_PAIRS // world)
+        c = torch.zeros(world, dtype=torch.int64, device=dev)
+        c[rank] = n_mine
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        counts = [int(x) for x in c.tolist()]
+        ok = ok and sum(counts) == N_SEQUENCE_PAIRS           # every pair registered exactly once
+        longest = max(counts)
+    else:
+        counts = [n_mine]
+    static_longest = -(-N_SEQUENCE_PAIRS // world)
     return {"pairs": N_SEQUENCE_PAIRS, "n_gpus": world, "pairs_per_s": N_SEQUENCE_PAIRS / (ms * 1e-3), "ms_total": ms,
-            "pairs_on_the_longest_queue": longest, "ideal_speedup_over_one_gpu": N_SEQUENCE_PAIRS / longest, "all_pairs_converged_30_iterations": ok,
+            "deal": ("dynamic: pair indices drawn from one shared ticket counter (parallel.PairTickets, the process group's store)" if dynamic
+                     else "static round-robin (parallel.shard_pairs)"),
+            "pairs_per_rank": counts, "pairs_on_the_longest_queue": longest,
+            "ideal_speedup_over_one_gpu": N_SEQUENCE_PAIRS / static_longest, "all_pairs_converged_30_iterations": ok,
             "points_per_scan": len(pairs[0][0]) if pairs else None, "scaling": "strong", "collective": "none",
             "path": "sequence.alignPairs: icp_gpu_set_target / set_source (%s host arrays) + icp_gpu_estimate_pose_async / _finish, three contexts (streams) per GPU" % ("pageable" if args.pageable_queue else "page-locked"),
             "input_generation_s_rank0": t_gen}
@@ -416,6 +439,7 @@ def main():
     ap.add_argument("--max-dist2", type=float, default=10.0, help="squared matching distance; alignETH uses 10 (main.cpp:361)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multi", action="store_true", help="skip the config-5 workloads (pair_queue_44, sharded_3m)")
+    ap.add_argument("--static-deal", action="store_true", help="pair_queue_44 with the static round-robin deal at N > 1 (default: shared ticket counter)")
     ap.add_argument("--pageable-queue", action="store_true", help="pair_queue_44 from pageable host arrays (default: page-locked)")
     ap.add_argument("--no-sharded", action="store_true", help="skip sharded_3m only")
     ap.add_argument("--no-flush", action="store_true")

@@ -1,8 +1,9 @@
 """Host-side plumbing for several GPUs (one process per GPU, torch.distributed): how the registration work is
 partitioned.  No kernel lives here.
 
-  * a SEQUENCE of independent scan pairs (alignETH's loop, main.cpp:411-498): pairs are dealt to ranks, every
-    rank runs its own queue on its own context -- no collective on the data path;
+  * a SEQUENCE of independent scan pairs (alignETH's loop, main.cpp:411-498): pairs are dealt to ranks -- statically
+    (`shard_pairs`) or drawn from a shared ticket counter (`PairTickets`) -- every rank runs its own queue on its own
+    contexts; no collective on the data path;
   * ONE very large pair: every rank holds the whole target and a contiguous shard of the source; per iteration
     the ranks' partial normal-equation rows (<= 28 doubles) are summed and every rank solves the identical system.
     Two transports: (a) `attach_peers` + the ordinary `estimate_pose` -- the exchange runs INSIDE the reduction
@@ -18,6 +19,31 @@ import numpy as np
 def shard_pairs(n_pairs: int, world: int, rank: int) -> list[int]:
     """Round-robin deal of pair indices: rank r gets r, r+world, ...  (44 pairs on 8 GPUs: 6,6,6,6,5,5,5,5)."""
     return list(range(rank, n_pairs, world))
+
+
+class PairTickets:
+    """Dynamic deal of the pair queue: one shared counter in the process group's key-value store (the rendezvous store every
+    torch.distributed job already has; `add` is an atomic fetch-and-add served by rank 0's store thread, ~0.1 ms per draw against
+    milliseconds per registration).  Every rank draws the index of its next pair when one of its contexts becomes free, so a rank
+    that got cheap pairs takes more of them: the pairs of a sequence differ in cost by up to 5 x (share of far queries), and with 5-6
+    pairs per rank the static round-robin deal (`shard_pairs`) leaves the slowest rank 40 % behind the mean.  No collective on the
+    data path -- the counter is control plane.  Every rank must be able to read every pair (a shared file system, or -- the bench --
+    all scans in host memory); `key` must be the same on all ranks and fresh for every pass over the queue."""
+
+    def __init__(self, n_pairs: int, key: str = "icp_pair_tickets", store=None):
+        if store is None:
+            import torch.distributed as dist
+            store = dist.distributed_c10d._get_default_store()
+        self.n_pairs, self.key, self.store = int(n_pairs), str(key), store
+        self.drawn: list[int] = []
+
+    def next(self):
+        """Index of the next unclaimed pair, or None when the queue is empty."""
+        k = int(self.store.add(self.key, 1)) - 1
+        if k >= self.n_pairs:
+            return None
+        self.drawn.append(k)
+        return k
 
 
 def shard_points(n_points: int, world: int, rank: int) -> slice:

@@ -76,13 +76,16 @@ class PairResult:
     error: str | None = None
 
 
-def alignPairs(contexts, pairs, config, calculateErrors: bool = False):
+def alignPairs(contexts, pairs, config, calculateErrors: bool = False, tickets=None):
     """The pair loop of alignETH (main.cpp:343-514; experiment.cpp:276-412): independent (source, target[, unchanged source])
     registrations, identity start pose, dealt round-robin to the given contexts (one or two per GPU, any number of GPUs).
     Registration k+1 is uploaded and enqueued on the next context before registration k is waited for
     (icp_gpu_estimate_pose_async / _finish), so uploads, index builds and loops of different contexts overlap.
-    pairs: iterable of (source Cloud, target Cloud) or (source, target, unchangedSourcePoints [N,3]) -- the third entry feeds
-    ConvergenceMeasure(source points, unchanged points, runBenchmark=true) as main.cpp:439 does.  Returns [PairResult]."""
+    pairs: sequence of (source Cloud, target Cloud) or (source, target, unchangedSourcePoints [N,3]) -- the third entry feeds
+    ConvergenceMeasure(source points, unchanged points, runBenchmark=true) as main.cpp:439 does.  Returns [PairResult].
+    tickets (parallel.PairTickets or anything with next() -> index | None): several processes share ONE queue -- `pairs` is
+    the whole sequence on every process, the index of the next pair is drawn when a context is free, and the entries of the
+    result that other processes took stay None."""
     from . import capi
     pairs = list(pairs)
     results: list = [None] * len(pairs)
@@ -103,20 +106,29 @@ def alignPairs(contexts, pairs, config, calculateErrors: bool = False):
             r.rmseErrors, r.benchmarkErrors = [float(x) for x in rm], [float(x) for x in be]
         results[k] = r
 
-    for k, pr in enumerate(pairs):
-        ctx = contexts[k % len(contexts)]
-        # a context still busy with an earlier pair must be drained first
+    n_enqueued, k_static = 0, 0
+    while True:
+        ctx = contexts[n_enqueued % len(contexts)]
+        # a context still busy with an earlier pair must be drained first (and only then is the next ticket drawn: a process
+        # that waits holds no pair back from the others)
         for j, (kk, cc) in enumerate(pending):
             if cc is ctx:
                 finish(kk, cc)
                 pending.pop(j)
                 break
-        src, tgt = pr[0], pr[1]
+        if tickets is not None:
+            k = tickets.next()
+        else:
+            k, k_static = (k_static, k_static + 1) if k_static < len(pairs) else (None, k_static)
+        if k is None:
+            break
+        src, tgt = pairs[k][0], pairs[k][1]
         ctx.set_config(config)
         ctx.set_target(tgt.points, tgt.normals, tgt.colors)
         ctx.set_source(src.points, src.normals, src.colors)
         ctx.estimate_pose_async(np.eye(4, dtype=np.float32))
         pending.append((k, ctx))
+        n_enqueued += 1
     for kk, cc in pending:
         finish(kk, cc)
     return results
