@@ -171,6 +171,7 @@ struct MatchArgs {
     int collect_stats;       // work counters in DevState (atomics); off in timed runs
     int skip_finish;         // BVH path: the reduction evaluates stages 3-4 itself (ReduceArgs::fused), no match records
     int q_begin, q_end;      // BVH path: the sorted-source positions [q_begin, q_end) this launch searches (a chunk; the whole cloud by default)
+    int group_min;           // knn_group_kernel: fewest handed-over queries among 32 consecutive positions that share one descent
 };
 
 // Concurrency inside one iteration (api.cu, match.cu): the queries are cut into chunks, each chunk's {prep, walk} chain runs on its own

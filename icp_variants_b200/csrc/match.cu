@@ -253,8 +253,7 @@ __device__ __forceinline__ void bvh_visit(const MatchArgs& a, const BvhDesc& bvh
 //   match_finish_kernel thread per query: transformNormals, weighting, rejection -> the match records
 // One thread scans one leaf for its own query (fast path of knn_prep_kernel).
 template <bool COLOR>
-__device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query& q, Best& b, int& bleaf, unsigned int leaf, unsigned int& ev) {
-    const unsigned int ls = __ldg(&a.leaf_start[leaf]), le = __ldg(&a.leaf_start[leaf + 1]);
+__device__ __forceinline__ void thread_scan_range(const MatchArgs& a, const Query& q, Best& b, int& bleaf, unsigned int leaf, unsigned int ls, unsigned int le, unsigned int& ev) {
     // Contract D2 ((d, idx) lexicographic) without an index comparison per candidate: a leaf's records are stored in ORIGINAL index
     // order (grid.cu: bvh_level_kernel), so the first minimum of the distance in storage order is the lowest original index among
     // equal distances.  The scan accepts d <= the current best (`run` starts one ulp above it; d >= 0, so the bit pattern + 1 is the
@@ -272,6 +271,10 @@ __device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query
         const int idx = __float_as_int(__ldg(&a.tgt_pts[pos].w));
         if (better_key(run, idx, b)) { b.d = run; b.idx = idx; b.pos = pos; bleaf = (int)leaf; }
     }
+}
+template <bool COLOR>
+__device__ __forceinline__ void thread_scan_leaf(const MatchArgs& a, const Query& q, Best& b, int& bleaf, unsigned int leaf, unsigned int& ev) {
+    thread_scan_range<COLOR>(a, q, b, bleaf, leaf, __ldg(&a.leaf_start[leaf]), __ldg(&a.leaf_start[leaf + 1]), ev);
 }
 
 // Thread per query: selection predicate + transformPoints -> qbuf, and the FAST PATH of the search.  A query that
@@ -374,6 +377,288 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MIN_BLOCKS * 256 / PREP_THR
     }
     TL_END(0);
     if (STATS) flush_stats(a, 0u, 0u, ev, nd);     // STATS = false: the counters are dead code (2.6 % of the walk's instructions)
+}
+
+// ---------------------------------------------------------------------------- group search: 32 neighbouring queries, ONE descent
+// The queries the fast path defers come in runs: a scan region the target does not cover (an occlusion shadow, the far side of the
+// sensor's field of view) is a run of Morton-consecutive source points whose search balls -- 0.2 ... 3 m wide -- all touch the same
+// few target leaves at the edge of the covered region.  For such a query the walk's time goes into FINDING those leaves (about
+// 11 node visits of 32 box tests each for 2-5 leaf scans), and its 31 neighbours repeat the same descent.  Here one warp takes 32
+// consecutive positions of the sorted source (lane = query) and, if at least `group_min` of them were handed over with a bound,
+// descends ONCE for all of them: a node is kept when its box meets the bounding box of the members' search balls AND lies within
+// the largest member radius of the bounding box of the member points.  These bounds do not shrink during the descent, so it needs
+// no order: it runs breadth-first, level by level (lane = child; the frontier's child ranges are fetched in one round, the next
+// boxes of several nodes are requested together) -- a handful of dependent memory round trips instead of one per node.  The
+// surviving leaves (boxes and point ranges staged in shared memory) are a superset of every member's candidates; each member then
+// tests them against its own ball, and the few it still wants are scanned for it by the warp (lane = point) -- same candidates,
+// same (d, idx) rule, hence the same answer as the walk.  A group whose frontier or list outgrows its stage (a run
+// that jumps across the scene, a member without a neighbour inside the threshold) is left to the walk untouched.  A finished query
+// is marked like one the fast path finished (qbuf.x = NaN), so the walk skips it.
+#ifndef GROUP_CAP
+#define GROUP_CAP 48           // candidate leaves per group   (the kernel ends with its longest group: 128 / 128 / unlimited measured
+#endif                         //                               4.39 -> 5.3 ms on the bench pair against 4.25 with 48 / 64 / 160)
+#ifndef GROUP_FRONT
+#define GROUP_FRONT 64         // frontier nodes per level
+#endif
+#ifndef GROUP_WARPS
+#define GROUP_WARPS 4
+#endif
+#ifndef GROUP_UNROLL
+#define GROUP_UNROLL 3
+#endif
+#ifndef GROUP_STEP_LIMIT
+#define GROUP_STEP_LIMIT 160   // (member, leaf) scans per group
+#endif
+#ifndef GROUP_SIZE
+#define GROUP_SIZE 32          // consecutive positions per group (the members sit in the warp's first GROUP_SIZE lanes)
+#endif
+struct GroupStage {
+    unsigned int front[2][GROUP_FRONT];                       // frontier of the level being expanded / of the next level
+    unsigned int cfirst[GROUP_FRONT], clast[GROUP_FRONT];     // child ranges of the frontier's nodes
+    float4 lo[GROUP_CAP], hi[GROUP_CAP];                      // candidate leaves: box, id, point range
+    unsigned int leaf[GROUP_CAP], ls[GROUP_CAP], le[GROUP_CAP];
+};
+__device__ unsigned long long g_group_stats[12];   // STATS builds: windows seen, groups started, finished, members finished, leaves listed, leaf scans
+extern "C" int icp_gpu_debug_group_stats(unsigned long long* out12, int reset) {
+    if (reset) { void* p = nullptr; cudaGetSymbolAddress(&p, g_group_stats); return (int)cudaMemset(p, 0, sizeof(g_group_stats)); }
+    return (int)cudaMemcpyFromSymbol(out12, g_group_stats, sizeof(g_group_stats));
+}
+__device__ __forceinline__ unsigned int f2ord(float f) { const unsigned int u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+__device__ __forceinline__ float warp_min_f(float v) { return ord2f(__reduce_min_sync(0xFFFFFFFFu, f2ord(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return ord2f(__reduce_max_sync(0xFFFFFFFFu, f2ord(v))); }
+
+struct GroupBounds { float blx, bly, blz, bhx, bhy, bhz, qlx, qly, qlz, qhx, qhy, qhz, dlim; };
+__device__ __forceinline__ bool group_keeps(const GroupBounds& g, const float4 lo, const float4 hi) {
+    const bool meets = lo.x <= g.bhx && hi.x >= g.blx && lo.y <= g.bhy && hi.y >= g.bly && lo.z <= g.bhz && hi.z >= g.blz;
+    const float gx = fmaxf(fmaxf(lo.x - g.qhx, g.qlx - hi.x), 0.0f), gy = fmaxf(fmaxf(lo.y - g.qhy, g.qly - hi.y), 0.0f), gz = fmaxf(fmaxf(lo.z - g.qhz, g.qlz - hi.z), 0.0f);
+    return meets && !(gx * gx + gy * gy + gz * gz > g.dlim);
+}
+
+// One warp: the group's bounds, the breadth-first descent and pass A (which members want which listed leaf).  Returns the number
+// of wanted leaves, compacted to the front of the stage {leaf, ls, le, cfirst = mask of the wanting members} (0: the seed scans'
+// results are final), or GROUP_LEFT: the group is too wide (frontier, list or number of scans beyond the stage) and is left to the walk.
+#define GROUP_LEFT 0xFFFFFFFFu
+__device__ __forceinline__ unsigned int group_collect(const MatchArgs& a, const BvhDesc& bvh, GroupStage& sm, const Query& q, bool member, float bd, int own,
+                                                      int lane, unsigned int& nd, unsigned int& n_list_out, unsigned int& scans_out) {
+    const unsigned int FULL = 0xFFFFFFFFu;
+    // box of the members' balls (radius rounded up, as the fast path's "inside" test), box of the member points, largest squared
+    // radius (with a margin that covers D1's roundings against the box-to-box gap of group_keeps)
+    GroupBounds g;
+    {
+        const float INF = __int_as_float(0x7f800000);
+        const float r = member ? __fmul_ru(__fsqrt_ru(bd), 1.00001f) : 0.f;
+        g.blx = warp_min_f(member ? __fsub_rd(q.x, r) : INF); g.bhx = warp_max_f(member ? __fadd_ru(q.x, r) : -INF);
+        g.bly = warp_min_f(member ? __fsub_rd(q.y, r) : INF); g.bhy = warp_max_f(member ? __fadd_ru(q.y, r) : -INF);
+        g.blz = warp_min_f(member ? __fsub_rd(q.z, r) : INF); g.bhz = warp_max_f(member ? __fadd_ru(q.z, r) : -INF);
+        g.qlx = warp_min_f(member ? q.x : INF); g.qhx = warp_max_f(member ? q.x : -INF);
+        g.qly = warp_min_f(member ? q.y : INF); g.qhy = warp_max_f(member ? q.y : -INF);
+        g.qlz = warp_min_f(member ? q.z : INF); g.qhz = warp_max_f(member ? q.z : -INF);
+        g.dlim = __fadd_ru(__fmul_ru(warp_max_f(member ? bd : 0.f), 1.0001f), 1e-36f);
+    }
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int top_level = bvh.n_levels - 1;
+    const unsigned int n_top = (unsigned int)bvh.count[top_level];
+    unsigned int n_list = 0u, n_cur = 0u;
+    int cur = 0;
+    // top level: its nodes are tested directly (<= 32 of them unless the level cap was hit)
+    for (unsigned int base = 0; base < n_top; base += 32) {
+        const unsigned int c = base + lane;
+        bool keep = false; float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo; unsigned int ls = 0u, le = 0u;
+        if (c < n_top) {
+            lo = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[top_level] + c)]); hi = __ldg(&a.bvh_box[2 * (size_t)(bvh.offset[top_level] + c) + 1]);
+            if (top_level == 0) { ls = __ldg(&a.leaf_start[c]); le = __ldg(&a.leaf_start[c + 1]); }
+            keep = group_keeps(g, lo, hi);
+        }
+        const unsigned int mk = __ballot_sync(FULL, keep);
+        if (top_level == 0) {
+            if (n_list + __popc(mk) > GROUP_CAP) return GROUP_LEFT;
+            if (keep) { const unsigned int k = n_list + __popc(mk & lt_mask); sm.leaf[k] = c; sm.lo[k] = lo; sm.hi[k] = hi; sm.ls[k] = ls; sm.le[k] = le; }
+            n_list += __popc(mk);
+        } else {
+            if (n_cur + __popc(mk) > GROUP_FRONT) return GROUP_LEFT;
+            if (keep) sm.front[cur][n_cur + __popc(mk & lt_mask)] = c;
+            n_cur += __popc(mk);
+        }
+        if (lane == 0) ++nd;
+    }
+    __syncwarp();
+    // breadth-first: the frontier holds the kept nodes of level L; their children (level L - 1) are tested, lane = child
+    for (int L = top_level; L >= 1 && n_cur > 0u; --L) {
+        for (unsigned int j = lane; j < n_cur; j += 32) {
+            const unsigned int node = sm.front[cur][j];
+            sm.cfirst[j] = __ldg(&a.child_start[bvh.coffset[L] + node]); sm.clast[j] = __ldg(&a.child_start[bvh.coffset[L] + node + 1]);
+        }
+        __syncwarp();
+        const bool to_leaves = L == 1;
+        const size_t box0 = (size_t)bvh.offset[L - 1];
+        unsigned int n_nxt = 0u;
+        // the frontier in rounds of GROUP_UNROLL nodes: all their boxes are requested before the first is tested (one memory round
+        // trip per round instead of one per node)
+        for (unsigned int j0 = 0; j0 < n_cur; j0 += GROUP_UNROLL) {
+            unsigned int c[GROUP_UNROLL], ls[GROUP_UNROLL], le[GROUP_UNROLL]; bool v[GROUP_UNROLL]; float4 lo[GROUP_UNROLL], hi[GROUP_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GROUP_UNROLL; ++u) {
+                v[u] = false; c[u] = 0u; ls[u] = 0u; le[u] = 0u; lo[u] = make_float4(0.f, 0.f, 0.f, 0.f); hi[u] = lo[u];
+                if (j0 + u < n_cur) {
+                    c[u] = sm.cfirst[j0 + u] + lane; v[u] = c[u] < sm.clast[j0 + u];
+                    if (v[u]) {
+                        lo[u] = __ldg(&a.bvh_box[2 * (box0 + c[u])]); hi[u] = __ldg(&a.bvh_box[2 * (box0 + c[u]) + 1]);
+                        if (to_leaves) { ls[u] = __ldg(&a.leaf_start[c[u]]); le[u] = __ldg(&a.leaf_start[c[u] + 1]); }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GROUP_UNROLL; ++u) {
+                if (j0 + u >= n_cur) break;
+                const bool keep = v[u] && group_keeps(g, lo[u], hi[u]);
+                const unsigned int mk = __ballot_sync(FULL, keep);
+                if (to_leaves) {
+                    if (n_list + __popc(mk) > GROUP_CAP) return GROUP_LEFT;             // too wide a group: left to the walk
+                    if (keep) { const unsigned int k = n_list + __popc(mk & lt_mask); sm.leaf[k] = c[u]; sm.lo[k] = lo[u]; sm.hi[k] = hi[u]; sm.ls[k] = ls[u]; sm.le[k] = le[u]; }
+                    n_list += __popc(mk);
+                } else {
+                    if (n_nxt + __popc(mk) > GROUP_FRONT) return GROUP_LEFT;
+                    if (keep) sm.front[cur ^ 1][n_nxt + __popc(mk & lt_mask)] = c[u];
+                    n_nxt += __popc(mk);
+                }
+                if (lane == 0) ++nd;
+            }
+        }
+        __syncwarp();
+        cur ^= 1; n_cur = n_nxt;
+    }
+    // pass A (shared memory only): which members' own balls does each listed leaf's box meet -- three of the 32 on average, none
+    // for a quarter of the leaves; the list is compacted to the wanted leaves
+    unsigned int scans = 0u, n_w = 0u;
+    for (unsigned int j = 0; j < n_list; ++j) {
+        const unsigned int leaf = sm.leaf[j];
+        const bool want = member && (int)leaf != own && !(box_dist2(q, sm.lo[j], sm.hi[j]) > bd);
+        const unsigned int wm = __ballot_sync(FULL, want);
+        if (wm != 0u) {
+            const unsigned int ls = sm.ls[j], le = sm.le[j];
+            __syncwarp();
+            if (lane == 0) { sm.leaf[n_w] = leaf; sm.ls[n_w] = ls; sm.le[n_w] = le; sm.cfirst[n_w] = wm; }   // n_w <= j: in place
+            ++n_w; scans += __popc(wm);
+        }
+    }
+    __syncwarp();
+    n_list_out = n_list; scans_out = scans;
+    // a group with too many (member, leaf) scans ahead is a long chain of dependent steps on few warps: left to the walk's many
+    return scans > GROUP_STEP_LIMIT ? GROUP_LEFT : n_w;
+}
+
+// One warp per group.  (Measured and dropped: one block per group whose warps share the wanted leaves and merge their candidates
+// by the (d, idx) order -- the descent is the latency-bound part and then runs on a quarter of the resident warps: 4.98 against 4.39 ms.)
+template <bool STATS>
+__global__ void __launch_bounds__(GROUP_WARPS * 32, 6) knn_group_kernel(const MatchArgs a) {
+    __shared__ GroupStage s_stage[GROUP_WARPS];
+    __shared__ BvhDesc s_bvh;
+    if (a.desc_index < 0 && a.state_ro->converged) return;
+    if (threadIdx.x < sizeof(BvhDesc) / 4) reinterpret_cast<int*>(&s_bvh)[threadIdx.x] = reinterpret_cast<const int*>(a.bvh)[threadIdx.x];
+    __syncthreads();
+    const unsigned int FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const BvhDesc& bvh = s_bvh;
+    if (bvh.n_leaves <= 0) return;
+    GroupStage& sm = s_stage[wid];
+    const long long pl = (long long)a.q_begin + (long long)(blockIdx.x * GROUP_WARPS + wid) * GROUP_SIZE + lane;
+    const int p = (int)pl;
+    float4 q4 = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f), sb = make_float4(0.f, 0.f, 0.f, __int_as_float(-2));
+    int own = -1;
+    if (lane < GROUP_SIZE && pl < (long long)a.q_end) {
+        q4 = a.qbuf[p];                                                          // plain loads: written by the launch before
+        if (q4.x == q4.x) { sb = a.seedbuf[p]; own = a.nn_leaf[p]; }             // own = the seed leaf (scanned by the fast path already)
+    }
+    // member: deferred by the fast path after its seed-leaf scan, with a neighbour inside the threshold (a query whose bound is the
+    // threshold itself wants every leaf its threshold ball meets: such groups outgrow the stage, their descent would be wasted).
+    // (Measured: members restricted to the queries whose ball leaves even the level-1 node's inflated box, sb.w = -1: 4.54 against
+    // 4.25 ms on the bench pair -- the nearer deferred queries are the ones that share their leaves best.)
+    const bool member = q4.x == q4.x && __float_as_int(sb.w) >= -1 && __float_as_int(sb.y) != INT_MAX;
+    const int n_members = __popc(__ballot_sync(FULL, member));
+    if (STATS && lane == 0) { atomicAdd(&g_group_stats[0], 1ull); if (n_members >= a.group_min) atomicAdd(&g_group_stats[1], 1ull); }
+    if (n_members < a.group_min) return;                                         // (whole warp)
+    long long t_0 = 0, t_2 = 0;
+    if (STATS) t_0 = clock64();
+    Query q; q.x = q4.x; q.y = q4.y; q.z = q4.z;
+    q.cr = q.cg = q.cb = 0.f;                                                   // 3-D search only (icp_launch_match)
+    unsigned int ev = 0, nd = 0, n_list = 0u, scans = 0u;
+    const unsigned int n_w = group_collect(a, bvh, sm, q, member, sb.x, own, lane, nd, n_list, scans);
+    if (n_w == GROUP_LEFT) return;                                               // (whole warp) left to the walk
+    if (STATS) t_2 = clock64();
+    // Pass B: the scan is transposed -- the leaf's points sit in the lanes (lane = point, one coalesced read, three leaves in flight),
+    // the wanting members take turns, two at a time (independent chains), each broadcasting its query and receiving the leaf's
+    // (d, idx) minimum by a warp arg-min: the walk's leaf scan (bvh_scan_leaves) without the walk.
+    Best b; b.d = sb.x; b.idx = __float_as_int(sb.y); b.pos = __float_as_int(sb.z);
+    int bleaf = -1;
+    float4 pf[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        pf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const unsigned int j = (unsigned int)u;
+        if (j < n_w) {
+            const unsigned int i = sm.ls[j] + lane;
+            if (i < sm.le[j]) pf[u] = __ldg(&a.tgt_pts[i]);
+        }
+    }
+    for (unsigned int j0 = 0; j0 < n_w; j0 += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const unsigned int j = j0 + u;
+            if (j >= n_w) break;
+            const float4 pt = pf[u];
+            if (j + 3 < n_w) {
+                const unsigned int i = sm.ls[j + 3] + lane;
+                if (i < sm.le[j + 3]) pf[u] = __ldg(&a.tgt_pts[i]);
+            }
+            const unsigned int leaf = sm.leaf[j], ls = sm.ls[j], cnt = sm.le[j] - ls;
+            unsigned int wm = sm.cfirst[j];
+            const bool has = (unsigned int)lane < cnt;
+            const int pidx = __float_as_int(pt.w);
+            while (wm) {
+                const int m0 = __ffs((int)wm) - 1; wm &= wm - 1u;
+                const bool two = wm != 0u;
+                const int m1 = two ? __ffs((int)wm) - 1 : m0; wm &= wm - 1u;      // (0 & anything = 0)
+                Query q0, q1; Best b0, b1;
+                q0.x = __shfl_sync(FULL, q.x, m0); q0.y = __shfl_sync(FULL, q.y, m0); q0.z = __shfl_sync(FULL, q.z, m0);
+                q1.x = __shfl_sync(FULL, q.x, m1); q1.y = __shfl_sync(FULL, q.y, m1); q1.z = __shfl_sync(FULL, q.z, m1);
+                b0.d = __shfl_sync(FULL, b.d, m0); b0.idx = __shfl_sync(FULL, b.idx, m0); b0.pos = -1;
+                b1.d = __shfl_sync(FULL, b.d, m1); b1.idx = __shfl_sync(FULL, b.idx, m1); b1.pos = -1;
+                unsigned int key0 = 0xFFFFFFFFu, key1 = 0xFFFFFFFFu;
+                if (has) {
+                    key0 = __float_as_uint(dist3(q0, pt)); key1 = __float_as_uint(dist3(q1, pt));    // D1, operands (query - point)
+                }
+                ev += has ? (two ? 2u : 1u) : 0u;
+                const unsigned int dmin0 = __reduce_min_sync(FULL, key0), dmin1 = __reduce_min_sync(FULL, key1);
+                const int cand0 = (has && key0 == dmin0) ? pidx : INT_MAX, cand1 = (has && key1 == dmin1) ? pidx : INT_MAX;
+                const int imin0 = __reduce_min_sync(FULL, cand0), imin1 = __reduce_min_sync(FULL, cand1);
+                if (imin0 != INT_MAX && better_key(__uint_as_float(dmin0), imin0, b0)) {
+                    const int src = __ffs((int)__ballot_sync(FULL, cand0 == imin0)) - 1;
+                    if (lane == m0) { b.d = __uint_as_float(dmin0); b.idx = imin0; b.pos = (int)(ls + src); bleaf = (int)leaf; }
+                }
+                if (two && imin1 != INT_MAX && better_key(__uint_as_float(dmin1), imin1, b1)) {
+                    const int src = __ffs((int)__ballot_sync(FULL, cand1 == imin1)) - 1;
+                    if (lane == m1) { b.d = __uint_as_float(dmin1); b.idx = imin1; b.pos = (int)(ls + src); bleaf = (int)leaf; }
+                }
+            }
+        }
+    }
+    if (member) {
+        const int pos = b.idx == INT_MAX ? -1 : b.pos;
+        a.nn_pos[p] = pos;
+        a.nn_leaf[p] = pos >= 0 ? (bleaf >= 0 ? bleaf : own) : -1;                // no better point than the seed scan's: it lies in the seed leaf
+        a.qbuf[p].x = __int_as_float(0x7fc00000);                                // searched: nothing left for the walk
+    }
+    if (STATS) {
+        const long long t_3 = clock64();
+        if (lane == 0) {
+            atomicAdd(&g_group_stats[7], (unsigned long long)(t_2 - t_0)); atomicAdd(&g_group_stats[8], (unsigned long long)(t_3 - t_2));
+            atomicMax(&g_group_stats[9], (unsigned long long)(t_3 - t_0)); atomicAdd(&g_group_stats[10], (unsigned long long)nd);
+            atomicAdd(&g_group_stats[2], 1ull); atomicAdd(&g_group_stats[3], (unsigned long long)n_members);
+            atomicAdd(&g_group_stats[4], (unsigned long long)n_list); atomicAdd(&g_group_stats[5], (unsigned long long)scans);
+        }
+        flush_stats(a, 0u, 0u, ev, nd);
+    }
 }
 
 #ifndef WALK_MIN_BLOCKS
@@ -800,6 +1085,19 @@ cudaError_t icp_launch_match(const MatchArgs& a, int algorithm, int n_sms, cudaS
             else { if (a.color_icp) knn_prep_kernel<true, false><<<np, PREP_THREADS, 0, cs>>>(ac); else knn_prep_kernel<false, false><<<np, PREP_THREADS, 0, cs>>>(ac); }
             ++launches;
             if (after_prep) cudaEventRecord(after_prep, s);
+            // runs of deferred neighbours share one descent (knn_group_kernel); what it leaves goes to the walk
+            // Policy: on when the matcher's threshold admits far matches (max distance^2 >= 1: the reference's ETH driver uses 10,
+            // main.cpp:361) -- runs of far queries with a neighbour are what the group search is for (3 M-point pair 61.7 -> 47.8 ms,
+            // 44-pair queue 291 -> 324 pairs/s, far-heavy pairs -18 %; the bench pair +0.5 %); with a tight threshold (0.1 in the
+            // experiment runner) the far queries have no neighbour, the groups that remain cost more than they save (4.0 -> 4.75 ms).
+            const int group_min = getenv("ICP_GPU_GROUP_MIN") ? atoi(getenv("ICP_GPU_GROUP_MIN")) : (a.max_d2 >= 1.0f ? 8 : 0);   // knob; 0 = off
+            // (3-D search only: a 6-D bound holds colour differences too, as a radius in space it makes every group too wide)
+            if (group_min > 0 && a.fast_path && a.use_seed && !a.color_icp) {
+                ac.group_min = group_min;
+                const int ng = (nq + GROUP_SIZE * GROUP_WARPS - 1) / (GROUP_SIZE * GROUP_WARPS);
+                if (a.collect_stats) knn_group_kernel<true><<<ng, GROUP_WARPS * 32, 0, cs>>>(ac); else knn_group_kernel<false><<<ng, GROUP_WARPS * 32, 0, cs>>>(ac);
+                ++launches;
+            }
             // every chunk's walk gets the full grid (its warps then take fewer positions each): a heavy chunk left alone at the end
             // of the iteration still fills the machine
             int nb = (nq + BVH_WARPS - 1) / BVH_WARPS;
