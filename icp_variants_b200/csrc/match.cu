@@ -418,11 +418,17 @@ struct GroupStage {
     float4 lo[GROUP_CAP], hi[GROUP_CAP];                      // candidate leaves: box, id, point range
     unsigned int leaf[GROUP_CAP], ls[GROUP_CAP], le[GROUP_CAP];
 };
-__device__ unsigned long long g_group_stats[12];   // STATS builds: windows seen, groups started, finished, members finished, leaves listed, leaf scans
+#ifdef ICP_GROUP_PROBE   // diagnostic build (make groupprobe, profiles/probe_group.py): per launch with collect_stats -- windows seen, groups
+// started, finished, members finished, leaves listed, (member, leaf) scans, -, cycles of the descent, of the scans, longest group, box rounds
+__device__ unsigned long long g_group_stats[12];
 extern "C" int icp_gpu_debug_group_stats(unsigned long long* out12, int reset) {
     if (reset) { void* p = nullptr; cudaGetSymbolAddress(&p, g_group_stats); return (int)cudaMemset(p, 0, sizeof(g_group_stats)); }
     return (int)cudaMemcpyFromSymbol(out12, g_group_stats, sizeof(g_group_stats));
 }
+#define GROUP_PROBE(x) x
+#else
+#define GROUP_PROBE(x)
+#endif
 __device__ __forceinline__ unsigned int f2ord(float f) { const unsigned int u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
 __device__ __forceinline__ float warp_min_f(float v) { return ord2f(__reduce_min_sync(0xFFFFFFFFu, f2ord(v))); }
@@ -576,16 +582,15 @@ __global__ void __launch_bounds__(GROUP_WARPS * 32, 6) knn_group_kernel(const Ma
     // 4.25 ms on the bench pair -- the nearer deferred queries are the ones that share their leaves best.)
     const bool member = q4.x == q4.x && __float_as_int(sb.w) >= -1 && __float_as_int(sb.y) != INT_MAX;
     const int n_members = __popc(__ballot_sync(FULL, member));
-    if (STATS && lane == 0) { atomicAdd(&g_group_stats[0], 1ull); if (n_members >= a.group_min) atomicAdd(&g_group_stats[1], 1ull); }
+    GROUP_PROBE(if (STATS && lane == 0) { atomicAdd(&g_group_stats[0], 1ull); if (n_members >= a.group_min) atomicAdd(&g_group_stats[1], 1ull); })
     if (n_members < a.group_min) return;                                         // (whole warp)
-    long long t_0 = 0, t_2 = 0;
-    if (STATS) t_0 = clock64();
+    GROUP_PROBE(long long t_0 = 0; long long t_2 = 0; if (STATS) t_0 = clock64();)
     Query q; q.x = q4.x; q.y = q4.y; q.z = q4.z;
     q.cr = q.cg = q.cb = 0.f;                                                   // 3-D search only (icp_launch_match)
     unsigned int ev = 0, nd = 0, n_list = 0u, scans = 0u;
     const unsigned int n_w = group_collect(a, bvh, sm, q, member, sb.x, own, lane, nd, n_list, scans);
     if (n_w == GROUP_LEFT) return;                                               // (whole warp) left to the walk
-    if (STATS) t_2 = clock64();
+    GROUP_PROBE(if (STATS) t_2 = clock64();)
     // Pass B: the scan is transposed -- the leaf's points sit in the lanes (lane = point, one coalesced read, three leaves in flight),
     // the wanting members take turns, two at a time (independent chains), each broadcasting its query and receiving the leaf's
     // (d, idx) minimum by a warp arg-min: the walk's leaf scan (bvh_scan_leaves) without the walk.
@@ -650,6 +655,7 @@ __global__ void __launch_bounds__(GROUP_WARPS * 32, 6) knn_group_kernel(const Ma
         a.qbuf[p].x = __int_as_float(0x7fc00000);                                // searched: nothing left for the walk
     }
     if (STATS) {
+#ifdef ICP_GROUP_PROBE
         const long long t_3 = clock64();
         if (lane == 0) {
             atomicAdd(&g_group_stats[7], (unsigned long long)(t_2 - t_0)); atomicAdd(&g_group_stats[8], (unsigned long long)(t_3 - t_2));
@@ -657,6 +663,7 @@ __global__ void __launch_bounds__(GROUP_WARPS * 32, 6) knn_group_kernel(const Ma
             atomicAdd(&g_group_stats[2], 1ull); atomicAdd(&g_group_stats[3], (unsigned long long)n_members);
             atomicAdd(&g_group_stats[4], (unsigned long long)n_list); atomicAdd(&g_group_stats[5], (unsigned long long)scans);
         }
+#endif
         flush_stats(a, 0u, 0u, ev, nd);
     }
 }

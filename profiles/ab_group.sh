@@ -1,12 +1,13 @@
-for g in ${GMS:-8}; do echo "GROUP_MIN=$g"; ICP_GPU_GROUP_MIN=$g python bench.py --steps 10 --warmup 3 --no-multi --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['stage_ms_per_iteration'], d['pose_checksum'], d['gpu_launches_per_step'])"; done
-GROUP_MINS=${GMS:-8} python profiles/probe_group.py | python -c "
-import json,sys
-d=json.load(sys.stdin)
-for k,v in d.items():
-    for g,r in v.items(): print('pair',k,'group_min',g,'ms %.3f'%r['ms_30_iterations'],'group+walk us %.1f'%r['group_and_walk_us'],'chk',r['pose_checksum'],{a:round(b,1) for a,b in r['per_iteration'].items()})"
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_size_eth or chunk_chains or config4_full or index_edge or bench_config" 2>&1 | tail -3
-B="python bench.py --steps 1 --warmup 3 --no-multi --no-cpu-baseline"
-ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none -k regex:"knn_|reduce_kernel" -s 700 -c 130 --csv --log-file gpurun_out/group_launches.csv $B > /dev/null 2>&1
-python profiles/summarize_launches.py gpurun_out/group_launches.csv 2>&1 | tail -5
+# A/B of the group search (ICP_GPU_GROUP_MIN=0 off / 8 on): the bench line (headline, pair_queue_44, sharded_3m on one GPU) and the config timings
+for g in 0 8; do
+  ICP_GPU_GROUP_MIN=$g python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_gm$g.json 2> gpurun_out/bench_gm$g.err
+  ICP_GPU_GROUP_MIN=$g python profiles/measure_configs.py > gpurun_out/configs_gm$g.json 2> gpurun_out/configs_gm$g.err
+done
+python - <<'P'
+import json
+for g in (0, 8):
+    d = json.load(open(f'gpurun_out/bench_gm{g}.json'))
+    print('gm', g, 'ms', round(d['ms_per_step'], 3), 'e2e', round(d['e2e']['ms_per_step'], 3), 'launches', d['gpu_launches_per_step'], 'pq44', round(d['pair_queue_44']['pairs_per_s'], 1), round(d['pair_queue_44']['ms_total'], 1), 'sharded single', round(d['sharded_3m']['ms_single_gpu'], 2), 'chk', d['pose_checksum'])
+    c = json.load(open(f'gpurun_out/configs_gm{g}.json'))
+    print({k: round(v['ms'], 3) for k, v in c.items() if isinstance(v, dict) and 'ms' in v})
+P

@@ -1,3 +1,5 @@
+# Group search per pair (0 = the bench pair, 28 / 34 = far-heavy pairs of the 44-pair sequence), off / on, with the diagnostic counters when
+# the groupprobe build is selected (ICP_GPU_LIB_NAME=libicp_gpu_groupprobe.so), then the parity tests of the search
 run() { python profiles/probe_group.py | python -c "
 import json,sys
 d=json.load(sys.stdin)

@@ -1,5 +1,6 @@
 """knn_group_kernel: what it takes and what it leaves (instrumented registration: windows seen, groups started / finished, members
-finished, leaves listed, leaf scans) and the registration time with and without it, for pairs of different far-query shares."""
+finished, leaves listed, leaf scans; needs the diagnostic build: make -C icp_variants_b200/csrc groupprobe and
+ICP_GPU_LIB_NAME=libicp_gpu_groupprobe.so) and the registration time with and without it, for pairs of different far-query shares."""
 import ctypes as C, json, os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -26,9 +27,12 @@ for k in [int(x) for x in os.environ.get("PAIRS", "0,34").split(",")]:
         cfg.collect_stats = 1; ctx.set_config(cfg)
         ctx.set_target(tgt.points, tgt.normals, tgt.colors); ctx.set_source(src.points, src.normals, src.colors)
         g = (C.c_ulonglong * 12)()
-        capi.lib().icp_gpu_debug_group_stats(g, 1)
+        probe = hasattr(capi.lib(), "icp_gpu_debug_group_stats")
+        if probe:
+            capi.lib().icp_gpu_debug_group_stats(g, 1)
         ctx.estimate_pose(want_history=False); st = ctx.stats()
-        capi.lib().icp_gpu_debug_group_stats(g, 0)
+        if probe:
+            capi.lib().icp_gpu_debug_group_stats(g, 0)
         r[gm] = {"ms_30_iterations": best, "prep_us": tm.search_prep_ms / 30 * 1e3, "group_and_walk_us": (tm.matching_ms - tm.search_prep_ms) / 30 * 1e3,
                  "pose_checksum": float(np.abs(pose).sum()), "evals_per_launch": st.n_distance_evals / 30, "nodes_per_launch": st.n_nodes_visited / 30,
                  "per_iteration": {"windows": g[0] / 30, "groups_started": g[1] / 30, "groups_finished": g[2] / 30, "members_finished": g[3] / 30,
