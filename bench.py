@@ -552,7 +552,7 @@ def main():
     ctx.set_config(cfg)
     match_ms = tm.matching_ms / N_ITER
     prep_ms = tm.search_prep_ms / N_ITER
-    walk_ms = max(match_ms - prep_ms, 1e-6)          # knn_bvh_kernel alone (the dominant kernel)
+    walk_ms = max(match_ms - prep_ms, 1e-6)          # the search after the fast path: knn_group_kernel + knn_bvh_kernel of one chain (the dominant part)
     solve_ms = tm.solver_ms / N_ITER
     # the FP32 denominators, measured on this device in this run (peak.cu)
     ffma_tflops = ctx.measure_fp32_peak(0)
@@ -580,11 +580,14 @@ def main():
                     "h2d_bytes_per_step": int((ns + nt) * 28 + 64 + 32 * N_ITER), "d2h_bytes_per_step": int(64 + 16 * 4 * N_ITER + 1024)},
             "gpu_launches": launches,
             "gpu_launches_per_step": launches // max(args.steps * world, 1),
-            "roofline": {"kernel": "knn_bvh_kernel<false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "knn_group_kernel + knn_bvh_kernel<false> (the search after the fast path, timed together: one event pair per iteration)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic("knn_bvh_kernel"), "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": walk_ms,
-                         "note": "issue-bound tree search over L2-resident clouds; see roofline_fp32"},
-            "roofline_fp32": {"kernels": "knn_prep_kernel (fast path) + knn_bvh_kernel (walk)", "distance_evals_per_launch": evals_per_launch,
+                         "note": "issue-bound tree search over L2-resident clouds; see roofline_fp32; traffic = the committed cold-cache capture of knn_bvh_kernel "
+                                 "(profiles/r2_ncu_traffic.json, before the group search; with caches as the program leaves them both kernels read < 0.2 MB of DRAM "
+                                 "per launch, profiles/r2_ncu_full_search_kernels_group_search.txt)"},
+            "roofline_fp32": {"kernels": "knn_prep_kernel (fast path) + knn_group_kernel (runs of deferred neighbours) + knn_bvh_kernel (walk)", "distance_evals_per_launch": evals_per_launch,
                               "gevals_per_s": evals_per_launch / (match_ms * 1e-3) / 1e9, "flop_per_eval": 8, "tflops": search_tflops,
                               "peak_ffma_tflops_measured": ffma_tflops, "peak_fmul_fadd_tflops_measured": nonfma_tflops,
                               "frac_of_measured_non_fma_peak": search_tflops / nonfma_tflops if nonfma_tflops > 0 else None,
