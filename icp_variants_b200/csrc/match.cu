@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MIN_BLOCKS * 256 / PREP_THR
 #ifndef GROUP_SIZE
 #define GROUP_SIZE 32          // consecutive positions per group (the members sit in the warp's first GROUP_SIZE lanes)
 #endif
+static_assert(GROUP_CAP <= GROUP_FRONT, "pass A keeps the want masks of the listed leaves in cfirst[]");
 struct GroupStage {
     unsigned int front[2][GROUP_FRONT];                       // frontier of the level being expanded / of the next level
     unsigned int cfirst[GROUP_FRONT], clast[GROUP_FRONT];     // child ranges of the frontier's nodes

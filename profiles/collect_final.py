@@ -58,7 +58,7 @@ sass = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=
 sass = re.sub(r"[ \t]*/\* 0x[0-9a-f]{16} \*/", "", sass)
 sass = "\n".join(ln.rstrip() for ln in sass.splitlines() if ln.strip()) + "\n"
 funcs = re.split(r"(?=\n\s*Function : )", sass)
-groups = {"knn_prep": "knn_prep_kernel", "knn_bvh": "knn_bvh_kernel", "reduce": "reduce_kernel", "projective": "projective_kernel", "lm_eval": "lm_eval_kernel",
+groups = {"knn_prep": "knn_prep_kernel", "knn_group": "knn_group_kernel", "knn_bvh": "knn_bvh_kernel", "reduce": "reduce_kernel", "projective": "projective_kernel", "lm_eval": "lm_eval_kernel",
           "pca_normals": "pca_normals_kernel", "depth_cloud": "depth_cloud|flag_count|block_scan|flag_scatter",
           "index_build": "pack_bbox|pack_normals|keys_kernel|radix_|gather_records|level_flags|level_rank|upper_levels|bvh_level|leaf_adjacency|seed_from_keys",
           "other": None}
@@ -74,7 +74,7 @@ for g, pat in groups.items():
     if sel:
         # first template instance only for the big kernels, to keep the listings reviewable; every instance is named in the header
         names = [re.search(r"Function : (\S+)", fn).group(1) for fn in sel]
-        prefer = {"reduce": "ILi1ELb1E", "knn_prep": "ILb0ELb0E", "knn_bvh": "ILb0ELb0E", "projective": "ILi256E"}.get(g)    # the instance the bench runs
+        prefer = {"reduce": "ILi1ELb1E", "knn_prep": "ILb0ELb0E", "knn_group": "ILb0E", "knn_bvh": "ILb0ELb0E", "projective": "ILi256E"}.get(g)    # the instance the bench runs
         first = [fn for fn in sel if prefer and prefer in re.search(r"Function : (\S+)", fn).group(1)][:1] or sel[:1]
         keep = sel if g in ("index_build", "depth_cloud", "other") else first
         with open(os.path.join(P, f"{R}sass_{g}.txt"), "w") as f:
