@@ -840,6 +840,42 @@ def test_index_edge_shapes_against_brute_force(ctx, kind, n_tgt):
         assert_matches_equal(idx, w, ref2, f"{kind} n={n_tgt} max_d2={max_d2} shifted")
 
 
+@pytest.mark.parametrize("group_min", ["1", "8", "0"])
+@pytest.mark.parametrize("kind,n_tgt", [("uniform", 5000), ("clustered", 40000), ("plane_dups", 5000), ("line", 1025), ("identical", 100), ("uniform", 33)])
+def test_group_search_on_runs_of_far_queries_against_brute_force(kind, n_tgt, group_min, monkeypatch):
+    """knn_group_kernel (one shared descent for runs of deferred neighbours, ICP_GPU_GROUP_MIN: 1 = every run, 8 = default, 0 = off)
+    on degenerate targets: compact blobs of queries 0.5 - 5 units away from the target (runs of far queries that share their
+    candidate leaves), a blob straddling the target, scattered far queries (groups too wide: left to the walk) -- exactly the oracle's
+    brute-force answers (lowest index on ties) cold, warm-started and after a small motion, with and without a threshold."""
+    monkeypatch.setenv("ICP_GPU_GROUP_MIN", group_min)
+    rng = np.random.default_rng(n_tgt * 13 + len(kind) + int(group_min))
+    tgt = _cloud(kind, n_tgt, rng)
+    centre = tgt.mean(0)
+    blobs = [centre + np.array(off, np.float32) + rng.normal(0, s, size=(n, 3)).astype(np.float32)
+             for off, s, n in (((0.5, 0.2, 0.1), 0.05, 700), ((3.0, -2.0, 1.0), 0.2, 900), ((0.0, 0.0, 5.0), 0.02, 500), ((0.0, 0.0, 0.0), 0.3, 600))]
+    qry = np.concatenate(blobs + [rng.uniform(-60, 60, size=(200, 3)).astype(np.float32), tgt[:min(50, n_tgt)]]).astype(np.float32)
+    zt, zq = np.zeros_like(tgt), np.zeros_like(qry)
+    c = capi.Context(0)                                   # a fresh context: the knob is read when a search is enqueued
+    try:
+        for max_d2 in (1e30, 30.0, 2.0):                  # (the group search is launched for thresholds >= 1)
+            cfg = capi.default_config()
+            cfg.nn_algorithm, cfg.max_distance_sq, cfg.rejection = 2, max_d2, 0
+            c.set_config(cfg)
+            c.set_target(tgt, zt, None)
+            c.set_source(qry, zq, None)
+            ref = orc.knn_brute(tgt, qry, max_d2)
+            for attempt in range(3):                      # from the second call on warm-started: the fast path defers, the groups form
+                idx, w = c.query_matches(np.eye(4, dtype=np.float32))
+                assert_matches_equal(idx, w, ref, f"{kind} n={n_tgt} max_d2={max_d2} group_min={group_min} attempt {attempt}")
+            for step in (([0.01, -0.02, 0.005], [0.3, -0.2, 0.4]), ([0.05, 0.03, -0.04], [1.0, 0.5, -0.8])):
+                moved = synth.make_pose(*step)
+                ref2 = orc.knn_brute(tgt, orc.transform_points(moved, qry), max_d2)
+                idx, w = c.query_matches(moved)
+                assert_matches_equal(idx, w, ref2, f"{kind} n={n_tgt} max_d2={max_d2} group_min={group_min} moved")
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("minimizer", [0, 1])
 def test_early_stop_criterion(ctx, bunny, minimizer):
     """with thresholds set, the loop ends (on the device, inside the replayed graph) after the first iteration whose
