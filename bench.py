@@ -83,18 +83,40 @@ def ncu_traffic(kernel_substr):
     return None
 
 
+def _load_pair_cache(cache):
+    """A cached pair, or None when the file is absent or unreadable (a run killed while writing it)."""
+    from icp_variants_b200 import synth
+    if not os.path.exists(cache):
+        return None
+    try:
+        z = np.load(cache)
+        return (synth.Cloud(z["sp"], z["sn"], z["sc"]), synth.Cloud(z["tp"], z["tn"], z["tc"]))
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def _save_pair_cache(cache, src, tgt):
+    """Written under a private name and renamed: other ranks read these files (pair_queue_44's dynamic deal)."""
+    tmp = f"{cache}.{os.getpid()}.tmp.npz"
+    try:
+        np.savez(tmp, sp=src.points, sn=src.normals, sc=src.colors, tp=tgt.points, tn=tgt.normals, tc=tgt.colors)
+        os.replace(tmp, cache)
+    except OSError:
+        try:
+            os.remove(tmp)
+        except OSError:
+            pass
+
+
 def make_pair(pair_index=0, n_sweeps=344, n_beams=1077):
     """Synthetic ETH-shaped pair; cached under /tmp because k=5 PCA normals of 370k points take seconds."""
     from icp_variants_b200 import synth
     cache = f"/tmp/icp_b200_pair_{n_sweeps}x{n_beams}_{pair_index}.npz"
-    if os.path.exists(cache):
-        z = np.load(cache)
-        return (synth.Cloud(z["sp"], z["sn"], z["sc"]), synth.Cloud(z["tp"], z["tn"], z["tc"]))
+    hit = _load_pair_cache(cache)
+    if hit is not None:
+        return hit
     src, tgt, _ = synth.eth_pair(seed=1234, n_sweeps=n_sweeps, n_beams=n_beams, pair_index=pair_index)
-    try:
-        np.savez(cache, sp=src.points, sn=src.normals, sc=src.colors, tp=tgt.points, tn=tgt.normals, tc=tgt.colors)
-    except OSError:
-        pass
+    _save_pair_cache(cache, src, tgt)
     return src, tgt
 
 
@@ -110,14 +132,11 @@ def device_normals_fn(ctx):
 def make_pair_device_normals(ctx, pair_index, n_sweeps, n_beams):
     from icp_variants_b200 import synth
     cache = f"/tmp/icp_b200_pairdn_{n_sweeps}x{n_beams}_{pair_index}.npz"
-    if os.path.exists(cache):
-        z = np.load(cache)
-        return (synth.Cloud(z["sp"], z["sn"], z["sc"]), synth.Cloud(z["tp"], z["tn"], z["tc"]))
+    hit = _load_pair_cache(cache)
+    if hit is not None:
+        return hit
     src, tgt, _ = synth.eth_pair(seed=1234, n_sweeps=n_sweeps, n_beams=n_beams, pair_index=pair_index, normals_fn=device_normals_fn(ctx))
-    try:
-        np.savez(cache, sp=src.points, sn=src.normals, sc=src.colors, tp=tgt.points, tn=tgt.normals, tc=tgt.colors)
-    except OSError:
-        pass
+    _save_pair_cache(cache, src, tgt)
     return src, tgt
 
 
