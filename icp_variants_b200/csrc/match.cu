@@ -22,6 +22,9 @@
 //                     Every query starts from an upper bound: the neighbour it had the last time it was matched
 //                     (the pose moves little between ICP iterations), else the distance threshold.
 //                     In the 6-D colour search every node also carries its colour range, added to the lower bounds.
+//   knn_group_kernel  between the two (3-D search, thresholds that admit far matches): one warp per 32 consecutive positions; runs of
+//                     deferred neighbours share ONE breadth-first descent, then every member is scanned against the few listed
+//                     leaves its own ball meets.  What it finishes the walk skips; what outgrows its stage it leaves to the walk.
 //   knn_brute_kernel  small targets: one warp per query over the whole target, warp-shuffle arg-min.
 //   projective_kernel one thread per query over its 25 x 25 pixel window, staged in shared memory per block
 //                     (32 x 8 pixel tiles of a full-frame source, else 256 Morton-consecutive points).
@@ -435,6 +438,15 @@ __device__ __forceinline__ float ord2f(unsigned int u) { return __uint_as_float(
 __device__ __forceinline__ float warp_min_f(float v) { return ord2f(__reduce_min_sync(0xFFFFFFFFu, f2ord(v))); }
 __device__ __forceinline__ float warp_max_f(float v) { return ord2f(__reduce_max_sync(0xFFFFFFFFu, f2ord(v))); }
 
+// Why no candidate is lost.  Let p be a target point that can change member m's answer: its D1 distance d(q_m, p) (fp32, rounded as
+// contract D1 says) is <= the member's bound bd_m, the distance of a real point.  (1) |q_m.x - p.x| <= sqrt(bd_m) up to D1's rounding,
+// which the factor 1.00001 on the radius covers (the fast path's "inside" test makes the same step), so p lies in the box of m's
+// ball [q_m - r_m, q_m + r_m] (bounds rounded outwards), hence in the union box [bl, bh]; every box of the hierarchy is the exact
+// min / max of its points, so each ancestor box of p meets [bl, bh] -- comparisons only, nothing rounds.  (2) The gap between an
+// ancestor box and the box [ql, qh] of the member points is, per axis, at most |q_m - p| on that axis, so its exact squared norm
+// is <= the exact squared distance <= bd_m (1 + 4 ulp) <= the largest bound; the fp32 evaluation below (any association, FMA or not)
+// is off by a few ulp, the margin 1.0001 by a thousand, and 1e-36 covers products that underflow.  Ties (equal distance, lower
+// index) satisfy d <= bd_m as well.  So every leaf holding such a point survives both tests at every level.
 struct GroupBounds { float blx, bly, blz, bhx, bhy, bhz, qlx, qly, qlz, qhx, qhy, qhz, dlim; };
 __device__ __forceinline__ bool group_keeps(const GroupBounds& g, const float4 lo, const float4 hi) {
     const bool meets = lo.x <= g.bhx && hi.x >= g.blx && lo.y <= g.bhy && hi.y >= g.bly && lo.z <= g.bhz && hi.z >= g.blz;
