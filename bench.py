@@ -296,7 +296,8 @@ def pair_queue_block(torch, dist, capi, ctx, stream, world, rank, dev, args):
     rank runs its queue through sequence.alignPairs (host arrays in, poses out, three contexts per GPU so that the upload and the
     loops of different pairs overlap).  No collective on the data path; time = CUDA events around the queue, max over ranks."""
     from icp_variants_b200 import parallel, sequence, synth
-    dynamic = world > 1 and not args.static_deal
+    # the ticket counter lives in the process group's store (same torch on every rank: the same answer everywhere)
+    dynamic = world > 1 and not args.static_deal and hasattr(dist.distributed_c10d, "_get_default_store")
     mine = parallel.shard_pairs(N_SEQUENCE_PAIRS, world, rank)
     t0 = time.perf_counter()
     pairs = {k: make_pair_device_normals(ctx, k, args.sweeps, args.beams) for k in mine}     # (also fills the /tmp cache)

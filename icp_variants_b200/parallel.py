@@ -33,7 +33,10 @@ class PairTickets:
     def __init__(self, n_pairs: int, key: str = "icp_pair_tickets", store=None):
         if store is None:
             import torch.distributed as dist
-            store = dist.distributed_c10d._get_default_store()
+            get = getattr(dist.distributed_c10d, "_get_default_store", None)
+            if get is None:
+                raise RuntimeError("PairTickets: this torch has no default-store accessor; pass store= (any c10d Store with add())")
+            store = get()
         self.n_pairs, self.key, self.store = int(n_pairs), str(key), store
         self.drawn: list[int] = []
 
